@@ -1,0 +1,233 @@
+"""Media probing for the B200 encode backend.
+
+Mirrors the reference's ``core/probe.py`` interface (``VideoInfo`` :9-24,
+``probe_media`` :47-116): same 14 fields, same HDR rule (>= 2 of 4 features,
+:76-82), same "never raises, falls back to 1080p30 SDR" convention (:114-116).
+
+The reference shells out to ``ffprobe``; this image has none, so three probers
+are chained: ffprobe (if on PATH) -> Y4M / raw sidecar header -> OpenCV
+container probe.  A ``<file>.json`` sidecar can carry colour tags for raw or
+OpenCV-decoded inputs.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import shutil
+import subprocess
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+logger = logging.getLogger(__name__)
+
+
+@dataclass
+class VideoInfo:
+    # field order and defaults follow reference core/probe.py:9-24
+    width: int
+    height: int
+    fps: float
+    color_primaries: str
+    color_transfer: str
+    color_space: str
+    pix_fmt: str
+    master_display: str
+    max_cll: str
+    audio_channels: int
+    hdr: bool = False
+    audio_language: Optional[str] = 'eng'
+    nb_frames: Optional[int] = None
+    duration: Optional[float] = None
+
+
+# reference core/probe.py:26-29
+HDR_PIXFMTS = frozenset({'yuv420p10le', 'p010le', 'yuv444p10le'})
+HDR_COLOR_SPACES = frozenset({'bt2020', 'bt2020-ncl', 'bt2020nc'})
+HDR_TRANSFERS = frozenset({'smpte2084', 'pq'})
+HDR_PRIMARIES = frozenset({'bt2020', 'bt2020-ncl'})
+
+_FALLBACK = dict(width=1920, height=1080, fps=30.0, color_primaries='bt709',
+                 color_transfer='bt709', color_space='bt709', pix_fmt='yuv420p',
+                 master_display='', max_cll='', audio_channels=2, hdr=False,
+                 audio_language='eng', nb_frames=None, duration=None)
+
+
+def parse_fps(rate_str: str) -> float:
+    """'num/den' -> float; anything malformed -> 30.0 (reference core/probe.py:31-38)."""
+    try:
+        if not rate_str or '/' not in rate_str:
+            return 30.0
+        num, den = (int(t) for t in rate_str.split('/'))
+        return num / den if den else 30.0
+    except Exception:
+        return 30.0
+
+
+def classify_hdr(color_primaries: str, color_transfer: str, color_space: str, pix_fmt: str) -> bool:
+    """HDR when at least two of the four features match (reference core/probe.py:76-82)."""
+    hits = ((color_primaries in HDR_PRIMARIES) + (color_transfer in HDR_TRANSFERS)
+            + (color_space in HDR_COLOR_SPACES) + (pix_fmt in HDR_PIXFMTS))
+    return hits >= 2
+
+
+def _first_tag(tags: dict, *names: str, default: str = '') -> str:
+    for n in names:
+        val = tags.get(n)
+        if val:
+            return val
+    return default
+
+
+def info_from_ffprobe_json(doc: dict) -> VideoInfo:
+    """Interpret an ``ffprobe -show_streams -show_format`` document exactly as the
+    reference does (core/probe.py:53-111)."""
+    streams = doc.get('streams', [])
+    v = next((s for s in streams if s.get('codec_type') == 'video'), None)
+    if not v:
+        raise ValueError('no video stream')
+    width = int(v.get('width') or 1920)
+    height = int(v.get('height') or 1080)
+    rate = v.get('avg_frame_rate') or v.get('r_frame_rate') or '30/1'
+    if rate.strip() == '0/0' or not rate.strip():
+        fps = 30.0
+    else:
+        try:
+            num, den = (int(t) for t in rate.split('/'))
+            fps = num / den if den else 30.0
+        except Exception:
+            fps = 30.0
+    fmt = doc.get('format', {})
+    tags = fmt.get('tags', {}) or {}
+
+    def colour(key: str) -> str:
+        return (v.get(key) or tags.get(key.upper()) or tags.get(key) or 'bt709').lower()
+
+    prim, trc, spc = colour('color_primaries'), colour('color_transfer'), colour('color_space')
+    pix_fmt = (v.get('pix_fmt') or '').lower()
+    hdr = classify_hdr(prim, trc, spc, pix_fmt)
+    master_display = _first_tag(tags, 'master-display', 'MASTER_DISPLAY', 'master_display', 'mastering_display')
+    max_cll = _first_tag(tags, 'max-cll', 'MAX_CLL', 'max_cll')
+
+    a = next((s for s in streams if s.get('codec_type') == 'audio'), None)
+    if a:
+        atags = a.get('tags', {}) or {}
+        lang = atags.get('language') or atags.get('LANGUAGE') or 'eng'
+        channels = int(a.get('channels', a.get('CHANNELS', 2)))
+    else:
+        lang, channels = None, 0
+
+    try:
+        nb_frames = int(v.get('nb_frames')) if v.get('nb_frames') else None
+    except Exception:
+        nb_frames = None
+    try:
+        duration = float(fmt.get('duration')) if fmt.get('duration') else None
+    except Exception:
+        duration = None
+    return VideoInfo(width, height, fps, prim, trc, spc, pix_fmt, master_display, max_cll,
+                     channels, hdr, lang, nb_frames, duration)
+
+
+# ---------------------------------------------------------------- ffprobe-less probers
+
+_Y4M_CSP = {'420': 'yuv420p', '420jpeg': 'yuv420p', '420mpeg2': 'yuv420p', '420paldv': 'yuv420p',
+            '420p10': 'yuv420p10le', '444': 'yuv444p', '444p10': 'yuv444p10le', '422': 'yuv422p'}
+
+
+def _probe_y4m(path: Path) -> dict:
+    with open(path, 'rb') as fh:
+        head = fh.readline(512)
+    if not head.startswith(b'YUV4MPEG2'):
+        raise ValueError('not y4m')
+    out = {'pix_fmt': 'yuv420p'}
+    for tok in head.decode('ascii', 'replace').split()[1:]:
+        k, val = tok[0], tok[1:]
+        if k == 'W':
+            out['width'] = int(val)
+        elif k == 'H':
+            out['height'] = int(val)
+        elif k == 'F':
+            n, d = val.split(':')
+            out['fps'] = int(n) / int(d) if int(d) else 30.0
+        elif k == 'C':
+            out['pix_fmt'] = _Y4M_CSP.get(val, 'yuv420p')
+    out['header_len'] = len(head)
+    bps = 2 if '10' in out['pix_fmt'] else 1
+    w, h = out['width'], out['height']
+    if out['pix_fmt'].startswith('yuv444'):
+        fsz = w * h * 3 * bps
+    elif out['pix_fmt'].startswith('yuv422'):
+        fsz = w * h * 2 * bps
+    else:
+        fsz = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)) * bps
+    out['frame_bytes'] = fsz
+    out['nb_frames'] = (path.stat().st_size - len(head)) // (fsz + 6)  # 'FRAME\n' per frame
+    return out
+
+
+def _probe_cv2(path: Path) -> dict:
+    import cv2  # deferred: optional dependency
+    cap = cv2.VideoCapture(str(path))
+    try:
+        if not cap.isOpened():
+            raise ValueError('cv2 cannot open')
+        out = {'width': int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), 'height': int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)),
+               'fps': float(cap.get(cv2.CAP_PROP_FPS)) or 30.0, 'nb_frames': int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) or None,
+               'pix_fmt': 'yuv420p'}
+        if out['width'] <= 0 or out['height'] <= 0:
+            raise ValueError('cv2 reports no video')
+        return out
+    finally:
+        cap.release()
+
+
+def _sidecar(path: Path) -> dict:
+    side = path.with_suffix(path.suffix + '.json')
+    if side.exists():
+        try:
+            return json.loads(side.read_text())
+        except Exception:
+            logger.debug('bad sidecar %s', side, exc_info=True)
+    return {}
+
+
+def _probe_without_ffprobe(path: Path) -> VideoInfo:
+    side = _sidecar(path)
+    try:
+        base = _probe_y4m(path)
+    except Exception:
+        if path.suffix.lower() in ('.yuv', '.raw', '.p010') and side:
+            base = {}
+        else:
+            base = _probe_cv2(path)
+    base.update({k: v for k, v in side.items() if v is not None})
+    prim = str(base.get('color_primaries', 'bt709')).lower()
+    trc = str(base.get('color_transfer', 'bt709')).lower()
+    spc = str(base.get('color_space', 'bt709')).lower()
+    pix = str(base.get('pix_fmt', 'yuv420p')).lower()
+    fps = float(base.get('fps', 30.0))
+    nb = base.get('nb_frames')
+    dur = base.get('duration')
+    if dur is None and nb and fps:
+        dur = nb / fps
+    achan = int(base.get('audio_channels', 0))
+    return VideoInfo(int(base['width']), int(base['height']), fps, prim, trc, spc, pix,
+                     str(base.get('master_display', '')), str(base.get('max_cll', '')), achan,
+                     classify_hdr(prim, trc, spc, pix), base.get('audio_language', 'eng' if achan else None),
+                     int(nb) if nb else None, float(dur) if dur else None)
+
+
+def probe_media(file_path: Path) -> VideoInfo:
+    """Same contract as reference core/probe.py:47: returns a VideoInfo, never raises."""
+    file_path = Path(file_path)
+    try:
+        if shutil.which('ffprobe'):
+            res = subprocess.run(['ffprobe', '-v', 'quiet', '-print_format', 'json', '-show_streams',
+                                  '-show_format', str(file_path)],
+                                 capture_output=True, text=True, check=True, encoding='utf-8')
+            return info_from_ffprobe_json(json.loads(res.stdout))
+        return _probe_without_ffprobe(file_path)
+    except Exception as exc:
+        logger.error('probe failed: %s, %s', file_path.name, exc)
+        return VideoInfo(**_FALLBACK)
