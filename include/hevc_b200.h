@@ -1,0 +1,113 @@
+/* hevc_b200 -- C ABI of the B200-native HEVC encode backend.
+ *
+ * This is the drop-in boundary for the encode step of the reference pipeline.  The reference has no FFI:
+ * its "operator API" to the codec is the ffmpeg argv built at core/transcoder.py:452-495 and executed at
+ * core/transcoder.py:497-535 (run_ffmpeg -> subprocess.Popen).  Each entry point below cites the part of
+ * that child process it replaces.  Plain C types only; device pointers are CUDA device addresses of the
+ * calling process (any allocator: cudaMalloc, torch, ...).  Every function returns 0 on success and a
+ * negative hb_status on failure; hb_last_error() gives the text.  One hb_ctx owns one device + one
+ * CUDA stream; use one per worker thread (reference threading model: gui/mainwindow.py:289-301).
+ */
+#ifndef HEVC_B200_H
+#define HEVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+typedef enum hb_status {
+    HB_OK = 0,
+    HB_ERR_ARG = -1,       /* bad argument */
+    HB_ERR_CUDA = -2,      /* CUDA runtime / driver failure */
+    HB_ERR_NOMEM = -3,
+    HB_ERR_SPACE = -4,     /* caller buffer too small */
+    HB_ERR_STOPPED = -5,   /* hb_enc_request_stop() was honoured */
+    HB_ERR_STATE = -6
+} hb_status;
+
+typedef struct hb_ctx hb_ctx;
+typedef uint64_t hb_devptr;
+
+int hb_abi_version(void);
+int hb_device_count(void);
+/* create a context on `device` with its own non-blocking stream */
+int hb_create(int device, hb_ctx **out);
+void hb_destroy(hb_ctx *ctx);
+const char *hb_last_error(const hb_ctx *ctx);
+int hb_sync(hb_ctx *ctx);
+/* the context's cudaStream_t, for callers that record their own CUDA events around launches */
+uint64_t hb_stream(const hb_ctx *ctx);
+/* number of kernels this context has launched since creation */
+uint64_t hb_launch_count(const hb_ctx *ctx);
+/* device scratch allocation owned by the context (freed by hb_free or hb_destroy) */
+int hb_alloc(hb_ctx *ctx, size_t bytes, hb_devptr *out);
+int hb_free(hb_ctx *ctx, hb_devptr p);
+int hb_upload(hb_ctx *ctx, hb_devptr dst, const void *src, size_t bytes);     /* async on the ctx stream */
+int hb_download(hb_ctx *ctx, void *dst, hb_devptr src, size_t bytes);         /* async on the ctx stream */
+/* event timing on the context's stream: start/stop bracket launches, elapsed is in milliseconds */
+int hb_timer_start(hb_ctx *ctx);
+int hb_timer_stop(hb_ctx *ctx, float *ms);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Pre-encode pixel pipeline.  Replaces the libswscale stage ffmpeg auto-inserts for `-pix_fmt`
+ * (reference core/transcoder.py:464; p010le requested at :364) and the geometry of the upscale path
+ * (upscale_gui_final.py:81-87).  Strides are in BYTES.  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* 8-bit planar 4:2:0 -> P010 (16-bit containers, value << 8, UV interleaved).  4.5 bytes / pixel. */
+int hb_pack_p010(hb_ctx *ctx, hb_devptr y, int y_stride, hb_devptr u, int u_stride, hb_devptr v, int v_stride,
+                 int width, int height, hb_devptr dst_y, int dst_y_stride, hb_devptr dst_uv, int dst_uv_stride);
+
+typedef enum hb_matrix { HB_MATRIX_BT709 = 1, HB_MATRIX_BT601 = 6, HB_MATRIX_BT2020 = 9 } hb_matrix;
+typedef enum hb_rgb_order { HB_RGB = 0, HB_BGR = 1 } hb_rgb_order;
+
+/* packed 8-bit full-range RGB/BGR -> limited-range 4:2:0, Q14 matrix, 2x2 box chroma.
+ * depth 8: dst_y/dst_u/dst_v are 8-bit planes.  depth 10: dst_y is a P010 luma plane, dst_u a P010
+ * interleaved UV plane (dst_v ignored).  6 bytes / pixel at depth 10. */
+int hb_rgb_to_yuv420(hb_ctx *ctx, hb_devptr rgb, int rgb_stride, int order, int matrix, int depth, int width, int height,
+                     hb_devptr dst_y, int dst_y_stride, hb_devptr dst_u, int dst_u_stride, hb_devptr dst_v, int dst_v_stride);
+
+/* 4-tap Catmull-Rom polyphase scaler (64 phases, Q14 taps, Q6 int16 intermediate) of one 8-bit plane.
+ * out_depth 8 -> 8-bit plane; out_depth 10 -> 16-bit samples, shifted left by `out_shift` (6 = P010).
+ * dst_pixel_step = distance between successive output samples in SAMPLES (2 to write one half of an
+ * interleaved UV plane). */
+int hb_scale_plane(hb_ctx *ctx, hb_devptr src, int src_stride, int src_w, int src_h,
+                   hb_devptr dst, int dst_stride, int dst_w, int dst_h, int out_depth, int out_shift, int dst_pixel_step);
+
+/* fused upscale path: 8-bit planar 4:2:0 (src_w x src_h) -> P010 (dst_w x dst_h), three hb_scale_plane passes */
+int hb_scale_yuv420_to_p010(hb_ctx *ctx, hb_devptr y, int y_stride, hb_devptr u, int u_stride, hb_devptr v, int v_stride,
+                            int src_w, int src_h, hb_devptr dst_y, int dst_y_stride, hb_devptr dst_uv, int dst_uv_stride,
+                            int dst_w, int dst_h);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Encoder primitives, batched over blocks (BASELINE config 5).  These are the functions libx265 spends
+ * its time in behind `-c:v libx265` (reference core/transcoder.py:398-412): x265 primitives sad / satd /
+ * sa8d / dct / idct / dst / nquant / dequant_normal / intra_pred.  Samples are uint16_t for every bit
+ * depth, coefficients int16_t.  Blocks are dense: block i of a WxH batch starts at i*W*H samples.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* out[i] = SAD / SATD of block i of `a` against block i of `b`; out is int32[n] */
+int hb_sad(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int w, int h, hb_devptr out);
+int hb_satd(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int w, int h, hb_devptr out);
+/* square blocks, size 4 (== satd 4x4), 8, 16, 32, 64 */
+int hb_sa8d(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int size, hb_devptr out);
+/* forward / inverse core transform, size 4/8/16/32; is_dst selects DST-VII (size 4 only) */
+int hb_fwd_transform(hb_ctx *ctx, hb_devptr residual, int n, int size, int bit_depth, int is_dst, hb_devptr coef);
+int hb_inv_transform(hb_ctx *ctx, hb_devptr coef, int n, int size, int bit_depth, int is_dst, hb_devptr residual);
+/* flat-matrix quantisation without RDOQ (x265 nquant): qp already includes QpBdOffset; numsig int32[n] */
+int hb_quant(hb_ctx *ctx, hb_devptr coef, int n, int size, int qp, int bit_depth, int is_intra, hb_devptr level, hb_devptr numsig);
+int hb_dequant(hb_ctx *ctx, hb_devptr level, int n, int size, int qp, int bit_depth, hb_devptr coef);
+/* all 35 intra predictions per block.  neighbours: uint16[n][4*size+1] = {top-left, top[2N], left[2N]};
+ * pred: uint16[n][35][size*size].  is_luma enables reference smoothing + DC/H/V edge filters. */
+int hb_intra_pred_all(hb_ctx *ctx, hb_devptr neighbours, int n, int size, int is_luma, int strong_smoothing,
+                      int bit_depth, hb_devptr pred);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEVC_B200_H */
