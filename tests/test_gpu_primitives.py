@@ -136,6 +136,7 @@ def test_large_batch_checksum(env):
     g = torch.Generator(device='cuda').manual_seed(1)
     a = torch.randint(0, 1024, (n, 8, 8), device='cuda', generator=g, dtype=torch.int16)
     b = torch.randint(0, 1024, (n, 8, 8), device='cuda', generator=g, dtype=torch.int16)
+    torch.cuda.synchronize()          # inputs were produced on torch's stream; the context has its own
     satd = ops.satd(ctx, a, b)
     sad = ops.sad(ctx, a, b)
     ctx.sync()
