@@ -168,31 +168,49 @@ class HevcDecoder:
             yield tuple(planes)
 
     def decode(self, stream: bytes) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
-        """Decode a whole elementary stream; returns frames in output (display) order."""
+        """Decode a whole Annex-B elementary stream; returns frames in output (display) order.
+        Access units are split here (one packet per AU) rather than through the libavcodec parser."""
         out: List[Tuple[np.ndarray, np.ndarray, np.ndarray]] = []
-        buf = C.create_string_buffer(bytes(stream) + b'\0' * _PAD, len(stream) + _PAD)
-        base = C.addressof(buf)
-        pos, size = 0, len(stream)
-        optr, osz = C.c_void_p(), C.c_int()
-        nopts = -0x8000000000000000
-        while True:
-            n = self.avc.av_parser_parse2(self.parser, self.ctx, C.byref(optr), C.byref(osz),
-                                          C.c_void_p(base + pos) if pos < size else None, size - pos, nopts, nopts, 0)
-            if n < 0:
-                raise DecodeError('parser error')
-            pos += n
-            if osz.value:
-                pk = _AVPacketHead.from_address(self.pkt)
-                pk.data, pk.size = optr.value, osz.value
-                rc = self.avc.avcodec_send_packet(self.ctx, self.pkt)
-                if rc < 0:
-                    raise DecodeError(f'avcodec_send_packet -> {rc} (bitstream rejected or picture-hash mismatch)')
-                out.extend(self._drain())
-            elif pos >= size:
-                break
+        for au in split_access_units(stream):
+            buf = C.create_string_buffer(au + b'\0' * _PAD, len(au) + _PAD)
+            pk = _AVPacketHead.from_address(self.pkt)
+            pk.data, pk.size = C.addressof(buf), len(au)
+            rc = self.avc.avcodec_send_packet(self.ctx, self.pkt)
+            pk.data, pk.size = None, 0
+            if rc < 0:
+                raise DecodeError(f'avcodec_send_packet -> {rc} (bitstream rejected or picture-hash mismatch)')
+            out.extend(self._drain())
         self.avc.avcodec_send_packet(self.ctx, None)
         out.extend(self._drain())
         return out
+
+
+def iter_nals(stream: bytes):
+    """Yield (offset_of_start_code, nal_type, payload_offset) for every NAL unit of an Annex-B stream."""
+    i, n = 0, len(stream)
+    while True:
+        j = stream.find(b'\x00\x00\x01', i)
+        if j < 0 or j + 5 > n:
+            return
+        sc = j - 1 if j > 0 and stream[j - 1] == 0 else j
+        yield sc, (stream[j + 3] >> 1) & 0x3f, j + 3
+        i = j + 3
+
+
+def split_access_units(stream: bytes) -> List[bytes]:
+    """Cut an Annex-B stream into access units (H.265 7.4.2.4.4, restricted to the NAL types used here)."""
+    cuts, seen_vcl = [], False
+    for sc, typ, pay in iter_nals(stream):
+        is_vcl = typ < 32
+        first_slice = is_vcl and pay + 2 < len(stream) and (stream[pay + 2] & 0x80) != 0
+        starts = typ in (32, 33, 34, 35, 39) or first_slice
+        if not cuts or (seen_vcl and starts):
+            cuts.append(sc)
+            seen_vcl = False
+        if is_vcl:
+            seen_vcl = True
+    cuts.append(len(stream))
+    return [bytes(stream[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
 
 
 def decode_hevc(stream: bytes, verify_hash: bool = True):

@@ -1,0 +1,492 @@
+/* TEST INFRASTRUCTURE -- CPU oracle: frame-level encoder model (decisions, reconstruction, access units).
+ *
+ * This is the executable specification of the B200 encoder (DESIGN.md "encoder specification"); the CUDA
+ * path must produce byte-identical access units.  It replaces what the reference gets from
+ * `ffmpeg -c:v libx265` (core/transcoder.py:398-412,506) for the tool subset described there:
+ *   IDR + P frames (one reference, closed GOP), CTU 32, CU 16x16, 35-mode intra search by SATD,
+ *   hierarchical motion search (quarter-resolution full search, integer refinement by SAD, half- and
+ *   quarter-sample refinement by SATD), 16x16/8x8 DCT with flat dead-zone quantisation, WPP CABAC.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hevc_model.h"
+
+int orc_intra_mpm(const orc_frame_syntax *f, int cx, int cy, int mpm[3]);
+
+/* round(256 * sqrt(0.57 * 2^((qp - 12) / 3))) */
+static const uint16_t k_lambda_q8[52] = {48, 54, 61, 68, 77, 86, 97, 108, 122, 137, 153, 172, 193, 217, 244, 273, 307, 344, 387, 434, 487, 547, 614,
+                                         689, 773, 868, 974, 1093, 1227, 1378, 1546, 1736, 1948, 2187, 2454, 2755, 3092, 3471, 3896, 4373, 4909, 5510,
+                                         6185, 6942, 7792, 8747, 9818, 11020, 12370, 13884, 15585, 17493};
+static const uint8_t k_chroma_qp[14] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37};   /* qPi 30..43 */
+
+#define CME_RANGE 12      /* quarter-resolution search range (+-48 luma samples) */
+#define MV_OVERHANG 64    /* a predicted block may leave the picture by this many luma samples */
+
+typedef struct plane {
+    pixel *base, *p;      /* p points at sample (0,0) inside the padded allocation */
+    int stride, w, h, pad;
+} plane;
+
+struct orc_encoder {
+    orc_enc_params prm;
+    int wc, hc, cuw, cuh, ctuw, ctuh;
+    plane src[3], rec[2][3];
+    int cur;                         /* index of the reconstruction being written */
+    plane ds[2];                     /* quarter-resolution source: [cur_ds], [1 - cur_ds] = previous frame */
+    int cur_ds;
+    orc_cu *cus;
+    int16_t *coefs;
+    int16_t *cmv;                    /* [ctuh][ctuw][2] coarse vectors, quarter-resolution samples */
+    int frame_no, poc, since_bp;
+    uint8_t *payload;                /* CABAC sub-streams */
+    size_t payload_cap;
+    uint32_t *row_off, *row_len;
+};
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+static void plane_alloc(plane *pl, int w, int h, int pad)
+{
+    pl->w = w; pl->h = h; pl->pad = pad;
+    pl->stride = w + 2 * pad;
+    pl->base = (pixel *)calloc((size_t)pl->stride * (h + 2 * pad), sizeof(pixel));
+    pl->p = pl->base + (size_t)pad * pl->stride + pad;
+}
+
+static void plane_extend(plane *pl)
+{
+    for (int y = 0; y < pl->h; y++) {
+        pixel *row = pl->p + (size_t)y * pl->stride;
+        for (int x = 1; x <= pl->pad; x++) { row[-x] = row[0]; row[pl->w - 1 + x] = row[pl->w - 1]; }
+    }
+    for (int y = 1; y <= pl->pad; y++) {
+        memcpy(pl->p + (size_t)(-y) * pl->stride - pl->pad, pl->p - pl->pad, sizeof(pixel) * pl->stride);
+        memcpy(pl->p + (size_t)(pl->h - 1 + y) * pl->stride - pl->pad, pl->p + (size_t)(pl->h - 1) * pl->stride - pl->pad,
+               sizeof(pixel) * pl->stride);
+    }
+}
+
+orc_encoder *orc_enc_create(const orc_enc_params *p)
+{
+    orc_encoder *e = (orc_encoder *)calloc(1, sizeof *e);
+    e->prm = *p;
+    e->wc = (p->width + 15) & ~15; e->hc = (p->height + 15) & ~15;
+    e->cuw = e->wc / 16; e->cuh = e->hc / 16;
+    e->ctuw = (e->wc + 31) / 32; e->ctuh = (e->hc + 31) / 32;
+    for (int c = 0; c < 3; c++) {
+        const int sh = c ? 1 : 0;
+        plane_alloc(&e->src[c], e->wc >> sh, e->hc >> sh, 0);
+        plane_alloc(&e->rec[0][c], e->wc >> sh, e->hc >> sh, ORC_PAD >> sh);
+        plane_alloc(&e->rec[1][c], e->wc >> sh, e->hc >> sh, ORC_PAD >> sh);
+    }
+    plane_alloc(&e->ds[0], e->wc / 4, e->hc / 4, 0);
+    plane_alloc(&e->ds[1], e->wc / 4, e->hc / 4, 0);
+    e->cus = (orc_cu *)calloc((size_t)e->cuw * e->cuh, sizeof(orc_cu));
+    e->coefs = (int16_t *)calloc((size_t)e->cuw * e->cuh * ORC_CU_COEFS, sizeof(int16_t));
+    e->cmv = (int16_t *)calloc((size_t)e->ctuw * e->ctuh * 2, sizeof(int16_t));
+    e->payload_cap = (size_t)e->wc * e->hc * 3 + 65536;
+    e->payload = (uint8_t *)malloc(e->payload_cap);
+    e->row_off = (uint32_t *)calloc(e->ctuh, sizeof(uint32_t));
+    e->row_len = (uint32_t *)calloc(e->ctuh, sizeof(uint32_t));
+    return e;
+}
+
+void orc_enc_destroy(orc_encoder *e)
+{
+    if (!e) return;
+    for (int c = 0; c < 3; c++) { free(e->src[c].base); free(e->rec[0][c].base); free(e->rec[1][c].base); }
+    free(e->ds[0].base); free(e->ds[1].base);
+    free(e->cus); free(e->coefs); free(e->cmv); free(e->payload); free(e->row_off); free(e->row_len);
+    free(e);
+}
+
+void orc_enc_coded_size(const orc_encoder *e, int *wc, int *hc) { *wc = e->wc; *hc = e->hc; }
+const orc_cu *orc_enc_last_cus(const orc_encoder *e) { return e->cus; }
+const int16_t *orc_enc_last_coefs(const orc_encoder *e) { return e->coefs; }
+const int16_t *orc_enc_last_coarse_mv(const orc_encoder *e) { return e->cmv; }
+
+void orc_enc_get_recon(const orc_encoder *e, pixel *y, pixel *u, pixel *v)
+{
+    pixel *dst[3] = {y, u, v};
+    const plane *r = e->rec[1 - e->cur];      /* cur was flipped after the frame was finished */
+    for (int c = 0; c < 3; c++)
+        for (int row = 0; row < r[c].h; row++)
+            memcpy(dst[c] + (size_t)row * r[c].w, r[c].p + (size_t)row * r[c].stride, sizeof(pixel) * r[c].w);
+}
+
+size_t orc_enc_headers(orc_encoder *e, uint8_t *out, size_t cap)
+{
+    size_t o = 0;
+    o += orc_write_vps(&e->prm, out + o, cap - o);
+    o += orc_write_sps(&e->prm, out + o, cap - o);
+    o += orc_write_pps(&e->prm, out + o, cap - o);
+    return o;
+}
+
+/* ------------------------------------------------------------------ ingest */
+
+static void load_source(orc_encoder *e, const pixel *y, int ys, const pixel *u, const pixel *v, int cs)
+{
+    const pixel *in[3] = {y, u, v};
+    for (int c = 0; c < 3; c++) {
+        const int sh = c ? 1 : 0, w = e->prm.width >> sh, h = e->prm.height >> sh, st = c ? cs : ys;
+        plane *d = &e->src[c];
+        for (int row = 0; row < d->h; row++) {
+            const pixel *s = in[c] + (size_t)(row < h ? row : h - 1) * st;
+            pixel *o = d->p + (size_t)row * d->stride;
+            memcpy(o, s, sizeof(pixel) * w);
+            for (int x = w; x < d->w; x++) o[x] = s[w - 1];      /* replicate into the coded-size padding */
+        }
+    }
+    plane *ds = &e->ds[e->cur_ds];
+    const plane *s = &e->src[0];
+    for (int yy = 0; yy < ds->h; yy++)
+        for (int xx = 0; xx < ds->w; xx++) {
+            int acc = 8;
+            for (int j = 0; j < 4; j++)
+                for (int i = 0; i < 4; i++)
+                    acc += s->p[(size_t)(4 * yy + j) * s->stride + 4 * xx + i];
+            ds->p[(size_t)yy * ds->stride + xx] = (pixel)(acc >> 4);
+        }
+}
+
+/* ------------------------------------------------------------------ shared residual path */
+
+static int chroma_qp(int qp_y)
+{
+    const int qpi = clampi(qp_y, 0, 57);
+    return qpi < 30 ? qpi : qpi >= 44 ? qpi - 6 : k_chroma_qp[qpi - 30];
+}
+
+/* transform + quantise + reconstruct one NxN block; returns cbf */
+static int code_block(const orc_encoder *e, const pixel *src, int ss, const pixel *pred, int ps, pixel *rec, int rs, int N, int qp,
+                      int intra, int16_t *level)
+{
+    int16_t res[32 * 32], coef[32 * 32], deq[32 * 32];
+    const int bd = e->prm.bit_depth, maxv = (1 << bd) - 1;
+    for (int y = 0; y < N; y++)
+        for (int x = 0; x < N; x++)
+            res[y * N + x] = (int16_t)((int)src[y * ss + x] - (int)pred[y * ps + x]);
+    orc_fwd_transform(res, N, coef, N, bd, 0);
+    const int nsig = orc_quant(coef, level, N, qp + 6 * (bd - 8), bd, intra);
+    if (nsig) {
+        orc_dequant(level, deq, N, qp + 6 * (bd - 8), bd);
+        orc_inv_transform(deq, res, N, N, bd, 0);
+    }
+    for (int y = 0; y < N; y++)
+        for (int x = 0; x < N; x++)
+            rec[y * rs + x] = (pixel)(nsig ? clampi(pred[y * ps + x] + res[y * N + x], 0, maxv) : pred[y * ps + x]);
+    return nsig != 0;
+}
+
+/* ------------------------------------------------------------------ intra frame */
+
+static int cu_order(const orc_encoder *e, int cx, int cy) { return ((cy >> 1) * e->ctuw + (cx >> 1)) * 4 + ((cy & 1) << 1) + (cx & 1); }
+static int cu_avail(const orc_encoder *e, int cx, int cy, int nx, int ny)
+{
+    if (nx < 0 || ny < 0 || nx >= e->cuw || ny >= e->cuh) return 0;
+    return cu_order(e, nx, ny) < cu_order(e, cx, cy);
+}
+
+/* 8.4.4.2.2 reference sample gathering + substitution for the NxN block of CU (cx, cy) in plane `r` */
+static void gather_neighbours(const orc_encoder *e, const plane *r, int cx, int cy, int N, pixel *nb)
+{
+    const int x0 = cx * N, y0 = cy * N, n2 = 2 * N, bd = e->prm.bit_depth;
+    /* availability per N-sample segment: [bottom-left, left, corner, top, top-right] */
+    const int a_bl = cu_avail(e, cx, cy, cx - 1, cy + 1), a_l = cu_avail(e, cx, cy, cx - 1, cy), a_c = cu_avail(e, cx, cy, cx - 1, cy - 1);
+    const int a_t = cu_avail(e, cx, cy, cx, cy - 1), a_tr = cu_avail(e, cx, cy, cx + 1, cy - 1);
+    pixel *top = nb + 1, *left = nb + 1 + n2;
+    if (!(a_bl | a_l | a_c | a_t | a_tr)) {
+        for (int i = 0; i < 4 * N + 1; i++) nb[i] = (pixel)(1 << (bd - 1));
+        return;
+    }
+    /* walk from the bottom-most left sample up to the corner, then along the top to the right */
+    int have = 0;
+    pixel last = 0;
+    /* first available sample in walk order */
+    if (a_bl) last = r->p[(size_t)(y0 + n2 - 1) * r->stride + x0 - 1];
+    else if (a_l) last = r->p[(size_t)(y0 + N - 1) * r->stride + x0 - 1];
+    else if (a_c) last = r->p[(size_t)(y0 - 1) * r->stride + x0 - 1];
+    else if (a_t) last = r->p[(size_t)(y0 - 1) * r->stride + x0];
+    else last = r->p[(size_t)(y0 - 1) * r->stride + x0 + N];
+    (void)have;
+    for (int i = n2 - 1; i >= 0; i--) {
+        const int av = i >= N ? a_bl : a_l;
+        if (av) last = r->p[(size_t)(y0 + i) * r->stride + x0 - 1];
+        left[i] = last;
+    }
+    if (a_c) last = r->p[(size_t)(y0 - 1) * r->stride + x0 - 1];
+    nb[0] = last;
+    for (int i = 0; i < n2; i++) {
+        const int av = i >= N ? a_tr : a_t;
+        if (av) last = r->p[(size_t)(y0 - 1) * r->stride + x0 + i];
+        top[i] = last;
+    }
+}
+
+static void encode_intra_frame(orc_encoder *e, int qp)
+{
+    const int bd = e->prm.bit_depth;
+    const int lambda = k_lambda_q8[qp] << (bd - 8);
+    plane *rec = e->rec[e->cur];
+    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, 1, qp, e->cus, e->coefs};
+    for (int ctu = 0; ctu < e->ctuw * e->ctuh; ctu++)
+        for (int k = 0; k < 4; k++) {
+            const int cx = (ctu % e->ctuw) * 2 + (k & 1), cy = (ctu / e->ctuw) * 2 + (k >> 1);
+            if (cx >= e->cuw || cy >= e->cuh) continue;
+            orc_cu *cu = &e->cus[cy * e->cuw + cx];
+            int16_t *coef = e->coefs + (size_t)(cy * e->cuw + cx) * ORC_CU_COEFS;
+            pixel nb[65], flt[65], pred[256];
+            int mpm[3];
+            const pixel *src = e->src[0].p + (size_t)cy * 16 * e->src[0].stride + cx * 16;
+            gather_neighbours(e, &rec[0], cx, cy, 16, nb);
+            orc_intra_filter(nb, flt, 16, 0, bd);
+            cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->skip = 0;
+            orc_intra_mpm(&fs, cx, cy, mpm);
+            long best = -1;
+            int best_mode = 0;
+            for (int mode = 0; mode < 35; mode++) {
+                orc_intra_pred(orc_intra_use_filter(16, mode) ? flt : nb, pred, 16, 16, mode, 1, bd);
+                const int bits = mode == mpm[0] ? 2 : (mode == mpm[1] || mode == mpm[2]) ? 3 : 6;
+                const long cost = orc_satd(src, e->src[0].stride, pred, 16, 16, 16) + ((lambda * bits) >> 8);
+                if (best < 0 || cost < best) { best = cost; best_mode = mode; }
+            }
+            cu->intra_mode = (uint8_t)best_mode;
+            orc_intra_pred(orc_intra_use_filter(16, best_mode) ? flt : nb, pred, 16, 16, best_mode, 1, bd);
+            pixel *ry = rec[0].p + (size_t)cy * 16 * rec[0].stride + cx * 16;
+            int cbf = code_block(e, src, e->src[0].stride, pred, 16, ry, rec[0].stride, 16, qp, 1, coef);
+            for (int c = 1; c < 3; c++) {
+                pixel cnb[33], cpred[64];
+                const pixel *cs = e->src[c].p + (size_t)cy * 8 * e->src[c].stride + cx * 8;
+                pixel *rc = rec[c].p + (size_t)cy * 8 * rec[c].stride + cx * 8;
+                gather_neighbours(e, &rec[c], cx, cy, 8, cnb);
+                orc_intra_pred(cnb, cpred, 8, 8, best_mode, 0, bd);
+                cbf |= code_block(e, cs, e->src[c].stride, cpred, 8, rc, rec[c].stride, 8, chroma_qp(qp), 1, coef + (c == 1 ? 256 : 320)) << c;
+            }
+            cu->cbf = (uint8_t)cbf;
+        }
+}
+
+/* ------------------------------------------------------------------ inter frame */
+
+static int mv_bits1(int v)
+{
+    int a = abs(v), n = 0;
+    while ((a + 1) >> (n + 1)) n++;
+    return 2 * n + 1;
+}
+static int mv_cost(int lambda, int mvx, int mvy, int px, int py) { return (lambda * (mv_bits1(mvx - px) + mv_bits1(mvy - py))) >> 8; }
+
+static pixel ds_at(const plane *d, int x, int y) { return d->p[(size_t)clampi(y, 0, d->h - 1) * d->stride + clampi(x, 0, d->w - 1)]; }
+
+static void coarse_search(orc_encoder *e)
+{
+    const plane *cur = &e->ds[e->cur_ds], *prev = &e->ds[1 - e->cur_ds];
+    const int bias = 1 << (e->prm.bit_depth - 8);
+    for (int ty = 0; ty < e->ctuh; ty++)
+        for (int tx = 0; tx < e->ctuw; tx++) {
+            long best = -1;
+            int bdx = 0, bdy = 0;
+            for (int dy = -CME_RANGE; dy <= CME_RANGE; dy++)
+                for (int dx = -CME_RANGE; dx <= CME_RANGE; dx++) {
+                    long sad = 0;
+                    for (int j = 0; j < 8; j++)
+                        for (int i = 0; i < 8; i++)
+                            sad += abs((int)ds_at(cur, tx * 8 + i, ty * 8 + j) - (int)ds_at(prev, tx * 8 + i + dx, ty * 8 + j + dy));
+                    const long cost = sad + bias * (abs(dx) + abs(dy));
+                    if (best < 0 || cost < best) { best = cost; bdx = dx; bdy = dy; }
+                }
+            e->cmv[(ty * e->ctuw + tx) * 2] = (int16_t)bdx;
+            e->cmv[(ty * e->ctuw + tx) * 2 + 1] = (int16_t)bdy;
+        }
+}
+
+typedef struct { int x, y; } mv_t;
+
+static mv_t clamp_mv(const orc_encoder *e, int x0, int y0, mv_t m)
+{
+    m.x = clampi(m.x, -(x0 + MV_OVERHANG) * 4, (e->wc - x0 - 16 + MV_OVERHANG) * 4);
+    m.y = clampi(m.y, -(y0 + MV_OVERHANG) * 4, (e->hc - y0 - 16 + MV_OVERHANG) * 4);
+    return m;
+}
+
+static mv_t ctu_mv(const orc_encoder *e, int tx, int ty)
+{
+    tx = clampi(tx, 0, e->ctuw - 1); ty = clampi(ty, 0, e->ctuh - 1);
+    mv_t m = {e->cmv[(ty * e->ctuw + tx) * 2] * 16, e->cmv[(ty * e->ctuw + tx) * 2 + 1] * 16};
+    return m;
+}
+
+static void predict_luma(const orc_encoder *e, const plane *ref, int x0, int y0, mv_t m, pixel *dst)
+{
+    const pixel *r = ref->p + (size_t)(y0 + (m.y >> 2)) * ref->stride + x0 + (m.x >> 2);
+    orc_interp_luma(r, ref->stride, dst, 16, 16, 16, m.x & 3, m.y & 3, e->prm.bit_depth);
+}
+
+static void encode_inter_frame(orc_encoder *e, int qp)
+{
+    const int bd = e->prm.bit_depth;
+    const int lambda = k_lambda_q8[qp] << (bd - 8);
+    plane *rec = e->rec[e->cur];
+    const plane *ref = e->rec[1 - e->cur];
+    coarse_search(e);
+    for (int cy = 0; cy < e->cuh; cy++)
+        for (int cx = 0; cx < e->cuw; cx++) {
+            orc_cu *cu = &e->cus[cy * e->cuw + cx];
+            int16_t *coef = e->coefs + (size_t)(cy * e->cuw + cx) * ORC_CU_COEFS;
+            const int x0 = cx * 16, y0 = cy * 16, tx = cx >> 1, ty = cy >> 1;
+            const pixel *src = e->src[0].p + (size_t)y0 * e->src[0].stride + x0;
+            const int ss = e->src[0].stride;
+            const mv_t pred = clamp_mv(e, x0, y0, ctu_mv(e, tx, ty));
+            mv_t cand[6] = {{0, 0}, pred, ctu_mv(e, tx - 1, ty), ctu_mv(e, tx, ty - 1), ctu_mv(e, tx + 1, ty), ctu_mv(e, tx, ty + 1)};
+            mv_t best = {0, 0};
+            long bcost = -1;
+            /* integer stage: SAD */
+            for (int k = 0; k < 6; k++) {
+                const mv_t m = clamp_mv(e, x0, y0, cand[k]);
+                const pixel *r = ref[0].p + (size_t)(y0 + (m.y >> 2)) * ref[0].stride + x0 + (m.x >> 2);
+                const long cost = orc_sad(src, ss, r, ref[0].stride, 16, 16) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                if (bcost < 0 || cost < bcost) { bcost = cost; best = m; }
+            }
+            {
+                const mv_t centre = best;
+                for (int dy = -2; dy <= 2; dy++)
+                    for (int dx = -2; dx <= 2; dx++) {
+                        if (!dx && !dy) continue;
+                        mv_t m = {centre.x + 4 * dx, centre.y + 4 * dy};
+                        const mv_t cm = clamp_mv(e, x0, y0, m);
+                        if (cm.x != m.x || cm.y != m.y) continue;
+                        const pixel *r = ref[0].p + (size_t)(y0 + (m.y >> 2)) * ref[0].stride + x0 + (m.x >> 2);
+                        const long cost = orc_sad(src, ss, r, ref[0].stride, 16, 16) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                        if (cost < bcost) { bcost = cost; best = m; }
+                    }
+            }
+            /* sub-sample stages: SATD on the normative interpolation */
+            pixel blk[256];
+            predict_luma(e, &ref[0], x0, y0, best, blk);
+            bcost = orc_satd(src, ss, blk, 16, 16, 16) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+            for (int step = 2; step >= 1; step--) {
+                const mv_t centre = best;
+                for (int dy = -1; dy <= 1; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        if (!dx && !dy) continue;
+                        mv_t m = {centre.x + step * dx, centre.y + step * dy};
+                        const mv_t cm = clamp_mv(e, x0, y0, m);
+                        if (cm.x != m.x || cm.y != m.y) continue;
+                        predict_luma(e, &ref[0], x0, y0, m, blk);
+                        const long cost = orc_satd(src, ss, blk, 16, 16, 16) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                        if (cost < bcost) { bcost = cost; best = m; }
+                    }
+            }
+            cu->pred_mode = 1; cu->intra_mode = 1; cu->skip = 0;
+            cu->mvx = (int16_t)best.x; cu->mvy = (int16_t)best.y;
+            /* reconstruct */
+            predict_luma(e, &ref[0], x0, y0, best, blk);
+            pixel *ry = rec[0].p + (size_t)y0 * rec[0].stride + x0;
+            int cbf = code_block(e, src, ss, blk, 16, ry, rec[0].stride, 16, qp, 0, coef);
+            for (int c = 1; c < 3; c++) {
+                pixel cpred[64];
+                const pixel *r = ref[c].p + (size_t)(cy * 8 + (best.y >> 3)) * ref[c].stride + cx * 8 + (best.x >> 3);
+                orc_interp_chroma(r, ref[c].stride, cpred, 8, 8, 8, best.x & 7, best.y & 7, bd);
+                const pixel *cs = e->src[c].p + (size_t)cy * 8 * e->src[c].stride + cx * 8;
+                pixel *rc = rec[c].p + (size_t)cy * 8 * rec[c].stride + cx * 8;
+                cbf |= code_block(e, cs, e->src[c].stride, cpred, 8, rc, rec[c].stride, 8, chroma_qp(qp), 0, coef + (c == 1 ? 256 : 320)) << c;
+            }
+            cu->cbf = (uint8_t)cbf;
+        }
+}
+
+/* ------------------------------------------------------------------ access unit */
+
+static void picture_md5(const orc_encoder *e, const plane *rec, uint8_t md5[3][16])
+{
+    const int bps = e->prm.bit_depth > 8 ? 2 : 1;
+    for (int c = 0; c < 3; c++) {
+        const size_t n = (size_t)rec[c].w * rec[c].h * bps;
+        uint8_t *buf = (uint8_t *)malloc(n), *o = buf;
+        for (int y = 0; y < rec[c].h; y++)
+            for (int x = 0; x < rec[c].w; x++) {
+                const pixel v = rec[c].p[(size_t)y * rec[c].stride + x];
+                *o++ = (uint8_t)v;
+                if (bps == 2) *o++ = (uint8_t)(v >> 8);
+            }
+        orc_md5(buf, n, md5[c]);
+        free(buf);
+    }
+}
+
+long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const pixel *v, int cs, int force_idr, uint8_t *out,
+                   size_t cap, orc_frame_info *info)
+{
+    const orc_enc_params *p = &e->prm;
+    const int idr = force_idr || e->frame_no == 0 || (p->keyint > 0 && e->poc + 1 >= p->keyint);
+    if (idr) e->poc = 0; else e->poc++;
+    const int qp = clampi(idr ? p->qp_i : p->qp_p, 0, 51);
+    load_source(e, y, ys, u, v, cs);
+    if (idr) encode_intra_frame(e, qp); else encode_inter_frame(e, qp);
+    plane *rec = e->rec[e->cur];
+    for (int c = 0; c < 3; c++) plane_extend(&rec[c]);
+
+    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, idr, qp, e->cus, e->coefs};
+    if (orc_cabac_encode_frame(&fs, e->payload, e->payload_cap, e->row_off, e->row_len) != 0)
+        return -1;
+
+    size_t o = 0;
+    if (p->aud) o += orc_write_aud(idr ? 0 : 1, out + o, cap - o);
+    if (idr && (e->frame_no == 0 || p->repeat_headers)) o += orc_enc_headers(e, out + o, cap - o);
+    if (p->hrd) {
+        if (idr) { o += orc_write_sei_buffering_period(p, out + o, cap - o); e->since_bp = 0; }
+        o += orc_write_sei_pic_timing(p, e->since_bp > 0 ? e->since_bp : 1, out + o, cap - o);
+        e->since_bp++;
+    }
+    if (idr && p->hdr10) o += orc_write_sei_hdr10(p, out + o, cap - o);
+
+    /* slice NAL: header + escaped sub-streams (entry points count escaped bytes) */
+    {
+        size_t total = 0;
+        uint32_t *entry = (uint32_t *)malloc(sizeof(uint32_t) * e->ctuh);
+        uint8_t *esc = (uint8_t *)malloc(e->payload_cap + e->payload_cap / 2 + 64);
+        for (int r = 0; r < e->ctuh; r++) {
+            const size_t n = orc_escape(esc + total, e->payload_cap * 3 / 2 + 64 - total, e->payload + e->row_off[r], e->row_len[r]);
+            entry[r] = (uint32_t)n;
+            total += n;
+        }
+        uint8_t hdr[1024], hdr_esc[1600];
+        const int nal_type = idr ? 19 : 1;      /* IDR_W_RADL : TRAIL_R */
+        const size_t hn = orc_write_slice_header(p, nal_type, idr ? 2 : 1, e->poc, qp, entry, e->ctuh - 1, hdr, sizeof hdr);
+        const size_t he = orc_escape(hdr_esc, sizeof hdr_esc, hdr, hn);
+        if (o + 6 + he + total > cap) { free(entry); free(esc); return -1; }
+        const int long_start = o == 0;
+        if (long_start) out[o++] = 0;
+        out[o++] = 0; out[o++] = 0; out[o++] = 1;
+        out[o++] = (uint8_t)(nal_type << 1); out[o++] = 1;
+        memcpy(out + o, hdr_esc, he); o += he;
+        memcpy(out + o, esc, total); o += total;
+        free(entry); free(esc);
+    }
+    if (p->hash_sei) {
+        uint8_t md5[3][16];
+        picture_md5(e, rec, md5);
+        o += orc_write_sei_hash(md5, out + o, cap - o);
+    }
+    if (info) {
+        info->is_idr = idr; info->poc = e->poc; info->qp = qp; info->bytes = (int)o;
+        info->n_skip = info->n_merge = info->n_intra = 0;
+        double sse = 0;
+        for (int i = 0; i < e->cuw * e->cuh; i++) { info->n_skip += e->cus[i].skip; info->n_intra += e->cus[i].pred_mode == 0; }
+        for (int yy = 0; yy < p->height; yy++)
+            for (int xx = 0; xx < p->width; xx++) {
+                const double d = (double)e->src[0].p[(size_t)yy * e->src[0].stride + xx] - rec[0].p[(size_t)yy * rec[0].stride + xx];
+                sse += d * d;
+            }
+        const double peak = (double)((1 << p->bit_depth) - 1);
+        info->psnr_y = sse > 0 ? 10.0 * log10(peak * peak * p->width * p->height / sse) : 99.0;
+    }
+    e->cur = 1 - e->cur;
+    e->cur_ds = 1 - e->cur_ds;
+    e->frame_no++;
+    return (long)o;
+}
