@@ -1,0 +1,631 @@
+// Frame-level encoder kernels for sm_100a: ingest (+ quarter-resolution plane), hierarchical motion search,
+// fused inter prediction / transform / quantisation / reconstruction (one warp per 16x16 CU), wavefront intra
+// frames (one CTA per CTU row), border extension.  Bit-exact against oracle/hevc_encode.c.
+#include "enc_kernels.cuh"
+
+namespace hb {
+
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ int clampd(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ================================================================================================ ingest
+// one thread per 4x4 luma block: copies (with edge replication into the coded-size padding), converts the
+// input sample format and produces the quarter-resolution sample (sum + 8) >> 4
+__global__ void __launch_bounds__(256) k_ingest(IngestParams p)
+{
+    const Geom &g = p.g;
+    const int total = g.dsw * g.dsh;
+    const int cw = p.w >> 1, ch = p.h >> 1;
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < total; blk += gridDim.x * blockDim.x) {
+        const int bx = blk % g.dsw, by = blk / g.dsw;
+        int acc = 8;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int yy = min(4 * by + j, p.h - 1);
+            const uint8_t *row = p.in_y + (size_t)yy * p.in_ys;
+            uint32_t px[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int xx = min(4 * bx + i, p.w - 1);
+                uint32_t v;
+                if (p.fmt == HB_FMT_YUV420P8) v = (uint32_t)row[xx] << p.up_shift;
+                else v = (uint32_t)reinterpret_cast<const uint16_t *>(row)[xx] >> p.down_shift;
+                px[i] = v;
+                acc += v;
+            }
+            uint2 o = make_uint2(px[0] | (px[1] << 16), px[2] | (px[3] << 16));
+            *reinterpret_cast<uint2 *>(p.src.y + (size_t)(4 * by + j) * g.src_stride + 4 * bx) = o;
+        }
+        p.ds[(size_t)by * g.dsw + bx] = (pixel)(acc >> 4);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int yy = min(2 * by + j, ch - 1);
+            uint32_t uu[2], vv[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int xx = min(2 * bx + i, cw - 1);
+                if (p.fmt == HB_FMT_YUV420P8) {
+                    uu[i] = (uint32_t)p.in_u[(size_t)yy * p.in_us + xx] << p.up_shift;
+                    vv[i] = (uint32_t)p.in_v[(size_t)yy * p.in_vs + xx] << p.up_shift;
+                } else if (p.fmt == HB_FMT_P010) {      // interleaved UV plane in in_u
+                    const uint16_t *r = reinterpret_cast<const uint16_t *>(p.in_u + (size_t)yy * p.in_us);
+                    uu[i] = (uint32_t)r[2 * xx] >> p.down_shift;
+                    vv[i] = (uint32_t)r[2 * xx + 1] >> p.down_shift;
+                } else {
+                    uu[i] = (uint32_t)reinterpret_cast<const uint16_t *>(p.in_u + (size_t)yy * p.in_us)[xx] >> p.down_shift;
+                    vv[i] = (uint32_t)reinterpret_cast<const uint16_t *>(p.in_v + (size_t)yy * p.in_vs)[xx] >> p.down_shift;
+                }
+            }
+            *reinterpret_cast<uint32_t *>(p.src.u + (size_t)(2 * by + j) * g.srcc_stride + 2 * bx) = uu[0] | (uu[1] << 16);
+            *reinterpret_cast<uint32_t *>(p.src.v + (size_t)(2 * by + j) * g.srcc_stride + 2 * bx) = vv[0] | (vv[1] << 16);
+        }
+    }
+}
+
+// ================================================================================================ border extension
+// blockIdx.y = plane; threads enumerate only the border samples of the padded plane
+__global__ void __launch_bounds__(256) k_border(Planes rec, Geom g)
+{
+    const int pl = blockIdx.y;
+    pixel *base = pl == 0 ? rec.y : pl == 1 ? rec.u : rec.v;
+    const int w = pl ? g.wc >> 1 : g.wc, h = pl ? g.hc >> 1 : g.hc, pad = pl ? kPad >> 1 : kPad;
+    const int stride = pl ? g.recc_stride : g.rec_stride;
+    const int fullw = w + 2 * pad;
+    const int n_tb = 2 * pad * fullw, n_side = h * 2 * pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tb + n_side; i += gridDim.x * blockDim.x) {
+        int x, y;
+        if (i < n_tb) {
+            const int r = i / fullw;
+            x = i % fullw - pad;
+            y = r < pad ? r - pad : h + (r - pad);
+        } else {
+            const int j = i - n_tb, r = j / (2 * pad), c = j % (2 * pad);
+            y = r;
+            x = c < pad ? c - pad : w + (c - pad);
+        }
+        base[(ptrdiff_t)y * stride + x] = base[(ptrdiff_t)clampd(y, 0, h - 1) * stride + clampd(x, 0, w - 1)];
+    }
+}
+
+// ================================================================================================ coarse search
+// one CTA per CTU (8x8 block of the quarter-resolution plane), blockIdx.y = frame of the batch.
+// 625 candidates (+-12), SAD + bias * (|dx| + |dy|); winner = min over (cost << 10 | raster index).
+__global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
+{
+    __shared__ pixel cur[8][8];
+    __shared__ pixel win[32][33];
+    __shared__ unsigned long long best[4];
+    const Geom &g = p.g;
+    const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw, f = blockIdx.y;
+    const pixel *dcur = p.ds + (size_t)(f + 1) * p.ds_frame_stride, *dprev = p.ds + (size_t)f * p.ds_frame_stride;
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int i = tid & 7, j = tid >> 3;
+        cur[j][i] = dcur[(size_t)clampd(ty * 8 + j, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i, 0, g.dsw - 1)];
+    }
+    for (int k = tid; k < 32 * 32; k += 128) {
+        const int i = k & 31, j = k >> 5;
+        win[j][i] = dprev[(size_t)clampd(ty * 8 + j - kCmeRange, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i - kCmeRange, 0, g.dsw - 1)];
+    }
+    __syncthreads();
+    const int bias = 1 << (g.bit_depth - 8);
+    unsigned long long mine = ~0ull;
+    for (int c = tid; c < 625; c += 128) {
+        const int dy = c / 25, dx = c % 25;     // offsets already shifted by +12
+        int sad = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                sad += abs((int)cur[j][i] - (int)win[j + dy][i + dx]);
+        const unsigned long long key = ((unsigned long long)(sad + bias * (abs(dx - kCmeRange) + abs(dy - kCmeRange))) << 10) | (unsigned)c;
+        mine = key < mine ? key : mine;
+    }
+    for (int off = 16; off; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, mine, off);
+        mine = o < mine ? o : mine;
+    }
+    if ((tid & 31) == 0) best[tid >> 5] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = best[0];
+        for (int k = 1; k < 4; k++) b = best[k] < b ? best[k] : b;
+        const int c = (int)(b & 1023);
+        int16_t *out = p.cmv + ((size_t)f * g.ctuw * g.ctuh + blockIdx.x) * 2;
+        out[0] = (int16_t)(c % 25 - kCmeRange);
+        out[1] = (int16_t)(c / 25 - kCmeRange);
+    }
+}
+
+// ================================================================================================ inter frame
+struct WarpScratch {
+    pixel src[16][16];
+    pixel win[28][30];
+    int16_t tmp[23][18];
+    pixel pred[16][16];
+    int16_t a[16][18], b[16][18];
+};
+
+struct MV { int x, y; };
+
+__device__ __forceinline__ MV clamp_mv(const Geom &g, int x0, int y0, MV m)
+{
+    m.x = clampd(m.x, -(x0 + kMvOverhang) * 4, (g.wc - x0 - 16 + kMvOverhang) * 4);
+    m.y = clampd(m.y, -(y0 + kMvOverhang) * 4, (g.hc - y0 - 16 + kMvOverhang) * 4);
+    return m;
+}
+
+__device__ __forceinline__ MV ctu_mv(const Geom &g, const int16_t *cmv, int tx, int ty)
+{
+    tx = clampd(tx, 0, g.ctuw - 1); ty = clampd(ty, 0, g.ctuh - 1);
+    const int16_t *c = cmv + (ty * g.ctuw + tx) * 2;
+    return MV{c[0] * 16, c[1] * 16};
+}
+
+// luma prediction of the 16x16 block whose integer sample (0,0) sits at window position (ix, iy);
+// unified two-pass form (bit-exact with the normative one-pass cases)
+__device__ __forceinline__ void interp_window(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane)
+{
+    const int shift1 = bd - 8, s14 = 14 - bd, off14 = 1 << (s14 - 1), maxv = (1 << bd) - 1;
+    for (int o = lane; o < 23 * 16; o += 32) {
+        const int r = o >> 4, c = o & 15;
+        const pixel *w = &s.win[iy - 3 + r][ix - 3 + c];
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            acc += luma_tap(fx, t) * w[t];
+        s.tmp[r][c] = (int16_t)(acc >> shift1);
+    }
+    __syncwarp();
+    const int row = lane >> 1, c0 = (lane & 1) * 8;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            acc += luma_tap(fy, t) * s.tmp[row + t][c0 + c];
+        s.pred[row][c0 + c] = (pixel)clampd(((acc >> 6) + off14) >> s14, 0, maxv);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int satd16_smem(const WarpScratch &s, int lane)
+{
+    int v = 0;
+    if (lane < 16) {
+        const int sx = (lane & 3) * 4, sy = (lane >> 2) * 4;
+        int d[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                d[y][x] = (int)s.src[sy + y][sx + x] - (int)s.pred[sy + y][sx + x];
+        v = hadamard4x4_abs(d) >> 1;
+    }
+    return warp_sum(v);
+}
+
+__global__ void __launch_bounds__(128) k_inter(InterParams p)
+{
+    __shared__ WarpScratch scratch[4];
+    const Geom &g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw;
+    const int cx = 2 * tx + (warp & 1), cy = 2 * ty + (warp >> 1);
+    if (cx >= g.cuw || cy >= g.cuh)
+        return;
+    WarpScratch &s = scratch[warp];
+    const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth, maxv = (1 << bd) - 1;
+    const int lambda = lambda_q8(p.qp) << (bd - 8);
+    const int row = lane >> 1, c0 = (lane & 1) * 8;
+
+    // source block: registers (for SAD) + shared memory (for SATD)
+    int sp[8];
+    {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p.src.y + (size_t)(y0 + row) * g.src_stride + x0 + c0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { sp[2 * k] = w[k] & 0xffff; sp[2 * k + 1] = w[k] >> 16; }
+        *reinterpret_cast<uint4 *>(&s.src[row][c0]) = v;
+    }
+    const MV pred = clamp_mv(g, x0, y0, ctu_mv(g, p.cmv, tx, ty));
+    MV best{0, 0};
+    int bcost = 0x7fffffff;
+    // ---- integer stage 1: six candidates straight from global memory
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        MV c = k == 0 ? MV{0, 0} : k == 1 ? pred : k == 2 ? ctu_mv(g, p.cmv, tx - 1, ty) : k == 3 ? ctu_mv(g, p.cmv, tx, ty - 1)
+               : k == 4 ? ctu_mv(g, p.cmv, tx + 1, ty) : ctu_mv(g, p.cmv, tx, ty + 1);
+        c = clamp_mv(g, x0, y0, c);
+        const pixel *r = p.ref.y + (ptrdiff_t)(y0 + (c.y >> 2) + row) * g.rec_stride + x0 + (c.x >> 2) + c0;
+        int sad = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            sad += abs(sp[i] - (int)r[i]);
+        const int cost = warp_sum(sad) + mv_cost(lambda, c.x, c.y, pred.x, pred.y);
+        if (cost < bcost) { bcost = cost; best = c; }
+    }
+    // ---- stage the 28x28 reference window around the winner (covers +-2 integer, sub-sample taps)
+    const MV centre = best;
+    {
+        const pixel *r = p.ref.y + (ptrdiff_t)(y0 + (centre.y >> 2) - 6) * g.rec_stride + x0 + (centre.x >> 2) - 6;
+        for (int i = lane; i < 28 * 28; i += 32) {
+            const int wr = i / 28, wc = i % 28;
+            s.win[wr][wc] = r[(ptrdiff_t)wr * g.rec_stride + wc];
+        }
+    }
+    __syncwarp();
+    // ---- integer stage 2: 5x5 square, SAD from shared memory
+#pragma unroll 1
+    for (int dy = -2; dy <= 2; dy++)
+#pragma unroll 1
+        for (int dx = -2; dx <= 2; dx++) {
+            if (!dx && !dy) continue;
+            const MV m{centre.x + 4 * dx, centre.y + 4 * dy};
+            const MV cm = clamp_mv(g, x0, y0, m);
+            if (cm.x != m.x || cm.y != m.y) continue;
+            const pixel *w = &s.win[6 + dy + row][6 + dx + c0];
+            int sad = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                sad += abs(sp[i] - (int)w[i]);
+            const int cost = warp_sum(sad) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+            if (cost < bcost) { bcost = cost; best = m; }
+        }
+    // ---- sub-sample stages: SATD on the normative interpolation
+    const int wx0 = (centre.x >> 2) - 6, wy0 = (centre.y >> 2) - 6;     // window origin relative to the block position
+    interp_window(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane);
+    bcost = satd16_smem(s, lane) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+#pragma unroll 1
+    for (int step = 2; step >= 1; step--) {
+        const MV c2 = best;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll 1
+            for (int dx = -1; dx <= 1; dx++) {
+                if (!dx && !dy) continue;
+                const MV m{c2.x + step * dx, c2.y + step * dy};
+                const MV cm = clamp_mv(g, x0, y0, m);
+                if (cm.x != m.x || cm.y != m.y) continue;
+                interp_window(s, (m.x >> 2) - wx0, (m.y >> 2) - wy0, m.x & 3, m.y & 3, bd, lane);
+                const int cost = satd16_smem(s, lane) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                if (cost < bcost) { bcost = cost; best = m; }
+            }
+    }
+    // ---- luma: predict, transform, quantise, reconstruct
+    interp_window(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane);
+    int16_t *coef = p.coefs + (size_t)(cy * g.cuw + cx) * kCuCoefs;
+    int pr[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        pr[i] = s.pred[row][c0 + i];
+        s.a[row][c0 + i] = (int16_t)(sp[i] - pr[i]);
+    }
+    __syncwarp();
+    if (lane < 16) fwd_line<16, false>(&s.a[lane][0], 1, &s.b[0][lane], 18, 3 + (bd - 8));
+    __syncwarp();
+    if (lane < 16) fwd_line<16, false>(&s.b[lane][0], 1, &s.a[0][lane], 18, 10);
+    __syncwarp();
+    const QuantParam qy = make_quant(4, p.qp + 6 * (bd - 8), bd, 0);
+    int lv[8];
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        lv[i] = quant_one(s.a[row][c0 + i], qy);
+        nz |= lv[i] != 0;
+    }
+    {
+        uint4 o;
+        o.x = (uint32_t)(uint16_t)lv[0] | ((uint32_t)(uint16_t)lv[1] << 16);
+        o.y = (uint32_t)(uint16_t)lv[2] | ((uint32_t)(uint16_t)lv[3] << 16);
+        o.z = (uint32_t)(uint16_t)lv[4] | ((uint32_t)(uint16_t)lv[5] << 16);
+        o.w = (uint32_t)(uint16_t)lv[6] | ((uint32_t)(uint16_t)lv[7] << 16);
+        *reinterpret_cast<uint4 *>(coef + row * 16 + c0) = o;
+    }
+    const bool cbf_y = __any_sync(0xffffffffu, nz);
+    int rec[8];
+    if (cbf_y) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            s.a[row][c0 + i] = (int16_t)dequant_one(lv[i], qy);
+        __syncwarp();
+        if (lane < 16) inv_line<16, false>(&s.a[0][lane], 18, &s.b[lane][0], 1, 7);
+        __syncwarp();
+        if (lane < 16) inv_line<16, false>(&s.b[0][lane], 18, &s.a[lane][0], 1, 12 - (bd - 8));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            rec[i] = clampd(pr[i] + s.a[row][c0 + i], 0, maxv);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            rec[i] = pr[i];
+    }
+    {
+        uint4 o;
+        o.x = rec[0] | (rec[1] << 16); o.y = rec[2] | (rec[3] << 16); o.z = rec[4] | (rec[5] << 16); o.w = rec[6] | (rec[7] << 16);
+        *reinterpret_cast<uint4 *>(p.rec.y + (size_t)(y0 + row) * g.rec_stride + x0 + c0) = o;
+    }
+    __syncwarp();
+    // ---- chroma: both planes at once (lanes 0-15 -> Cb, 16-31 -> Cr for the per-sample stages)
+    const int fxc = best.x & 7, fyc = best.y & 7;
+    const int shift1 = bd - 8, s14 = 14 - bd, off14 = 1 << (s14 - 1);
+    pixel *cwin = &s.win[0][0];                 // [2][11][12]
+    int16_t *ctmp = &s.tmp[0][0];               // [2][11][8]
+    {
+        const ptrdiff_t off = (ptrdiff_t)(cy * 8 + (best.y >> 3) - 1) * g.recc_stride + cx * 8 + (best.x >> 3) - 1;
+        for (int i = lane; i < 2 * 11 * 11; i += 32) {
+            const int pl = i / 121, r = (i % 121) / 11, c = i % 11;
+            cwin[pl * 132 + r * 12 + c] = (pl ? p.ref.v : p.ref.u)[off + (ptrdiff_t)r * g.recc_stride + c];
+        }
+    }
+    __syncwarp();
+    for (int o = lane; o < 2 * 11 * 8; o += 32) {
+        const int pl = o / 88, r = (o % 88) >> 3, c = o & 7;
+        const pixel *w = cwin + pl * 132 + r * 12 + c;
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            acc += chroma_tap(fxc, t) * w[t];
+        ctmp[pl * 88 + r * 8 + c] = (int16_t)(acc >> shift1);
+    }
+    __syncwarp();
+    // each lane: 4 consecutive samples of one plane: plane = lane >> 4, row = (lane & 15) >> 1, col0 = (lane & 1) * 4
+    const int cpl = lane >> 4, crow = (lane & 15) >> 1, cc0 = (lane & 1) * 4;
+    int cpr[4], csrc[4];
+    {
+        const pixel *sp2 = (cpl ? p.src.v : p.src.u) + (size_t)(cy * 8 + crow) * g.srcc_stride + cx * 8 + cc0;
+        const uint2 v = *reinterpret_cast<const uint2 *>(sp2);
+        csrc[0] = v.x & 0xffff; csrc[1] = v.x >> 16; csrc[2] = v.y & 0xffff; csrc[3] = v.y >> 16;
+    }
+    int16_t(*ca)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.a[0][0]);     // [2][8][10]
+    int16_t(*cb)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.b[0][0]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            acc += chroma_tap(fyc, t) * ctmp[cpl * 88 + (crow + t) * 8 + cc0 + c];
+        cpr[c] = clampd(((acc >> 6) + off14) >> s14, 0, maxv);
+        ca[cpl][crow][cc0 + c] = (int16_t)(csrc[c] - cpr[c]);
+    }
+    __syncwarp();
+    if (lane < 16) fwd_line<8, false>(&ca[lane >> 3][lane & 7][0], 1, &cb[lane >> 3][0][lane & 7], 10, 2 + (bd - 8));
+    __syncwarp();
+    if (lane < 16) fwd_line<8, false>(&cb[lane >> 3][lane & 7][0], 1, &ca[lane >> 3][0][lane & 7], 10, 9);
+    __syncwarp();
+    const QuantParam qc = make_quant(3, chroma_qp(p.qp) + 6 * (bd - 8), bd, 0);
+    int clv[4];
+    bool cnz = false;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        clv[c] = quant_one(ca[cpl][crow][cc0 + c], qc);
+        cnz |= clv[c] != 0;
+    }
+    *reinterpret_cast<uint2 *>(coef + 256 + cpl * 64 + crow * 8 + cc0) =
+        make_uint2((uint32_t)(uint16_t)clv[0] | ((uint32_t)(uint16_t)clv[1] << 16), (uint32_t)(uint16_t)clv[2] | ((uint32_t)(uint16_t)clv[3] << 16));
+    const unsigned cmask = __ballot_sync(0xffffffffu, cnz);
+    const int cbf = (cbf_y ? 1 : 0) | ((cmask & 0xffffu) ? 2 : 0) | ((cmask >> 16) ? 4 : 0);
+    if (cmask) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            ca[cpl][crow][cc0 + c] = (int16_t)dequant_one(clv[c], qc);
+        __syncwarp();
+        if (lane < 16) inv_line<8, false>(&ca[lane >> 3][0][lane & 7], 10, &cb[lane >> 3][lane & 7][0], 1, 7);
+        __syncwarp();
+        if (lane < 16) inv_line<8, false>(&cb[lane >> 3][0][lane & 7], 10, &ca[lane >> 3][lane & 7][0], 1, 12 - (bd - 8));
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            cpr[c] = clampd(cpr[c] + ca[cpl][crow][cc0 + c], 0, maxv);
+    }
+    {
+        pixel *rp = (cpl ? p.rec.v : p.rec.u) + (size_t)(cy * 8 + crow) * g.recc_stride + cx * 8 + cc0;
+        *reinterpret_cast<uint2 *>(rp) = make_uint2(cpr[0] | (cpr[1] << 16), cpr[2] | (cpr[3] << 16));
+    }
+    if (lane == 0) {
+        CuInfo ci;
+        ci.pred_mode = 1; ci.intra_mode = 1; ci.cbf = (uint8_t)cbf; ci.skip = 0;
+        ci.mvx = (int16_t)best.x; ci.mvy = (int16_t)best.y;
+        p.cus[cy * g.cuw + cx] = ci;
+    }
+}
+
+// ================================================================================================ intra frame
+struct IntraScratch {
+    pixel nb[65], flt[65];
+    pixel cnb[2][33];
+    pixel src[16][16], pred[16][16];
+    int16_t a[16][18], b[16][18];
+    int cost[35];
+    int dc, best_mode;
+};
+
+// neighbour sample `i` of the (4N + 1)-sample reference array of an NxN block of CU (cx, cy), with the
+// substitution rule of 8.4.4.2.2 evaluated in closed form per 5 availability segments
+__device__ __forceinline__ pixel gather_one(const pixel *plane, int stride, const Geom &g, int cx, int cy, int N, int i, int bd)
+{
+    const int n2 = 2 * N, x0 = cx * N, y0 = cy * N;
+    const bool av[5] = {cu_avail(g, cx, cy, cx - 1, cy + 1), cu_avail(g, cx, cy, cx - 1, cy), cu_avail(g, cx, cy, cx - 1, cy - 1),
+                        cu_avail(g, cx, cy, cx, cy - 1), cu_avail(g, cx, cy, cx + 1, cy - 1)};
+    // walk order: bottom-left (bottom to top), left, corner, top, top-right
+    int seg, px, py;
+    if (i == 0) { seg = 2; px = -1; py = -1; }
+    else if (i <= n2) { seg = i <= N ? 3 : 4; px = i - 1; py = -1; }
+    else { const int k = i - 1 - n2; seg = k < N ? 1 : 0; px = -1; py = k; }
+    if (!av[seg]) {
+        int s2 = seg - 1;
+        while (s2 >= 0 && !av[s2]) s2--;
+        if (s2 >= 0) {          // last sample (in walk order) of the nearest earlier available segment
+            if (s2 == 0) { px = -1; py = N; }
+            else if (s2 == 1) { px = -1; py = 0; }
+            else if (s2 == 2) { px = -1; py = -1; }
+            else { px = N - 1; py = -1; }
+        } else {                // first sample of the first later available segment
+            s2 = seg + 1;
+            while (s2 < 5 && !av[s2]) s2++;
+            if (s2 >= 5) return (pixel)(1 << (bd - 1));
+            if (s2 == 1) { px = -1; py = N - 1; }
+            else if (s2 == 2) { px = -1; py = -1; }
+            else if (s2 == 3) { px = 0; py = -1; }
+            else { px = N; py = -1; }
+        }
+    }
+    return __ldcg(plane + (ptrdiff_t)(y0 + py) * stride + x0 + px);
+}
+
+__device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
+{
+    const Geom &g = p.g;
+    const int tid = threadIdx.x, bd = g.bit_depth, maxv = (1 << bd) - 1;
+    const int x0 = cx * 16, y0 = cy * 16;
+    const int lambda = lambda_q8(p.qp) << (bd - 8);
+    // neighbours (luma + both chroma planes) and the source block
+    if (tid < 65) s.nb[tid] = gather_one(p.rec.y, g.rec_stride, g, cx, cy, 16, tid, bd);
+    else if (tid >= 96 && tid < 96 + 66) {
+        const int k = tid - 96, pl = k / 33;
+        s.cnb[pl][k % 33] = gather_one(pl ? p.rec.v : p.rec.u, g.recc_stride, g, cx, cy, 8, k % 33, bd);
+    }
+    s.src[tid >> 4][tid & 15] = p.src.y[(size_t)(y0 + (tid >> 4)) * g.src_stride + x0 + (tid & 15)];
+    if (tid < 35) s.cost[tid] = 0;
+    __syncthreads();
+    if (tid < 65) s.flt[tid] = (pixel)intra_filtered(s.nb, 16, tid);
+    if (tid >= 64 && tid < 96) {
+        const int l = tid - 64;
+        int v = l < 16 ? s.nb[1 + l] + s.nb[33 + l] : 0;
+        v = warp_sum(v);
+        if (l == 0) s.dc = (v + 16) >> 5;
+    }
+    __syncthreads();
+    // 35 modes x 16 sub-blocks: SATD accumulated per mode
+    for (int t = tid; t < 35 * 16; t += 256) {
+        const int mode = t >> 4, sb = t & 15, sx = (sb & 3) * 4, sy = (sb >> 2) * 4;
+        const pixel *nbuf = intra_use_filter(4, mode) ? s.flt : s.nb;
+        int d[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                d[y][x] = (int)s.src[sy + y][sx + x] - intra_sample(nbuf, 16, 4, mode, sx + x, sy + y, true, maxv, s.dc);
+        atomicAdd(&s.cost[mode], hadamard4x4_abs(d) >> 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int a = 1, b = 1, mpm[3];
+        if (cu_avail(g, cx, cy, cx - 1, cy)) a = __ldcg(reinterpret_cast<const uint8_t *>(&p.cus[cy * g.cuw + cx - 1]) + 1);
+        if ((cy & 1) && cu_avail(g, cx, cy, cx, cy - 1)) b = __ldcg(reinterpret_cast<const uint8_t *>(&p.cus[(cy - 1) * g.cuw + cx]) + 1);
+        if (a == b) {
+            if (a < 2) { mpm[0] = 0; mpm[1] = 1; mpm[2] = 26; }
+            else { mpm[0] = a; mpm[1] = 2 + ((a + 29) & 31); mpm[2] = 2 + ((a - 1) & 31); }
+        } else {
+            mpm[0] = a; mpm[1] = b;
+            mpm[2] = (a != 0 && b != 0) ? 0 : (a != 1 && b != 1) ? 1 : 26;
+        }
+        int best = 0x7fffffff, bm = 0;
+        for (int m = 0; m < 35; m++) {
+            const int bits = m == mpm[0] ? 2 : (m == mpm[1] || m == mpm[2]) ? 3 : 6;
+            const int c = s.cost[m] + ((lambda * bits) >> 8);
+            if (c < best) { best = c; bm = m; }
+        }
+        s.best_mode = bm;
+    }
+    __syncthreads();
+    const int mode = s.best_mode;
+    int16_t *coef = p.coefs + (size_t)(cy * g.cuw + cx) * kCuCoefs;
+    // ---- luma
+    const int py = tid >> 4, px = tid & 15;
+    const int pv = intra_sample(intra_use_filter(4, mode) ? s.flt : s.nb, 16, 4, mode, px, py, true, maxv, s.dc);
+    s.a[py][px] = (int16_t)((int)s.src[py][px] - pv);
+    __syncthreads();
+    if (tid < 16) fwd_line<16, false>(&s.a[tid][0], 1, &s.b[0][tid], 18, 3 + (bd - 8));
+    __syncthreads();
+    if (tid < 16) fwd_line<16, false>(&s.b[tid][0], 1, &s.a[0][tid], 18, 10);
+    __syncthreads();
+    const QuantParam qy = make_quant(4, p.qp + 6 * (bd - 8), bd, 1);
+    const int lv = quant_one(s.a[py][px], qy);
+    coef[tid] = (int16_t)lv;
+    const int cbf_y = __syncthreads_or(lv != 0);
+    int recv = pv;
+    if (cbf_y) {
+        s.a[py][px] = (int16_t)dequant_one(lv, qy);
+        __syncthreads();
+        if (tid < 16) inv_line<16, false>(&s.a[0][tid], 18, &s.b[tid][0], 1, 7);
+        __syncthreads();
+        if (tid < 16) inv_line<16, false>(&s.b[0][tid], 18, &s.a[tid][0], 1, 12 - (bd - 8));
+        __syncthreads();
+        recv = clampd(pv + s.a[py][px], 0, maxv);
+    }
+    p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)recv;
+    __syncthreads();
+    // ---- chroma (derived mode = luma mode; no smoothing, no edge filters): threads 0..127 = (plane, sample)
+    int16_t(*ca)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.a[0][0]);
+    int16_t(*cb)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.b[0][0]);
+    const int cpl = (tid >> 6) & 1, cyy = (tid >> 3) & 7, cxx = tid & 7;
+    int cpv = 0;
+    if (tid < 128) {
+        const pixel *nbuf = s.cnb[cpl];
+        int dcs = 8;
+        for (int i = 0; i < 8; i++) dcs += nbuf[1 + i] + nbuf[17 + i];
+        cpv = intra_sample(nbuf, 8, 3, mode, cxx, cyy, false, maxv, dcs >> 4);
+        const pixel sv = (cpl ? p.src.v : p.src.u)[(size_t)(cy * 8 + cyy) * g.srcc_stride + cx * 8 + cxx];
+        ca[cpl][cyy][cxx] = (int16_t)((int)sv - cpv);
+    }
+    __syncthreads();
+    if (tid < 16) fwd_line<8, false>(&ca[tid >> 3][tid & 7][0], 1, &cb[tid >> 3][0][tid & 7], 10, 2 + (bd - 8));
+    __syncthreads();
+    if (tid < 16) fwd_line<8, false>(&cb[tid >> 3][tid & 7][0], 1, &ca[tid >> 3][0][tid & 7], 10, 9);
+    __syncthreads();
+    const QuantParam qc = make_quant(3, chroma_qp(p.qp) + 6 * (bd - 8), bd, 1);
+    int clv = 0;
+    if (tid < 128) {
+        clv = quant_one(ca[cpl][cyy][cxx], qc);
+        coef[256 + tid] = (int16_t)clv;
+    }
+    const int cbf_u = __syncthreads_or(tid < 64 && clv != 0);
+    const int cbf_v = __syncthreads_or(tid >= 64 && tid < 128 && clv != 0);
+    if (tid < 128) ca[cpl][cyy][cxx] = (int16_t)dequant_one(clv, qc);
+    __syncthreads();
+    if (tid < 16) inv_line<8, false>(&ca[tid >> 3][0][tid & 7], 10, &cb[tid >> 3][tid & 7][0], 1, 7);
+    __syncthreads();
+    if (tid < 16) inv_line<8, false>(&cb[tid >> 3][0][tid & 7], 10, &ca[tid >> 3][tid & 7][0], 1, 12 - (bd - 8));
+    __syncthreads();
+    if (tid < 128)
+        (cpl ? p.rec.v : p.rec.u)[(size_t)(cy * 8 + cyy) * g.recc_stride + cx * 8 + cxx] = (pixel)clampd(cpv + ca[cpl][cyy][cxx], 0, maxv);
+    if (tid == 0) {
+        CuInfo ci;
+        ci.pred_mode = 0; ci.intra_mode = (uint8_t)mode; ci.cbf = (uint8_t)(cbf_y ? 1 : 0) | (cbf_u ? 2 : 0) | (cbf_v ? 4 : 0);
+        ci.skip = 0; ci.mvx = 0; ci.mvy = 0;
+        p.cus[cy * g.cuw + cx] = ci;
+    }
+    __syncthreads();
+}
+
+// one CTA per CTU row; row r may process CTU x once row r-1 has finished CTU x+1 (top-right dependency)
+__global__ void __launch_bounds__(256) k_intra(IntraParams p)
+{
+    __shared__ IntraScratch s;
+    const Geom &g = p.g;
+    const int r = blockIdx.x;
+    for (int x = 0; x < g.ctuw; x++) {
+        if (r > 0) {
+            if (threadIdx.x == 0) {
+                const int need = min(x + 2, g.ctuw);
+                while (*reinterpret_cast<volatile int *>(p.progress + r - 1) < need)
+                    __nanosleep(64);
+            }
+            __syncthreads();
+            __threadfence();
+        }
+        for (int k = 0; k < 4; k++) {
+            const int cx = 2 * x + (k & 1), cy = 2 * r + (k >> 1);
+            if (cx < g.cuw && cy < g.cuh)
+                intra_cu(p, s, cx, cy);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0)
+            atomicExch(p.progress + r, x + 1);
+    }
+}
+
+}  // namespace hb

@@ -1,0 +1,689 @@
+// Host driver of the stream encoder: batch scheduling of the kernels, parameter sets / SEI / slice headers
+// (Rec. ITU-T H.265 7.3, Annex D, Annex E), emulation prevention and access-unit assembly.
+#include <atomic>
+#include <memory>
+
+#include "common.cuh"
+#include "enc_kernels.cuh"
+
+using namespace hb;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ bit writer
+class BitWriter {
+public:
+    void put(uint32_t v, int n)
+    {
+        for (int i = n - 1; i >= 0; i--) {
+            acc_ = (uint8_t)((acc_ << 1) | ((v >> i) & 1));
+            if (++fill_ == 8) { bytes_.push_back(acc_); acc_ = 0; fill_ = 0; }
+        }
+    }
+    void flag(bool b) { put(b ? 1 : 0, 1); }
+    void ue(uint32_t v)
+    {
+        const uint64_t x = (uint64_t)v + 1;
+        int len = 0;
+        while ((x >> (len + 1)) != 0) len++;
+        put(0, len);
+        for (int i = len; i >= 0; i--) put((uint32_t)((x >> i) & 1), 1);
+    }
+    void se(int v) { ue(v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * (long long)v)); }
+    void trailing()          // rbsp_trailing_bits() / byte_alignment()
+    {
+        put(1, 1);
+        while (fill_) put(0, 1);
+    }
+    bool aligned() const { return fill_ == 0; }
+    const std::vector<uint8_t> &bytes() const { return bytes_; }
+
+private:
+    std::vector<uint8_t> bytes_;
+    uint8_t acc_ = 0;
+    int fill_ = 0;
+};
+
+void append_escaped(std::vector<uint8_t> &out, const uint8_t *in, size_t n)
+{
+    int zeros = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (zeros >= 2 && in[i] <= 3) { out.push_back(3); zeros = 0; }
+        out.push_back(in[i]);
+        zeros = in[i] == 0 ? zeros + 1 : 0;
+    }
+}
+
+void append_nal(std::vector<uint8_t> &out, int type, const std::vector<uint8_t> &rbsp, bool long_start)
+{
+    if (long_start) out.push_back(0);
+    out.push_back(0); out.push_back(0); out.push_back(1);
+    out.push_back((uint8_t)(type << 1));
+    out.push_back(1);
+    append_escaped(out, rbsp.data(), rbsp.size());
+}
+
+enum { NAL_TRAIL_R = 1, NAL_IDR_W_RADL = 19, NAL_VPS = 32, NAL_SPS = 33, NAL_PPS = 34, NAL_AUD = 35, NAL_SEI_PREFIX = 39, NAL_SEI_SUFFIX = 40 };
+
+void write_ptl(BitWriter &b, const hb_enc_params &p)
+{
+    b.put(0, 2); b.put(p.tier, 1); b.put(p.profile_idc, 5);
+    for (int j = 0; j < 32; j++) b.flag(j == p.profile_idc || (p.profile_idc == 1 && j == 2));
+    b.flag(true); b.flag(false); b.flag(false); b.flag(true);      // progressive, !interlaced, !non-packed, frame-only
+    b.put(0, 32); b.put(0, 11); b.put(0, 1);
+    b.put(p.level_idc, 8);
+}
+
+std::vector<uint8_t> make_vps(const hb_enc_params &p)
+{
+    BitWriter b;
+    b.put(0, 4); b.put(3, 2); b.put(0, 6); b.put(0, 3); b.flag(true); b.put(0xffff, 16);
+    write_ptl(b, p);
+    b.flag(true); b.ue(1); b.ue(0); b.ue(0);
+    b.put(0, 6); b.ue(0); b.flag(false); b.flag(false);
+    b.trailing();
+    return b.bytes();
+}
+
+std::vector<uint8_t> make_sps(const hb_enc_params &p, int wc, int hc)
+{
+    BitWriter b;
+    b.put(0, 4); b.put(0, 3); b.flag(true);
+    write_ptl(b, p);
+    b.ue(0); b.ue(1); b.ue(wc); b.ue(hc);
+    if (wc != p.width || hc != p.height) {
+        b.flag(true); b.ue(0); b.ue((wc - p.width) / 2); b.ue(0); b.ue((hc - p.height) / 2);
+    } else {
+        b.flag(false);
+    }
+    b.ue(p.bit_depth - 8); b.ue(p.bit_depth - 8);
+    b.ue(4);                                         // POC lsb: 8 bits
+    b.flag(true); b.ue(1); b.ue(0); b.ue(0);         // DPB 2 pictures, no reordering
+    b.ue(0); b.ue(2);                                // CB 8..32
+    b.ue(0); b.ue(3);                                // TB 4..32
+    b.ue(0); b.ue(0);                                // transform hierarchy depth inter / intra
+    b.flag(false); b.flag(false); b.flag(false); b.flag(false);   // scaling lists, AMP, SAO, PCM
+    b.ue(1); b.ue(1); b.ue(0); b.ue(0); b.flag(true);             // one RPS: previous picture
+    b.flag(false); b.flag(false); b.flag(false);                  // long-term, temporal MVP, strong smoothing
+    b.flag(true);                                                 // VUI
+    b.flag(true); b.put(1, 8);                                    //   square samples
+    b.flag(false);
+    b.flag(true); b.put(5, 3); b.flag(p.full_range != 0); b.flag(p.vui_colour != 0);
+    if (p.vui_colour) { b.put(p.colour_primaries, 8); b.put(p.transfer_characteristics, 8); b.put(p.matrix_coeffs, 8); }
+    if (p.chroma_loc >= 0) { b.flag(true); b.ue(p.chroma_loc); b.ue(p.chroma_loc); }
+    else b.flag(false);
+    b.flag(false); b.flag(false); b.flag(false); b.flag(false);
+    b.flag(true); b.put((uint32_t)p.fps_den, 32); b.put((uint32_t)p.fps_num, 32); b.flag(false);
+    b.flag(p.hrd != 0);
+    if (p.hrd) {
+        b.flag(true); b.flag(false); b.flag(false);
+        b.put(0, 4); b.put(0, 4);                                 // 64 bit/s and 16 bit units
+        b.put(23, 5); b.put(23, 5); b.put(23, 5);
+        b.flag(false); b.flag(false); b.flag(false); b.ue(0);
+        b.ue((uint32_t)((long long)p.vbv_maxrate_kbps * 1000 / 64 - 1));
+        b.ue((uint32_t)((long long)p.vbv_bufsize_kbit * 1000 / 16 - 1));
+        b.flag(false);
+    }
+    b.flag(false);                                                // bitstream restriction
+    b.flag(false);                                                // extension
+    b.trailing();
+    return b.bytes();
+}
+
+std::vector<uint8_t> make_pps(const hb_enc_params &)
+{
+    BitWriter b;
+    b.ue(0); b.ue(0);
+    b.flag(false); b.flag(false); b.put(0, 3); b.flag(false); b.flag(false);
+    b.ue(0); b.ue(0); b.se(0);
+    b.flag(false); b.flag(false); b.flag(false);                  // constrained intra, transform skip, cu_qp_delta
+    b.se(0); b.se(0); b.flag(false);
+    b.flag(false); b.flag(false); b.flag(false); b.flag(false);   // weighted x2, transquant bypass, tiles
+    b.flag(true);                                                 // entropy_coding_sync_enabled
+    b.flag(false);                                                // loop filter across slices
+    b.flag(true); b.flag(false); b.flag(true);                    // deblocking control: no override, disabled
+    b.flag(false); b.flag(false); b.ue(0); b.flag(false); b.flag(false);
+    b.trailing();
+    return b.bytes();
+}
+
+std::vector<uint8_t> make_sei(int type, const std::vector<uint8_t> &payload)
+{
+    BitWriter b;
+    int t = type;
+    size_t s = payload.size();
+    while (t >= 255) { b.put(255, 8); t -= 255; }
+    b.put(t, 8);
+    while (s >= 255) { b.put(255, 8); s -= 255; }
+    b.put((uint32_t)s, 8);
+    for (uint8_t v : payload) b.put(v, 8);
+    b.trailing();
+    return b.bytes();
+}
+
+// RFC 1321
+void md5(const uint8_t *data, size_t n, uint8_t out[16])
+{
+    static const uint32_t K[64] = {
+        0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1,
+        0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453,
+        0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942,
+        0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05,
+        0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d,
+        0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+    static const int S[4][4] = {{7, 12, 17, 22}, {5, 9, 14, 20}, {4, 11, 16, 23}, {6, 10, 15, 21}};
+    uint32_t h[4] = {0x67452301, 0xefcdab89, 0x98badcfe, 0x10325476};
+    std::vector<uint8_t> msg(data, data + n);
+    msg.push_back(0x80);
+    while (msg.size() % 64 != 56) msg.push_back(0);
+    for (int i = 0; i < 8; i++) msg.push_back((uint8_t)(((uint64_t)n * 8) >> (8 * i)));
+    for (size_t off = 0; off < msg.size(); off += 64) {
+        uint32_t M[16], a = h[0], b = h[1], c = h[2], d = h[3];
+        for (int i = 0; i < 16; i++) memcpy(&M[i], &msg[off + 4 * i], 4);
+        for (int i = 0; i < 64; i++) {
+            uint32_t f;
+            int g;
+            switch (i >> 4) {
+            case 0: f = (b & c) | (~b & d); g = i; break;
+            case 1: f = (d & b) | (~d & c); g = (5 * i + 1) & 15; break;
+            case 2: f = b ^ c ^ d; g = (3 * i + 5) & 15; break;
+            default: f = c ^ (b | ~d); g = (7 * i) & 15; break;
+            }
+            const uint32_t x = a + f + K[i] + M[g];
+            const int r = S[i >> 4][i & 3];
+            a = d; d = c; c = b;
+            b = b + ((x << r) | (x >> (32 - r)));
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+    }
+    memcpy(out, h, 16);
+}
+
+struct FrameSlot {
+    Planes src{};
+    CuInfo *cus = nullptr;
+    CuSyntax *syn = nullptr;
+    int16_t *coefs = nullptr;
+    uint8_t *rows = nullptr;
+    uint32_t *row_len = nullptr;
+    Planes keep{};            // verification copy of the reconstruction (unpadded strides = rec strides)
+};
+
+}  // namespace
+
+struct hb_encoder {
+    hb_ctx *ctx = nullptr;
+    hb_enc_params prm{};
+    Geom g{};
+    int max_batch = 0;
+    uint32_t row_cap = 0;
+    // device memory
+    std::vector<void *> dev;          // everything to free
+    std::vector<FrameSlot> slot;
+    pixel *rec_base[2][3] = {};
+    Planes rec[2];
+    pixel *ds = nullptr;              // [max_batch + 1][dsh * dsw]
+    int16_t *cmv = nullptr;           // [max_batch][ctus][2]
+    uint8_t *staging = nullptr;       // raw input frames
+    size_t staging_bytes = 0;
+    int *progress = nullptr, *overflow = nullptr;
+    EntropyFrame *eframes_dev = nullptr;
+    uint32_t *offsets_dev = nullptr;
+    uint8_t *packed_dev = nullptr;
+    size_t packed_cap = 0;
+    // pinned host
+    uint32_t *offsets_host = nullptr;
+    uint8_t *packed_host = nullptr;
+    int *overflow_host = nullptr;
+    // stream state
+    int cur = 0;                      // reconstruction buffer being written
+    long long frame_no = 0;
+    int poc = 0, since_bp = 0;
+    std::atomic<int> stop{0}, done{0};
+    cudaEvent_t ev[4] = {};
+    float last_total_ms = 0, last_kernel_ms = 0;
+    std::vector<uint8_t> vps, sps, pps;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(hb_encoder *e, T **out, size_t count)
+{
+    void *p = nullptr;
+    cudaError_t err = cudaMalloc(&p, count * sizeof(T) + 256);
+    if (err != cudaSuccess)
+        return hb_fail(e->ctx, HB_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(err));
+    e->dev.push_back(p);
+    *out = reinterpret_cast<T *>(p);
+    return HB_OK;
+}
+
+#define HB_TRY(x)                  \
+    do {                           \
+        int rc_ = (x);             \
+        if (rc_ != HB_OK) return rc_; \
+    } while (0)
+
+int alloc_planes(hb_encoder *e, Planes *pl, int wc, int hc)
+{
+    HB_TRY(dev_alloc(e, &pl->y, (size_t)wc * hc));
+    HB_TRY(dev_alloc(e, &pl->u, (size_t)(wc / 2) * (hc / 2)));
+    HB_TRY(dev_alloc(e, &pl->v, (size_t)(wc / 2) * (hc / 2)));
+    return HB_OK;
+}
+
+size_t input_frame_bytes(const hb_enc_params &p, int fmt)
+{
+    const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
+    return fmt == HB_PIX_YUV420P8 ? luma + 2 * chroma : 2 * (luma + 2 * chroma);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_encoder **out)
+{
+    HB_ARG(ctx, ctx && params && out && max_batch >= 1 && max_batch <= 1024);
+    const hb_enc_params &p = *params;
+    HB_ARG(ctx, p.width >= 16 && p.height >= 16 && (p.width % 2) == 0 && (p.height % 2) == 0 && p.width <= 8192 && p.height <= 8192);
+    HB_ARG(ctx, p.bit_depth == 8 || p.bit_depth == 10);
+    HB_ARG(ctx, p.qp_i >= 0 && p.qp_i <= 51 && p.qp_p >= 0 && p.qp_p <= 51 && p.keyint >= 1 && p.fps_num > 0 && p.fps_den > 0);
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<hb_encoder> e(new hb_encoder());
+    e->ctx = ctx;
+    e->prm = p;
+    e->max_batch = max_batch;
+    Geom &g = e->g;
+    g.wc = (p.width + 15) & ~15; g.hc = (p.height + 15) & ~15;
+    g.cuw = g.wc / 16; g.cuh = g.hc / 16; g.ctuw = (g.wc + 31) / 32; g.ctuh = (g.hc + 31) / 32;
+    g.bit_depth = p.bit_depth;
+    g.src_stride = g.wc; g.srcc_stride = g.wc / 2;
+    g.rec_stride = g.wc + 2 * kPad; g.recc_stride = g.wc / 2 + kPad;
+    g.dsw = g.wc / 4; g.dsh = g.hc / 4;
+    // worst-case CABAC payload of one CTU row: half the raw samples, at least 16 KiB
+    e->row_cap = (uint32_t)std::max<size_t>(16384, (size_t)32 * g.wc * 3 / 2 * (p.bit_depth > 8 ? 2 : 1) / 2);
+    e->row_cap = (e->row_cap + 255) & ~255u;
+    const int ncu = g.cuw * g.cuh, nctu = g.ctuw * g.ctuh;
+    hb_encoder *E = e.get();
+    E->slot.resize(max_batch);
+    for (int i = 0; i < max_batch; i++) {
+        FrameSlot &s = E->slot[i];
+        HB_TRY(alloc_planes(E, &s.src, g.wc, g.hc));
+        HB_TRY(dev_alloc(E, &s.cus, (size_t)ncu));
+        HB_TRY(dev_alloc(E, &s.syn, (size_t)ncu));
+        HB_TRY(dev_alloc(E, &s.coefs, (size_t)ncu * kCuCoefs));
+        HB_TRY(dev_alloc(E, &s.rows, (size_t)g.ctuh * E->row_cap));
+        HB_TRY(dev_alloc(E, &s.row_len, (size_t)g.ctuh));
+        if (p.keep_recon || p.hash_sei) HB_TRY(alloc_planes(E, &s.keep, g.wc, g.hc));
+    }
+    for (int k = 0; k < 2; k++)
+        for (int c = 0; c < 3; c++) {
+            const int w = c ? g.wc / 2 : g.wc, h = c ? g.hc / 2 : g.hc, pad = c ? kPad / 2 : kPad;
+            const int stride = c ? g.recc_stride : g.rec_stride;
+            HB_TRY(dev_alloc(E, &E->rec_base[k][c], (size_t)stride * (h + 2 * pad)));
+            HB_CUDA(ctx, cudaMemsetAsync(E->rec_base[k][c], 0, (size_t)stride * (h + 2 * pad) * sizeof(pixel), ctx->stream));
+            pixel *origin = E->rec_base[k][c] + (size_t)pad * stride + pad;
+            (void)w;
+            if (c == 0) E->rec[k].y = origin; else if (c == 1) E->rec[k].u = origin; else E->rec[k].v = origin;
+        }
+    HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
+    HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
+    E->staging_bytes = (size_t)max_batch * input_frame_bytes(p, HB_PIX_P010);
+    HB_TRY(dev_alloc(E, &E->staging, E->staging_bytes));
+    HB_TRY(dev_alloc(E, &E->progress, (size_t)g.ctuh));
+    HB_TRY(dev_alloc(E, &E->overflow, 1));
+    HB_TRY(dev_alloc(E, &E->eframes_dev, (size_t)max_batch));
+    HB_TRY(dev_alloc(E, &E->offsets_dev, (size_t)max_batch * g.ctuh + 1));
+    E->packed_cap = (size_t)max_batch * g.ctuh * E->row_cap / 4 + (1 << 20);
+    HB_TRY(dev_alloc(E, &E->packed_dev, E->packed_cap));
+    HB_CUDA(ctx, cudaMallocHost(&E->offsets_host, ((size_t)max_batch * g.ctuh + 1) * sizeof(uint32_t)));
+    HB_CUDA(ctx, cudaMallocHost(&E->packed_host, E->packed_cap));
+    HB_CUDA(ctx, cudaMallocHost(&E->overflow_host, sizeof(int)));
+    for (auto &ev : E->ev) HB_CUDA(ctx, cudaEventCreate(&ev));
+    HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    E->vps = make_vps(p);
+    E->sps = make_sps(p, g.wc, g.hc);
+    E->pps = make_pps(p);
+    HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = e.release();
+    return HB_OK;
+}
+
+void hb_enc_destroy(hb_encoder *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    for (void *p : e->dev) cudaFree(p);
+    if (e->offsets_host) cudaFreeHost(e->offsets_host);
+    if (e->packed_host) cudaFreeHost(e->packed_host);
+    if (e->overflow_host) cudaFreeHost(e->overflow_host);
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    delete e;
+}
+
+int hb_enc_headers(hb_encoder *e, uint8_t *out, size_t cap, size_t *len)
+{
+    if (!e) return HB_ERR_ARG;
+    HB_ARG(e->ctx, out && len);
+    std::vector<uint8_t> buf;
+    append_nal(buf, NAL_VPS, e->vps, true);
+    append_nal(buf, NAL_SPS, e->sps, true);
+    append_nal(buf, NAL_PPS, e->pps, true);
+    if (buf.size() > cap) return hb_fail(e->ctx, HB_ERR_SPACE, "%s", "header buffer too small");
+    memcpy(out, buf.data(), buf.size());
+    *len = buf.size();
+    return HB_OK;
+}
+
+int hb_enc_coded_size(const hb_encoder *e, int *wc, int *hc)
+{
+    if (!e || !wc || !hc) return HB_ERR_ARG;
+    *wc = e->g.wc; *hc = e->g.hc;
+    return HB_OK;
+}
+
+int hb_enc_request_stop(hb_encoder *e)
+{
+    if (!e) return HB_ERR_ARG;
+    e->stop.store(1);
+    return HB_OK;
+}
+
+int hb_enc_poll_progress(const hb_encoder *e, int *frames_done)
+{
+    if (!e || !frames_done) return HB_ERR_ARG;
+    *frames_done = e->done.load();
+    return HB_OK;
+}
+
+int hb_enc_last_timing(const hb_encoder *e, float *total_ms, float *kernel_ms)
+{
+    if (!e) return HB_ERR_ARG;
+    if (total_ms) *total_ms = e->last_total_ms;
+    if (kernel_ms) *kernel_ms = e->last_kernel_ms;
+    return HB_OK;
+}
+
+int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *out, size_t cap, size_t *out_len, hb_frame_stat *stats)
+{
+    if (!e) return HB_ERR_ARG;
+    hb_ctx *ctx = e->ctx;
+    HB_ARG(ctx, fr && fr->data && out && out_len && fr->n_frames >= 0);
+    HB_ARG(ctx, fr->format == HB_PIX_YUV420P8 || fr->format == HB_PIX_P010 || fr->format == HB_PIX_YUV420P16);
+    const hb_enc_params &p = e->prm;
+    const Geom &g = e->g;
+    const size_t fbytes = input_frame_bytes(p, fr->format);
+    HB_ARG(ctx, fr->frame_bytes >= fbytes);
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int ncu = g.cuw * g.cuh, nctu = g.ctuw * g.ctuh;
+    const size_t ds_stride = (size_t)g.dsw * g.dsh;
+    size_t written = 0;
+    float total_ms = 0, kernel_ms = 0;
+    e->done.store(0);
+
+    for (int base = 0; base < fr->n_frames; base += e->max_batch) {
+        const int n = std::min(e->max_batch, fr->n_frames - base);
+        if (e->stop.load()) return hb_fail(ctx, HB_ERR_STOPPED, "%s", "stopped");
+        HB_CUDA(ctx, cudaEventRecord(e->ev[0], st));
+        // ---- upload + ingest
+        const uint8_t *in = static_cast<const uint8_t *>(fr->data) + (size_t)base * fr->frame_bytes;
+        const uint8_t *dev_in = in;
+        size_t dev_fb = fr->frame_bytes;
+        if (!fr->on_device) {
+            if (fr->frame_bytes == fbytes) {
+                HB_CUDA(ctx, cudaMemcpyAsync(e->staging, in, fbytes * n, cudaMemcpyHostToDevice, st));
+            } else {
+                for (int i = 0; i < n; i++)
+                    HB_CUDA(ctx, cudaMemcpyAsync(e->staging + (size_t)i * fbytes, in + (size_t)i * fr->frame_bytes, fbytes, cudaMemcpyHostToDevice, st));
+            }
+            dev_in = e->staging;
+            dev_fb = fbytes;
+        }
+        HB_CUDA(ctx, cudaEventRecord(e->ev[1], st));
+        for (int i = 0; i < n; i++) {
+            IngestParams ip;
+            ip.g = g;
+            const uint8_t *f = dev_in + (size_t)i * dev_fb;
+            const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
+            if (fr->format == HB_PIX_YUV420P8) {
+                ip.in_y = f; ip.in_u = f + luma; ip.in_v = f + luma + chroma;
+                ip.in_ys = p.width; ip.in_us = ip.in_vs = p.width / 2;
+                ip.up_shift = p.bit_depth - 8; ip.down_shift = 0;
+            } else if (fr->format == HB_PIX_P010) {
+                ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = nullptr;
+                ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = 2 * p.width;
+                ip.up_shift = 0; ip.down_shift = 16 - p.bit_depth;
+            } else {
+                ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = f + 2 * luma + 2 * chroma;
+                ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = p.width;
+                ip.up_shift = 0; ip.down_shift = 0;
+            }
+            ip.fmt = fr->format; ip.w = p.width; ip.h = p.height;
+            ip.src = e->slot[i].src;
+            ip.ds = e->ds + (size_t)(i + 1) * ds_stride;
+            k_ingest<<<hb_grid_for(ctx, (long long)g.dsw * g.dsh, 256, 8), 256, 0, st>>>(ip);
+            HB_LAUNCHED(ctx);
+        }
+        // ---- coarse motion search for every frame of the batch at once (source-based, independent of the recon chain)
+        {
+            CoarseParams cp;
+            cp.g = g; cp.ds = e->ds; cp.ds_frame_stride = ds_stride; cp.cmv = e->cmv;
+            k_coarse<<<dim3(nctu, n), 128, 0, st>>>(cp);
+            HB_LAUNCHED(ctx);
+        }
+        // ---- frame chain
+        std::vector<int> is_idr(n), qps(n), pocs(n);
+        for (int i = 0; i < n; i++) {
+            const bool idr = (force_idr && base == 0 && i == 0) || e->frame_no == 0 || e->poc + 1 >= p.keyint;
+            e->poc = idr ? 0 : e->poc + 1;
+            is_idr[i] = idr; pocs[i] = e->poc;
+            const int qp = idr ? p.qp_i : p.qp_p;
+            qps[i] = qp;
+            FrameSlot &s = e->slot[i];
+            const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
+            if (idr) {
+                HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+                IntraParams ip;
+                ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress; ip.qp = qp;
+                k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+            } else {
+                InterParams ip;
+                ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
+                ip.cus = s.cus; ip.coefs = s.coefs; ip.qp = qp;
+                k_inter<<<nctu, 128, 0, st>>>(ip);
+            }
+            HB_LAUNCHED(ctx);
+            {
+                const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
+                k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(rec, g);
+                HB_LAUNCHED(ctx);
+            }
+            if (p.keep_recon || p.hash_sei) {
+                const pixel *srcp[3] = {rec.y, rec.u, rec.v};
+                pixel *dstp[3] = {s.keep.y, s.keep.u, s.keep.v};
+                for (int c = 0; c < 3; c++) {
+                    const int w = c ? g.wc / 2 : g.wc, h = c ? g.hc / 2 : g.hc, stride = c ? g.recc_stride : g.rec_stride;
+                    HB_CUDA(ctx, cudaMemcpy2DAsync(dstp[c], (size_t)w * sizeof(pixel), srcp[c], (size_t)stride * sizeof(pixel), (size_t)w * sizeof(pixel), h,
+                                                   cudaMemcpyDeviceToDevice, st));
+                }
+            }
+            ModeParams mp;
+            mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.is_intra = idr;
+            k_modes<<<(ncu + 255) / 256, 256, 0, st>>>(mp);
+            HB_LAUNCHED(ctx);
+            e->cur = 1 - e->cur;
+            e->frame_no++;
+        }
+        // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
+        HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
+        // ---- entropy coding of the whole batch, compaction, download
+        std::vector<EntropyFrame> ef(n);
+        for (int i = 0; i < n; i++) {
+            FrameSlot &s = e->slot[i];
+            ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
+            ef[i].is_intra = is_idr[i]; ef[i].qp = qps[i];
+        }
+        HB_CUDA(ctx, cudaMemcpyAsync(e->eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
+        HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
+        {
+            EntropyParams ep;
+            ep.g = g; ep.frames = e->eframes_dev; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
+            const size_t smem = entropy_smem_bytes(g.ctuh);
+            k_entropy<<<n, 32 * 32, smem, st>>>(ep);
+            HB_LAUNCHED(ctx);
+            PackParams pp;
+            pp.frames = e->eframes_dev; pp.n_frames = n; pp.rows = g.ctuh; pp.row_cap = e->row_cap; pp.packed = e->packed_dev; pp.offsets = e->offsets_dev;
+            k_pack_scan<<<1, 1024, 0, st>>>(pp);
+            HB_LAUNCHED(ctx);
+            k_pack_copy<<<n * g.ctuh, 128, 0, st>>>(pp);
+            HB_LAUNCHED(ctx);
+        }
+        HB_CUDA(ctx, cudaEventRecord(e->ev[2], st));
+        HB_CUDA(ctx, cudaMemcpyAsync(e->offsets_host, e->offsets_dev, sizeof(uint32_t) * ((size_t)n * g.ctuh + 1), cudaMemcpyDeviceToHost, st));
+        HB_CUDA(ctx, cudaMemcpyAsync(e->overflow_host, e->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+        HB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (*e->overflow_host) return hb_fail(ctx, HB_ERR_SPACE, "%s", "CABAC sub-stream exceeded its row buffer");
+        const uint32_t total = e->offsets_host[(size_t)n * g.ctuh];
+        if (total > e->packed_cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "packed bitstream exceeds the download buffer");
+        HB_CUDA(ctx, cudaMemcpyAsync(e->packed_host, e->packed_dev, total, cudaMemcpyDeviceToHost, st));
+        HB_CUDA(ctx, cudaEventRecord(e->ev[3], st));
+        HB_CUDA(ctx, cudaStreamSynchronize(st));
+        {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, e->ev[0], e->ev[3]);
+            cudaEventElapsedTime(&b, e->ev[1], e->ev[2]);
+            total_ms += a; kernel_ms += b;
+        }
+        // ---- access-unit assembly on the host
+        std::vector<uint8_t> au, slice;
+        std::vector<uint16_t> hostrec;
+        for (int i = 0; i < n; i++) {
+            au.clear();
+            const bool idr = is_idr[i] != 0;
+            const bool first_of_stream = e->frame_no - n + i == 0;
+            if (p.aud) { BitWriter b; b.put(idr ? 0 : 1, 3); b.trailing(); append_nal(au, NAL_AUD, b.bytes(), true); }
+            if (idr && (first_of_stream || p.repeat_headers || (force_idr && base == 0 && i == 0))) {
+                append_nal(au, NAL_VPS, e->vps, true);
+                append_nal(au, NAL_SPS, e->sps, true);
+                append_nal(au, NAL_PPS, e->pps, true);
+            }
+            if (p.hrd) {
+                if (idr) {
+                    BitWriter m;
+                    const uint32_t delay = (uint32_t)((long long)90000 * 9 * p.vbv_bufsize_kbit / ((long long)10 * p.vbv_maxrate_kbps));
+                    m.ue(0); m.flag(false); m.flag(false); m.put(0, 24); m.put(delay, 24); m.put(0, 24);
+                    if (!m.aligned()) m.trailing();
+                    append_nal(au, NAL_SEI_PREFIX, make_sei(0, m.bytes()), false);
+                    e->since_bp = 0;
+                }
+                BitWriter m;
+                m.put((uint32_t)(e->since_bp > 0 ? e->since_bp - 1 : 0), 24); m.put(0, 24);
+                append_nal(au, NAL_SEI_PREFIX, make_sei(1, m.bytes()), false);
+                e->since_bp++;
+            }
+            if (idr && p.hdr10) {
+                BitWriter m;
+                for (int k = 0; k < 8; k++) m.put(p.master_display[k], 16);
+                m.put(p.master_display[8], 32); m.put(p.master_display[9], 32);
+                append_nal(au, NAL_SEI_PREFIX, make_sei(137, m.bytes()), false);
+                BitWriter c;
+                c.put(p.max_cll, 16); c.put(p.max_fall, 16);
+                append_nal(au, NAL_SEI_PREFIX, make_sei(144, c.bytes()), false);
+            }
+            // slice: sub-streams are escaped independently (none can end in 0x00), entry points count escaped bytes
+            slice.clear();
+            std::vector<uint32_t> entry(g.ctuh);
+            for (int r = 0; r < g.ctuh; r++) {
+                const uint32_t o0 = e->offsets_host[(size_t)i * g.ctuh + r], o1 = e->offsets_host[(size_t)i * g.ctuh + r + 1];
+                const size_t before = slice.size();
+                append_escaped(slice, e->packed_host + o0, o1 - o0);
+                entry[r] = (uint32_t)(slice.size() - before);
+            }
+            BitWriter h;
+            const int nal_type = idr ? NAL_IDR_W_RADL : NAL_TRAIL_R;
+            h.flag(true);
+            if (idr) h.flag(false);
+            h.ue(0);
+            h.ue(idr ? 2 : 1);
+            if (!idr) { h.put(pocs[i] & 255, 8); h.flag(true); }
+            if (!idr) { h.flag(false); h.ue(0); }
+            h.se(qps[i] - 26);
+            h.ue(g.ctuh - 1);
+            if (g.ctuh > 1) {
+                uint32_t mx = 0;
+                for (int r = 0; r + 1 < g.ctuh; r++) mx = std::max(mx, entry[r] - 1);
+                int len = 1;
+                while (len < 32 && (mx >> len) != 0) len++;
+                h.ue(len - 1);
+                for (int r = 0; r + 1 < g.ctuh; r++) h.put(entry[r] - 1, len);
+            }
+            h.trailing();
+            const bool long_start = au.empty();
+            if (long_start) au.push_back(0);
+            au.push_back(0); au.push_back(0); au.push_back(1);
+            au.push_back((uint8_t)(nal_type << 1)); au.push_back(1);
+            append_escaped(au, h.bytes().data(), h.bytes().size());
+            au.insert(au.end(), slice.begin(), slice.end());
+            if (p.hash_sei) {
+                std::vector<uint8_t> pl(49, 0);
+                const pixel *kp[3] = {e->slot[i].keep.y, e->slot[i].keep.u, e->slot[i].keep.v};
+                for (int c = 0; c < 3; c++) {
+                    const size_t cnt = (size_t)(c ? g.wc / 2 : g.wc) * (c ? g.hc / 2 : g.hc);
+                    hostrec.resize(cnt);
+                    HB_CUDA(ctx, cudaMemcpy(hostrec.data(), kp[c], cnt * sizeof(pixel), cudaMemcpyDeviceToHost));
+                    if (p.bit_depth > 8) {
+                        md5(reinterpret_cast<const uint8_t *>(hostrec.data()), cnt * 2, &pl[1 + 16 * c]);
+                    } else {
+                        std::vector<uint8_t> b8(cnt);
+                        for (size_t k = 0; k < cnt; k++) b8[k] = (uint8_t)hostrec[k];
+                        md5(b8.data(), cnt, &pl[1 + 16 * c]);
+                    }
+                }
+                append_nal(au, NAL_SEI_SUFFIX, make_sei(132, pl), false);
+            }
+            if (written + au.size() > cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "output buffer too small");
+            memcpy(out + written, au.data(), au.size());
+            written += au.size();
+            if (stats) {
+                hb_frame_stat &s = stats[base + i];
+                s.is_idr = idr; s.poc = pocs[i]; s.qp = qps[i]; s.bytes = (uint32_t)au.size(); s.n_skip = 0; s.n_merge = 0;
+            }
+            e->done.fetch_add(1);
+        }
+    }
+    e->last_total_ms = total_ms;
+    e->last_kernel_ms = kernel_ms;
+    *out_len = written;
+    return HB_OK;
+}
+
+int hb_enc_read_recon(hb_encoder *e, int i, uint16_t *y, uint16_t *u, uint16_t *v)
+{
+    if (!e) return HB_ERR_ARG;
+    hb_ctx *ctx = e->ctx;
+    HB_ARG(ctx, (e->prm.keep_recon || e->prm.hash_sei) && i >= 0 && i < e->max_batch && y && u && v);
+    const Geom &g = e->g;
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    HB_CUDA(ctx, cudaMemcpy(y, e->slot[i].keep.y, (size_t)g.wc * g.hc * 2, cudaMemcpyDeviceToHost));
+    HB_CUDA(ctx, cudaMemcpy(u, e->slot[i].keep.u, (size_t)g.wc * g.hc / 2, cudaMemcpyDeviceToHost));
+    HB_CUDA(ctx, cudaMemcpy(v, e->slot[i].keep.v, (size_t)g.wc * g.hc / 2, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_enc_read_decisions(hb_encoder *e, int i, void *cus, int16_t *coefs)
+{
+    if (!e) return HB_ERR_ARG;
+    hb_ctx *ctx = e->ctx;
+    HB_ARG(ctx, i >= 0 && i < e->max_batch);
+    const size_t ncu = (size_t)e->g.cuw * e->g.cuh;
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (cus) HB_CUDA(ctx, cudaMemcpy(cus, e->slot[i].cus, ncu * sizeof(CuInfo), cudaMemcpyDeviceToHost));
+    if (coefs) HB_CUDA(ctx, cudaMemcpy(coefs, e->slot[i].coefs, ncu * kCuCoefs * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Kernel parameter blocks shared between the encoder kernels (enc_frame.cu, enc_entropy.cu) and the host
+// driver (enc_host.cu).
+#pragma once
+#include "enc_dev.cuh"
+
+enum { HB_FMT_YUV420P8 = 0, HB_FMT_P010 = 1, HB_FMT_YUV420P16 = 2 };
+
+namespace hb {
+
+struct IngestParams {
+    Geom g;
+    const uint8_t *in_y, *in_u, *in_v;   // P010: in_u is the interleaved UV plane
+    int in_ys, in_us, in_vs;             // bytes
+    int fmt, w, h;                       // display size
+    int up_shift, down_shift;
+    Planes src;
+    pixel *ds;
+};
+
+struct CoarseParams {
+    Geom g;
+    const pixel *ds;                     // [slots][dsh * dsw]; frame f of the batch = slot f + 1, slot f = its predecessor
+    size_t ds_frame_stride;
+    int16_t *cmv;                        // [frames][ctuh * ctuw][2]
+};
+
+struct InterParams {
+    Geom g;
+    Planes src, ref, rec;
+    const int16_t *cmv;                  // this frame's coarse vectors
+    CuInfo *cus;
+    int16_t *coefs;
+    int qp;
+};
+
+struct IntraParams {
+    Geom g;
+    Planes src, rec;
+    CuInfo *cus;
+    int16_t *coefs;
+    int *progress;                       // [ctuh], zeroed before launch
+    int qp;
+};
+
+struct ModeParams {
+    Geom g;
+    const CuInfo *cus;
+    CuSyntax *syn;
+    int is_intra;
+};
+
+struct EntropyFrame {
+    const CuInfo *cus;
+    const CuSyntax *syn;
+    const int16_t *coefs;
+    uint8_t *out;                        // [ctuh][row_cap]
+    uint32_t *row_len;                   // [ctuh]
+    int is_intra, qp;
+};
+
+struct EntropyParams {
+    Geom g;
+    const EntropyFrame *frames;          // device array, one per CTA
+    uint32_t row_cap;
+    int *overflow;
+};
+
+struct PackParams {
+    const EntropyFrame *frames;
+    int n_frames, rows;
+    uint32_t row_cap;
+    uint8_t *packed;                     // contiguous: frame 0 rows, frame 1 rows, ...
+    uint32_t *offsets;                   // [n_frames * rows + 1] exclusive prefix of row lengths
+};
+
+constexpr int kEntropyWarps = 32;
+struct EntropyWarpScratch {
+    int16_t lv[kCuCoefs];
+    uint16_t masks[24];
+    uint8_t ctx[kNumCtx + 2];
+};
+static_assert(sizeof(EntropyWarpScratch) % 16 == 0, "per-warp scratch must keep 16-byte alignment");
+// dynamic shared memory of k_entropy: per-warp scratch, context snapshots per CTU row, row-ready flags
+inline size_t entropy_smem_bytes(int ctuh)
+{
+    return sizeof(EntropyWarpScratch) * kEntropyWarps + (((size_t)ctuh * kNumCtx + 15) & ~(size_t)15) + sizeof(int) * (size_t)ctuh;
+}
+
+__global__ void k_ingest(IngestParams p);
+__global__ void k_border(Planes rec, Geom g);
+__global__ void k_coarse(CoarseParams p);
+__global__ void k_inter(InterParams p);
+__global__ void k_intra(IntraParams p);
+__global__ void k_modes(ModeParams p);
+__global__ void k_entropy(EntropyParams p);
+__global__ void k_pack_scan(PackParams p);
+__global__ void k_pack_copy(PackParams p);
+
+}  // namespace hb

@@ -1,0 +1,175 @@
+"""Host-side session of the B200 HEVC encoder: thin ctypes layer over ``hb_enc_*`` (include/hevc_b200.h).
+
+The parameters come from ``derive.derive_b200_params`` -- i.e. from the same derivation the reference feeds to
+``-x265-params`` (core/transcoder.py:398-412) -- so this object stands where the reference's ffmpeg child stands
+(``run_ffmpeg``, core/transcoder.py:497-535) for the video-encode step."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _cabi
+from .derive import B200Params
+
+PIX_YUV420P8, PIX_P010, PIX_YUV420P16 = 0, 1, 2
+
+
+class HbEncParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        'width', 'height', 'fps_num', 'fps_den', 'bit_depth', 'profile_idc', 'level_idc', 'tier', 'qp_i', 'qp_p', 'keyint', 'min_keyint',
+        'vbv_maxrate_kbps', 'vbv_bufsize_kbit', 'colour_primaries', 'transfer_characteristics', 'matrix_coeffs', 'vui_colour',
+        'chroma_loc', 'full_range', 'aud', 'repeat_headers', 'hrd', 'hdr10')] + [
+        ('master_display', C.c_uint32 * 10), ('max_cll', C.c_int), ('max_fall', C.c_int), ('hash_sei', C.c_int),
+        ('keep_recon', C.c_int), ('rate_control', C.c_int), ('reserved', C.c_int * 8)]
+
+
+class HbFrames(C.Structure):
+    _fields_ = [('data', C.c_void_p), ('on_device', C.c_int), ('format', C.c_int), ('n_frames', C.c_int), ('frame_bytes', C.c_size_t)]
+
+
+class HbFrameStat(C.Structure):
+    _fields_ = [('is_idr', C.c_int), ('poc', C.c_int), ('qp', C.c_int), ('bytes', C.c_uint32), ('n_skip', C.c_uint32), ('n_merge', C.c_uint32)]
+
+
+CU_DTYPE = np.dtype([('pred_mode', 'u1'), ('intra_mode', 'u1'), ('cbf', 'u1'), ('skip', 'u1'), ('mvx', '<i2'), ('mvy', '<i2')])
+
+
+def crf_to_qp(crf: int) -> Tuple[int, int]:
+    """Base QPs for the constant-quality operating point ``crf=`` (reference core/transcoder.py:399): the CRF value
+    is taken as the P-frame quantiser minus 2, with key frames 2 below that (x265's default ipratio is ~ -2.9 QP)."""
+    qp_p = max(0, min(51, crf + 2))
+    return max(0, min(51, qp_p - 2)), qp_p
+
+
+def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: bool = False, keep_recon: bool = False) -> HbEncParams:
+    c = HbEncParams()
+    qp_i, qp_p = qp if qp is not None else crf_to_qp(p.crf)
+    for name in ('width', 'height', 'fps_num', 'fps_den', 'bit_depth', 'profile_idc', 'level_idc', 'tier', 'keyint', 'min_keyint',
+                 'vbv_maxrate_kbps', 'vbv_bufsize_kbit', 'colour_primaries', 'transfer_characteristics', 'matrix_coeffs',
+                 'vui_colour', 'full_range', 'aud', 'repeat_headers', 'hrd', 'hdr10', 'max_cll', 'max_fall'):
+        setattr(c, name, int(getattr(p, name)))
+    c.chroma_loc = int(p.chroma_loc) if p.hdr10 else -1       # only the HDR path passes chromaloc= (core/utils.py:67)
+    c.qp_i, c.qp_p = qp_i, qp_p
+    md = tuple(p.master_display) if p.hdr10 else (0,) * 10
+    for i in range(10):
+        c.master_display[i] = int(md[i])
+    c.hash_sei, c.keep_recon = int(hash_sei), int(keep_recon)
+    return c
+
+
+@dataclass
+class FrameStat:
+    is_idr: bool
+    poc: int
+    qp: int
+    bytes: int
+
+
+class B200Encoder:
+    """One encoder = one stream state (reference picture, POC, GOP position) on one ``Context``."""
+
+    def __init__(self, ctx: _cabi.Context, params: HbEncParams, max_batch: int = 32):
+        self.ctx, self.params, self.max_batch = ctx, params, max_batch
+        L = _cabi.lib()
+        L.hb_enc_create.argtypes = [C.c_void_p, C.POINTER(HbEncParams), C.c_int, C.POINTER(C.c_void_p)]
+        L.hb_enc_destroy.argtypes = [C.c_void_p]
+        L.hb_enc_destroy.restype = None
+        L.hb_enc_headers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.hb_enc_coded_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.hb_enc_encode.argtypes = [C.c_void_p, C.POINTER(HbFrames), C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+        L.hb_enc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.hb_enc_request_stop.argtypes = [C.c_void_p]
+        L.hb_enc_poll_progress.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.hb_enc_read_recon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hb_enc_read_decisions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.L = L
+        h = C.c_void_p()
+        rc = L.hb_enc_create(ctx.h, C.byref(params), max_batch, C.byref(h))
+        if rc != 0:
+            raise _cabi.HbError(rc, L.hb_last_error(ctx.h).decode('utf-8', 'replace'))
+        self.h = h
+        wc, hc = C.c_int(), C.c_int()
+        L.hb_enc_coded_size(h, C.byref(wc), C.byref(hc))
+        self.coded_w, self.coded_h = wc.value, hc.value
+        self._out = np.empty(max(1 << 22, params.width * params.height * 3), np.uint8)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.hb_enc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise _cabi.HbError(rc, self.L.hb_last_error(self.ctx.h).decode('utf-8', 'replace'))
+
+    def headers(self) -> bytes:
+        buf = (C.c_uint8 * 1024)()
+        n = C.c_size_t()
+        self._check(self.L.hb_enc_headers(self.h, buf, 1024, C.byref(n)))
+        return bytes(buf[:n.value])
+
+    def frame_bytes(self, fmt: int) -> int:
+        w, h = self.params.width, self.params.height
+        n = w * h + 2 * (w // 2) * (h // 2)
+        return n if fmt == PIX_YUV420P8 else 2 * n
+
+    def encode(self, data, n_frames: int, fmt: int = PIX_YUV420P8, force_idr: bool = False, on_device: bool = False,
+               frame_bytes: Optional[int] = None) -> Tuple[bytes, List[FrameStat]]:
+        """``data``: numpy array (host; pinned memory avoids a staging copy in the driver) or an integer device address."""
+        fr = HbFrames()
+        if on_device:
+            fr.data = int(data)
+        else:
+            arr = np.ascontiguousarray(data)
+            fr.data = arr.ctypes.data
+        fr.on_device, fr.format, fr.n_frames = int(on_device), fmt, n_frames
+        fr.frame_bytes = frame_bytes or self.frame_bytes(fmt)
+        need = n_frames * self.frame_bytes(PIX_YUV420P8) + (1 << 20)
+        if self._out.size < need:
+            self._out = np.empty(need, np.uint8)
+        stats = (HbFrameStat * max(1, n_frames))()
+        n = C.c_size_t()
+        self._check(self.L.hb_enc_encode(self.h, C.byref(fr), int(force_idr), self._out.ctypes.data, self._out.size, C.byref(n), stats))
+        out = self._out[:n.value].tobytes()
+        return out, [FrameStat(bool(s.is_idr), s.poc, s.qp, s.bytes) for s in stats[:n_frames]]
+
+    def last_timing(self) -> Tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        self.L.hb_enc_last_timing(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def request_stop(self):
+        self.L.hb_enc_request_stop(self.h)
+
+    def progress(self) -> int:
+        n = C.c_int()
+        self.L.hb_enc_poll_progress(self.h, C.byref(n))
+        return n.value
+
+    def read_recon(self, i: int):
+        y = np.empty((self.coded_h, self.coded_w), np.uint16)
+        u = np.empty((self.coded_h // 2, self.coded_w // 2), np.uint16)
+        v = np.empty_like(u)
+        self._check(self.L.hb_enc_read_recon(self.h, i, y.ctypes.data, u.ctypes.data, v.ctypes.data))
+        return y, u, v
+
+    def read_decisions(self, i: int):
+        ncu = (self.coded_w // 16) * (self.coded_h // 16)
+        cus = np.empty(ncu, CU_DTYPE)
+        coefs = np.empty((ncu, 384), np.int16)
+        self._check(self.L.hb_enc_read_decisions(self.h, i, cus.ctypes.data, coefs.ctypes.data))
+        return cus.reshape(self.coded_h // 16, self.coded_w // 16), coefs
+
+
+def pack_yuv420p8(frames: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]]) -> np.ndarray:
+    """[(y, u, v)] uint8 planes -> one contiguous buffer in the layout ``hb_frames`` expects."""
+    return np.concatenate([np.concatenate([p.reshape(-1) for p in f]) for f in frames]).astype(np.uint8, copy=False)

@@ -107,6 +107,75 @@ int hb_dequant(hb_ctx *ctx, hb_devptr level, int n, int size, int qp, int bit_de
 int hb_intra_pred_all(hb_ctx *ctx, hb_devptr neighbours, int n, int size, int is_luma, int strong_smoothing,
                       int bit_depth, hb_devptr pred);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stream encoder.  Replaces `ffmpeg ... -c:v libx265 -x265-params ...` (argv built at reference
+ * core/transcoder.py:398-412,452-495, executed by run_ffmpeg :497-535).  hb_enc_params carries what that
+ * argv carries: the outputs of calculate_apple_hevc_level (:174), calculate_dynamic_values (:263) and
+ * build_hdr_metadata (core/utils.py:29).  Output is an Annex-B elementary stream (the mov muxing the
+ * reference leaves to ffmpeg is done by the host package, hevc_b200/mp4.py).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct hb_enc_params {
+    int width, height;                 /* display size, even */
+    int fps_num, fps_den;
+    int bit_depth;                     /* 8 = Main, 10 = Main10 */
+    int profile_idc, level_idc, tier;  /* level_idc = 30 * level */
+    int qp_i, qp_p;                    /* base QPs derived from crf= by the host (hevc_b200/encoder.py) */
+    int keyint, min_keyint;
+    int vbv_maxrate_kbps, vbv_bufsize_kbit;
+    int colour_primaries, transfer_characteristics, matrix_coeffs;
+    int vui_colour;                    /* signal the colour description */
+    int chroma_loc;                    /* chromaloc=; -1 = not signalled */
+    int full_range;                    /* -color_range tv -> 0 */
+    int aud, repeat_headers, hrd, hdr10;
+    uint32_t master_display[10];       /* Gx,Gy,Bx,By,Rx,Ry,WPx,WPy (0.00002), Lmax,Lmin (0.0001 cd/m2) */
+    int max_cll, max_fall;
+    int hash_sei;                      /* verification: emit MD5 decoded-picture-hash SEI (reads back every reconstruction) */
+    int keep_recon;                    /* verification: keep every reconstruction / decision of the last batch readable */
+    int rate_control;                  /* 0 = constant QP, 1 = VBV-constrained */
+    int reserved[8];
+} hb_enc_params;
+
+typedef enum hb_pix_fmt { HB_PIX_YUV420P8 = 0, HB_PIX_P010 = 1, HB_PIX_YUV420P16 = 2 } hb_pix_fmt;
+
+/* a run of consecutive frames, tightly packed per frame: Y plane, then U and V planes (P010: Y then UV) */
+typedef struct hb_frames {
+    const void *data;                  /* host pointer, or device pointer when on_device != 0 */
+    int on_device;
+    int format;                        /* hb_pix_fmt */
+    int n_frames;
+    size_t frame_bytes;                /* distance between successive frames */
+} hb_frames;
+
+typedef struct hb_frame_stat {
+    int is_idr, poc, qp;
+    uint32_t bytes;                    /* size of the access unit */
+    uint32_t n_skip, n_merge;
+} hb_frame_stat;
+
+typedef struct hb_encoder hb_encoder;
+
+int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_encoder **out);
+void hb_enc_destroy(hb_encoder *enc);
+/* VPS + SPS + PPS as Annex-B (for the hvcC box) */
+int hb_enc_headers(hb_encoder *enc, uint8_t *out, size_t cap, size_t *len);
+int hb_enc_coded_size(const hb_encoder *enc, int *coded_w, int *coded_h);
+/* Encode frames->n_frames consecutive frames, continuing the stream (closed GOP of params.keyint frames;
+ * force_idr restarts the GOP at the first frame: closed-GOP segment sharding).  Appends one access unit per
+ * frame to out; stats (optional) receives one entry per frame.  The call returns when the bytes are in out. */
+int hb_enc_encode(hb_encoder *enc, const hb_frames *frames, int force_idr, uint8_t *out, size_t cap, size_t *out_len,
+                  hb_frame_stat *stats);
+/* device time of the last hb_enc_encode call, measured with CUDA events on the encoder's stream:
+ * total (first upload to last download) and kernels only */
+int hb_enc_last_timing(const hb_encoder *enc, float *total_ms, float *kernel_ms);
+/* cooperative cancel (reference stop_event, core/transcoder.py:511-516): polled between frames */
+int hb_enc_request_stop(hb_encoder *enc);
+int hb_enc_poll_progress(const hb_encoder *enc, int *frames_done);
+/* verification access (needs keep_recon): frame i of the last batch, coded size, 16-bit samples */
+int hb_enc_read_recon(hb_encoder *enc, int i, uint16_t *y, uint16_t *u, uint16_t *v);
+/* per-CU decisions {pred_mode,intra_mode,cbf,skip,mvx,mvy} (8 bytes each) and levels (384 int16 each) of frame i */
+int hb_enc_read_decisions(hb_encoder *enc, int i, void *cus, int16_t *coefs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -436,7 +436,7 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
 
     size_t o = 0;
     if (p->aud) o += orc_write_aud(idr ? 0 : 1, out + o, cap - o);
-    if (idr && (e->frame_no == 0 || p->repeat_headers)) o += orc_enc_headers(e, out + o, cap - o);
+    if (idr && (e->frame_no == 0 || p->repeat_headers || force_idr)) o += orc_enc_headers(e, out + o, cap - o);
     if (p->hrd) {
         if (idr) { o += orc_write_sei_buffering_period(p, out + o, cap - o); e->since_bp = 0; }
         o += orc_write_sei_pic_timing(p, e->since_bp > 0 ? e->since_bp : 1, out + o, cap - o);

@@ -1,0 +1,100 @@
+"""GPU parity of the stream encoder, through the C ABI:
+  1. every decision, level, reconstructed sample and output byte equals the CPU model (oracle/hevc_encode.c);
+  2. every stream decodes under the FFmpeg hevc decoder to exactly the encoder's own reconstruction
+     (decoded-picture-hash verification on)."""
+import numpy as np
+import pytest
+
+from tests import enc_common as ec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from hevc_b200 import _cabi
+    c = _cabi.Context(0)
+    yield c
+    c.close()
+
+
+def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True):
+    from hevc_b200 import encoder as E
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True), max_batch=batch)
+    stream, recs, decs = b'', [], []
+    pos = 0
+    for n in (split or [len(frames8)]):
+        out, _ = enc.encode(E.pack_yuv420p8(frames8[pos:pos + n]), n)
+        stream += out
+        if read_back and n <= batch:          # the encoder keeps the reconstructions of its last batch
+            for i in range(n):
+                recs.append(enc.read_recon(i))
+                decs.append(enc.read_decisions(i))
+        pos += n
+    enc.close()
+    return stream, recs, decs
+
+
+CASES = [(192, 112, 8, 6, (26, 28)), (200, 120, 10, 5, (22, 24)), (64, 64, 8, 3, (40, 42)), (416, 240, 8, 5, (10, 12)),
+         (32, 16, 10, 3, (30, 30)), (328, 184, 10, 6, (35, 37))]
+
+
+@pytest.mark.parametrize('w,h,depth,n,qp', CASES)
+def test_matches_cpu_model_bit_for_bit(ctx, w, h, depth, n, qp):
+    p = ec.b200_params(w, h, depth, keyint=4)
+    frames = ec.clip_frames(w, h, n)
+    m_stream, m_aus, m_recs, m_decs = ec.run_model(p, frames, qp[0], qp[1], hash_sei=True)
+    g_stream, g_recs, g_decs = _gpu_encode(ctx, p, frames, qp, batch=8)
+    for i in range(n):
+        mc, ml = m_decs[i]
+        gc, gl = g_decs[i]
+        for field in ('pred_mode', 'intra_mode', 'mvx', 'mvy', 'cbf'):
+            bad = np.argwhere(mc[field] != gc[field])
+            assert bad.size == 0, f'frame {i} {field} differs first at CU {bad[0].tolist()}: model {mc[field][tuple(bad[0])]} gpu {gc[field][tuple(bad[0])]}'
+        coded = (mc['cbf'].reshape(-1) != 0)
+        assert (ml[coded] == gl[coded]).all(), f'frame {i} levels differ'
+        for c in range(3):
+            assert (m_recs[i][c] == g_recs[i][c]).all(), f'frame {i} plane {c} reconstruction differs'
+    assert g_stream == m_stream
+
+
+@pytest.mark.parametrize('w,h,depth,n,qp', CASES[:4])
+def test_decoder_reproduces_encoder_reconstruction(ctx, w, h, depth, n, qp):
+    from oracle import fforacle
+    p = ec.b200_params(w, h, depth, keyint=4)
+    frames = ec.clip_frames(w, h, n, seed=3)
+    stream, recs, _ = _gpu_encode(ctx, p, frames, qp, batch=8)
+    decoded = fforacle.decode_hevc(stream, verify_hash=True)
+    assert len(decoded) == n
+    for dec, rec in zip(decoded, recs):
+        for c in range(3):
+            assert (dec[c] == rec[c][:dec[c].shape[0], :dec[c].shape[1]]).all()
+
+
+def test_batches_and_calls_do_not_change_the_stream(ctx):
+    """the same 10 frames through one call, through batches of 3, and through three calls give identical bytes"""
+    w, h = 192, 112
+    p = ec.b200_params(w, h, 8, keyint=5)
+    frames = ec.clip_frames(w, h, 10, seed=5)
+    a, _, _ = _gpu_encode(ctx, p, frames, (27, 29), batch=16, hash_sei=False, read_back=False)
+    b, _, _ = _gpu_encode(ctx, p, frames, (27, 29), batch=3, hash_sei=False, read_back=False)
+    c, _, _ = _gpu_encode(ctx, p, frames, (27, 29), batch=4, hash_sei=False, split=[4, 1, 5], read_back=False)
+    assert a == b == c
+    m_stream, _, _, _ = ec.run_model(p, frames, 27, 29, hash_sei=False)
+    assert a == m_stream
+
+
+def test_1080p_frame_pair(ctx):
+    """full-size geometry (1080 is not a multiple of 16: conformance window, partial last CTU row)"""
+    from oracle import fforacle
+    w, h = 1920, 1080
+    p = ec.b200_params(w, h, 8, keyint=30)
+    frames = ec.clip_frames(w, h, 2, seed=2)
+    stream, recs, _ = _gpu_encode(ctx, p, frames, (24, 26), batch=2)
+    decoded = fforacle.decode_hevc(stream, verify_hash=True)
+    assert len(decoded) == 2 and decoded[0][0].shape == (1080, 1920)
+    for dec, rec in zip(decoded, recs):
+        for c in range(3):
+            assert (dec[c] == rec[c][:dec[c].shape[0], :dec[c].shape[1]]).all()
+    m_stream, _, _, _ = ec.run_model(p, frames, 24, 26, hash_sei=True)
+    assert stream == m_stream
