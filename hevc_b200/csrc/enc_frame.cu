@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
 }
 
 // ================================================================================================ inter frame
-struct WarpScratch {
+struct __align__(16) WarpScratch {
     pixel src[16][16];
     pixel win[28][30];
     int16_t tmp[23][18];
