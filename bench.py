@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Headline benchmark: 4K60 HDR10 Main10 HEVC encode frames/s on B200 (BASELINE.json configs[1]).
+
+One step = one pass of the encode hot path over one synthetic clip (default 120 frames = one closed GOP at the
+reference's keyint for 4K60 HDR).  ``value`` is device-timed with the clip resident in HBM; ``e2e`` goes through
+the C ABI with HOST buffers (upload, encode, bitstream download, access-unit assembly) on the wall clock.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU, no collective on
+                                                                                      the data path: every rank encodes its own clip)
+    python bench.py --impl reference ...      the CPU restatement (oracle/) on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = '4K60 HDR10 Main10 HEVC encode throughput'
+UNIT = 'frames/s'
+
+
+def clip_info(name: str, frames: int):
+    from hevc_b200.probe import VideoInfo
+    from hevc_b200.synth import CLIP_TYPES
+    w, h, fps, hdr = CLIP_TYPES[name]
+    tags = ('bt2020', 'smpte2084', 'bt2020nc') if hdr else ('bt709', 'bt709', 'bt709')
+    # the reference's fixtures are 5 s clips (tests/generate_test_videos.py:30); CRF/VBV derive from that duration
+    return VideoInfo(w, h, float(fps), *tags, 'yuv420p', '', '', 0, hdr, None, None, 5.0)
+
+
+def workload_config(args, params, n_gpus):
+    return {'workload': f'{args.clip}: {params.width}x{params.height}@{params.fps_num}/{params.fps_den} '
+                        f'{"Main10 HDR10" if params.bit_depth == 10 else "Main"} yuv420p8 source -> P010-depth encode',
+            'frames_per_step': args.frames, 'keyint': params.keyint, 'crf': params.crf,
+            'vbv_maxrate_kbps': params.vbv_maxrate_kbps, 'vbv_bufsize_kbit': params.vbv_bufsize_kbit,
+            'level_idc': params.level_idc, 'rate_control': 'constant QP from crf (qp_i, qp_p) = %s' % (str(args.qp),),
+            'parallelism': f'{n_gpus} independent clips, one per GPU' if n_gpus > 1 else 'single GPU',
+            'l2': 'inputs (%.1f GB/step) exceed the 126 MB L2' % (args.frames * params.width * params.height * 1.5 / 1e9)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks line from the profiling recipe, sampled during the timed region"""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False).name
+            q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+                 'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        try:
+            rows = [r.split(', ') for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = sorted(float(r[1]) for r in rows)
+            out['sm_mhz'] = sm[len(sm) // 2]
+            out['sm_max_mhz'] = float(rows[0][2])
+            out['samples'] = len(rows)
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            for k, name in enumerate(names):
+                if any(r[5 + k].strip().lower().startswith('active') for r in rows):
+                    out['reasons'].append(name)
+        except Exception:
+            pass
+        return out
+
+
+def measured_peaks():
+    try:
+        return json.loads((ROOT / 'MEASURED_PEAKS.json').read_text()), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+# ------------------------------------------------------------------------------------------------ CPU restatement arm
+def _model_segment(job):
+    """encode one forced-IDR segment with the CPU model (runs in a worker process)"""
+    frames, depth, qp, keyint, w, h = job
+    from hevc_b200.derive import B200Params  # noqa: F401  (package import check)
+    from oracle import encoder_model as em
+    enc = em.ModelEncoder(em.make_params(w, h, depth, qp_i=qp[0], qp_p=qp[1], keyint=keyint, hdr10=(depth == 10), hash_sei=False,
+                                         level_idc=153, vbv_maxrate_kbps=23520, vbv_bufsize_kbit=28224))
+    sh = depth - 8
+    total = 0
+    lw, cw = w * h, (w // 2) * (h // 2)
+    for f in frames:
+        y = f[:lw].reshape(h, w).astype(np.uint16) << sh
+        u = f[lw:lw + cw].reshape(h // 2, w // 2).astype(np.uint16) << sh
+        v = f[lw + cw:].reshape(h // 2, w // 2).astype(np.uint16) << sh
+        au, _ = enc.encode(y, u, v)
+        total += len(au)
+    enc.close()
+    return total
+
+
+def cpu_model_fps(host_frames, depth, qp, keyint, w, h, workers, frames_per_worker):
+    """frames/s of the CPU model over workers x frames_per_worker frames (independent closed-GOP segments)"""
+    import multiprocessing as mp
+    jobs = []
+    for k in range(workers):
+        seg = [host_frames[(k * frames_per_worker + i) % len(host_frames)] for i in range(frames_per_worker)]
+        jobs.append((seg, depth, qp, keyint, w, h))
+    t0 = time.perf_counter()
+    if workers == 1:
+        sizes = [_model_segment(jobs[0])]
+    else:
+        with mp.get_context('fork').Pool(workers) as pool:
+            sizes = pool.map(_model_segment, jobs)
+    dt = time.perf_counter() - t0
+    return workers * frames_per_worker / dt, dt, sum(sizes)
+
+
+def host_sample_frames(args, params, count):
+    """first `count` frames of the rank-0 clip on the host (generated on the GPU when there is one)"""
+    import torch
+    from hevc_b200.synth import TorchSynthClip
+    dev = 'cuda' if torch.cuda.is_available() else 'cpu'
+    clip = TorchSynthClip(params.width, params.height, seed=0, device=dev)
+    return [clip.frame(i).cpu().numpy() for i in range(count)]
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from hevc_b200 import derive
+    from hevc_b200.encoder import crf_to_qp
+    from oracle import cmodel
+    cmodel.build()
+    params = derive.derive_b200_params(clip_info(args.clip, args.frames))
+    args.qp = crf_to_qp(params.crf)
+    cores = os.cpu_count() or 1
+    per_worker = 2
+    frames = host_sample_frames(args, params, min(args.frames, 2 * per_worker * 2))
+    vals = []
+    for step in range(args.warmup + args.steps):
+        if step < args.warmup and step > 0:
+            continue            # one warm-up pass is enough to page the library in; each pass costs ~10 s of all cores
+        fps, dt, _ = cpu_model_fps(frames, params.bit_depth, args.qp, params.keyint, params.width, params.height, cores, per_worker)
+        if step >= args.warmup:
+            vals.append((fps, dt))
+    fps = sum(v[0] for v in vals) / len(vals)
+    ms = 1000.0 * sum(v[1] for v in vals) / len(vals)
+    sample = (f'{cores} worker processes x {per_worker} frames each (independent closed-GOP segments: 1 IDR + {per_worker - 1} P per worker) '
+              f'of the same synthetic clip, per step')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': round(fps, 4), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': round(ms, 2), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u16' if params.bit_depth > 8 else 'u8', 'data': 'synthetic',
+            'config': workload_config(args, params, 1),
+            'cpu_baseline': {'value': round(fps, 4), 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': round(fps, 4), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'libx265 (the reference CPU encoder, core/transcoder.py:398) is not in the image; this is the CPU '
+                    'restatement of the same algorithm the CUDA path runs (oracle/hevc_encode.c)'}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from hevc_b200 import _cabi, derive
+    from hevc_b200.encoder import B200Encoder, crf_to_qp, to_c_params
+    from hevc_b200.synth import TorchSynthClip
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the B200 backend has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    params = derive.derive_b200_params(clip_info(args.clip, args.frames))
+    args.qp = crf_to_qp(params.crf)
+    ctx = _cabi.Context(local)
+    enc = B200Encoder(ctx, to_c_params(params), max_batch=args.batch)
+    clip = TorchSynthClip(params.width, params.height, seed=rank, device=f'cuda:{local}')
+    dev_frames = clip.frames(0, args.frames).contiguous()          # resident in HBM
+    host_frames = torch.empty(dev_frames.shape, dtype=torch.uint8, pin_memory=True)
+    host_frames.copy_(dev_frames)
+    torch.cuda.synchronize()
+    n, fb = args.frames, clip.frame_bytes
+
+    def step_resident():
+        out, stats = enc.encode(dev_frames.data_ptr(), n, on_device=True, force_idr=True, frame_bytes=fb)
+        return len(out), enc.last_timing()
+
+    def step_host():
+        out, stats = enc.encode(host_frames.numpy(), n, on_device=False, force_idr=True, frame_bytes=fb)
+        return len(out)
+
+    for _ in range(args.warmup):
+        step_resident()
+    step_host()
+    # ---- timed: device-resident input, CUDA-event time of the encoder's stream
+    launches0 = ctx.launches
+    enc.profile(1)
+    barrier()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        dev_ms, bytes_out = 0.0, 0
+        for _ in range(args.steps):
+            nbytes, (total_ms, kernel_ms) = step_resident()
+            dev_ms += total_ms
+            bytes_out = nbytes
+        barrier()
+        wall_resident = time.perf_counter() - t0
+    prof_ms, prof_n = enc.profile(0)
+    launches = ctx.launches - launches0
+    # ---- timed: host buffers through the C ABI (upload + encode + download + access-unit assembly), wall clock
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    wall_host = time.perf_counter() - t0
+
+    times = torch.tensor([dev_ms / 1000.0, wall_resident, wall_host], device=f'cuda:{local}', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, wall_res_s, wall_host_s = (float(x) for x in times.cpu())
+    total_frames = world * n * args.steps
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        w, h = params.width, params.height
+        wc, hc = (w + 15) & ~15, (h + 15) & ~15
+        # algorithmic bytes of one inter-frame launch: read source + read reference + write reconstruction + write levels
+        # (all 4:2:0 planes of 16-bit samples) + per-CU records
+        inter_bytes = 4 * (wc * hc * 3 // 2) * 2 + (wc // 16) * (hc // 16) * 8
+        inter_n = max(1, prof_n['inter'])
+        inter_ms = prof_ms['inter'] / inter_n
+        achieved = inter_bytes / (inter_ms * 1e-3) / 1e9 if inter_ms > 0 else 0.0
+        line = {
+            'metric': METRIC, 'value': round(total_frames / dev_s, 3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': round(1000.0 * dev_s / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u16' if params.bit_depth > 8 else 'u8', 'data': 'synthetic', 'config': workload_config(args, params, world),
+            'timing': 'CUDA events on the encoder stream (first kernel to end of bitstream download), summed over batches, max over ranks',
+            'wall_ms_per_step_resident': round(1000.0 * wall_res_s / args.steps, 3),
+            'e2e': {'value': round(total_frames / wall_host_s, 3), 'unit': UNIT, 'h2d_bytes_per_step': n * fb, 'd2h_bytes_per_step': bytes_out,
+                    'timing': 'wall clock around hb_enc_encode with pinned host buffers'},
+            'gpu_launches': int(launches),
+            'bitrate_kbps': round(bytes_out * 8 / 1000.0 / (n * params.fps_den / params.fps_num), 1),
+            'roofline': {'kernel': 'k_inter (one launch per P frame)', 'bound': 'hbm', 'achieved': round(achieved, 2), 'peak': peaks['hbm_gbs'],
+                         'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 5), 'traffic': None, 'peak_kind': peak_kind,
+                         'algorithmic_bytes_per_launch': inter_bytes, 'avg_launch_ms': round(inter_ms, 4),
+                         'note': 'integer-ALU / latency bound motion search + transform kernel, not HBM bound: the HBM fraction is '
+                                 'reported because the contract asks for hbm|tensor; see profiles/ for pipe utilisation'},
+            'kernel_ms_per_step': {k: round(v / args.steps, 3) for k, v in prof_ms.items()},
+            'clocks': clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cmodel
+            cmodel.build()
+            sample_n = 3
+            frames_h = [host_frames[i].numpy() for i in range(sample_n)]
+            fps, dt, _ = cpu_model_fps(frames_h, params.bit_depth, args.qp, params.keyint, w, h, 1, sample_n)
+            line['cpu_baseline'] = {'value': round(fps, 4), 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                                    'sample': f'first {sample_n} frames (1 IDR + {sample_n - 1} P) of the same clip, single thread, {dt:.1f} s'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    enc.close()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--clip', default='4k60_hdr')
+    ap.add_argument('--frames', type=int, default=120, help='frames per step (one closed GOP of the 4K60 HDR configuration)')
+    ap.add_argument('--batch', type=int, default=40, help='frames per device batch')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -241,6 +241,10 @@ struct hb_encoder {
     int poc = 0, since_bp = 0;
     std::atomic<int> stop{0}, done{0};
     cudaEvent_t ev[4] = {};
+    std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
+    int profiling = 0;
+    float prof_ms[6] = {};            // inter, intra, coarse, entropy(+pack), ingest, other
+    int prof_launches[6] = {};
     float last_total_ms = 0, last_kernel_ms = 0;
     std::vector<uint8_t> vps, sps, pps;
 };
@@ -342,6 +346,8 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     HB_CUDA(ctx, cudaMallocHost(&E->packed_host, E->packed_cap));
     HB_CUDA(ctx, cudaMallocHost(&E->overflow_host, sizeof(int)));
     for (auto &ev : E->ev) HB_CUDA(ctx, cudaEventCreate(&ev));
+    E->kev.resize((size_t)2 * max_batch + 8);
+    for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     E->vps = make_vps(p);
     E->sps = make_sps(p, g.wc, g.hc);
@@ -361,6 +367,7 @@ void hb_enc_destroy(hb_encoder *e)
     if (e->packed_host) cudaFreeHost(e->packed_host);
     if (e->overflow_host) cudaFreeHost(e->overflow_host);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->kev) if (ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -444,6 +451,8 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             dev_fb = fbytes;
         }
         HB_CUDA(ctx, cudaEventRecord(e->ev[1], st));
+        const size_t kb = (size_t)2 * e->max_batch;      // batch-level events start here
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 0], st));
         for (int i = 0; i < n; i++) {
             IngestParams ip;
             ip.g = g;
@@ -468,6 +477,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             k_ingest<<<hb_grid_for(ctx, (long long)g.dsw * g.dsh, 256, 8), 256, 0, st>>>(ip);
             HB_LAUNCHED(ctx);
         }
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 1], st));
         // ---- coarse motion search for every frame of the batch at once (source-based, independent of the recon chain)
         {
             CoarseParams cp;
@@ -475,6 +485,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             k_coarse<<<dim3(nctu, n), 128, 0, st>>>(cp);
             HB_LAUNCHED(ctx);
         }
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 2], st));
         // ---- frame chain
         std::vector<int> is_idr(n), qps(n), pocs(n);
         for (int i = 0; i < n; i++) {
@@ -485,8 +496,9 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             qps[i] = qp;
             FrameSlot &s = e->slot[i];
             const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
+            if (idr) HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+            if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i], st));
             if (idr) {
-                HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
                 IntraParams ip;
                 ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress; ip.qp = qp;
                 k_intra<<<g.ctuh, 256, 0, st>>>(ip);
@@ -497,6 +509,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 k_inter<<<nctu, 128, 0, st>>>(ip);
             }
             HB_LAUNCHED(ctx);
+            if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
             {
                 const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
                 k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(rec, g);
@@ -521,6 +534,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
         HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
         // ---- entropy coding of the whole batch, compaction, download
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
         std::vector<EntropyFrame> ef(n);
         for (int i = 0; i < n; i++) {
             FrameSlot &s = e->slot[i];
@@ -543,6 +557,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             HB_LAUNCHED(ctx);
         }
         HB_CUDA(ctx, cudaEventRecord(e->ev[2], st));
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 4], st));
         HB_CUDA(ctx, cudaMemcpyAsync(e->offsets_host, e->offsets_dev, sizeof(uint32_t) * ((size_t)n * g.ctuh + 1), cudaMemcpyDeviceToHost, st));
         HB_CUDA(ctx, cudaMemcpyAsync(e->overflow_host, e->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
         HB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -557,6 +572,18 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             cudaEventElapsedTime(&a, e->ev[0], e->ev[3]);
             cudaEventElapsedTime(&b, e->ev[1], e->ev[2]);
             total_ms += a; kernel_ms += b;
+        }
+        if (e->profiling) {
+            float ms = 0;
+            for (int i = 0; i < n; i++) {
+                cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev[2 * i + 1]);
+                const int k = is_idr[i] ? 1 : 0;
+                e->prof_ms[k] += ms; e->prof_launches[k]++;
+            }
+            cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 1]); e->prof_ms[4] += ms; e->prof_launches[4] += n;
+            cudaEventElapsedTime(&ms, e->kev[kb + 1], e->kev[kb + 2]); e->prof_ms[2] += ms; e->prof_launches[2] += 1;
+            cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 3;
+            cudaEventElapsedTime(&ms, e->kev[kb + 2], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 2 * n;
         }
         // ---- access-unit assembly on the host
         std::vector<uint8_t> au, slice;
@@ -658,6 +685,19 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
     e->last_total_ms = total_ms;
     e->last_kernel_ms = kernel_ms;
     *out_len = written;
+    return HB_OK;
+}
+
+int hb_enc_profile(hb_encoder *e, int enable, float ms[6], int launches[6])
+{
+    if (!e) return HB_ERR_ARG;
+    if (ms) memcpy(ms, e->prof_ms, sizeof(e->prof_ms));
+    if (launches) memcpy(launches, e->prof_launches, sizeof(e->prof_launches));
+    if (enable >= 0) {
+        e->profiling = enable;
+        memset(e->prof_ms, 0, sizeof(e->prof_ms));
+        memset(e->prof_launches, 0, sizeof(e->prof_launches));
+    }
     return HB_OK;
 }
 

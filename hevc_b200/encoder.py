@@ -147,6 +147,14 @@ class B200Encoder:
         self.L.hb_enc_last_timing(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def profile(self, enable: int = -1):
+        """-> ({class: ms}, {class: launches}) accumulated since the last reset; enable=1/0 switches recording and resets."""
+        ms, ln = (C.c_float * 6)(), (C.c_int * 6)()
+        self.L.hb_enc_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.L.hb_enc_profile(self.h, enable, ms, ln)
+        names = ('inter', 'intra', 'coarse', 'entropy', 'ingest', 'chain')
+        return dict(zip(names, ms)), dict(zip(names, ln))
+
     def request_stop(self):
         self.L.hb_enc_request_stop(self.h)
 

@@ -68,3 +68,68 @@ class SynthClip:
         u8 = np.clip(np.rint(cb[0::2, 0::2]), 16, 240).astype(np.uint8)
         v8 = np.clip(np.rint(cr[0::2, 0::2]), 16, 240).astype(np.uint8)
         return y8, u8, v8
+
+
+class TorchSynthClip:
+    """Same recipe as ``SynthClip`` generated with torch on a device (fast enough for 4K60 benches).  Output layout is
+    the encoder's packed planar 4:2:0 8-bit frame: Y plane, U plane, V plane.  Deterministic per (seed, frame)."""
+
+    def __init__(self, width: int, height: int, seed: int = 0, noise: float = 2.0, device='cuda'):
+        import torch
+        import torch.nn.functional as F
+        self.torch, self.w, self.h, self.seed, self.noise, self.device = torch, width, height, seed, noise, device
+        g = torch.Generator(device='cpu').manual_seed(seed)
+        tw, th = width + 512, height + 512
+        low = torch.randn((1, 1, th // 8 + 2, tw // 8 + 2), generator=g).to(device)
+        tex = F.interpolate(low, size=(th, tw), mode='bicubic', align_corners=False)[0, 0]
+        yy, xx = torch.meshgrid(torch.arange(th, device=device, dtype=torch.float32),
+                                torch.arange(tw, device=device, dtype=torch.float32), indexing='ij')
+        self.tex = tex * 28 + 14 * torch.sin(xx / 11.0 + yy / 23.0) + 10 * torch.sin(xx / 5.3 - yy / 7.1)
+        self.yy, self.xx = yy[:height, :width], xx[:height, :width]
+        rng = np.random.default_rng(seed)
+        self.patches = [(int(rng.integers(0, width - width // 4)), int(rng.integers(0, height - height // 4)),
+                         width // 6 + int(rng.integers(0, width // 8)), height // 6 + int(rng.integers(0, height // 8)),
+                         float(rng.choice([-3, -1.25, 0.5, 2, 3.75])), float(rng.choice([-2, -0.75, 0.25, 1, 2.5])),
+                         int(rng.integers(0, 256)), int(rng.integers(0, 256))) for _ in range(5)]
+        bar = (self.xx[0] * 8 / width).long().clamp(0, 7)
+        self.bar_y = torch.tensor([180, 162, 131, 112, 84, 65, 35, 16], device=device, dtype=torch.float32)[bar]
+        self.bar_cb = torch.tensor([128, 44, 156, 72, 184, 100, 212, 128], device=device, dtype=torch.float32)[bar]
+        self.bar_cr = torch.tensor([128, 142, 44, 58, 198, 212, 114, 128], device=device, dtype=torch.float32)[bar]
+
+    @property
+    def frame_bytes(self) -> int:
+        return self.w * self.h * 3 // 2
+
+    def frame(self, n: int):
+        torch = self.torch
+        w, h, t = self.w, self.h, self.tex
+        ox, oy = 0.75 * n, 0.25 * n
+        ix, iy = int(np.floor(ox)), int(np.floor(oy))
+        fx, fy = ox - ix, oy - iy
+        x0, y0 = 128 + ix % 256, 128 + iy % 256
+        bg = ((1 - fx) * (1 - fy) * t[y0:y0 + h, x0:x0 + w] + fx * (1 - fy) * t[y0:y0 + h, x0 + 1:x0 + w + 1]
+              + (1 - fx) * fy * t[y0 + 1:y0 + h + 1, x0:x0 + w] + fx * fy * t[y0 + 1:y0 + h + 1, x0 + 1:x0 + w + 1])
+        luma = 110 + 40 * torch.sin((self.xx + 2 * n) / (w / 6.0)) * torch.cos(self.yy / (h / 4.0)) + bg
+        cb = 128 + 30 * torch.sin((self.xx - n) / (w / 3.0))
+        cr = 128 + 30 * torch.cos((self.yy + n) / (h / 3.0))
+        for (px, py, pw, ph, vx, vy, pcb, pcr) in self.patches:
+            jx, jy = int(np.floor(px + vx * n)) % (w - pw), int(np.floor(py + vy * n)) % (h - ph)
+            sub = t[300 + jy % 64:300 + jy % 64 + ph, 40 + jx % 64:40 + jx % 64 + pw]
+            luma[jy:jy + ph, jx:jx + pw] = 128 + 1.6 * sub
+            cb[jy:jy + ph, jx:jx + pw] = 0.5 * cb[jy:jy + ph, jx:jx + pw] + 0.5 * pcb
+            cr[jy:jy + ph, jx:jx + pw] = 0.5 * cr[jy:jy + ph, jx:jx + pw] + 0.5 * pcr
+        bars = h - h // 8
+        luma[bars:, :] = self.bar_y[None, :]
+        cb[bars:, :] = self.bar_cb[None, :]
+        cr[bars:, :] = self.bar_cr[None, :]
+        if self.noise > 0:
+            g = torch.Generator(device=self.device).manual_seed(self.seed * 100003 + n)
+            luma = luma + torch.randn(luma.shape, generator=g, device=self.device) * self.noise
+        y8 = luma.round().clamp(16, 235).to(torch.uint8)
+        u8 = cb[0::2, 0::2].round().clamp(16, 240).to(torch.uint8)
+        v8 = cr[0::2, 0::2].round().clamp(16, 240).to(torch.uint8)
+        return torch.cat([y8.reshape(-1), u8.reshape(-1), v8.reshape(-1)])
+
+    def frames(self, start: int, count: int):
+        """uint8 tensor [count, frame_bytes] on the device"""
+        return self.torch.stack([self.frame(start + i) for i in range(count)])

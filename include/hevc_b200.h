@@ -168,6 +168,11 @@ int hb_enc_encode(hb_encoder *enc, const hb_frames *frames, int force_idr, uint8
 /* device time of the last hb_enc_encode call, measured with CUDA events on the encoder's stream:
  * total (first upload to last download) and kernels only */
 int hb_enc_last_timing(const hb_encoder *enc, float *total_ms, float *kernel_ms);
+/* per-kernel-class device time (CUDA events around each launch on the encoder's stream), accumulated since the
+ * last call: index 0 inter-frame kernel, 1 intra-frame kernel, 2 coarse search, 3 entropy + compaction, 4 ingest,
+ * 5 whole frame chain (inter/intra + border + mode kernels).  enable: 1/0 switches the event recording and
+ * resets the accumulators, -1 only reads. */
+int hb_enc_profile(hb_encoder *enc, int enable, float ms[6], int launches[6]);
 /* cooperative cancel (reference stop_event, core/transcoder.py:511-516): polled between frames */
 int hb_enc_request_stop(hb_encoder *enc);
 int hb_enc_poll_progress(const hb_encoder *enc, int *frames_done);
