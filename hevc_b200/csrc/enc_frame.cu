@@ -6,6 +6,11 @@
 namespace hb {
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// interpolation taps in constant memory: the fraction is warp-uniform, so these are broadcast LDCs
+__constant__ int8_t c_luma_taps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+__constant__ int8_t c_chroma_taps[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
+                                           {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
 __device__ __forceinline__ int clampd(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ================================================================================================ ingest
@@ -167,13 +172,16 @@ __device__ __forceinline__ MV ctu_mv(const Geom &g, const int16_t *cmv, int tx, 
 __device__ __forceinline__ void interp_window(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane)
 {
     const int shift1 = bd - 8, s14 = 14 - bd, off14 = 1 << (s14 - 1), maxv = (1 << bd) - 1;
+    int tx[8], ty[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) { tx[t] = c_luma_taps[fx][t]; ty[t] = c_luma_taps[fy][t]; }
     for (int o = lane; o < 23 * 16; o += 32) {
         const int r = o >> 4, c = o & 15;
         const pixel *w = &s.win[iy - 3 + r][ix - 3 + c];
         int acc = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++)
-            acc += luma_tap(fx, t) * w[t];
+            acc += tx[t] * w[t];
         s.tmp[r][c] = (int16_t)(acc >> shift1);
     }
     __syncwarp();
@@ -183,7 +191,7 @@ __device__ __forceinline__ void interp_window(WarpScratch &s, int ix, int iy, in
         int acc = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++)
-            acc += luma_tap(fy, t) * s.tmp[row + t][c0 + c];
+            acc += ty[t] * s.tmp[row + t][c0 + c];
         s.pred[row][c0 + c] = (pixel)clampd(((acc >> 6) + off14) >> s14, 0, maxv);
     }
     __syncwarp();
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
         return;
     WarpScratch &s = scratch[warp];
     const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth, maxv = (1 << bd) - 1;
-    const int lambda = lambda_q8(p.qp) << (bd - 8);
+    const int lambda = p.lambda;
     const int row = lane >> 1, c0 = (lane & 1) * 8;
 
     // source block: registers (for SAD) + shared memory (for SATD)
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
     __syncwarp();
     if (lane < 16) fwd_line<16, false>(&s.b[lane][0], 1, &s.a[0][lane], 18, 10);
     __syncwarp();
-    const QuantParam qy = make_quant(4, p.qp + 6 * (bd - 8), bd, 0);
+    const QuantParam qy = p.qy;
     int lv[8];
     bool nz = false;
 #pragma unroll
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
         int acc = 0;
 #pragma unroll
         for (int t = 0; t < 4; t++)
-            acc += chroma_tap(fxc, t) * w[t];
+            acc += c_chroma_taps[fxc][t] * w[t];
         ctmp[pl * 88 + r * 8 + c] = (int16_t)(acc >> shift1);
     }
     __syncwarp();
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
         int acc = 0;
 #pragma unroll
         for (int t = 0; t < 4; t++)
-            acc += chroma_tap(fyc, t) * ctmp[cpl * 88 + (crow + t) * 8 + cc0 + c];
+            acc += c_chroma_taps[fyc][t] * ctmp[cpl * 88 + (crow + t) * 8 + cc0 + c];
         cpr[c] = clampd(((acc >> 6) + off14) >> s14, 0, maxv);
         ca[cpl][crow][cc0 + c] = (int16_t)(csrc[c] - cpr[c]);
     }
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
     __syncwarp();
     if (lane < 16) fwd_line<8, false>(&cb[lane >> 3][lane & 7][0], 1, &ca[lane >> 3][0][lane & 7], 10, 9);
     __syncwarp();
-    const QuantParam qc = make_quant(3, chroma_qp(p.qp) + 6 * (bd - 8), bd, 0);
+    const QuantParam qc = p.qc;
     int clv[4];
     bool cnz = false;
 #pragma unroll
@@ -479,7 +487,7 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     const Geom &g = p.g;
     const int tid = threadIdx.x, bd = g.bit_depth, maxv = (1 << bd) - 1;
     const int x0 = cx * 16, y0 = cy * 16;
-    const int lambda = lambda_q8(p.qp) << (bd - 8);
+    const int lambda = p.lambda;
     // neighbours (luma + both chroma planes) and the source block
     if (tid < 65) s.nb[tid] = gather_one(p.rec.y, g.rec_stride, g, cx, cy, 16, tid, bd);
     else if (tid >= 96 && tid < 96 + 66) {
@@ -541,7 +549,7 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     __syncthreads();
     if (tid < 16) fwd_line<16, false>(&s.b[tid][0], 1, &s.a[0][tid], 18, 10);
     __syncthreads();
-    const QuantParam qy = make_quant(4, p.qp + 6 * (bd - 8), bd, 1);
+    const QuantParam qy = p.qy;
     const int lv = quant_one(s.a[py][px], qy);
     coef[tid] = (int16_t)lv;
     const int cbf_y = __syncthreads_or(lv != 0);
@@ -575,7 +583,7 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     __syncthreads();
     if (tid < 16) fwd_line<8, false>(&cb[tid >> 3][tid & 7][0], 1, &ca[tid >> 3][0][tid & 7], 10, 9);
     __syncthreads();
-    const QuantParam qc = make_quant(3, chroma_qp(p.qp) + 6 * (bd - 8), bd, 1);
+    const QuantParam qc = p.qc;
     int clv = 0;
     if (tid < 128) {
         clv = quant_one(ca[cpl][cyy][cxx], qc);

@@ -501,11 +501,17 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             if (idr) {
                 IntraParams ip;
                 ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress; ip.qp = qp;
+                ip.lambda = lambda_q8(qp) << (p.bit_depth - 8);
+                ip.qy = make_quant(4, qp + 6 * (p.bit_depth - 8), p.bit_depth, 1);
+                ip.qc = make_quant(3, chroma_qp(qp) + 6 * (p.bit_depth - 8), p.bit_depth, 1);
                 k_intra<<<g.ctuh, 256, 0, st>>>(ip);
             } else {
                 InterParams ip;
                 ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
                 ip.cus = s.cus; ip.coefs = s.coefs; ip.qp = qp;
+                ip.lambda = lambda_q8(qp) << (p.bit_depth - 8);
+                ip.qy = make_quant(4, qp + 6 * (p.bit_depth - 8), p.bit_depth, 0);
+                ip.qc = make_quant(3, chroma_qp(qp) + 6 * (p.bit_depth - 8), p.bit_depth, 0);
                 k_inter<<<nctu, 128, 0, st>>>(ip);
             }
             HB_LAUNCHED(ctx);

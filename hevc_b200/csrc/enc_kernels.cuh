@@ -31,6 +31,8 @@ struct InterParams {
     CuInfo *cus;
     int16_t *coefs;
     int qp;
+    int lambda;                          // lambda_q8(qp) << (bit_depth - 8), from the host
+    QuantParam qy, qc;                   // luma / chroma quantiser (inter rounding)
 };
 
 struct IntraParams {
@@ -40,6 +42,8 @@ struct IntraParams {
     int16_t *coefs;
     int *progress;                       // [ctuh], zeroed before launch
     int qp;
+    int lambda;
+    QuantParam qy, qc;                   // intra rounding
 };
 
 struct ModeParams {

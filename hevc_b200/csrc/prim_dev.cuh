@@ -266,17 +266,12 @@ HB_DEV int hadamard8x8_abs(int m[8][8])
 }
 
 // ---- intra prediction (H.265 8.4.4.2).  Neighbour buffer: nb[0] corner, nb[1..2N] top, nb[2N+1..4N] left.
-HB_HD constexpr int intra_angle(int mode)
-{
-    constexpr int t[35] = {0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
-                           -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
-    return t[mode];
-}
-HB_HD constexpr int intra_inv_angle(int mode)
-{
-    constexpr int t[15] = {-4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096};
-    return (mode >= 11 && mode <= 25) ? t[mode - 11] : 0;
-}
+// mode -> intraPredAngle / invAngle (H.265 Tables 8-4, 8-5); constant memory: indexed by a run-time mode
+static __constant__ int8_t c_intra_angle[35] = {0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
+                                                -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
+static __constant__ int16_t c_intra_inv_angle[15] = {-4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096};
+HB_DEV int intra_angle(int mode) { return c_intra_angle[mode]; }
+HB_DEV int intra_inv_angle(int mode) { return (mode >= 11 && mode <= 25) ? c_intra_inv_angle[mode - 11] : 0; }
 
 HB_HD bool intra_use_filter(int log2n, int mode)
 {

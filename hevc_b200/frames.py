@@ -1,0 +1,114 @@
+"""Source-frame readers for the B200 encode path (the decode step of the reference's ffmpeg child).
+
+The image has no ffmpeg binary, so inputs are read natively: Y4M (8- and 10-bit 4:2:0), raw planar .yuv with a JSON
+sidecar, or anything OpenCV's bundled FFmpeg can decode (BGR frames, converted on the GPU by hb_rgb_to_yuv420)."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Iterator, Tuple
+
+import numpy as np
+
+from .encoder import PIX_YUV420P8, PIX_YUV420P16
+from .probe import VideoInfo, _probe_y4m
+
+
+class Y4MReader:
+    """Yields batches as (uint8 buffer in hb_frames layout, n_frames, pix_fmt)."""
+
+    def __init__(self, path: Path):
+        self.path = Path(path)
+        self.meta = _probe_y4m(self.path)
+        if not self.meta['pix_fmt'].startswith('yuv420'):
+            raise ValueError(f"unsupported Y4M chroma format {self.meta['pix_fmt']}")
+        self.fmt = PIX_YUV420P16 if '10' in self.meta['pix_fmt'] else PIX_YUV420P8
+        self.frame_bytes = self.meta['frame_bytes']
+        self.kind = 'yuv'
+
+    def batches(self, batch: int) -> Iterator[Tuple[np.ndarray, int, int]]:
+        with open(self.path, 'rb') as fh:
+            fh.seek(self.meta['header_len'])
+            while True:
+                buf = np.empty((batch, self.frame_bytes), np.uint8)
+                n = 0
+                while n < batch:
+                    line = fh.readline()
+                    if not line.startswith(b'FRAME'):
+                        break
+                    got = fh.readinto(memoryview(buf[n]))
+                    if got != self.frame_bytes:
+                        break
+                    n += 1
+                if n == 0:
+                    return
+                yield buf[:n], n, self.fmt
+                if n < batch:
+                    return
+
+
+class RawYuvReader:
+    """Headerless planar 4:2:0; geometry and bit depth come from the probe (sidecar JSON)."""
+
+    def __init__(self, path: Path, info: VideoInfo):
+        self.path = Path(path)
+        bps = 2 if '10' in info.pix_fmt else 1
+        self.fmt = PIX_YUV420P16 if bps == 2 else PIX_YUV420P8
+        self.frame_bytes = (info.width * info.height + 2 * (info.width // 2) * (info.height // 2)) * bps
+        self.kind = 'yuv'
+
+    def batches(self, batch: int):
+        with open(self.path, 'rb') as fh:
+            while True:
+                raw = fh.read(batch * self.frame_bytes)
+                n = len(raw) // self.frame_bytes
+                if n == 0:
+                    return
+                yield np.frombuffer(raw[:n * self.frame_bytes], np.uint8).reshape(n, self.frame_bytes), n, self.fmt
+
+
+class Cv2Reader:
+    """Container files through cv2.VideoCapture: yields BGR frame batches [n, h, w, 3] (kind == 'bgr')."""
+
+    def __init__(self, path: Path):
+        import cv2
+        self.cap = cv2.VideoCapture(str(path))
+        if not self.cap.isOpened():
+            raise ValueError(f'cannot open {path}')
+        self.kind = 'bgr'
+
+    def batches(self, batch: int):
+        while True:
+            frames = []
+            while len(frames) < batch:
+                ok, f = self.cap.read()
+                if not ok:
+                    break
+                frames.append(f)
+            if not frames:
+                self.cap.release()
+                return
+            yield np.stack(frames), len(frames), -1
+            if len(frames) < batch:
+                self.cap.release()
+                return
+
+
+def open_reader(path: Path, info: VideoInfo):
+    path = Path(path)
+    with open(path, 'rb') as fh:
+        magic = fh.read(9)
+    if magic == b'YUV4MPEG2':
+        return Y4MReader(path)
+    if path.suffix.lower() in ('.yuv', '.raw'):
+        return RawYuvReader(path, info)
+    return Cv2Reader(path)
+
+
+def write_y4m(path: Path, frames, width: int, height: int, fps: Tuple[int, int] = (30, 1), ten_bit: bool = False):
+    """Test/fixture helper: frames = iterable of (y, u, v) planes."""
+    with open(path, 'wb') as fh:
+        fh.write(f'YUV4MPEG2 W{width} H{height} F{fps[0]}:{fps[1]} Ip A1:1 C{"420p10" if ten_bit else "420"}\n'.encode())
+        for y, u, v in frames:
+            fh.write(b'FRAME\n')
+            for p in (y, u, v):
+                fh.write(np.ascontiguousarray(p, dtype='<u2' if ten_bit else np.uint8).tobytes())

@@ -1,0 +1,205 @@
+"""Minimal ISO-BMFF (MP4) writer for one HEVC video track.
+
+Stands in for the mov muxer inside the reference's ffmpeg child and reproduces the container-level contract
+of its command line (core/transcoder.py:452-495): ``-tag:v hvc1`` (:466) -> ``hvc1`` sample entry with the
+parameter sets in ``hvcC``; ``-brand mp42`` (:491); ``-movflags +write_colr+faststart`` (:492) -> ``colr nclx``
+box and ``moov`` before ``mdat``; ``handler_name=VideoHandler`` (:414).  HDR10 streams also get ``mdcv``/``clli``.
+Audio is not handled."""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+NAL_VPS, NAL_SPS, NAL_PPS, NAL_AUD = 32, 33, 34, 35
+
+
+def split_nals(annexb: bytes) -> List[bytes]:
+    """Annex-B byte stream -> NAL units (without start codes, emulation prevention untouched)."""
+    out, i, n = [], 0, len(annexb)
+    starts = []
+    while True:
+        j = annexb.find(b'\x00\x00\x01', i)
+        if j < 0:
+            break
+        starts.append(j)
+        i = j + 3
+    for k, s in enumerate(starts):
+        end = starts[k + 1] if k + 1 < len(starts) else n
+        nal = annexb[s + 3:end]
+        while nal and nal[-1] == 0 and k + 1 < len(starts):       # trailing zero_byte of the next start code
+            nal = nal[:-1]
+        out.append(nal)
+    return out
+
+
+def nal_type(nal: bytes) -> int:
+    return (nal[0] >> 1) & 0x3f
+
+
+def split_access_units(annexb: bytes) -> List[List[bytes]]:
+    """Group NAL units into access units (AUD / parameter set / prefix SEI / first slice after a VCL NAL starts a new one)."""
+    aus: List[List[bytes]] = []
+    seen_vcl = False
+    for nal in split_nals(annexb):
+        t = nal_type(nal)
+        is_vcl = t < 32
+        first_slice = is_vcl and len(nal) > 2 and (nal[2] & 0x80) != 0
+        if not aus or (seen_vcl and (t in (32, 33, 34, 35, 39) or first_slice)):
+            aus.append([])
+            seen_vcl = False
+        aus[-1].append(nal)
+        seen_vcl = seen_vcl or is_vcl
+    return aus
+
+
+def box(kind: bytes, *payload: bytes) -> bytes:
+    body = b''.join(payload)
+    return struct.pack('>I4s', 8 + len(body), kind) + body
+
+
+def full_box(kind: bytes, version: int, flags: int, *payload: bytes) -> bytes:
+    return box(kind, struct.pack('>I', (version << 24) | flags), *payload)
+
+
+@dataclass
+class TrackInfo:
+    width: int
+    height: int
+    fps_num: int
+    fps_den: int
+    profile_idc: int
+    level_idc: int
+    tier: int
+    bit_depth: int
+    colour_primaries: int = 2
+    transfer_characteristics: int = 2
+    matrix_coeffs: int = 2
+    full_range: int = 0
+    master_display: Optional[Sequence[int]] = None      # Gx,Gy,Bx,By,Rx,Ry,WPx,WPy,Lmax,Lmin
+    max_cll: int = 0
+    max_fall: int = 0
+
+
+def hvcc(info: TrackInfo, vps: bytes, sps: bytes, pps: bytes) -> bytes:
+    compat = (1 << (31 - info.profile_idc)) | ((1 << (31 - 2)) if info.profile_idc == 1 else 0)
+    constraint = 0x9 << 44                           # progressive_source + frame_only_constraint
+    rec = struct.pack('>B', 1)
+    rec += struct.pack('>B', (0 << 6) | (info.tier << 5) | info.profile_idc)
+    rec += struct.pack('>I', compat)
+    rec += constraint.to_bytes(6, 'big')
+    rec += struct.pack('>B', info.level_idc)
+    rec += struct.pack('>H', 0xf000 | 0)             # min_spatial_segmentation_idc
+    rec += struct.pack('>B', 0xfc | 3)               # parallelismType 3: entropy-coding-sync (WPP)
+    rec += struct.pack('>B', 0xfc | 1)               # chroma_format_idc 4:2:0
+    rec += struct.pack('>B', 0xf8 | (info.bit_depth - 8))
+    rec += struct.pack('>B', 0xf8 | (info.bit_depth - 8))
+    rec += struct.pack('>H', 0)                      # avgFrameRate unspecified
+    rec += struct.pack('>B', (0 << 6) | (1 << 3) | (1 << 2) | 3)   # constantFrameRate 0, 1 temporal layer, nested, 4-byte lengths
+    rec += struct.pack('>B', 3)
+    for t, nal in ((NAL_VPS, vps), (NAL_SPS, sps), (NAL_PPS, pps)):
+        rec += struct.pack('>BHH', 0x80 | t, 1, len(nal)) + nal
+    return box(b'hvcC', rec)
+
+
+def sample_entry(info: TrackInfo, vps: bytes, sps: bytes, pps: bytes) -> bytes:
+    visual = struct.pack('>6xH', 1)                                  # reserved, data_reference_index
+    visual += struct.pack('>HH12x', 0, 0)                            # pre_defined, reserved, pre_defined[3]
+    visual += struct.pack('>HH', info.width, info.height)
+    visual += struct.pack('>II', 0x00480000, 0x00480000)             # 72 dpi
+    visual += struct.pack('>IH', 0, 1)                               # reserved, frame_count
+    name = b'hevc_b200'
+    visual += bytes([len(name)]) + name + b'\0' * (31 - len(name))   # compressorname
+    visual += struct.pack('>Hh', 0x0018, -1)                         # depth, pre_defined
+    extra = hvcc(info, vps, sps, pps)
+    extra += box(b'colr', b'nclx', struct.pack('>HHHB', info.colour_primaries, info.transfer_characteristics, info.matrix_coeffs,
+                                               0x80 if info.full_range else 0))
+    if info.master_display:
+        md = list(info.master_display)
+        extra += box(b'mdcv', struct.pack('>8HII', *md[:8], md[8], md[9]))
+        extra += box(b'clli', struct.pack('>HH', info.max_cll, info.max_fall))
+    extra += box(b'pasp', struct.pack('>II', 1, 1))
+    return box(b'hvc1', visual, extra)
+
+
+def mux(info: TrackInfo, access_units: Iterable[Tuple[List[bytes], bool]]) -> bytes:
+    """access_units: (NAL units of one frame, is_sync).  Parameter sets are taken from the first access unit that carries
+    them and are removed from the samples (``hvc1`` keeps them out of band).  Returns the complete file, moov first."""
+    vps = sps = pps = None
+    samples: List[bytes] = []
+    sync: List[int] = []
+    for i, (nals, is_sync) in enumerate(access_units):
+        body = bytearray()
+        for nal in nals:
+            t = nal_type(nal)
+            if t == NAL_VPS:
+                vps = vps or nal
+            elif t == NAL_SPS:
+                sps = sps or nal
+            elif t == NAL_PPS:
+                pps = pps or nal
+            else:
+                body += struct.pack('>I', len(nal)) + nal
+        samples.append(bytes(body))
+        if is_sync:
+            sync.append(i + 1)
+    if not (vps and sps and pps):
+        raise ValueError('stream carries no VPS/SPS/PPS')
+    n = len(samples)
+    timescale, delta = info.fps_num, info.fps_den
+    duration = n * delta
+    matrix = struct.pack('>9I', 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000)
+
+    stbl_fixed = [
+        full_box(b'stsd', 0, 0, struct.pack('>I', 1), sample_entry(info, vps, sps, pps)),
+        full_box(b'stts', 0, 0, struct.pack('>III', 1, n, delta)),
+        full_box(b'stss', 0, 0, struct.pack('>I', len(sync)), b''.join(struct.pack('>I', s) for s in sync)),
+        full_box(b'stsc', 0, 0, struct.pack('>IIII', 1, 1, n, 1)),       # one chunk holding every sample
+        full_box(b'stsz', 0, 0, struct.pack('>II', 0, n), b''.join(struct.pack('>I', len(s)) for s in samples)),
+    ]
+
+    def moov(chunk_offset: int) -> bytes:
+        stco = full_box(b'co64', 0, 0, struct.pack('>IQ', 1, chunk_offset))
+        stbl = box(b'stbl', *stbl_fixed, stco)
+        dinf = box(b'dinf', full_box(b'dref', 0, 0, struct.pack('>I', 1), full_box(b'url ', 0, 1)))
+        minf = box(b'minf', full_box(b'vmhd', 0, 1, struct.pack('>HHHH', 0, 0, 0, 0)), dinf, stbl)
+        hdlr = full_box(b'hdlr', 0, 0, struct.pack('>I4s12x', 0, b'vide'), b'VideoHandler\0')
+        mdhd = full_box(b'mdhd', 0, 0, struct.pack('>IIIIHH', 0, 0, timescale, duration, 0x55c4, 0))
+        mdia = box(b'mdia', mdhd, hdlr, minf)
+        tkhd = full_box(b'tkhd', 0, 3, struct.pack('>IIIII8xHHHH', 0, 0, 1, 0, duration, 0, 0, 0, 0), matrix,
+                        struct.pack('>II', info.width << 16, info.height << 16))
+        mvhd = full_box(b'mvhd', 0, 0, struct.pack('>IIIIIH10x', 0, 0, timescale, duration, 0x10000, 0x100), matrix,
+                        struct.pack('>24xI', 2))
+        return box(b'moov', mvhd, box(b'trak', tkhd, mdia))
+
+    ftyp = box(b'ftyp', b'mp42', struct.pack('>I', 0), b'mp42', b'isom', b'iso2')
+    payload = b''.join(samples)
+    head = ftyp + moov(0)
+    offset = len(head) + 16                                              # 64-bit mdat header
+    head = ftyp + moov(offset)
+    mdat = struct.pack('>I4sQ', 1, b'mdat', 16 + len(payload))
+    return head + mdat + payload
+
+
+def mux_annexb(info: TrackInfo, annexb: bytes) -> bytes:
+    aus = split_access_units(annexb)
+    return mux(info, [(au, any(16 <= nal_type(x) <= 23 for x in au)) for au in aus])
+
+
+def parse_boxes(data: bytes, start: int = 0, end: Optional[int] = None, depth: int = 0):
+    """Tiny box walker used by the compliance checks: yields (path-depth, type, payload_start, payload_end)."""
+    end = len(data) if end is None else end
+    pos = start
+    containers = {b'moov', b'trak', b'mdia', b'minf', b'stbl', b'dinf'}
+    while pos + 8 <= end:
+        size, kind = struct.unpack('>I4s', data[pos:pos + 8])
+        hdr = 8
+        if size == 1:
+            size = struct.unpack('>Q', data[pos + 8:pos + 16])[0]
+            hdr = 16
+        if size < hdr:
+            break
+        yield depth, kind, pos + hdr, pos + size
+        if kind in containers:
+            yield from parse_boxes(data, pos + hdr, pos + size, depth + 1)
+        pos += size

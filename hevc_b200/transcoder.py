@@ -1,0 +1,350 @@
+"""Per-file transcode driver with the B200 backend as a third encoder choice.
+
+Drop-in for the reference's ``core/transcoder.py``: ``convert_video`` keeps its signature, result dictionary,
+progress / cancel / never-raise conventions (:537-638); ``build_ffmpeg_params`` / ``build_ffmpeg_command`` /
+``run_ffmpeg`` keep building and running the reference's libx265 / NVENC command lines (:357-535) for
+``encoder='cpu'|'nvenc'``; ``encoder='b200'`` replaces the ffmpeg child by the CUDA encoder and the MP4 writer.
+The default ``encoder='auto'`` preserves the old behaviour unless the environment variable HEVC_B200_ENCODER says
+otherwise, so existing callers (gui/worker.py:30-41) keep working unchanged."""
+from __future__ import annotations
+
+import logging
+import os
+import shutil
+import subprocess
+import threading
+from collections import OrderedDict
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+from . import derive
+from .derive import FFmpegParams, calculate_dynamic_values
+from .probe import VideoInfo, probe_media
+
+logger = logging.getLogger(__name__)
+
+ProgressCb = Optional[Callable[[str, int, int], None]]
+
+# ------------------------------------------------------------------ reference command-line branch (a3, a8-a10)
+
+NVENC_RETRIES = [
+    {'-bf': '3', '-b_ref_mode': 'middle'},
+    {'-bf': '0', '-b_ref_mode': 'disabled'},
+    {'-bf': '0', '-b_ref_mode': 'disabled', '-temporal-aq': '0'},
+    {'-bf': '0', '-b_ref_mode': 'disabled', '-temporal-aq': '0', '-spatial-aq': '0'},
+]
+VIDEO_METADATA_FLAGS = ['-metadata:s:v:0', 'handler_name=VideoHandler']
+
+
+def has_nvenc() -> bool:
+    """core/utils.py:9-15"""
+    try:
+        res = subprocess.run(['ffmpeg', '-hide_banner', '-encoders'], capture_output=True, text=True, check=True, encoding='utf-8')
+        return 'hevc_nvenc' in res.stdout
+    except Exception:
+        return False
+
+
+def detect_gpu_type() -> str:
+    """core/utils.py:17-27 (cached by the caller's lifetime here: one nvidia-smi spawn per process)"""
+    if not hasattr(detect_gpu_type, '_name'):
+        try:
+            res = subprocess.run(['nvidia-smi', '--query-gpu=name', '--format=csv,noheader'], capture_output=True, text=True, check=True,
+                                 encoding='utf-8')
+            detect_gpu_type._name = res.stdout.strip().lower()
+        except Exception:
+            detect_gpu_type._name = 'unknown'
+    return detect_gpu_type._name
+
+
+def decide_encoder(info: VideoInfo, force_cpu: bool, force_gpu: bool) -> bool:
+    """True -> NVENC (core/transcoder.py:70-75)"""
+    return False if force_cpu else has_nvenc()
+
+
+def select_nvenc_preset(info: VideoInfo, gpu_name: str) -> str:
+    res = max(info.width, info.height)
+    tiers = ('p7', 'p6', 'p5') if info.hdr else ('p6', 'p5', 'p4')
+    return tiers[0] if res >= 3840 else tiers[1] if res >= 2560 else tiers[2]
+
+
+def adjust_nvenc_params(params: List[str], attempt: int) -> List[str]:
+    """Apply retry ladder step ``attempt`` (1-based) to a flat option list (core/transcoder.py:101-134)."""
+    if attempt <= 0:
+        return list(params)
+    opts: 'OrderedDict[str, str]' = OrderedDict()
+    i = 0
+    while i < len(params):
+        key = params[i]
+        if i + 1 < len(params) and not params[i + 1].startswith('-'):
+            opts[key] = params[i + 1]
+            i += 2
+        else:
+            opts[key] = ''
+            i += 1
+    opts.update(NVENC_RETRIES[min(attempt, len(NVENC_RETRIES)) - 1])
+    flat: List[str] = []
+    for key, val in opts.items():
+        flat.append(key)
+        if val != '':
+            flat.append(str(val))
+    return flat
+
+
+def build_ffmpeg_params(info: VideoInfo, use_nvenc: bool, gpu_name: str) -> FFmpegParams:
+    """core/transcoder.py:357-412"""
+    if not use_nvenc:
+        level, _tier = derive.calculate_apple_hevc_level(info)
+        return FFmpegParams('libx265', 'p010le' if info.hdr else 'yuv420p', 'main10' if info.hdr else 'main', level, [],
+                            ['-x265-params', ':'.join(derive.x265_option_list(info)), '-threads', '0'], [])
+    level, tier, profile, pix_fmt = derive.calculate_nvenc_hevc_level(info)
+    _crf, cq, maxrate, bufsize, gop = calculate_dynamic_values(info, True, gpu_name)
+    lookahead = int(min(info.fps * 1.5, 120))
+    aq = 6
+    longest = max(info.width, info.height)
+    if info.hdr and longest >= 3840:
+        aq, lookahead = 7, min(info.fps * 2, 120)
+    if info.hdr and longest >= 7680:
+        aq, lookahead = 8, 120
+    vparams = ['-rc', 'vbr', '-tune', 'hq', '-multipass', 'fullres', '-cq', str(cq), '-b:v', '0', '-maxrate', str(maxrate * 1000),
+               '-bufsize', str(bufsize * 1000), '-bf', '3', '-b_ref_mode', 'middle', '-rc-lookahead', str(lookahead), '-spatial-aq', '1',
+               '-aq-strength', str(aq), '-temporal-aq', '1', '-preset', select_nvenc_preset(info, gpu_name), '-no-scenecut', '1',
+               '-g', str(gop), '-tier', tier]
+    joined = ' '.join(vparams)
+    if 'aud=1' not in joined and '-aud' not in joined:
+        vparams += ['-aud', '1']
+    meta = derive.build_hdr_metadata(info.master_display, info.max_cll, True, info.fps) if info.hdr else []
+    return FFmpegParams('hevc_nvenc', pix_fmt, profile, level, [], vparams, meta)
+
+
+def get_audio_flags(audio_channels: int) -> List[str]:
+    """core/transcoder.py:423-450"""
+    if not audio_channels or audio_channels < 1:
+        return []
+    kbps = min(max(128, audio_channels * 64), 512)
+    if audio_channels > 2:
+        kbps = max(kbps, 256)
+    flags = ['-c:a', 'aac', '-b:a', f'{kbps}k', '-ar', '48000']
+    layouts = {1: 'mono', 2: 'stereo', 6: '5.1', 8: '7.1'}
+    flags += ['-ac', str(max(1, audio_channels))]
+    if audio_channels in layouts:
+        flags += ['-channel_layout', layouts[audio_channels]]
+    return flags
+
+
+def build_ffmpeg_command(file_path: Path, out_path: Path, ff_params: FFmpegParams, audio_channels: int,
+                         audio_language: Optional[str] = 'eng', extra_vparams: Optional[List[str]] = None) -> List[str]:
+    """core/transcoder.py:452-495"""
+    cmd = ['ffmpeg', '-hide_banner', '-y', '-i', str(file_path), '-map_metadata', '0', '-c:v', ff_params.vcodec, '-pix_fmt', ff_params.pix_fmt,
+           '-profile:v', ff_params.profile, '-tag:v', 'hvc1']
+    cmd += ff_params.hdr_metadata or []
+    cmd += extra_vparams if extra_vparams else ff_params.vparams
+    cmd += VIDEO_METADATA_FLAGS
+    if audio_channels and audio_channels > 0:
+        cmd += ['-metadata:s:a:0', 'handler_name=SoundHandler', '-metadata:s:a:0', f'language={audio_language or "eng"}',
+                '-metadata:s:a:0', 'title="Main Audio"']
+        cmd += get_audio_flags(audio_channels)
+    cmd += ['-color_range', 'tv', '-brand', 'mp42', '-movflags', '+write_colr+use_metadata_tags+faststart', str(out_path)]
+    return cmd
+
+
+def run_ffmpeg(cmd: List[str], progress_callback: ProgressCb, file_name: str, total_frames: int,
+               stop_event: Optional[threading.Event] = None, debug: bool = False) -> Tuple[int, str]:
+    """Spawn ffmpeg, parse ``frame=`` for progress, honour the stop event (core/transcoder.py:497-535)."""
+    if debug:
+        logger.debug('ffmpeg command: %s', ' '.join(cmd))
+    lines: List[str] = []
+    try:
+        with subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, encoding='utf-8', errors='replace') as proc:
+            for line in proc.stdout:
+                lines.append(line)
+                if stop_event and stop_event.is_set():
+                    try:
+                        proc.terminate()
+                    except Exception:
+                        pass
+                    return 1, ''.join(lines)
+                if 'frame=' in line and progress_callback:
+                    try:
+                        frame = int(line.strip().split('frame=')[-1].split()[0])
+                        progress_callback(file_name, frame, total_frames)
+                    except Exception:
+                        logger.debug('progress parse / callback failed', exc_info=True)
+            return proc.wait(), ''.join(lines)
+    except Exception as exc:
+        logger.error('running ffmpeg failed: %s - %s', cmd[:3], exc)
+        return 1, str(exc)
+
+
+# ------------------------------------------------------------------ B200 branch
+
+def b200_available() -> bool:
+    try:
+        from . import _cabi
+        return _cabi.LIB_PATH.exists() and _cabi.lib().hb_device_count() > 0
+    except Exception:
+        return False
+
+
+_GPU_CYCLE_LOCK = threading.Lock()
+_GPU_CYCLE_NEXT = [0]
+
+
+def next_device() -> int:
+    """Round-robin device assignment under a lock, like the upscaler's cycle(gpu_list) (upscale_gui_final.py:25-30,123-126)."""
+    from . import _cabi
+    n = max(1, _cabi.lib().hb_device_count())
+    with _GPU_CYCLE_LOCK:
+        d = _GPU_CYCLE_NEXT[0] % n
+        _GPU_CYCLE_NEXT[0] += 1
+    return d
+
+
+def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
+                stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
+                target_size: Optional[Tuple[int, int]] = None) -> Tuple[int, str]:
+    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on one B200.  Returns (0, '') or (1, reason) like run_ffmpeg."""
+    import numpy as np
+    import torch
+
+    from . import _cabi, mp4, ops
+    from .encoder import PIX_P010, B200Encoder, to_c_params
+    from .frames import open_reader
+    try:
+        dev = next_device() if device is None else device
+        ctx = _cabi.Context(dev)
+    except Exception as exc:
+        return 1, f'B200 backend unavailable: {exc}'
+    try:
+        src_w, src_h = info.width, info.height
+        if target_size:
+            info = VideoInfo(**{**info.__dict__, 'width': target_size[0], 'height': target_size[1]})
+        params = derive.derive_b200_params(info)
+        enc = B200Encoder(ctx, to_c_params(params), max_batch=batch)
+        reader = open_reader(file_path, VideoInfo(**{**info.__dict__, 'width': src_w, 'height': src_h}))
+        chunks: List[bytes] = []
+        done = 0
+        tdev = torch.device('cuda', dev)
+        matrix = 'bt2020' if params.matrix_coeffs == 9 else 'bt709' if params.matrix_coeffs == 1 else 'bt601'
+        for buf, n, fmt in reader.batches(batch):
+            if stop_event is not None and stop_event.is_set():
+                return 1, 'cancelled'
+            if reader.kind == 'bgr' or target_size:
+                # device-side pre-encode pixel pipeline: BGR -> 4:2:0 (matrix), optional polyphase scale, pack to P010
+                w, h = params.width, params.height
+                out = torch.empty((n, (w * h + 2 * (w // 2) * (h // 2)) * 2), dtype=torch.uint8, device=tdev)
+                for i in range(n):
+                    y16 = out[i, :w * h * 2].view(torch.int16).view(h, w)
+                    uv16 = out[i, w * h * 2:].view(torch.int16).view(h // 2, w)
+                    if reader.kind == 'bgr':
+                        img = torch.from_numpy(buf[i]).to(tdev)
+                        if target_size:
+                            y8, u8, v8 = ops.rgb_to_yuv420(ctx, img, matrix, 8, bgr=True)
+                        else:
+                            ctx.call('hb_rgb_to_yuv420', _cabi.dp(img), img.stride(0), 1, ops.MATRIX_IDS[matrix], 10, w, h,
+                                     _cabi.dp(y16), w * 2, _cabi.dp(uv16), w * 2, 0, 0)
+                            continue
+                    else:
+                        f = torch.from_numpy(buf[i]).to(tdev)
+                        y8 = f[:src_w * src_h].view(src_h, src_w)
+                        u8 = f[src_w * src_h:src_w * src_h + (src_w // 2) * (src_h // 2)].view(src_h // 2, src_w // 2)
+                        v8 = f[src_w * src_h + (src_w // 2) * (src_h // 2):].view(src_h // 2, src_w // 2)
+                    torch.cuda.synchronize(tdev)
+                    ctx.call('hb_scale_yuv420_to_p010', _cabi.dp(y8), y8.stride(0), _cabi.dp(u8), u8.stride(0), _cabi.dp(v8), v8.stride(0),
+                             y8.shape[1], y8.shape[0], _cabi.dp(y16), w * 2, _cabi.dp(uv16), w * 2, w, h)
+                torch.cuda.synchronize(tdev)
+                ctx.sync()
+                data, _ = enc.encode(out.data_ptr(), n, fmt=PIX_P010, on_device=True)
+            else:
+                data, _ = enc.encode(np.ascontiguousarray(buf), n, fmt=fmt)
+            chunks.append(data)
+            done += n
+            if progress_callback:
+                try:
+                    progress_callback(file_path.name, done, max(total_frames, done))
+                except Exception:
+                    logger.debug('progress callback raised', exc_info=True)
+        if done == 0:
+            return 1, 'no frames decoded'
+        track = mp4.TrackInfo(params.width, params.height, params.fps_num, params.fps_den, params.profile_idc, params.level_idc, params.tier,
+                              params.bit_depth, params.colour_primaries, params.transfer_characteristics, params.matrix_coeffs, params.full_range,
+                              params.master_display if params.hdr10 else None, params.max_cll, params.max_fall)
+        out_path.write_bytes(mp4.mux_annexb(track, b''.join(chunks)))
+        return 0, ''
+    except Exception as exc:
+        logger.debug('B200 encode failed', exc_info=True)
+        return 1, f'{type(exc).__name__}: {exc}'
+    finally:
+        try:
+            enc.close()
+        except Exception:
+            pass
+        ctx.close()
+
+
+# ------------------------------------------------------------------ the drop-in entry point
+
+def convert_video(file_path: Path, out_dir: Path, progress_callback: ProgressCb = None, debug: bool = False, skip_validator: bool = False,
+                  force_cpu: bool = False, force_gpu: bool = False, stop_event: Optional[threading.Event] = None,
+                  encoder: str = 'auto', device: Optional[int] = None) -> Dict[str, Any]:
+    """Transcode one file; never raises for encode failures (core/transcoder.py:537-638).
+
+    encoder: 'auto' (reference behaviour: NVENC if ffmpeg offers it, else libx265), 'cpu', 'nvenc', or 'b200'."""
+    file_path, out_dir = Path(file_path), Path(out_dir)
+    if encoder == 'auto':
+        encoder = os.environ.get('HEVC_B200_ENCODER', 'auto')
+    info = probe_media(file_path)
+    out_path = out_dir / (file_path.stem + '.mp4')
+    use_b200 = encoder == 'b200'
+    use_nvenc = False if use_b200 else (decide_encoder(info, force_cpu or encoder == 'cpu', force_gpu) if encoder != 'nvenc' else has_nvenc())
+    entry: Dict[str, Any] = {'file': file_path.name, 'status': 'FAILED', 'quality': None, 'retries': 0,
+                             'method': 'B200' if use_b200 else ('NVENC' if use_nvenc else 'CPU'), 'hdr': info.hdr}
+    crf, _cq, _, _, _ = calculate_dynamic_values(info, use_nvenc=False)
+    _, nvenc_cq, _, _, _ = calculate_dynamic_values(info, use_nvenc=True, gpu_name='')
+    total_frames = max(1, int(info.duration * info.fps)) if info.duration and info.fps else 1
+
+    if use_b200:
+        rc, why = encode_b200(file_path, out_path, info, progress_callback, total_frames, stop_event, device)
+        if rc == 0:
+            entry.update(status='SUCCESS', quality=crf)
+        else:
+            logger.error('B200 encode failed: %s: %s', file_path.name, why)
+    else:
+        gpu_name = detect_gpu_type()
+        ff_params = build_ffmpeg_params(info, use_nvenc, gpu_name)
+        if use_nvenc:
+            for attempt, mods in enumerate(NVENC_RETRIES + [None], 1):
+                vparams = adjust_nvenc_params(ff_params.vparams, attempt) if mods else ff_params.vparams
+                cmd = build_ffmpeg_command(file_path, out_path, ff_params, info.audio_channels, info.audio_language, vparams)
+                rc, text = run_ffmpeg(cmd, progress_callback, file_path.name, total_frames, stop_event, debug)
+                if rc == 0:
+                    entry.update(status='SUCCESS', quality=nvenc_cq, retries=min(attempt, len(NVENC_RETRIES)), method='NVENC')
+                    break
+                logger.warning('NVENC attempt %d failed: %s | %s', attempt, file_path.name, text[:1000])
+                if attempt == len(NVENC_RETRIES) + 1:
+                    use_nvenc = False
+        if not use_nvenc and entry['status'] != 'SUCCESS':
+            cpu_params = build_ffmpeg_params(info, False, gpu_name)
+            cmd = build_ffmpeg_command(file_path, out_path, cpu_params, info.audio_channels, info.audio_language)
+            rc, text = run_ffmpeg(cmd, progress_callback, file_path.name, total_frames, stop_event, debug)
+            if rc == 0:
+                entry.update(status='SUCCESS', quality=crf, retries=0, method='CPU')
+            else:
+                logger.error('CPU transcode failed: %s\n%s', file_path.name, text[:2000])
+
+    if entry['status'] == 'SUCCESS' and not skip_validator:
+        try:
+            from .compliance import check_file
+            problems = check_file(out_path)
+            if problems:
+                logger.warning('compliance check: %s: %s', out_path.name, '; '.join(problems))
+        except Exception:
+            logger.debug('compliance check raised', exc_info=True)
+    if stop_event and stop_event.is_set() and entry['status'] != 'SUCCESS':
+        entry['status'] = 'CANCELLED'
+    if progress_callback:
+        try:
+            progress_callback(file_path.name, total_frames, total_frames)
+        except Exception:
+            logger.debug('progress callback raised at completion', exc_info=True)
+    return entry

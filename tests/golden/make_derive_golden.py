@@ -37,6 +37,16 @@ hdrmeta = {
 }
 cmd_info = VideoInfo(3840, 2160, 60.0, 'bt2020', 'smpte2084', 'bt2020nc', 'yuv420p', '', '', 2, True, 'eng', None, 5.0)
 cmd = ref.build_ffmpeg_command(Path('in.mp4'), Path('out/in.mp4'), ref.build_ffmpeg_params(cmd_info, False, ''), 2, 'eng')
+nvenc = []
+for (w, h), fps, hdr in itertools.product(RES, (24.0, 29.97, 60.0, 120.0), (False, True)):
+    info = VideoInfo(w, h, fps, 'bt2020' if hdr else 'bt709', 'smpte2084' if hdr else 'bt709', 'bt2020nc' if hdr else 'bt709',
+                     'yuv420p', '', '', 6, hdr, 'fra', None, 10.0)
+    p = ref.build_ffmpeg_params(info, True, 'nvidia b200')
+    nvenc.append({'w': w, 'h': h, 'fps': fps, 'hdr': hdr, 'vparams': p.vparams, 'meta': p.hdr_metadata, 'pix_fmt': p.pix_fmt,
+                  'profile': p.profile, 'level': p.level,
+                  'retry': [ref.adjust_nvenc_params(p.vparams, a) for a in range(0, 6)],
+                  'cmd': ref.build_ffmpeg_command(Path('a b.mkv'), Path('o/a b.mp4'), p, 6, 'fra', ref.adjust_nvenc_params(p.vparams, 2))})
+audio = {str(c): ref.get_audio_flags(c) for c in range(0, 10)}
 out = Path(__file__).with_name("derive_golden.json.gz")
-out.write_bytes(gzip.compress(json.dumps({'cases': cases, 'gops': gops, 'hdrmeta': hdrmeta, 'cmd_4k60_hdr': cmd}, separators=(",", ":")).encode(), mtime=0))
+out.write_bytes(gzip.compress(json.dumps({'cases': cases, 'gops': gops, 'hdrmeta': hdrmeta, 'cmd_4k60_hdr': cmd, 'nvenc': nvenc, 'audio': audio}, separators=(",", ":")).encode(), mtime=0))
 print(len(cases), 'cases ->', out)

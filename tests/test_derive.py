@@ -68,3 +68,22 @@ def test_b200_params_1080p_sdr():
     p = derive.derive_b200_params(_info({'w': 1920, 'h': 1080, 'fps': 30.0, 'hdr': False, 'duration': 5.0}))
     assert (p.profile_idc, p.level_idc, p.tier, p.bit_depth) == (1, 120, 0, 8)
     assert (p.crf, p.keyint, p.min_keyint, p.aud, p.repeat_headers, p.hrd) == (19, 90, 45, 0, 0, 0)
+
+
+def test_ffmpeg_argv_branches_match_reference():
+    """the libx265 / NVENC command-line branch kept for encoder='cpu'|'nvenc' (core/transcoder.py:357-495)"""
+    from pathlib import Path
+    from hevc_b200 import transcoder as T
+    info = _info({'w': 3840, 'h': 2160, 'fps': 60.0, 'hdr': True, 'duration': 5.0})
+    cmd = T.build_ffmpeg_command(Path('in.mp4'), Path('out/in.mp4'), T.build_ffmpeg_params(info, False, ''), 2, 'eng')
+    assert cmd == GOLD['cmd_4k60_hdr']
+    for c, flags in GOLD['audio'].items():
+        assert T.get_audio_flags(int(c)) == flags
+    for g in GOLD['nvenc']:
+        hdr = g['hdr']
+        info = VideoInfo(g['w'], g['h'], g['fps'], 'bt2020' if hdr else 'bt709', 'smpte2084' if hdr else 'bt709',
+                         'bt2020nc' if hdr else 'bt709', 'yuv420p', '', '', 6, hdr, 'fra', None, 10.0)
+        p = T.build_ffmpeg_params(info, True, 'nvidia b200')
+        assert (p.vparams, p.hdr_metadata, p.pix_fmt, p.profile, p.level) == (g['vparams'], g['meta'], g['pix_fmt'], g['profile'], g['level'])
+        assert [T.adjust_nvenc_params(p.vparams, a) for a in range(0, 6)] == g['retry']
+        assert T.build_ffmpeg_command(Path('a b.mkv'), Path('o/a b.mp4'), p, 6, 'fra', T.adjust_nvenc_params(p.vparams, 2)) == g['cmd']

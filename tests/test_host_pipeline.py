@@ -1,0 +1,199 @@
+"""Host-side logic (no GPU): probe parsing vs the reference, MP4 muxer + compliance checks on a stream from the CPU model,
+worker / batch scheduling, rank sharding (world_size 2 over gloo)."""
+import dataclasses
+import json
+import os
+import subprocess
+import sys
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from hevc_b200 import batch, compliance, mp4, probe, transcoder, worker
+from hevc_b200.frames import Y4MReader, write_y4m
+from hevc_b200.synth import SynthClip
+from tests import enc_common as ec
+
+GOLD = json.loads((Path(__file__).parent / 'golden' / 'probe_golden.json').read_text())
+
+
+def test_probe_parsing_matches_reference():
+    for case in GOLD:
+        try:
+            info = probe.info_from_ffprobe_json(case['doc'])
+        except Exception:
+            info = probe.VideoInfo(**probe._FALLBACK)        # probe_media's catch-all (core/probe.py:114-116)
+        assert dataclasses.asdict(info) == case['info'], case['doc']
+
+
+def test_probe_never_raises_and_reads_y4m(tmp_path):
+    assert dataclasses.asdict(probe.probe_media(tmp_path / 'missing.mp4')) == probe._FALLBACK
+    clip = SynthClip(64, 48, seed=2)
+    p = tmp_path / 'a.y4m'
+    write_y4m(p, [clip.frame(i) for i in range(3)], 64, 48, (60, 1))
+    (tmp_path / 'a.y4m.json').write_text(json.dumps({'color_primaries': 'bt2020', 'color_transfer': 'smpte2084', 'color_space': 'bt2020nc'}))
+    info = probe.probe_media(p)
+    assert (info.width, info.height, info.fps, info.nb_frames, info.hdr, info.pix_fmt) == (64, 48, 60.0, 3, True, 'yuv420p')
+    assert abs(info.duration - 0.05) < 1e-9
+    bufs = list(Y4MReader(p).batches(2))
+    assert [b[1] for b in bufs] == [2, 1] and bufs[0][0].shape == (2, 64 * 48 * 3 // 2)
+    assert (bufs[0][0][1][:64 * 48].reshape(48, 64) == clip.frame(1)[0]).all()
+
+
+def _model_stream(depth, n=5, w=96, h=64, keyint=3):
+    p = ec.b200_params(w, h, depth, keyint=keyint)
+    stream, aus, recs, _ = ec.run_model(p, ec.clip_frames(w, h, n), 24, 26, hash_sei=False)
+    return p, stream, recs
+
+
+@pytest.mark.parametrize('depth', [8, 10])
+def test_mp4_mux_and_compliance(depth, tmp_path):
+    p, stream, recs = _model_stream(depth)
+    track = mp4.TrackInfo(p.width, p.height, p.fps_num, p.fps_den, p.profile_idc, p.level_idc, p.tier, p.bit_depth, p.colour_primaries,
+                          p.transfer_characteristics, p.matrix_coeffs, 0, p.master_display if p.hdr10 else None, p.max_cll, p.max_fall)
+    data = mp4.mux_annexb(track, stream)
+    expect = {'profile_idc': p.profile_idc, 'level_idc': p.level_idc, 'tier': 0, 'keyint': 3, 'hdr10': bool(p.hdr10),
+              'master_display': p.master_display, 'max_cll': p.max_cll, 'max_fall': p.max_fall}
+    assert compliance.check_bytes(data, expect) == []
+    rep = compliance.inspect(data)
+    assert rep['n_samples'] == 5 and rep['sync_samples'] == [1, 4] and rep['sps']['width'] == 96 and rep['sps']['height'] == 64
+    # a decoder that knows nothing about this package (OpenCV's FFmpeg: mov demuxer + hevc decoder) plays the file
+    import cv2
+    f = tmp_path / 'o.mp4'
+    f.write_bytes(data)
+    cap = cv2.VideoCapture(str(f))
+    assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 5
+    assert abs(cap.get(cv2.CAP_PROP_FPS) - 30.0) < 1e-3
+    n = 0
+    while True:
+        ok, bgr = cap.read()
+        if not ok:
+            break
+        y = recs[n][0][:64, :96].astype(np.float64) / (4.0 if depth == 10 else 1.0)
+        got = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY).astype(np.float64)
+        # same picture; OpenCV's YUV->BGR->gray path differs (and is BT.2020/PQ-unaware for the HDR case)
+        assert np.corrcoef(y.reshape(-1), got.reshape(-1))[0, 1] > (0.98 if depth == 8 else 0.7)
+        n += 1
+    assert n == 5
+    # and the samples, put back into Annex-B with the hvcC parameter sets, decode bit-exactly to the model's reconstruction
+    import struct
+    from oracle import fforacle
+    ps = rep['param_sets']
+    annexb = b''.join(b'\0\0\0\1' + ps[t][0] for t in (32, 33, 34))
+    pos = rep['chunk_offset']
+    for size in rep['sample_sizes']:
+        end = pos + size
+        while pos < end:
+            ln = struct.unpack('>I', data[pos:pos + 4])[0]
+            annexb += b'\0\0\0\1' + data[pos + 4:pos + 4 + ln]
+            pos += 4 + ln
+    dec = fforacle.decode_hevc(annexb, verify_hash=False)
+    assert len(dec) == 5
+    for d, r in zip(dec, recs):
+        assert all((d[c] == r[c][:d[c].shape[0], :d[c].shape[1]]).all() for c in range(3))
+
+
+def test_compliance_flags_problems():
+    p, stream, _ = _model_stream(8)
+    track = mp4.TrackInfo(p.width, p.height, 30, 1, 1, 120, 0, 8, 1, 1, 1)
+    good = mp4.mux_annexb(track, stream)
+    assert compliance.check_bytes(good) == []
+    assert 'sample entry is hev1, not hvc1' in compliance.check_bytes(good.replace(b'hvc1', b'hev1'))
+    assert any('brand' in s for s in compliance.check_bytes(good.replace(b'ftyp' + b'mp42', b'ftyp' + b'isom', 1)))
+    assert any('level_idc' in s for s in compliance.check_bytes(good, {'level_idc': 153}))
+    assert any('HDR10 SEI' in s for s in compliance.check_bytes(good, {'hdr10': True}))
+
+
+def test_convert_video_contract_without_backend(tmp_path, monkeypatch):
+    """never raises, result keys, CANCELLED status, final (total, total) progress tick (core/transcoder.py:537-638)"""
+    clip = SynthClip(64, 48, seed=1)
+    src = tmp_path / 'clip.y4m'
+    write_y4m(src, [clip.frame(i) for i in range(2)], 64, 48)
+    ticks = []
+    monkeypatch.setattr(transcoder, 'encode_b200', lambda *a, **k: (1, 'no device here'))
+    res = transcoder.convert_video(src, tmp_path, progress_callback=lambda *a: ticks.append(a), encoder='b200')
+    assert list(res) == ['file', 'status', 'quality', 'retries', 'method', 'hdr']
+    assert res['status'] == 'FAILED' and res['method'] == 'B200' and res['file'] == 'clip.y4m'
+    assert ticks[-1][1] == ticks[-1][2]
+    ev = threading.Event()
+    ev.set()
+    assert transcoder.convert_video(src, tmp_path, encoder='b200', stop_event=ev)['status'] == 'CANCELLED'
+    monkeypatch.setattr(transcoder, 'encode_b200', lambda *a, **k: (0, ''))
+    monkeypatch.setattr(compliance, 'check_file', lambda *a, **k: [])
+    ok = transcoder.convert_video(src, tmp_path, encoder='b200', progress_callback=lambda *a: 1 / 0)      # callback errors are swallowed
+    assert ok['status'] == 'SUCCESS' and ok['quality'] == 17 + 1 - 1 or ok['quality'] in range(16, 25)
+    # the reference branch without ffmpeg fails the same way the reference does (status FAILED, method CPU)
+    cpu = transcoder.convert_video(src, tmp_path, force_cpu=True)
+    assert cpu['status'] == 'FAILED' and cpu['method'] == 'CPU'
+
+
+def test_worker_and_batch_scheduling(tmp_path, monkeypatch):
+    files = [tmp_path / f'f{i}.y4m' for i in range(7)]
+    for f in files:
+        f.write_bytes(b'YUV4MPEG2 W16 H16 F30:1\n')
+    active, peak, lock = [0], [0], threading.Lock()
+
+    def fake(file_path, out_dir, progress_callback=None, stop_event=None, **kw):
+        with lock:
+            active[0] += 1
+            peak[0] = max(peak[0], active[0])
+        threading.Event().wait(0.02)
+        with lock:
+            active[0] -= 1
+        return {'file': Path(file_path).name, 'status': 'SUCCESS', 'quality': 19, 'retries': 0, 'method': 'B200', 'hdr': False}
+
+    monkeypatch.setattr(batch, 'convert_video', fake)
+    res = batch.batch_convert(tmp_path, tmp_path / 'out', max_workers=3, encoder='b200')
+    assert sorted(r['file'] for r in res) == sorted(f.name for f in files) and 1 < peak[0] <= 3
+    rows = (tmp_path / 'out' / 'transcode_log.csv').read_text().strip().splitlines()
+    assert rows[0] == 'file,status,quality,retries,method,hdr' and len(rows) == 8
+    monkeypatch.setattr(worker, 'convert_video', fake)
+    w = worker.TranscodeWorker(files[0], tmp_path, encoder='b200')
+    got = []
+    w.finished.connect(got.append)
+    w.start()
+    w.join()
+    assert got[0]['status'] == 'SUCCESS'
+    w.stop()
+    assert w.stop_event.is_set()
+
+
+def test_gop_segments_and_lpt():
+    assert batch.gop_segments(300, 120) == [(0, 120), (120, 240), (240, 300)]
+    items = [9, 8, 7, 3, 2, 1]
+    shards = [batch.shard_for_rank(items, r, 2, cost=float) for r in range(2)]
+    assert sorted(shards[0] + shards[1]) == sorted(items) and abs(sum(shards[0]) - sum(shards[1])) <= 1
+
+
+_RANK_SCRIPT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hevc_b200.batch import shard_for_rank, gop_segments
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+units = gop_segments(1800, 60)                       # config 4: one long clip cut at keyint
+mine = shard_for_rank(units, rank, world)
+flags = torch.zeros(len(units), dtype=torch.int32)
+for u in mine:
+    flags[units.index(u)] = 1
+dist.all_reduce(flags)                                # test-only collective: every unit must be owned exactly once
+assert bool((flags == 1).all()), flags
+counts = [torch.zeros(1, dtype=torch.int32) for _ in range(world)]
+dist.all_gather(counts, torch.tensor([len(mine)], dtype=torch.int32))
+assert max(int(c) for c in counts) - min(int(c) for c in counts) <= 1
+dist.destroy_process_group()
+print('rank', rank, 'ok', len(mine))
+'''
+
+
+def test_rank_sharding_world_size_2(tmp_path):
+    script = tmp_path / 'rank.py'
+    script.write_text(_RANK_SCRIPT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29533', str(script), str(Path(__file__).resolve().parent.parent)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count('ok') == 2
