@@ -78,4 +78,98 @@ HB_HD bool cu_avail(const Geom &g, int cx, int cy, int nx, int ny)
     return cu_order(g.ctuw, nx, ny) < cu_order(g.ctuw, cx, cy);
 }
 
+// ---------------------------------------------------------------------------------------------- rate control
+// Deterministic integer controller shared (as a specification) with oracle/hevc_rc.c: the QP of a frame is chosen on the
+// device from the size *estimates* of earlier frames, so the frame chain never waits for the entropy coder or the host.
+struct FrameCtl {
+    int qp, lambda, is_idr, redo;
+    QuantParam qy, qc;
+    unsigned long long est16;      // size estimate accumulated by the frame kernel, 1/16 bit
+};
+
+struct RcState {
+    long long t16, b16, fullness;
+    int have[2], qp_prev[2];
+    long long est_prev[2];
+    int qp_i, qp_p, rate_control, bit_depth;
+};
+
+HB_HD long long rc_pow2_sixth(int k)      // round(65536 * 2^(k/6))
+{
+    constexpr unsigned t[37] = {65536, 73562, 82570, 92682, 104032, 116772, 131072, 147123, 165140, 185364, 208064, 233544, 262144,
+                                294247, 330281, 370728, 416128, 467088, 524288, 588493, 660561, 741455, 832255, 934175, 1048576,
+                                1176987, 1321123, 1482910, 1664511, 1868350, 2097152, 2353974, 2642246, 2965821, 3329021, 3736700, 4194304};
+    return t[k];
+}
+
+HB_HD int rc_step(long long est, long long budget)
+{
+    if (budget < 1) budget = 1;
+    if (est > budget) {
+        for (int k = 1; k <= 36; k++)
+            if (est * 65536 <= budget * rc_pow2_sixth(k)) return k;
+        return 36;
+    }
+    int j = 0;
+    while (j < 12 && est * rc_pow2_sixth(j + 1) <= budget * 65536) j++;
+    return -j;
+}
+
+HB_HD long long rc_budget(const RcState &rc, int is_idr)
+{
+    long long fill = rc.fullness + rc.t16;
+    if (fill > rc.b16) fill = rc.b16;
+    long long budget;
+    if (is_idr) {
+        budget = fill / 2;
+        if (budget > 8 * rc.t16) budget = 8 * rc.t16;
+    } else {
+        budget = rc.t16 * fill / (rc.b16 / 2);
+        if (budget < rc.t16 / 2) budget = rc.t16 / 2;
+        if (budget > 2 * rc.t16) budget = 2 * rc.t16;
+    }
+    return budget;
+}
+
+HB_HD int rc_pick_qp(const RcState &rc, int is_idr)
+{
+    const int base = is_idr ? rc.qp_i : rc.qp_p;
+    if (!rc.rate_control) return base;
+    const long long budget = rc_budget(rc, is_idr);
+    const int t = is_idr ? 1 : 0;
+    int qp = base;
+    if (rc.have[t]) {
+        int step = rc_step(rc.est_prev[t], budget);
+        if (step < 0) step = rc.est_prev[t] * 5 <= budget * 4 ? -1 : 0;
+        qp = rc.qp_prev[t] + step;
+    } else if (!is_idr && rc.have[1]) {
+        int step = rc_step(rc.est_prev[1] / 4, budget);
+        if (step < 0) step = 0;
+        qp = rc.qp_prev[1] + (rc.qp_p - rc.qp_i) + step;
+    }
+    return qp < base ? base : qp > 51 ? 51 : qp;
+}
+
+HB_HD void rc_update(RcState &rc, int is_idr, int qp, long long est16)
+{
+    const int t = is_idr ? 1 : 0;
+    rc.fullness += rc.t16;
+    if (rc.fullness > rc.b16) rc.fullness = rc.b16;
+    rc.fullness -= est16;
+    if (rc.fullness < 0) rc.fullness = 0;
+    rc.have[t] = 1;
+    rc.qp_prev[t] = qp;
+    rc.est_prev[t] = est16;
+}
+
+HB_HD void ctl_set_qp(FrameCtl &c, int qp, int is_idr, int bit_depth)
+{
+    c.qp = qp;
+    c.is_idr = is_idr;
+    c.lambda = lambda_q8(qp) << (bit_depth - 8);
+    c.qy = make_quant(4, qp + 6 * (bit_depth - 8), bit_depth, is_idr);
+    c.qc = make_quant(3, chroma_qp(qp) + 6 * (bit_depth - 8), bit_depth, is_idr);
+    c.est16 = 0;
+}
+
 }  // namespace hb

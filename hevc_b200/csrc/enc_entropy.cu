@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
     for (int row = warp; row < g.ctuh; row += kEntropyWarps) {
         // ---- context initialisation: fresh for row 0 (or 1-CTU-wide pictures), else the snapshot of the row above
         if (row == 0 || g.ctuw < 2) {
-            const int q = min(max(fr.qp, 0), 51);
+            const int q = min(max(fr.ctl->qp, 0), 51);
             for (int i = lane; i < kNumCtx; i += 32) {
                 const int v = c_ctx_init[init_type][i];
                 const int m = (v >> 4) * 5 - 45, n = ((v & 15) << 3) - 16;

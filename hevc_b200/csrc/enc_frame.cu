@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
         return;
     WarpScratch &s = scratch[warp];
     const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth, maxv = (1 << bd) - 1;
-    const int lambda = p.lambda;
+    const FrameCtl ctl = *p.ctl;
+    const int lambda = ctl.lambda;
     const int row = lane >> 1, c0 = (lane & 1) * 8;
 
     // source block: registers (for SAD) + shared memory (for SATD)
@@ -314,13 +315,28 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
     __syncwarp();
     if (lane < 16) fwd_line<16, false>(&s.b[lane][0], 1, &s.a[0][lane], 18, 10);
     __syncwarp();
-    const QuantParam qy = p.qy;
+    const QuantParam qy = ctl.qy;
     int lv[8];
     bool nz = false;
+    int e_nnz = 0, e_slog = 0;         // size estimate (rate control): non-zero count, sum floor(log2 |level|)
+    unsigned nz_lo = 0, nz_hi = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         lv[i] = quant_one(s.a[row][c0 + i], qy);
+        if (lv[i]) {
+            e_nnz++;
+            e_slog += 31 - __clz(abs(lv[i]));
+            if (i < 4) nz_lo = 1; else nz_hi = 1;
+        }
         nz |= lv[i] != 0;
+    }
+    int e_nsb;
+    {   // coded 4x4 sub-blocks of the 16x16 block: a sub-block is 4 rows (lanes l, l+2, l+4, l+6) x one half-row group
+        const unsigned mlo = __ballot_sync(0xffffffffu, nz_lo), mhi = __ballot_sync(0xffffffffu, nz_hi);
+        const int sy = (lane >> 2) & 3, sxx = lane & 3, h = sxx >> 1;
+        const unsigned m = (sxx & 1) ? mhi : mlo;
+        const bool f = lane < 16 && ((m >> (8 * sy + h)) & 0x55u) != 0;
+        e_nsb = __popc(__ballot_sync(0xffffffffu, f));
     }
     {
         uint4 o;
@@ -402,18 +418,30 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
     __syncwarp();
     if (lane < 16) fwd_line<8, false>(&cb[lane >> 3][lane & 7][0], 1, &ca[lane >> 3][0][lane & 7], 10, 9);
     __syncwarp();
-    const QuantParam qc = p.qc;
+    const QuantParam qc = ctl.qc;
     int clv[4];
     bool cnz = false;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         clv[c] = quant_one(ca[cpl][crow][cc0 + c], qc);
+        if (clv[c]) {
+            e_nnz++;
+            e_slog += 31 - __clz(abs(clv[c]));
+        }
         cnz |= clv[c] != 0;
     }
     *reinterpret_cast<uint2 *>(coef + 256 + cpl * 64 + crow * 8 + cc0) =
         make_uint2((uint32_t)(uint16_t)clv[0] | ((uint32_t)(uint16_t)clv[1] << 16), (uint32_t)(uint16_t)clv[2] | ((uint32_t)(uint16_t)clv[3] << 16));
     const unsigned cmask = __ballot_sync(0xffffffffu, cnz);
     const int cbf = (cbf_y ? 1 : 0) | ((cmask & 0xffffu) ? 2 : 0) | ((cmask >> 16) ? 4 : 0);
+    {   // chroma sub-blocks: plane (lane >> 4), 4-row group ((lane >> 3) & 1), column half (lane & 1)
+        const int pl = (lane >> 2) & 1, sy = (lane >> 1) & 1, h = lane & 1;
+        const bool f = lane < 8 && ((cmask >> (16 * pl + 8 * sy + h)) & 0x55u) != 0;
+        e_nsb += __popc(__ballot_sync(0xffffffffu, f));
+        const int nnz = warp_sum(e_nnz), slog = warp_sum(e_slog);
+        if (lane == 0)
+            atomicAdd(&p.ctl->est16, cbf ? (unsigned long long)(47 * nnz + 22 * slog + 104 * e_nsb + 160) : 80ull);
+    }
     if (cmask) {
 #pragma unroll
         for (int c = 0; c < 4; c++)
@@ -447,6 +475,7 @@ struct IntraScratch {
     int16_t a[16][18], b[16][18];
     int cost[35];
     int dc, best_mode;
+    int e_nnz, e_slog, sbflag[24];
 };
 
 // neighbour sample `i` of the (4N + 1)-sample reference array of an NxN block of CU (cx, cy), with the
@@ -487,7 +516,7 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     const Geom &g = p.g;
     const int tid = threadIdx.x, bd = g.bit_depth, maxv = (1 << bd) - 1;
     const int x0 = cx * 16, y0 = cy * 16;
-    const int lambda = p.lambda;
+    const int lambda = p.ctl->lambda;
     // neighbours (luma + both chroma planes) and the source block
     if (tid < 65) s.nb[tid] = gather_one(p.rec.y, g.rec_stride, g, cx, cy, 16, tid, bd);
     else if (tid >= 96 && tid < 96 + 66) {
@@ -549,10 +578,17 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     __syncthreads();
     if (tid < 16) fwd_line<16, false>(&s.b[tid][0], 1, &s.a[0][tid], 18, 10);
     __syncthreads();
-    const QuantParam qy = p.qy;
+    const QuantParam qy = p.ctl->qy;
     const int lv = quant_one(s.a[py][px], qy);
     coef[tid] = (int16_t)lv;
+    if (tid < 24) s.sbflag[tid] = 0;
+    if (tid == 0) { s.e_nnz = 0; s.e_slog = 0; }
     const int cbf_y = __syncthreads_or(lv != 0);
+    if (lv) {
+        atomicAdd(&s.e_nnz, 1);
+        atomicAdd(&s.e_slog, 31 - __clz(abs(lv)));
+        s.sbflag[(py >> 2) * 4 + (px >> 2)] = 1;
+    }
     int recv = pv;
     if (cbf_y) {
         s.a[py][px] = (int16_t)dequant_one(lv, qy);
@@ -583,11 +619,16 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     __syncthreads();
     if (tid < 16) fwd_line<8, false>(&cb[tid >> 3][tid & 7][0], 1, &ca[tid >> 3][0][tid & 7], 10, 9);
     __syncthreads();
-    const QuantParam qc = p.qc;
+    const QuantParam qc = p.ctl->qc;
     int clv = 0;
     if (tid < 128) {
         clv = quant_one(ca[cpl][cyy][cxx], qc);
         coef[256 + tid] = (int16_t)clv;
+        if (clv) {
+            atomicAdd(&s.e_nnz, 1);
+            atomicAdd(&s.e_slog, 31 - __clz(abs(clv)));
+            s.sbflag[16 + cpl * 4 + (cyy >> 2) * 2 + (cxx >> 2)] = 1;
+        }
     }
     const int cbf_u = __syncthreads_or(tid < 64 && clv != 0);
     const int cbf_v = __syncthreads_or(tid >= 64 && tid < 128 && clv != 0);
@@ -604,6 +645,9 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
         ci.pred_mode = 0; ci.intra_mode = (uint8_t)mode; ci.cbf = (uint8_t)(cbf_y ? 1 : 0) | (cbf_u ? 2 : 0) | (cbf_v ? 4 : 0);
         ci.skip = 0; ci.mvx = 0; ci.mvy = 0;
         p.cus[cy * g.cuw + cx] = ci;
+        int nsb = 0;
+        for (int i = 0; i < 24; i++) nsb += s.sbflag[i];
+        atomicAdd(&p.ctl->est16, ci.cbf ? (unsigned long long)(47 * s.e_nnz + 22 * s.e_slog + 104 * nsb + 160) : 80ull);
     }
     __syncthreads();
 }
@@ -614,6 +658,8 @@ __global__ void __launch_bounds__(256) k_intra(IntraParams p)
     __shared__ IntraScratch s;
     const Geom &g = p.g;
     const int r = blockIdx.x;
+    if (p.second_pass && !p.ctl->redo)
+        return;
     for (int x = 0; x < g.ctuw; x++) {
         if (r > 0) {
             if (threadIdx.x == 0) {
@@ -634,6 +680,41 @@ __global__ void __launch_bounds__(256) k_intra(IntraParams p)
         if (threadIdx.x == 0)
             atomicExch(p.progress + r, x + 1);
     }
+}
+
+// ================================================================================================ rate control steps
+// single-thread kernels: close the books of the frame that just finished and choose the QP of the next one
+__global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    RcState s = *rc;
+    if (done) rc_update(s, done->is_idr, done->qp, (long long)done->est16);
+    if (next) {
+        FrameCtl c;
+        ctl_set_qp(c, rc_pick_qp(s, next_is_idr), next_is_idr, s.bit_depth);
+        c.redo = 0;
+        *next = c;
+    }
+    *rc = s;
+}
+
+// first key frame of a stream under rate control: if the first try overshoots its budget, ask for a second pass
+__global__ void k_rc_redo(RcState *rc, FrameCtl *ctl)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const RcState s = *rc;
+    FrameCtl c = *ctl;
+    c.redo = 0;
+    if (s.rate_control && !s.have[1]) {
+        const long long budget = rc_budget(s, 1), est = (long long)c.est16;
+        int qp2 = c.qp + rc_step(est, budget);
+        qp2 = qp2 < c.qp ? c.qp : qp2 > 51 ? 51 : qp2;
+        if (est > budget && qp2 != c.qp) {
+            ctl_set_qp(c, qp2, 1, s.bit_depth);
+            c.redo = 1;
+        }
+    }
+    *ctl = c;
 }
 
 }  // namespace hb

@@ -227,6 +227,9 @@ struct hb_encoder {
     uint8_t *staging = nullptr;       // raw input frames
     size_t staging_bytes = 0;
     int *progress = nullptr, *overflow = nullptr;
+    RcState *rc_dev = nullptr;
+    FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
+    bool rc_have_idr = false;
     EntropyFrame *eframes_dev = nullptr;
     uint32_t *offsets_dev = nullptr;
     uint8_t *packed_dev = nullptr;
@@ -293,6 +296,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     const hb_enc_params &p = *params;
     HB_ARG(ctx, p.width >= 16 && p.height >= 16 && (p.width % 2) == 0 && (p.height % 2) == 0 && p.width <= 8192 && p.height <= 8192);
     HB_ARG(ctx, p.bit_depth == 8 || p.bit_depth == 10);
+    HB_ARG(ctx, !p.rate_control || (p.vbv_maxrate_kbps > 0 && p.vbv_bufsize_kbit > 0));
     HB_ARG(ctx, p.qp_i >= 0 && p.qp_i <= 51 && p.qp_p >= 0 && p.qp_p <= 51 && p.keyint >= 1 && p.fps_num > 0 && p.fps_den > 0);
     HB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::unique_ptr<hb_encoder> e(new hb_encoder());
@@ -338,6 +342,18 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     HB_TRY(dev_alloc(E, &E->staging, E->staging_bytes));
     HB_TRY(dev_alloc(E, &E->progress, (size_t)g.ctuh));
     HB_TRY(dev_alloc(E, &E->overflow, 1));
+    HB_TRY(dev_alloc(E, &E->rc_dev, 1));
+    HB_TRY(dev_alloc(E, &E->ctl_dev, (size_t)max_batch));
+    HB_CUDA(ctx, cudaMallocHost(&E->ctl_host, sizeof(FrameCtl) * max_batch));
+    {
+        RcState rc{};
+        rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
+        rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
+        rc.fullness = rc.b16 * 9 / 10;
+        rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
+        HB_CUDA(ctx, cudaMemcpyAsync(E->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     HB_TRY(dev_alloc(E, &E->eframes_dev, (size_t)max_batch));
     HB_TRY(dev_alloc(E, &E->offsets_dev, (size_t)max_batch * g.ctuh + 1));
     E->packed_cap = (size_t)max_batch * g.ctuh * E->row_cap / 4 + (1 << 20);
@@ -366,6 +382,7 @@ void hb_enc_destroy(hb_encoder *e)
     if (e->offsets_host) cudaFreeHost(e->offsets_host);
     if (e->packed_host) cudaFreeHost(e->packed_host);
     if (e->overflow_host) cudaFreeHost(e->overflow_host);
+    if (e->ctl_host) cudaFreeHost(e->ctl_host);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->kev) if (ev) cudaEventDestroy(ev);
     delete e;
@@ -492,29 +509,35 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             const bool idr = (force_idr && base == 0 && i == 0) || e->frame_no == 0 || e->poc + 1 >= p.keyint;
             e->poc = idr ? 0 : e->poc + 1;
             is_idr[i] = idr; pocs[i] = e->poc;
-            const int qp = idr ? p.qp_i : p.qp_p;
-            qps[i] = qp;
             FrameSlot &s = e->slot[i];
             const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
+            // rate control on the device: account for the previous frame, choose this frame's QP
+            k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? e->ctl_dev + i - 1 : nullptr, e->ctl_dev + i, idr ? 1 : 0);
+            HB_LAUNCHED(ctx);
             if (idr) HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
             if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i], st));
             if (idr) {
                 IntraParams ip;
-                ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress; ip.qp = qp;
-                ip.lambda = lambda_q8(qp) << (p.bit_depth - 8);
-                ip.qy = make_quant(4, qp + 6 * (p.bit_depth - 8), p.bit_depth, 1);
-                ip.qc = make_quant(3, chroma_qp(qp) + 6 * (p.bit_depth - 8), p.bit_depth, 1);
+                ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
+                ip.ctl = e->ctl_dev + i; ip.second_pass = 0;
                 k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+                HB_LAUNCHED(ctx);
+                if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
+                    k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + i);
+                    HB_LAUNCHED(ctx);
+                    HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+                    ip.second_pass = 1;
+                    k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                }
+                e->rc_have_idr = true;
             } else {
                 InterParams ip;
                 ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
-                ip.cus = s.cus; ip.coefs = s.coefs; ip.qp = qp;
-                ip.lambda = lambda_q8(qp) << (p.bit_depth - 8);
-                ip.qy = make_quant(4, qp + 6 * (p.bit_depth - 8), p.bit_depth, 0);
-                ip.qc = make_quant(3, chroma_qp(qp) + 6 * (p.bit_depth - 8), p.bit_depth, 0);
+                ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
                 k_inter<<<nctu, 128, 0, st>>>(ip);
+                HB_LAUNCHED(ctx);
             }
-            HB_LAUNCHED(ctx);
             if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
             {
                 const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
@@ -537,6 +560,8 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             e->cur = 1 - e->cur;
             e->frame_no++;
         }
+        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
+        HB_LAUNCHED(ctx);
         // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
         HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
         // ---- entropy coding of the whole batch, compaction, download
@@ -545,7 +570,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         for (int i = 0; i < n; i++) {
             FrameSlot &s = e->slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
-            ef[i].is_intra = is_idr[i]; ef[i].qp = qps[i];
+            ef[i].is_intra = is_idr[i]; ef[i].ctl = e->ctl_dev + i;
         }
         HB_CUDA(ctx, cudaMemcpyAsync(e->eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
         HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
@@ -566,8 +591,10 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 4], st));
         HB_CUDA(ctx, cudaMemcpyAsync(e->offsets_host, e->offsets_dev, sizeof(uint32_t) * ((size_t)n * g.ctuh + 1), cudaMemcpyDeviceToHost, st));
         HB_CUDA(ctx, cudaMemcpyAsync(e->overflow_host, e->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+        HB_CUDA(ctx, cudaMemcpyAsync(e->ctl_host, e->ctl_dev, sizeof(FrameCtl) * n, cudaMemcpyDeviceToHost, st));
         HB_CUDA(ctx, cudaStreamSynchronize(st));
         if (*e->overflow_host) return hb_fail(ctx, HB_ERR_SPACE, "%s", "CABAC sub-stream exceeded its row buffer");
+        for (int i = 0; i < n; i++) qps[i] = e->ctl_host[i].qp;
         const uint32_t total = e->offsets_host[(size_t)n * g.ctuh];
         if (total > e->packed_cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "packed bitstream exceeds the download buffer");
         HB_CUDA(ctx, cudaMemcpyAsync(e->packed_host, e->packed_dev, total, cudaMemcpyDeviceToHost, st));

@@ -30,9 +30,7 @@ struct InterParams {
     const int16_t *cmv;                  // this frame's coarse vectors
     CuInfo *cus;
     int16_t *coefs;
-    int qp;
-    int lambda;                          // lambda_q8(qp) << (bit_depth - 8), from the host
-    QuantParam qy, qc;                   // luma / chroma quantiser (inter rounding)
+    FrameCtl *ctl;                       // QP / lambda / quantisers chosen on the device; receives the size estimate
 };
 
 struct IntraParams {
@@ -41,9 +39,8 @@ struct IntraParams {
     CuInfo *cus;
     int16_t *coefs;
     int *progress;                       // [ctuh], zeroed before launch
-    int qp;
-    int lambda;
-    QuantParam qy, qc;                   // intra rounding
+    FrameCtl *ctl;
+    int second_pass;                     // 1: run only when ctl->redo is set (first key frame of a stream under rate control)
 };
 
 struct ModeParams {
@@ -59,7 +56,8 @@ struct EntropyFrame {
     const int16_t *coefs;
     uint8_t *out;                        // [ctuh][row_cap]
     uint32_t *row_len;                   // [ctuh]
-    int is_intra, qp;
+    const FrameCtl *ctl;                 // slice QP (context initialisation)
+    int is_intra;
 };
 
 struct EntropyParams {
@@ -96,6 +94,8 @@ __global__ void k_coarse(CoarseParams p);
 __global__ void k_inter(InterParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_modes(ModeParams p);
+__global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr);
+__global__ void k_rc_redo(RcState *rc, FrameCtl *ctl);
 __global__ void k_entropy(EntropyParams p);
 __global__ void k_pack_scan(PackParams p);
 __global__ void k_pack_copy(PackParams p);

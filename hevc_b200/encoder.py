@@ -44,7 +44,8 @@ def crf_to_qp(crf: int) -> Tuple[int, int]:
     return max(0, min(51, qp_p - 2)), qp_p
 
 
-def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: bool = False, keep_recon: bool = False) -> HbEncParams:
+def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: bool = False, keep_recon: bool = False,
+                rate_control: bool = True) -> HbEncParams:
     c = HbEncParams()
     qp_i, qp_p = qp if qp is not None else crf_to_qp(p.crf)
     for name in ('width', 'height', 'fps_num', 'fps_den', 'bit_depth', 'profile_idc', 'level_idc', 'tier', 'keyint', 'min_keyint',
@@ -57,6 +58,8 @@ def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: b
     for i in range(10):
         c.master_display[i] = int(md[i])
     c.hash_sei, c.keep_recon = int(hash_sei), int(keep_recon)
+    # crf= with vbv-maxrate= / vbv-bufsize= (core/transcoder.py:398-403): CRF is the quality ceiling, the VBV model caps the rate
+    c.rate_control = int(rate_control)
     return c
 
 

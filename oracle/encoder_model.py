@@ -14,12 +14,12 @@ class EncParams(C.Structure):
         'width', 'height', 'fps_num', 'fps_den', 'bit_depth', 'profile_idc', 'level_idc', 'tier', 'qp_i', 'qp_p', 'keyint',
         'colour_primaries', 'transfer_characteristics', 'matrix_coeffs', 'vui_colour', 'chroma_loc', 'full_range',
         'aud', 'repeat_headers', 'hrd', 'hdr10', 'vbv_maxrate_kbps', 'vbv_bufsize_kbit')] + [
-        ('master_display', C.c_uint32 * 10), ('max_cll', C.c_int), ('max_fall', C.c_int), ('hash_sei', C.c_int), ('deblock', C.c_int)]
+        ('master_display', C.c_uint32 * 10), ('max_cll', C.c_int), ('max_fall', C.c_int), ('hash_sei', C.c_int), ('deblock', C.c_int), ('rate_control', C.c_int)]
 
 
 class FrameInfo(C.Structure):
     _fields_ = [('is_idr', C.c_int), ('poc', C.c_int), ('qp', C.c_int), ('bytes', C.c_int), ('n_skip', C.c_int),
-                ('n_merge', C.c_int), ('n_intra', C.c_int), ('psnr_y', C.c_double)]
+                ('n_merge', C.c_int), ('n_intra', C.c_int), ('psnr_y', C.c_double), ('est_bits16', C.c_longlong)]
 
 
 def make_params(width, height, bit_depth=8, qp_i=24, qp_p=26, keyint=60, fps=(30, 1), hdr10=False, hash_sei=True, **kw) -> EncParams:
@@ -42,6 +42,7 @@ def make_params(width, height, bit_depth=8, qp_i=24, qp_p=26, keyint=60, fps=(30
     p.vbv_maxrate_kbps, p.vbv_bufsize_kbit = kw.get('vbv_maxrate_kbps', 2940), kw.get('vbv_bufsize_kbit', 3528)
     p.hash_sei = int(hash_sei)
     p.deblock = int(kw.get('deblock', 0))
+    p.rate_control = int(kw.get('rate_control', 0))
     for k in ('aud', 'repeat_headers', 'hrd'):
         if k in kw:
             setattr(p, k, int(kw[k]))

@@ -44,6 +44,7 @@ struct orc_encoder {
     uint8_t *payload;                /* CABAC sub-streams */
     size_t payload_cap;
     uint32_t *row_off, *row_len;
+    orc_rc rc;
 };
 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
@@ -91,6 +92,7 @@ orc_encoder *orc_enc_create(const orc_enc_params *p)
     e->payload = (uint8_t *)malloc(e->payload_cap);
     e->row_off = (uint32_t *)calloc(e->ctuh, sizeof(uint32_t));
     e->row_len = (uint32_t *)calloc(e->ctuh, sizeof(uint32_t));
+    orc_rc_init(&e->rc, p);
     return e;
 }
 
@@ -424,11 +426,27 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
     const orc_enc_params *p = &e->prm;
     const int idr = force_idr || e->frame_no == 0 || (p->keyint > 0 && e->poc + 1 >= p->keyint);
     if (idr) e->poc = 0; else e->poc++;
-    const int qp = clampi(idr ? p->qp_i : p->qp_p, 0, 51);
+    int qp = clampi(orc_rc_pick_qp(&e->rc, p, idr), 0, 51);
     load_source(e, y, ys, u, v, cs);
     if (idr) encode_intra_frame(e, qp); else encode_inter_frame(e, qp);
+    long long est16 = 0;
+    for (int i = 0; i < e->cuw * e->cuh; i++)
+        est16 += orc_rc_cu_estimate(e->coefs + (size_t)i * ORC_CU_COEFS, e->cus[i].cbf);
+    if (p->rate_control && idr && !e->rc.have[1]) {
+        /* first key frame of a stream: no history to predict from, so it is coded twice when the first try overshoots */
+        const long long budget = orc_rc_budget(&e->rc, 1);
+        const int qp2 = clampi(qp + orc_rc_step(est16, budget), qp, 51);
+        if (est16 > budget && qp2 != qp) {
+            qp = qp2;
+            encode_intra_frame(e, qp);
+            est16 = 0;
+            for (int i = 0; i < e->cuw * e->cuh; i++)
+                est16 += orc_rc_cu_estimate(e->coefs + (size_t)i * ORC_CU_COEFS, e->cus[i].cbf);
+        }
+    }
     plane *rec = e->rec[e->cur];
     for (int c = 0; c < 3; c++) plane_extend(&rec[c]);
+    orc_rc_update(&e->rc, idr, qp, est16);
 
     orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, idr, qp, e->cus, e->coefs};
     if (orc_cabac_encode_frame(&fs, e->payload, e->payload_cap, e->row_off, e->row_len) != 0)
@@ -473,7 +491,7 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
         o += orc_write_sei_hash(md5, out + o, cap - o);
     }
     if (info) {
-        info->is_idr = idr; info->poc = e->poc; info->qp = qp; info->bytes = (int)o;
+        info->is_idr = idr; info->poc = e->poc; info->qp = qp; info->bytes = (int)o; info->est_bits16 = est16;
         info->n_skip = info->n_merge = info->n_intra = 0;
         double sse = 0;
         for (int i = 0; i < e->cuw * e->cuh; i++) { info->n_skip += e->cus[i].skip; info->n_intra += e->cus[i].pred_mode == 0; }

@@ -31,6 +31,7 @@ typedef struct orc_enc_params {
     int max_cll, max_fall;
     int hash_sei;                 /* emit decoded-picture-hash (MD5) suffix SEI */
     int deblock;                  /* in-loop deblocking filter enabled */
+    int rate_control;             /* 0 constant QP, 1 VBV-constrained (vbv_maxrate / vbv_bufsize) */
 } orc_enc_params;
 
 /* per-CU side information, also the interface between the decide/reconstruct stage and the entropy stage */
@@ -100,6 +101,7 @@ typedef struct orc_frame_info {
     int is_idr, poc, qp, bytes;
     int n_skip, n_merge, n_intra;
     double psnr_y;
+    long long est_bits16;         /* rate-control size estimate of this frame, 1/16 bit units */
 } orc_frame_info;
 
 orc_encoder *orc_enc_create(const orc_enc_params *p);
@@ -114,6 +116,21 @@ void orc_enc_coded_size(const orc_encoder *e, int *wc, int *hc);
 const orc_cu *orc_enc_last_cus(const orc_encoder *e);
 const int16_t *orc_enc_last_coefs(const orc_encoder *e);
 const int16_t *orc_enc_last_coarse_mv(const orc_encoder *e);
+
+/* ---- rate control (hevc_rc.c): deterministic, integer-only, driven by a size estimate computed from the levels */
+typedef struct orc_rc {
+    long long t16, b16;           /* bits*16 per frame interval, buffer size */
+    long long fullness;           /* bits*16 currently in the decoder buffer model */
+    int have[2], qp_prev[2];      /* [0] P frames, [1] IDR frames */
+    long long est_prev[2];
+} orc_rc;
+void orc_rc_init(orc_rc *rc, const orc_enc_params *p);
+int orc_rc_pick_qp(const orc_rc *rc, const orc_enc_params *p, int is_idr);
+void orc_rc_update(orc_rc *rc, int is_idr, int qp, long long est16);
+long long orc_rc_budget(const orc_rc *rc, int is_idr);
+int orc_rc_step(long long est, long long budget);
+/* size estimate of one CU from its levels, 1/16 bit: 47 nnz + 22 sum floor(log2|l|) + 104 coded 4x4 sub-blocks + 160 (coded) | 80 */
+long long orc_rc_cu_estimate(const int16_t *coef, int cbf);
 
 /* from primitives.c */
 int orc_sad(const pixel *a, int sa, const pixel *b, int sb, int w, int h);

@@ -18,14 +18,16 @@ def ctx():
     c.close()
 
 
-def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True):
+def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True, rate_control=False):
     from hevc_b200 import encoder as E
-    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True), max_batch=batch)
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True, rate_control=rate_control), max_batch=batch)
     stream, recs, decs = b'', [], []
+    _gpu_encode.last_qps = []
     pos = 0
     for n in (split or [len(frames8)]):
-        out, _ = enc.encode(E.pack_yuv420p8(frames8[pos:pos + n]), n)
+        out, stats = enc.encode(E.pack_yuv420p8(frames8[pos:pos + n]), n)
         stream += out
+        _gpu_encode.last_qps = getattr(_gpu_encode, 'last_qps', []) + [s.qp for s in stats]
         if read_back and n <= batch:          # the encoder keeps the reconstructions of its last batch
             for i in range(n):
                 recs.append(enc.read_recon(i))
@@ -98,3 +100,24 @@ def test_1080p_frame_pair(ctx):
             assert (dec[c] == rec[c][:dec[c].shape[0], :dec[c].shape[1]]).all()
     m_stream, _, _, _ = ec.run_model(p, frames, 24, 26, hash_sei=True)
     assert stream == m_stream
+
+
+@pytest.mark.parametrize('depth,kbps', [(8, 300), (10, 900), (8, 50000)])
+def test_rate_control_matches_cpu_model(ctx, depth, kbps):
+    """VBV-constrained mode: the QP trajectory is decided on the device from size estimates and must equal the model's,
+    including the two-pass first key frame, across batch boundaries and calls"""
+    from oracle import fforacle
+    w, h, n = 320, 192, 14
+    p = ec.b200_params(w, h, depth, keyint=6)
+    p.vbv_maxrate_kbps, p.vbv_bufsize_kbit = kbps, int(kbps * 1.2)
+    frames = ec.clip_frames(w, h, n, seed=7)
+    m_stream, _, m_recs, _ = ec.run_model(p, frames, 20, 22, hash_sei=True, rate_control=True)
+    m_qps = list(ec.run_model.last_qps)
+    g_stream, g_recs, _ = _gpu_encode(ctx, p, frames, (20, 22), batch=4, rate_control=True, split=[5, 9], read_back=False)
+    assert _gpu_encode.last_qps == m_qps
+    if kbps < 1000:
+        assert max(m_qps) > 24            # the cap really binds in these cases
+    else:
+        assert set(m_qps) == {20, 22}
+    assert g_stream == m_stream
+    assert len(fforacle.decode_hevc(g_stream, verify_hash=True)) == n
