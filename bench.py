@@ -304,7 +304,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--clip', default='4k60_hdr')
     ap.add_argument('--frames', type=int, default=120, help='frames per step (one closed GOP of the 4K60 HDR configuration)')
-    ap.add_argument('--batch', type=int, default=40, help='frames per device batch')
+    ap.add_argument('--batch', type=int, default=120, help='frames per device batch (one GOP: lets the entropy stage use one SM per frame)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

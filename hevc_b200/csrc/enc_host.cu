@@ -199,6 +199,9 @@ void md5(const uint8_t *data, size_t n, uint8_t out[16])
     memcpy(out, h, 16);
 }
 
+constexpr int kChunk = 8;            // frames per upload / entropy chunk
+constexpr int kMaxChunks = 1024 / kChunk + 1;
+
 struct FrameSlot {
     Planes src{};
     CuInfo *cus = nullptr;
@@ -244,6 +247,9 @@ struct hb_encoder {
     int poc = 0, since_bp = 0;
     std::atomic<int> stop{0}, done{0};
     cudaEvent_t ev[4] = {};
+    cudaStream_t st_copy = nullptr, st_entropy = nullptr;
+    cudaEvent_t ev_misc[2] = {};
+    std::vector<cudaEvent_t> ev_chunk;   // [0, kMaxChunks): upload done, [kMaxChunks, 2 kMaxChunks): chain done
     std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
     int profiling = 0;
     float prof_ms[6] = {};            // inter, intra, coarse, entropy(+pack), ingest, other
@@ -362,6 +368,11 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     HB_CUDA(ctx, cudaMallocHost(&E->packed_host, E->packed_cap));
     HB_CUDA(ctx, cudaMallocHost(&E->overflow_host, sizeof(int)));
     for (auto &ev : E->ev) HB_CUDA(ctx, cudaEventCreate(&ev));
+    for (auto &ev : E->ev_misc) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    E->ev_chunk.resize((size_t)2 * kMaxChunks);
+    for (auto &ev : E->ev_chunk) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_entropy, cudaStreamNonBlocking));
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -384,6 +395,10 @@ void hb_enc_destroy(hb_encoder *e)
     if (e->overflow_host) cudaFreeHost(e->overflow_host);
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_misc) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
+    if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
+    if (e->st_entropy) { cudaStreamSynchronize(e->st_entropy); cudaStreamDestroy(e->st_entropy); }
     for (auto &ev : e->kev) if (ev) cudaEventDestroy(ev);
     delete e;
 }
@@ -453,119 +468,18 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         const int n = std::min(e->max_batch, fr->n_frames - base);
         if (e->stop.load()) return hb_fail(ctx, HB_ERR_STOPPED, "%s", "stopped");
         HB_CUDA(ctx, cudaEventRecord(e->ev[0], st));
-        // ---- upload + ingest
-        const uint8_t *in = static_cast<const uint8_t *>(fr->data) + (size_t)base * fr->frame_bytes;
-        const uint8_t *dev_in = in;
-        size_t dev_fb = fr->frame_bytes;
-        if (!fr->on_device) {
-            if (fr->frame_bytes == fbytes) {
-                HB_CUDA(ctx, cudaMemcpyAsync(e->staging, in, fbytes * n, cudaMemcpyHostToDevice, st));
-            } else {
-                for (int i = 0; i < n; i++)
-                    HB_CUDA(ctx, cudaMemcpyAsync(e->staging + (size_t)i * fbytes, in + (size_t)i * fr->frame_bytes, fbytes, cudaMemcpyHostToDevice, st));
-            }
-            dev_in = e->staging;
-            dev_fb = fbytes;
-        }
-        HB_CUDA(ctx, cudaEventRecord(e->ev[1], st));
-        const size_t kb = (size_t)2 * e->max_batch;      // batch-level events start here
-        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 0], st));
-        for (int i = 0; i < n; i++) {
-            IngestParams ip;
-            ip.g = g;
-            const uint8_t *f = dev_in + (size_t)i * dev_fb;
-            const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
-            if (fr->format == HB_PIX_YUV420P8) {
-                ip.in_y = f; ip.in_u = f + luma; ip.in_v = f + luma + chroma;
-                ip.in_ys = p.width; ip.in_us = ip.in_vs = p.width / 2;
-                ip.up_shift = p.bit_depth - 8; ip.down_shift = 0;
-            } else if (fr->format == HB_PIX_P010) {
-                ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = nullptr;
-                ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = 2 * p.width;
-                ip.up_shift = 0; ip.down_shift = 16 - p.bit_depth;
-            } else {
-                ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = f + 2 * luma + 2 * chroma;
-                ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = p.width;
-                ip.up_shift = 0; ip.down_shift = 0;
-            }
-            ip.fmt = fr->format; ip.w = p.width; ip.h = p.height;
-            ip.src = e->slot[i].src;
-            ip.ds = e->ds + (size_t)(i + 1) * ds_stride;
-            k_ingest<<<hb_grid_for(ctx, (long long)g.dsw * g.dsh, 256, 8), 256, 0, st>>>(ip);
-            HB_LAUNCHED(ctx);
-        }
-        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 1], st));
-        // ---- coarse motion search for every frame of the batch at once (source-based, independent of the recon chain)
-        {
-            CoarseParams cp;
-            cp.g = g; cp.ds = e->ds; cp.ds_frame_stride = ds_stride; cp.cmv = e->cmv;
-            k_coarse<<<dim3(nctu, n), 128, 0, st>>>(cp);
-            HB_LAUNCHED(ctx);
-        }
-        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 2], st));
-        // ---- frame chain
+        // ---- frame types of the batch (pure host state) and the entropy-stage descriptors
         std::vector<int> is_idr(n), qps(n), pocs(n);
-        for (int i = 0; i < n; i++) {
-            const bool idr = (force_idr && base == 0 && i == 0) || e->frame_no == 0 || e->poc + 1 >= p.keyint;
-            e->poc = idr ? 0 : e->poc + 1;
-            is_idr[i] = idr; pocs[i] = e->poc;
-            FrameSlot &s = e->slot[i];
-            const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
-            // rate control on the device: account for the previous frame, choose this frame's QP
-            k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? e->ctl_dev + i - 1 : nullptr, e->ctl_dev + i, idr ? 1 : 0);
-            HB_LAUNCHED(ctx);
-            if (idr) HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
-            if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i], st));
-            if (idr) {
-                IntraParams ip;
-                ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
-                ip.ctl = e->ctl_dev + i; ip.second_pass = 0;
-                k_intra<<<g.ctuh, 256, 0, st>>>(ip);
-                HB_LAUNCHED(ctx);
-                if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
-                    k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + i);
-                    HB_LAUNCHED(ctx);
-                    HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
-                    ip.second_pass = 1;
-                    k_intra<<<g.ctuh, 256, 0, st>>>(ip);
-                    HB_LAUNCHED(ctx);
-                }
-                e->rc_have_idr = true;
-            } else {
-                InterParams ip;
-                ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
-                ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
-                k_inter<<<nctu, 128, 0, st>>>(ip);
-                HB_LAUNCHED(ctx);
+        {
+            int poc = e->poc;
+            long long fno = e->frame_no;
+            for (int i = 0; i < n; i++, fno++) {
+                const bool idr = (force_idr && base == 0 && i == 0) || fno == 0 || poc + 1 >= p.keyint;
+                poc = idr ? 0 : poc + 1;
+                is_idr[i] = idr; pocs[i] = poc;
             }
-            if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
-            {
-                const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
-                k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(rec, g);
-                HB_LAUNCHED(ctx);
-            }
-            if (p.keep_recon || p.hash_sei) {
-                const pixel *srcp[3] = {rec.y, rec.u, rec.v};
-                pixel *dstp[3] = {s.keep.y, s.keep.u, s.keep.v};
-                for (int c = 0; c < 3; c++) {
-                    const int w = c ? g.wc / 2 : g.wc, h = c ? g.hc / 2 : g.hc, stride = c ? g.recc_stride : g.rec_stride;
-                    HB_CUDA(ctx, cudaMemcpy2DAsync(dstp[c], (size_t)w * sizeof(pixel), srcp[c], (size_t)stride * sizeof(pixel), (size_t)w * sizeof(pixel), h,
-                                                   cudaMemcpyDeviceToDevice, st));
-                }
-            }
-            ModeParams mp;
-            mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.is_intra = idr;
-            k_modes<<<(ncu + 255) / 256, 256, 0, st>>>(mp);
-            HB_LAUNCHED(ctx);
-            e->cur = 1 - e->cur;
-            e->frame_no++;
+            e->poc = poc;
         }
-        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
-        HB_LAUNCHED(ctx);
-        // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
-        HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
-        // ---- entropy coding of the whole batch, compaction, download
-        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
         std::vector<EntropyFrame> ef(n);
         for (int i = 0; i < n; i++) {
             FrameSlot &s = e->slot[i];
@@ -574,12 +488,139 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         }
         HB_CUDA(ctx, cudaMemcpyAsync(e->eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
         HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
+        HB_CUDA(ctx, cudaEventRecord(e->ev_misc[0], st));
+        HB_CUDA(ctx, cudaStreamWaitEvent(e->st_copy, e->ev_misc[0], 0));   // staging may still be read by the previous batch
+        HB_CUDA(ctx, cudaStreamWaitEvent(e->st_entropy, e->ev_misc[0], 0));
+        const uint8_t *in = static_cast<const uint8_t *>(fr->data) + (size_t)base * fr->frame_bytes;
+        const size_t kb = (size_t)2 * e->max_batch;      // batch-level profiling events start here
+        float ingest_ms = 0, coarse_ms = 0;
+        (void)ingest_ms; (void)coarse_ms;
+        // ---- chunks: upload (copy stream) | ingest + coarse search + frame chain (main stream) | CABAC (entropy stream)
+        for (int c0 = 0, chunk = 0; c0 < n; c0 += kChunk, chunk++) {
+            const int cn = std::min(kChunk, n - c0);
+            const uint8_t *dev_in = in + (size_t)c0 * fr->frame_bytes;
+            size_t dev_fb = fr->frame_bytes;
+            if (!fr->on_device) {
+                if (fr->frame_bytes == fbytes) {
+                    HB_CUDA(ctx, cudaMemcpyAsync(e->staging + (size_t)c0 * fbytes, dev_in, fbytes * cn, cudaMemcpyHostToDevice, e->st_copy));
+                } else {
+                    for (int i = 0; i < cn; i++)
+                        HB_CUDA(ctx, cudaMemcpyAsync(e->staging + (size_t)(c0 + i) * fbytes, dev_in + (size_t)i * fr->frame_bytes, fbytes,
+                                                     cudaMemcpyHostToDevice, e->st_copy));
+                }
+                HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[chunk], e->st_copy));
+                HB_CUDA(ctx, cudaStreamWaitEvent(st, e->ev_chunk[chunk], 0));
+                dev_in = e->staging + (size_t)c0 * fbytes;
+                dev_fb = fbytes;
+            }
+            if (c0 == 0) {
+                HB_CUDA(ctx, cudaEventRecord(e->ev[1], st));
+                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 0], st));
+            }
+            for (int i = 0; i < cn; i++) {
+                IngestParams ip;
+                ip.g = g;
+                const uint8_t *f = dev_in + (size_t)i * dev_fb;
+                const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
+                if (fr->format == HB_PIX_YUV420P8) {
+                    ip.in_y = f; ip.in_u = f + luma; ip.in_v = f + luma + chroma;
+                    ip.in_ys = p.width; ip.in_us = ip.in_vs = p.width / 2;
+                    ip.up_shift = p.bit_depth - 8; ip.down_shift = 0;
+                } else if (fr->format == HB_PIX_P010) {
+                    ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = nullptr;
+                    ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = 2 * p.width;
+                    ip.up_shift = 0; ip.down_shift = 16 - p.bit_depth;
+                } else {
+                    ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = f + 2 * luma + 2 * chroma;
+                    ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = p.width;
+                    ip.up_shift = 0; ip.down_shift = 0;
+                }
+                ip.fmt = fr->format; ip.w = p.width; ip.h = p.height;
+                ip.src = e->slot[c0 + i].src;
+                ip.ds = e->ds + (size_t)(c0 + i + 1) * ds_stride;
+                k_ingest<<<hb_grid_for(ctx, (long long)g.dsw * g.dsh, 256, 8), 256, 0, st>>>(ip);
+                HB_LAUNCHED(ctx);
+            }
+            // coarse motion search for the whole chunk in one launch (source-based, independent of the reconstruction chain)
+            {
+                CoarseParams cp;
+                cp.g = g; cp.ds = e->ds + (size_t)c0 * ds_stride; cp.ds_frame_stride = ds_stride; cp.cmv = e->cmv + (size_t)c0 * nctu * 2;
+                k_coarse<<<dim3(nctu, cn), 128, 0, st>>>(cp);
+                HB_LAUNCHED(ctx);
+            }
+            // frame chain
+            for (int i = c0; i < c0 + cn; i++) {
+                const bool idr = is_idr[i] != 0;
+                FrameSlot &s = e->slot[i];
+                const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
+                // rate control on the device: account for the previous frame, choose this frame's QP
+                k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? e->ctl_dev + i - 1 : nullptr, e->ctl_dev + i, idr ? 1 : 0);
+                HB_LAUNCHED(ctx);
+                if (idr) HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i], st));
+                if (idr) {
+                    IntraParams ip;
+                    ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
+                    ip.ctl = e->ctl_dev + i; ip.second_pass = 0;
+                    k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                    if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
+                        k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + i);
+                        HB_LAUNCHED(ctx);
+                        HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+                        ip.second_pass = 1;
+                        k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+                        HB_LAUNCHED(ctx);
+                    }
+                    e->rc_have_idr = true;
+                } else {
+                    InterParams ip;
+                    ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
+                    ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
+                    k_inter<<<nctu, 128, 0, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                }
+                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
+                {
+                    const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
+                    k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(rec, g);
+                    HB_LAUNCHED(ctx);
+                }
+                if (p.keep_recon || p.hash_sei) {
+                    const pixel *srcp[3] = {rec.y, rec.u, rec.v};
+                    pixel *dstp[3] = {s.keep.y, s.keep.u, s.keep.v};
+                    for (int c = 0; c < 3; c++) {
+                        const int w = c ? g.wc / 2 : g.wc, h = c ? g.hc / 2 : g.hc, stride = c ? g.recc_stride : g.rec_stride;
+                        HB_CUDA(ctx, cudaMemcpy2DAsync(dstp[c], (size_t)w * sizeof(pixel), srcp[c], (size_t)stride * sizeof(pixel),
+                                                       (size_t)w * sizeof(pixel), h, cudaMemcpyDeviceToDevice, st));
+                    }
+                }
+                ModeParams mp;
+                mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.is_intra = idr;
+                k_modes<<<(ncu + 255) / 256, 256, 0, st>>>(mp);
+                HB_LAUNCHED(ctx);
+                e->cur = 1 - e->cur;
+                e->frame_no++;
+            }
+            // CABAC of this chunk on the entropy stream, overlapping the frame chain of the following chunks
+            HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[kMaxChunks + chunk], st));
+            HB_CUDA(ctx, cudaStreamWaitEvent(e->st_entropy, e->ev_chunk[kMaxChunks + chunk], 0));
+            {
+                EntropyParams ep;
+                ep.g = g; ep.frames = e->eframes_dev + c0; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
+                k_entropy<<<cn, 32 * 32, entropy_smem_bytes(g.ctuh), e->st_entropy>>>(ep);
+                HB_LAUNCHED(ctx);
+            }
+        }
+        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
+        HB_LAUNCHED(ctx);
+        // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
+        HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
+        // ---- join the entropy stream, compaction, download
+        HB_CUDA(ctx, cudaEventRecord(e->ev_misc[1], e->st_entropy));
+        HB_CUDA(ctx, cudaStreamWaitEvent(st, e->ev_misc[1], 0));
         {
-            EntropyParams ep;
-            ep.g = g; ep.frames = e->eframes_dev; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
-            const size_t smem = entropy_smem_bytes(g.ctuh);
-            k_entropy<<<n, 32 * 32, smem, st>>>(ep);
-            HB_LAUNCHED(ctx);
             PackParams pp;
             pp.frames = e->eframes_dev; pp.n_frames = n; pp.rows = g.ctuh; pp.row_cap = e->row_cap; pp.packed = e->packed_dev; pp.offsets = e->offsets_dev;
             k_pack_scan<<<1, 1024, 0, st>>>(pp);
@@ -613,10 +654,8 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 const int k = is_idr[i] ? 1 : 0;
                 e->prof_ms[k] += ms; e->prof_launches[k]++;
             }
-            cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 1]); e->prof_ms[4] += ms; e->prof_launches[4] += n;
-            cudaEventElapsedTime(&ms, e->kev[kb + 1], e->kev[kb + 2]); e->prof_ms[2] += ms; e->prof_launches[2] += 1;
-            cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 3;
-            cudaEventElapsedTime(&ms, e->kev[kb + 2], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 2 * n;
+            cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
+            cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
         }
         // ---- access-unit assembly on the host
         std::vector<uint8_t> au, slice;
