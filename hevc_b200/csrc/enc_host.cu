@@ -201,6 +201,7 @@ void md5(const uint8_t *data, size_t n, uint8_t out[16])
 
 constexpr int kChunk = 8;            // frames per upload / entropy chunk
 constexpr int kMaxChunks = 1024 / kChunk + 1;
+constexpr int kEntropyStreams = 4;
 
 struct FrameSlot {
     Planes src{};
@@ -247,8 +248,10 @@ struct hb_encoder {
     int poc = 0, since_bp = 0;
     std::atomic<int> stop{0}, done{0};
     cudaEvent_t ev[4] = {};
-    cudaStream_t st_copy = nullptr, st_entropy = nullptr;
-    cudaEvent_t ev_misc[2] = {};
+    cudaStream_t st_copy = nullptr;
+    cudaStream_t st_entropy[kEntropyStreams] = {};   // CABAC launches round-robin over these, concurrent with the frame chain
+    int next_entropy_stream = 0;
+    cudaEvent_t ev_misc[2] = {}, ev_join[kEntropyStreams] = {};
     std::vector<cudaEvent_t> ev_chunk;   // [0, kMaxChunks): upload done, [kMaxChunks, 2 kMaxChunks): chain done
     std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
     int profiling = 0;
@@ -369,10 +372,11 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     HB_CUDA(ctx, cudaMallocHost(&E->overflow_host, sizeof(int)));
     for (auto &ev : E->ev) HB_CUDA(ctx, cudaEventCreate(&ev));
     for (auto &ev : E->ev_misc) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : E->ev_join) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     E->ev_chunk.resize((size_t)2 * kMaxChunks);
     for (auto &ev : E->ev_chunk) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
-    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_entropy, cudaStreamNonBlocking));
+    for (auto &q : E->st_entropy) HB_CUDA(ctx, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -396,9 +400,10 @@ void hb_enc_destroy(hb_encoder *e)
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_misc) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_join) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
-    if (e->st_entropy) { cudaStreamSynchronize(e->st_entropy); cudaStreamDestroy(e->st_entropy); }
+    for (auto &q : e->st_entropy) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
     for (auto &ev : e->kev) if (ev) cudaEventDestroy(ev);
     delete e;
 }
@@ -490,7 +495,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
         HB_CUDA(ctx, cudaEventRecord(e->ev_misc[0], st));
         HB_CUDA(ctx, cudaStreamWaitEvent(e->st_copy, e->ev_misc[0], 0));   // staging may still be read by the previous batch
-        HB_CUDA(ctx, cudaStreamWaitEvent(e->st_entropy, e->ev_misc[0], 0));
+        for (auto &q : e->st_entropy) HB_CUDA(ctx, cudaStreamWaitEvent(q, e->ev_misc[0], 0));
         const uint8_t *in = static_cast<const uint8_t *>(fr->data) + (size_t)base * fr->frame_bytes;
         const size_t kb = (size_t)2 * e->max_batch;      // batch-level profiling events start here
         float ingest_ms = 0, coarse_ms = 0;
@@ -602,13 +607,15 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 e->cur = 1 - e->cur;
                 e->frame_no++;
             }
-            // CABAC of this chunk on the entropy stream, overlapping the frame chain of the following chunks
-            HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[kMaxChunks + chunk], st));
-            HB_CUDA(ctx, cudaStreamWaitEvent(e->st_entropy, e->ev_chunk[kMaxChunks + chunk], 0));
+            // CABAC of this chunk on a side stream, overlapping the frame chain of the following chunks
             {
+                cudaStream_t q = e->st_entropy[e->next_entropy_stream];
+                e->next_entropy_stream = (e->next_entropy_stream + 1) % kEntropyStreams;
+                HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[kMaxChunks + chunk], st));
+                HB_CUDA(ctx, cudaStreamWaitEvent(q, e->ev_chunk[kMaxChunks + chunk], 0));
                 EntropyParams ep;
                 ep.g = g; ep.frames = e->eframes_dev + c0; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
-                k_entropy<<<cn, 32 * 32, entropy_smem_bytes(g.ctuh), e->st_entropy>>>(ep);
+                k_entropy<<<cn, 32 * 32, entropy_smem_bytes(g.ctuh), q>>>(ep);
                 HB_LAUNCHED(ctx);
             }
         }
@@ -618,8 +625,10 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
         if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
         // ---- join the entropy stream, compaction, download
-        HB_CUDA(ctx, cudaEventRecord(e->ev_misc[1], e->st_entropy));
-        HB_CUDA(ctx, cudaStreamWaitEvent(st, e->ev_misc[1], 0));
+        for (int k = 0; k < kEntropyStreams; k++) {
+            HB_CUDA(ctx, cudaEventRecord(e->ev_join[k], e->st_entropy[k]));
+            HB_CUDA(ctx, cudaStreamWaitEvent(st, e->ev_join[k], 0));
+        }
         {
             PackParams pp;
             pp.frames = e->eframes_dev; pp.n_frames = n; pp.rows = g.ctuh; pp.row_cap = e->row_cap; pp.packed = e->packed_dev; pp.offsets = e->offsets_dev;
