@@ -121,3 +121,37 @@ def test_rate_control_matches_cpu_model(ctx, depth, kbps):
         assert set(m_qps) == {20, 22}
     assert g_stream == m_stream
     assert len(fforacle.decode_hevc(g_stream, verify_hash=True)) == n
+
+
+def test_4k60_hdr10_full_size(ctx):
+    """BASELINE configs[1] at full size (3840x2160 Main10, level 5.1, HDR10 SEI, VBV rate control): the stream decodes
+    under the FFmpeg decoder with picture-hash verification on, to exactly the encoder's reconstruction; the first
+    access unit equals the CPU model's byte for byte"""
+    from hevc_b200 import derive, encoder as E
+    from hevc_b200.probe import VideoInfo
+    from hevc_b200.synth import TorchSynthClip
+    from oracle import fforacle
+    info = VideoInfo(3840, 2160, 60.0, 'bt2020', 'smpte2084', 'bt2020nc', 'yuv420p', '', '', 0, True, None, None, 5.0)
+    p = derive.derive_b200_params(info)
+    assert (p.level_idc, p.keyint, p.vbv_maxrate_kbps, p.crf) == (153, 120, 23520, 19)
+    clip = TorchSynthClip(3840, 2160, seed=11, device='cuda:0')
+    n = 4
+    frames = clip.frames(0, n).cpu().numpy()
+    enc = E.B200Encoder(ctx, E.to_c_params(p, hash_sei=True, keep_recon=True), max_batch=n)
+    stream, stats = enc.encode(frames, n)
+    recs = [enc.read_recon(i) for i in range(n)]
+    enc.close()
+    dec = fforacle.decode_hevc(stream, verify_hash=True)
+    assert len(dec) == n and dec[0][0].shape == (2160, 3840) and dec[0][0].dtype == np.uint16
+    for d, r in zip(dec, recs):
+        for c in range(3):
+            assert (d[c] == r[c][:d[c].shape[0], :d[c].shape[1]]).all()
+    types = [t for _, t, _ in fforacle.iter_nals(stream)]
+    assert types[:4] == [35, 32, 33, 34] and types.count(19) == 1 and types.count(1) == n - 1
+    # first access unit (two-pass rate-controlled IDR) against the CPU model
+    lw, cw = 3840 * 2160, 1920 * 1080
+    f0 = frames[0]
+    qi, qp = E.crf_to_qp(p.crf)
+    m_stream, m_aus, _, _ = ec.run_model(p, [(f0[:lw].reshape(2160, 3840), f0[lw:lw + cw].reshape(1080, 1920), f0[lw + cw:].reshape(1080, 1920))],
+                                         qi, qp, hash_sei=True, rate_control=True)
+    assert stream[:stats[0].bytes] == m_aus[0]
