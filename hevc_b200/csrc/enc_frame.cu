@@ -9,6 +9,8 @@ __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffff
 
 // interpolation taps in constant memory: the fraction is warp-uniform, so these are broadcast LDCs
 __constant__ int8_t c_luma_taps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+// the same luma taps packed for dp2a: {E0123, E4567, O(0,t0,t1,t2), O(t3,t4,t5,t6), O(t7,0,0,0)} (bytes, little end first)
+__constant__ int c_luma_pack[4][5];
 __constant__ int8_t c_chroma_taps[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
                                            {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
 __device__ __forceinline__ int clampd(int v, int lo, int hi) { return min(max(v, lo), hi); }
@@ -145,8 +147,8 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
 // ================================================================================================ inter frame
 struct __align__(16) WarpScratch {
     pixel src[16][16];
-    pixel win[28][30];
-    int16_t tmp[23][18];
+    pixel win[28][32];          // reference window; 64-byte rows so that sample pairs are aligned 32-bit words
+    int16_t tmpT[16][24];       // horizontal-pass output, TRANSPOSED: [column][row], rows 0..22 used
     pixel pred[16][16];
     int16_t a[16][18], b[16][18];
 };
@@ -167,50 +169,98 @@ __device__ __forceinline__ MV ctu_mv(const Geom &g, const int16_t *cmv, int tx, 
     return MV{c[0] * 16, c[1] * 16};
 }
 
-// luma prediction of the 16x16 block whose integer sample (0,0) sits at window position (ix, iy);
-// unified two-pass form (bit-exact with the normative one-pass cases)
-__device__ __forceinline__ void interp_window(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane)
+// 8-tap filter on sample pairs held as 32-bit words: result for the sample at position `rel` (in samples) of w[]
+//   even rel: taps (t0,t1)(t2,t3)(t4,t5)(t6,t7) on words rel/2 ..;  odd rel: (0,t0)(t1,t2)(t3,t4)(t5,t6)(t7,0) on words (rel-1)/2 ..
+template <int REL>
+__device__ __forceinline__ int tap8(const int (&w)[8], const int (&t)[5])
+{
+    if constexpr ((REL & 1) == 0) {
+        constexpr int b = REL / 2;
+        int acc = __dp2a_lo(w[b], t[0], 0);
+        acc = __dp2a_hi(w[b + 1], t[0], acc);
+        acc = __dp2a_lo(w[b + 2], t[1], acc);
+        return __dp2a_hi(w[b + 3], t[1], acc);
+    } else {
+        constexpr int b = (REL - 1) / 2;
+        int acc = __dp2a_lo(w[b], t[2], 0);
+        acc = __dp2a_hi(w[b + 1], t[2], acc);
+        acc = __dp2a_lo(w[b + 2], t[3], acc);
+        acc = __dp2a_hi(w[b + 3], t[3], acc);
+        return __dp2a_lo(w[b + 4], t[4], acc);
+    }
+}
+
+template <int PAR>
+__device__ __forceinline__ void hpass8(const int (&w)[8], const int (&t)[5], int shift1, int16_t *dst /* tmpT[c0][r], column stride 24 */)
+{
+    dst[0 * 24] = (int16_t)(tap8<0 + PAR>(w, t) >> shift1);
+    dst[1 * 24] = (int16_t)(tap8<1 + PAR>(w, t) >> shift1);
+    dst[2 * 24] = (int16_t)(tap8<2 + PAR>(w, t) >> shift1);
+    dst[3 * 24] = (int16_t)(tap8<3 + PAR>(w, t) >> shift1);
+    dst[4 * 24] = (int16_t)(tap8<4 + PAR>(w, t) >> shift1);
+    dst[5 * 24] = (int16_t)(tap8<5 + PAR>(w, t) >> shift1);
+    dst[6 * 24] = (int16_t)(tap8<6 + PAR>(w, t) >> shift1);
+    dst[7 * 24] = (int16_t)(tap8<7 + PAR>(w, t) >> shift1);
+}
+
+// Luma prediction of the 16x16 block whose integer sample (0,0) sits at window position (ix, iy), in the unified two-pass
+// form (bit-exact with the normative one-pass cases).  Both passes run on packed sample pairs with
+// dp2a.  Lane mapping of the result: lane -> column c = lane >> 1, rows r0 = 8 * (lane & 1) .. r0 + 7 (pv[k] = row r0 + k).
+__device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane, int (&pv)[8])
 {
     const int shift1 = bd - 8, s14 = 14 - bd, off14 = 1 << (s14 - 1), maxv = (1 << bd) - 1;
-    int tx[8], ty[8];
+    int th[5], tv[5];
 #pragma unroll
-    for (int t = 0; t < 8; t++) { tx[t] = c_luma_taps[fx][t]; ty[t] = c_luma_taps[fy][t]; }
-    for (int o = lane; o < 23 * 16; o += 32) {
-        const int r = o >> 4, c = o & 15;
-        const pixel *w = &s.win[iy - 3 + r][ix - 3 + c];
-        int acc = 0;
+    for (int k = 0; k < 5; k++) { th[k] = c_luma_pack[fx][k]; tv[k] = c_luma_pack[fy][k]; }
+    // horizontal: 23 rows x 2 half-rows of 8 outputs
+    for (int task = lane; task < 46; task += 32) {
+        const int r = task >> 1, c0 = (task & 1) * 8;
+        const int s0 = ix - 3 + c0, w0 = s0 >> 1;
+        const int *wp = reinterpret_cast<const int *>(&s.win[iy - 3 + r][0]) + w0;
+        int w[8];
 #pragma unroll
-        for (int t = 0; t < 8; t++)
-            acc += tx[t] * w[t];
-        s.tmp[r][c] = (int16_t)(acc >> shift1);
+        for (int k = 0; k < 8; k++) w[k] = wp[k];
+        int16_t *dst = &s.tmpT[c0][r];
+        if (s0 & 1) hpass8<1>(w, th, shift1, dst);
+        else hpass8<0>(w, th, shift1, dst);
     }
     __syncwarp();
-    const int row = lane >> 1, c0 = (lane & 1) * 8;
+    // vertical: one column segment of 8 outputs per lane, two 128-bit loads
+    const int c = lane >> 1, r0 = (lane & 1) * 8;
+    const int4 lo = *reinterpret_cast<const int4 *>(&s.tmpT[c][r0]), hi = *reinterpret_cast<const int4 *>(&s.tmpT[c][r0 + 8]);
+    const int w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    int acc[8];
+    acc[0] = tap8<0>(w, tv); acc[1] = tap8<1>(w, tv); acc[2] = tap8<2>(w, tv); acc[3] = tap8<3>(w, tv);
+    acc[4] = tap8<4>(w, tv); acc[5] = tap8<5>(w, tv); acc[6] = tap8<6>(w, tv); acc[7] = tap8<7>(w, tv);
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int acc = 0;
-#pragma unroll
-        for (int t = 0; t < 8; t++)
-            acc += ty[t] * s.tmp[row + t][c0 + c];
-        s.pred[row][c0 + c] = (pixel)clampd(((acc >> 6) + off14) >> s14, 0, maxv);
-    }
+    for (int k = 0; k < 8; k++)
+        pv[k] = clampd(((acc[k] >> 6) + off14) >> s14, 0, maxv);
     __syncwarp();
 }
 
-__device__ __forceinline__ int satd16_smem(const WarpScratch &s, int lane)
+// SATD of the 16x16 block from column segments held in registers: vertical 4-point Hadamard in the lane, horizontal one
+// across the four lanes that hold the four columns of a 4x4 block (lane xor 2, xor 4).  Sum of |H D H| over all 16 blocks
+// is even per block, so the per-block ">> 1" of satd_4x4 can be applied to the total.
+__device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8], int lane)
 {
-    int v = 0;
-    if (lane < 16) {
-        const int sx = (lane & 3) * 4, sy = (lane >> 2) * 4;
-        int d[4][4];
+    int v[8];
 #pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-                d[y][x] = (int)s.src[sy + y][sx + x] - (int)s.pred[sy + y][sx + x];
-        v = hadamard4x4_abs(d) >> 1;
+    for (int g = 0; g < 8; g += 4) {
+        const int d0 = st[g] - pv[g], d1 = st[g + 1] - pv[g + 1], d2 = st[g + 2] - pv[g + 2], d3 = st[g + 3] - pv[g + 3];
+        const int a0 = d0 + d1, a1 = d0 - d1, a2 = d2 + d3, a3 = d2 - d3;
+        v[g] = a0 + a2; v[g + 1] = a1 + a3; v[g + 2] = a0 - a2; v[g + 3] = a1 - a3;
     }
-    return warp_sum(v);
+#pragma unroll
+    for (int m = 2; m <= 4; m <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int o = __shfl_xor_sync(0xffffffffu, v[k], m);
+            v[k] = (lane & m) ? o - v[k] : v[k] + o;
+        }
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += abs(v[k]);
+    return warp_sum(sum) >> 1;
 }
 
 __global__ void __launch_bounds__(128) k_inter(InterParams p)
@@ -262,6 +312,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
             const int wr = i / 28, wc = i % 28;
             s.win[wr][wc] = r[(ptrdiff_t)wr * g.rec_stride + wc];
         }
+        if (lane < 28) *reinterpret_cast<uint2 *>(&s.win[lane][28]) = make_uint2(0, 0);     // pad columns read as pair partners
     }
     __syncwarp();
     // ---- integer stage 2: 5x5 square, SAD from shared memory
@@ -283,8 +334,11 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
         }
     // ---- sub-sample stages: SATD on the normative interpolation
     const int wx0 = (centre.x >> 2) - 6, wy0 = (centre.y >> 2) - 6;     // window origin relative to the block position
-    interp_window(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane);
-    bcost = satd16_smem(s, lane) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+    int st[8], pv[8];        // source / prediction column segments: column lane >> 1, rows 8 * (lane & 1) + k
+#pragma unroll
+    for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];
+    interp_cols(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane, pv);
+    bcost = satd_cols(st, pv, lane) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
 #pragma unroll 1
     for (int step = 2; step >= 1; step--) {
         const MV c2 = best;
@@ -296,13 +350,16 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
                 const MV m{c2.x + step * dx, c2.y + step * dy};
                 const MV cm = clamp_mv(g, x0, y0, m);
                 if (cm.x != m.x || cm.y != m.y) continue;
-                interp_window(s, (m.x >> 2) - wx0, (m.y >> 2) - wy0, m.x & 3, m.y & 3, bd, lane);
-                const int cost = satd16_smem(s, lane) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                interp_cols(s, (m.x >> 2) - wx0, (m.y >> 2) - wy0, m.x & 3, m.y & 3, bd, lane, pv);
+                const int cost = satd_cols(st, pv, lane) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
                 if (cost < bcost) { bcost = cost; best = m; }
             }
     }
     // ---- luma: predict, transform, quantise, reconstruct
-    interp_window(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane);
+    interp_cols(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane, pv);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s.pred[(lane & 1) * 8 + k][lane >> 1] = (pixel)pv[k];    // back to row-major for the residual path
+    __syncwarp();
     int16_t *coef = p.coefs + (size_t)(cy * g.cuw + cx) * kCuCoefs;
     int pr[8];
 #pragma unroll
@@ -375,7 +432,7 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
     const int fxc = best.x & 7, fyc = best.y & 7;
     const int shift1 = bd - 8, s14 = 14 - bd, off14 = 1 << (s14 - 1);
     pixel *cwin = &s.win[0][0];                 // [2][11][12]
-    int16_t *ctmp = &s.tmp[0][0];               // [2][11][8]
+    int16_t *ctmp = &s.tmpT[0][0];              // [2][11][8]
     {
         const ptrdiff_t off = (ptrdiff_t)(cy * 8 + (best.y >> 3) - 1) * g.recc_stride + cx * 8 + (best.x >> 3) - 1;
         for (int i = lane; i < 2 * 11 * 11; i += 32) {
@@ -680,6 +737,22 @@ __global__ void __launch_bounds__(256) k_intra(IntraParams p)
         if (threadIdx.x == 0)
             atomicExch(p.progress + r, x + 1);
     }
+}
+
+cudaError_t upload_inter_constants(cudaStream_t st)
+{
+    static const int8_t taps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+    int pack[4][5];
+    auto b = [](int v) { return (unsigned)(uint8_t)(int8_t)v; };
+    for (int f = 0; f < 4; f++) {
+        const int8_t *t = taps[f];
+        pack[f][0] = (int)(b(t[0]) | (b(t[1]) << 8) | (b(t[2]) << 16) | (b(t[3]) << 24));
+        pack[f][1] = (int)(b(t[4]) | (b(t[5]) << 8) | (b(t[6]) << 16) | (b(t[7]) << 24));
+        pack[f][2] = (int)((b(t[0]) << 8) | (b(t[1]) << 16) | (b(t[2]) << 24));
+        pack[f][3] = (int)(b(t[3]) | (b(t[4]) << 8) | (b(t[5]) << 16) | (b(t[6]) << 24));
+        pack[f][4] = (int)b(t[7]);
+    }
+    return cudaMemcpyToSymbolAsync(c_luma_pack, pack, sizeof(pack), 0, cudaMemcpyHostToDevice, st);
 }
 
 // ================================================================================================ rate control steps

@@ -379,6 +379,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     for (auto &q : E->st_entropy) HB_CUDA(ctx, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
+    HB_CUDA(ctx, upload_inter_constants(ctx->stream));
     HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     E->vps = make_vps(p);
     E->sps = make_sps(p, g.wc, g.hc);

@@ -88,6 +88,9 @@ inline size_t entropy_smem_bytes(int ctuh)
     return sizeof(EntropyWarpScratch) * kEntropyWarps + (((size_t)ctuh * kNumCtx + 15) & ~(size_t)15) + sizeof(int) * (size_t)ctuh;
 }
 
+// uploads the dp2a-packed interpolation taps into constant memory (call once per process/device before k_inter)
+cudaError_t upload_inter_constants(cudaStream_t st);
+
 __global__ void k_ingest(IngestParams p);
 __global__ void k_border(Planes rec, Geom g);
 __global__ void k_coarse(CoarseParams p);
