@@ -162,7 +162,7 @@ __device__ __forceinline__ void cb_byte(Cabac &c, uint32_t v)
     c.pos++;
 }
 
-__device__ __forceinline__ void cb_write_out(Cabac &c)
+__device__ __noinline__ void cb_write_out(Cabac &c)
 {
     const uint32_t lead = c.low >> (24 - c.bits_left);
     c.bits_left += 8;
@@ -181,7 +181,9 @@ __device__ __forceinline__ void cb_write_out(Cabac &c)
     }
 }
 
-__device__ __forceinline__ void cb_bin(Cabac &c, int ctx, int bin)
+// Not inlined on purpose: the syntax code calls these from ~100 sites; inlining them made a 45 k-instruction kernel that
+// spent 57 % of its stall samples waiting for instruction fetch (profiles/round1_summary.md).
+__device__ __noinline__ void cb_bin(Cabac &c, int ctx, int bin)
 {
     const uint32_t s = c.ctx[ctx];
     const uint32_t st = s >> 1, mps = s & 1;
@@ -203,7 +205,7 @@ __device__ __forceinline__ void cb_bin(Cabac &c, int ctx, int bin)
     if (c.bits_left < 12) cb_write_out(c);
 }
 
-__device__ __forceinline__ void cb_bypass(Cabac &c, int bin)
+__device__ __forceinline__ void cb_bypass_inl(Cabac &c, int bin)
 {
     c.low <<= 1;
     if (bin) c.low += c.range;
@@ -211,12 +213,14 @@ __device__ __forceinline__ void cb_bypass(Cabac &c, int bin)
     if (c.bits_left < 12) cb_write_out(c);
 }
 
-__device__ __forceinline__ void cb_bypass_bits(Cabac &c, uint32_t v, int n)
+__device__ __noinline__ void cb_bypass(Cabac &c, int bin) { cb_bypass_inl(c, bin); }
+
+__device__ __noinline__ void cb_bypass_bits(Cabac &c, uint32_t v, int n)
 {
-    for (int i = n - 1; i >= 0; i--) cb_bypass(c, (v >> i) & 1);
+    for (int i = n - 1; i >= 0; i--) cb_bypass_inl(c, (v >> i) & 1);
 }
 
-__device__ __forceinline__ void cb_terminate(Cabac &c, int bin)
+__device__ __noinline__ void cb_terminate(Cabac &c, int bin)
 {
     c.range -= 2;
     if (bin) {
@@ -234,7 +238,7 @@ __device__ __forceinline__ void cb_terminate(Cabac &c, int bin)
     if (c.bits_left < 12) cb_write_out(c);
 }
 
-__device__ __forceinline__ uint32_t cb_finish(Cabac &c)
+__device__ __noinline__ uint32_t cb_finish(Cabac &c)
 {
     if (c.low >> (32 - c.bits_left)) {
         cb_byte(c, c.held + 1);
@@ -254,7 +258,7 @@ __device__ __forceinline__ uint32_t cb_finish(Cabac &c)
 }
 
 // ------------------------------------------------------------------------------------------------ residual_coding (lane 0)
-__device__ __forceinline__ void write_remaining(Cabac &c, int value, int rice)
+__device__ __noinline__ void write_remaining(Cabac &c, int value, int rice)
 {
     if (value < (3 << rice)) {
         const int len = value >> rice;
@@ -272,7 +276,7 @@ __device__ __forceinline__ void write_remaining(Cabac &c, int value, int rice)
 
 // lv: raster levels of the transform block in shared memory; masks: per sub-block (raster sub-block index)
 // 16-bit significance mask in diagonal scan order.  log2n is 4 (luma) or 3 (chroma); diagonal scan only.
-__device__ void residual_coding(Cabac &c, const int16_t *lv, const uint16_t *masks, int log2n, int c_idx)
+__device__ __noinline__ void residual_coding(Cabac &c, const int16_t *lv, const uint16_t *masks, int log2n, int c_idx)
 {
     const int n = 1 << log2n, sbw = n >> 2, nsb = sbw * sbw;
     const uint8_t *sbscan = sbw == 4 ? c_diag4 : c_diag2;
@@ -377,7 +381,7 @@ __device__ void residual_coding(Cabac &c, const int16_t *lv, const uint16_t *mas
     }
 }
 
-__device__ __forceinline__ void write_mvd(Cabac &c, int dx, int dy)
+__device__ __noinline__ void write_mvd(Cabac &c, int dx, int dy)
 {
     const int ax = abs(dx), ay = abs(dy);
     cb_bin(c, CX_MVD_GR0, ax > 0);

@@ -263,7 +263,7 @@ __device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8],
     return warp_sum(sum) >> 1;
 }
 
-__global__ void __launch_bounds__(128) k_inter(InterParams p)
+__device__ __forceinline__ void inter_body(const InterParams &p)
 {
     __shared__ WarpScratch scratch[4];
     const Geom &g = p.g;
@@ -523,6 +523,11 @@ __global__ void __launch_bounds__(128) k_inter(InterParams p)
         p.cus[cy * g.cuw + cx] = ci;
     }
 }
+
+__global__ void __launch_bounds__(128, 7) k_inter(InterParams p) { inter_body(p); }
+__global__ void __launch_bounds__(128, 8) k_inter_mb8(InterParams p) { inter_body(p); }
+__global__ void __launch_bounds__(128, 10) k_inter_mb10(InterParams p) { inter_body(p); }
+__global__ void __launch_bounds__(128, 12) k_inter_mb12(InterParams p) { inter_body(p); }
 
 // ================================================================================================ intra frame
 struct IntraScratch {

@@ -234,6 +234,8 @@ struct hb_encoder {
     RcState *rc_dev = nullptr;
     FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
     bool rc_have_idr = false;
+    int serial_entropy = 0;           // experiment knob: HB_ENTROPY_SERIAL=1 keeps CABAC on the main stream (no overlap)
+    int inter_variant = 0;            // experiment knob: HB_INTER_MB = 8 | 10 | 12 selects a launch-bounds variant of k_inter
     EntropyFrame *eframes_dev = nullptr;
     uint32_t *offsets_dev = nullptr;
     uint8_t *packed_dev = nullptr;
@@ -381,6 +383,8 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, upload_inter_constants(ctx->stream));
     HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    if (const char *v = getenv("HB_INTER_MB")) E->inter_variant = atoi(v);
+    if (const char *v = getenv("HB_ENTROPY_SERIAL")) E->serial_entropy = atoi(v);
     E->vps = make_vps(p);
     E->sps = make_sps(p, g.wc, g.hc);
     E->pps = make_pps(p);
@@ -583,7 +587,12 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     InterParams ip;
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
                     ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
-                    k_inter<<<nctu, 128, 0, st>>>(ip);
+                    switch (e->inter_variant) {
+                    case 8: k_inter_mb8<<<nctu, 128, 0, st>>>(ip); break;
+                    case 10: k_inter_mb10<<<nctu, 128, 0, st>>>(ip); break;
+                    case 12: k_inter_mb12<<<nctu, 128, 0, st>>>(ip); break;
+                    default: k_inter<<<nctu, 128, 0, st>>>(ip); break;
+                    }
                     HB_LAUNCHED(ctx);
                 }
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
@@ -610,7 +619,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             }
             // CABAC of this chunk on a side stream, overlapping the frame chain of the following chunks
             {
-                cudaStream_t q = e->st_entropy[e->next_entropy_stream];
+                cudaStream_t q = e->serial_entropy ? st : e->st_entropy[e->next_entropy_stream];
                 e->next_entropy_stream = (e->next_entropy_stream + 1) % kEntropyStreams;
                 HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[kMaxChunks + chunk], st));
                 HB_CUDA(ctx, cudaStreamWaitEvent(q, e->ev_chunk[kMaxChunks + chunk], 0));

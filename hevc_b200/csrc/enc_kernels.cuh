@@ -95,6 +95,9 @@ __global__ void k_ingest(IngestParams p);
 __global__ void k_border(Planes rec, Geom g);
 __global__ void k_coarse(CoarseParams p);
 __global__ void k_inter(InterParams p);
+__global__ void k_inter_mb8(InterParams p);
+__global__ void k_inter_mb10(InterParams p);
+__global__ void k_inter_mb12(InterParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_modes(ModeParams p);
 __global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr);
