@@ -1,6 +1,8 @@
 // Frame-level encoder kernels for sm_100a: ingest (+ quarter-resolution plane), hierarchical motion search,
 // fused inter prediction / transform / quantisation / reconstruction (one warp per 16x16 CU), wavefront intra
 // frames (one CTA per CTU row), border extension.  Bit-exact against oracle/hevc_encode.c.
+#include <cuda.h>
+
 #include "enc_kernels.cuh"
 
 namespace hb {
@@ -145,13 +147,39 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
 }
 
 // ================================================================================================ inter frame
-struct __align__(16) WarpScratch {
+struct __align__(128) WarpScratch {
+    pixel win[28][32];          // reference window, written by TMA (box 32 x 28 samples); 64-byte rows = aligned sample pairs
     pixel src[16][16];
-    pixel win[28][32];          // reference window; 64-byte rows so that sample pairs are aligned 32-bit words
     int16_t tmpT[16][24];       // horizontal-pass output, TRANSPOSED: [column][row], rows 0..22 used
     pixel pred[16][16];
     int16_t a[16][18], b[16][18];
+    unsigned long long mbar;    // mbarrier the TMA load completes on
 };
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers, PTX as in the CUDA 12.9 ISA
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (spins > (1u << 26)) __trap();       // a broken descriptor must fail loudly, not hang the device
+    }
+}
 
 struct MV { int x, y; };
 
@@ -263,7 +291,7 @@ __device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8],
     return warp_sum(sum) >> 1;
 }
 
-__device__ __forceinline__ void inter_body(const InterParams &p)
+__global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterParams p, const __grid_constant__ CUtensorMap ref_map)
 {
     __shared__ WarpScratch scratch[4];
     const Geom &g = p.g;
@@ -273,6 +301,9 @@ __device__ __forceinline__ void inter_body(const InterParams &p)
     if (cx >= g.cuw || cy >= g.cuh)
         return;
     WarpScratch &s = scratch[warp];
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
     const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth, maxv = (1 << bd) - 1;
     const FrameCtl ctl = *p.ctl;
     const int lambda = ctl.lambda;
@@ -304,17 +335,12 @@ __device__ __forceinline__ void inter_body(const InterParams &p)
         const int cost = warp_sum(sad) + mv_cost(lambda, c.x, c.y, pred.x, pred.y);
         if (cost < bcost) { bcost = cost; best = c; }
     }
-    // ---- stage the 28x28 reference window around the winner (covers +-2 integer, sub-sample taps)
+    // ---- stage the reference window around the winner with one TMA tile load per warp: box 32 x 28 samples of the padded
+    //      reconstruction plane (covers +-2 integer positions plus the 8-tap support; coordinates never leave the plane)
     const MV centre = best;
-    {
-        const pixel *r = p.ref.y + (ptrdiff_t)(y0 + (centre.y >> 2) - 6) * g.rec_stride + x0 + (centre.x >> 2) - 6;
-        for (int i = lane; i < 28 * 28; i += 32) {
-            const int wr = i / 28, wc = i % 28;
-            s.win[wr][wc] = r[(ptrdiff_t)wr * g.rec_stride + wc];
-        }
-        if (lane < 28) *reinterpret_cast<uint2 *>(&s.win[lane][28]) = make_uint2(0, 0);     // pad columns read as pair partners
-    }
-    __syncwarp();
+    if (lane == 0)
+        tma_load_2d(win_smem, &ref_map, x0 + (centre.x >> 2) - 6 + kPad, y0 + (centre.y >> 2) - 6 + kPad, bar, 28 * 32 * sizeof(pixel));
+    mbar_wait(bar, 0);
     // ---- integer stage 2: 5x5 square, SAD from shared memory
 #pragma unroll 1
     for (int dy = -2; dy <= 2; dy++)
@@ -524,10 +550,6 @@ __device__ __forceinline__ void inter_body(const InterParams &p)
     }
 }
 
-__global__ void __launch_bounds__(128, 7) k_inter(InterParams p) { inter_body(p); }
-__global__ void __launch_bounds__(128, 8) k_inter_mb8(InterParams p) { inter_body(p); }
-__global__ void __launch_bounds__(128, 10) k_inter_mb10(InterParams p) { inter_body(p); }
-__global__ void __launch_bounds__(128, 12) k_inter_mb12(InterParams p) { inter_body(p); }
 
 // ================================================================================================ intra frame
 struct IntraScratch {
