@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
 
 // ================================================================================================ inter frame
 struct __align__(128) WarpScratch {
-    pixel win[28][32];          // reference window, written by TMA (box 32 x 28 samples); 64-byte rows = aligned sample pairs
+    pixel win[28][40];          // reference window: 28 rows of 80 bytes, each written by one TMA bulk copy (cp.async.bulk)
     pixel src[16][16];
     int16_t tmpT[16][24];       // horizontal-pass output, TRANSPOSED: [column][row], rows 0..22 used
     pixel pred[16][16];
@@ -162,11 +162,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP): 16-byte aligned source / destination, size a multiple of 16
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -291,7 +295,7 @@ __device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8],
     return warp_sum(sum) >> 1;
 }
 
-__global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterParams p, const __grid_constant__ CUtensorMap ref_map)
+__global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterParams p)
 {
     __shared__ WarpScratch scratch[4];
     const Geom &g = p.g;
@@ -335,11 +339,16 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         const int cost = warp_sum(sad) + mv_cost(lambda, c.x, c.y, pred.x, pred.y);
         if (cost < bcost) { bcost = cost; best = c; }
     }
-    // ---- stage the reference window around the winner with one TMA tile load per warp: box 32 x 28 samples of the padded
-    //      reconstruction plane (covers +-2 integer positions plus the 8-tap support; coordinates never leave the plane)
+    // ---- stage the reference window around the winner with TMA bulk copies: 28 rows x 80 bytes, one copy per lane, all
+    //      completing on the warp's mbarrier.  The source is rounded down to 16 bytes (8 samples); `woff` is what remains.
+    //      Covers +-2 integer positions plus the 8-tap support; the padded plane keeps every row inside the allocation.
     const MV centre = best;
-    if (lane == 0)
-        tma_load_2d(win_smem, &ref_map, x0 + (centre.x >> 2) - 6 + kPad, y0 + (centre.y >> 2) - 6 + kPad, bar, 28 * 32 * sizeof(pixel));
+    const int wx = x0 + (centre.x >> 2) - 6, wy = y0 + (centre.y >> 2) - 6;
+    const int ax = wx & ~7, woff = wx - ax;
+    if (lane == 0) mbar_expect_tx(bar, 28 * 40 * sizeof(pixel));
+    __syncwarp();
+    if (lane < 28)
+        tma_bulk_load(win_smem + lane * 40 * sizeof(pixel), p.ref.y + (ptrdiff_t)(wy + lane) * g.rec_stride + ax, 40 * sizeof(pixel), bar);
     mbar_wait(bar, 0);
     // ---- integer stage 2: 5x5 square, SAD from shared memory
 #pragma unroll 1
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
             const MV m{centre.x + 4 * dx, centre.y + 4 * dy};
             const MV cm = clamp_mv(g, x0, y0, m);
             if (cm.x != m.x || cm.y != m.y) continue;
-            const pixel *w = &s.win[6 + dy + row][6 + dx + c0];
+            const pixel *w = &s.win[6 + dy + row][6 + dx + c0 + woff];
             int sad = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
             if (cost < bcost) { bcost = cost; best = m; }
         }
     // ---- sub-sample stages: SATD on the normative interpolation
-    const int wx0 = (centre.x >> 2) - 6, wy0 = (centre.y >> 2) - 6;     // window origin relative to the block position
+    const int wx0 = (centre.x >> 2) - 6 - woff, wy0 = (centre.y >> 2) - 6;     // window origin (sample [0][0]) relative to the block position
     int st[8], pv[8];        // source / prediction column segments: column lane >> 1, rows 8 * (lane & 1) + k
 #pragma unroll
     for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];

@@ -3,8 +3,6 @@
 #include <atomic>
 #include <memory>
 
-#include <cuda.h>
-
 #include "common.cuh"
 #include "enc_kernels.cuh"
 
@@ -236,7 +234,6 @@ struct hb_encoder {
     RcState *rc_dev = nullptr;
     FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
     bool rc_have_idr = false;
-    CUtensorMap ref_map[2];           // TMA descriptors of the two padded luma reconstruction planes (box 32 x 28)
     EntropyFrame *eframes_dev = nullptr;
     uint32_t *offsets_dev = nullptr;
     uint8_t *packed_dev = nullptr;
@@ -383,26 +380,6 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, upload_inter_constants(ctx->stream));
-    {   // tensor maps for the TMA window loads of k_inter; the driver entry point is resolved at run time (no libcuda link dependency)
-        typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        HB_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess)
-            return hb_fail(ctx, HB_ERR_CUDA, "%s", "cuTensorMapEncodeTiled is not available in this driver");
-        for (int k = 0; k < 2; k++) {
-            const cuuint64_t dims[2] = {(cuuint64_t)g.rec_stride, (cuuint64_t)(g.hc + 2 * kPad)};
-            const cuuint64_t strides[1] = {(cuuint64_t)g.rec_stride * sizeof(pixel)};
-            const cuuint32_t box[2] = {32, 28}, estr[2] = {1, 1};
-            const CUresult rc = reinterpret_cast<EncodeTiled>(fn)(&E->ref_map[k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, E->rec_base[k][0], dims, strides,
-                                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (rc != CUDA_SUCCESS)
-                return hb_fail(ctx, HB_ERR_CUDA, "%s", "cuTensorMapEncodeTiled failed for the reconstruction plane");
-        }
-    }
     HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     E->vps = make_vps(p);
     E->sps = make_sps(p, g.wc, g.hc);
@@ -606,7 +583,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     InterParams ip;
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
                     ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
-                    k_inter<<<nctu, 128, 0, st>>>(ip, e->ref_map[1 - e->cur]);
+                    k_inter<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                 }
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));

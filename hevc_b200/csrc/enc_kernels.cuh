@@ -1,8 +1,6 @@
 // Kernel parameter blocks shared between the encoder kernels (enc_frame.cu, enc_entropy.cu) and the host
 // driver (enc_host.cu).
 #pragma once
-#include <cuda.h>
-
 #include "enc_dev.cuh"
 
 enum { HB_FMT_YUV420P8 = 0, HB_FMT_P010 = 1, HB_FMT_YUV420P16 = 2 };
@@ -96,7 +94,7 @@ cudaError_t upload_inter_constants(cudaStream_t st);
 __global__ void k_ingest(IngestParams p);
 __global__ void k_border(Planes rec, Geom g);
 __global__ void k_coarse(CoarseParams p);
-__global__ void k_inter(const __grid_constant__ InterParams p, const __grid_constant__ CUtensorMap ref_map);
+__global__ void k_inter(const __grid_constant__ InterParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_modes(ModeParams p);
 __global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr);
