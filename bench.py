@@ -45,7 +45,8 @@ def workload_config(args, params, n_gpus):
                         f'{"Main10 HDR10" if params.bit_depth == 10 else "Main"} yuv420p8 source -> P010-depth encode',
             'frames_per_step': args.frames, 'keyint': params.keyint, 'crf': params.crf,
             'vbv_maxrate_kbps': params.vbv_maxrate_kbps, 'vbv_bufsize_kbit': params.vbv_bufsize_kbit,
-            'level_idc': params.level_idc, 'rate_control': 'constant QP from crf (qp_i, qp_p) = %s' % (str(args.qp),),
+            'level_idc': params.level_idc,
+            'rate_control': 'crf quality ceiling (qp_i, qp_p) = %s, VBV-constrained on the device (vbv-maxrate / vbv-bufsize)' % (str(args.qp),),
             'parallelism': f'{n_gpus} independent clips, one per GPU' if n_gpus > 1 else 'single GPU',
             'l2': 'inputs (%.1f GB/step) exceed the 126 MB L2' % (args.frames * params.width * params.height * 1.5 / 1e9)}
 
@@ -61,7 +62,7 @@ class ClockSampler:
             self.path = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False).name
             q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
                  'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '200'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

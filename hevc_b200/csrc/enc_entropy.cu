@@ -428,8 +428,13 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
                 s.ctx[i] = (uint8_t)(((mps ? pre - 64 : 63 - pre) << 1) | mps);
             }
         } else {
-            if (lane == 0)
-                while (!row_ready[row - 1]) __nanosleep(100);
+            if (lane == 0) {
+                unsigned ns = 200;          // back off: polling warps share the SM's issue slots with the coding warps
+                while (!row_ready[row - 1]) {
+                    __nanosleep(ns);
+                    ns = ns < 4000 ? ns * 2 : 4000;
+                }
+            }
             __syncwarp();
             __threadfence_block();
             for (int i = lane; i < kNumCtx; i += 32) s.ctx[i] = ctx_save[(row - 1) * kNumCtx + i];

@@ -289,6 +289,22 @@ int alloc_planes(hb_encoder *e, Planes *pl, int wc, int hc)
     return HB_OK;
 }
 
+// launch the WPP CABAC kernel for frames [first, first + count) of the current batch on the next side stream, ordered after
+// everything issued so far on the main stream
+int launch_entropy(hb_encoder *e, int first, int count, cudaEvent_t ev)
+{
+    hb_ctx *ctx = e->ctx;
+    cudaStream_t q = e->st_entropy[e->next_entropy_stream];
+    e->next_entropy_stream = (e->next_entropy_stream + 1) % kEntropyStreams;
+    HB_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+    HB_CUDA(ctx, cudaStreamWaitEvent(q, ev, 0));
+    EntropyParams ep;
+    ep.g = e->g; ep.frames = e->eframes_dev + first; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
+    k_entropy<<<count, 32 * 32, entropy_smem_bytes(e->g.ctuh), q>>>(ep);
+    HB_LAUNCHED(ctx);
+    return HB_OK;
+}
+
 size_t input_frame_bytes(const hb_enc_params &p, int fmt)
 {
     const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
@@ -376,7 +392,12 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     E->ev_chunk.resize((size_t)2 * kMaxChunks);
     for (auto &ev : E->ev_chunk) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
-    for (auto &q : E->st_entropy) HB_CUDA(ctx, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    {   // CABAC launches run at the highest stream priority: their CTAs need a whole SM each and would otherwise starve behind
+        // the thousands of pending k_inter CTAs of the frame chain
+        int lo = 0, hi = 0;
+        HB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (auto &q : E->st_entropy) HB_CUDA(ctx, cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, hi));
+    }
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, upload_inter_constants(ctx->stream));
@@ -605,19 +626,18 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.is_intra = idr;
                 k_modes<<<(ncu + 255) / 256, 256, 0, st>>>(mp);
                 HB_LAUNCHED(ctx);
+                if (idr) HB_TRY(launch_entropy(e, i, 1, e->ev_chunk[kMaxChunks + chunk]));
                 e->cur = 1 - e->cur;
                 e->frame_no++;
             }
-            // CABAC of this chunk on a side stream, overlapping the frame chain of the following chunks
-            {
-                cudaStream_t q = e->st_entropy[e->next_entropy_stream];
-                e->next_entropy_stream = (e->next_entropy_stream + 1) % kEntropyStreams;
-                HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[kMaxChunks + chunk], st));
-                HB_CUDA(ctx, cudaStreamWaitEvent(q, e->ev_chunk[kMaxChunks + chunk], 0));
-                EntropyParams ep;
-                ep.g = g; ep.frames = e->eframes_dev + c0; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
-                k_entropy<<<cn, 32 * 32, entropy_smem_bytes(g.ctuh), q>>>(ep);
-                HB_LAUNCHED(ctx);
+            // CABAC of this chunk on a side stream, overlapping the frame chain of the following chunks (key frames were
+            // already launched on their own right after their mode kernel: they carry ~8x the bins of a P frame)
+            for (int i0 = c0; i0 < c0 + cn;) {
+                if (is_idr[i0]) { i0++; continue; }
+                int i1 = i0;
+                while (i1 < c0 + cn && !is_idr[i1]) i1++;
+                HB_TRY(launch_entropy(e, i0, i1 - i0, e->ev_chunk[kMaxChunks + chunk]));
+                i0 = i1;
             }
         }
         k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
