@@ -402,21 +402,23 @@ __device__ __noinline__ void write_mvd(Cabac &c, int dx, int dy)
 }
 
 // ------------------------------------------------------------------------------------------------ WPP CABAC kernel
+// grid = (ceil(ctuh / kEntropyWarps), frames); CTA = kEntropyWarps warps, one CTU row per warp.  The CTAs are deliberately small
+// (4 warps, ~8 K registers, ~4 KB shared memory) so that they fit into the hole a retiring k_inter CTA leaves and really
+// overlap the frame chain.  Rows hand the context snapshot down through global memory (sync area of the frame); CTAs of a
+// grid are dispatched in index order, so the CTA owning row r-1 is always resident (or done) when row r waits for it.
 __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ EntropyWarpScratch ws[kEntropyWarps];
     const Geom &g = p.g;
-    EntropyWarpScratch *ws = reinterpret_cast<EntropyWarpScratch *>(smem_raw);
-    uint8_t *ctx_save = smem_raw + sizeof(EntropyWarpScratch) * kEntropyWarps;            // [ctuh][kNumCtx]
-    volatile int *row_ready = reinterpret_cast<volatile int *>(ctx_save + ((g.ctuh * kNumCtx + 15) & ~15));   // [ctuh]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const EntropyFrame fr = p.frames[blockIdx.x];
-    for (int r = threadIdx.x; r < g.ctuh; r += blockDim.x) row_ready[r] = 0;
-    __syncthreads();
+    const EntropyFrame fr = p.frames[blockIdx.y];
+    uint8_t *ctx_save = fr.ctx_save;                              // [ctuh][kNumCtx]
+    volatile int *row_ready = fr.row_ready;                       // [ctuh], zeroed before the launch
     EntropyWarpScratch &s = ws[warp];
     const int init_type = fr.is_intra ? 0 : 1;
 
-    for (int row = warp; row < g.ctuh; row += kEntropyWarps) {
+    const int row = blockIdx.x * kEntropyWarps + warp;
+    if (row < g.ctuh) {
         // ---- context initialisation: fresh for row 0 (or 1-CTU-wide pictures), else the snapshot of the row above
         if (row == 0 || g.ctuw < 2) {
             const int q = min(max(fr.ctl->qp, 0), 51);
@@ -429,15 +431,16 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
             }
         } else {
             if (lane == 0) {
-                unsigned ns = 200;          // back off: polling warps share the SM's issue slots with the coding warps
+                unsigned ns = 200, spins = 0;     // back off: polling warps share issue slots with the coding warps
                 while (!row_ready[row - 1]) {
                     __nanosleep(ns);
                     ns = ns < 4000 ? ns * 2 : 4000;
+                    if (++spins > (1u << 24)) __trap();       // ~1 minute: a lost hand-off must fail loudly, not hang the device
                 }
             }
             __syncwarp();
-            __threadfence_block();
-            for (int i = lane; i < kNumCtx; i += 32) s.ctx[i] = ctx_save[(row - 1) * kNumCtx + i];
+            __threadfence();
+            for (int i = lane; i < kNumCtx; i += 32) s.ctx[i] = __ldcg(ctx_save + (row - 1) * kNumCtx + i);
         }
         __syncwarp();
         Cabac c;
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
             if (x == 1) {       // snapshot for the row below (taken before the terminating bin, contexts only)
                 __syncwarp();
                 for (int i = lane; i < kNumCtx; i += 32) ctx_save[row * kNumCtx + i] = s.ctx[i];
-                __threadfence_block();
+                __threadfence();
                 __syncwarp();
                 if (lane == 0) row_ready[row] = 1;
             }

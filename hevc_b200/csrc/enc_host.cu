@@ -210,6 +210,8 @@ struct FrameSlot {
     int16_t *coefs = nullptr;
     uint8_t *rows = nullptr;
     uint32_t *row_len = nullptr;
+    uint8_t *ctx_save = nullptr;      // WPP hand-off area of the entropy stage
+    int *row_ready = nullptr;
     Planes keep{};            // verification copy of the reconstruction (unpadded strides = rec strides)
 };
 
@@ -230,7 +232,7 @@ struct hb_encoder {
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
     uint8_t *staging = nullptr;       // raw input frames
     size_t staging_bytes = 0;
-    int *progress = nullptr, *overflow = nullptr;
+    int *progress = nullptr, *overflow = nullptr, *row_ready_all = nullptr;
     RcState *rc_dev = nullptr;
     FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
     bool rc_have_idr = false;
@@ -300,7 +302,7 @@ int launch_entropy(hb_encoder *e, int first, int count, cudaEvent_t ev)
     HB_CUDA(ctx, cudaStreamWaitEvent(q, ev, 0));
     EntropyParams ep;
     ep.g = e->g; ep.frames = e->eframes_dev + first; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
-    k_entropy<<<count, 32 * 32, entropy_smem_bytes(e->g.ctuh), q>>>(ep);
+    k_entropy<<<dim3((e->g.ctuh + kEntropyWarps - 1) / kEntropyWarps, count), kEntropyWarps * 32, 0, q>>>(ep);
     HB_LAUNCHED(ctx);
     return HB_OK;
 }
@@ -349,6 +351,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
         HB_TRY(dev_alloc(E, &s.coefs, (size_t)ncu * kCuCoefs));
         HB_TRY(dev_alloc(E, &s.rows, (size_t)g.ctuh * E->row_cap));
         HB_TRY(dev_alloc(E, &s.row_len, (size_t)g.ctuh));
+        HB_TRY(dev_alloc(E, &s.ctx_save, (size_t)g.ctuh * kNumCtx));
         if (p.keep_recon || p.hash_sei) HB_TRY(alloc_planes(E, &s.keep, g.wc, g.hc));
     }
     for (int k = 0; k < 2; k++)
@@ -361,6 +364,8 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
             (void)w;
             if (c == 0) E->rec[k].y = origin; else if (c == 1) E->rec[k].u = origin; else E->rec[k].v = origin;
         }
+    HB_TRY(dev_alloc(E, &E->row_ready_all, (size_t)max_batch * g.ctuh));
+    for (int i = 0; i < max_batch; i++) E->slot[i].row_ready = E->row_ready_all + (size_t)i * g.ctuh;
     HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
     E->staging_bytes = (size_t)max_batch * input_frame_bytes(p, HB_PIX_P010);
@@ -401,7 +406,6 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, upload_inter_constants(ctx->stream));
-    HB_CUDA(ctx, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     E->vps = make_vps(p);
     E->sps = make_sps(p, g.wc, g.hc);
     E->pps = make_pps(p);
@@ -511,10 +515,11 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         for (int i = 0; i < n; i++) {
             FrameSlot &s = e->slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
-            ef[i].is_intra = is_idr[i]; ef[i].ctl = e->ctl_dev + i;
+            ef[i].is_intra = is_idr[i]; ef[i].ctl = e->ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
         }
         HB_CUDA(ctx, cudaMemcpyAsync(e->eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
         HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
+        HB_CUDA(ctx, cudaMemsetAsync(e->row_ready_all, 0, sizeof(int) * (size_t)n * g.ctuh, st));
         HB_CUDA(ctx, cudaEventRecord(e->ev_misc[0], st));
         HB_CUDA(ctx, cudaStreamWaitEvent(e->st_copy, e->ev_misc[0], 0));   // staging may still be read by the previous batch
         for (auto &q : e->st_entropy) HB_CUDA(ctx, cudaStreamWaitEvent(q, e->ev_misc[0], 0));

@@ -57,6 +57,8 @@ struct EntropyFrame {
     uint8_t *out;                        // [ctuh][row_cap]
     uint32_t *row_len;                   // [ctuh]
     const FrameCtl *ctl;                 // slice QP (context initialisation)
+    uint8_t *ctx_save;                   // [ctuh][kNumCtx] WPP context snapshots (after the 2nd CTU of each row)
+    int *row_ready;                      // [ctuh] snapshot-published flags, zeroed before the launch
     int is_intra;
 };
 
@@ -75,19 +77,13 @@ struct PackParams {
     uint32_t *offsets;                   // [n_frames * rows + 1] exclusive prefix of row lengths
 };
 
-constexpr int kEntropyWarps = 32;
+constexpr int kEntropyWarps = 4;
 struct EntropyWarpScratch {
     int16_t lv[kCuCoefs];
     uint16_t masks[24];
     uint8_t ctx[kNumCtx + 2];
 };
 static_assert(sizeof(EntropyWarpScratch) % 16 == 0, "per-warp scratch must keep 16-byte alignment");
-// dynamic shared memory of k_entropy: per-warp scratch, context snapshots per CTU row, row-ready flags
-inline size_t entropy_smem_bytes(int ctuh)
-{
-    return sizeof(EntropyWarpScratch) * kEntropyWarps + (((size_t)ctuh * kNumCtx + 15) & ~(size_t)15) + sizeof(int) * (size_t)ctuh;
-}
-
 // uploads the dp2a-packed interpolation taps into constant memory (call once per process/device before k_inter)
 cudaError_t upload_inter_constants(cudaStream_t st);
 
