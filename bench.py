@@ -107,7 +107,7 @@ def _model_segment(job):
     from hevc_b200.derive import B200Params  # noqa: F401  (package import check)
     from oracle import encoder_model as em
     enc = em.ModelEncoder(em.make_params(w, h, depth, qp_i=qp[0], qp_p=qp[1], keyint=keyint, hdr10=(depth == 10), hash_sei=False,
-                                         level_idc=153, vbv_maxrate_kbps=23520, vbv_bufsize_kbit=28224))
+                                         level_idc=153, vbv_maxrate_kbps=23520, vbv_bufsize_kbit=28224, rate_control=1))
     sh = depth - 8
     total = 0
     lw, cw = w * h, (w // 2) * (h // 2)
@@ -158,7 +158,7 @@ def run_reference(args):
     params = derive.derive_b200_params(clip_info(args.clip, args.frames))
     args.qp = crf_to_qp(params.crf)
     cores = os.cpu_count() or 1
-    per_worker = 2
+    per_worker = 4
     frames = host_sample_frames(args, params, min(args.frames, 2 * per_worker * 2))
     vals = []
     for step in range(args.warmup + args.steps):
