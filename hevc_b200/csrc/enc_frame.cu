@@ -775,6 +775,95 @@ __global__ void __launch_bounds__(256) k_intra(IntraParams p)
     }
 }
 
+// ================================================================================================ deblocking filter
+// H.265 8.7.2 restricted to this encoder's edges: CU boundaries (every 16 luma samples).  One thread per 4-line edge
+// segment (plus the two chroma lines it covers when the boundary strength is 2).  dir 0: vertical edges, dir 1: horizontal
+// edges; the horizontal pass is a second launch because it consumes the output of the vertical one.
+__constant__ uint8_t c_tc_table[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4,
+                                       5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
+__constant__ uint8_t c_beta_table[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24,
+                                         26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
+
+__device__ __forceinline__ void deblock_luma_segment(pixel *s, ptrdiff_t step, ptrdiff_t line, int beta, int tc, int maxv)
+{
+    int p[4][4], q[4][4];        // [line][distance from the edge]
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            p[k][i] = s[k * line - (i + 1) * step];
+            q[k][i] = s[k * line + i * step];
+        }
+    const int dp0 = abs(p[0][2] - 2 * p[0][1] + p[0][0]), dp3 = abs(p[3][2] - 2 * p[3][1] + p[3][0]);
+    const int dq0 = abs(q[0][2] - 2 * q[0][1] + q[0][0]), dq3 = abs(q[3][2] - 2 * q[3][1] + q[3][0]);
+    const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3;
+    if (dpq0 + dpq3 >= beta) return;
+    const bool strong0 = 2 * dpq0 < (beta >> 2) && abs(p[0][3] - p[0][0]) + abs(q[0][0] - q[0][3]) < (beta >> 3) &&
+                         abs(p[0][0] - q[0][0]) < ((5 * tc + 1) >> 1);
+    const bool strong3 = 2 * dpq3 < (beta >> 2) && abs(p[3][3] - p[3][0]) + abs(q[3][0] - q[3][3]) < (beta >> 3) &&
+                         abs(p[3][0] - q[3][0]) < ((5 * tc + 1) >> 1);
+    const bool strong = strong0 && strong3;
+    const bool dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int p0 = p[k][0], p1 = p[k][1], p2 = p[k][2], p3 = p[k][3], q0 = q[k][0], q1 = q[k][1], q2 = q[k][2], q3 = q[k][3];
+        pixel *l = s + k * line;
+        if (strong) {
+            l[-1 * step] = (pixel)clampd((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3, p0 - 2 * tc, p0 + 2 * tc);
+            l[-2 * step] = (pixel)clampd((p2 + p1 + p0 + q0 + 2) >> 2, p1 - 2 * tc, p1 + 2 * tc);
+            l[-3 * step] = (pixel)clampd((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3, p2 - 2 * tc, p2 + 2 * tc);
+            l[0] = (pixel)clampd((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3, q0 - 2 * tc, q0 + 2 * tc);
+            l[step] = (pixel)clampd((p0 + q0 + q1 + q2 + 2) >> 2, q1 - 2 * tc, q1 + 2 * tc);
+            l[2 * step] = (pixel)clampd((p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3, q2 - 2 * tc, q2 + 2 * tc);
+        } else {
+            int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (abs(delta) < 10 * tc) {
+                delta = clampd(delta, -tc, tc);
+                l[-1 * step] = (pixel)clampd(p0 + delta, 0, maxv);
+                l[0] = (pixel)clampd(q0 - delta, 0, maxv);
+                if (dep) l[-2 * step] = (pixel)clampd(p1 + clampd((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -(tc >> 1), tc >> 1), 0, maxv);
+                if (deq) l[step] = (pixel)clampd(q1 + clampd((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -(tc >> 1), tc >> 1), 0, maxv);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_deblock(DeblockParams p)
+{
+    const Geom &g = p.g;
+    const int total = g.cuw * g.cuh * 4;
+    const int qp = p.ctl->qp, bd = g.bit_depth, maxv = (1 << bd) - 1;
+    const int beta = c_beta_table[min(max(qp, 0), 51)] << (bd - 8);
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        const int cu = item >> 2, seg = item & 3, cx = cu % g.cuw, cy = cu / g.cuw;
+        if ((p.dir == 0 && cx == 0) || (p.dir == 1 && cy == 0)) continue;
+        const CuInfo q = p.cus[cu], pp = p.cus[p.dir == 0 ? cu - 1 : cu - g.cuw];
+        int bs = 0;
+        if (pp.pred_mode == 0 || q.pred_mode == 0) bs = 2;
+        else if (((pp.cbf | q.cbf) & 1) || abs(pp.mvx - q.mvx) >= 4 || abs(pp.mvy - q.mvy) >= 4) bs = 1;
+        if (!bs) continue;
+        const int tc = c_tc_table[min(max(qp + 2 * (bs - 1), 0), 53)] << (bd - 8);
+        pixel *y = p.rec.y + (size_t)cy * 16 * g.rec_stride + cx * 16;
+        if (p.dir == 0) deblock_luma_segment(y + (size_t)seg * 4 * g.rec_stride, 1, g.rec_stride, beta, tc, maxv);
+        else deblock_luma_segment(y + seg * 4, g.rec_stride, 1, beta, tc, maxv);
+        if (bs == 2) {
+            const int tcc = c_tc_table[min(max(chroma_qp(qp) + 2, 0), 53)] << (bd - 8);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                pixel *u = (c ? p.rec.v : p.rec.u) + (size_t)cy * 8 * g.recc_stride + cx * 8;
+                const ptrdiff_t step = p.dir == 0 ? 1 : g.recc_stride, line = p.dir == 0 ? g.recc_stride : 1;
+                for (int k = 2 * seg; k < 2 * seg + 2; k++) {
+                    pixel *l = u + k * line;
+                    const int p0 = l[-step], p1 = l[-2 * step], q0 = l[0], q1 = l[step];
+                    const int delta = clampd((((q0 - p0) << 2) + p1 - q1 + 4) >> 3, -tcc, tcc);
+                    l[-step] = (pixel)clampd(p0 + delta, 0, maxv);
+                    l[0] = (pixel)clampd(q0 - delta, 0, maxv);
+                }
+            }
+        }
+    }
+}
+
 cudaError_t upload_inter_constants(cudaStream_t st)
 {
     static const int8_t taps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};

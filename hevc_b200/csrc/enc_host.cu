@@ -130,7 +130,7 @@ std::vector<uint8_t> make_sps(const hb_enc_params &p, int wc, int hc)
     return b.bytes();
 }
 
-std::vector<uint8_t> make_pps(const hb_enc_params &)
+std::vector<uint8_t> make_pps(const hb_enc_params &p)
 {
     BitWriter b;
     b.ue(0); b.ue(0);
@@ -141,7 +141,8 @@ std::vector<uint8_t> make_pps(const hb_enc_params &)
     b.flag(false); b.flag(false); b.flag(false); b.flag(false);   // weighted x2, transquant bypass, tiles
     b.flag(true);                                                 // entropy_coding_sync_enabled
     b.flag(false);                                                // loop filter across slices
-    b.flag(true); b.flag(false); b.flag(true);                    // deblocking control: no override, disabled
+    b.flag(true); b.flag(false); b.flag(!p.deblock);              // deblocking control: no override, enabled per params
+    if (p.deblock) { b.se(0); b.se(0); }                          //   beta / tc offsets
     b.flag(false); b.flag(false); b.ue(0); b.flag(false); b.flag(false);
     b.trailing();
     return b.bytes();
@@ -613,6 +614,14 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     HB_LAUNCHED(ctx);
                 }
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
+                if (p.deblock) {
+                    DeblockParams dp;
+                    dp.g = g; dp.rec = rec; dp.cus = s.cus; dp.ctl = e->ctl_dev + i;
+                    for (dp.dir = 0; dp.dir < 2; dp.dir++) {
+                        k_deblock<<<hb_grid_for(ctx, (long long)ncu * 4, 256, 8), 256, 0, st>>>(dp);
+                        HB_LAUNCHED(ctx);
+                    }
+                }
                 {
                     const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
                     k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(rec, g);

@@ -43,6 +43,14 @@ struct IntraParams {
     int second_pass;                     // 1: run only when ctl->redo is set (first key frame of a stream under rate control)
 };
 
+struct DeblockParams {
+    Geom g;
+    Planes rec;
+    const CuInfo *cus;
+    const FrameCtl *ctl;
+    int dir;                             // 0 vertical edges, 1 horizontal edges
+};
+
 struct ModeParams {
     Geom g;
     const CuInfo *cus;
@@ -92,6 +100,7 @@ __global__ void k_border(Planes rec, Geom g);
 __global__ void k_coarse(CoarseParams p);
 __global__ void k_inter(const __grid_constant__ InterParams p);
 __global__ void k_intra(IntraParams p);
+__global__ void k_deblock(DeblockParams p);
 __global__ void k_modes(ModeParams p);
 __global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr);
 __global__ void k_rc_redo(RcState *rc, FrameCtl *ctl);

@@ -133,7 +133,8 @@ typedef struct hb_enc_params {
     int hash_sei;                      /* verification: emit MD5 decoded-picture-hash SEI (reads back every reconstruction) */
     int keep_recon;                    /* verification: keep every reconstruction / decision of the last batch readable */
     int rate_control;                  /* 0 = constant QP, 1 = VBV-constrained */
-    int reserved[8];
+    int deblock;                       /* in-loop deblocking filter (x265 default: on) */
+    int reserved[7];
 } hb_enc_params;
 
 typedef enum hb_pix_fmt { HB_PIX_YUV420P8 = 0, HB_PIX_P010 = 1, HB_PIX_YUV420P16 = 2 } hb_pix_fmt;

@@ -41,7 +41,7 @@ def make_params(width, height, bit_depth=8, qp_i=24, qp_p=26, keyint=60, fps=(30
     p.vui_colour = 1
     p.vbv_maxrate_kbps, p.vbv_bufsize_kbit = kw.get('vbv_maxrate_kbps', 2940), kw.get('vbv_bufsize_kbit', 3528)
     p.hash_sei = int(hash_sei)
-    p.deblock = int(kw.get('deblock', 0))
+    p.deblock = int(kw.get('deblock', 1))
     p.rate_control = int(kw.get('rate_control', 0))
     for k in ('aud', 'repeat_headers', 'hrd'):
         if k in kw:

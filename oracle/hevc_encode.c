@@ -401,6 +401,107 @@ static void encode_inter_frame(orc_encoder *e, int qp)
         }
 }
 
+/* ------------------------------------------------------------------ in-loop deblocking filter (H.265 8.7.2) */
+
+static const uint8_t k_tc_table[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4,
+                                       5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
+static const uint8_t k_beta_table[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24,
+                                         26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
+
+/* boundary strength between two neighbouring CUs (8.7.2.4): 2 intra, 1 coefficients or vectors apart by a sample, else 0 */
+static int boundary_strength(const orc_cu *p, const orc_cu *q)
+{
+    if (p->pred_mode == 0 || q->pred_mode == 0) return 2;
+    if ((p->cbf | q->cbf) & 1) return 1;
+    if (abs(p->mvx - q->mvx) >= 4 || abs(p->mvy - q->mvy) >= 4) return 1;
+    return 0;
+}
+
+/* one luma edge segment of 4 lines; s points at q0 of line 0; `step` = distance across the edge, `line` = distance between lines */
+static void deblock_luma_segment(pixel *s, ptrdiff_t step, ptrdiff_t line, int beta, int tc, int maxv)
+{
+#define P(i, k) ((int)s[(k) * line - ((i) + 1) * step])
+#define Q(i, k) ((int)s[(k) * line + (i) * step])
+    const int dp0 = abs(P(2, 0) - 2 * P(1, 0) + P(0, 0)), dp3 = abs(P(2, 3) - 2 * P(1, 3) + P(0, 3));
+    const int dq0 = abs(Q(2, 0) - 2 * Q(1, 0) + Q(0, 0)), dq3 = abs(Q(2, 3) - 2 * Q(1, 3) + Q(0, 3));
+    const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3, d = dpq0 + dpq3;
+    if (d >= beta) return;
+    const int strong0 = 2 * dpq0 < (beta >> 2) && abs(P(3, 0) - P(0, 0)) + abs(Q(0, 0) - Q(3, 0)) < (beta >> 3) &&
+                        abs(P(0, 0) - Q(0, 0)) < ((5 * tc + 1) >> 1);
+    const int strong3 = 2 * dpq3 < (beta >> 2) && abs(P(3, 3) - P(0, 3)) + abs(Q(0, 3) - Q(3, 3)) < (beta >> 3) &&
+                        abs(P(0, 3) - Q(0, 3)) < ((5 * tc + 1) >> 1);
+    const int strong = strong0 && strong3;
+    const int dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
+    for (int k = 0; k < 4; k++) {
+        const int p0 = P(0, k), p1 = P(1, k), p2 = P(2, k), p3 = P(3, k), q0 = Q(0, k), q1 = Q(1, k), q2 = Q(2, k), q3 = Q(3, k);
+        if (strong) {
+            s[k * line - 1 * step] = (pixel)clampi((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3, p0 - 2 * tc, p0 + 2 * tc);
+            s[k * line - 2 * step] = (pixel)clampi((p2 + p1 + p0 + q0 + 2) >> 2, p1 - 2 * tc, p1 + 2 * tc);
+            s[k * line - 3 * step] = (pixel)clampi((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3, p2 - 2 * tc, p2 + 2 * tc);
+            s[k * line + 0 * step] = (pixel)clampi((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3, q0 - 2 * tc, q0 + 2 * tc);
+            s[k * line + 1 * step] = (pixel)clampi((p0 + q0 + q1 + q2 + 2) >> 2, q1 - 2 * tc, q1 + 2 * tc);
+            s[k * line + 2 * step] = (pixel)clampi((p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3, q2 - 2 * tc, q2 + 2 * tc);
+        } else {
+            int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (abs(delta) < 10 * tc) {
+                delta = clampi(delta, -tc, tc);
+                s[k * line - 1 * step] = (pixel)clampi(p0 + delta, 0, maxv);
+                s[k * line + 0 * step] = (pixel)clampi(q0 - delta, 0, maxv);
+                if (dep) {
+                    const int dlt = clampi((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -(tc >> 1), tc >> 1);
+                    s[k * line - 2 * step] = (pixel)clampi(p1 + dlt, 0, maxv);
+                }
+                if (deq) {
+                    const int dlt = clampi((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -(tc >> 1), tc >> 1);
+                    s[k * line + 1 * step] = (pixel)clampi(q1 + dlt, 0, maxv);
+                }
+            }
+        }
+    }
+#undef P
+#undef Q
+}
+
+static void deblock_chroma_segment(pixel *s, ptrdiff_t step, ptrdiff_t line, int tc, int maxv, int lines)
+{
+    for (int k = 0; k < lines; k++) {
+        const int p0 = s[k * line - step], p1 = s[k * line - 2 * step], q0 = s[k * line], q1 = s[k * line + step];
+        const int delta = clampi((((q0 - p0) << 2) + p1 - q1 + 4) >> 3, -tc, tc);
+        s[k * line - step] = (pixel)clampi(p0 + delta, 0, maxv);
+        s[k * line] = (pixel)clampi(q0 - delta, 0, maxv);
+    }
+}
+
+/* all vertical CU edges of the picture first, then all horizontal ones (8.7.2); CU edges are the only transform /
+ * prediction edges in this encoder and all lie on the 8x8 luma (8-sample chroma) grid */
+static void deblock_frame(orc_encoder *e, plane *rec, int qp)
+{
+    const int bd = e->prm.bit_depth, maxv = (1 << bd) - 1;
+    const int beta = k_beta_table[clampi(qp, 0, 51)] << (bd - 8);
+    for (int dir = 0; dir < 2; dir++)
+        for (int cy = 0; cy < e->cuh; cy++)
+            for (int cx = 0; cx < e->cuw; cx++) {
+                if ((dir == 0 && cx == 0) || (dir == 1 && cy == 0)) continue;
+                const orc_cu *q = &e->cus[cy * e->cuw + cx], *p = dir == 0 ? q - 1 : q - e->cuw;
+                const int bs = boundary_strength(p, q);
+                if (!bs) continue;
+                const int tc = k_tc_table[clampi(qp + 2 * (bs - 1), 0, 53)] << (bd - 8);
+                pixel *y = rec[0].p + (size_t)cy * 16 * rec[0].stride + cx * 16;
+                for (int seg = 0; seg < 4; seg++) {
+                    if (dir == 0) deblock_luma_segment(y + (size_t)seg * 4 * rec[0].stride, 1, rec[0].stride, beta, tc, maxv);
+                    else deblock_luma_segment(y + seg * 4, rec[0].stride, 1, beta, tc, maxv);
+                }
+                if (bs == 2) {
+                    const int tcc = k_tc_table[clampi(chroma_qp(qp) + 2, 0, 53)] << (bd - 8);
+                    for (int c = 1; c < 3; c++) {
+                        pixel *u = rec[c].p + (size_t)cy * 8 * rec[c].stride + cx * 8;
+                        if (dir == 0) deblock_chroma_segment(u, 1, rec[c].stride, tcc, maxv, 8);
+                        else deblock_chroma_segment(u, rec[c].stride, 1, tcc, maxv, 8);
+                    }
+                }
+            }
+}
+
 /* ------------------------------------------------------------------ access unit */
 
 static void picture_md5(const orc_encoder *e, const plane *rec, uint8_t md5[3][16])
@@ -445,6 +546,7 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
         }
     }
     plane *rec = e->rec[e->cur];
+    if (p->deblock) deblock_frame(e, rec, qp);
     for (int c = 0; c < 3; c++) plane_extend(&rec[c]);
     orc_rc_update(&e->rc, idr, qp, est16);
 

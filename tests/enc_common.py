@@ -19,11 +19,11 @@ def b200_params(w, h, depth, keyint=4, hdr10=None):
     return p
 
 
-def model_params(p: B200Params, qp_i, qp_p, hash_sei, rate_control=False):
+def model_params(p: B200Params, qp_i, qp_p, hash_sei, rate_control=False, deblock=True):
     from oracle import encoder_model as em
     m = em.make_params(p.width, p.height, p.bit_depth, qp_i=qp_i, qp_p=qp_p, keyint=p.keyint, fps=(p.fps_num, p.fps_den),
                        hdr10=bool(p.hdr10), hash_sei=hash_sei, level_idc=p.level_idc, tier=p.tier,
-                       vbv_maxrate_kbps=p.vbv_maxrate_kbps, vbv_bufsize_kbit=p.vbv_bufsize_kbit, rate_control=int(rate_control))
+                       vbv_maxrate_kbps=p.vbv_maxrate_kbps, vbv_bufsize_kbit=p.vbv_bufsize_kbit, rate_control=int(rate_control), deblock=int(deblock))
     return m
 
 
@@ -32,10 +32,10 @@ def clip_frames(w, h, n, seed=1, noise=2.0):
     return [clip.frame(i) for i in range(n)]
 
 
-def run_model(p, frames8, qp_i, qp_p, hash_sei=False, force_idr_at=(), rate_control=False):
+def run_model(p, frames8, qp_i, qp_p, hash_sei=False, force_idr_at=(), rate_control=False, deblock=True):
     """-> (stream bytes, per-frame AUs, per-frame recon, per-frame (cus, coefs))"""
     from oracle import encoder_model as em
-    enc = em.ModelEncoder(model_params(p, qp_i, qp_p, hash_sei, rate_control))
+    enc = em.ModelEncoder(model_params(p, qp_i, qp_p, hash_sei, rate_control, deblock))
     aus, recs, decs, qps = [], [], [], []
     sh = p.bit_depth - 8
     for i, (y, u, v) in enumerate(frames8):

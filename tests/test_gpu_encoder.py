@@ -18,9 +18,9 @@ def ctx():
     c.close()
 
 
-def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True, rate_control=False):
+def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True, rate_control=False, deblock=True):
     from hevc_b200 import encoder as E
-    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True, rate_control=rate_control), max_batch=batch)
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True, rate_control=rate_control, deblock=deblock), max_batch=batch)
     stream, recs, decs = b'', [], []
     _gpu_encode.last_qps = []
     pos = 0
@@ -155,3 +155,14 @@ def test_4k60_hdr10_full_size(ctx):
     m_stream, m_aus, _, _ = ec.run_model(p, [(f0[:lw].reshape(2160, 3840), f0[lw:lw + cw].reshape(1080, 1920), f0[lw + cw:].reshape(1080, 1920))],
                                          qi, qp, hash_sei=True, rate_control=True)
     assert stream[:stats[0].bytes] == m_aus[0]
+
+
+def test_deblocking_off_also_matches(ctx):
+    w, h, n = 200, 120, 5
+    p = ec.b200_params(w, h, 8, keyint=4)
+    frames = ec.clip_frames(w, h, n, seed=9)
+    m_stream, _, m_recs, _ = ec.run_model(p, frames, 36, 38, hash_sei=True, deblock=False)
+    g_stream, g_recs, _ = _gpu_encode(ctx, p, frames, (36, 38), batch=8, deblock=False)
+    assert g_stream == m_stream
+    on_stream, _, _ = _gpu_encode(ctx, p, frames, (36, 38), batch=8, deblock=True)
+    assert on_stream != g_stream
