@@ -80,3 +80,44 @@ def batch_convert(input_dir: Path, output_dir: Path, max_workers: int = 2, progr
     for t in threads:
         t.join()
     return results
+
+
+def encode_clip_segmented(frames, n_frames: int, params, devices: Sequence[int], fmt: int = 0, max_batch: int = 32,
+                          c_params_kwargs: Optional[dict] = None) -> bytes:
+    """Encode one clip as independent closed-GOP segments spread round-robin over ``devices`` (one worker thread and one
+    encoder per device), then concatenate the Annex-B outputs in display order (BASELINE config 4).
+
+    ``frames``: uint8 array [n_frames, frame_bytes] in the ``hb_frames`` layout.  Each segment starts with an IDR and its
+    own parameter sets, so the concatenation is one valid stream.  Rate control restarts per segment (documented caveat)."""
+    import numpy as np
+
+    from . import _cabi
+    from .encoder import B200Encoder, to_c_params
+    segs = gop_segments(n_frames, params.keyint)
+    outputs: List[Optional[bytes]] = [None] * len(segs)
+    errors: List[BaseException] = []
+
+    def work(slot: int, device: int):
+        try:
+            ctx = _cabi.Context(device)
+            try:
+                for k in range(slot, len(segs), len(devices)):
+                    a, b = segs[k]
+                    enc = B200Encoder(ctx, to_c_params(params, **(c_params_kwargs or {})), max_batch=min(max_batch, b - a))
+                    try:
+                        outputs[k], _ = enc.encode(np.ascontiguousarray(frames[a:b]), b - a, fmt=fmt, force_idr=True)
+                    finally:
+                        enc.close()
+            finally:
+                ctx.close()
+        except BaseException as exc:      # surfaced to the caller below
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i, d), daemon=True) for i, d in enumerate(devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return b''.join(o for o in outputs if o is not None)

@@ -166,3 +166,24 @@ def test_deblocking_off_also_matches(ctx):
     assert g_stream == m_stream
     on_stream, _, _ = _gpu_encode(ctx, p, frames, (36, 38), batch=8, deblock=True)
     assert on_stream != g_stream
+
+
+def test_closed_gop_segments_concatenate(ctx):
+    """config 4 in miniature: segments encoded by independent encoders (two worker threads on device 0) concatenate into
+    one stream that the decoder plays through, IDR at every segment start"""
+    from hevc_b200 import batch, encoder as E
+    from oracle import fforacle
+    w, h, n = 192, 112, 14
+    p = ec.b200_params(w, h, 8, keyint=4)
+    frames = ec.clip_frames(w, h, n, seed=12)
+    buf = E.pack_yuv420p8(frames).reshape(n, -1)
+    stream = batch.encode_clip_segmented(buf, n, p, devices=[0, 0], c_params_kwargs={'hash_sei': True, 'qp': (28, 30), 'rate_control': False})
+    dec = fforacle.decode_hevc(stream, verify_hash=True)
+    assert len(dec) == n
+    types = [t for _, t, _ in fforacle.iter_nals(stream)]
+    assert types.count(19) == 4 and types.count(33) == 4          # 4 segments, each with its own IDR + SPS
+    # identical to one encoder running through the clip with the same GOP cadence (constant QP: no state crosses a GOP)
+    whole, _, _ = _gpu_encode(ctx, p, frames, (28, 30), batch=16, read_back=False)
+    assert [len(d[0]) for d in fforacle.decode_hevc(whole, verify_hash=True)] == [len(d[0]) for d in dec]
+    for a, b in zip(fforacle.decode_hevc(whole, verify_hash=False), dec):
+        assert all((a[c] == b[c]).all() for c in range(3))
