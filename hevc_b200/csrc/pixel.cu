@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
 {
     __shared__ uint8_t foot[PLANES][SC_FH][SC_FW];
     __shared__ short hp[PLANES][SC_FH][SC_TW];
+    __shared__ short xtap[SC_TW][4], ytap[SC_TH][4];     // per-tile copies of the phase taps (constant memory serialises on divergent phases)
+    __shared__ int xfirst[SC_TW], yfirst[SC_TH];
     const int tiles_x = (dw + SC_TW - 1) / SC_TW, tiles_y = (dh + SC_TH - 1) / SC_TH;
     const int tid = threadIdx.x;
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
@@ -220,6 +222,17 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
         const bool staged = fw <= SC_FW && fh <= SC_FH;
         const int shift = 20 - (out_depth - 8), maxv = (1 << out_depth) - 1;
         __syncthreads();
+        if (tid < tw) {
+            const int2 xp = xtab[ox0 + tid];
+            xfirst[tid] = xp.x;
+#pragma unroll
+            for (int t = 0; t < 4; t++) xtap[tid][t] = c_bicubic[xp.y][t];
+        } else if (tid >= 64 && tid < 64 + th) {
+            const int2 yp = ytab[oy0 + tid - 64];
+            yfirst[tid - 64] = yp.x;
+#pragma unroll
+            for (int t = 0; t < 4; t++) ytap[tid - 64][t] = c_bicubic[yp.y][t];
+        }
         if (staged) {
             for (int i = tid; i < fw * fh; i += 256) {
                 const int r = i / fw, cidx = i % fw;
@@ -231,14 +244,13 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
             __syncthreads();
             for (int i = tid; i < fh * tw; i += 256) {
                 const int r = i / tw, ox = i % tw;
-                const int2 xp = xtab[ox0 + ox];
-                const int base = xp.x - fx0;
+                const int base = xfirst[ox] - fx0;
 #pragma unroll
                 for (int p = 0; p < PLANES; p++) {
                     int acc = 128;
 #pragma unroll
                     for (int t = 0; t < 4; t++)
-                        acc += c_bicubic[xp.y][t] * foot[p][r][base + t];
+                        acc += xtap[ox][t] * foot[p][r][base + t];
                     hp[p][r][ox] = (short)(acc >> 8);
                 }
             }
@@ -252,10 +264,10 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
             for (int p = 0; p < PLANES; p++) {
                 int acc = 1 << (shift - 1);
                 if (staged) {
-                    const int base = yp.x - fy0;
+                    const int base = yfirst[oy] - fy0;
 #pragma unroll
                     for (int t = 0; t < 4; t++)
-                        acc += c_bicubic[yp.y][t] * hp[p][base + t][ox];
+                        acc += ytap[oy][t] * hp[p][base + t][ox];
                 } else {  // extreme down-scale ratios: read the source directly
                     const uint8_t *sp = p ? s1 : s0;
                     const int2 xp = xtab[ox0 + ox];

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128) k_transform(const int16_t *__restrict__ s
 {
     constexpr int PER_WARP = 32 / N, PAD = N + 2, L2 = ilog2c(N);
     __shared__ int16_t tile[4][PER_WARP][N][PAD];
+    __shared__ int16_t otile[INVERSE ? 4 : 1][INVERSE ? PER_WARP : 1][INVERSE ? N : 1][INVERSE ? PAD : 2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane / N, line = lane % N;
     const long long warps = (long long)gridDim.x * 4;
@@ -157,13 +158,24 @@ __global__ void __launch_bounds__(128) k_transform(const int16_t *__restrict__ s
                 inv_line<N, DST>(src + blk * N * N + line, N, &t[line][0], 1, shift1);
         }
         __syncwarp();
-        if (blk < n) {
-            if (!INVERSE)
-                fwd_line<N, DST>(&t[line][0], 1, dst + blk * N * N + line, N, shift2);
-            else
-                inv_line<N, DST>(&t[0][line], PAD, dst + blk * N * N + line * N, 1, shift2);
+        if constexpr (!INVERSE) {
+            if (blk < n) fwd_line<N, DST>(&t[line][0], 1, dst + blk * N * N + line, N, shift2);
+            __syncwarp();
+        } else {
+            // second inverse stage produces residual ROWS per thread: stage them in shared memory (second tile) and let the
+            // whole warp write the PER_WARP blocks back as contiguous 32-bit words instead of 2-byte strided stores
+            int16_t(*o)[PAD] = otile[warp][sub];
+            if (blk < n) inv_line<N, DST>(&t[0][line], PAD, &o[line][0], 1, shift2);
+            __syncwarp();
+            const long long remaining = (long long)n - base;
+            const int nblk = remaining < PER_WARP ? (int)remaining : PER_WARP;
+            uint32_t *g32 = reinterpret_cast<uint32_t *>(dst + base * N * N);
+            for (int w = lane; w < nblk * N * N / 2; w += 32) {
+                const int e = 2 * w, b = e / (N * N), r = (e % (N * N)) / N, c = e % N;
+                g32[w] = (uint32_t)(uint16_t)otile[warp][b][r][c] | ((uint32_t)(uint16_t)otile[warp][b][r][c + 1] << 16);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
