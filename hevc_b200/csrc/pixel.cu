@@ -234,16 +234,20 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
             for (int t = 0; t < 4; t++) ytap[tid - 64][t] = c_bicubic[yp.y][t];
         }
         if (staged) {
-            for (int i = tid; i < fw * fh; i += 256) {
-                const int r = i / fw, cidx = i % fw;
-                const int sy = min(max(fy0 + r, 0), sh - 1), sx = min(max(fx0 + cidx, 0), sw - 1);
-                foot[0][r][cidx] = s0[(size_t)sy * ss + sx];
-                if (PLANES == 2)
-                    foot[1][r][cidx] = s1[(size_t)sy * ss + sx];
+            // no run-time divisions in the tile loops: warps walk rows, lanes walk columns
+            for (int r = tid >> 5; r < fh; r += 8) {
+                const int sy = min(max(fy0 + r, 0), sh - 1);
+                for (int cidx = tid & 31; cidx < fw; cidx += 32) {
+                    const int sx = min(max(fx0 + cidx, 0), sw - 1);
+                    foot[0][r][cidx] = s0[(size_t)sy * ss + sx];
+                    if (PLANES == 2)
+                        foot[1][r][cidx] = s1[(size_t)sy * ss + sx];
+                }
             }
             __syncthreads();
-            for (int i = tid; i < fh * tw; i += 256) {
-                const int r = i / tw, ox = i % tw;
+            for (int i = tid; i < fh * SC_TW; i += 256) {
+                const int r = i >> 6, ox = i & (SC_TW - 1);
+                if (ox >= tw) continue;
                 const int base = xfirst[ox] - fx0;
 #pragma unroll
                 for (int p = 0; p < PLANES; p++) {
@@ -256,8 +260,9 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
             }
             __syncthreads();
         }
-        for (int i = tid; i < tw * th; i += 256) {
-            const int oy = i / tw, ox = i % tw;
+        for (int i = tid; i < SC_TW * SC_TH; i += 256) {
+            const int oy = i >> 6, ox = i & (SC_TW - 1);
+            if (ox >= tw || oy >= th) continue;
             const int2 yp = ytab[oy0 + oy];
             int outv[PLANES];
 #pragma unroll
@@ -357,7 +362,7 @@ int launch_scale(hb_ctx *ctx, const uint8_t *s0, const uint8_t *s1, int ss, int 
     rc = scale_table(ctx, sh, dh, &yt);
     if (rc) return rc;
     const int tiles = ((dw + SC_TW - 1) / SC_TW) * ((dh + SC_TH - 1) / SC_TH);
-    const int grid = tiles < ctx->sm_count * 8 ? tiles : ctx->sm_count * 8;
+    const int grid = tiles;      // one CTA per tile: the block scheduler overlaps the staging loads of one tile with the math of another
     if (s1)
         k_scale<2><<<grid, 256, 0, ctx->stream>>>(s0, s1, ss, sw, sh, dst, ds, dw, dh, xt, yt, out_depth, out_shift, step);
     else
