@@ -569,6 +569,7 @@ struct IntraScratch {
     int cost[35];
     int dc, best_mode;
     int e_nnz, e_slog, sbflag[24];
+    int16_t m16[16 * 16], m8[8 * 8];      // core transform matrices (H.265 8.6.4.2) for the matrix-form, all-threads transforms
 };
 
 // neighbour sample `i` of the (4N + 1)-sample reference array of an NxN block of CU (cx, cy), with the
@@ -604,6 +605,38 @@ __device__ __forceinline__ pixel gather_one(const pixel *plane, int stride, cons
     return __ldcg(plane + (ptrdiff_t)(y0 + py) * stride + x0 + px);
 }
 
+// entry (k, n) of the N-point core transform at run time (same folding as the compile-time odd_entry)
+__device__ int tmat_rt(int N, int k, int n)
+{
+    while (true) {
+        if (k == 0) return 64;
+        if (N == 2) return n == 0 ? 64 : -64;
+        if (k & 1) return odd_entry(N, k, n);
+        n = n < N / 2 ? n : N - 1 - n;
+        N >>= 1;
+        k >>= 1;
+    }
+}
+
+// one output sample of a separable transform stage in matrix form (exact integer sums, so identical to the butterflies):
+//   forward: out[i][j] = (sum_t M[i][t] * in[j][t] + add) >> shift          inverse: out[i][j] = clip16((sum_t M[t][j] * in[t][i] + add) >> shift)
+template <int N, int LD>
+__device__ __forceinline__ void fwd_stage(const int16_t *M, const int16_t *in, int16_t *out, int i, int j, int shift)
+{
+    int acc = shift > 0 ? 1 << (shift - 1) : 0;
+#pragma unroll
+    for (int t = 0; t < N; t++) acc += M[i * N + t] * in[j * LD + t];
+    out[i * LD + j] = (int16_t)(acc >> shift);
+}
+template <int N, int LD>
+__device__ __forceinline__ void inv_stage(const int16_t *M, const int16_t *in, int16_t *out, int i, int j, int shift)
+{
+    int acc = 1 << (shift - 1);
+#pragma unroll
+    for (int t = 0; t < N; t++) acc += M[t * N + j] * in[t * LD + i];
+    out[i * LD + j] = (int16_t)clampd(acc >> shift, -32768, 32767);
+}
+
 __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
 {
     const Geom &g = p.g;
@@ -616,7 +649,8 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
         const int k = tid - 96, pl = k / 33;
         s.cnb[pl][k % 33] = gather_one(pl ? p.rec.v : p.rec.u, g.recc_stride, g, cx, cy, 8, k % 33, bd);
     }
-    s.src[tid >> 4][tid & 15] = p.src.y[(size_t)(y0 + (tid >> 4)) * g.src_stride + x0 + (tid & 15)];
+    const bool act = tid < 256;      // threads that own one luma sample
+    if (act) s.src[tid >> 4][tid & 15] = p.src.y[(size_t)(y0 + (tid >> 4)) * g.src_stride + x0 + (tid & 15)];
     if (tid < 35) s.cost[tid] = 0;
     __syncthreads();
     if (tid < 65) s.flt[tid] = (pixel)intra_filtered(s.nb, 16, tid);
@@ -628,7 +662,7 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     }
     __syncthreads();
     // 35 modes x 16 sub-blocks: SATD accumulated per mode
-    for (int t = tid; t < 35 * 16; t += 256) {
+    for (int t = tid; t < 35 * 16; t += kIntraThreads) {
         const int mode = t >> 4, sb = t & 15, sx = (sb & 3) * 4, sy = (sb >> 2) * 4;
         const pixel *nbuf = intra_use_filter(4, mode) ? s.flt : s.nb;
         int d[4][4];
@@ -663,17 +697,23 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     const int mode = s.best_mode;
     int16_t *coef = p.coefs + (size_t)(cy * g.cuw + cx) * kCuCoefs;
     // ---- luma
-    const int py = tid >> 4, px = tid & 15;
-    const int pv = intra_sample(intra_use_filter(4, mode) ? s.flt : s.nb, 16, 4, mode, px, py, true, maxv, s.dc);
-    s.a[py][px] = (int16_t)((int)s.src[py][px] - pv);
+    const int py = (tid >> 4) & 15, px = tid & 15;
+    int pv = 0;
+    if (act) {
+        pv = intra_sample(intra_use_filter(4, mode) ? s.flt : s.nb, 16, 4, mode, px, py, true, maxv, s.dc);
+        s.a[py][px] = (int16_t)((int)s.src[py][px] - pv);
+    }
     __syncthreads();
-    if (tid < 16) fwd_line<16, false>(&s.a[tid][0], 1, &s.b[0][tid], 18, 3 + (bd - 8));
+    if (act) fwd_stage<16, 18>(s.m16, &s.a[0][0], &s.b[0][0], py, px, 3 + (bd - 8));
     __syncthreads();
-    if (tid < 16) fwd_line<16, false>(&s.b[tid][0], 1, &s.a[0][tid], 18, 10);
+    if (act) fwd_stage<16, 18>(s.m16, &s.b[0][0], &s.a[0][0], py, px, 10);
     __syncthreads();
     const QuantParam qy = p.ctl->qy;
-    const int lv = quant_one(s.a[py][px], qy);
-    coef[tid] = (int16_t)lv;
+    int lv = 0;
+    if (act) {
+        lv = quant_one(s.a[py][px], qy);
+        coef[tid] = (int16_t)lv;
+    }
     if (tid < 24) s.sbflag[tid] = 0;
     if (tid == 0) { s.e_nnz = 0; s.e_slog = 0; }
     const int cbf_y = __syncthreads_or(lv != 0);
@@ -684,15 +724,15 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     }
     int recv = pv;
     if (cbf_y) {
-        s.a[py][px] = (int16_t)dequant_one(lv, qy);
+        if (act) s.a[py][px] = (int16_t)dequant_one(lv, qy);
         __syncthreads();
-        if (tid < 16) inv_line<16, false>(&s.a[0][tid], 18, &s.b[tid][0], 1, 7);
+        if (act) inv_stage<16, 18>(s.m16, &s.a[0][0], &s.b[0][0], py, px, 7);
         __syncthreads();
-        if (tid < 16) inv_line<16, false>(&s.b[0][tid], 18, &s.a[tid][0], 1, 12 - (bd - 8));
+        if (act) inv_stage<16, 18>(s.m16, &s.b[0][0], &s.a[0][0], py, px, 12 - (bd - 8));
         __syncthreads();
-        recv = clampd(pv + s.a[py][px], 0, maxv);
+        if (act) recv = clampd(pv + s.a[py][px], 0, maxv);
     }
-    p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)recv;
+    if (act) p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)recv;
     __syncthreads();
     // ---- chroma (derived mode = luma mode; no smoothing, no edge filters): threads 0..127 = (plane, sample)
     int16_t(*ca)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.a[0][0]);
@@ -708,9 +748,9 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
         ca[cpl][cyy][cxx] = (int16_t)((int)sv - cpv);
     }
     __syncthreads();
-    if (tid < 16) fwd_line<8, false>(&ca[tid >> 3][tid & 7][0], 1, &cb[tid >> 3][0][tid & 7], 10, 2 + (bd - 8));
+    if (tid < 128) fwd_stage<8, 10>(s.m8, &ca[cpl][0][0], &cb[cpl][0][0], cyy, cxx, 2 + (bd - 8));
     __syncthreads();
-    if (tid < 16) fwd_line<8, false>(&cb[tid >> 3][tid & 7][0], 1, &ca[tid >> 3][0][tid & 7], 10, 9);
+    if (tid < 128) fwd_stage<8, 10>(s.m8, &cb[cpl][0][0], &ca[cpl][0][0], cyy, cxx, 9);
     __syncthreads();
     const QuantParam qc = p.ctl->qc;
     int clv = 0;
@@ -727,9 +767,9 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     const int cbf_v = __syncthreads_or(tid >= 64 && tid < 128 && clv != 0);
     if (tid < 128) ca[cpl][cyy][cxx] = (int16_t)dequant_one(clv, qc);
     __syncthreads();
-    if (tid < 16) inv_line<8, false>(&ca[tid >> 3][0][tid & 7], 10, &cb[tid >> 3][tid & 7][0], 1, 7);
+    if (tid < 128) inv_stage<8, 10>(s.m8, &ca[cpl][0][0], &cb[cpl][0][0], cyy, cxx, 7);
     __syncthreads();
-    if (tid < 16) inv_line<8, false>(&cb[tid >> 3][0][tid & 7], 10, &ca[tid >> 3][tid & 7][0], 1, 12 - (bd - 8));
+    if (tid < 128) inv_stage<8, 10>(s.m8, &cb[cpl][0][0], &ca[cpl][0][0], cyy, cxx, 12 - (bd - 8));
     __syncthreads();
     if (tid < 128)
         (cpl ? p.rec.v : p.rec.u)[(size_t)(cy * 8 + cyy) * g.recc_stride + cx * 8 + cxx] = (pixel)clampd(cpv + ca[cpl][cyy][cxx], 0, maxv);
@@ -746,13 +786,16 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
 }
 
 // one CTA per CTU row; row r may process CTU x once row r-1 has finished CTU x+1 (top-right dependency)
-__global__ void __launch_bounds__(256) k_intra(IntraParams p)
+__global__ void __launch_bounds__(kIntraThreads) k_intra(IntraParams p)
 {
     __shared__ IntraScratch s;
     const Geom &g = p.g;
     const int r = blockIdx.x;
     if (p.second_pass && !p.ctl->redo)
         return;
+    for (int i = threadIdx.x; i < 256; i += kIntraThreads) s.m16[i] = (int16_t)tmat_rt(16, i >> 4, i & 15);
+    for (int i = threadIdx.x; i < 64; i += kIntraThreads) s.m8[i] = (int16_t)tmat_rt(8, i >> 3, i & 7);
+    __syncthreads();
     for (int x = 0; x < g.ctuw; x++) {
         if (r > 0) {
             if (threadIdx.x == 0) {

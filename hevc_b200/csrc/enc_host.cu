@@ -595,14 +595,14 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     IntraParams ip;
                     ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
                     ip.ctl = e->ctl_dev + i; ip.second_pass = 0;
-                    k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+                    k_intra<<<g.ctuh, kIntraThreads, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
                         k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + i);
                         HB_LAUNCHED(ctx);
                         HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
                         ip.second_pass = 1;
-                        k_intra<<<g.ctuh, 256, 0, st>>>(ip);
+                        k_intra<<<g.ctuh, kIntraThreads, 0, st>>>(ip);
                         HB_LAUNCHED(ctx);
                     }
                     e->rc_have_idr = true;

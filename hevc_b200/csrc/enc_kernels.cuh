@@ -86,6 +86,7 @@ struct PackParams {
 };
 
 constexpr int kEntropyWarps = 4;
+constexpr int kIntraThreads = 576;        // k_intra CTA: the 35 x 16 mode-search tasks in one round; 256 threads own one luma sample each
 struct EntropyWarpScratch {
     int16_t lv[kCuCoefs];
     uint16_t masks[24];
