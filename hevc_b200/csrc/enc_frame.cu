@@ -295,7 +295,76 @@ __device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8],
     return warp_sum(sum) >> 1;
 }
 
-__global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterParams p)
+// Stage the 28-row x 40-sample luma window around integer position `centre` (quarter-sample vector) with TMA bulk copies, one
+// row per lane, all completing on the warp's mbarrier (first use of the barrier: phase 0).  The source is rounded down to
+// 16 bytes (8 samples); the remainder is returned.  Covers +-2 integer positions plus the 8-tap support; the padded plane
+// keeps every row inside the allocation.
+__device__ __forceinline__ int stage_window(const InterParams &p, uint32_t bar, uint32_t win_smem, int x0, int y0, MV centre, int lane)
+{
+    const Geom &g = p.g;
+    const int wx = x0 + (centre.x >> 2) - 6, wy = y0 + (centre.y >> 2) - 6;
+    const int ax = wx & ~7, woff = wx - ax;
+    if (lane == 0) mbar_expect_tx(bar, 28 * 40 * sizeof(pixel));
+    __syncwarp();
+    if (lane < 28)
+        tma_bulk_load(win_smem + lane * 40 * sizeof(pixel), p.ref.y + (ptrdiff_t)(wy + lane) * g.rec_stride + ax, 40 * sizeof(pixel), bar);
+    mbar_wait(bar, 0);
+    return woff;
+}
+
+__device__ __forceinline__ uint32_t pack_mv(MV m) { return (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16); }
+__device__ __forceinline__ MV unpack_mv(uint32_t v) { return MV{(int)(int16_t)(v & 0xffff), (int)(int16_t)(v >> 16)}; }
+
+// One merge-aware pass for one CU (warp-uniform): compare the CU's own vector with the vectors its five merge-candidate
+// neighbours (A1, B1, B0, A0, B2) held after the previous pass and with the zero vector (oracle/hevc_encode.c, "merge-aware
+// passes").  The window in `s.win` is centred on the own vector; candidates further than +-2 integer samples are not tried.
+__device__ __forceinline__ void merge_decide(const InterParams &p, WarpScratch &s, int cx, int cy, int lambda, int wx0, int wy0,
+                                             const int (&st)[8], int lane, MV &best, int &bsatd)
+{
+    const Geom &g = p.g;
+    const int x0 = cx * 16, y0 = cy * 16, idx = cy * g.cuw + cx;
+    const MV own = unpack_mv(p.mv_in[idx]);
+    MV cand[6];
+    bool ok[6];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int nx = cx + (k == 2 ? 1 : k == 1 ? 0 : -1), ny = cy + (k == 0 ? 0 : k == 3 ? 1 : -1);
+        ok[k] = nx >= 0 && ny >= 0 && nx < g.cuw && ny < g.cuh;
+        cand[k] = ok[k] ? unpack_mv(p.mv_in[ny * g.cuw + nx]) : MV{0, 0};
+    }
+    cand[5] = MV{0, 0};
+    ok[5] = true;
+    int own_bits = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (ok[k]) {
+            const int bts = (cand[k].x == own.x && cand[k].y == own.y) ? 0 : mv_bits1(own.x - cand[k].x) + mv_bits1(own.y - cand[k].y);
+            own_bits = min(own_bits, bts);
+        }
+    best = own;
+    bsatd = p.satd_in[idx];
+    int bcost = bsatd + ((lambda * (own_bits + 2)) >> 8) + 1;         // +1: ties go to a merge candidate
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        if (!ok[k]) continue;
+        const MV m = cand[k];
+        bool dup = m.x == own.x && m.y == own.y;
+#pragma unroll
+        for (int j = 0; j < k; j++) dup |= ok[j] && cand[j].x == m.x && cand[j].y == m.y;
+        if (dup) continue;
+        const MV cm = clamp_mv(g, x0, y0, m);
+        if (cm.x != m.x || cm.y != m.y) continue;
+        if (abs((m.x >> 2) - (own.x >> 2)) > 2 || abs((m.y >> 2) - (own.y >> 2)) > 2) continue;
+        int pv[8];
+        interp_cols(s, (m.x >> 2) - wx0, (m.y >> 2) - wy0, m.x & 3, m.y & 3, g.bit_depth, lane, pv);
+        const int sd = satd_cols(st, pv, lane);
+        const int cost = sd + ((lambda * 2) >> 8);
+        if (cost < bcost) { bcost = cost; best = m; bsatd = sd; }
+    }
+}
+
+// pass 1 of the motion search: per CU, integer candidates -> 5x5 -> half / quarter sample; writes the vector field and its SATD
+__global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterParams p)
 {
     __shared__ WarpScratch scratch[4];
     const Geom &g = p.g;
@@ -308,9 +377,8 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth, maxv = (1 << bd) - 1;
-    const FrameCtl ctl = *p.ctl;
-    const int lambda = ctl.lambda;
+    const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth;
+    const int lambda = p.ctl->lambda;
     const int row = lane >> 1, c0 = (lane & 1) * 8;
 
     // source block: registers (for SAD) + shared memory (for SATD)
@@ -339,17 +407,8 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         const int cost = warp_sum(sad) + mv_cost(lambda, c.x, c.y, pred.x, pred.y);
         if (cost < bcost) { bcost = cost; best = c; }
     }
-    // ---- stage the reference window around the winner with TMA bulk copies: 28 rows x 80 bytes, one copy per lane, all
-    //      completing on the warp's mbarrier.  The source is rounded down to 16 bytes (8 samples); `woff` is what remains.
-    //      Covers +-2 integer positions plus the 8-tap support; the padded plane keeps every row inside the allocation.
     const MV centre = best;
-    const int wx = x0 + (centre.x >> 2) - 6, wy = y0 + (centre.y >> 2) - 6;
-    const int ax = wx & ~7, woff = wx - ax;
-    if (lane == 0) mbar_expect_tx(bar, 28 * 40 * sizeof(pixel));
-    __syncwarp();
-    if (lane < 28)
-        tma_bulk_load(win_smem + lane * 40 * sizeof(pixel), p.ref.y + (ptrdiff_t)(wy + lane) * g.rec_stride + ax, 40 * sizeof(pixel), bar);
-    mbar_wait(bar, 0);
+    const int woff = stage_window(p, bar, win_smem, x0, y0, centre, lane);
     // ---- integer stage 2: 5x5 square, SAD from shared memory
 #pragma unroll 1
     for (int dy = -2; dy <= 2; dy++)
@@ -389,6 +448,85 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
                 const int cost = satd_cols(st, pv, lane) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
                 if (cost < bcost) { bcost = cost; best = m; }
             }
+    }
+    if (lane == 0) {
+        p.mv_out[cy * g.cuw + cx] = pack_mv(best);
+        p.satd_out[cy * g.cuw + cx] = bcost - mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+    }
+}
+
+// one merge-aware (Jacobi) pass over the motion field: mv_in / satd_in -> mv_out / satd_out
+__global__ void __launch_bounds__(128, 7) k_merge(const __grid_constant__ InterParams p)
+{
+    __shared__ WarpScratch scratch[4];
+    const Geom &g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw;
+    const int cx = 2 * tx + (warp & 1), cy = 2 * ty + (warp >> 1);
+    if (cx >= g.cuw || cy >= g.cuh)
+        return;
+    WarpScratch &s = scratch[warp];
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth;
+    const int lambda = p.ctl->lambda;
+    const int row = lane >> 1, c0 = (lane & 1) * 8;
+    *reinterpret_cast<uint4 *>(&s.src[row][c0]) = *reinterpret_cast<const uint4 *>(p.src.y + (size_t)(y0 + row) * g.src_stride + x0 + c0);
+    const MV own = unpack_mv(p.mv_in[cy * g.cuw + cx]);
+    const int woff = stage_window(p, bar, win_smem, x0, y0, own, lane);
+    const int wx0 = (own.x >> 2) - 6 - woff, wy0 = (own.y >> 2) - 6;
+    int st[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];
+    MV best;
+    int bsatd;
+    merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd);
+    if (lane == 0) {
+        p.mv_out[cy * g.cuw + cx] = pack_mv(best);
+        p.satd_out[cy * g.cuw + cx] = bsatd;
+    }
+}
+
+// last merge-aware pass + reconstruction: prediction, transform, quantisation and reconstruction of every CU of a P frame
+__global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterParams p)
+{
+    __shared__ WarpScratch scratch[4];
+    const Geom &g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw;
+    const int cx = 2 * tx + (warp & 1), cy = 2 * ty + (warp >> 1);
+    if (cx >= g.cuw || cy >= g.cuh)
+        return;
+    WarpScratch &s = scratch[warp];
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const int x0 = cx * 16, y0 = cy * 16, bd = g.bit_depth;
+    const int maxv = (1 << bd) - 1;
+    const FrameCtl ctl = *p.ctl;
+    const int lambda = ctl.lambda;
+    const int row = lane >> 1, c0 = (lane & 1) * 8;
+
+    // source block: registers (for SAD) + shared memory (for SATD)
+    int sp[8];
+    {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p.src.y + (size_t)(y0 + row) * g.src_stride + x0 + c0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { sp[2 * k] = w[k] & 0xffff; sp[2 * k + 1] = w[k] >> 16; }
+        *reinterpret_cast<uint4 *>(&s.src[row][c0]) = v;
+    }
+    const MV own = unpack_mv(p.mv_in[cy * g.cuw + cx]);
+    const int woff = stage_window(p, bar, win_smem, x0, y0, own, lane);
+    const int wx0 = (own.x >> 2) - 6 - woff, wy0 = (own.y >> 2) - 6;
+    int st[8], pv[8];        // source / prediction column segments: column lane >> 1, rows 8 * (lane & 1) + k
+#pragma unroll
+    for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];
+    MV best;
+    {
+        int bsatd;
+        merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd);
     }
     // ---- luma: predict, transform, quantise, reconstruct
     interp_cols(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane, pv);

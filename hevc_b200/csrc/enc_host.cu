@@ -231,6 +231,8 @@ struct hb_encoder {
     Planes rec[2];
     pixel *ds = nullptr;              // [max_batch + 1][dsh * dsw]
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
+    uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
+    int *satdf[2] = {nullptr, nullptr};
     uint8_t *staging = nullptr;       // raw input frames
     size_t staging_bytes = 0;
     int *progress = nullptr, *overflow = nullptr, *row_ready_all = nullptr;
@@ -369,6 +371,10 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     for (int i = 0; i < max_batch; i++) E->slot[i].row_ready = E->row_ready_all + (size_t)i * g.ctuh;
     HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
+    for (int k = 0; k < 2; k++) {
+        HB_TRY(dev_alloc(E, &E->mvf[k], (size_t)g.cuw * g.cuh));
+        HB_TRY(dev_alloc(E, &E->satdf[k], (size_t)g.cuw * g.cuh));
+    }
     E->staging_bytes = (size_t)max_batch * input_frame_bytes(p, HB_PIX_P010);
     HB_TRY(dev_alloc(E, &E->staging, E->staging_bytes));
     HB_TRY(dev_alloc(E, &E->progress, (size_t)g.ctuh));
@@ -610,6 +616,14 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     InterParams ip;
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
                     ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
+                    // motion search, then two merge-aware passes over the field (the second one inside k_inter)
+                    ip.mv_in = nullptr; ip.satd_in = nullptr; ip.mv_out = e->mvf[0]; ip.satd_out = e->satdf[0];
+                    k_me<<<nctu, 128, 0, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                    ip.mv_in = e->mvf[0]; ip.satd_in = e->satdf[0]; ip.mv_out = e->mvf[1]; ip.satd_out = e->satdf[1];
+                    k_merge<<<nctu, 128, 0, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                    ip.mv_in = e->mvf[1]; ip.satd_in = e->satdf[1]; ip.mv_out = nullptr; ip.satd_out = nullptr;
                     k_inter<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                 }

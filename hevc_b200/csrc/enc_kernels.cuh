@@ -31,6 +31,10 @@ struct InterParams {
     CuInfo *cus;
     int16_t *coefs;
     FrameCtl *ctl;                       // QP / lambda / quantisers chosen on the device; receives the size estimate
+    const uint32_t *mv_in;               // [cuh][cuw] motion field of the previous pass (x | y << 16, quarter samples) ...
+    const int *satd_in;                  // ... and the luma SATD of each vector
+    uint32_t *mv_out;
+    int *satd_out;
 };
 
 struct IntraParams {
@@ -99,6 +103,8 @@ cudaError_t upload_inter_constants(cudaStream_t st);
 __global__ void k_ingest(IngestParams p);
 __global__ void k_border(Planes rec, Geom g);
 __global__ void k_coarse(CoarseParams p);
+__global__ void k_me(const __grid_constant__ InterParams p);
+__global__ void k_merge(const __grid_constant__ InterParams p);
 __global__ void k_inter(const __grid_constant__ InterParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_deblock(DeblockParams p);

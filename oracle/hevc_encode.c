@@ -24,6 +24,7 @@ static const uint8_t k_chroma_qp[14] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 
 
 #define CME_RANGE 12      /* quarter-resolution search range (+-48 luma samples) */
 #define MV_OVERHANG 64    /* a predicted block may leave the picture by this many luma samples */
+#define MERGE_PASSES 2    /* merge-aware refinement passes over the motion field */
 
 typedef struct plane {
     pixel *base, *p;      /* p points at sample (0,0) inside the padded allocation */
@@ -40,6 +41,8 @@ struct orc_encoder {
     orc_cu *cus;
     int16_t *coefs;
     int16_t *cmv;                    /* [ctuh][ctuw][2] coarse vectors, quarter-resolution samples */
+    int16_t *mvf[2];                 /* [cuh][cuw][2] motion field, ping-pong between the merge-aware passes */
+    int32_t *satdf[2];               /* [cuh][cuw] SATD of that vector */
     int frame_no, poc, since_bp;
     uint8_t *payload;                /* CABAC sub-streams */
     size_t payload_cap;
@@ -88,6 +91,10 @@ orc_encoder *orc_enc_create(const orc_enc_params *p)
     e->cus = (orc_cu *)calloc((size_t)e->cuw * e->cuh, sizeof(orc_cu));
     e->coefs = (int16_t *)calloc((size_t)e->cuw * e->cuh * ORC_CU_COEFS, sizeof(int16_t));
     e->cmv = (int16_t *)calloc((size_t)e->ctuw * e->ctuh * 2, sizeof(int16_t));
+    for (int k = 0; k < 2; k++) {
+        e->mvf[k] = (int16_t *)calloc((size_t)e->cuw * e->cuh * 2, sizeof(int16_t));
+        e->satdf[k] = (int32_t *)calloc((size_t)e->cuw * e->cuh, sizeof(int32_t));
+    }
     e->payload_cap = (size_t)e->wc * e->hc * 3 + 65536;
     e->payload = (uint8_t *)malloc(e->payload_cap);
     e->row_off = (uint32_t *)calloc(e->ctuh, sizeof(uint32_t));
@@ -101,7 +108,7 @@ void orc_enc_destroy(orc_encoder *e)
     if (!e) return;
     for (int c = 0; c < 3; c++) { free(e->src[c].base); free(e->rec[0][c].base); free(e->rec[1][c].base); }
     free(e->ds[0].base); free(e->ds[1].base);
-    free(e->cus); free(e->coefs); free(e->cmv); free(e->payload); free(e->row_off); free(e->row_len);
+    free(e->cus); free(e->coefs); free(e->cmv); free(e->mvf[0]); free(e->mvf[1]); free(e->satdf[0]); free(e->satdf[1]); free(e->payload); free(e->row_off); free(e->row_len);
     free(e);
 }
 
@@ -337,8 +344,6 @@ static void encode_inter_frame(orc_encoder *e, int qp)
     coarse_search(e);
     for (int cy = 0; cy < e->cuh; cy++)
         for (int cx = 0; cx < e->cuw; cx++) {
-            orc_cu *cu = &e->cus[cy * e->cuw + cx];
-            int16_t *coef = e->coefs + (size_t)(cy * e->cuw + cx) * ORC_CU_COEFS;
             const int x0 = cx * 16, y0 = cy * 16, tx = cx >> 1, ty = cy >> 1;
             const pixel *src = e->src[0].p + (size_t)y0 * e->src[0].stride + x0;
             const int ss = e->src[0].stride;
@@ -383,6 +388,72 @@ static void encode_inter_frame(orc_encoder *e, int qp)
                         if (cost < bcost) { bcost = cost; best = m; }
                     }
             }
+            e->mvf[0][(cy * e->cuw + cx) * 2] = (int16_t)best.x;
+            e->mvf[0][(cy * e->cuw + cx) * 2 + 1] = (int16_t)best.y;
+            e->satdf[0][cy * e->cuw + cx] = (int32_t)(bcost - mv_cost(lambda, best.x, best.y, pred.x, pred.y));
+        }
+    /* Merge-aware passes (MERGE_PASSES Jacobi iterations).  Each CU compares its vector with the vectors its five merge-candidate
+     * neighbours (A1, B1, B0, A0, B2) held after the previous pass, and with the zero vector: taking a neighbour's vector costs
+     * a merge index (~2 bits) instead of a vector difference.  Reading the previous pass keeps every pass order-independent
+     * (data-parallel); the normative merge / AMVP derivation still happens afterwards on the final field. */
+    for (int pass = 0; pass < MERGE_PASSES; pass++) {
+        const int16_t *mvi = e->mvf[pass & 1];
+        const int32_t *sdi = e->satdf[pass & 1];
+        int16_t *mvo = e->mvf[(pass + 1) & 1];
+        int32_t *sdo = e->satdf[(pass + 1) & 1];
+        for (int cy = 0; cy < e->cuh; cy++)
+            for (int cx = 0; cx < e->cuw; cx++) {
+                const int x0 = cx * 16, y0 = cy * 16, idx = cy * e->cuw + cx;
+                const pixel *src = e->src[0].p + (size_t)y0 * e->src[0].stride + x0;
+                const int ss = e->src[0].stride;
+                const mv_t own = {mvi[idx * 2], mvi[idx * 2 + 1]};
+                static const int nbx[5] = {-1, 0, 1, -1, -1}, nby[5] = {0, -1, -1, 1, -1};
+                mv_t cand[6];
+                int ncand = 0;
+                for (int k = 0; k < 5; k++) {
+                    const int nx = cx + nbx[k], ny = cy + nby[k];
+                    if (nx < 0 || ny < 0 || nx >= e->cuw || ny >= e->cuh) continue;
+                    cand[ncand].x = mvi[(ny * e->cuw + nx) * 2];
+                    cand[ncand].y = mvi[(ny * e->cuw + nx) * 2 + 1];
+                    ncand++;
+                }
+                cand[ncand].x = 0; cand[ncand].y = 0; ncand++;
+                int own_bits = -1;
+                for (int k = 0; k < ncand; k++) {
+                    const int bts = (cand[k].x == own.x && cand[k].y == own.y) ? 0 : mv_bits1(own.x - cand[k].x) + mv_bits1(own.y - cand[k].y);
+                    if (own_bits < 0 || bts < own_bits) own_bits = bts;
+                }
+                mv_t best = own;
+                long bsatd = sdi[idx];
+                long bcost = bsatd + ((lambda * (own_bits + 2)) >> 8) + 1;      /* +1: ties go to a merge candidate */
+                pixel blk[256];
+                for (int k = 0; k < ncand; k++) {
+                    const mv_t m = cand[k];
+                    int dup = (m.x == own.x && m.y == own.y);
+                    for (int j = 0; j < k && !dup; j++) dup = cand[j].x == m.x && cand[j].y == m.y;
+                    if (dup) continue;
+                    const mv_t cm = clamp_mv(e, x0, y0, m);
+                    if (cm.x != m.x || cm.y != m.y) continue;
+                    if (abs((m.x >> 2) - (own.x >> 2)) > 2 || abs((m.y >> 2) - (own.y >> 2)) > 2) continue;   /* inside the staged window */
+                    predict_luma(e, &ref[0], x0, y0, m, blk);
+                    const long sd = orc_satd(src, ss, blk, 16, 16, 16);
+                    const long cost = sd + ((lambda * 2) >> 8);
+                    if (cost < bcost) { bcost = cost; best = m; bsatd = sd; }
+                }
+                mvo[idx * 2] = (int16_t)best.x; mvo[idx * 2 + 1] = (int16_t)best.y;
+                sdo[idx] = (int32_t)bsatd;
+            }
+    }
+    const int16_t *mvfinal = e->mvf[MERGE_PASSES & 1];
+    for (int cy = 0; cy < e->cuh; cy++)
+        for (int cx = 0; cx < e->cuw; cx++) {
+            orc_cu *cu = &e->cus[cy * e->cuw + cx];
+            int16_t *coef = e->coefs + (size_t)(cy * e->cuw + cx) * ORC_CU_COEFS;
+            const int x0 = cx * 16, y0 = cy * 16;
+            const pixel *src = e->src[0].p + (size_t)y0 * e->src[0].stride + x0;
+            const int ss = e->src[0].stride;
+            const mv_t best = {mvfinal[(cy * e->cuw + cx) * 2], mvfinal[(cy * e->cuw + cx) * 2 + 1]};
+            pixel blk[256];
             cu->pred_mode = 1; cu->intra_mode = 1; cu->skip = 0;
             cu->mvx = (int16_t)best.x; cu->mvy = (int16_t)best.y;
             /* reconstruct */
