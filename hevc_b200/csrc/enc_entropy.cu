@@ -147,413 +147,576 @@ __global__ void __launch_bounds__(256) k_modes(ModeParams p)
 }
 
 // ------------------------------------------------------------------------------------------------ CABAC engine (lane 0)
-struct Cabac {
-    uint32_t low, range;
-    int bits_left, buffered;
-    uint32_t held;
-    uint8_t *out;
-    uint32_t pos, cap;
-    uint8_t *ctx;          // shared memory, kNumCtx entries: (state << 1) | mps
-};
+// Per-warp scratch at file scope so that the (deliberately not inlined) coding primitives address it as shared memory.
+__shared__ EntropyWarpScratch g_ews[kEntropyWarps];
 
-__device__ __forceinline__ void cb_byte(Cabac &c, uint32_t v)
+// Arithmetic-coder state, passed and returned BY VALUE through the primitives so that it lives in registers
+// (a struct passed by reference to the non-inlined primitives sat in local memory: ~10 % of all executed instructions were
+// local loads / stores, all on the critical path of every bin -- profiles/round1_summary.md).  x: low; y: range | bits_left << 16.
+typedef uint2 CabacState;
+__device__ __forceinline__ CabacState cs_make(uint32_t low, uint32_t range, int bits_left) { return make_uint2(low, range | ((uint32_t)bits_left << 16)); }
+
+__device__ __forceinline__ void cb_byte(EntropyWarpScratch &o, uint32_t v)
 {
-    if (c.pos < c.cap) c.out[c.pos] = (uint8_t)v;
-    c.pos++;
+    if (o.pos < o.cap) o.out[o.pos] = (uint8_t)v;
+    o.pos++;
 }
 
-__device__ __noinline__ void cb_write_out(Cabac &c)
+// one byte leaves the coder (bits_left < 12); the byte-output state stays in shared memory, it is touched once per 8 bits
+__device__ __noinline__ CabacState cb_write_out(uint32_t low, uint32_t range, int bits_left, int w)
 {
-    const uint32_t lead = c.low >> (24 - c.bits_left);
-    c.bits_left += 8;
-    c.low &= 0xffffffffu >> c.bits_left;
+    EntropyWarpScratch &o = g_ews[w];
+    const uint32_t lead = low >> (24 - bits_left);
+    bits_left += 8;
+    low &= 0xffffffffu >> bits_left;
     if (lead == 0xff) {
-        c.buffered++;
-    } else if (c.buffered > 0) {
+        o.buffered++;
+    } else if (o.buffered > 0) {
         const uint32_t carry = lead >> 8;
-        cb_byte(c, c.held + carry);
-        c.held = lead & 0xff;
+        cb_byte(o, o.held + carry);
+        o.held = lead & 0xff;
         const uint32_t fill = (0xff + carry) & 0xff;
-        while (c.buffered > 1) { cb_byte(c, fill); c.buffered--; }
+        while (o.buffered > 1) { cb_byte(o, fill); o.buffered--; }
     } else {
-        c.buffered = 1;
-        c.held = lead;
+        o.buffered = 1;
+        o.held = lead;
     }
+    return cs_make(low, range, bits_left);
 }
 
 // Not inlined on purpose: the syntax code calls these from ~100 sites; inlining them made a 45 k-instruction kernel that
 // spent 57 % of its stall samples waiting for instruction fetch (profiles/round1_summary.md).
-__device__ __noinline__ void cb_bin(Cabac &c, int ctx, int bin)
+__device__ __noinline__ CabacState cb_bin(CabacState st, int w, int ctx, int bin)
 {
-    const uint32_t s = c.ctx[ctx];
-    const uint32_t st = s >> 1, mps = s & 1;
-    const uint32_t lps = c_range_lps[st][(c.range >> 6) & 3];
-    c.range -= lps;
+    uint8_t *cp = &g_ews[w].ctx[ctx];
+    const uint32_t s = *cp;
+    uint32_t low = st.x, range = st.y & 0xffffu;
+    int bits_left = (int)(st.y >> 16);
+    const uint32_t sidx = s >> 1, mps = s & 1;
+    const uint32_t lps = c_range_lps[sidx][(range >> 6) & 3];
+    range -= lps;
     if ((uint32_t)bin != mps) {
         const int nb = __clz(lps) - 23;             // renormalisation shift: lps in [6, 240] -> 1..6
-        c.low = (c.low + c.range) << nb;
-        c.range = lps << nb;
-        c.ctx[ctx] = (uint8_t)((c_next_lps[st] << 1) | (st == 0 ? 1 - mps : mps));
-        c.bits_left -= nb;
+        low = (low + range) << nb;
+        range = lps << nb;
+        *cp = (uint8_t)((c_next_lps[sidx] << 1) | (sidx == 0 ? 1 - mps : mps));
+        bits_left -= nb;
     } else {
-        c.ctx[ctx] = (uint8_t)(((st < 62 ? st + 1 : st) << 1) | mps);
-        if (c.range >= 256) return;
-        c.low <<= 1;
-        c.range <<= 1;
-        c.bits_left--;
+        *cp = (uint8_t)(((sidx < 62 ? sidx + 1 : sidx) << 1) | mps);
+        if (range >= 256) return cs_make(low, range, bits_left);
+        low <<= 1;
+        range <<= 1;
+        bits_left--;
     }
-    if (c.bits_left < 12) cb_write_out(c);
+    if (bits_left < 12) return cb_write_out(low, range, bits_left, w);
+    return cs_make(low, range, bits_left);
 }
 
-__device__ __forceinline__ void cb_bypass_inl(Cabac &c, int bin)
+// n <= 8 equiprobable bins at once (H.265 9.3.4.3.4 applied n times: low = low * 2^n + range * v)
+__device__ __forceinline__ CabacState cb_bypass_chunk(CabacState st, int w, uint32_t v, int n)
 {
-    c.low <<= 1;
-    if (bin) c.low += c.range;
-    c.bits_left--;
-    if (c.bits_left < 12) cb_write_out(c);
+    const uint32_t range = st.y & 0xffffu;
+    const int bits_left = (int)(st.y >> 16) - n;
+    const uint32_t low = (st.x << n) + range * v;
+    if (bits_left < 12) return cb_write_out(low, range, bits_left, w);
+    return cs_make(low, range, bits_left);
 }
 
-__device__ __noinline__ void cb_bypass(Cabac &c, int bin) { cb_bypass_inl(c, bin); }
+__device__ __noinline__ CabacState cb_bypass(CabacState st, int w, int bin) { return cb_bypass_chunk(st, w, bin ? 1u : 0u, 1); }
 
-__device__ __noinline__ void cb_bypass_bits(Cabac &c, uint32_t v, int n)
+// v: n bins, most significant first, n <= 32
+__device__ __noinline__ CabacState cb_bypass_bits(CabacState st, int w, uint32_t v, int n)
 {
-    for (int i = n - 1; i >= 0; i--) cb_bypass_inl(c, (v >> i) & 1);
+    while (n > 8) {
+        n -= 8;
+        st = cb_bypass_chunk(st, w, (v >> n) & 0xffu, 8);
+    }
+    if (n > 0) st = cb_bypass_chunk(st, w, v & ((1u << n) - 1), n);
+    return st;
 }
 
-__device__ __noinline__ void cb_terminate(Cabac &c, int bin)
+__device__ __noinline__ CabacState cb_terminate(CabacState st, int w, int bin)
 {
-    c.range -= 2;
+    uint32_t low = st.x, range = (st.y & 0xffffu) - 2;
+    int bits_left = (int)(st.y >> 16);
     if (bin) {
-        c.low += c.range;
-        c.low <<= 7;
-        c.range = 2 << 7;
-        c.bits_left -= 7;
-    } else if (c.range >= 256) {
-        return;
+        low += range;
+        low <<= 7;
+        range = 2 << 7;
+        bits_left -= 7;
+    } else if (range >= 256) {
+        return cs_make(low, range, bits_left);
     } else {
-        c.low <<= 1;
-        c.range <<= 1;
-        c.bits_left--;
+        low <<= 1;
+        range <<= 1;
+        bits_left--;
     }
-    if (c.bits_left < 12) cb_write_out(c);
+    if (bits_left < 12) return cb_write_out(low, range, bits_left, w);
+    return cs_make(low, range, bits_left);
 }
 
-__device__ __noinline__ uint32_t cb_finish(Cabac &c)
+__device__ __noinline__ uint32_t cb_finish(CabacState st, int w)
 {
-    if (c.low >> (32 - c.bits_left)) {
-        cb_byte(c, c.held + 1);
-        while (c.buffered > 1) { cb_byte(c, 0x00); c.buffered--; }
-        c.low -= 1u << (32 - c.bits_left);
+    EntropyWarpScratch &o = g_ews[w];
+    uint32_t low = st.x;
+    const int bits_left = (int)(st.y >> 16);
+    if (low >> (32 - bits_left)) {
+        cb_byte(o, o.held + 1);
+        while (o.buffered > 1) { cb_byte(o, 0x00); o.buffered--; }
+        low -= 1u << (32 - bits_left);
     } else {
-        if (c.buffered > 0) cb_byte(c, c.held);
-        while (c.buffered > 1) { cb_byte(c, 0xff); c.buffered--; }
+        if (o.buffered > 0) cb_byte(o, o.held);
+        while (o.buffered > 1) { cb_byte(o, 0xff); o.buffered--; }
     }
-    int n = 24 - c.bits_left + 1;
-    unsigned long long v = ((unsigned long long)(c.low >> 8) << 1) | 1;   // remaining bits + rbsp stop bit
+    int n = 24 - bits_left + 1;
+    unsigned long long v = ((unsigned long long)(low >> 8) << 1) | 1;   // remaining bits + rbsp stop bit
     const int pad = (8 - (n & 7)) & 7;
     v <<= pad;
     n += pad;
-    for (int i = n - 8; i >= 0; i -= 8) cb_byte(c, (uint32_t)(v >> i) & 0xff);
-    return c.pos;
+    for (int i = n - 8; i >= 0; i -= 8) cb_byte(o, (uint32_t)(v >> i) & 0xff);
+    return o.pos;
 }
 
-// ------------------------------------------------------------------------------------------------ residual_coding (lane 0)
-__device__ __noinline__ void write_remaining(Cabac &c, int value, int rice)
-{
-    if (value < (3 << rice)) {
-        const int len = value >> rice;
-        cb_bypass_bits(c, (1u << (len + 1)) - 2, len + 1);
-        cb_bypass_bits(c, value & ((1 << rice) - 1), rice);
-    } else {
-        int len = rice;
-        value -= 3 << rice;
-        while (value >= (1 << len)) { value -= 1 << len; len++; }
-        const int pre = 3 + len + 1 - rice;
-        cb_bypass_bits(c, (1u << pre) - 2, pre);
-        cb_bypass_bits(c, value, len);
-    }
-}
+#define CB_BIN(ctx, bin) st = cb_bin(st, w, (ctx), (bin))
+#define CB_BYPASS(bin) st = cb_bypass(st, w, (bin))
+#define CB_BITS(v, n) st = cb_bypass_bits(st, w, (v), (n))
 
-// lv: raster levels of the transform block in shared memory; masks: per sub-block (raster sub-block index)
-// 16-bit significance mask in diagonal scan order.  log2n is 4 (luma) or 3 (chroma); diagonal scan only.
-__device__ __noinline__ void residual_coding(Cabac &c, const int16_t *lv, const uint16_t *masks, int log2n, int c_idx)
+// ------------------------------------------------------------------------------------------------ residual coding
+// Two stages per coded CU.  Binarisation (lanes 0-23, one 4x4 sub-block each, lane = TU base + sub-block scan index): every
+// lane turns its sub-block into a list of bins in shared memory -- context index + value for context-coded bins, (count, bits)
+// for bypass runs.  All context selection (9.3.4.2.4 - 9.3.4.2.7) happens here, in parallel.  Coding (lane 0): walks the lists
+// in coding order through one tight arithmetic-coder loop.  Bin entry: bits 0-7 kind (context index, kBypass or kUnary),
+// bits 8-15 bin value / bin count, bits 16-31 bypass bits.
+constexpr uint32_t kBypass = 254, kUnary = 253;
+
+__device__ __forceinline__ uint32_t bin_ctx(int ctx, int bin) { return (uint32_t)ctx | ((uint32_t)bin << 8); }
+__device__ __forceinline__ uint32_t bin_bypass(uint32_t v, int n) { return kBypass | ((uint32_t)n << 8) | (v << 16); }
+
+// Binarise the three transform blocks of the CU whose levels sit in s.lv[buf] and whose masks are in s.masks.  Called by the
+// whole warp; returns (per lane, lane-uniform within a TU) the mask of coded sub-blocks in scan order for lanes of that TU.
+__device__ __forceinline__ void binarise_cu(EntropyWarpScratch &s, int buf, int lane)
 {
-    const int n = 1 << log2n, sbw = n >> 2, nsb = sbw * sbw;
-    const uint8_t *sbscan = sbw == 4 ? c_diag4 : c_diag2;
-    int last_sb = 0;
-    for (int i = nsb - 1; i >= 0; i--)
-        if (masks[sbscan[i]]) { last_sb = i; break; }
-    const int last_mask = masks[sbscan[last_sb]];
-    const int last_pos = 31 - __clz(last_mask);
-    {
-        const int sr = sbscan[last_sb], pr = c_diag4[last_pos];
-        const int px = ((sr % sbw) << 2) + (pr & 3), py = ((sr / sbw) << 2) + (pr >> 2);
-        const int gx = c_group_idx[px], gy = c_group_idx[py], cmax = c_group_idx[n - 1];
-        int off, shift;
-        if (c_idx == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
-        else { off = 15; shift = log2n - 2; }
-        for (int i = 0; i < gx; i++) cb_bin(c, CX_LAST_X + off + (i >> shift), 1);
-        if (gx < cmax) cb_bin(c, CX_LAST_X + off + (gx >> shift), 0);
-        for (int i = 0; i < gy; i++) cb_bin(c, CX_LAST_Y + off + (i >> shift), 1);
-        if (gy < cmax) cb_bin(c, CX_LAST_Y + off + (gy >> shift), 0);
-        if (gx > 3) cb_bypass_bits(c, px - c_min_in_group[gx], (gx - 2) >> 1);
-        if (gy > 3) cb_bypass_bits(c, py - c_min_in_group[gy], (gy - 2) >> 1);
-    }
-    int greater1_ctx = 1;
-    for (int i = last_sb; i >= 0; i--) {
-        const int sr = sbscan[i], xs = sr % sbw, ys = sr / sbw;
-        const int mask = masks[sr];
-        // coded_sub_block_flag of the right / below neighbours: coded (or inferred) sub-blocks are exactly those
-        // with a non-zero mask, plus the DC sub-block and the last one which are inferred 1
+    const int tu = lane < 16 ? 0 : lane < 20 ? 1 : 2, base = tu == 0 ? 0 : tu == 1 ? 16 : 20;
+    const int log2n = tu == 0 ? 4 : 3, n = 1 << log2n, sbw = n >> 2, nsb = sbw * sbw, c_idx = tu;
+    const int i = lane - base;                                   // scan index of this lane's sub-block
+    const bool lane_ok = lane < 24;
+    const int sr = lane_ok ? (sbw == 4 ? c_diag4[i] : c_diag2[i]) : 0;
+    const uint16_t *masks = s.masks + base;
+    const int16_t *lv = s.lv[buf] + (tu == 0 ? 0 : 256 + (tu - 1) * 64);
+    const int mask = lane_ok ? masks[sr] : 0;
+    const uint32_t coded_all = __ballot_sync(0xffffffffu, mask != 0);
+    const uint32_t tmask = (coded_all >> base) & ((1u << nsb) - 1);
+    const int last_sb = tmask ? 31 - __clz(tmask) : -1;
+    const bool active = lane_ok && i <= last_sb;
+    uint32_t *out = s.bins[lane_ok ? lane : 0];
+    int nb = 0;
+    const int xs = sr % sbw, ys = sr / sbw;
+    int cnt = 0, first_g1 = -1, a_first_g1 = 0, start = 15;
+    uint32_t signs = 0;
+    bool any_g1 = false;
+    if (active) {
+        const int last_sr = sbw == 4 ? c_diag4[last_sb] : c_diag2[last_sb];
+        // coded_sub_block_flag of the right / below neighbours: coded (or inferred) sub-blocks are exactly those with a
+        // non-zero mask, plus the DC sub-block and the last one which are inferred 1
         auto csbf_of = [&](int x, int y) -> int {
             if (x >= sbw || y >= sbw) return 0;
             const int r = y * sbw + x;
-            return masks[r] != 0 || r == 0 || r == sbscan[last_sb];
+            return masks[r] != 0 || r == 0 || r == last_sr;
         };
         const int right = csbf_of(xs + 1, ys), below = csbf_of(xs, ys + 1);
         int infer_dc = 0;
         if (i < last_sb && i > 0) {
-            cb_bin(c, CX_CSBF + ((right | below) ? 1 : 0) + (c_idx ? 2 : 0), mask != 0);
+            out[nb++] = bin_ctx(CX_CSBF + ((right | below) ? 1 : 0) + (c_idx ? 2 : 0), mask != 0);
             infer_dc = 1;
-            if (!mask) continue;
         }
-        const int start = i == last_sb ? last_pos : 15;
-        const int prev_csbf = right | (below << 1);
-        int abs_lv[16];
-        uint32_t signs = 0;
-        int cnt = 0;
-        for (int k = start; k >= 0; k--) {
-            const int pr = c_diag4[k], xp = pr & 3, yp = pr >> 2;
-            const int x = (xs << 2) + xp, y = (ys << 2) + yp;
-            const int sigf = (mask >> k) & 1;
-            const bool is_last = i == last_sb && k == last_pos;
-            if (!is_last && (k > 0 || !infer_dc)) {
-                int sig;
-                if (x == 0 && y == 0) {
-                    sig = 0;
-                } else {
-                    if (prev_csbf == 0) sig = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
-                    else if (prev_csbf == 1) sig = yp == 0 ? 2 : yp == 1 ? 1 : 0;
-                    else if (prev_csbf == 2) sig = xp == 0 ? 2 : xp == 1 ? 1 : 0;
-                    else sig = 2;
-                    if (c_idx == 0) {
-                        if (xs > 0 || ys > 0) sig += 3;
-                        sig += log2n == 3 ? 9 : 21;
+        if (mask || i == 0) {            // the DC sub-block is inferred coded: all-zero it still carries its 16 flags
+            const int last_pos = 31 - __clz(mask);
+            if (i == last_sb) start = last_pos;
+            const int prev_csbf = right | (below << 1);
+            for (int k = start; k >= 0; k--) {
+                const int pr = c_diag4[k], xp = pr & 3, yp = pr >> 2;
+                const int x = (xs << 2) + xp, y = (ys << 2) + yp;
+                const int sigf = (mask >> k) & 1;
+                const bool is_last = i == last_sb && k == last_pos;
+                if (!is_last && (k > 0 || !infer_dc)) {
+                    int sig;
+                    if (x == 0 && y == 0) {
+                        sig = 0;
                     } else {
-                        sig += log2n == 3 ? 9 : 12;
+                        if (prev_csbf == 0) sig = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+                        else if (prev_csbf == 1) sig = yp == 0 ? 2 : yp == 1 ? 1 : 0;
+                        else if (prev_csbf == 2) sig = xp == 0 ? 2 : xp == 1 ? 1 : 0;
+                        else sig = 2;
+                        if (c_idx == 0) {
+                            if (xs > 0 || ys > 0) sig += 3;
+                            sig += log2n == 3 ? 9 : 21;
+                        } else {
+                            sig += log2n == 3 ? 9 : 12;
+                        }
                     }
+                    out[nb++] = bin_ctx(CX_SIG + (c_idx == 0 ? sig : 27 + sig), sigf);
+                    if (sigf) infer_dc = 0;
                 }
-                cb_bin(c, CX_SIG + (c_idx == 0 ? sig : 27 + sig), sigf);
-                if (sigf) infer_dc = 0;
-            }
-            if (sigf) {
-                const int v = lv[y * n + x];
-                abs_lv[cnt++] = abs(v);
-                signs = (signs << 1) | (v < 0 ? 1u : 0u);
-            }
-        }
-        if (!cnt) continue;
-        int ctx_set = (i > 0 && c_idx == 0) ? 2 : 0;
-        if (i != last_sb && greater1_ctx == 0) ctx_set++;
-        greater1_ctx = 1;
-        int first_g1 = -1;
-        const int n_g1 = cnt < 8 ? cnt : 8;
-        for (int k = 0; k < n_g1; k++) {
-            const int g1 = abs_lv[k] > 1;
-            cb_bin(c, CX_GR1 + (ctx_set << 2) + greater1_ctx + (c_idx ? 16 : 0), g1);
-            if (g1) {
-                greater1_ctx = 0;
-                if (first_g1 < 0) first_g1 = k;
-            } else if (greater1_ctx > 0 && greater1_ctx < 3) {
-                greater1_ctx++;
-            }
-        }
-        if (first_g1 >= 0) cb_bin(c, CX_GR2 + ctx_set + (c_idx ? 4 : 0), abs_lv[first_g1] > 2);
-        cb_bypass_bits(c, signs, cnt);
-        int rice = 0;
-        for (int k = 0; k < cnt; k++) {
-            const int base = k < 8 ? (k == first_g1 ? 3 : 2) : 1;
-            if (abs_lv[k] >= base) {
-                write_remaining(c, abs_lv[k] - base, rice);
-                if (abs_lv[k] > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;
+                if (sigf) {
+                    const int v = lv[y * n + x];
+                    if (cnt < 8 && abs(v) > 1) {
+                        any_g1 = true;
+                        if (first_g1 < 0) { first_g1 = cnt; a_first_g1 = abs(v); }
+                    }
+                    cnt++;
+                    signs = (signs << 1) | (v < 0 ? 1u : 0u);
+                }
             }
         }
     }
+    // greater1 context set: +1 when the previously coded sub-block (next higher scan index with levels) ended with
+    // greater1Ctx == 0, i.e. had a level above 1 among its first eight
+    const uint32_t g1_all = __ballot_sync(0xffffffffu, any_g1);
+    if (active && cnt) {
+        const uint32_t tu_lanes = ((1u << nsb) - 1) << base;
+        const uint32_t higher = coded_all & tu_lanes & ~((2u << lane) - 1);
+        const bool prev_zero = higher && ((g1_all >> (__ffs(higher) - 1)) & 1);
+        const int ctx_set = ((i > 0 && c_idx == 0) ? 2 : 0) + (prev_zero ? 1 : 0);
+        int greater1_ctx = 1, seen = 0;
+        for (int k = start; k >= 0 && seen < 8; k--) {
+            if (!((mask >> k) & 1)) continue;
+            const int pr = c_diag4[k];
+            const int a = abs((int)lv[((ys << 2) + (pr >> 2)) * n + (xs << 2) + (pr & 3)]);
+            const int g1 = a > 1;
+            out[nb++] = bin_ctx(CX_GR1 + (ctx_set << 2) + greater1_ctx + (c_idx ? 16 : 0), g1);
+            if (g1) greater1_ctx = 0;
+            else if (greater1_ctx > 0 && greater1_ctx < 3) greater1_ctx++;
+            seen++;
+        }
+        // coeff_abs_level_greater2 (first level above 1 only), signs, then the remaining levels
+        if (first_g1 >= 0) out[nb++] = bin_ctx(CX_GR2 + ctx_set + (c_idx ? 4 : 0), a_first_g1 > 2);
+        out[nb++] = bin_bypass(signs, cnt);
+        int rice = 0;
+        seen = 0;
+        for (int k = start; k >= 0; k--) {
+            if (!((mask >> k) & 1)) continue;
+            const int pr = c_diag4[k];
+            const int a = abs((int)lv[((ys << 2) + (pr >> 2)) * n + (xs << 2) + (pr & 3)]);
+            const int basev = seen < 8 ? (seen == first_g1 ? 3 : 2) : 1;
+            if (a >= basev) {
+                int value = a - basev;
+                if (value < (3 << rice)) {
+                    out[nb++] = kUnary | ((uint32_t)(value >> rice) << 8);
+                    if (rice) out[nb++] = bin_bypass(value & ((1 << rice) - 1), rice);
+                } else {
+                    int len = rice;
+                    value -= 3 << rice;
+                    while (value >= (1 << len)) { value -= 1 << len; len++; }
+                    out[nb++] = kUnary | ((uint32_t)(3 + len - rice) << 8);
+                    out[nb++] = bin_bypass(value, len);
+                }
+                if (a > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;
+            }
+            seen++;
+        }
+    }
+    if (lane_ok) s.nbins[lane] = (uint8_t)nb;
 }
 
-__device__ __noinline__ void write_mvd(Cabac &c, int dx, int dy)
+// lane 0: code the bin lists of sub-blocks base + last_sb .. base of one transform block
+__device__ __noinline__ CabacState code_bins(CabacState st, int w, int base, int last_sb)
+{
+    EntropyWarpScratch &s = g_ews[w];
+    for (int i = last_sb; i >= 0; i--) {
+        const uint32_t *e = s.bins[base + i];
+        const int nb = s.nbins[base + i];
+        for (int k = 0; k < nb; k++) {
+            const uint32_t v = e[k], kind = v & 0xff, arg = (v >> 8) & 0xff;
+            if (kind < kUnary) CB_BIN((int)kind, (int)arg);
+            else if (kind == kBypass) { if (arg) CB_BITS(v >> 16, (int)arg); }
+            else CB_BITS((2u << arg) - 2, (int)arg + 1);          // arg ones, then a zero
+        }
+    }
+    return st;
+}
+
+// lane 0: last significant coefficient position of the block, then the sub-block lists
+__device__ __noinline__ CabacState residual_coding(CabacState st, int w, int base, int log2n, int c_idx)
+{
+    EntropyWarpScratch &s = g_ews[w];
+    const int n = 1 << log2n, sbw = n >> 2, nsb = sbw * sbw;
+    const uint8_t *sbscan = sbw == 4 ? c_diag4 : c_diag2;
+    const uint16_t *masks = s.masks + base;
+    int last_sb = 0;
+    for (int i = nsb - 1; i >= 0; i--)
+        if (masks[sbscan[i]]) { last_sb = i; break; }
+    const int last_pos = 31 - __clz((int)masks[sbscan[last_sb]]);
+    const int sr = sbscan[last_sb], pr = c_diag4[last_pos];
+    const int px = ((sr % sbw) << 2) + (pr & 3), py = ((sr / sbw) << 2) + (pr >> 2);
+    const int gx = c_group_idx[px], gy = c_group_idx[py], cmax = c_group_idx[n - 1];
+    int off, shift;
+    if (c_idx == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
+    else { off = 15; shift = log2n - 2; }
+    for (int i = 0; i < gx; i++) CB_BIN(CX_LAST_X + off + (i >> shift), 1);
+    if (gx < cmax) CB_BIN(CX_LAST_X + off + (gx >> shift), 0);
+    for (int i = 0; i < gy; i++) CB_BIN(CX_LAST_Y + off + (i >> shift), 1);
+    if (gy < cmax) CB_BIN(CX_LAST_Y + off + (gy >> shift), 0);
+    if (gx > 3) CB_BITS(px - c_min_in_group[gx], (gx - 2) >> 1);
+    if (gy > 3) CB_BITS(py - c_min_in_group[gy], (gy - 2) >> 1);
+    return code_bins(st, w, base, last_sb);
+}
+
+__device__ __noinline__ CabacState write_mvd(CabacState st, int w, int dx, int dy)
 {
     const int ax = abs(dx), ay = abs(dy);
-    cb_bin(c, CX_MVD_GR0, ax > 0);
-    cb_bin(c, CX_MVD_GR0, ay > 0);
-    if (ax > 0) cb_bin(c, CX_MVD_GR1, ax > 1);
-    if (ay > 0) cb_bin(c, CX_MVD_GR1, ay > 1);
+    CB_BIN(CX_MVD_GR0, ax > 0);
+    CB_BIN(CX_MVD_GR0, ay > 0);
+    if (ax > 0) CB_BIN(CX_MVD_GR1, ax > 1);
+    if (ay > 0) CB_BIN(CX_MVD_GR1, ay > 1);
     for (int comp = 0; comp < 2; comp++) {
         const int a = comp ? ay : ax, neg = (comp ? dy : dx) < 0;
         if (a == 0) continue;
         if (a > 1) {
             int v = a - 2, k = 1;
-            while (v >= (1 << k)) { cb_bypass(c, 1); v -= 1 << k; k++; }
-            cb_bypass(c, 0);
-            cb_bypass_bits(c, v, k);
+            while (v >= (1 << k)) { CB_BYPASS(1); v -= 1 << k; k++; }
+            CB_BYPASS(0);
+            CB_BITS(v, k);
         }
-        cb_bypass(c, neg);
+        CB_BYPASS(neg);
     }
+    return st;
 }
 
 // ------------------------------------------------------------------------------------------------ WPP CABAC kernel
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stage the CU records of CTU x of this row (and the syntax of the two CUs above it) into ring slot x % 3
+__device__ __forceinline__ void stage_ctu(EntropyWarpScratch &s, const EntropyFrame &fr, const Geom &g, int row, int x, int lane)
+{
+    if (x >= g.ctuw) return;
+    const int slot = x % 3;
+    if (lane < 4) {
+        const int cx = 2 * x + (lane & 1), cy = 2 * row + (lane >> 1);
+        if (cx < g.cuw && cy < g.cuh) {
+            cp_async8(&s.cu[slot][lane].info, fr.cus + cy * g.cuw + cx);
+            cp_async8(&s.cu[slot][lane].syn, fr.syn + cy * g.cuw + cx);
+        }
+    } else if (lane < 6) {
+        const int cx = 2 * x + (lane - 4), cy = 2 * row - 1;
+        if (cx < g.cuw && cy >= 0) cp_async8(&s.above[slot][lane - 4], fr.syn + cy * g.cuw + cx);
+    }
+}
+
+// first coded CU after (x, k) within CTU x and the (already staged) CTU x + 1; -1 if none
+__device__ __forceinline__ int next_coded_cu(const EntropyWarpScratch &s, const Geom &g, int row, int x, int k)
+{
+    for (int t = k + 1; t < 8; t++) {
+        const int xx = x + (t >> 2), kk = t & 3;
+        if (xx >= g.ctuw) break;
+        const int cx = 2 * xx + (kk & 1), cy = 2 * row + (kk >> 1);
+        if (cx >= g.cuw || cy >= g.cuh) continue;
+        if (s.cu[xx % 3][kk].info.cbf) return cy * g.cuw + cx;
+    }
+    return -1;
+}
+
 // grid = (ceil(ctuh / kEntropyWarps), frames); CTA = kEntropyWarps warps, one CTU row per warp.  The CTAs are deliberately small
-// (4 warps, ~8 K registers, ~4 KB shared memory) so that they fit into the hole a retiring k_inter CTA leaves and really
-// overlap the frame chain.  Rows hand the context snapshot down through global memory (sync area of the frame); CTAs of a
-// grid are dispatched in index order, so the CTA owning row r-1 is always resident (or done) when row r waits for it.
+// so that they fit beside the resident motion-search CTAs and really overlap the frame chain.  Rows hand the context snapshot
+// down through global memory (sync area of the frame); CTAs of a grid are dispatched in index order, so the CTA owning row
+// r-1 is always resident (or done) when row r waits for it.  Nothing on the per-CU path waits for global memory: CU records
+// are staged two CTUs ahead and levels one coded CU ahead with cp.async.
 __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
 {
-    __shared__ EntropyWarpScratch ws[kEntropyWarps];
     const Geom &g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const EntropyFrame fr = p.frames[blockIdx.y];
     uint8_t *ctx_save = fr.ctx_save;                              // [ctuh][kNumCtx]
     volatile int *row_ready = fr.row_ready;                       // [ctuh], zeroed before the launch
-    EntropyWarpScratch &s = ws[warp];
+    EntropyWarpScratch &s = g_ews[warp];
+    const int w = warp;
     const int init_type = fr.is_intra ? 0 : 1;
 
     const int row = blockIdx.x * kEntropyWarps + warp;
-    if (row < g.ctuh) {
-        // ---- context initialisation: fresh for row 0 (or 1-CTU-wide pictures), else the snapshot of the row above
-        if (row == 0 || g.ctuw < 2) {
-            const int q = min(max(fr.ctl->qp, 0), 51);
-            for (int i = lane; i < kNumCtx; i += 32) {
-                const int v = c_ctx_init[init_type][i];
-                const int m = (v >> 4) * 5 - 45, n = ((v & 15) << 3) - 16;
-                const int pre = min(max(((m * q) >> 4) + n, 1), 126);
-                const int mps = pre > 63;
-                s.ctx[i] = (uint8_t)(((mps ? pre - 64 : 63 - pre) << 1) | mps);
+    if (row >= g.ctuh) return;
+    stage_ctu(s, fr, g, row, 0, lane);
+    stage_ctu(s, fr, g, row, 1, lane);
+    cp_async_commit();
+    // ---- context initialisation: fresh for row 0 (or 1-CTU-wide pictures), else the snapshot of the row above
+    if (row == 0 || g.ctuw < 2) {
+        const int q = min(max(fr.ctl->qp, 0), 51);
+        for (int i = lane; i < kNumCtx; i += 32) {
+            const int v = c_ctx_init[init_type][i];
+            const int m = (v >> 4) * 5 - 45, n = ((v & 15) << 3) - 16;
+            const int pre = min(max(((m * q) >> 4) + n, 1), 126);
+            const int mps = pre > 63;
+            s.ctx[i] = (uint8_t)(((mps ? pre - 64 : 63 - pre) << 1) | mps);
+        }
+    } else {
+        if (lane == 0) {
+            unsigned ns = 100, spins = 0;     // back off: polling warps share issue slots with the coding warps
+            while (!row_ready[row - 1]) {
+                __nanosleep(ns);
+                ns = ns < 1600 ? ns * 2 : 1600;
+                if (++spins > (1u << 25)) __trap();       // ~1 minute: a lost hand-off must fail loudly, not hang the device
             }
-        } else {
-            if (lane == 0) {
-                unsigned ns = 200, spins = 0;     // back off: polling warps share issue slots with the coding warps
-                while (!row_ready[row - 1]) {
-                    __nanosleep(ns);
-                    ns = ns < 4000 ? ns * 2 : 4000;
-                    if (++spins > (1u << 24)) __trap();       // ~1 minute: a lost hand-off must fail loudly, not hang the device
+        }
+        __syncwarp();
+        __threadfence();
+        for (int i = lane; i < kNumCtx; i += 32) s.ctx[i] = __ldcg(ctx_save + (row - 1) * kNumCtx + i);
+    }
+    unsigned long long t_start = 0;
+    if (fr.trace && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    CabacState st = cs_make(0, 510, 23);
+    if (lane == 0) { s.buffered = 0; s.held = 0xff; s.out = fr.out + (size_t)row * p.row_cap; s.pos = 0; s.cap = p.row_cap; }
+    cp_async_wait<0>();
+    __syncwarp();
+
+    int pf_idx = -1, pf_buf = 0;          // CU whose levels are in flight / ready in s.lv[pf_buf]
+    bool pf_before_stage = false;         // that copy was committed before the newest CTU staging group
+    int left_skip0 = 0, left_skip1 = 0;   // skip flags of the two CUs left of the CTU (lane 0)
+    for (int x = 0; x < g.ctuw; x++) {
+        const int slot = x % 3;
+        // CTU x and x + 1 are staged (the wait at the end of the previous iteration); start on x + 2
+        stage_ctu(s, fr, g, row, x + 2, lane);
+        cp_async_commit();
+        pf_before_stage = true;
+        const int cx0 = 2 * x, cy0 = 2 * row;
+        for (int k = 0; k < 4; k++) {
+            const int cx = cx0 + (k & 1), cy = cy0 + (k >> 1);
+            if (cx >= g.cuw || cy >= g.cuh) continue;
+            const int idx = cy * g.cuw + cx;
+            const CuInfo cu = s.cu[slot][k].info;
+            const CuSyntax sy = s.cu[slot][k].syn;
+            // ---- all lanes: levels of this CU (normally already in flight), sub-block masks, next prefetch, binarisation
+            if (cu.cbf) {
+                int buf;
+                if (pf_idx == idx) {
+                    buf = pf_buf;
+                    if (pf_before_stage) cp_async_wait<1>(); else cp_async_wait<0>();
+                } else {
+                    buf = pf_buf ^ 1;
+                    const uint4 *src = reinterpret_cast<const uint4 *>(fr.coefs + (size_t)idx * kCuCoefs);
+                    for (int i = lane; i < kCuCoefs / 8; i += 32) cp_async16(reinterpret_cast<uint4 *>(s.lv[buf]) + i, src + i);
+                    cp_async_commit();
+                    cp_async_wait<0>();
                 }
+                __syncwarp();
+                if (lane < 24) {
+                    const int16_t *blk;
+                    int stride, sx, sy2;
+                    if (lane < 16) { blk = s.lv[buf]; stride = 16; sx = (lane & 3) * 4; sy2 = (lane >> 2) * 4; }
+                    else { const int q = lane - 16; blk = s.lv[buf] + 256 + (q >> 2) * 64; stride = 8; sx = (q & 1) * 4; sy2 = ((q >> 1) & 1) * 4; }
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int t = 0; t < 16; t++) {
+                        const int pr = c_diag4[t];
+                        m |= (blk[(sy2 + (pr >> 2)) * stride + sx + (pr & 3)] != 0 ? 1u : 0u) << t;
+                    }
+                    s.masks[lane] = (uint16_t)m;
+                }
+                __syncwarp();
+                pf_idx = next_coded_cu(s, g, row, x, k);
+                pf_buf = buf ^ 1;
+                pf_before_stage = false;
+                if (pf_idx >= 0) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(fr.coefs + (size_t)pf_idx * kCuCoefs);
+                    for (int i = lane; i < kCuCoefs / 8; i += 32) cp_async16(reinterpret_cast<uint4 *>(s.lv[pf_buf]) + i, src + i);
+                }
+                cp_async_commit();
+                binarise_cu(s, buf, lane);
+                __syncwarp();
+            }
+            // ---- lane 0: syntax elements
+            if (lane == 0) {
+                if (k == 0 || (cx == cx0 && cy == cy0)) {
+                    if (32 * x + 32 <= g.wc && 32 * row + 32 <= g.hc) {
+                        const int inc = (cu_avail(g, cx0, cy0, cx0 - 1, cy0) ? 1 : 0) + (cu_avail(g, cx0, cy0, cx0, cy0 - 1) ? 1 : 0);
+                        CB_BIN(CX_SPLIT_CU + inc, 1);
+                    }
+                }
+                CB_BIN(CX_SPLIT_CU, 0);
+                const int cb_y = cu.cbf & 1, cb_u = (cu.cbf >> 1) & 1, cb_v = (cu.cbf >> 2) & 1;
+                bool coded_residual = true;
+                if (!fr.is_intra) {
+                    // skip-flag context: left / above CUs always precede this one in decoding order when they exist
+                    const int skipL = (k & 1) ? s.cu[slot][k - 1].syn.skip : (x > 0 ? ((k >> 1) ? left_skip1 : left_skip0) : 0);
+                    const int skipA = (k >> 1) ? s.cu[slot][k - 2].syn.skip : (row > 0 ? s.above[slot][k].skip : 0);
+                    CB_BIN(CX_SKIP + (skipL ? 1 : 0) + (skipA ? 1 : 0), sy.skip);
+                    if (sy.merge_idx >= 0) {
+                        if (!sy.skip) {
+                            CB_BIN(CX_PRED_MODE, 0);
+                            CB_BIN(CX_PART_MODE, 1);
+                            CB_BIN(CX_MERGE_FLAG, 1);
+                        }
+                        CB_BIN(CX_MERGE_IDX, sy.merge_idx > 0);
+                        if (sy.merge_idx > 0)
+                            for (int t = 1; t < 4; t++) {
+                                CB_BYPASS(sy.merge_idx > t);
+                                if (sy.merge_idx <= t) break;
+                            }
+                        if (sy.skip) coded_residual = false;
+                    } else {
+                        CB_BIN(CX_PRED_MODE, 0);
+                        CB_BIN(CX_PART_MODE, 1);
+                        CB_BIN(CX_MERGE_FLAG, 0);
+                        st = write_mvd(st, w, sy.mvdx, sy.mvdy);
+                        CB_BIN(CX_MVP_FLAG, sy.mvp_idx);
+                        CB_BIN(CX_ROOT_CBF, cu.cbf != 0);
+                        if (!cu.cbf) coded_residual = false;
+                    }
+                } else {
+                    CB_BIN(CX_PREV_INTRA, sy.merge_idx >= 0);
+                    if (sy.merge_idx >= 0) {
+                        CB_BYPASS(sy.merge_idx > 0);
+                        if (sy.merge_idx > 0) CB_BYPASS(sy.merge_idx > 1);
+                    } else {
+                        CB_BITS((uint32_t)sy.mvdx, 5);
+                    }
+                    CB_BIN(CX_CHROMA_PRED, 0);
+                }
+                if (coded_residual) {
+                    CB_BIN(CX_CBF_CHROMA, cb_u);
+                    CB_BIN(CX_CBF_CHROMA, cb_v);
+                    if (fr.is_intra || cb_u || cb_v) CB_BIN(CX_CBF_LUMA + 1, cb_y);
+                    if (cb_y) st = residual_coding(st, w, 0, 4, 0);
+                    if (cb_u) st = residual_coding(st, w, 16, 3, 1);
+                    if (cb_v) st = residual_coding(st, w, 20, 3, 2);
+                }
+                if (k & 1) { if (k >> 1) left_skip1 = sy.skip; else left_skip0 = sy.skip; }
             }
             __syncwarp();
-            __threadfence();
-            for (int i = lane; i < kNumCtx; i += 32) s.ctx[i] = __ldcg(ctx_save + (row - 1) * kNumCtx + i);
         }
-        __syncwarp();
-        Cabac c;
-        c.low = 0; c.range = 510; c.bits_left = 23; c.buffered = 0; c.held = 0xff;
-        c.out = fr.out + (size_t)row * p.row_cap; c.pos = 0; c.cap = p.row_cap; c.ctx = s.ctx;
-
-        for (int x = 0; x < g.ctuw; x++) {
-            const int cx0 = 2 * x, cy0 = 2 * row;
-            for (int k = 0; k < 4; k++) {
-                const int cx = cx0 + (k & 1), cy = cy0 + (k >> 1);
-                if (cx >= g.cuw || cy >= g.cuh) continue;
-                const int idx = cy * g.cuw + cx;
-                const CuInfo cu = fr.cus[idx];
-                const CuSyntax sy = fr.syn[idx];
-                // ---- all lanes: stage this CU's levels and build the sub-block significance masks
-                if (cu.cbf) {
-                    const uint2 *src = reinterpret_cast<const uint2 *>(fr.coefs + (size_t)idx * kCuCoefs);
-                    uint2 *dst = reinterpret_cast<uint2 *>(s.lv);
-                    for (int i = lane; i < kCuCoefs / 4; i += 32) dst[i] = src[i];
-                    __syncwarp();
-                    if (lane < 24) {
-                        const int16_t *blk;
-                        int stride, sx, sy2;
-                        if (lane < 16) { blk = s.lv; stride = 16; sx = (lane & 3) * 4; sy2 = (lane >> 2) * 4; }
-                        else { const int q = lane - 16; blk = s.lv + 256 + (q >> 2) * 64; stride = 8; sx = (q & 1) * 4; sy2 = ((q >> 1) & 1) * 4; }
-                        uint32_t m = 0;
-#pragma unroll
-                        for (int t = 0; t < 16; t++) {
-                            const int pr = c_diag4[t];
-                            m |= (blk[(sy2 + (pr >> 2)) * stride + sx + (pr & 3)] != 0 ? 1u : 0u) << t;
-                        }
-                        s.masks[lane] = (uint16_t)m;
-                    }
-                    __syncwarp();
-                }
-                // ---- lane 0: syntax elements
-                if (lane == 0) {
-                    if (k == 0 || (cx == cx0 && cy == cy0)) {
-                        if (32 * x + 32 <= g.wc && 32 * row + 32 <= g.hc) {
-                            const int inc = (cu_avail(g, cx0, cy0, cx0 - 1, cy0) ? 1 : 0) + (cu_avail(g, cx0, cy0, cx0, cy0 - 1) ? 1 : 0);
-                            cb_bin(c, CX_SPLIT_CU + inc, 1);
-                        }
-                    }
-                    cb_bin(c, CX_SPLIT_CU, 0);
-                    const int cb_y = cu.cbf & 1, cb_u = (cu.cbf >> 1) & 1, cb_v = (cu.cbf >> 2) & 1;
-                    bool coded_residual = true;
-                    if (!fr.is_intra) {
-                        const int availL = cu_avail(g, cx, cy, cx - 1, cy), availA = cu_avail(g, cx, cy, cx, cy - 1);
-                        const int ctx = (availL && fr.syn[idx - 1].skip ? 1 : 0) + (availA && fr.syn[idx - g.cuw].skip ? 1 : 0);
-                        cb_bin(c, CX_SKIP + ctx, sy.skip);
-                        if (sy.merge_idx >= 0) {
-                            if (!sy.skip) {
-                                cb_bin(c, CX_PRED_MODE, 0);
-                                cb_bin(c, CX_PART_MODE, 1);
-                                cb_bin(c, CX_MERGE_FLAG, 1);
-                            }
-                            cb_bin(c, CX_MERGE_IDX, sy.merge_idx > 0);
-                            if (sy.merge_idx > 0)
-                                for (int t = 1; t < 4; t++) {
-                                    cb_bypass(c, sy.merge_idx > t);
-                                    if (sy.merge_idx <= t) break;
-                                }
-                            if (sy.skip) coded_residual = false;
-                        } else {
-                            cb_bin(c, CX_PRED_MODE, 0);
-                            cb_bin(c, CX_PART_MODE, 1);
-                            cb_bin(c, CX_MERGE_FLAG, 0);
-                            write_mvd(c, sy.mvdx, sy.mvdy);
-                            cb_bin(c, CX_MVP_FLAG, sy.mvp_idx);
-                            cb_bin(c, CX_ROOT_CBF, cu.cbf != 0);
-                            if (!cu.cbf) coded_residual = false;
-                        }
-                    } else {
-                        cb_bin(c, CX_PREV_INTRA, sy.merge_idx >= 0);
-                        if (sy.merge_idx >= 0) {
-                            cb_bypass(c, sy.merge_idx > 0);
-                            if (sy.merge_idx > 0) cb_bypass(c, sy.merge_idx > 1);
-                        } else {
-                            cb_bypass_bits(c, (uint32_t)sy.mvdx, 5);
-                        }
-                        cb_bin(c, CX_CHROMA_PRED, 0);
-                    }
-                    if (coded_residual) {
-                        cb_bin(c, CX_CBF_CHROMA, cb_u);
-                        cb_bin(c, CX_CBF_CHROMA, cb_v);
-                        if (fr.is_intra || cb_u || cb_v) cb_bin(c, CX_CBF_LUMA + 1, cb_y);
-                        if (cb_y) residual_coding(c, s.lv, s.masks, 4, 0);
-                        if (cb_u) residual_coding(c, s.lv + 256, s.masks + 16, 3, 1);
-                        if (cb_v) residual_coding(c, s.lv + 320, s.masks + 20, 3, 2);
-                    }
-                }
-                __syncwarp();
-            }
-            // ---- end of CTU
-            if (x == 1) {       // snapshot for the row below (taken before the terminating bin, contexts only)
-                __syncwarp();
-                for (int i = lane; i < kNumCtx; i += 32) ctx_save[row * kNumCtx + i] = s.ctx[i];
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) row_ready[row] = 1;
-            }
-            if (lane == 0) {
-                const bool last_in_pic = row == g.ctuh - 1 && x == g.ctuw - 1;
-                cb_terminate(c, last_in_pic);
-                if (x == g.ctuw - 1 && !last_in_pic) cb_terminate(c, 1);
-            }
+        // ---- end of CTU
+        if (x == 1) {       // snapshot for the row below (taken before the terminating bin, contexts only)
+            __syncwarp();
+            for (int i = lane; i < kNumCtx; i += 32) ctx_save[row * kNumCtx + i] = s.ctx[i];
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) row_ready[row] = 1;
         }
         if (lane == 0) {
-            const uint32_t n = cb_finish(c);
-            fr.row_len[row] = n;
-            if (n > p.row_cap) atomicExch(p.overflow, 1);
+            const bool last_in_pic = row == g.ctuh - 1 && x == g.ctuw - 1;
+            st = cb_terminate(st, w, last_in_pic);
+            if (x == g.ctuw - 1 && !last_in_pic) st = cb_terminate(st, w, 1);
         }
+        // the staging of CTU x + 2 has had a whole CTU of time; the level prefetch (if any) is the only younger group
+        if (pf_before_stage) cp_async_wait<0>(); else cp_async_wait<1>();
         __syncwarp();
+    }
+    if (lane == 0) {
+        const uint32_t n = cb_finish(st, w);
+        fr.row_len[row] = n;
+        if (fr.trace) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            fr.trace[2 * row] = t_start; fr.trace[2 * row + 1] = t_end;
+        }
+        if (n > p.row_cap) atomicExch(p.overflow, 1);
     }
 }
 

@@ -240,6 +240,8 @@ struct hb_encoder {
     FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
     bool rc_have_idr = false;
     EntropyFrame *eframes_dev = nullptr;
+    unsigned long long *trace_dev = nullptr;   // debug: per-row CABAC timestamps, only with HB_ENTROPY_TRACE=<file>
+    const char *trace_path = nullptr;
     uint32_t *offsets_dev = nullptr;
     uint8_t *packed_dev = nullptr;
     size_t packed_cap = 0;
@@ -392,6 +394,9 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
         HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     HB_TRY(dev_alloc(E, &E->eframes_dev, (size_t)max_batch));
+    E->trace_path = getenv("HB_ENTROPY_TRACE");
+    if (E->trace_path && *E->trace_path) HB_TRY(dev_alloc(E, &E->trace_dev, (size_t)max_batch * g.ctuh * 2));
+    else E->trace_path = nullptr;
     HB_TRY(dev_alloc(E, &E->offsets_dev, (size_t)max_batch * g.ctuh + 1));
     E->packed_cap = (size_t)max_batch * g.ctuh * E->row_cap / 4 + (1 << 20);
     HB_TRY(dev_alloc(E, &E->packed_dev, E->packed_cap));
@@ -523,6 +528,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             FrameSlot &s = e->slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
             ef[i].is_intra = is_idr[i]; ef[i].ctl = e->ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
+            ef[i].trace = e->trace_dev ? e->trace_dev + (size_t)i * g.ctuh * 2 : nullptr;
         }
         HB_CUDA(ctx, cudaMemcpyAsync(e->eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
         HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
@@ -714,6 +720,19 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             }
             cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
             cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
+        }
+        if (e->trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes}
+            std::vector<unsigned long long> tr((size_t)n * g.ctuh * 2);
+            cudaMemcpy(tr.data(), e->trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(e->trace_path, "wb")) {
+                const unsigned long long hdr[2] = {(unsigned long long)n, (unsigned long long)g.ctuh};
+                fwrite(hdr, sizeof(hdr), 1, f);
+                for (size_t k = 0; k < (size_t)n * g.ctuh; k++) {
+                    const unsigned long long rec[3] = {tr[2 * k], tr[2 * k + 1], (unsigned long long)(e->offsets_host[k + 1] - e->offsets_host[k])};
+                    fwrite(rec, sizeof(rec), 1, f);
+                }
+                fclose(f);
+            }
         }
         // ---- access-unit assembly on the host
         std::vector<uint8_t> au, slice;

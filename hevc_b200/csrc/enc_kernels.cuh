@@ -72,6 +72,7 @@ struct EntropyFrame {
     uint8_t *ctx_save;                   // [ctuh][kNumCtx] WPP context snapshots (after the 2nd CTU of each row)
     int *row_ready;                      // [ctuh] snapshot-published flags, zeroed before the launch
     int is_intra;
+    unsigned long long *trace;           // debug (HB_ENTROPY_TRACE): [ctuh][2] globaltimer at row start (after the hand-off) / end, or null
 };
 
 struct EntropyParams {
@@ -91,10 +92,24 @@ struct PackParams {
 
 constexpr int kEntropyWarps = 4;
 constexpr int kIntraThreads = 576;        // k_intra CTA: the 35 x 16 mode-search tasks in one round; 256 threads own one luma sample each
-struct EntropyWarpScratch {
-    int16_t lv[kCuCoefs];
-    uint16_t masks[24];
+constexpr int kBinStride = 61;            // 32-bit words per sub-block bin list (<= 60 entries, odd stride: no bank conflicts)
+struct CuStage {
+    CuInfo info;
+    CuSyntax syn;
+};
+struct __align__(16) EntropyWarpScratch {
+    int16_t lv[2][kCuCoefs];             // levels of the CU being coded / of the next coded CU (cp.async, one coded CU ahead)
+    uint32_t bins[24][kBinStride];       // per sub-block bin lists written by the binarisation lanes, consumed by lane 0
+    uint16_t masks[24];                  // per sub-block significance masks in diagonal scan order, raster sub-block index
+    uint8_t nbins[24];
     uint8_t ctx[kNumCtx + 2];
+    CuStage cu[3][4];                    // ring of staged CTUs (cp.async, two CTUs ahead)
+    CuSyntax above[3][2];                // syntax of the two CUs above each staged CTU (skip-flag context)
+    // byte-output side of the arithmetic coder (touched only when a byte leaves it)
+    uint8_t *out;
+    uint32_t pos, cap;
+    int buffered;
+    uint32_t held;
 };
 static_assert(sizeof(EntropyWarpScratch) % 16 == 0, "per-warp scratch must keep 16-byte alignment");
 // uploads the dp2a-packed interpolation taps into constant memory (call once per process/device before k_inter)
