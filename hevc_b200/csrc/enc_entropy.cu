@@ -147,12 +147,14 @@ __global__ void __launch_bounds__(256) k_modes(ModeParams p)
 }
 
 // ------------------------------------------------------------------------------------------------ CABAC engine (lane 0)
-// Per-warp scratch at file scope so that the (deliberately not inlined) coding primitives address it as shared memory.
+// Per-warp scratch at file scope so that the (deliberately not inlined) coding functions address it as shared memory.
 __shared__ EntropyWarpScratch g_ews[kEntropyWarps];
+// per state: x = the four rangeTabLps bytes, y = the state after an LPS (built once per CTA from the constant tables)
+__shared__ uint2 g_state_tab[64];
 
-// Arithmetic-coder state, passed and returned BY VALUE through the primitives so that it lives in registers
-// (a struct passed by reference to the non-inlined primitives sat in local memory: ~10 % of all executed instructions were
-// local loads / stores, all on the critical path of every bin -- profiles/round1_summary.md).  x: low; y: range | bits_left << 16.
+// Arithmetic-coder state, passed and returned BY VALUE so that it lives in registers (a struct passed by reference to
+// non-inlined functions sat in local memory and put local loads / stores on the critical path of every bin).
+// x: low; y: range | bits_left << 16.
 typedef uint2 CabacState;
 __device__ __forceinline__ CabacState cs_make(uint32_t low, uint32_t range, int bits_left) { return make_uint2(low, range | ((uint32_t)bits_left << 16)); }
 
@@ -184,77 +186,6 @@ __device__ __noinline__ CabacState cb_write_out(uint32_t low, uint32_t range, in
     return cs_make(low, range, bits_left);
 }
 
-// Not inlined on purpose: the syntax code calls these from ~100 sites; inlining them made a 45 k-instruction kernel that
-// spent 57 % of its stall samples waiting for instruction fetch (profiles/round1_summary.md).
-__device__ __noinline__ CabacState cb_bin(CabacState st, int w, int ctx, int bin)
-{
-    uint8_t *cp = &g_ews[w].ctx[ctx];
-    const uint32_t s = *cp;
-    uint32_t low = st.x, range = st.y & 0xffffu;
-    int bits_left = (int)(st.y >> 16);
-    const uint32_t sidx = s >> 1, mps = s & 1;
-    const uint32_t lps = c_range_lps[sidx][(range >> 6) & 3];
-    range -= lps;
-    if ((uint32_t)bin != mps) {
-        const int nb = __clz(lps) - 23;             // renormalisation shift: lps in [6, 240] -> 1..6
-        low = (low + range) << nb;
-        range = lps << nb;
-        *cp = (uint8_t)((c_next_lps[sidx] << 1) | (sidx == 0 ? 1 - mps : mps));
-        bits_left -= nb;
-    } else {
-        *cp = (uint8_t)(((sidx < 62 ? sidx + 1 : sidx) << 1) | mps);
-        if (range >= 256) return cs_make(low, range, bits_left);
-        low <<= 1;
-        range <<= 1;
-        bits_left--;
-    }
-    if (bits_left < 12) return cb_write_out(low, range, bits_left, w);
-    return cs_make(low, range, bits_left);
-}
-
-// n <= 8 equiprobable bins at once (H.265 9.3.4.3.4 applied n times: low = low * 2^n + range * v)
-__device__ __forceinline__ CabacState cb_bypass_chunk(CabacState st, int w, uint32_t v, int n)
-{
-    const uint32_t range = st.y & 0xffffu;
-    const int bits_left = (int)(st.y >> 16) - n;
-    const uint32_t low = (st.x << n) + range * v;
-    if (bits_left < 12) return cb_write_out(low, range, bits_left, w);
-    return cs_make(low, range, bits_left);
-}
-
-__device__ __noinline__ CabacState cb_bypass(CabacState st, int w, int bin) { return cb_bypass_chunk(st, w, bin ? 1u : 0u, 1); }
-
-// v: n bins, most significant first, n <= 32
-__device__ __noinline__ CabacState cb_bypass_bits(CabacState st, int w, uint32_t v, int n)
-{
-    while (n > 8) {
-        n -= 8;
-        st = cb_bypass_chunk(st, w, (v >> n) & 0xffu, 8);
-    }
-    if (n > 0) st = cb_bypass_chunk(st, w, v & ((1u << n) - 1), n);
-    return st;
-}
-
-__device__ __noinline__ CabacState cb_terminate(CabacState st, int w, int bin)
-{
-    uint32_t low = st.x, range = (st.y & 0xffffu) - 2;
-    int bits_left = (int)(st.y >> 16);
-    if (bin) {
-        low += range;
-        low <<= 7;
-        range = 2 << 7;
-        bits_left -= 7;
-    } else if (range >= 256) {
-        return cs_make(low, range, bits_left);
-    } else {
-        low <<= 1;
-        range <<= 1;
-        bits_left--;
-    }
-    if (bits_left < 12) return cb_write_out(low, range, bits_left, w);
-    return cs_make(low, range, bits_left);
-}
-
 __device__ __noinline__ uint32_t cb_finish(CabacState st, int w)
 {
     EntropyWarpScratch &o = g_ews[w];
@@ -277,9 +208,97 @@ __device__ __noinline__ uint32_t cb_finish(CabacState st, int w)
     return o.pos;
 }
 
-#define CB_BIN(ctx, bin) st = cb_bin(st, w, (ctx), (bin))
-#define CB_BYPASS(bin) st = cb_bypass(st, w, (bin))
-#define CB_BITS(v, n) st = cb_bypass_bits(st, w, (v), (n))
+constexpr uint32_t kBypass = 254, kUnary = 253, kTerminate = 252;
+__device__ __forceinline__ uint32_t bin_ctx(int ctx, int bin) { return (uint32_t)ctx | ((uint32_t)bin << 8); }
+__device__ __forceinline__ uint32_t bin_bypass(uint32_t v, int n) { return kBypass | ((uint32_t)n << 8) | (v << 16); }
+__device__ __forceinline__ uint32_t bin_unary(int ones) { return kUnary | ((uint32_t)ones << 8); }      // `ones` 1-bins, then a 0-bin
+__device__ __forceinline__ uint2 ctx_entry(int state, int mps)
+{
+    const uint2 t = g_state_tab[state];
+    return make_uint2(t.x, (t.y << 8) | ((uint32_t)state << 1) | (uint32_t)mps);
+}
+
+// Lane 0: the arithmetic coder proper, one tight loop over a bin list in shared memory (word offset `off` inside the warp's
+// scratch).  Per context-coded bin the critical path is one 64-bit shared load (the context entry carries the four LPS ranges
+// of its state), a byte select and the range / low update; the state transition (one more table load and the store) is off it.
+__device__ __forceinline__ CabacState code_list(CabacState st, int w, int off, int n)
+{
+    EntropyWarpScratch &s = g_ews[w];
+    const uint32_t *e = reinterpret_cast<const uint32_t *>(&s) + off;
+    uint32_t low = st.x, range = st.y & 0xffffu;
+    int bits_left = (int)(st.y >> 16);
+    for (int k = 0; k < n; k++) {
+        const uint32_t v = e[k];
+        const uint32_t kind = v & 0xff, arg = (v >> 8) & 0xff;
+        if (kind < kTerminate) {
+            const uint2 c = s.ctx[kind];
+            const uint32_t lps = __byte_perm(c.x, 0, 0x4440u | ((range >> 6) & 3));
+            const uint32_t state = (c.y >> 1) & 63;
+            uint32_t mps = c.y & 1, next;
+            range -= lps;
+            if (arg != mps) {
+                const int nb = __clz(lps) - 23;             // renormalisation shift: lps in [6, 240] -> 1..6
+                low = (low + range) << nb;
+                range = lps << nb;
+                bits_left -= nb;
+                next = (c.y >> 8) & 0xff;
+                if (state == 0) mps ^= 1;
+            } else {
+                next = state < 62 ? state + 1 : state;
+                if (range < 256) { low <<= 1; range <<= 1; bits_left--; }
+            }
+            s.ctx[kind] = ctx_entry((int)next, (int)mps);
+            if (bits_left < 12) { const CabacState r = cb_write_out(low, range, bits_left, w); low = r.x; bits_left = (int)(r.y >> 16); }
+        } else if (kind == kTerminate) {
+            range -= 2;
+            if (arg) {
+                low = (low + range) << 7;
+                range = 2 << 7;
+                bits_left -= 7;
+            } else if (range < 256) {
+                low <<= 1; range <<= 1; bits_left--;
+            }
+            if (bits_left < 12) { const CabacState r = cb_write_out(low, range, bits_left, w); low = r.x; bits_left = (int)(r.y >> 16); }
+        } else {
+            // equiprobable bins, up to 8 at a time (H.265 9.3.4.3.4 applied c times: low = low * 2^c + range * bits)
+            uint32_t bits = kind == kBypass ? v >> 16 : (2u << arg) - 2;
+            int nbit = kind == kBypass ? (int)arg : (int)arg + 1;
+            while (nbit > 0) {
+                const int c = nbit > 8 ? 8 : nbit;
+                nbit -= c;
+                low = (low << c) + range * ((bits >> nbit) & ((1u << c) - 1));
+                bits_left -= c;
+                if (bits_left < 12) { const CabacState r = cb_write_out(low, range, bits_left, w); low = r.x; bits_left = (int)(r.y >> 16); }
+            }
+        }
+    }
+    return cs_make(low, range, bits_left);
+}
+
+#define EWS_OFF(member) ((int)(offsetof(EntropyWarpScratch, member) / 4))
+
+// lane 0: everything CU `k` of the current CTU contributes: header list, then per coded transform block its last-position list
+// and the sub-block lists in coding order
+__device__ __noinline__ CabacState code_cu(CabacState st, int w, int k, int cbf)
+{
+    EntropyWarpScratch &s = g_ews[w];
+    st = code_list(st, w, EWS_OFF(hdr) + k * kHdrBins, s.nhdr[k]);
+    for (int tu = 0; tu < 3; tu++) {
+        if (!((cbf >> tu) & 1)) continue;
+        const int base = tu == 0 ? 0 : 12 + 4 * tu;
+        st = code_list(st, w, EWS_OFF(tuh) + tu * kTuHdrBins, s.ntuh[tu]);
+        for (int i = s.last_sb[tu]; i >= 0; i--) st = code_list(st, w, EWS_OFF(bins) + (base + i) * kBinStride, s.nbins[base + i]);
+    }
+    return st;
+}
+
+// lane 0: one stand-alone list entry (end_of_slice_segment_flag / end_of_subset_one_bit)
+__device__ __noinline__ CabacState code_terminate(CabacState st, int w, int bin)
+{
+    EntropyWarpScratch &s = g_ews[w];
+    s.hdr[0][0] = kTerminate | ((uint32_t)bin << 8);
+    return code_list(st, w, EWS_OFF(hdr), 1);
+}
 
 // ------------------------------------------------------------------------------------------------ residual coding
 // Two stages per coded CU.  Binarisation (lanes 0-23, one 4x4 sub-block each, lane = TU base + sub-block scan index): every
@@ -287,11 +306,6 @@ __device__ __noinline__ uint32_t cb_finish(CabacState st, int w)
 // for bypass runs.  All context selection (9.3.4.2.4 - 9.3.4.2.7) happens here, in parallel.  Coding (lane 0): walks the lists
 // in coding order through one tight arithmetic-coder loop.  Bin entry: bits 0-7 kind (context index, kBypass or kUnary),
 // bits 8-15 bin value / bin count, bits 16-31 bypass bits.
-constexpr uint32_t kBypass = 254, kUnary = 253;
-
-__device__ __forceinline__ uint32_t bin_ctx(int ctx, int bin) { return (uint32_t)ctx | ((uint32_t)bin << 8); }
-__device__ __forceinline__ uint32_t bin_bypass(uint32_t v, int n) { return kBypass | ((uint32_t)n << 8) | (v << 16); }
-
 // Binarise the three transform blocks of the CU whose levels sit in s.lv[buf] and whose masks are in s.masks.  Called by the
 // whole warp; returns (per lane, lane-uniform within a TU) the mask of coded sub-blocks in scan order for lanes of that TU.
 __device__ __forceinline__ void binarise_cu(EntropyWarpScratch &s, int buf, int lane)
@@ -418,68 +432,109 @@ __device__ __forceinline__ void binarise_cu(EntropyWarpScratch &s, int buf, int 
     if (lane_ok) s.nbins[lane] = (uint8_t)nb;
 }
 
-// lane 0: code the bin lists of sub-blocks base + last_sb .. base of one transform block
-__device__ __noinline__ CabacState code_bins(CabacState st, int w, int base, int last_sb)
-{
-    EntropyWarpScratch &s = g_ews[w];
-    for (int i = last_sb; i >= 0; i--) {
-        const uint32_t *e = s.bins[base + i];
-        const int nb = s.nbins[base + i];
-        for (int k = 0; k < nb; k++) {
-            const uint32_t v = e[k], kind = v & 0xff, arg = (v >> 8) & 0xff;
-            if (kind < kUnary) CB_BIN((int)kind, (int)arg);
-            else if (kind == kBypass) { if (arg) CB_BITS(v >> 16, (int)arg); }
-            else CB_BITS((2u << arg) - 2, (int)arg + 1);          // arg ones, then a zero
-        }
-    }
-    return st;
-}
 
-// lane 0: last significant coefficient position of the block, then the sub-block lists
-__device__ __noinline__ CabacState residual_coding(CabacState st, int w, int base, int log2n, int c_idx)
+// Lanes 28-30: last significant coefficient position of transform block `tu` (9.3.3.x prefixes context-coded, suffixes bypass)
+__device__ __forceinline__ void binarise_last_pos(EntropyWarpScratch &s, int tu)
 {
-    EntropyWarpScratch &s = g_ews[w];
+    const int base = tu == 0 ? 0 : 12 + 4 * tu, log2n = tu == 0 ? 4 : 3, c_idx = tu;
     const int n = 1 << log2n, sbw = n >> 2, nsb = sbw * sbw;
     const uint8_t *sbscan = sbw == 4 ? c_diag4 : c_diag2;
     const uint16_t *masks = s.masks + base;
-    int last_sb = 0;
+    int last_sb = -1;
     for (int i = nsb - 1; i >= 0; i--)
         if (masks[sbscan[i]]) { last_sb = i; break; }
-    const int last_pos = 31 - __clz((int)masks[sbscan[last_sb]]);
-    const int sr = sbscan[last_sb], pr = c_diag4[last_pos];
-    const int px = ((sr % sbw) << 2) + (pr & 3), py = ((sr / sbw) << 2) + (pr >> 2);
-    const int gx = c_group_idx[px], gy = c_group_idx[py], cmax = c_group_idx[n - 1];
-    int off, shift;
-    if (c_idx == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
-    else { off = 15; shift = log2n - 2; }
-    for (int i = 0; i < gx; i++) CB_BIN(CX_LAST_X + off + (i >> shift), 1);
-    if (gx < cmax) CB_BIN(CX_LAST_X + off + (gx >> shift), 0);
-    for (int i = 0; i < gy; i++) CB_BIN(CX_LAST_Y + off + (i >> shift), 1);
-    if (gy < cmax) CB_BIN(CX_LAST_Y + off + (gy >> shift), 0);
-    if (gx > 3) CB_BITS(px - c_min_in_group[gx], (gx - 2) >> 1);
-    if (gy > 3) CB_BITS(py - c_min_in_group[gy], (gy - 2) >> 1);
-    return code_bins(st, w, base, last_sb);
+    s.last_sb[tu] = (int8_t)last_sb;
+    uint32_t *out = s.tuh[tu];
+    int nb = 0;
+    if (last_sb >= 0) {
+        const int last_pos = 31 - __clz((int)masks[sbscan[last_sb]]);
+        const int sr = sbscan[last_sb], pr = c_diag4[last_pos];
+        const int px = ((sr % sbw) << 2) + (pr & 3), py = ((sr / sbw) << 2) + (pr >> 2);
+        const int gx = c_group_idx[px], gy = c_group_idx[py], cmax = c_group_idx[n - 1];
+        int off, shift;
+        if (c_idx == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
+        else { off = 15; shift = log2n - 2; }
+        for (int i = 0; i < gx; i++) out[nb++] = bin_ctx(CX_LAST_X + off + (i >> shift), 1);
+        if (gx < cmax) out[nb++] = bin_ctx(CX_LAST_X + off + (gx >> shift), 0);
+        for (int i = 0; i < gy; i++) out[nb++] = bin_ctx(CX_LAST_Y + off + (i >> shift), 1);
+        if (gy < cmax) out[nb++] = bin_ctx(CX_LAST_Y + off + (gy >> shift), 0);
+        if (gx > 3) out[nb++] = bin_bypass(px - c_min_in_group[gx], (gx - 2) >> 1);
+        if (gy > 3) out[nb++] = bin_bypass(py - c_min_in_group[gy], (gy - 2) >> 1);
+    }
+    s.ntuh[tu] = (uint8_t)nb;
 }
 
-__device__ __noinline__ CabacState write_mvd(CabacState st, int w, int dx, int dy)
+// Lanes 24-27: syntax of CU `k` of the CTU up to (and including) its coded block flags
+struct CuHeaderIn {
+    CuInfo cu;
+    CuSyntax sy;
+    int is_intra, split_flag_coded, first_in_ctu, split_inc, skip_l, skip_a;
+};
+__device__ __forceinline__ void binarise_header(EntropyWarpScratch &s, int k, const CuHeaderIn &h)
 {
-    const int ax = abs(dx), ay = abs(dy);
-    CB_BIN(CX_MVD_GR0, ax > 0);
-    CB_BIN(CX_MVD_GR0, ay > 0);
-    if (ax > 0) CB_BIN(CX_MVD_GR1, ax > 1);
-    if (ay > 0) CB_BIN(CX_MVD_GR1, ay > 1);
-    for (int comp = 0; comp < 2; comp++) {
-        const int a = comp ? ay : ax, neg = (comp ? dy : dx) < 0;
-        if (a == 0) continue;
-        if (a > 1) {
-            int v = a - 2, k = 1;
-            while (v >= (1 << k)) { CB_BYPASS(1); v -= 1 << k; k++; }
-            CB_BYPASS(0);
-            CB_BITS(v, k);
+    uint32_t *out = s.hdr[k];
+    int nb = 0;
+    const CuInfo &cu = h.cu;
+    const CuSyntax &sy = h.sy;
+    if (h.first_in_ctu && h.split_flag_coded) out[nb++] = bin_ctx(CX_SPLIT_CU + h.split_inc, 1);
+    out[nb++] = bin_ctx(CX_SPLIT_CU, 0);
+    const int cb_y = cu.cbf & 1, cb_u = (cu.cbf >> 1) & 1, cb_v = (cu.cbf >> 2) & 1;
+    bool coded_residual = true;
+    if (!h.is_intra) {
+        out[nb++] = bin_ctx(CX_SKIP + (h.skip_l ? 1 : 0) + (h.skip_a ? 1 : 0), sy.skip);
+        if (sy.merge_idx >= 0) {
+            if (!sy.skip) {
+                out[nb++] = bin_ctx(CX_PRED_MODE, 0);
+                out[nb++] = bin_ctx(CX_PART_MODE, 1);
+                out[nb++] = bin_ctx(CX_MERGE_FLAG, 1);
+            }
+            out[nb++] = bin_ctx(CX_MERGE_IDX, sy.merge_idx > 0);
+            if (sy.merge_idx > 0) {                      // truncated unary, cMax 4: bins 1.. are bypass
+                const int ones = sy.merge_idx - 1;
+                if (sy.merge_idx < 4) out[nb++] = bin_unary(ones);
+                else out[nb++] = bin_bypass(7, 3);
+            }
+            if (sy.skip) coded_residual = false;
+        } else {
+            out[nb++] = bin_ctx(CX_PRED_MODE, 0);
+            out[nb++] = bin_ctx(CX_PART_MODE, 1);
+            out[nb++] = bin_ctx(CX_MERGE_FLAG, 0);
+            const int dx = sy.mvdx, dy = sy.mvdy, ax = abs(dx), ay = abs(dy);
+            out[nb++] = bin_ctx(CX_MVD_GR0, ax > 0);
+            out[nb++] = bin_ctx(CX_MVD_GR0, ay > 0);
+            if (ax > 0) out[nb++] = bin_ctx(CX_MVD_GR1, ax > 1);
+            if (ay > 0) out[nb++] = bin_ctx(CX_MVD_GR1, ay > 1);
+            for (int comp = 0; comp < 2; comp++) {
+                const int a = comp ? ay : ax, neg = (comp ? dy : dx) < 0;
+                if (a == 0) continue;
+                if (a > 1) {                            // abs_mvd_minus2: Exp-Golomb order 1
+                    int v = a - 2, kk = 1;
+                    while (v >= (1 << kk)) { v -= 1 << kk; kk++; }
+                    out[nb++] = bin_unary(kk - 1);
+                    out[nb++] = bin_bypass(v, kk);
+                }
+                out[nb++] = bin_bypass(neg, 1);
+            }
+            out[nb++] = bin_ctx(CX_MVP_FLAG, sy.mvp_idx);
+            out[nb++] = bin_ctx(CX_ROOT_CBF, cu.cbf != 0);
+            if (!cu.cbf) coded_residual = false;
         }
-        CB_BYPASS(neg);
+    } else {
+        out[nb++] = bin_ctx(CX_PREV_INTRA, sy.merge_idx >= 0);
+        if (sy.merge_idx >= 0) {
+            if (sy.merge_idx == 0) out[nb++] = bin_bypass(0, 1);
+            else out[nb++] = bin_bypass(2 | (sy.merge_idx > 1 ? 1 : 0), 2);
+        } else {
+            out[nb++] = bin_bypass((uint32_t)sy.mvdx & 31, 5);
+        }
+        out[nb++] = bin_ctx(CX_CHROMA_PRED, 0);
     }
-    return st;
+    if (coded_residual) {
+        out[nb++] = bin_ctx(CX_CBF_CHROMA, cb_u);
+        out[nb++] = bin_ctx(CX_CBF_CHROMA, cb_v);
+        if (h.is_intra || cb_u || cb_v) out[nb++] = bin_ctx(CX_CBF_LUMA + 1, cb_y);
+    }
+    s.nhdr[k] = (uint8_t)nb;
 }
 
 // ------------------------------------------------------------------------------------------------ WPP CABAC kernel
@@ -534,6 +589,12 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
 {
     const Geom &g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) {
+        const int t = threadIdx.x;
+        g_state_tab[t] = make_uint2((uint32_t)c_range_lps[t][0] | ((uint32_t)c_range_lps[t][1] << 8) | ((uint32_t)c_range_lps[t][2] << 16) |
+                                        ((uint32_t)c_range_lps[t][3] << 24), c_next_lps[t]);
+    }
+    __syncthreads();
     const EntropyFrame fr = p.frames[blockIdx.y];
     uint8_t *ctx_save = fr.ctx_save;                              // [ctuh][kNumCtx]
     volatile int *row_ready = fr.row_ready;                       // [ctuh], zeroed before the launch
@@ -554,7 +615,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
             const int m = (v >> 4) * 5 - 45, n = ((v & 15) << 3) - 16;
             const int pre = min(max(((m * q) >> 4) + n, 1), 126);
             const int mps = pre > 63;
-            s.ctx[i] = (uint8_t)(((mps ? pre - 64 : 63 - pre) << 1) | mps);
+            s.ctx[i] = ctx_entry(mps ? pre - 64 : 63 - pre, mps);
         }
     } else {
         if (lane == 0) {
@@ -567,7 +628,10 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
         }
         __syncwarp();
         __threadfence();
-        for (int i = lane; i < kNumCtx; i += 32) s.ctx[i] = __ldcg(ctx_save + (row - 1) * kNumCtx + i);
+        for (int i = lane; i < kNumCtx; i += 32) {
+            const int b = __ldcg(ctx_save + (row - 1) * kNumCtx + i);
+            s.ctx[i] = ctx_entry(b >> 1, b & 1);
+        }
     }
     unsigned long long t_start = 0;
     if (fr.trace && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -578,7 +642,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
 
     int pf_idx = -1, pf_buf = 0;          // CU whose levels are in flight / ready in s.lv[pf_buf]
     bool pf_before_stage = false;         // that copy was committed before the newest CTU staging group
-    int left_skip0 = 0, left_skip1 = 0;   // skip flags of the two CUs left of the CTU (lane 0)
+    int left_skip0 = 0, left_skip1 = 0;   // skip flags of the two CUs left of the CTU
     for (int x = 0; x < g.ctuw; x++) {
         const int slot = x % 3;
         // CTU x and x + 1 are staged (the wait at the end of the previous iteration); start on x + 2
@@ -586,14 +650,33 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
         cp_async_commit();
         pf_before_stage = true;
         const int cx0 = 2 * x, cy0 = 2 * row;
+        // ---- lanes 24-27: syntax of the four CUs up to the coded block flags
+        if (lane >= 24 && lane < 28) {
+            const int k = lane - 24, cx = cx0 + (k & 1), cy = cy0 + (k >> 1);
+            if (cx < g.cuw && cy < g.cuh) {
+                CuHeaderIn h;
+                h.cu = s.cu[slot][k].info;
+                h.sy = s.cu[slot][k].syn;
+                h.is_intra = fr.is_intra;
+                h.first_in_ctu = k == 0;
+                h.split_flag_coded = 32 * x + 32 <= g.wc && 32 * row + 32 <= g.hc;
+                h.split_inc = (x > 0 ? 1 : 0) + (row > 0 ? 1 : 0);
+                // skip-flag context: left / above CUs always precede this one in decoding order when they exist
+                h.skip_l = (k & 1) ? s.cu[slot][k - 1].syn.skip : (x > 0 ? ((k >> 1) ? left_skip1 : left_skip0) : 0);
+                h.skip_a = (k >> 1) ? s.cu[slot][k - 2].syn.skip : (row > 0 ? s.above[slot][k].skip : 0);
+                binarise_header(s, k, h);
+            }
+        }
+        left_skip0 = s.cu[slot][1].syn.skip;
+        left_skip1 = s.cu[slot][3].syn.skip;
+        __syncwarp();
         for (int k = 0; k < 4; k++) {
             const int cx = cx0 + (k & 1), cy = cy0 + (k >> 1);
             if (cx >= g.cuw || cy >= g.cuh) continue;
             const int idx = cy * g.cuw + cx;
-            const CuInfo cu = s.cu[slot][k].info;
-            const CuSyntax sy = s.cu[slot][k].syn;
+            const int cbf = s.cu[slot][k].info.cbf;
             // ---- all lanes: levels of this CU (normally already in flight), sub-block masks, next prefetch, binarisation
-            if (cu.cbf) {
+            if (cbf) {
                 int buf;
                 if (pf_idx == idx) {
                     buf = pf_buf;
@@ -629,80 +712,24 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
                 }
                 cp_async_commit();
                 binarise_cu(s, buf, lane);
+                if (lane >= 28 && lane < 31 && ((cbf >> (lane - 28)) & 1)) binarise_last_pos(s, lane - 28);
                 __syncwarp();
             }
-            // ---- lane 0: syntax elements
-            if (lane == 0) {
-                if (k == 0 || (cx == cx0 && cy == cy0)) {
-                    if (32 * x + 32 <= g.wc && 32 * row + 32 <= g.hc) {
-                        const int inc = (cu_avail(g, cx0, cy0, cx0 - 1, cy0) ? 1 : 0) + (cu_avail(g, cx0, cy0, cx0, cy0 - 1) ? 1 : 0);
-                        CB_BIN(CX_SPLIT_CU + inc, 1);
-                    }
-                }
-                CB_BIN(CX_SPLIT_CU, 0);
-                const int cb_y = cu.cbf & 1, cb_u = (cu.cbf >> 1) & 1, cb_v = (cu.cbf >> 2) & 1;
-                bool coded_residual = true;
-                if (!fr.is_intra) {
-                    // skip-flag context: left / above CUs always precede this one in decoding order when they exist
-                    const int skipL = (k & 1) ? s.cu[slot][k - 1].syn.skip : (x > 0 ? ((k >> 1) ? left_skip1 : left_skip0) : 0);
-                    const int skipA = (k >> 1) ? s.cu[slot][k - 2].syn.skip : (row > 0 ? s.above[slot][k].skip : 0);
-                    CB_BIN(CX_SKIP + (skipL ? 1 : 0) + (skipA ? 1 : 0), sy.skip);
-                    if (sy.merge_idx >= 0) {
-                        if (!sy.skip) {
-                            CB_BIN(CX_PRED_MODE, 0);
-                            CB_BIN(CX_PART_MODE, 1);
-                            CB_BIN(CX_MERGE_FLAG, 1);
-                        }
-                        CB_BIN(CX_MERGE_IDX, sy.merge_idx > 0);
-                        if (sy.merge_idx > 0)
-                            for (int t = 1; t < 4; t++) {
-                                CB_BYPASS(sy.merge_idx > t);
-                                if (sy.merge_idx <= t) break;
-                            }
-                        if (sy.skip) coded_residual = false;
-                    } else {
-                        CB_BIN(CX_PRED_MODE, 0);
-                        CB_BIN(CX_PART_MODE, 1);
-                        CB_BIN(CX_MERGE_FLAG, 0);
-                        st = write_mvd(st, w, sy.mvdx, sy.mvdy);
-                        CB_BIN(CX_MVP_FLAG, sy.mvp_idx);
-                        CB_BIN(CX_ROOT_CBF, cu.cbf != 0);
-                        if (!cu.cbf) coded_residual = false;
-                    }
-                } else {
-                    CB_BIN(CX_PREV_INTRA, sy.merge_idx >= 0);
-                    if (sy.merge_idx >= 0) {
-                        CB_BYPASS(sy.merge_idx > 0);
-                        if (sy.merge_idx > 0) CB_BYPASS(sy.merge_idx > 1);
-                    } else {
-                        CB_BITS((uint32_t)sy.mvdx, 5);
-                    }
-                    CB_BIN(CX_CHROMA_PRED, 0);
-                }
-                if (coded_residual) {
-                    CB_BIN(CX_CBF_CHROMA, cb_u);
-                    CB_BIN(CX_CBF_CHROMA, cb_v);
-                    if (fr.is_intra || cb_u || cb_v) CB_BIN(CX_CBF_LUMA + 1, cb_y);
-                    if (cb_y) st = residual_coding(st, w, 0, 4, 0);
-                    if (cb_u) st = residual_coding(st, w, 16, 3, 1);
-                    if (cb_v) st = residual_coding(st, w, 20, 3, 2);
-                }
-                if (k & 1) { if (k >> 1) left_skip1 = sy.skip; else left_skip0 = sy.skip; }
-            }
+            // ---- lane 0: the arithmetic coder over this CU's lists
+            if (lane == 0) st = code_cu(st, w, k, cbf);
             __syncwarp();
         }
         // ---- end of CTU
         if (x == 1) {       // snapshot for the row below (taken before the terminating bin, contexts only)
-            __syncwarp();
-            for (int i = lane; i < kNumCtx; i += 32) ctx_save[row * kNumCtx + i] = s.ctx[i];
+            for (int i = lane; i < kNumCtx; i += 32) ctx_save[row * kNumCtx + i] = (uint8_t)(s.ctx[i].y & 0xff);
             __threadfence();
             __syncwarp();
             if (lane == 0) row_ready[row] = 1;
         }
         if (lane == 0) {
             const bool last_in_pic = row == g.ctuh - 1 && x == g.ctuw - 1;
-            st = cb_terminate(st, w, last_in_pic);
-            if (x == g.ctuw - 1 && !last_in_pic) st = cb_terminate(st, w, 1);
+            st = code_terminate(st, w, last_in_pic);
+            if (x == g.ctuw - 1 && !last_in_pic) st = code_terminate(st, w, 1);
         }
         // the staging of CTU x + 2 has had a whole CTU of time; the level prefetch (if any) is the only younger group
         if (pf_before_stage) cp_async_wait<0>(); else cp_async_wait<1>();

@@ -789,7 +789,7 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     }
     const bool act = tid < 256;      // threads that own one luma sample
     if (act) s.src[tid >> 4][tid & 15] = p.src.y[(size_t)(y0 + (tid >> 4)) * g.src_stride + x0 + (tid & 15)];
-    if (tid < 35) s.cost[tid] = 0;
+    if (tid >= 192 && tid < 192 + 35) s.cost[tid - 192] = __ldcg(p.mode_cost + (size_t)(cy * g.cuw + cx) * 35 + tid - 192);   // k_intra_search
     __syncthreads();
     if (tid < 65) s.flt[tid] = (pixel)intra_filtered(s.nb, 16, tid);
     if (tid >= 64 && tid < 96) {
@@ -797,19 +797,6 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
         int v = l < 16 ? s.nb[1 + l] + s.nb[33 + l] : 0;
         v = warp_sum(v);
         if (l == 0) s.dc = (v + 16) >> 5;
-    }
-    __syncthreads();
-    // 35 modes x 16 sub-blocks: SATD accumulated per mode
-    for (int t = tid; t < 35 * 16; t += kIntraThreads) {
-        const int mode = t >> 4, sb = t & 15, sx = (sb & 3) * 4, sy = (sb >> 2) * 4;
-        const pixel *nbuf = intra_use_filter(4, mode) ? s.flt : s.nb;
-        int d[4][4];
-#pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-                d[y][x] = (int)s.src[sy + y][sx + x] - intra_sample(nbuf, 16, 4, mode, sx + x, sy + y, true, maxv, s.dc);
-        atomicAdd(&s.cost[mode], hadamard4x4_abs(d) >> 1);
     }
     __syncthreads();
     if (tid == 0) {
@@ -923,16 +910,66 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     __syncthreads();
 }
 
+// Intra mode search for every CU of a key frame at once: SATD of the 35 luma predictions built from the SOURCE picture's
+// neighbour samples (same availability / substitution rules as the real prediction), so that nothing here depends on the
+// reconstruction.  Writes the 35 distortions per CU; the wavefront kernel adds the signalling cost (which needs the real
+// most-probable modes), picks the mode and reconstructs.  One CTA walks CUs in a grid-stride loop.
+struct IntraSearchScratch {
+    pixel nb[65], flt[65];
+    pixel src[16][16];
+    int cost[35];
+    int dc;
+};
+__global__ void __launch_bounds__(kIntraThreads) k_intra_search(IntraParams p)
+{
+    __shared__ IntraSearchScratch s;
+    const Geom &g = p.g;
+    const int tid = threadIdx.x, bd = g.bit_depth, maxv = (1 << bd) - 1;
+    for (int cu = blockIdx.x; cu < g.cuw * g.cuh; cu += gridDim.x) {
+        const int cx = cu % g.cuw, cy = cu / g.cuw, x0 = cx * 16, y0 = cy * 16;
+        if (tid < 65) s.nb[tid] = gather_one(p.src.y, g.src_stride, g, cx, cy, 16, tid, bd);
+        if (tid >= 96 && tid < 96 + 35) s.cost[tid - 96] = 0;
+        if (tid >= 256 && tid < 512) {
+            const int t = tid - 256;
+            s.src[t >> 4][t & 15] = p.src.y[(size_t)(y0 + (t >> 4)) * g.src_stride + x0 + (t & 15)];
+        }
+        __syncthreads();
+        if (tid < 65) s.flt[tid] = (pixel)intra_filtered(s.nb, 16, tid);
+        if (tid >= 64 && tid < 96) {
+            const int l = tid - 64;
+            int v = l < 16 ? s.nb[1 + l] + s.nb[33 + l] : 0;
+            v = warp_sum(v);
+            if (l == 0) s.dc = (v + 16) >> 5;
+        }
+        __syncthreads();
+        // 35 modes x 16 sub-blocks: SATD accumulated per mode
+        for (int t = tid; t < 35 * 16; t += kIntraThreads) {
+            const int mode = t >> 4, sb = t & 15, sx = (sb & 3) * 4, sy = (sb >> 2) * 4;
+            const pixel *nbuf = intra_use_filter(4, mode) ? s.flt : s.nb;
+            int d[4][4];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                    d[y][x] = (int)s.src[sy + y][sx + x] - intra_sample(nbuf, 16, 4, mode, sx + x, sy + y, true, maxv, s.dc);
+            atomicAdd(&s.cost[mode], hadamard4x4_abs(d) >> 1);
+        }
+        __syncthreads();
+        if (tid < 35) p.mode_cost[(size_t)cu * 35 + tid] = s.cost[tid];
+        __syncthreads();
+    }
+}
+
 // one CTA per CTU row; row r may process CTU x once row r-1 has finished CTU x+1 (top-right dependency)
-__global__ void __launch_bounds__(kIntraThreads) k_intra(IntraParams p)
+__global__ void __launch_bounds__(kIntraReconThreads) k_intra(IntraParams p)
 {
     __shared__ IntraScratch s;
     const Geom &g = p.g;
     const int r = blockIdx.x;
     if (p.second_pass && !p.ctl->redo)
         return;
-    for (int i = threadIdx.x; i < 256; i += kIntraThreads) s.m16[i] = (int16_t)tmat_rt(16, i >> 4, i & 15);
-    for (int i = threadIdx.x; i < 64; i += kIntraThreads) s.m8[i] = (int16_t)tmat_rt(8, i >> 3, i & 7);
+    for (int i = threadIdx.x; i < 256; i += kIntraReconThreads) s.m16[i] = (int16_t)tmat_rt(16, i >> 4, i & 15);
+    for (int i = threadIdx.x; i < 64; i += kIntraReconThreads) s.m8[i] = (int16_t)tmat_rt(8, i >> 3, i & 7);
     __syncthreads();
     for (int x = 0; x < g.ctuw; x++) {
         if (r > 0) {

@@ -231,6 +231,7 @@ struct hb_encoder {
     Planes rec[2];
     pixel *ds = nullptr;              // [max_batch + 1][dsh * dsw]
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
+    int *mode_cost = nullptr;         // [cus][35] intra mode search result of the key frame in flight
     uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
     int *satdf[2] = {nullptr, nullptr};
     uint8_t *staging = nullptr;       // raw input frames
@@ -373,6 +374,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     for (int i = 0; i < max_batch; i++) E->slot[i].row_ready = E->row_ready_all + (size_t)i * g.ctuh;
     HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
+    HB_TRY(dev_alloc(E, &E->mode_cost, (size_t)g.cuw * g.cuh * 35));
     for (int k = 0; k < 2; k++) {
         HB_TRY(dev_alloc(E, &E->mvf[k], (size_t)g.cuw * g.cuh));
         HB_TRY(dev_alloc(E, &E->satdf[k], (size_t)g.cuw * g.cuh));
@@ -606,15 +608,17 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 if (idr) {
                     IntraParams ip;
                     ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
-                    ip.ctl = e->ctl_dev + i; ip.second_pass = 0;
-                    k_intra<<<g.ctuh, kIntraThreads, 0, st>>>(ip);
+                    ip.ctl = e->ctl_dev + i; ip.second_pass = 0; ip.mode_cost = e->mode_cost;
+                    k_intra_search<<<std::min(g.cuw * g.cuh, 4 * ctx->sm_count), kIntraThreads, 0, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                    k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
                         k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + i);
                         HB_LAUNCHED(ctx);
                         HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
                         ip.second_pass = 1;
-                        k_intra<<<g.ctuh, kIntraThreads, 0, st>>>(ip);
+                        k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(ip);
                         HB_LAUNCHED(ctx);
                     }
                     e->rc_have_idr = true;

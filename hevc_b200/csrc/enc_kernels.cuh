@@ -1,6 +1,7 @@
 // Kernel parameter blocks shared between the encoder kernels (enc_frame.cu, enc_entropy.cu) and the host
 // driver (enc_host.cu).
 #pragma once
+#include <cstddef>
 #include "enc_dev.cuh"
 
 enum { HB_FMT_YUV420P8 = 0, HB_FMT_P010 = 1, HB_FMT_YUV420P16 = 2 };
@@ -44,6 +45,7 @@ struct IntraParams {
     int16_t *coefs;
     int *progress;                       // [ctuh], zeroed before launch
     FrameCtl *ctl;
+    int *mode_cost;                      // [cus][35] luma SATD per intra mode from k_intra_search
     int second_pass;                     // 1: run only when ctl->redo is set (first key frame of a stream under rate control)
 };
 
@@ -91,26 +93,37 @@ struct PackParams {
 };
 
 constexpr int kEntropyWarps = 4;
-constexpr int kIntraThreads = 576;        // k_intra CTA: the 35 x 16 mode-search tasks in one round; 256 threads own one luma sample each
+constexpr int kIntraThreads = 576;        // k_intra_search CTA: the 35 x 16 mode-search tasks in one round
+constexpr int kIntraReconThreads = 256;   // k_intra CTA: one thread per luma sample of the CU
 constexpr int kBinStride = 61;            // 32-bit words per sub-block bin list (<= 60 entries, odd stride: no bank conflicts)
+constexpr int kHdrBins = 40, kTuHdrBins = 24;
 struct CuStage {
     CuInfo info;
     CuSyntax syn;
 };
+// Per-warp (= per CTU row) working set of the CABAC kernel.  Bin lists are written by the binarisation lanes and consumed by
+// lane 0; an entry is kind (bits 0-7: context index, or one of the kBypass / kUnary / kTerminate codes), argument (bits 8-15:
+// bin value or bin count) and bypass bits (16-31).
 struct __align__(16) EntropyWarpScratch {
     int16_t lv[2][kCuCoefs];             // levels of the CU being coded / of the next coded CU (cp.async, one coded CU ahead)
-    uint32_t bins[24][kBinStride];       // per sub-block bin lists written by the binarisation lanes, consumed by lane 0
-    uint16_t masks[24];                  // per sub-block significance masks in diagonal scan order, raster sub-block index
-    uint8_t nbins[24];
-    uint8_t ctx[kNumCtx + 2];
-    CuStage cu[3][4];                    // ring of staged CTUs (cp.async, two CTUs ahead)
+    uint2 ctx[kNumCtx + 2];              // x: the four rangeTabLps bytes of the context's state; y: state << 1 | mps, next-LPS state << 8
+    CuStage cu[3][4];                    // ring of staged CTUs (cp.async, two CTUs ahead); 8-byte aligned for the copies
     CuSyntax above[3][2];                // syntax of the two CUs above each staged CTU (skip-flag context)
     // byte-output side of the arithmetic coder (touched only when a byte leaves it)
     uint8_t *out;
     uint32_t pos, cap;
     int buffered;
     uint32_t held;
+    uint32_t bins[24][kBinStride];       // per sub-block bin lists
+    uint32_t hdr[4][kHdrBins];           // per CU: syntax up to the coded block flags
+    uint32_t tuh[3][kTuHdrBins];         // per transform block: last significant coefficient position
+    uint16_t masks[24];                  // per sub-block significance masks in diagonal scan order, raster sub-block index
+    uint8_t nbins[24];
+    uint8_t nhdr[4], ntuh[3], pad0;
+    int8_t last_sb[3], pad1;
+    uint32_t pad2;
 };
+static_assert(offsetof(EntropyWarpScratch, cu) % 8 == 0 && offsetof(EntropyWarpScratch, above) % 8 == 0, "cp.async destinations");
 static_assert(sizeof(EntropyWarpScratch) % 16 == 0, "per-warp scratch must keep 16-byte alignment");
 // uploads the dp2a-packed interpolation taps into constant memory (call once per process/device before k_inter)
 cudaError_t upload_inter_constants(cudaStream_t st);
@@ -121,6 +134,7 @@ __global__ void k_coarse(CoarseParams p);
 __global__ void k_me(const __grid_constant__ InterParams p);
 __global__ void k_merge(const __grid_constant__ InterParams p);
 __global__ void k_inter(const __grid_constant__ InterParams p);
+__global__ void k_intra_search(IntraParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_deblock(DeblockParams p);
 __global__ void k_modes(ModeParams p);

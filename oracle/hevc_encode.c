@@ -253,12 +253,18 @@ static void encode_intra_frame(orc_encoder *e, int qp)
             const pixel *src = e->src[0].p + (size_t)cy * 16 * e->src[0].stride + cx * 16;
             gather_neighbours(e, &rec[0], cx, cy, 16, nb);
             orc_intra_filter(nb, flt, 16, 0, bd);
+            /* The mode search predicts from the SOURCE picture's neighbour samples (same availability rules), so that it does not
+             * depend on the reconstruction and can run for all CUs at once; only the chosen mode is then predicted from the
+             * reconstructed neighbours.  The signalling cost still uses the real most-probable modes. */
+            pixel nbs[65], flts[65];
+            gather_neighbours(e, &e->src[0], cx, cy, 16, nbs);
+            orc_intra_filter(nbs, flts, 16, 0, bd);
             cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->skip = 0;
             orc_intra_mpm(&fs, cx, cy, mpm);
             long best = -1;
             int best_mode = 0;
             for (int mode = 0; mode < 35; mode++) {
-                orc_intra_pred(orc_intra_use_filter(16, mode) ? flt : nb, pred, 16, 16, mode, 1, bd);
+                orc_intra_pred(orc_intra_use_filter(16, mode) ? flts : nbs, pred, 16, 16, mode, 1, bd);
                 const int bits = mode == mpm[0] ? 2 : (mode == mpm[1] || mode == mpm[2]) ? 3 : 6;
                 const long cost = orc_satd(src, e->src[0].stride, pred, 16, 16, 16) + ((lambda * bits) >> 8);
                 if (best < 0 || cost < best) { best = cost; best_mode = mode; }

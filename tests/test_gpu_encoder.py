@@ -38,7 +38,9 @@ def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back
 
 
 CASES = [(192, 112, 8, 6, (26, 28)), (200, 120, 10, 5, (22, 24)), (64, 64, 8, 3, (40, 42)), (416, 240, 8, 5, (10, 12)),
-         (32, 16, 10, 3, (30, 30)), (328, 184, 10, 6, (35, 37))]
+         (32, 16, 10, 3, (30, 30)), (328, 184, 10, 6, (35, 37)),
+         # geometry edge cases of the CABAC staging ring / wavefronts: one CU, odd CU counts, exactly three CTUs in one row
+         (16, 16, 8, 3, (30, 32)), (80, 48, 8, 4, (24, 26)), (96, 32, 10, 4, (20, 22))]
 
 
 @pytest.mark.parametrize('w,h,depth,n,qp', CASES)
