@@ -702,11 +702,15 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
 struct IntraScratch {
     pixel nb[65], flt[65];
     pixel cnb[2][33];
-    pixel src[16][16], pred[16][16];
-    int16_t a[16][18], b[16][18];
+    pixel src[16][16];
+    int16_t a[16][18], b[16][18];         // luma residual / coefficient ping-pong
+    int16_t ca[2][8][10], cb[2][8][10];   // chroma (both planes)
     int cost[35];
     int dc, best_mode;
-    int e_nnz, e_slog, sbflag[24];
+    int e_nnz, e_slog, sbflag[24], cbf[3];
+    int left_mode[2], top_mode[2];        // luma modes of the CUs left of / above the next CUs (most-probable-mode derivation)
+    int lambda;
+    QuantParam qy, qc;
     int16_t m16[16 * 16], m8[8 * 8];      // core transform matrices (H.265 8.6.4.2) for the matrix-form, all-threads transforms
 };
 
@@ -775,137 +779,125 @@ __device__ __forceinline__ void inv_stage(const int16_t *M, const int16_t *in, i
     out[i * LD + j] = (int16_t)clampd(acc >> shift, -32768, 32767);
 }
 
+// One intra CU on a 384-thread CTA: threads 0-255 own one luma sample each, threads 256-383 one chroma sample each (both
+// planes), so the luma and chroma pipelines run through the same nine barriers.  The mode is the argmin of the precomputed
+// source-neighbour distortions (k_intra_search) plus the signalling cost against the real most-probable modes.
 __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
 {
     const Geom &g = p.g;
     const int tid = threadIdx.x, bd = g.bit_depth, maxv = (1 << bd) - 1;
-    const int x0 = cx * 16, y0 = cy * 16;
-    const int lambda = p.ctl->lambda;
-    // neighbours (luma + both chroma planes) and the source block
+    const int x0 = cx * 16, y0 = cy * 16, k = (cx & 1) | ((cy & 1) << 1);
+    const bool luma = tid < 256, chroma = tid >= 256;
+    const int py = (tid >> 4) & 15, px = tid & 15;
+    const int ct = tid - 256, cpl = (ct >> 6) & 1, cyy = (ct >> 3) & 7, cxx = ct & 7;
+    // ---- stage 0: neighbours (luma + both chroma planes), source samples, search result
     if (tid < 65) s.nb[tid] = gather_one(p.rec.y, g.rec_stride, g, cx, cy, 16, tid, bd);
     else if (tid >= 96 && tid < 96 + 66) {
-        const int k = tid - 96, pl = k / 33;
-        s.cnb[pl][k % 33] = gather_one(pl ? p.rec.v : p.rec.u, g.recc_stride, g, cx, cy, 8, k % 33, bd);
+        const int i = tid - 96, pl = i / 33;
+        s.cnb[pl][i % 33] = gather_one(pl ? p.rec.v : p.rec.u, g.recc_stride, g, cx, cy, 8, i % 33, bd);
+    } else if (tid >= 192 && tid < 192 + 35) {
+        s.cost[tid - 192] = __ldcg(p.mode_cost + (size_t)(cy * g.cuw + cx) * 35 + tid - 192);
+    } else if (tid >= 228 && tid < 252) {
+        s.sbflag[tid - 228] = 0;
+    } else if (tid >= 252 && tid < 256) {
+        if (tid == 252) { s.e_nnz = 0; s.e_slog = 0; }
+        else s.cbf[tid - 253] = 0;
     }
-    const bool act = tid < 256;      // threads that own one luma sample
-    if (act) s.src[tid >> 4][tid & 15] = p.src.y[(size_t)(y0 + (tid >> 4)) * g.src_stride + x0 + (tid & 15)];
-    if (tid >= 192 && tid < 192 + 35) s.cost[tid - 192] = __ldcg(p.mode_cost + (size_t)(cy * g.cuw + cx) * 35 + tid - 192);   // k_intra_search
+    int srcv;
+    if (luma) srcv = p.src.y[(size_t)(y0 + py) * g.src_stride + x0 + px];
+    else srcv = (cpl ? p.src.v : p.src.u)[(size_t)(cy * 8 + cyy) * g.srcc_stride + cx * 8 + cxx];
     __syncthreads();
+    // ---- stage 1: smoothing filter, DC, mode decision (warp 3)
     if (tid < 65) s.flt[tid] = (pixel)intra_filtered(s.nb, 16, tid);
     if (tid >= 64 && tid < 96) {
         const int l = tid - 64;
         int v = l < 16 ? s.nb[1 + l] + s.nb[33 + l] : 0;
         v = warp_sum(v);
         if (l == 0) s.dc = (v + 16) >> 5;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int a = 1, b = 1, mpm[3];
-        if (cu_avail(g, cx, cy, cx - 1, cy)) a = __ldcg(reinterpret_cast<const uint8_t *>(&p.cus[cy * g.cuw + cx - 1]) + 1);
-        if ((cy & 1) && cu_avail(g, cx, cy, cx, cy - 1)) b = __ldcg(reinterpret_cast<const uint8_t *>(&p.cus[(cy - 1) * g.cuw + cx]) + 1);
+    } else if (tid >= 96 && tid < 128) {
+        const int l = tid - 96;
+        int a = 1, b = 1, mpm0, mpm1, mpm2;
+        if (cx > 0) a = s.left_mode[k >> 1];
+        if (k >> 1) b = s.top_mode[k & 1];
         if (a == b) {
-            if (a < 2) { mpm[0] = 0; mpm[1] = 1; mpm[2] = 26; }
-            else { mpm[0] = a; mpm[1] = 2 + ((a + 29) & 31); mpm[2] = 2 + ((a - 1) & 31); }
+            if (a < 2) { mpm0 = 0; mpm1 = 1; mpm2 = 26; }
+            else { mpm0 = a; mpm1 = 2 + ((a + 29) & 31); mpm2 = 2 + ((a - 1) & 31); }
         } else {
-            mpm[0] = a; mpm[1] = b;
-            mpm[2] = (a != 0 && b != 0) ? 0 : (a != 1 && b != 1) ? 1 : 26;
+            mpm0 = a; mpm1 = b;
+            mpm2 = (a != 0 && b != 0) ? 0 : (a != 1 && b != 1) ? 1 : 26;
         }
-        int best = 0x7fffffff, bm = 0;
-        for (int m = 0; m < 35; m++) {
-            const int bits = m == mpm[0] ? 2 : (m == mpm[1] || m == mpm[2]) ? 3 : 6;
-            const int c = s.cost[m] + ((lambda * bits) >> 8);
-            if (c < best) { best = c; bm = m; }
+        unsigned key = 0xffffffffu;
+#pragma unroll
+        for (int m = l; m < 35; m += 32) {
+            const int bits = m == mpm0 ? 2 : (m == mpm1 || m == mpm2) ? 3 : 6;
+            key = min(key, ((unsigned)(s.cost[m] + ((s.lambda * bits) >> 8)) << 6) | (unsigned)m);    // ties: lowest mode
         }
-        s.best_mode = bm;
+        key = __reduce_min_sync(0xffffffffu, key);
+        if (l == 0) s.best_mode = (int)(key & 63);
     }
     __syncthreads();
     const int mode = s.best_mode;
     int16_t *coef = p.coefs + (size_t)(cy * g.cuw + cx) * kCuCoefs;
-    // ---- luma
-    const int py = (tid >> 4) & 15, px = tid & 15;
-    int pv = 0;
-    if (act) {
+    // ---- stage 2: prediction and residual
+    int pv;
+    if (luma) {
         pv = intra_sample(intra_use_filter(4, mode) ? s.flt : s.nb, 16, 4, mode, px, py, true, maxv, s.dc);
-        s.a[py][px] = (int16_t)((int)s.src[py][px] - pv);
-    }
-    __syncthreads();
-    if (act) fwd_stage<16, 18>(s.m16, &s.a[0][0], &s.b[0][0], py, px, 3 + (bd - 8));
-    __syncthreads();
-    if (act) fwd_stage<16, 18>(s.m16, &s.b[0][0], &s.a[0][0], py, px, 10);
-    __syncthreads();
-    const QuantParam qy = p.ctl->qy;
-    int lv = 0;
-    if (act) {
-        lv = quant_one(s.a[py][px], qy);
-        coef[tid] = (int16_t)lv;
-    }
-    if (tid < 24) s.sbflag[tid] = 0;
-    if (tid == 0) { s.e_nnz = 0; s.e_slog = 0; }
-    const int cbf_y = __syncthreads_or(lv != 0);
-    if (lv) {
-        atomicAdd(&s.e_nnz, 1);
-        atomicAdd(&s.e_slog, 31 - __clz(abs(lv)));
-        s.sbflag[(py >> 2) * 4 + (px >> 2)] = 1;
-    }
-    int recv = pv;
-    if (cbf_y) {
-        if (act) s.a[py][px] = (int16_t)dequant_one(lv, qy);
-        __syncthreads();
-        if (act) inv_stage<16, 18>(s.m16, &s.a[0][0], &s.b[0][0], py, px, 7);
-        __syncthreads();
-        if (act) inv_stage<16, 18>(s.m16, &s.b[0][0], &s.a[0][0], py, px, 12 - (bd - 8));
-        __syncthreads();
-        if (act) recv = clampd(pv + s.a[py][px], 0, maxv);
-    }
-    if (act) p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)recv;
-    __syncthreads();
-    // ---- chroma (derived mode = luma mode; no smoothing, no edge filters): threads 0..127 = (plane, sample)
-    int16_t(*ca)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.a[0][0]);
-    int16_t(*cb)[8][10] = reinterpret_cast<int16_t(*)[8][10]>(&s.b[0][0]);
-    const int cpl = (tid >> 6) & 1, cyy = (tid >> 3) & 7, cxx = tid & 7;
-    int cpv = 0;
-    if (tid < 128) {
+        s.a[py][px] = (int16_t)(srcv - pv);
+    } else {
         const pixel *nbuf = s.cnb[cpl];
         int dcs = 8;
+#pragma unroll
         for (int i = 0; i < 8; i++) dcs += nbuf[1 + i] + nbuf[17 + i];
-        cpv = intra_sample(nbuf, 8, 3, mode, cxx, cyy, false, maxv, dcs >> 4);
-        const pixel sv = (cpl ? p.src.v : p.src.u)[(size_t)(cy * 8 + cyy) * g.srcc_stride + cx * 8 + cxx];
-        ca[cpl][cyy][cxx] = (int16_t)((int)sv - cpv);
+        pv = intra_sample(nbuf, 8, 3, mode, cxx, cyy, false, maxv, dcs >> 4);
+        s.ca[cpl][cyy][cxx] = (int16_t)(srcv - pv);
     }
     __syncthreads();
-    if (tid < 128) fwd_stage<8, 10>(s.m8, &ca[cpl][0][0], &cb[cpl][0][0], cyy, cxx, 2 + (bd - 8));
+    // ---- stages 3-4: forward transform
+    if (luma) fwd_stage<16, 18>(s.m16, &s.a[0][0], &s.b[0][0], py, px, 3 + (bd - 8));
+    else fwd_stage<8, 10>(s.m8, &s.ca[cpl][0][0], &s.cb[cpl][0][0], cyy, cxx, 2 + (bd - 8));
     __syncthreads();
-    if (tid < 128) fwd_stage<8, 10>(s.m8, &cb[cpl][0][0], &ca[cpl][0][0], cyy, cxx, 9);
+    if (luma) fwd_stage<16, 18>(s.m16, &s.b[0][0], &s.a[0][0], py, px, 10);
+    else fwd_stage<8, 10>(s.m8, &s.cb[cpl][0][0], &s.ca[cpl][0][0], cyy, cxx, 9);
     __syncthreads();
-    const QuantParam qc = p.ctl->qc;
-    int clv = 0;
-    if (tid < 128) {
-        clv = quant_one(ca[cpl][cyy][cxx], qc);
-        coef[256 + tid] = (int16_t)clv;
-        if (clv) {
-            atomicAdd(&s.e_nnz, 1);
-            atomicAdd(&s.e_slog, 31 - __clz(abs(clv)));
-            s.sbflag[16 + cpl * 4 + (cyy >> 2) * 2 + (cxx >> 2)] = 1;
+    // ---- stage 5: quantisation, levels out, size-estimate statistics, dequantisation in place
+    int lv;
+    if (luma) {
+        lv = quant_one(s.a[py][px], s.qy);
+        coef[tid] = (int16_t)lv;
+        s.a[py][px] = (int16_t)dequant_one(lv, s.qy);
+        if (lv) { s.sbflag[(py >> 2) * 4 + (px >> 2)] = 1; s.cbf[0] = 1; }
+    } else {
+        lv = quant_one(s.ca[cpl][cyy][cxx], s.qc);
+        coef[tid] = (int16_t)lv;                                  // tid - 256 + 256
+        s.ca[cpl][cyy][cxx] = (int16_t)dequant_one(lv, s.qc);
+        if (lv) { s.sbflag[16 + cpl * 4 + (cyy >> 2) * 2 + (cxx >> 2)] = 1; s.cbf[1 + cpl] = 1; }
+    }
+    {
+        const int nnz = warp_sum(lv != 0), slog = warp_sum(lv ? 31 - __clz(abs(lv)) : 0);
+        if ((tid & 31) == 0 && nnz) { atomicAdd(&s.e_nnz, nnz); atomicAdd(&s.e_slog, slog); }
+    }
+    __syncthreads();
+    // ---- stages 6-7: inverse transform
+    if (luma) inv_stage<16, 18>(s.m16, &s.a[0][0], &s.b[0][0], py, px, 7);
+    else inv_stage<8, 10>(s.m8, &s.ca[cpl][0][0], &s.cb[cpl][0][0], cyy, cxx, 7);
+    __syncthreads();
+    if (luma) inv_stage<16, 18>(s.m16, &s.b[0][0], &s.a[0][0], py, px, 12 - (bd - 8));
+    else inv_stage<8, 10>(s.m8, &s.cb[cpl][0][0], &s.ca[cpl][0][0], cyy, cxx, 12 - (bd - 8));
+    __syncthreads();
+    // ---- stage 8: reconstruction, CU record, size estimate
+    if (luma) p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)clampd(pv + s.a[py][px], 0, maxv);
+    else (cpl ? p.rec.v : p.rec.u)[(size_t)(cy * 8 + cyy) * g.recc_stride + cx * 8 + cxx] = (pixel)clampd(pv + s.ca[cpl][cyy][cxx], 0, maxv);
+    if (tid < 32) {
+        const int nsb = __popc(__ballot_sync(0xffffffffu, tid < 24 && s.sbflag[tid < 24 ? tid : 0] != 0));
+        if (tid == 0) {
+            CuInfo ci;
+            ci.pred_mode = 0; ci.intra_mode = (uint8_t)mode; ci.cbf = (uint8_t)((s.cbf[0] ? 1 : 0) | (s.cbf[1] ? 2 : 0) | (s.cbf[2] ? 4 : 0));
+            ci.skip = 0; ci.mvx = 0; ci.mvy = 0;
+            p.cus[cy * g.cuw + cx] = ci;
+            atomicAdd(&p.ctl->est16, ci.cbf ? (unsigned long long)(47 * s.e_nnz + 22 * s.e_slog + 104 * nsb + 160) : 80ull);
+            s.left_mode[k >> 1] = mode;
+            if (!(k >> 1)) s.top_mode[k & 1] = mode;
         }
-    }
-    const int cbf_u = __syncthreads_or(tid < 64 && clv != 0);
-    const int cbf_v = __syncthreads_or(tid >= 64 && tid < 128 && clv != 0);
-    if (tid < 128) ca[cpl][cyy][cxx] = (int16_t)dequant_one(clv, qc);
-    __syncthreads();
-    if (tid < 128) inv_stage<8, 10>(s.m8, &ca[cpl][0][0], &cb[cpl][0][0], cyy, cxx, 7);
-    __syncthreads();
-    if (tid < 128) inv_stage<8, 10>(s.m8, &cb[cpl][0][0], &ca[cpl][0][0], cyy, cxx, 12 - (bd - 8));
-    __syncthreads();
-    if (tid < 128)
-        (cpl ? p.rec.v : p.rec.u)[(size_t)(cy * 8 + cyy) * g.recc_stride + cx * 8 + cxx] = (pixel)clampd(cpv + ca[cpl][cyy][cxx], 0, maxv);
-    if (tid == 0) {
-        CuInfo ci;
-        ci.pred_mode = 0; ci.intra_mode = (uint8_t)mode; ci.cbf = (uint8_t)(cbf_y ? 1 : 0) | (cbf_u ? 2 : 0) | (cbf_v ? 4 : 0);
-        ci.skip = 0; ci.mvx = 0; ci.mvy = 0;
-        p.cus[cy * g.cuw + cx] = ci;
-        int nsb = 0;
-        for (int i = 0; i < 24; i++) nsb += s.sbflag[i];
-        atomicAdd(&p.ctl->est16, ci.cbf ? (unsigned long long)(47 * s.e_nnz + 22 * s.e_slog + 104 * nsb + 160) : 80ull);
     }
     __syncthreads();
 }
@@ -970,6 +962,7 @@ __global__ void __launch_bounds__(kIntraReconThreads) k_intra(IntraParams p)
         return;
     for (int i = threadIdx.x; i < 256; i += kIntraReconThreads) s.m16[i] = (int16_t)tmat_rt(16, i >> 4, i & 15);
     for (int i = threadIdx.x; i < 64; i += kIntraReconThreads) s.m8[i] = (int16_t)tmat_rt(8, i >> 3, i & 7);
+    if (threadIdx.x == 0) { s.lambda = p.ctl->lambda; s.qy = p.ctl->qy; s.qc = p.ctl->qc; }
     __syncthreads();
     for (int x = 0; x < g.ctuw; x++) {
         if (r > 0) {
