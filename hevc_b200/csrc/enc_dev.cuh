@@ -60,12 +60,14 @@ HB_HD constexpr int chroma_qp(int qp_y)
     return q < 30 ? q : q >= 44 ? q - 6 : t[q - 30];
 }
 
-HB_HD int mv_bits1(int v)
+HB_HD int mv_bits1(int v)      // 2 * floor(log2(|v| + 1)) + 1
 {
-    const int a = v < 0 ? -v : v;
-    int n = 0;
-    while ((a + 1) >> (n + 1)) n++;
-    return 2 * n + 1;
+    const unsigned a = (unsigned)(v < 0 ? -v : v) + 1;
+#ifdef __CUDA_ARCH__
+    return 2 * (31 - __clz((int)a)) + 1;
+#else
+    return 2 * (31 - __builtin_clz(a)) + 1;
+#endif
 }
 
 HB_HD int mv_cost(int lambda, int mvx, int mvy, int px, int py) { return (lambda * (mv_bits1(mvx - px) + mv_bits1(mvy - py))) >> 8; }

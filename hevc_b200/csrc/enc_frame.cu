@@ -236,19 +236,20 @@ __device__ __forceinline__ void hpass8(const int (&w)[8], const int (&t)[5], int
 }
 
 // Luma prediction of the 16x16 block whose integer sample (0,0) sits at window position (ix, iy), in the unified two-pass
-// form (bit-exact with the normative one-pass cases).  Both passes run on packed sample pairs with
-// dp2a.  Lane mapping of the result: lane -> column c = lane >> 1, rows r0 = 8 * (lane & 1) .. r0 + 7 (pv[k] = row r0 + k).
-__device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane, int (&pv)[8])
+// form (bit-exact with the normative one-pass cases).  Both passes run on packed sample pairs with dp2a.
+// The horizontal pass filters `rows` (23 or 24) window rows starting at iy0 - 3 into tmpT[column][row]; the vertical pass
+// reads 16 of them starting at row `ro` (0 or 1), so up to three candidates that differ only vertically share one
+// horizontal pass.  Lane mapping of the result: lane -> column c = lane >> 1, rows r0 = 8 * (lane & 1) .. r0 + 7.
+__device__ __forceinline__ void interp_hpass(WarpScratch &s, int ix, int iy0, int fx, int rows, int bd, int lane)
 {
-    const int shift1 = bd - 8, s14 = 14 - bd, off14 = 1 << (s14 - 1), maxv = (1 << bd) - 1;
-    int th[5], tv[5];
+    const int shift1 = bd - 8;
+    int th[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) { th[k] = c_luma_pack[fx][k]; tv[k] = c_luma_pack[fy][k]; }
-    // horizontal: 23 rows x 2 half-rows of 8 outputs
-    for (int task = lane; task < 46; task += 32) {
+    for (int k = 0; k < 5; k++) th[k] = c_luma_pack[fx][k];
+    for (int task = lane; task < 2 * rows; task += 32) {
         const int r = task >> 1, c0 = (task & 1) * 8;
         const int s0 = ix - 3 + c0, w0 = s0 >> 1;
-        const int *wp = reinterpret_cast<const int *>(&s.win[iy - 3 + r][0]) + w0;
+        const int *wp = reinterpret_cast<const int *>(&s.win[iy0 - 3 + r][0]) + w0;
         int w[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) w[k] = wp[k];
@@ -257,16 +258,35 @@ __device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int 
         else hpass8<0>(w, th, shift1, dst);
     }
     __syncwarp();
-    // vertical: one column segment of 8 outputs per lane, two 128-bit loads
+}
+
+__device__ __forceinline__ void interp_vpass(WarpScratch &s, int ro, int fy, int bd, int lane, int (&pv)[8])
+{
+    const int s14 = 14 - bd, off14 = 1 << (s14 - 1), maxv = (1 << bd) - 1;
+    int tv[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) tv[k] = c_luma_pack[fy][k];
+    // one column segment of 8 outputs per lane, two 128-bit loads
     const int c = lane >> 1, r0 = (lane & 1) * 8;
     const int4 lo = *reinterpret_cast<const int4 *>(&s.tmpT[c][r0]), hi = *reinterpret_cast<const int4 *>(&s.tmpT[c][r0 + 8]);
     const int w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     int acc[8];
-    acc[0] = tap8<0>(w, tv); acc[1] = tap8<1>(w, tv); acc[2] = tap8<2>(w, tv); acc[3] = tap8<3>(w, tv);
-    acc[4] = tap8<4>(w, tv); acc[5] = tap8<5>(w, tv); acc[6] = tap8<6>(w, tv); acc[7] = tap8<7>(w, tv);
+    if (ro) {
+        acc[0] = tap8<1>(w, tv); acc[1] = tap8<2>(w, tv); acc[2] = tap8<3>(w, tv); acc[3] = tap8<4>(w, tv);
+        acc[4] = tap8<5>(w, tv); acc[5] = tap8<6>(w, tv); acc[6] = tap8<7>(w, tv); acc[7] = tap8<8>(w, tv);
+    } else {
+        acc[0] = tap8<0>(w, tv); acc[1] = tap8<1>(w, tv); acc[2] = tap8<2>(w, tv); acc[3] = tap8<3>(w, tv);
+        acc[4] = tap8<4>(w, tv); acc[5] = tap8<5>(w, tv); acc[6] = tap8<6>(w, tv); acc[7] = tap8<7>(w, tv);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++)
         pv[k] = clampd(((acc[k] >> 6) + off14) >> s14, 0, maxv);
+}
+
+__device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane, int (&pv)[8])
+{
+    interp_hpass(s, ix, iy, fx, 23, bd, lane);
+    interp_vpass(s, 0, fy, bd, lane, pv);
     __syncwarp();
 }
 
@@ -409,23 +429,31 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
     }
     const MV centre = best;
     const int woff = stage_window(p, bar, win_smem, x0, y0, centre, lane);
-    // ---- integer stage 2: 5x5 square, SAD from shared memory
-#pragma unroll 1
-    for (int dy = -2; dy <= 2; dy++)
-#pragma unroll 1
-        for (int dx = -2; dx <= 2; dx++) {
-            if (!dx && !dy) continue;
-            const MV m{centre.x + 4 * dx, centre.y + 4 * dy};
-            const MV cm = clamp_mv(g, x0, y0, m);
-            if (cm.x != m.x || cm.y != m.y) continue;
-            const pixel *w = &s.win[6 + dy + row][6 + dx + c0 + woff];
-            int sad = 0;
+    // ---- integer stage 2: 5x5 square, SAD from shared memory.  Lane -> column lane >> 1, rows (lane & 1) + 2k: the 32 lanes of
+    //      one load then touch 16-18 distinct words in two runs 20 banks apart -- no bank conflicts (the row-per-lane layout of
+    //      stage 1 is 4-way conflicted on the 80-byte window rows).
+    {
+        const int col = lane >> 1, h = lane & 1;
+        int sq[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                sad += abs(sp[i] - (int)w[i]);
-            const int cost = warp_sum(sad) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
-            if (cost < bcost) { bcost = cost; best = m; }
-        }
+        for (int k = 0; k < 8; k++) sq[k] = s.src[h + 2 * k][col];
+#pragma unroll 1
+        for (int dy = -2; dy <= 2; dy++)
+#pragma unroll 1
+            for (int dx = -2; dx <= 2; dx++) {
+                if (!dx && !dy) continue;
+                const MV m{centre.x + 4 * dx, centre.y + 4 * dy};
+                const MV cm = clamp_mv(g, x0, y0, m);
+                if (cm.x != m.x || cm.y != m.y) continue;
+                const pixel *w = &s.win[6 + dy + h][6 + dx + col + woff];
+                int sad = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    sad += abs(sq[k] - (int)w[2 * k * 40]);
+                const int cost = warp_sum(sad) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                if (cost < bcost) { bcost = cost; best = m; }
+            }
+    }
     // ---- sub-sample stages: SATD on the normative interpolation
     const int wx0 = (centre.x >> 2) - 6 - woff, wy0 = (centre.y >> 2) - 6;     // window origin (sample [0][0]) relative to the block position
     int st[8], pv[8];        // source / prediction column segments: column lane >> 1, rows 8 * (lane & 1) + k
@@ -436,18 +464,31 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
 #pragma unroll 1
     for (int step = 2; step >= 1; step--) {
         const MV c2 = best;
+        const int iy_min = (c2.y - step) >> 2;                    // the three rows of candidates start at integer row iy_min or iy_min + 1
 #pragma unroll 1
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll 1
-            for (int dx = -1; dx <= 1; dx++) {
-                if (!dx && !dy) continue;
-                const MV m{c2.x + step * dx, c2.y + step * dy};
+        for (int dx = -1; dx <= 1; dx++) {
+            const int mx = c2.x + step * dx;
+            bool ok[3];
+            bool any = false;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const MV m{mx, c2.y + step * dy};
                 const MV cm = clamp_mv(g, x0, y0, m);
-                if (cm.x != m.x || cm.y != m.y) continue;
-                interp_cols(s, (m.x >> 2) - wx0, (m.y >> 2) - wy0, m.x & 3, m.y & 3, bd, lane, pv);
+                ok[dy + 1] = (dx || dy) && cm.x == m.x && cm.y == m.y;
+                any |= ok[dy + 1];
+            }
+            if (!any) continue;
+            interp_hpass(s, (mx >> 2) - wx0, iy_min - wy0, mx & 3, 24, bd, lane);       // shared by the column's candidates
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                if (!ok[dy + 1]) continue;
+                const MV m{mx, c2.y + step * dy};
+                interp_vpass(s, (m.y >> 2) - iy_min, m.y & 3, bd, lane, pv);
                 const int cost = satd_cols(st, pv, lane) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
                 if (cost < bcost) { bcost = cost; best = m; }
             }
+            __syncwarp();
+        }
     }
     if (lane == 0) {
         p.mv_out[cy * g.cuw + cx] = pack_mv(best);
@@ -719,16 +760,18 @@ struct IntraScratch {
 __device__ __forceinline__ pixel gather_one(const pixel *plane, int stride, const Geom &g, int cx, int cy, int N, int i, int bd)
 {
     const int n2 = 2 * N, x0 = cx * N, y0 = cy * N;
-    const bool av[5] = {cu_avail(g, cx, cy, cx - 1, cy + 1), cu_avail(g, cx, cy, cx - 1, cy), cu_avail(g, cx, cy, cx - 1, cy - 1),
-                        cu_avail(g, cx, cy, cx, cy - 1), cu_avail(g, cx, cy, cx + 1, cy - 1)};
+    // availability of the five neighbour segments as a bit mask (bit s = segment s), kept in a register
+    const unsigned av = (cu_avail(g, cx, cy, cx - 1, cy + 1) ? 1u : 0u) | (cu_avail(g, cx, cy, cx - 1, cy) ? 2u : 0u) |
+                        (cu_avail(g, cx, cy, cx - 1, cy - 1) ? 4u : 0u) | (cu_avail(g, cx, cy, cx, cy - 1) ? 8u : 0u) |
+                        (cu_avail(g, cx, cy, cx + 1, cy - 1) ? 16u : 0u);
     // walk order: bottom-left (bottom to top), left, corner, top, top-right
     int seg, px, py;
     if (i == 0) { seg = 2; px = -1; py = -1; }
     else if (i <= n2) { seg = i <= N ? 3 : 4; px = i - 1; py = -1; }
     else { const int k = i - 1 - n2; seg = k < N ? 1 : 0; px = -1; py = k; }
-    if (!av[seg]) {
+    if (!((av >> seg) & 1)) {
         int s2 = seg - 1;
-        while (s2 >= 0 && !av[s2]) s2--;
+        while (s2 >= 0 && !((av >> s2) & 1)) s2--;
         if (s2 >= 0) {          // last sample (in walk order) of the nearest earlier available segment
             if (s2 == 0) { px = -1; py = N; }
             else if (s2 == 1) { px = -1; py = 0; }
@@ -736,7 +779,7 @@ __device__ __forceinline__ pixel gather_one(const pixel *plane, int stride, cons
             else { px = N - 1; py = -1; }
         } else {                // first sample of the first later available segment
             s2 = seg + 1;
-            while (s2 < 5 && !av[s2]) s2++;
+            while (s2 < 5 && !((av >> s2) & 1)) s2++;
             if (s2 >= 5) return (pixel)(1 << (bd - 1));
             if (s2 == 1) { px = -1; py = N - 1; }
             else if (s2 == 2) { px = -1; py = -1; }

@@ -383,8 +383,9 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             bcost = orc_satd(src, ss, blk, 16, 16, 16) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
             for (int step = 2; step >= 1; step--) {
                 const mv_t centre = best;
-                for (int dy = -1; dy <= 1; dy++)
-                    for (int dx = -1; dx <= 1; dx++) {
+                /* column by column: the three candidates of a column share their horizontal filter pass on the GPU */
+                for (int dx = -1; dx <= 1; dx++)
+                    for (int dy = -1; dy <= 1; dy++) {
                         if (!dx && !dy) continue;
                         mv_t m = {centre.x + step * dx, centre.y + step * dy};
                         const mv_t cm = clamp_mv(e, x0, y0, m);
