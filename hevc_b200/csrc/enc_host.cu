@@ -44,14 +44,28 @@ private:
     int fill_ = 0;
 };
 
+// emulation prevention (H.265 7.4.2): 0x03 before any byte <= 3 that follows two zero bytes.  Zero-free stretches (almost all of
+// a CABAC payload) are found with memchr and copied in bulk.
 void append_escaped(std::vector<uint8_t> &out, const uint8_t *in, size_t n)
 {
+    size_t start = 0, i = 0;
     int zeros = 0;
-    for (size_t i = 0; i < n; i++) {
-        if (zeros >= 2 && in[i] <= 3) { out.push_back(3); zeros = 0; }
-        out.push_back(in[i]);
+    while (i < n) {
+        if (zeros == 0) {
+            const uint8_t *z = static_cast<const uint8_t *>(memchr(in + i, 0, n - i));
+            if (!z) break;
+            i = (size_t)(z - in);
+        }
+        if (zeros >= 2 && in[i] <= 3) {
+            out.insert(out.end(), in + start, in + i);
+            out.push_back(3);
+            start = i;
+            zeros = 0;
+        }
         zeros = in[i] == 0 ? zeros + 1 : 0;
+        i++;
     }
+    out.insert(out.end(), in + start, in + n);
 }
 
 void append_nal(std::vector<uint8_t> &out, int type, const std::vector<uint8_t> &rbsp, bool long_start)
@@ -203,6 +217,8 @@ void md5(const uint8_t *data, size_t n, uint8_t out[16])
 constexpr int kChunk = 8;            // frames per upload / entropy chunk
 constexpr int kMaxChunks = 1024 / kChunk + 1;
 constexpr int kEntropyStreams = 4;
+constexpr int kGroupFrames = 32;     // frames per drain group (a multiple of kChunk)
+constexpr int kMaxGroups = 1024 / kGroupFrames + 1;
 
 struct FrameSlot {
     Planes src{};
@@ -260,6 +276,11 @@ struct hb_encoder {
     cudaStream_t st_entropy[kEntropyStreams] = {};   // CABAC launches round-robin over these, concurrent with the frame chain
     int next_entropy_stream = 0;
     cudaEvent_t ev_misc[2] = {}, ev_join[kEntropyStreams] = {};
+    // drain: every kGroupFrames frames the finished CABAC payload is compacted and downloaded (own streams) and the host
+    // assembles those access units while the GPU is still encoding the rest of the batch
+    cudaStream_t st_drain = nullptr, st_dl = nullptr;
+    cudaEvent_t ev_grp[kMaxGroups][kEntropyStreams] = {}, ev_off[kMaxGroups] = {};
+    size_t frame_cap = 0;             // bytes of the packed buffer reserved per frame
     std::vector<cudaEvent_t> ev_chunk;   // [0, kMaxChunks): upload done, [kMaxChunks, 2 kMaxChunks): chain done
     std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
     int profiling = 0;
@@ -399,10 +420,11 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     E->trace_path = getenv("HB_ENTROPY_TRACE");
     if (E->trace_path && *E->trace_path) HB_TRY(dev_alloc(E, &E->trace_dev, (size_t)max_batch * g.ctuh * 2));
     else E->trace_path = nullptr;
-    HB_TRY(dev_alloc(E, &E->offsets_dev, (size_t)max_batch * g.ctuh + 1));
-    E->packed_cap = (size_t)max_batch * g.ctuh * E->row_cap / 4 + (1 << 20);
+    HB_TRY(dev_alloc(E, &E->offsets_dev, (size_t)max_batch * g.ctuh + kMaxGroups + 1));
+    E->frame_cap = ((size_t)g.ctuh * E->row_cap / 4 + 65536 + 255) & ~(size_t)255;
+    E->packed_cap = (size_t)max_batch * E->frame_cap;
     HB_TRY(dev_alloc(E, &E->packed_dev, E->packed_cap));
-    HB_CUDA(ctx, cudaMallocHost(&E->offsets_host, ((size_t)max_batch * g.ctuh + 1) * sizeof(uint32_t)));
+    HB_CUDA(ctx, cudaMallocHost(&E->offsets_host, ((size_t)max_batch * g.ctuh + kMaxGroups + 1) * sizeof(uint32_t)));
     HB_CUDA(ctx, cudaMallocHost(&E->packed_host, E->packed_cap));
     HB_CUDA(ctx, cudaMallocHost(&E->overflow_host, sizeof(int)));
     for (auto &ev : E->ev) HB_CUDA(ctx, cudaEventCreate(&ev));
@@ -411,6 +433,10 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     E->ev_chunk.resize((size_t)2 * kMaxChunks);
     for (auto &ev : E->ev_chunk) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_drain, cudaStreamNonBlocking));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_dl, cudaStreamNonBlocking));
+    for (auto &row : E->ev_grp) for (auto &ev : row) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : E->ev_off) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     {   // CABAC launches run at the highest stream priority: their CTAs need a whole SM each and would otherwise starve behind
         // the thousands of pending k_inter CTAs of the frame chain
         int lo = 0, hi = 0;
@@ -440,6 +466,10 @@ void hb_enc_destroy(hb_encoder *e)
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_misc) if (ev) cudaEventDestroy(ev);
+    for (auto &row : e->ev_grp) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_off) if (ev) cudaEventDestroy(ev);
+    if (e->st_drain) { cudaStreamSynchronize(e->st_drain); cudaStreamDestroy(e->st_drain); }
+    if (e->st_dl) { cudaStreamSynchronize(e->st_dl); cudaStreamDestroy(e->st_dl); }
     for (auto &ev : e->ev_join) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
@@ -677,71 +707,89 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 HB_TRY(launch_entropy(e, i0, i1 - i0, e->ev_chunk[kMaxChunks + chunk]));
                 i0 = i1;
             }
+            // ---- end of a drain group: compaction + download of its sub-stream sizes behind its CABAC kernels
+            if ((c0 + cn) % kGroupFrames == 0 || c0 + cn == n) {
+                const int grp = c0 / kGroupFrames, f0 = grp * kGroupFrames, cnt = c0 + cn - f0;
+                for (int k = 0; k < kEntropyStreams; k++) {
+                    HB_CUDA(ctx, cudaEventRecord(e->ev_grp[grp][k], e->st_entropy[k]));
+                    HB_CUDA(ctx, cudaStreamWaitEvent(e->st_drain, e->ev_grp[grp][k], 0));
+                }
+                PackParams pp;
+                pp.frames = e->eframes_dev + f0; pp.n_frames = cnt; pp.rows = g.ctuh; pp.row_cap = e->row_cap;
+                pp.packed = e->packed_dev + (size_t)f0 * e->frame_cap; pp.offsets = e->offsets_dev + (size_t)f0 * g.ctuh + grp;
+                k_pack_scan<<<1, 1024, 0, e->st_drain>>>(pp);
+                HB_LAUNCHED(ctx);
+                k_pack_copy<<<cnt * g.ctuh, 128, 0, e->st_drain>>>(pp);
+                HB_LAUNCHED(ctx);
+                HB_CUDA(ctx, cudaMemcpyAsync(e->offsets_host + (size_t)f0 * g.ctuh + grp, pp.offsets, sizeof(uint32_t) * ((size_t)cnt * g.ctuh + 1),
+                                             cudaMemcpyDeviceToHost, e->st_drain));
+                HB_CUDA(ctx, cudaMemcpyAsync(e->ctl_host + f0, e->ctl_dev + f0, sizeof(FrameCtl) * cnt, cudaMemcpyDeviceToHost, e->st_drain));
+                if (c0 + cn == n) {
+                    HB_CUDA(ctx, cudaMemcpyAsync(e->overflow_host, e->overflow, sizeof(int), cudaMemcpyDeviceToHost, e->st_drain));
+                    HB_CUDA(ctx, cudaEventRecord(e->ev[2], e->st_drain));
+                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 4], e->st_drain));
+                }
+                HB_CUDA(ctx, cudaEventRecord(e->ev_off[grp], e->st_drain));
+            }
         }
         k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
         HB_LAUNCHED(ctx);
         // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
         HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
         if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
-        // ---- join the entropy stream, compaction, download
-        for (int k = 0; k < kEntropyStreams; k++) {
-            HB_CUDA(ctx, cudaEventRecord(e->ev_join[k], e->st_entropy[k]));
-            HB_CUDA(ctx, cudaStreamWaitEvent(st, e->ev_join[k], 0));
-        }
+        // ---- drain: per group wait for its sizes, download its payload, assemble its access units (the GPU keeps encoding)
+        std::vector<uint8_t> au, slice;
+        std::vector<uint16_t> hostrec;
+        const int n_groups = (n + kGroupFrames - 1) / kGroupFrames;
+        for (int grp = 0; grp < n_groups; grp++) {
+        const int f0 = grp * kGroupFrames, f1 = std::min(n, f0 + kGroupFrames);
+        const uint32_t *goff = e->offsets_host + (size_t)f0 * g.ctuh + grp;
+        const uint8_t *gpay = e->packed_host + (size_t)f0 * e->frame_cap;
+        HB_CUDA(ctx, cudaEventSynchronize(e->ev_off[grp]));
         {
-            PackParams pp;
-            pp.frames = e->eframes_dev; pp.n_frames = n; pp.rows = g.ctuh; pp.row_cap = e->row_cap; pp.packed = e->packed_dev; pp.offsets = e->offsets_dev;
-            k_pack_scan<<<1, 1024, 0, st>>>(pp);
-            HB_LAUNCHED(ctx);
-            k_pack_copy<<<n * g.ctuh, 128, 0, st>>>(pp);
-            HB_LAUNCHED(ctx);
+            const uint32_t total = goff[(size_t)(f1 - f0) * g.ctuh];
+            if (total > (size_t)(f1 - f0) * e->frame_cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "packed bitstream exceeds the download buffer");
+            HB_CUDA(ctx, cudaMemcpyAsync(e->packed_host + (size_t)f0 * e->frame_cap, e->packed_dev + (size_t)f0 * e->frame_cap, total,
+                                         cudaMemcpyDeviceToHost, e->st_dl));
+            if (grp == n_groups - 1) HB_CUDA(ctx, cudaEventRecord(e->ev[3], e->st_dl));
+            HB_CUDA(ctx, cudaStreamSynchronize(e->st_dl));
         }
-        HB_CUDA(ctx, cudaEventRecord(e->ev[2], st));
-        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 4], st));
-        HB_CUDA(ctx, cudaMemcpyAsync(e->offsets_host, e->offsets_dev, sizeof(uint32_t) * ((size_t)n * g.ctuh + 1), cudaMemcpyDeviceToHost, st));
-        HB_CUDA(ctx, cudaMemcpyAsync(e->overflow_host, e->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-        HB_CUDA(ctx, cudaMemcpyAsync(e->ctl_host, e->ctl_dev, sizeof(FrameCtl) * n, cudaMemcpyDeviceToHost, st));
-        HB_CUDA(ctx, cudaStreamSynchronize(st));
-        if (*e->overflow_host) return hb_fail(ctx, HB_ERR_SPACE, "%s", "CABAC sub-stream exceeded its row buffer");
-        for (int i = 0; i < n; i++) qps[i] = e->ctl_host[i].qp;
-        const uint32_t total = e->offsets_host[(size_t)n * g.ctuh];
-        if (total > e->packed_cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "packed bitstream exceeds the download buffer");
-        HB_CUDA(ctx, cudaMemcpyAsync(e->packed_host, e->packed_dev, total, cudaMemcpyDeviceToHost, st));
-        HB_CUDA(ctx, cudaEventRecord(e->ev[3], st));
-        HB_CUDA(ctx, cudaStreamSynchronize(st));
-        {
+        if (grp == n_groups - 1) {
+            HB_CUDA(ctx, cudaStreamSynchronize(st));
+            if (*e->overflow_host) return hb_fail(ctx, HB_ERR_SPACE, "%s", "CABAC sub-stream exceeded its row buffer");
             float a = 0, b = 0;
             cudaEventElapsedTime(&a, e->ev[0], e->ev[3]);
             cudaEventElapsedTime(&b, e->ev[1], e->ev[2]);
             total_ms += a; kernel_ms += b;
-        }
-        if (e->profiling) {
-            float ms = 0;
-            for (int i = 0; i < n; i++) {
-                cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev[2 * i + 1]);
-                const int k = is_idr[i] ? 1 : 0;
-                e->prof_ms[k] += ms; e->prof_launches[k]++;
-            }
-            cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
-            cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
-        }
-        if (e->trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes}
-            std::vector<unsigned long long> tr((size_t)n * g.ctuh * 2);
-            cudaMemcpy(tr.data(), e->trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-            if (FILE *f = fopen(e->trace_path, "wb")) {
-                const unsigned long long hdr[2] = {(unsigned long long)n, (unsigned long long)g.ctuh};
-                fwrite(hdr, sizeof(hdr), 1, f);
-                for (size_t k = 0; k < (size_t)n * g.ctuh; k++) {
-                    const unsigned long long rec[3] = {tr[2 * k], tr[2 * k + 1], (unsigned long long)(e->offsets_host[k + 1] - e->offsets_host[k])};
-                    fwrite(rec, sizeof(rec), 1, f);
+            if (e->profiling) {
+                float ms = 0;
+                for (int i = 0; i < n; i++) {
+                    cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev[2 * i + 1]);
+                    const int k = is_idr[i] ? 1 : 0;
+                    e->prof_ms[k] += ms; e->prof_launches[k]++;
                 }
-                fclose(f);
+                cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
+                cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
+            }
+            if (e->trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes}
+                std::vector<unsigned long long> tr((size_t)n * g.ctuh * 2);
+                cudaMemcpy(tr.data(), e->trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                if (FILE *f = fopen(e->trace_path, "wb")) {
+                    const unsigned long long hdr[2] = {(unsigned long long)n, (unsigned long long)g.ctuh};
+                    fwrite(hdr, sizeof(hdr), 1, f);
+                    for (size_t k = 0; k < (size_t)n * g.ctuh; k++) {
+                        const size_t fi = k / g.ctuh, gi = fi / kGroupFrames;
+                        const uint32_t *o = e->offsets_host + k + gi;
+                        const unsigned long long rec[3] = {tr[2 * k], tr[2 * k + 1], (unsigned long long)(o[1] - o[0])};
+                        fwrite(rec, sizeof(rec), 1, f);
+                    }
+                    fclose(f);
+                }
             }
         }
-        // ---- access-unit assembly on the host
-        std::vector<uint8_t> au, slice;
-        std::vector<uint16_t> hostrec;
-        for (int i = 0; i < n; i++) {
+        for (int i = f0; i < f1; i++) qps[i] = e->ctl_host[i].qp;
+        for (int i = f0; i < f1; i++) {
+
             au.clear();
             const bool idr = is_idr[i] != 0;
             const bool first_of_stream = e->frame_no - n + i == 0;
@@ -778,9 +826,9 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             slice.clear();
             std::vector<uint32_t> entry(g.ctuh);
             for (int r = 0; r < g.ctuh; r++) {
-                const uint32_t o0 = e->offsets_host[(size_t)i * g.ctuh + r], o1 = e->offsets_host[(size_t)i * g.ctuh + r + 1];
+                const uint32_t o0 = goff[(size_t)(i - f0) * g.ctuh + r], o1 = goff[(size_t)(i - f0) * g.ctuh + r + 1];
                 const size_t before = slice.size();
-                append_escaped(slice, e->packed_host + o0, o1 - o0);
+                append_escaped(slice, gpay + o0, o1 - o0);
                 entry[r] = (uint32_t)(slice.size() - before);
             }
             BitWriter h;
@@ -834,6 +882,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             }
             e->done.fetch_add(1);
         }
+        }      // drain groups
     }
     e->last_total_ms = total_ms;
     e->last_kernel_ms = kernel_ms;
