@@ -949,49 +949,61 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
 // neighbour samples (same availability / substitution rules as the real prediction), so that nothing here depends on the
 // reconstruction.  Writes the 35 distortions per CU; the wavefront kernel adds the signalling cost (which needs the real
 // most-probable modes), picks the mode and reconstructs.  One CTA walks CUs in a grid-stride loop.
-struct IntraSearchScratch {
-    pixel nb[65], flt[65];
+struct __align__(16) IntraSearchScratch {
+    pixel nb[68], flt[68];
     pixel src[16][16];
-    int cost[35];
     int dc;
 };
-__global__ void __launch_bounds__(kIntraThreads) k_intra_search(IntraParams p)
+// one warp per CU (grid-stride), no block barriers: lanes 0-15 / 16-31 take the 16 sub-blocks of two modes per round and
+// reduce their SATD with shuffles
+__global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParams p)
 {
-    __shared__ IntraSearchScratch s;
+    __shared__ IntraSearchScratch scratch[kIntraSearchThreads / 32];
     const Geom &g = p.g;
-    const int tid = threadIdx.x, bd = g.bit_depth, maxv = (1 << bd) - 1;
-    for (int cu = blockIdx.x; cu < g.cuw * g.cuh; cu += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, bd = g.bit_depth, maxv = (1 << bd) - 1;
+    IntraSearchScratch &s = scratch[warp];
+    const int nwarps = gridDim.x * (kIntraSearchThreads / 32);
+    for (int cu = blockIdx.x * (kIntraSearchThreads / 32) + warp; cu < g.cuw * g.cuh; cu += nwarps) {
         const int cx = cu % g.cuw, cy = cu / g.cuw, x0 = cx * 16, y0 = cy * 16;
-        if (tid < 65) s.nb[tid] = gather_one(p.src.y, g.src_stride, g, cx, cy, 16, tid, bd);
-        if (tid >= 96 && tid < 96 + 35) s.cost[tid - 96] = 0;
-        if (tid >= 256 && tid < 512) {
-            const int t = tid - 256;
-            s.src[t >> 4][t & 15] = p.src.y[(size_t)(y0 + (t >> 4)) * g.src_stride + x0 + (t & 15)];
+        for (int i = lane; i < 65; i += 32) s.nb[i] = gather_one(p.src.y, g.src_stride, g, cx, cy, 16, i, bd);
+        {
+            const int row = lane >> 1, c0 = (lane & 1) * 8;
+            *reinterpret_cast<uint4 *>(&s.src[row][c0]) = *reinterpret_cast<const uint4 *>(p.src.y + (size_t)(y0 + row) * g.src_stride + x0 + c0);
         }
-        __syncthreads();
-        if (tid < 65) s.flt[tid] = (pixel)intra_filtered(s.nb, 16, tid);
-        if (tid >= 64 && tid < 96) {
-            const int l = tid - 64;
-            int v = l < 16 ? s.nb[1 + l] + s.nb[33 + l] : 0;
+        __syncwarp();
+        int fl[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) fl[r] = lane + 32 * r < 65 ? intra_filtered(s.nb, 16, lane + 32 * r) : 0;
+        {
+            int v = lane < 16 ? s.nb[1 + lane] + s.nb[33 + lane] : 0;
             v = warp_sum(v);
-            if (l == 0) s.dc = (v + 16) >> 5;
+            if (lane == 0) s.dc = (v + 16) >> 5;
         }
-        __syncthreads();
-        // 35 modes x 16 sub-blocks: SATD accumulated per mode
-        for (int t = tid; t < 35 * 16; t += kIntraThreads) {
-            const int mode = t >> 4, sb = t & 15, sx = (sb & 3) * 4, sy = (sb >> 2) * 4;
+#pragma unroll
+        for (int r = 0; r < 3; r++) if (lane + 32 * r < 65) s.flt[lane + 32 * r] = (pixel)fl[r];
+        __syncwarp();
+        const int sb = lane & 15, sx = (sb & 3) * 4, sy = (sb >> 2) * 4;
+        int sv[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) sv[y][x] = s.src[sy + y][sx + x];
+#pragma unroll 1
+        for (int m0 = 0; m0 < 36; m0 += 2) {
+            const int mode = min(m0 + (lane >> 4), 34);          // the upper half idles on mode 34 twice in the last round
             const pixel *nbuf = intra_use_filter(4, mode) ? s.flt : s.nb;
             int d[4][4];
 #pragma unroll
             for (int y = 0; y < 4; y++)
 #pragma unroll
                 for (int x = 0; x < 4; x++)
-                    d[y][x] = (int)s.src[sy + y][sx + x] - intra_sample(nbuf, 16, 4, mode, sx + x, sy + y, true, maxv, s.dc);
-            atomicAdd(&s.cost[mode], hadamard4x4_abs(d) >> 1);
+                    d[y][x] = sv[y][x] - intra_sample(nbuf, 16, 4, mode, sx + x, sy + y, true, maxv, s.dc);
+            int c = hadamard4x4_abs(d) >> 1;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (sb == 0 && m0 + (lane >> 4) < 35) p.mode_cost[(size_t)cu * 35 + mode] = c;
         }
-        __syncthreads();
-        if (tid < 35) p.mode_cost[(size_t)cu * 35 + tid] = s.cost[tid];
-        __syncthreads();
+        __syncwarp();
     }
 }
 

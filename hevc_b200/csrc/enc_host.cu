@@ -639,7 +639,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     IntraParams ip;
                     ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
                     ip.ctl = e->ctl_dev + i; ip.second_pass = 0; ip.mode_cost = e->mode_cost;
-                    k_intra_search<<<std::min(g.cuw * g.cuh, 4 * ctx->sm_count), kIntraThreads, 0, st>>>(ip);
+                    k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);

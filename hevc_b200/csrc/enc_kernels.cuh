@@ -93,7 +93,7 @@ struct PackParams {
 };
 
 constexpr int kEntropyWarps = 4;
-constexpr int kIntraThreads = 576;        // k_intra_search CTA: the 35 x 16 mode-search tasks in one round
+constexpr int kIntraSearchThreads = 128;   // k_intra_search CTA: four warps, one CU each
 constexpr int kIntraReconThreads = 384;   // k_intra CTA: one thread per luma sample + one per chroma sample (both planes) of the CU
 constexpr int kBinStride = 61;            // 32-bit words per sub-block bin list (<= 60 entries, odd stride: no bank conflicts)
 constexpr int kHdrBins = 40, kTuHdrBins = 24;
