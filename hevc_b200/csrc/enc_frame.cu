@@ -364,13 +364,19 @@ __device__ __forceinline__ void merge_decide(const InterParams &p, WarpScratch &
     best = own;
     bsatd = p.satd_in[idx];
     int bcost = bsatd + ((lambda * (own_bits + 2)) >> 8) + 1;         // +1: ties go to a merge candidate
-#pragma unroll
+    // not unrolled: the body holds a full interpolation + SATD, six copies of it made the kernel miss the instruction cache
+    // (k_inter: 35 % of issue cycles stalled on instruction fetch); the candidate is picked with a select chain instead
+#pragma unroll 1
     for (int k = 0; k < 6; k++) {
-        if (!ok[k]) continue;
-        const MV m = cand[k];
+        MV m = cand[0];
+        bool okk = ok[0];
+#pragma unroll
+        for (int j = 1; j < 6; j++)
+            if (k == j) { m = cand[j]; okk = ok[j]; }
+        if (!okk) continue;
         bool dup = m.x == own.x && m.y == own.y;
 #pragma unroll
-        for (int j = 0; j < k; j++) dup |= ok[j] && cand[j].x == m.x && cand[j].y == m.y;
+        for (int j = 0; j < 5; j++) dup |= j < k && ok[j] && cand[j].x == m.x && cand[j].y == m.y;
         if (dup) continue;
         const MV cm = clamp_mv(g, x0, y0, m);
         if (cm.x != m.x || cm.y != m.y) continue;

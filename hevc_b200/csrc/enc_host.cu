@@ -284,8 +284,9 @@ struct hb_encoder {
     std::vector<cudaEvent_t> ev_chunk;   // [0, kMaxChunks): upload done, [kMaxChunks, 2 kMaxChunks): chain done
     std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
     int profiling = 0;
-    float prof_ms[6] = {};            // inter, intra, coarse, entropy(+pack), ingest, other
-    int prof_launches[6] = {};
+    float prof_ms[8] = {};            // inter (3 kernels), intra, coarse, entropy(+pack), ingest, chain, k_me alone, spare
+    int prof_launches[8] = {};
+    std::vector<cudaEvent_t> kev_me;  // after the motion-search kernel of each P frame
     float last_total_ms = 0, last_kernel_ms = 0;
     std::vector<uint8_t> vps, sps, pps;
 };
@@ -445,6 +446,8 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     }
     E->kev.resize((size_t)2 * max_batch + 8);
     for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
+    E->kev_me.resize((size_t)max_batch);
+    for (auto &ev : E->kev_me) HB_CUDA(ctx, cudaEventCreate(&ev));
     HB_CUDA(ctx, upload_inter_constants(ctx->stream));
     E->vps = make_vps(p);
     E->sps = make_sps(p, g.wc, g.hc);
@@ -475,6 +478,7 @@ void hb_enc_destroy(hb_encoder *e)
     if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
     for (auto &q : e->st_entropy) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
     for (auto &ev : e->kev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->kev_me) if (ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -660,6 +664,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     ip.mv_in = nullptr; ip.satd_in = nullptr; ip.mv_out = e->mvf[0]; ip.satd_out = e->satdf[0];
                     k_me<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
+                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev_me[i], st));
                     ip.mv_in = e->mvf[0]; ip.satd_in = e->satdf[0]; ip.mv_out = e->mvf[1]; ip.satd_out = e->satdf[1];
                     k_merge<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
@@ -767,6 +772,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev[2 * i + 1]);
                     const int k = is_idr[i] ? 1 : 0;
                     e->prof_ms[k] += ms; e->prof_launches[k]++;
+                    if (!is_idr[i]) { cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev_me[i]); e->prof_ms[6] += ms; e->prof_launches[6]++; }
                 }
                 cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
                 cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
@@ -890,7 +896,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
     return HB_OK;
 }
 
-int hb_enc_profile(hb_encoder *e, int enable, float ms[6], int launches[6])
+int hb_enc_profile(hb_encoder *e, int enable, float ms[8], int launches[8])
 {
     if (!e) return HB_ERR_ARG;
     if (ms) memcpy(ms, e->prof_ms, sizeof(e->prof_ms));

@@ -153,10 +153,10 @@ class B200Encoder:
 
     def profile(self, enable: int = -1):
         """-> ({class: ms}, {class: launches}) accumulated since the last reset; enable=1/0 switches recording and resets."""
-        ms, ln = (C.c_float * 6)(), (C.c_int * 6)()
+        ms, ln = (C.c_float * 8)(), (C.c_int * 8)()
         self.L.hb_enc_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         self.L.hb_enc_profile(self.h, enable, ms, ln)
-        names = ('inter', 'intra', 'coarse', 'entropy', 'ingest', 'chain')
+        names = ('inter', 'intra', 'coarse', 'entropy', 'ingest', 'chain', 'me', 'spare')
         return dict(zip(names, ms)), dict(zip(names, ln))
 
     def request_stop(self):

@@ -171,9 +171,10 @@ int hb_enc_encode(hb_encoder *enc, const hb_frames *frames, int force_idr, uint8
 int hb_enc_last_timing(const hb_encoder *enc, float *total_ms, float *kernel_ms);
 /* per-kernel-class device time (CUDA events around each launch on the encoder's stream), accumulated since the
  * last call: index 0 inter-frame kernel, 1 intra-frame kernel, 2 coarse search, 3 entropy + compaction, 4 ingest,
- * 5 whole frame chain (inter/intra + border + mode kernels).  enable: 1/0 switches the event recording and
- * resets the accumulators, -1 only reads. */
-int hb_enc_profile(hb_encoder *enc, int enable, float ms[6], int launches[6]);
+ * 5 whole frame chain (inter/intra + border + mode kernels), 6 the motion-search kernel k_me alone, 7 unused.  Index 0 spans
+ * the three inter kernels (k_me, k_merge, k_inter) of a P frame.  enable: 1/0 switches the event recording and resets the
+ * accumulators, -1 only reads. */
+int hb_enc_profile(hb_encoder *enc, int enable, float ms[8], int launches[8]);
 /* cooperative cancel (reference stop_event, core/transcoder.py:511-516): polled between frames */
 int hb_enc_request_stop(hb_encoder *enc);
 int hb_enc_poll_progress(const hb_encoder *enc, int *frames_done);
