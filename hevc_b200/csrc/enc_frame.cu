@@ -246,6 +246,17 @@ __device__ __forceinline__ void interp_hpass(WarpScratch &s, int ix, int iy0, in
     int th[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) th[k] = c_luma_pack[fx][k];
+    if (fx == 0) {           // integer column: taps (0,0,0,64,0,0,0,0) -- a shift, no filtering
+        const int sh = 6 - shift1;
+        for (int task = lane; task < 2 * rows; task += 32) {
+            const int r = task >> 1, c0 = (task & 1) * 8;
+            const pixel *wp = &s.win[iy0 - 3 + r][ix + c0];
+#pragma unroll
+            for (int k = 0; k < 8; k++) s.tmpT[c0 + k][r] = (int16_t)((int)wp[k] << sh);
+        }
+        __syncwarp();
+        return;
+    }
     for (int task = lane; task < 2 * rows; task += 32) {
         const int r = task >> 1, c0 = (task & 1) * 8;
         const int s0 = ix - 3 + c0, w0 = s0 >> 1;
@@ -443,29 +454,37 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
         int sq[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) sq[k] = s.src[h + 2 * k][col];
+        // lane t < 25 owns position t (raster over dy, dx): its validity and vector cost are computed once, in parallel
+        int my_cost = -1;
+        if (lane < 25 && lane != 12) {
+            const MV m{centre.x + 4 * (lane % 5 - 2), centre.y + 4 * (lane / 5 - 2)};
+            const MV cm = clamp_mv(g, x0, y0, m);
+            if (cm.x == m.x && cm.y == m.y) my_cost = mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+        }
 #pragma unroll 1
-        for (int dy = -2; dy <= 2; dy++)
-#pragma unroll 1
-            for (int dx = -2; dx <= 2; dx++) {
-                if (!dx && !dy) continue;
-                const MV m{centre.x + 4 * dx, centre.y + 4 * dy};
-                const MV cm = clamp_mv(g, x0, y0, m);
-                if (cm.x != m.x || cm.y != m.y) continue;
-                const pixel *w = &s.win[6 + dy + h][6 + dx + col + woff];
-                int sad = 0;
+        for (int t = 0; t < 25; t++) {
+            const int vc = __shfl_sync(0xffffffffu, my_cost, t);
+            if (vc < 0) continue;
+            const int dx = t % 5 - 2, dy = t / 5 - 2;
+            const pixel *w = &s.win[6 + dy + h][6 + dx + col + woff];
+            int sad = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    sad += abs(sq[k] - (int)w[2 * k * 40]);
-                const int cost = warp_sum(sad) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
-                if (cost < bcost) { bcost = cost; best = m; }
-            }
+            for (int k = 0; k < 8; k++)
+                sad += abs(sq[k] - (int)w[2 * k * 40]);
+            const int cost = warp_sum(sad) + vc;
+            if (cost < bcost) { bcost = cost; best = MV{centre.x + 4 * dx, centre.y + 4 * dy}; }
+        }
     }
     // ---- sub-sample stages: SATD on the normative interpolation
     const int wx0 = (centre.x >> 2) - 6 - woff, wy0 = (centre.y >> 2) - 6;     // window origin (sample [0][0]) relative to the block position
     int st[8], pv[8];        // source / prediction column segments: column lane >> 1, rows 8 * (lane & 1) + k
 #pragma unroll
     for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];
-    interp_cols(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane, pv);
+    {   // `best` is an integer position here: its prediction is the window itself (the two-pass filter reduces to the identity)
+        const pixel *w = &s.win[(best.y >> 2) - wy0 + (lane & 1) * 8][(best.x >> 2) - wx0 + (lane >> 1)];
+#pragma unroll
+        for (int k = 0; k < 8; k++) pv[k] = w[k * 40];
+    }
     bcost = satd_cols(st, pv, lane) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
 #pragma unroll 1
     for (int step = 2; step >= 1; step--) {
