@@ -16,6 +16,19 @@ __constant__ int c_luma_pack[4][5];
 __constant__ int8_t c_chroma_taps[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
                                            {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
 __device__ __forceinline__ int clampd(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// sum of absolute differences of four packed bytes, accumulated: one VABSDIFF4.U8.ACC
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t acc)
+{
+    uint32_t r;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(acc));
+    return r;
+}
+// 8 most significant bits of four 16-bit samples held as two pair words -> four packed bytes
+__device__ __forceinline__ uint32_t pack4_msb8(uint32_t lo, uint32_t hi, int sh)
+{
+    const uint32_t a = (lo >> sh) & 0x00ff00ffu, b = (hi >> sh) & 0x00ff00ffu;     // bytes 0,2 of each
+    return __byte_perm(a, b, 0x6420);
+}
 
 // ================================================================================================ ingest
 // one thread per 4x4 luma block: copies (with edge replication into the coded-size padding), converts the
@@ -45,7 +58,7 @@ __global__ void __launch_bounds__(256) k_ingest(IngestParams p)
             uint2 o = make_uint2(px[0] | (px[1] << 16), px[2] | (px[3] << 16));
             *reinterpret_cast<uint2 *>(p.src.y + (size_t)(4 * by + j) * g.src_stride + 4 * bx) = o;
         }
-        p.ds[(size_t)by * g.dsw + bx] = (pixel)(acc >> 4);
+        p.ds[(size_t)by * g.dsw + bx] = (uint8_t)((acc >> 4) >> (g.bit_depth - 8));     // coarse search works on the 8 MSBs
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const int yy = min(2 * by + j, ch - 1);
@@ -97,37 +110,46 @@ __global__ void __launch_bounds__(256) k_border(Planes rec, Geom g)
 }
 
 // ================================================================================================ coarse search
-// one CTA per CTU (8x8 block of the quarter-resolution plane), blockIdx.y = frame of the batch.
-// 625 candidates (+-12), SAD + bias * (|dx| + |dy|); winner = min over (cost << 10 | raster index).
+// one CTA per CTU (8x8 block of the 8-bit quarter-resolution plane), blockIdx.y = frame of the batch.
+// 625 candidates (+-12), byte SAD (VABSDIFF4: four samples + accumulate per instruction) + |dx| + |dy|; winner = min over
+// (cost << 10 | raster index).  The 32x32 search window is kept in four byte-shifted copies so that every candidate reads
+// aligned words; the current block sits in 16 registers.
+constexpr int kCoarseCopyWords = 32 * 9 + 8;       // row stride 36 bytes; +8 words so that the copies start 8 banks apart
 __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
 {
-    __shared__ pixel cur[8][8];
-    __shared__ pixel win[32][33];
+    __shared__ uint32_t curw[16];
+    __shared__ uint32_t win[4][kCoarseCopyWords];
     __shared__ unsigned long long best[4];
     const Geom &g = p.g;
     const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw, f = blockIdx.y;
-    const pixel *dcur = p.ds + (size_t)(f + 1) * p.ds_frame_stride, *dprev = p.ds + (size_t)f * p.ds_frame_stride;
+    const uint8_t *dcur = p.ds + (size_t)(f + 1) * p.ds_frame_stride, *dprev = p.ds + (size_t)f * p.ds_frame_stride;
     const int tid = threadIdx.x;
     if (tid < 64) {
         const int i = tid & 7, j = tid >> 3;
-        cur[j][i] = dcur[(size_t)clampd(ty * 8 + j, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i, 0, g.dsw - 1)];
+        reinterpret_cast<uint8_t *>(curw)[tid] = dcur[(size_t)clampd(ty * 8 + j, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i, 0, g.dsw - 1)];
     }
     for (int k = tid; k < 32 * 32; k += 128) {
         const int i = k & 31, j = k >> 5;
-        win[j][i] = dprev[(size_t)clampd(ty * 8 + j - kCmeRange, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i - kCmeRange, 0, g.dsw - 1)];
+        const uint8_t v = dprev[(size_t)clampd(ty * 8 + j - kCmeRange, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i - kCmeRange, 0, g.dsw - 1)];
+#pragma unroll
+        for (int sft = 0; sft < 4; sft++)
+            if (i >= sft) reinterpret_cast<uint8_t *>(win[sft])[j * 36 + i - sft] = v;
     }
     __syncthreads();
-    const int bias = 1 << (g.bit_depth - 8);
+    uint32_t c[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) c[t] = curw[t];
     unsigned long long mine = ~0ull;
-    for (int c = tid; c < 625; c += 128) {
-        const int dy = c / 25, dx = c % 25;     // offsets already shifted by +12
-        int sad = 0;
+    for (int cand = tid; cand < 625; cand += 128) {
+        const int dy = cand / 25, dx = cand % 25;     // offsets already shifted by +12
+        const uint32_t *w = win[dx & 3] + dy * 9 + (dx >> 2);
+        uint32_t sad = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                sad += abs((int)cur[j][i] - (int)win[j + dy][i + dx]);
-        const unsigned long long key = ((unsigned long long)(sad + bias * (abs(dx - kCmeRange) + abs(dy - kCmeRange))) << 10) | (unsigned)c;
+        for (int j = 0; j < 8; j++) {
+            sad = sad4(c[2 * j], w[j * 9], sad);
+            sad = sad4(c[2 * j + 1], w[j * 9 + 1], sad);
+        }
+        const unsigned long long key = ((unsigned long long)(sad + abs(dx - kCmeRange) + abs(dy - kCmeRange)) << 10) | (unsigned)cand;
         mine = key < mine ? key : mine;
     }
     for (int off = 16; off; off >>= 1) {
@@ -139,10 +161,10 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
     if (tid == 0) {
         unsigned long long b = best[0];
         for (int k = 1; k < 4; k++) b = best[k] < b ? best[k] : b;
-        const int c = (int)(b & 1023);
+        const int cbest = (int)(b & 1023);
         int16_t *out = p.cmv + ((size_t)f * g.ctuw * g.ctuh + blockIdx.x) * 2;
-        out[0] = (int16_t)(c % 25 - kCmeRange);
-        out[1] = (int16_t)(c / 25 - kCmeRange);
+        out[0] = (int16_t)(cbest % 25 - kCmeRange);
+        out[1] = (int16_t)(cbest / 25 - kCmeRange);
     }
 }
 
@@ -418,62 +440,64 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
     const int lambda = p.ctl->lambda;
     const int row = lane >> 1, c0 = (lane & 1) * 8;
 
-    // source block: registers (for SAD) + shared memory (for SATD)
-    int sp[8];
+    // source block: shared memory (for SATD) + its 8 most significant bits as packed bytes in registers (for the integer SADs)
+    const int sh8 = bd - 8, lambda8 = lambda >> sh8;          // the integer stages compare 8-bit samples, lambda at 8-bit scale
+    uint32_t s8lo, s8hi;
     {
         const uint4 v = *reinterpret_cast<const uint4 *>(p.src.y + (size_t)(y0 + row) * g.src_stride + x0 + c0);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) { sp[2 * k] = w[k] & 0xffff; sp[2 * k + 1] = w[k] >> 16; }
         *reinterpret_cast<uint4 *>(&s.src[row][c0]) = v;
+        s8lo = pack4_msb8(v.x, v.y, sh8);
+        s8hi = pack4_msb8(v.z, v.w, sh8);
     }
     const MV pred = clamp_mv(g, x0, y0, ctu_mv(g, p.cmv, tx, ty));
     MV best{0, 0};
     int bcost = 0x7fffffff;
-    // ---- integer stage 1: six candidates straight from global memory
+    // ---- integer stage 1: six candidates straight from global memory (lane -> row lane >> 1, 8 samples)
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
         MV c = k == 0 ? MV{0, 0} : k == 1 ? pred : k == 2 ? ctu_mv(g, p.cmv, tx - 1, ty) : k == 3 ? ctu_mv(g, p.cmv, tx, ty - 1)
                : k == 4 ? ctu_mv(g, p.cmv, tx + 1, ty) : ctu_mv(g, p.cmv, tx, ty + 1);
         c = clamp_mv(g, x0, y0, c);
         const pixel *r = p.ref.y + (ptrdiff_t)(y0 + (c.y >> 2) + row) * g.rec_stride + x0 + (c.x >> 2) + c0;
-        int sad = 0;
+        uint32_t rw[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            sad += abs(sp[i] - (int)r[i]);
-        const int cost = warp_sum(sad) + mv_cost(lambda, c.x, c.y, pred.x, pred.y);
+        for (int i = 0; i < 4; i++) rw[i] = (uint32_t)r[2 * i] | ((uint32_t)r[2 * i + 1] << 16);
+        const uint32_t sad = sad4(s8hi, pack4_msb8(rw[2], rw[3], sh8), sad4(s8lo, pack4_msb8(rw[0], rw[1], sh8), 0));
+        const int cost = warp_sum((int)sad) + mv_cost(lambda8, c.x, c.y, pred.x, pred.y);
         if (cost < bcost) { bcost = cost; best = c; }
     }
     const MV centre = best;
     const int woff = stage_window(p, bar, win_smem, x0, y0, centre, lane);
-    // ---- integer stage 2: 5x5 square, SAD from shared memory.  Lane -> column lane >> 1, rows (lane & 1) + 2k: the 32 lanes of
-    //      one load then touch 16-18 distinct words in two runs 20 banks apart -- no bank conflicts (the row-per-lane layout of
-    //      stage 1 is 4-way conflicted on the 80-byte window rows).
+    // ---- integer stage 2: 5x5 square by byte SAD.  The window's 8 MSBs are packed once into a byte copy (aliased onto the
+    //      interpolation scratch, unused so far); a candidate row is three aligned words funnel-shifted to the block position.
     {
-        const int col = lane >> 1, h = lane & 1;
-        int sq[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) sq[k] = s.src[h + 2 * k][col];
+        uint32_t *win8 = reinterpret_cast<uint32_t *>(&s.tmpT[0][0]);           // [28][10] words = 28 rows x 40 bytes
+        for (int t = lane; t < 28 * 10; t += 32) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(&s.win[t / 10][(t % 10) * 4]);
+            win8[t] = pack4_msb8(v.x, v.y, sh8);
+        }
+        __syncwarp();
         // lane t < 25 owns position t (raster over dy, dx): its validity and vector cost are computed once, in parallel
         int my_cost = -1;
         if (lane < 25 && lane != 12) {
             const MV m{centre.x + 4 * (lane % 5 - 2), centre.y + 4 * (lane / 5 - 2)};
             const MV cm = clamp_mv(g, x0, y0, m);
-            if (cm.x == m.x && cm.y == m.y) my_cost = mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+            if (cm.x == m.x && cm.y == m.y) my_cost = mv_cost(lambda8, m.x, m.y, pred.x, pred.y);
         }
 #pragma unroll 1
         for (int t = 0; t < 25; t++) {
             const int vc = __shfl_sync(0xffffffffu, my_cost, t);
             if (vc < 0) continue;
             const int dx = t % 5 - 2, dy = t / 5 - 2;
-            const pixel *w = &s.win[6 + dy + h][6 + dx + col + woff];
-            int sad = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                sad += abs(sq[k] - (int)w[2 * k * 40]);
-            const int cost = warp_sum(sad) + vc;
+            const int colb = 6 + dx + woff + c0;                              // byte column of this lane's first sample
+            const uint32_t *w = win8 + (6 + dy + row) * 10 + (colb >> 2);
+            const int fs = (colb & 3) * 8;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const uint32_t sad = sad4(s8hi, __funnelshift_r(w1, w2, fs), sad4(s8lo, __funnelshift_r(w0, w1, fs), 0));
+            const int cost = warp_sum((int)sad) + vc;
             if (cost < bcost) { bcost = cost; best = MV{centre.x + 4 * dx, centre.y + 4 * dy}; }
         }
+        __syncwarp();
     }
     // ---- sub-sample stages: SATD on the normative interpolation
     const int wx0 = (centre.x >> 2) - 6 - woff, wy0 = (centre.y >> 2) - 6;     // window origin (sample [0][0]) relative to the block position

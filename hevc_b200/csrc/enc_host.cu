@@ -245,7 +245,7 @@ struct hb_encoder {
     std::vector<FrameSlot> slot;
     pixel *rec_base[2][3] = {};
     Planes rec[2];
-    pixel *ds = nullptr;              // [max_batch + 1][dsh * dsw]
+    uint8_t *ds = nullptr;            // [max_batch + 1][dsh * dsw] quarter-resolution planes (8 MSBs)
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
     int *mode_cost = nullptr;         // [cus][35] intra mode search result of the key frame in flight
     uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
@@ -740,7 +740,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
         HB_LAUNCHED(ctx);
         // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
-        HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(pixel), cudaMemcpyDeviceToDevice, st));
+        HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(uint8_t), cudaMemcpyDeviceToDevice, st));
         if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
         // ---- drain: per group wait for its sizes, download its payload, assemble its access units (the GPU keeps encoding)
         std::vector<uint8_t> au, slice;

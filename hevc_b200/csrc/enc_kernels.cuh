@@ -15,12 +15,12 @@ struct IngestParams {
     int fmt, w, h;                       // display size
     int up_shift, down_shift;
     Planes src;
-    pixel *ds;
+    uint8_t *ds;                         // quarter-resolution plane, 8 most significant bits
 };
 
 struct CoarseParams {
     Geom g;
-    const pixel *ds;                     // [slots][dsh * dsw]; frame f of the batch = slot f + 1, slot f = its predecessor
+    const uint8_t *ds;                   // [slots][dsh * dsw]; frame f of the batch = slot f + 1, slot f = its predecessor
     size_t ds_frame_stride;
     int16_t *cmv;                        // [frames][ctuh * ctuw][2]
 };

@@ -300,7 +300,8 @@ static pixel ds_at(const plane *d, int x, int y) { return d->p[(size_t)clampi(y,
 static void coarse_search(orc_encoder *e)
 {
     const plane *cur = &e->ds[e->cur_ds], *prev = &e->ds[1 - e->cur_ds];
-    const int bias = 1 << (e->prm.bit_depth - 8);
+    /* the search runs on the 8 most significant bits of the quarter-resolution samples (byte SAD on the GPU) */
+    const int sh = e->prm.bit_depth - 8, bias = 1;
     for (int ty = 0; ty < e->ctuh; ty++)
         for (int tx = 0; tx < e->ctuw; tx++) {
             long best = -1;
@@ -310,7 +311,7 @@ static void coarse_search(orc_encoder *e)
                     long sad = 0;
                     for (int j = 0; j < 8; j++)
                         for (int i = 0; i < 8; i++)
-                            sad += abs((int)ds_at(cur, tx * 8 + i, ty * 8 + j) - (int)ds_at(prev, tx * 8 + i + dx, ty * 8 + j + dy));
+                            sad += abs((int)(ds_at(cur, tx * 8 + i, ty * 8 + j) >> sh) - (int)(ds_at(prev, tx * 8 + i + dx, ty * 8 + j + dy) >> sh));
                     const long cost = sad + bias * (abs(dx) + abs(dy));
                     if (best < 0 || cost < best) { best = cost; bdx = dx; bdy = dy; }
                 }
@@ -320,6 +321,16 @@ static void coarse_search(orc_encoder *e)
 }
 
 typedef struct { int x, y; } mv_t;
+
+/* SAD of a 16x16 block on the 8 most significant bits of the samples (integer search stages; byte SAD on the GPU) */
+static long sad8_16x16(const pixel *a, int sa, const pixel *b, int sb, int sh)
+{
+    long s = 0;
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++)
+            s += abs((int)(a[y * sa + x] >> sh) - (int)(b[y * sb + x] >> sh));
+    return s;
+}
 
 static mv_t clamp_mv(const orc_encoder *e, int x0, int y0, mv_t m)
 {
@@ -357,11 +368,12 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             mv_t cand[6] = {{0, 0}, pred, ctu_mv(e, tx - 1, ty), ctu_mv(e, tx, ty - 1), ctu_mv(e, tx + 1, ty), ctu_mv(e, tx, ty + 1)};
             mv_t best = {0, 0};
             long bcost = -1;
-            /* integer stage: SAD */
+            /* integer stages: SAD on 8-bit samples, lambda at 8-bit scale */
+            const int lambda8 = k_lambda_q8[qp], sh8 = bd - 8;
             for (int k = 0; k < 6; k++) {
                 const mv_t m = clamp_mv(e, x0, y0, cand[k]);
                 const pixel *r = ref[0].p + (size_t)(y0 + (m.y >> 2)) * ref[0].stride + x0 + (m.x >> 2);
-                const long cost = orc_sad(src, ss, r, ref[0].stride, 16, 16) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                const long cost = sad8_16x16(src, ss, r, ref[0].stride, sh8) + mv_cost(lambda8, m.x, m.y, pred.x, pred.y);
                 if (bcost < 0 || cost < bcost) { bcost = cost; best = m; }
             }
             {
@@ -373,7 +385,7 @@ static void encode_inter_frame(orc_encoder *e, int qp)
                         const mv_t cm = clamp_mv(e, x0, y0, m);
                         if (cm.x != m.x || cm.y != m.y) continue;
                         const pixel *r = ref[0].p + (size_t)(y0 + (m.y >> 2)) * ref[0].stride + x0 + (m.x >> 2);
-                        const long cost = orc_sad(src, ss, r, ref[0].stride, 16, 16) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                        const long cost = sad8_16x16(src, ss, r, ref[0].stride, sh8) + mv_cost(lambda8, m.x, m.y, pred.x, pred.y);
                         if (cost < bcost) { bcost = cost; best = m; }
                     }
             }
