@@ -485,10 +485,9 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
             if (cm.x == m.x && cm.y == m.y) my_cost = mv_cost(lambda8, m.x, m.y, pred.x, pred.y);
         }
 #pragma unroll 1
-        for (int t = 0; t < 25; t++) {
+        for (int t = 0, dx = -2, dy = -2; t < 25; t++, dx = dx == 2 ? -2 : dx + 1, dy += dx == -2) {
             const int vc = __shfl_sync(0xffffffffu, my_cost, t);
             if (vc < 0) continue;
-            const int dx = t % 5 - 2, dy = t / 5 - 2;
             const int colb = 6 + dx + woff + c0;                              // byte column of this lane's first sample
             const uint32_t *w = win8 + (6 + dy + row) * 10 + (colb >> 2);
             const int fs = (colb & 3) * 8;
@@ -698,9 +697,15 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
     int16_t *ctmp = &s.tmpT[0][0];              // [2][11][8]
     {
         const ptrdiff_t off = (ptrdiff_t)(cy * 8 + (best.y >> 3) - 1) * g.recc_stride + cx * 8 + (best.x >> 3) - 1;
-        for (int i = lane; i < 2 * 11 * 11; i += 32) {
-            const int pl = i / 121, r = (i % 121) / 11, c = i % 11;
-            cwin[pl * 132 + r * 12 + c] = (pl ? p.ref.v : p.ref.u)[off + (ptrdiff_t)r * g.recc_stride + c];
+        // lane -> (plane, column); the 11 rows are 11 independent loads in flight (no per-sample index arithmetic)
+        const int pl = lane >> 4, c = lane & 15;
+        if (c < 11) {
+            const pixel *src = (pl ? p.ref.v : p.ref.u) + off + c;
+            pixel v[11];
+#pragma unroll
+            for (int r = 0; r < 11; r++) v[r] = src[(ptrdiff_t)r * g.recc_stride];
+#pragma unroll
+            for (int r = 0; r < 11; r++) cwin[pl * 132 + r * 12 + c] = v[r];
         }
     }
     __syncwarp();
