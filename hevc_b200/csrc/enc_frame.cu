@@ -226,17 +226,17 @@ __device__ __forceinline__ MV ctu_mv(const Geom &g, const int16_t *cmv, int tx, 
 // 8-tap filter on sample pairs held as 32-bit words: result for the sample at position `rel` (in samples) of w[]
 //   even rel: taps (t0,t1)(t2,t3)(t4,t5)(t6,t7) on words rel/2 ..;  odd rel: (0,t0)(t1,t2)(t3,t4)(t5,t6)(t7,0) on words (rel-1)/2 ..
 template <int REL>
-__device__ __forceinline__ int tap8(const int (&w)[8], const int (&t)[5])
+__device__ __forceinline__ int tap8(const int (&w)[8], const int (&t)[5], int init = 0)
 {
     if constexpr ((REL & 1) == 0) {
         constexpr int b = REL / 2;
-        int acc = __dp2a_lo(w[b], t[0], 0);
+        int acc = __dp2a_lo(w[b], t[0], init);
         acc = __dp2a_hi(w[b + 1], t[0], acc);
         acc = __dp2a_lo(w[b + 2], t[1], acc);
         return __dp2a_hi(w[b + 3], t[1], acc);
     } else {
         constexpr int b = (REL - 1) / 2;
-        int acc = __dp2a_lo(w[b], t[2], 0);
+        int acc = __dp2a_lo(w[b], t[2], init);
         acc = __dp2a_hi(w[b + 1], t[2], acc);
         acc = __dp2a_lo(w[b + 2], t[3], acc);
         acc = __dp2a_hi(w[b + 3], t[3], acc);
@@ -295,7 +295,9 @@ __device__ __forceinline__ void interp_hpass(WarpScratch &s, int ix, int iy0, in
 
 __device__ __forceinline__ void interp_vpass(WarpScratch &s, int ro, int fy, int bd, int lane, int (&pv)[8])
 {
-    const int s14 = 14 - bd, off14 = 1 << (s14 - 1), maxv = (1 << bd) - 1;
+    // ((acc >> 6) + off14) >> s14 == (acc + (off14 << 6)) >> (6 + s14) (nested floor divisions), so the rounding offset is the
+    // accumulator's start value and one shift remains
+    const int s14 = 14 - bd, rnd = (1 << (s14 - 1)) << 6, sh = 6 + s14, maxv = (1 << bd) - 1;
     int tv[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) tv[k] = c_luma_pack[fy][k];
@@ -305,15 +307,15 @@ __device__ __forceinline__ void interp_vpass(WarpScratch &s, int ro, int fy, int
     const int w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     int acc[8];
     if (ro) {
-        acc[0] = tap8<1>(w, tv); acc[1] = tap8<2>(w, tv); acc[2] = tap8<3>(w, tv); acc[3] = tap8<4>(w, tv);
-        acc[4] = tap8<5>(w, tv); acc[5] = tap8<6>(w, tv); acc[6] = tap8<7>(w, tv); acc[7] = tap8<8>(w, tv);
+        acc[0] = tap8<1>(w, tv, rnd); acc[1] = tap8<2>(w, tv, rnd); acc[2] = tap8<3>(w, tv, rnd); acc[3] = tap8<4>(w, tv, rnd);
+        acc[4] = tap8<5>(w, tv, rnd); acc[5] = tap8<6>(w, tv, rnd); acc[6] = tap8<7>(w, tv, rnd); acc[7] = tap8<8>(w, tv, rnd);
     } else {
-        acc[0] = tap8<0>(w, tv); acc[1] = tap8<1>(w, tv); acc[2] = tap8<2>(w, tv); acc[3] = tap8<3>(w, tv);
-        acc[4] = tap8<4>(w, tv); acc[5] = tap8<5>(w, tv); acc[6] = tap8<6>(w, tv); acc[7] = tap8<7>(w, tv);
+        acc[0] = tap8<0>(w, tv, rnd); acc[1] = tap8<1>(w, tv, rnd); acc[2] = tap8<2>(w, tv, rnd); acc[3] = tap8<3>(w, tv, rnd);
+        acc[4] = tap8<4>(w, tv, rnd); acc[5] = tap8<5>(w, tv, rnd); acc[6] = tap8<6>(w, tv, rnd); acc[7] = tap8<7>(w, tv, rnd);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        pv[k] = clampd(((acc[k] >> 6) + off14) >> s14, 0, maxv);
+        pv[k] = clampd(acc[k] >> sh, 0, maxv);
 }
 
 __device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane, int (&pv)[8])
