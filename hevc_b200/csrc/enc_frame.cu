@@ -338,12 +338,12 @@ __device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8],
         v[g] = a0 + a2; v[g + 1] = a1 + a3; v[g + 2] = a0 - a2; v[g + 3] = a1 - a3;
     }
 #pragma unroll
-    for (int m = 2; m <= 4; m <<= 1)
+    for (int m = 2; m <= 4; m <<= 1) {
+        int sgn = (lane & m) ? -1 : 1;                // butterfly as one multiply-add per value: partner + sign * own
+        asm("" : "+r"(sgn));                          // opaque, or the compiler turns the product back into select + negate + add
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int o = __shfl_xor_sync(0xffffffffu, v[k], m);
-            v[k] = (lane & m) ? o - v[k] : v[k] + o;
-        }
+        for (int k = 0; k < 8; k++) v[k] = __shfl_xor_sync(0xffffffffu, v[k], m) + sgn * v[k];
+    }
     int sum = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) sum += abs(v[k]);
