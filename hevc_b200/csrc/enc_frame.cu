@@ -320,6 +320,12 @@ __device__ __forceinline__ void interp_vpass(WarpScratch &s, int ro, int fy, int
 
 __device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane, int (&pv)[8])
 {
+    if ((fx | fy) == 0) {        // integer position (e.g. the zero vector): the two-pass filter reduces to the identity
+        const pixel *w = &s.win[iy + (lane & 1) * 8][ix + (lane >> 1)];
+#pragma unroll
+        for (int k = 0; k < 8; k++) pv[k] = w[k * 40];
+        return;
+    }
     interp_hpass(s, ix, iy, fx, 23, bd, lane);
     interp_vpass(s, 0, fy, bd, lane, pv);
     __syncwarp();
