@@ -234,6 +234,35 @@ struct FrameSlot {
 
 }  // namespace
 
+// Everything one batch owns between being enqueued and being drained.  Two sets alternate, so that the frame chain of the
+// next batch (and its uploads) run while the CABAC tail of the previous one finishes and the host assembles its access units.
+struct BatchSet {
+    std::vector<FrameSlot> slot;      // src planes are shared between the sets (the frame chain is serial)
+    uint8_t *staging = nullptr;       // raw input frames
+    int *overflow = nullptr, *row_ready_all = nullptr;
+    FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
+    EntropyFrame *eframes_dev = nullptr;
+    unsigned long long *trace_dev = nullptr;   // debug: per-row CABAC timestamps, only with HB_ENTROPY_TRACE=<file>
+    uint32_t *offsets_dev = nullptr;
+    uint8_t *packed_dev = nullptr;
+    // pinned host
+    uint32_t *offsets_host = nullptr;
+    uint8_t *packed_host = nullptr;
+    int *overflow_host = nullptr;
+    cudaEvent_t ev[4] = {};
+    cudaEvent_t ev_misc[2] = {};
+    cudaEvent_t ev_grp[kMaxGroups][kEntropyStreams] = {}, ev_off[kMaxGroups] = {};
+    std::vector<cudaEvent_t> ev_chunk;   // [0, kMaxChunks): upload done, [kMaxChunks, 2 kMaxChunks): chain done
+    std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
+    std::vector<cudaEvent_t> kev_me;  // after the motion-search kernel of each P frame
+    // host bookkeeping of the batch in flight
+    bool pending = false;
+    int n = 0;
+    bool forced_first = false;
+    long long first_frame_no = 0;
+    std::vector<int> is_idr, qps, pocs;
+};
+
 struct hb_encoder {
     hb_ctx *ctx = nullptr;
     hb_enc_params prm{};
@@ -242,7 +271,9 @@ struct hb_encoder {
     uint32_t row_cap = 0;
     // device memory
     std::vector<void *> dev;          // everything to free
-    std::vector<FrameSlot> slot;
+    BatchSet set[2];
+    int next_set = 0;                 // set the next batch is enqueued into
+    BatchSet *last_drained = nullptr; // what read_recon / read_decisions look at
     pixel *rec_base[2][3] = {};
     Planes rec[2];
     uint8_t *ds = nullptr;            // [max_batch + 1][dsh * dsw] quarter-resolution planes (8 MSBs)
@@ -250,44 +281,30 @@ struct hb_encoder {
     int *mode_cost = nullptr;         // [cus][35] intra mode search result of the key frame in flight
     uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
     int *satdf[2] = {nullptr, nullptr};
-    uint8_t *staging = nullptr;       // raw input frames
     size_t staging_bytes = 0;
-    int *progress = nullptr, *overflow = nullptr, *row_ready_all = nullptr;
+    int *progress = nullptr;
     RcState *rc_dev = nullptr;
-    FrameCtl *ctl_dev = nullptr, *ctl_host = nullptr;
     bool rc_have_idr = false;
-    EntropyFrame *eframes_dev = nullptr;
-    unsigned long long *trace_dev = nullptr;   // debug: per-row CABAC timestamps, only with HB_ENTROPY_TRACE=<file>
     const char *trace_path = nullptr;
-    uint32_t *offsets_dev = nullptr;
-    uint8_t *packed_dev = nullptr;
     size_t packed_cap = 0;
-    // pinned host
-    uint32_t *offsets_host = nullptr;
-    uint8_t *packed_host = nullptr;
-    int *overflow_host = nullptr;
     // stream state
     int cur = 0;                      // reconstruction buffer being written
     long long frame_no = 0;
     int poc = 0, since_bp = 0;
     std::atomic<int> stop{0}, done{0};
-    cudaEvent_t ev[4] = {};
     cudaStream_t st_copy = nullptr;
     cudaStream_t st_entropy[kEntropyStreams] = {};   // CABAC launches round-robin over these, concurrent with the frame chain
     int next_entropy_stream = 0;
-    cudaEvent_t ev_misc[2] = {}, ev_join[kEntropyStreams] = {};
     // drain: every kGroupFrames frames the finished CABAC payload is compacted and downloaded (own streams) and the host
     // assembles those access units while the GPU is still encoding the rest of the batch
     cudaStream_t st_drain = nullptr, st_dl = nullptr;
-    cudaEvent_t ev_grp[kMaxGroups][kEntropyStreams] = {}, ev_off[kMaxGroups] = {};
     size_t frame_cap = 0;             // bytes of the packed buffer reserved per frame
-    std::vector<cudaEvent_t> ev_chunk;   // [0, kMaxChunks): upload done, [kMaxChunks, 2 kMaxChunks): chain done
-    std::vector<cudaEvent_t> kev;     // 2 per frame of a batch + 6 per batch: per-kernel-class timing
     int profiling = 0;
     float prof_ms[8] = {};            // inter (3 kernels), intra, coarse, entropy(+pack), ingest, chain, k_me alone, spare
     int prof_launches[8] = {};
-    std::vector<cudaEvent_t> kev_me;  // after the motion-search kernel of each P frame
     float last_total_ms = 0, last_kernel_ms = 0;
+    cudaEvent_t ev_mark = nullptr, ev_last_done = nullptr;   // region timing across pipelined calls (hb_enc_mark / hb_enc_elapsed)
+    bool have_last_done = false;
     std::vector<uint8_t> vps, sps, pps;
 };
 
@@ -321,7 +338,7 @@ int alloc_planes(hb_encoder *e, Planes *pl, int wc, int hc)
 
 // launch the WPP CABAC kernel for frames [first, first + count) of the current batch on the next side stream, ordered after
 // everything issued so far on the main stream
-int launch_entropy(hb_encoder *e, int first, int count, cudaEvent_t ev)
+int launch_entropy(hb_encoder *e, BatchSet &B, int first, int count, cudaEvent_t ev)
 {
     hb_ctx *ctx = e->ctx;
     cudaStream_t q = e->st_entropy[e->next_entropy_stream];
@@ -329,7 +346,7 @@ int launch_entropy(hb_encoder *e, int first, int count, cudaEvent_t ev)
     HB_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
     HB_CUDA(ctx, cudaStreamWaitEvent(q, ev, 0));
     EntropyParams ep;
-    ep.g = e->g; ep.frames = e->eframes_dev + first; ep.row_cap = e->row_cap; ep.overflow = e->overflow;
+    ep.g = e->g; ep.frames = B.eframes_dev + first; ep.row_cap = e->row_cap; ep.overflow = B.overflow;
     k_entropy<<<dim3((e->g.ctuh + kEntropyWarps - 1) / kEntropyWarps, count), kEntropyWarps * 32, 0, q>>>(ep);
     HB_LAUNCHED(ctx);
     return HB_OK;
@@ -341,219 +358,30 @@ size_t input_frame_bytes(const hb_enc_params &p, int fmt)
     return fmt == HB_PIX_YUV420P8 ? luma + 2 * chroma : 2 * (luma + 2 * chroma);
 }
 
-}  // namespace
 
-extern "C" {
-
-int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_encoder **out)
+// Enqueue everything one batch needs on the GPU -- uploads, frame chain, CABAC, per-group compaction -- without waiting for
+// any of it.  `fr` frames [base, base + n) go into batch set B, whose previous batch has been drained.
+int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int n, bool force_first)
 {
-    HB_ARG(ctx, ctx && params && out && max_batch >= 1 && max_batch <= 1024);
-    const hb_enc_params &p = *params;
-    HB_ARG(ctx, p.width >= 16 && p.height >= 16 && (p.width % 2) == 0 && (p.height % 2) == 0 && p.width <= 8192 && p.height <= 8192);
-    HB_ARG(ctx, p.bit_depth == 8 || p.bit_depth == 10);
-    HB_ARG(ctx, !p.rate_control || (p.vbv_maxrate_kbps > 0 && p.vbv_bufsize_kbit > 0));
-    HB_ARG(ctx, p.qp_i >= 0 && p.qp_i <= 51 && p.qp_p >= 0 && p.qp_p <= 51 && p.keyint >= 1 && p.fps_num > 0 && p.fps_den > 0);
-    HB_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::unique_ptr<hb_encoder> e(new hb_encoder());
-    e->ctx = ctx;
-    e->prm = p;
-    e->max_batch = max_batch;
-    Geom &g = e->g;
-    g.wc = (p.width + 15) & ~15; g.hc = (p.height + 15) & ~15;
-    g.cuw = g.wc / 16; g.cuh = g.hc / 16; g.ctuw = (g.wc + 31) / 32; g.ctuh = (g.hc + 31) / 32;
-    g.bit_depth = p.bit_depth;
-    g.src_stride = g.wc; g.srcc_stride = g.wc / 2;
-    g.rec_stride = g.wc + 2 * kPad; g.recc_stride = g.wc / 2 + kPad;
-    g.dsw = g.wc / 4; g.dsh = g.hc / 4;
-    // worst-case CABAC payload of one CTU row: half the raw samples, at least 16 KiB
-    e->row_cap = (uint32_t)std::max<size_t>(16384, (size_t)32 * g.wc * 3 / 2 * (p.bit_depth > 8 ? 2 : 1) / 2);
-    e->row_cap = (e->row_cap + 255) & ~255u;
-    const int ncu = g.cuw * g.cuh, nctu = g.ctuw * g.ctuh;
-    hb_encoder *E = e.get();
-    E->slot.resize(max_batch);
-    for (int i = 0; i < max_batch; i++) {
-        FrameSlot &s = E->slot[i];
-        HB_TRY(alloc_planes(E, &s.src, g.wc, g.hc));
-        HB_TRY(dev_alloc(E, &s.cus, (size_t)ncu));
-        HB_TRY(dev_alloc(E, &s.syn, (size_t)ncu));
-        HB_TRY(dev_alloc(E, &s.coefs, (size_t)ncu * kCuCoefs));
-        HB_TRY(dev_alloc(E, &s.rows, (size_t)g.ctuh * E->row_cap));
-        HB_TRY(dev_alloc(E, &s.row_len, (size_t)g.ctuh));
-        HB_TRY(dev_alloc(E, &s.ctx_save, (size_t)g.ctuh * kNumCtx));
-        if (p.keep_recon || p.hash_sei) HB_TRY(alloc_planes(E, &s.keep, g.wc, g.hc));
-    }
-    for (int k = 0; k < 2; k++)
-        for (int c = 0; c < 3; c++) {
-            const int w = c ? g.wc / 2 : g.wc, h = c ? g.hc / 2 : g.hc, pad = c ? kPad / 2 : kPad;
-            const int stride = c ? g.recc_stride : g.rec_stride;
-            HB_TRY(dev_alloc(E, &E->rec_base[k][c], (size_t)stride * (h + 2 * pad)));
-            HB_CUDA(ctx, cudaMemsetAsync(E->rec_base[k][c], 0, (size_t)stride * (h + 2 * pad) * sizeof(pixel), ctx->stream));
-            pixel *origin = E->rec_base[k][c] + (size_t)pad * stride + pad;
-            (void)w;
-            if (c == 0) E->rec[k].y = origin; else if (c == 1) E->rec[k].u = origin; else E->rec[k].v = origin;
-        }
-    HB_TRY(dev_alloc(E, &E->row_ready_all, (size_t)max_batch * g.ctuh));
-    for (int i = 0; i < max_batch; i++) E->slot[i].row_ready = E->row_ready_all + (size_t)i * g.ctuh;
-    HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
-    HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
-    HB_TRY(dev_alloc(E, &E->mode_cost, (size_t)g.cuw * g.cuh * 35));
-    for (int k = 0; k < 2; k++) {
-        HB_TRY(dev_alloc(E, &E->mvf[k], (size_t)g.cuw * g.cuh));
-        HB_TRY(dev_alloc(E, &E->satdf[k], (size_t)g.cuw * g.cuh));
-    }
-    E->staging_bytes = (size_t)max_batch * input_frame_bytes(p, HB_PIX_P010);
-    HB_TRY(dev_alloc(E, &E->staging, E->staging_bytes));
-    HB_TRY(dev_alloc(E, &E->progress, (size_t)g.ctuh));
-    HB_TRY(dev_alloc(E, &E->overflow, 1));
-    HB_TRY(dev_alloc(E, &E->rc_dev, 1));
-    HB_TRY(dev_alloc(E, &E->ctl_dev, (size_t)max_batch));
-    HB_CUDA(ctx, cudaMallocHost(&E->ctl_host, sizeof(FrameCtl) * max_batch));
-    {
-        RcState rc{};
-        rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
-        rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
-        rc.fullness = rc.b16 * 9 / 10;
-        rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
-        HB_CUDA(ctx, cudaMemcpyAsync(E->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, ctx->stream));
-        HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    HB_TRY(dev_alloc(E, &E->eframes_dev, (size_t)max_batch));
-    E->trace_path = getenv("HB_ENTROPY_TRACE");
-    if (E->trace_path && *E->trace_path) HB_TRY(dev_alloc(E, &E->trace_dev, (size_t)max_batch * g.ctuh * 2));
-    else E->trace_path = nullptr;
-    HB_TRY(dev_alloc(E, &E->offsets_dev, (size_t)max_batch * g.ctuh + kMaxGroups + 1));
-    E->frame_cap = ((size_t)g.ctuh * E->row_cap / 4 + 65536 + 255) & ~(size_t)255;
-    E->packed_cap = (size_t)max_batch * E->frame_cap;
-    HB_TRY(dev_alloc(E, &E->packed_dev, E->packed_cap));
-    HB_CUDA(ctx, cudaMallocHost(&E->offsets_host, ((size_t)max_batch * g.ctuh + kMaxGroups + 1) * sizeof(uint32_t)));
-    HB_CUDA(ctx, cudaMallocHost(&E->packed_host, E->packed_cap));
-    HB_CUDA(ctx, cudaMallocHost(&E->overflow_host, sizeof(int)));
-    for (auto &ev : E->ev) HB_CUDA(ctx, cudaEventCreate(&ev));
-    for (auto &ev : E->ev_misc) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto &ev : E->ev_join) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    E->ev_chunk.resize((size_t)2 * kMaxChunks);
-    for (auto &ev : E->ev_chunk) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
-    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_drain, cudaStreamNonBlocking));
-    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_dl, cudaStreamNonBlocking));
-    for (auto &row : E->ev_grp) for (auto &ev : row) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto &ev : E->ev_off) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    {   // CABAC launches run at the highest stream priority: their CTAs need a whole SM each and would otherwise starve behind
-        // the thousands of pending k_inter CTAs of the frame chain
-        int lo = 0, hi = 0;
-        HB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        for (auto &q : E->st_entropy) HB_CUDA(ctx, cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, hi));
-    }
-    E->kev.resize((size_t)2 * max_batch + 8);
-    for (auto &ev : E->kev) HB_CUDA(ctx, cudaEventCreate(&ev));
-    E->kev_me.resize((size_t)max_batch);
-    for (auto &ev : E->kev_me) HB_CUDA(ctx, cudaEventCreate(&ev));
-    HB_CUDA(ctx, upload_inter_constants(ctx->stream));
-    E->vps = make_vps(p);
-    E->sps = make_sps(p, g.wc, g.hc);
-    E->pps = make_pps(p);
-    HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out = e.release();
-    return HB_OK;
-}
-
-void hb_enc_destroy(hb_encoder *e)
-{
-    if (!e) return;
-    cudaSetDevice(e->ctx->device);
-    cudaStreamSynchronize(e->ctx->stream);
-    for (void *p : e->dev) cudaFree(p);
-    if (e->offsets_host) cudaFreeHost(e->offsets_host);
-    if (e->packed_host) cudaFreeHost(e->packed_host);
-    if (e->overflow_host) cudaFreeHost(e->overflow_host);
-    if (e->ctl_host) cudaFreeHost(e->ctl_host);
-    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : e->ev_misc) if (ev) cudaEventDestroy(ev);
-    for (auto &row : e->ev_grp) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : e->ev_off) if (ev) cudaEventDestroy(ev);
-    if (e->st_drain) { cudaStreamSynchronize(e->st_drain); cudaStreamDestroy(e->st_drain); }
-    if (e->st_dl) { cudaStreamSynchronize(e->st_dl); cudaStreamDestroy(e->st_dl); }
-    for (auto &ev : e->ev_join) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
-    if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
-    for (auto &q : e->st_entropy) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
-    for (auto &ev : e->kev) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : e->kev_me) if (ev) cudaEventDestroy(ev);
-    delete e;
-}
-
-int hb_enc_headers(hb_encoder *e, uint8_t *out, size_t cap, size_t *len)
-{
-    if (!e) return HB_ERR_ARG;
-    HB_ARG(e->ctx, out && len);
-    std::vector<uint8_t> buf;
-    append_nal(buf, NAL_VPS, e->vps, true);
-    append_nal(buf, NAL_SPS, e->sps, true);
-    append_nal(buf, NAL_PPS, e->pps, true);
-    if (buf.size() > cap) return hb_fail(e->ctx, HB_ERR_SPACE, "%s", "header buffer too small");
-    memcpy(out, buf.data(), buf.size());
-    *len = buf.size();
-    return HB_OK;
-}
-
-int hb_enc_coded_size(const hb_encoder *e, int *wc, int *hc)
-{
-    if (!e || !wc || !hc) return HB_ERR_ARG;
-    *wc = e->g.wc; *hc = e->g.hc;
-    return HB_OK;
-}
-
-int hb_enc_request_stop(hb_encoder *e)
-{
-    if (!e) return HB_ERR_ARG;
-    e->stop.store(1);
-    return HB_OK;
-}
-
-int hb_enc_poll_progress(const hb_encoder *e, int *frames_done)
-{
-    if (!e || !frames_done) return HB_ERR_ARG;
-    *frames_done = e->done.load();
-    return HB_OK;
-}
-
-int hb_enc_last_timing(const hb_encoder *e, float *total_ms, float *kernel_ms)
-{
-    if (!e) return HB_ERR_ARG;
-    if (total_ms) *total_ms = e->last_total_ms;
-    if (kernel_ms) *kernel_ms = e->last_kernel_ms;
-    return HB_OK;
-}
-
-int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *out, size_t cap, size_t *out_len, hb_frame_stat *stats)
-{
-    if (!e) return HB_ERR_ARG;
     hb_ctx *ctx = e->ctx;
-    HB_ARG(ctx, fr && fr->data && out && out_len && fr->n_frames >= 0);
-    HB_ARG(ctx, fr->format == HB_PIX_YUV420P8 || fr->format == HB_PIX_P010 || fr->format == HB_PIX_YUV420P16);
     const hb_enc_params &p = e->prm;
     const Geom &g = e->g;
     const size_t fbytes = input_frame_bytes(p, fr->format);
-    HB_ARG(ctx, fr->frame_bytes >= fbytes);
-    HB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int ncu = g.cuw * g.cuh, nctu = g.ctuw * g.ctuh;
     const size_t ds_stride = (size_t)g.dsw * g.dsh;
-    size_t written = 0;
-    float total_ms = 0, kernel_ms = 0;
-    e->done.store(0);
-
-    for (int base = 0; base < fr->n_frames; base += e->max_batch) {
-        const int n = std::min(e->max_batch, fr->n_frames - base);
+    {
         if (e->stop.load()) return hb_fail(ctx, HB_ERR_STOPPED, "%s", "stopped");
-        HB_CUDA(ctx, cudaEventRecord(e->ev[0], st));
+        HB_CUDA(ctx, cudaEventRecord(B.ev[0], st));
         // ---- frame types of the batch (pure host state) and the entropy-stage descriptors
-        std::vector<int> is_idr(n), qps(n), pocs(n);
+        B.n = n; B.forced_first = force_first; B.first_frame_no = e->frame_no;
+        B.is_idr.assign(n, 0); B.qps.assign(n, 0); B.pocs.assign(n, 0);
+        std::vector<int> &is_idr = B.is_idr, &pocs = B.pocs;
         {
             int poc = e->poc;
             long long fno = e->frame_no;
             for (int i = 0; i < n; i++, fno++) {
-                const bool idr = (force_idr && base == 0 && i == 0) || fno == 0 || poc + 1 >= p.keyint;
+                const bool idr = (force_first && i == 0) || fno == 0 || poc + 1 >= p.keyint;
                 poc = idr ? 0 : poc + 1;
                 is_idr[i] = idr; pocs[i] = poc;
             }
@@ -561,17 +389,17 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         }
         std::vector<EntropyFrame> ef(n);
         for (int i = 0; i < n; i++) {
-            FrameSlot &s = e->slot[i];
+            FrameSlot &s = B.slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
-            ef[i].is_intra = is_idr[i]; ef[i].ctl = e->ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
-            ef[i].trace = e->trace_dev ? e->trace_dev + (size_t)i * g.ctuh * 2 : nullptr;
+            ef[i].is_intra = is_idr[i]; ef[i].ctl = B.ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
+            ef[i].trace = B.trace_dev ? B.trace_dev + (size_t)i * g.ctuh * 2 : nullptr;
         }
-        HB_CUDA(ctx, cudaMemcpyAsync(e->eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
-        HB_CUDA(ctx, cudaMemsetAsync(e->overflow, 0, sizeof(int), st));
-        HB_CUDA(ctx, cudaMemsetAsync(e->row_ready_all, 0, sizeof(int) * (size_t)n * g.ctuh, st));
-        HB_CUDA(ctx, cudaEventRecord(e->ev_misc[0], st));
-        HB_CUDA(ctx, cudaStreamWaitEvent(e->st_copy, e->ev_misc[0], 0));   // staging may still be read by the previous batch
-        for (auto &q : e->st_entropy) HB_CUDA(ctx, cudaStreamWaitEvent(q, e->ev_misc[0], 0));
+        HB_CUDA(ctx, cudaMemcpyAsync(B.eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
+        HB_CUDA(ctx, cudaMemsetAsync(B.overflow, 0, sizeof(int), st));
+        HB_CUDA(ctx, cudaMemsetAsync(B.row_ready_all, 0, sizeof(int) * (size_t)n * g.ctuh, st));
+        // (the set's staging buffer and sync areas are free: its previous batch has been drained)
+        HB_CUDA(ctx, cudaEventRecord(B.ev_misc[0], st));
+        for (auto &q : e->st_entropy) HB_CUDA(ctx, cudaStreamWaitEvent(q, B.ev_misc[0], 0));
         const uint8_t *in = static_cast<const uint8_t *>(fr->data) + (size_t)base * fr->frame_bytes;
         const size_t kb = (size_t)2 * e->max_batch;      // batch-level profiling events start here
         float ingest_ms = 0, coarse_ms = 0;
@@ -583,20 +411,20 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             size_t dev_fb = fr->frame_bytes;
             if (!fr->on_device) {
                 if (fr->frame_bytes == fbytes) {
-                    HB_CUDA(ctx, cudaMemcpyAsync(e->staging + (size_t)c0 * fbytes, dev_in, fbytes * cn, cudaMemcpyHostToDevice, e->st_copy));
+                    HB_CUDA(ctx, cudaMemcpyAsync(B.staging + (size_t)c0 * fbytes, dev_in, fbytes * cn, cudaMemcpyHostToDevice, e->st_copy));
                 } else {
                     for (int i = 0; i < cn; i++)
-                        HB_CUDA(ctx, cudaMemcpyAsync(e->staging + (size_t)(c0 + i) * fbytes, dev_in + (size_t)i * fr->frame_bytes, fbytes,
+                        HB_CUDA(ctx, cudaMemcpyAsync(B.staging + (size_t)(c0 + i) * fbytes, dev_in + (size_t)i * fr->frame_bytes, fbytes,
                                                      cudaMemcpyHostToDevice, e->st_copy));
                 }
-                HB_CUDA(ctx, cudaEventRecord(e->ev_chunk[chunk], e->st_copy));
-                HB_CUDA(ctx, cudaStreamWaitEvent(st, e->ev_chunk[chunk], 0));
-                dev_in = e->staging + (size_t)c0 * fbytes;
+                HB_CUDA(ctx, cudaEventRecord(B.ev_chunk[chunk], e->st_copy));
+                HB_CUDA(ctx, cudaStreamWaitEvent(st, B.ev_chunk[chunk], 0));
+                dev_in = B.staging + (size_t)c0 * fbytes;
                 dev_fb = fbytes;
             }
             if (c0 == 0) {
-                HB_CUDA(ctx, cudaEventRecord(e->ev[1], st));
-                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 0], st));
+                HB_CUDA(ctx, cudaEventRecord(B.ev[1], st));
+                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[kb + 0], st));
             }
             for (int i = 0; i < cn; i++) {
                 IngestParams ip;
@@ -617,7 +445,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     ip.up_shift = 0; ip.down_shift = 0;
                 }
                 ip.fmt = fr->format; ip.w = p.width; ip.h = p.height;
-                ip.src = e->slot[c0 + i].src;
+                ip.src = B.slot[c0 + i].src;
                 ip.ds = e->ds + (size_t)(c0 + i + 1) * ds_stride;
                 k_ingest<<<hb_grid_for(ctx, (long long)g.dsw * g.dsh, 256, 8), 256, 0, st>>>(ip);
                 HB_LAUNCHED(ctx);
@@ -632,23 +460,23 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             // frame chain
             for (int i = c0; i < c0 + cn; i++) {
                 const bool idr = is_idr[i] != 0;
-                FrameSlot &s = e->slot[i];
+                FrameSlot &s = B.slot[i];
                 const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
                 // rate control on the device: account for the previous frame, choose this frame's QP
-                k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? e->ctl_dev + i - 1 : nullptr, e->ctl_dev + i, idr ? 1 : 0);
+                k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? B.ctl_dev + i - 1 : nullptr, B.ctl_dev + i, idr ? 1 : 0);
                 HB_LAUNCHED(ctx);
                 if (idr) HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
-                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i], st));
+                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[2 * i], st));
                 if (idr) {
                     IntraParams ip;
                     ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
-                    ip.ctl = e->ctl_dev + i; ip.second_pass = 0; ip.mode_cost = e->mode_cost;
+                    ip.ctl = B.ctl_dev + i; ip.second_pass = 0; ip.mode_cost = e->mode_cost;
                     k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
-                        k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + i);
+                        k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, B.ctl_dev + i);
                         HB_LAUNCHED(ctx);
                         HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
                         ip.second_pass = 1;
@@ -659,12 +487,12 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 } else {
                     InterParams ip;
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
-                    ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = e->ctl_dev + i;
+                    ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = B.ctl_dev + i;
                     // motion search, then two merge-aware passes over the field (the second one inside k_inter)
                     ip.mv_in = nullptr; ip.satd_in = nullptr; ip.mv_out = e->mvf[0]; ip.satd_out = e->satdf[0];
                     k_me<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
-                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev_me[i], st));
+                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev_me[i], st));
                     ip.mv_in = e->mvf[0]; ip.satd_in = e->satdf[0]; ip.mv_out = e->mvf[1]; ip.satd_out = e->satdf[1];
                     k_merge<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
@@ -672,10 +500,10 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                     k_inter<<<nctu, 128, 0, st>>>(ip);
                     HB_LAUNCHED(ctx);
                 }
-                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[2 * i + 1], st));
+                if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[2 * i + 1], st));
                 if (p.deblock) {
                     DeblockParams dp;
-                    dp.g = g; dp.rec = rec; dp.cus = s.cus; dp.ctl = e->ctl_dev + i;
+                    dp.g = g; dp.rec = rec; dp.cus = s.cus; dp.ctl = B.ctl_dev + i;
                     for (dp.dir = 0; dp.dir < 2; dp.dir++) {
                         k_deblock<<<hb_grid_for(ctx, (long long)ncu * 4, 256, 8), 256, 0, st>>>(dp);
                         HB_LAUNCHED(ctx);
@@ -699,7 +527,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.is_intra = idr;
                 k_modes<<<(ncu + 255) / 256, 256, 0, st>>>(mp);
                 HB_LAUNCHED(ctx);
-                if (idr) HB_TRY(launch_entropy(e, i, 1, e->ev_chunk[kMaxChunks + chunk]));
+                if (idr) HB_TRY(launch_entropy(e, B, i, 1, B.ev_chunk[kMaxChunks + chunk]));
                 e->cur = 1 - e->cur;
                 e->frame_no++;
             }
@@ -709,83 +537,103 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 if (is_idr[i0]) { i0++; continue; }
                 int i1 = i0;
                 while (i1 < c0 + cn && !is_idr[i1]) i1++;
-                HB_TRY(launch_entropy(e, i0, i1 - i0, e->ev_chunk[kMaxChunks + chunk]));
+                HB_TRY(launch_entropy(e, B, i0, i1 - i0, B.ev_chunk[kMaxChunks + chunk]));
                 i0 = i1;
             }
             // ---- end of a drain group: compaction + download of its sub-stream sizes behind its CABAC kernels
             if ((c0 + cn) % kGroupFrames == 0 || c0 + cn == n) {
                 const int grp = c0 / kGroupFrames, f0 = grp * kGroupFrames, cnt = c0 + cn - f0;
                 for (int k = 0; k < kEntropyStreams; k++) {
-                    HB_CUDA(ctx, cudaEventRecord(e->ev_grp[grp][k], e->st_entropy[k]));
-                    HB_CUDA(ctx, cudaStreamWaitEvent(e->st_drain, e->ev_grp[grp][k], 0));
+                    HB_CUDA(ctx, cudaEventRecord(B.ev_grp[grp][k], e->st_entropy[k]));
+                    HB_CUDA(ctx, cudaStreamWaitEvent(e->st_drain, B.ev_grp[grp][k], 0));
                 }
                 PackParams pp;
-                pp.frames = e->eframes_dev + f0; pp.n_frames = cnt; pp.rows = g.ctuh; pp.row_cap = e->row_cap;
-                pp.packed = e->packed_dev + (size_t)f0 * e->frame_cap; pp.offsets = e->offsets_dev + (size_t)f0 * g.ctuh + grp;
+                pp.frames = B.eframes_dev + f0; pp.n_frames = cnt; pp.rows = g.ctuh; pp.row_cap = e->row_cap;
+                pp.packed = B.packed_dev + (size_t)f0 * e->frame_cap; pp.offsets = B.offsets_dev + (size_t)f0 * g.ctuh + grp;
                 k_pack_scan<<<1, 1024, 0, e->st_drain>>>(pp);
                 HB_LAUNCHED(ctx);
                 k_pack_copy<<<cnt * g.ctuh, 128, 0, e->st_drain>>>(pp);
                 HB_LAUNCHED(ctx);
-                HB_CUDA(ctx, cudaMemcpyAsync(e->offsets_host + (size_t)f0 * g.ctuh + grp, pp.offsets, sizeof(uint32_t) * ((size_t)cnt * g.ctuh + 1),
+                HB_CUDA(ctx, cudaMemcpyAsync(B.offsets_host + (size_t)f0 * g.ctuh + grp, pp.offsets, sizeof(uint32_t) * ((size_t)cnt * g.ctuh + 1),
                                              cudaMemcpyDeviceToHost, e->st_drain));
-                HB_CUDA(ctx, cudaMemcpyAsync(e->ctl_host + f0, e->ctl_dev + f0, sizeof(FrameCtl) * cnt, cudaMemcpyDeviceToHost, e->st_drain));
+                HB_CUDA(ctx, cudaMemcpyAsync(B.ctl_host + f0, B.ctl_dev + f0, sizeof(FrameCtl) * cnt, cudaMemcpyDeviceToHost, e->st_drain));
                 if (c0 + cn == n) {
-                    HB_CUDA(ctx, cudaMemcpyAsync(e->overflow_host, e->overflow, sizeof(int), cudaMemcpyDeviceToHost, e->st_drain));
-                    HB_CUDA(ctx, cudaEventRecord(e->ev[2], e->st_drain));
-                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 4], e->st_drain));
+                    HB_CUDA(ctx, cudaMemcpyAsync(B.overflow_host, B.overflow, sizeof(int), cudaMemcpyDeviceToHost, e->st_drain));
+                    HB_CUDA(ctx, cudaEventRecord(B.ev[2], e->st_drain));
+                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[kb + 4], e->st_drain));
                 }
-                HB_CUDA(ctx, cudaEventRecord(e->ev_off[grp], e->st_drain));
+                HB_CUDA(ctx, cudaEventRecord(B.ev_off[grp], e->st_drain));
             }
         }
-        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, e->ctl_dev + n - 1, nullptr, 0);
+        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, B.ctl_dev + n - 1, nullptr, 0);
         HB_LAUNCHED(ctx);
         // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
         HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(uint8_t), cudaMemcpyDeviceToDevice, st));
-        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(e->kev[kb + 3], st));
+        if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[kb + 3], st));
+        HB_CUDA(ctx, cudaEventRecord(B.ev_misc[1], st));        // end of this batch's frame chain
+        B.pending = true;
+    }
+    return HB_OK;
+}
+
+
+// Wait for a batch group by group, download its payload and assemble its access units into out[written...]; stats (may be
+// null) is indexed from the batch's first frame.
+int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &written, hb_frame_stat *stats, float &total_ms, float &kernel_ms)
+{
+    hb_ctx *ctx = e->ctx;
+    const hb_enc_params &p = e->prm;
+    const Geom &g = e->g;
+    const int n = B.n;
+    const size_t kb = (size_t)2 * e->max_batch;
+    std::vector<int> &is_idr = B.is_idr, &qps = B.qps, &pocs = B.pocs;
+    {
         // ---- drain: per group wait for its sizes, download its payload, assemble its access units (the GPU keeps encoding)
         std::vector<uint8_t> au, slice;
         std::vector<uint16_t> hostrec;
         const int n_groups = (n + kGroupFrames - 1) / kGroupFrames;
         for (int grp = 0; grp < n_groups; grp++) {
         const int f0 = grp * kGroupFrames, f1 = std::min(n, f0 + kGroupFrames);
-        const uint32_t *goff = e->offsets_host + (size_t)f0 * g.ctuh + grp;
-        const uint8_t *gpay = e->packed_host + (size_t)f0 * e->frame_cap;
-        HB_CUDA(ctx, cudaEventSynchronize(e->ev_off[grp]));
+        const uint32_t *goff = B.offsets_host + (size_t)f0 * g.ctuh + grp;
+        const uint8_t *gpay = B.packed_host + (size_t)f0 * e->frame_cap;
+        HB_CUDA(ctx, cudaEventSynchronize(B.ev_off[grp]));
         {
             const uint32_t total = goff[(size_t)(f1 - f0) * g.ctuh];
             if (total > (size_t)(f1 - f0) * e->frame_cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "packed bitstream exceeds the download buffer");
-            HB_CUDA(ctx, cudaMemcpyAsync(e->packed_host + (size_t)f0 * e->frame_cap, e->packed_dev + (size_t)f0 * e->frame_cap, total,
+            HB_CUDA(ctx, cudaMemcpyAsync(B.packed_host + (size_t)f0 * e->frame_cap, B.packed_dev + (size_t)f0 * e->frame_cap, total,
                                          cudaMemcpyDeviceToHost, e->st_dl));
-            if (grp == n_groups - 1) HB_CUDA(ctx, cudaEventRecord(e->ev[3], e->st_dl));
+            if (grp == n_groups - 1) HB_CUDA(ctx, cudaEventRecord(B.ev[3], e->st_dl));
             HB_CUDA(ctx, cudaStreamSynchronize(e->st_dl));
         }
         if (grp == n_groups - 1) {
-            HB_CUDA(ctx, cudaStreamSynchronize(st));
-            if (*e->overflow_host) return hb_fail(ctx, HB_ERR_SPACE, "%s", "CABAC sub-stream exceeded its row buffer");
+            HB_CUDA(ctx, cudaEventRecord(e->ev_last_done, e->st_dl));
+            e->have_last_done = true;
+            HB_CUDA(ctx, cudaEventSynchronize(B.ev_misc[1]));        // the batch's frame chain (the next batch may already be running)
+            if (*B.overflow_host) return hb_fail(ctx, HB_ERR_SPACE, "%s", "CABAC sub-stream exceeded its row buffer");
             float a = 0, b = 0;
-            cudaEventElapsedTime(&a, e->ev[0], e->ev[3]);
-            cudaEventElapsedTime(&b, e->ev[1], e->ev[2]);
+            cudaEventElapsedTime(&a, B.ev[0], B.ev[3]);
+            cudaEventElapsedTime(&b, B.ev[1], B.ev[2]);
             total_ms += a; kernel_ms += b;
             if (e->profiling) {
                 float ms = 0;
                 for (int i = 0; i < n; i++) {
-                    cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev[2 * i + 1]);
+                    cudaEventElapsedTime(&ms, B.kev[2 * i], B.kev[2 * i + 1]);
                     const int k = is_idr[i] ? 1 : 0;
                     e->prof_ms[k] += ms; e->prof_launches[k]++;
-                    if (!is_idr[i]) { cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev_me[i]); e->prof_ms[6] += ms; e->prof_launches[6]++; }
+                    if (!is_idr[i]) { cudaEventElapsedTime(&ms, B.kev[2 * i], B.kev_me[i]); e->prof_ms[6] += ms; e->prof_launches[6]++; }
                 }
-                cudaEventElapsedTime(&ms, e->kev[kb + 3], e->kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
-                cudaEventElapsedTime(&ms, e->kev[kb + 0], e->kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
+                cudaEventElapsedTime(&ms, B.kev[kb + 3], B.kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
+                cudaEventElapsedTime(&ms, B.kev[kb + 0], B.kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
             }
-            if (e->trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes}
+            if (B.trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes}
                 std::vector<unsigned long long> tr((size_t)n * g.ctuh * 2);
-                cudaMemcpy(tr.data(), e->trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                cudaMemcpy(tr.data(), B.trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
                 if (FILE *f = fopen(e->trace_path, "wb")) {
                     const unsigned long long hdr[2] = {(unsigned long long)n, (unsigned long long)g.ctuh};
                     fwrite(hdr, sizeof(hdr), 1, f);
                     for (size_t k = 0; k < (size_t)n * g.ctuh; k++) {
                         const size_t fi = k / g.ctuh, gi = fi / kGroupFrames;
-                        const uint32_t *o = e->offsets_host + k + gi;
+                        const uint32_t *o = B.offsets_host + k + gi;
                         const unsigned long long rec[3] = {tr[2 * k], tr[2 * k + 1], (unsigned long long)(o[1] - o[0])};
                         fwrite(rec, sizeof(rec), 1, f);
                     }
@@ -793,14 +641,14 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
                 }
             }
         }
-        for (int i = f0; i < f1; i++) qps[i] = e->ctl_host[i].qp;
+        for (int i = f0; i < f1; i++) qps[i] = B.ctl_host[i].qp;
         for (int i = f0; i < f1; i++) {
 
             au.clear();
             const bool idr = is_idr[i] != 0;
-            const bool first_of_stream = e->frame_no - n + i == 0;
+            const bool first_of_stream = B.first_frame_no + i == 0;
             if (p.aud) { BitWriter b; b.put(idr ? 0 : 1, 3); b.trailing(); append_nal(au, NAL_AUD, b.bytes(), true); }
-            if (idr && (first_of_stream || p.repeat_headers || (force_idr && base == 0 && i == 0))) {
+            if (idr && (first_of_stream || p.repeat_headers || (B.forced_first && i == 0))) {
                 append_nal(au, NAL_VPS, e->vps, true);
                 append_nal(au, NAL_SPS, e->sps, true);
                 append_nal(au, NAL_PPS, e->pps, true);
@@ -864,7 +712,7 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             au.insert(au.end(), slice.begin(), slice.end());
             if (p.hash_sei) {
                 std::vector<uint8_t> pl(49, 0);
-                const pixel *kp[3] = {e->slot[i].keep.y, e->slot[i].keep.u, e->slot[i].keep.v};
+                const pixel *kp[3] = {B.slot[i].keep.y, B.slot[i].keep.u, B.slot[i].keep.v};
                 for (int c = 0; c < 3; c++) {
                     const size_t cnt = (size_t)(c ? g.wc / 2 : g.wc) * (c ? g.hc / 2 : g.hc);
                     hostrec.resize(cnt);
@@ -883,16 +731,285 @@ int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
             memcpy(out + written, au.data(), au.size());
             written += au.size();
             if (stats) {
-                hb_frame_stat &s = stats[base + i];
+                hb_frame_stat &s = stats[i];
                 s.is_idr = idr; s.poc = pocs[i]; s.qp = qps[i]; s.bytes = (uint32_t)au.size(); s.n_skip = 0; s.n_merge = 0;
             }
             e->done.fetch_add(1);
         }
         }      // drain groups
     }
+    B.pending = false;
+    e->last_drained = &B;
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_encoder **out)
+{
+    HB_ARG(ctx, ctx && params && out && max_batch >= 1 && max_batch <= 1024);
+    const hb_enc_params &p = *params;
+    HB_ARG(ctx, p.width >= 16 && p.height >= 16 && (p.width % 2) == 0 && (p.height % 2) == 0 && p.width <= 8192 && p.height <= 8192);
+    HB_ARG(ctx, p.bit_depth == 8 || p.bit_depth == 10);
+    HB_ARG(ctx, !p.rate_control || (p.vbv_maxrate_kbps > 0 && p.vbv_bufsize_kbit > 0));
+    HB_ARG(ctx, p.qp_i >= 0 && p.qp_i <= 51 && p.qp_p >= 0 && p.qp_p <= 51 && p.keyint >= 1 && p.fps_num > 0 && p.fps_den > 0);
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<hb_encoder> e(new hb_encoder());
+    e->ctx = ctx;
+    e->prm = p;
+    e->max_batch = max_batch;
+    Geom &g = e->g;
+    g.wc = (p.width + 15) & ~15; g.hc = (p.height + 15) & ~15;
+    g.cuw = g.wc / 16; g.cuh = g.hc / 16; g.ctuw = (g.wc + 31) / 32; g.ctuh = (g.hc + 31) / 32;
+    g.bit_depth = p.bit_depth;
+    g.src_stride = g.wc; g.srcc_stride = g.wc / 2;
+    g.rec_stride = g.wc + 2 * kPad; g.recc_stride = g.wc / 2 + kPad;
+    g.dsw = g.wc / 4; g.dsh = g.hc / 4;
+    // worst-case CABAC payload of one CTU row: half the raw samples, at least 16 KiB
+    e->row_cap = (uint32_t)std::max<size_t>(16384, (size_t)32 * g.wc * 3 / 2 * (p.bit_depth > 8 ? 2 : 1) / 2);
+    e->row_cap = (e->row_cap + 255) & ~255u;
+    const int ncu = g.cuw * g.cuh, nctu = g.ctuw * g.ctuh;
+    hb_encoder *E = e.get();
+    // source planes: one set of slots, shared by both batch sets
+    std::vector<Planes> src(max_batch);
+    for (int i = 0; i < max_batch; i++) HB_TRY(alloc_planes(E, &src[i], g.wc, g.hc));
+    E->staging_bytes = (size_t)max_batch * input_frame_bytes(p, HB_PIX_P010);
+    E->frame_cap = ((size_t)g.ctuh * E->row_cap / 4 + 65536 + 255) & ~(size_t)255;
+    E->packed_cap = (size_t)max_batch * E->frame_cap;
+    E->trace_path = getenv("HB_ENTROPY_TRACE");
+    if (!(E->trace_path && *E->trace_path)) E->trace_path = nullptr;
+    for (BatchSet &B : E->set) {
+        B.slot.resize(max_batch);
+        for (int i = 0; i < max_batch; i++) {
+            FrameSlot &s = B.slot[i];
+            s.src = src[i];
+            HB_TRY(dev_alloc(E, &s.cus, (size_t)ncu));
+            HB_TRY(dev_alloc(E, &s.syn, (size_t)ncu));
+            HB_TRY(dev_alloc(E, &s.coefs, (size_t)ncu * kCuCoefs));
+            HB_TRY(dev_alloc(E, &s.rows, (size_t)g.ctuh * E->row_cap));
+            HB_TRY(dev_alloc(E, &s.row_len, (size_t)g.ctuh));
+            HB_TRY(dev_alloc(E, &s.ctx_save, (size_t)g.ctuh * kNumCtx));
+            if (p.keep_recon || p.hash_sei) HB_TRY(alloc_planes(E, &s.keep, g.wc, g.hc));
+        }
+        HB_TRY(dev_alloc(E, &B.row_ready_all, (size_t)max_batch * g.ctuh));
+        for (int i = 0; i < max_batch; i++) B.slot[i].row_ready = B.row_ready_all + (size_t)i * g.ctuh;
+        HB_TRY(dev_alloc(E, &B.staging, E->staging_bytes));
+        HB_TRY(dev_alloc(E, &B.overflow, 1));
+        HB_TRY(dev_alloc(E, &B.ctl_dev, (size_t)max_batch));
+        HB_CUDA(ctx, cudaMallocHost(&B.ctl_host, sizeof(FrameCtl) * max_batch));
+        HB_TRY(dev_alloc(E, &B.eframes_dev, (size_t)max_batch));
+        if (E->trace_path) HB_TRY(dev_alloc(E, &B.trace_dev, (size_t)max_batch * g.ctuh * 2));
+        HB_TRY(dev_alloc(E, &B.offsets_dev, (size_t)max_batch * g.ctuh + kMaxGroups + 1));
+        HB_TRY(dev_alloc(E, &B.packed_dev, E->packed_cap));
+        HB_CUDA(ctx, cudaMallocHost(&B.offsets_host, ((size_t)max_batch * g.ctuh + kMaxGroups + 1) * sizeof(uint32_t)));
+        HB_CUDA(ctx, cudaMallocHost(&B.packed_host, E->packed_cap));
+        HB_CUDA(ctx, cudaMallocHost(&B.overflow_host, sizeof(int)));
+        for (auto &ev : B.ev) HB_CUDA(ctx, cudaEventCreate(&ev));
+        for (auto &ev : B.ev_misc) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        B.ev_chunk.resize((size_t)2 * kMaxChunks);
+        for (auto &ev : B.ev_chunk) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto &row : B.ev_grp) for (auto &ev : row) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto &ev : B.ev_off) HB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        B.kev.resize((size_t)2 * max_batch + 8);
+        for (auto &ev : B.kev) HB_CUDA(ctx, cudaEventCreate(&ev));
+        B.kev_me.resize((size_t)max_batch);
+        for (auto &ev : B.kev_me) HB_CUDA(ctx, cudaEventCreate(&ev));
+    }
+    for (int k = 0; k < 2; k++)
+        for (int c = 0; c < 3; c++) {
+            const int h = c ? g.hc / 2 : g.hc, pad = c ? kPad / 2 : kPad;
+            const int stride = c ? g.recc_stride : g.rec_stride;
+            HB_TRY(dev_alloc(E, &E->rec_base[k][c], (size_t)stride * (h + 2 * pad)));
+            HB_CUDA(ctx, cudaMemsetAsync(E->rec_base[k][c], 0, (size_t)stride * (h + 2 * pad) * sizeof(pixel), ctx->stream));
+            pixel *origin = E->rec_base[k][c] + (size_t)pad * stride + pad;
+            if (c == 0) E->rec[k].y = origin; else if (c == 1) E->rec[k].u = origin; else E->rec[k].v = origin;
+        }
+    HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
+    HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
+    HB_TRY(dev_alloc(E, &E->mode_cost, (size_t)g.cuw * g.cuh * 35));
+    for (int k = 0; k < 2; k++) {
+        HB_TRY(dev_alloc(E, &E->mvf[k], (size_t)g.cuw * g.cuh));
+        HB_TRY(dev_alloc(E, &E->satdf[k], (size_t)g.cuw * g.cuh));
+    }
+    HB_TRY(dev_alloc(E, &E->progress, (size_t)g.ctuh));
+    HB_TRY(dev_alloc(E, &E->rc_dev, 1));
+    {
+        RcState rc{};
+        rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
+        rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
+        rc.fullness = rc.b16 * 9 / 10;
+        rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
+        HB_CUDA(ctx, cudaMemcpyAsync(E->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, ctx->stream));
+        HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    HB_CUDA(ctx, cudaEventCreate(&E->ev_mark));
+    HB_CUDA(ctx, cudaEventCreate(&E->ev_last_done));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_drain, cudaStreamNonBlocking));
+    HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_dl, cudaStreamNonBlocking));
+    {   // CABAC launches run at the highest stream priority: their CTAs would otherwise starve behind the thousands of pending
+        // CTAs of the frame chain
+        int lo = 0, hi = 0;
+        HB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (auto &q : E->st_entropy) HB_CUDA(ctx, cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, hi));
+    }
+    HB_CUDA(ctx, upload_inter_constants(ctx->stream));
+    E->vps = make_vps(p);
+    E->sps = make_sps(p, g.wc, g.hc);
+    E->pps = make_pps(p);
+    HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = e.release();
+    return HB_OK;
+}
+
+void hb_enc_destroy(hb_encoder *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
+    for (auto &q : e->st_entropy) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
+    if (e->st_drain) { cudaStreamSynchronize(e->st_drain); cudaStreamDestroy(e->st_drain); }
+    if (e->st_dl) { cudaStreamSynchronize(e->st_dl); cudaStreamDestroy(e->st_dl); }
+    for (void *p : e->dev) cudaFree(p);
+    for (BatchSet &B : e->set) {
+        if (B.offsets_host) cudaFreeHost(B.offsets_host);
+        if (B.packed_host) cudaFreeHost(B.packed_host);
+        if (B.overflow_host) cudaFreeHost(B.overflow_host);
+        if (B.ctl_host) cudaFreeHost(B.ctl_host);
+        for (auto &ev : B.ev) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : B.ev_misc) if (ev) cudaEventDestroy(ev);
+        for (auto &row : B.ev_grp) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : B.ev_off) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : B.ev_chunk) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : B.kev) if (ev) cudaEventDestroy(ev);
+        for (auto &ev : B.kev_me) if (ev) cudaEventDestroy(ev);
+    }
+    if (e->ev_mark) cudaEventDestroy(e->ev_mark);
+    if (e->ev_last_done) cudaEventDestroy(e->ev_last_done);
+    delete e;
+}
+
+int hb_enc_headers(hb_encoder *e, uint8_t *out, size_t cap, size_t *len)
+{
+    if (!e) return HB_ERR_ARG;
+    HB_ARG(e->ctx, out && len);
+    std::vector<uint8_t> buf;
+    append_nal(buf, NAL_VPS, e->vps, true);
+    append_nal(buf, NAL_SPS, e->sps, true);
+    append_nal(buf, NAL_PPS, e->pps, true);
+    if (buf.size() > cap) return hb_fail(e->ctx, HB_ERR_SPACE, "%s", "header buffer too small");
+    memcpy(out, buf.data(), buf.size());
+    *len = buf.size();
+    return HB_OK;
+}
+
+int hb_enc_coded_size(const hb_encoder *e, int *wc, int *hc)
+{
+    if (!e || !wc || !hc) return HB_ERR_ARG;
+    *wc = e->g.wc; *hc = e->g.hc;
+    return HB_OK;
+}
+
+int hb_enc_request_stop(hb_encoder *e)
+{
+    if (!e) return HB_ERR_ARG;
+    e->stop.store(1);
+    return HB_OK;
+}
+
+int hb_enc_poll_progress(const hb_encoder *e, int *frames_done)
+{
+    if (!e || !frames_done) return HB_ERR_ARG;
+    *frames_done = e->done.load();
+    return HB_OK;
+}
+
+int hb_enc_last_timing(const hb_encoder *e, float *total_ms, float *kernel_ms)
+{
+    if (!e) return HB_ERR_ARG;
+    if (total_ms) *total_ms = e->last_total_ms;
+    if (kernel_ms) *kernel_ms = e->last_kernel_ms;
+    return HB_OK;
+}
+
+namespace {
+int encode_common(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *out, size_t cap, size_t *out_len, hb_frame_stat *stats,
+                  int *frames_out, bool delayed)
+{
+    hb_ctx *ctx = e->ctx;
+    HB_ARG(ctx, out && out_len);
+    HB_ARG(ctx, delayed || fr);
+    if (fr) {
+        HB_ARG(ctx, fr->data && fr->n_frames >= 0);
+        HB_ARG(ctx, fr->format == HB_PIX_YUV420P8 || fr->format == HB_PIX_P010 || fr->format == HB_PIX_YUV420P16);
+        HB_ARG(ctx, fr->frame_bytes >= input_frame_bytes(e->prm, fr->format));
+    }
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t written = 0;
+    float total_ms = 0, kernel_ms = 0;
+    int emitted = 0;
+    e->done.store(0);
+    const int n_frames = fr ? fr->n_frames : 0;
+    for (int base = 0; base < n_frames; base += e->max_batch) {
+        const int n = std::min(e->max_batch, n_frames - base);
+        BatchSet &B = e->set[e->next_set];
+        BatchSet &prev = e->set[e->next_set ^ 1];
+        HB_TRY(enqueue_batch(e, B, fr, base, n, force_idr && base == 0));
+        e->next_set ^= 1;
+        if (prev.pending) {      // drain the batch before this one while the GPU works on this one
+            const int pn = prev.n;
+            HB_TRY(drain_batch(e, prev, out, cap, written, stats ? stats + emitted : nullptr, total_ms, kernel_ms));
+            emitted += pn;
+        }
+    }
+    if (!delayed || !fr) {       // synchronous call, or flush: nothing stays in flight
+        for (int k = 0; k < 2; k++) {
+            BatchSet &B = e->set[(e->next_set + k) & 1];      // older batch first
+            if (!B.pending) continue;
+            const int pn = B.n;
+            HB_TRY(drain_batch(e, B, out, cap, written, stats ? stats + emitted : nullptr, total_ms, kernel_ms));
+            emitted += pn;
+        }
+    }
     e->last_total_ms = total_ms;
     e->last_kernel_ms = kernel_ms;
     *out_len = written;
+    if (frames_out) *frames_out = emitted;
+    return HB_OK;
+}
+}  // namespace
+
+int hb_enc_encode(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *out, size_t cap, size_t *out_len, hb_frame_stat *stats)
+{
+    if (!e) return HB_ERR_ARG;
+    return encode_common(e, fr, force_idr, out, cap, out_len, stats, nullptr, false);
+}
+
+int hb_enc_encode_delayed(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *out, size_t cap, size_t *out_len, hb_frame_stat *stats,
+                          int *frames_out)
+{
+    if (!e) return HB_ERR_ARG;
+    return encode_common(e, fr, force_idr, out, cap, out_len, stats, frames_out, true);
+}
+
+int hb_enc_mark(hb_encoder *e)
+{
+    if (!e) return HB_ERR_ARG;
+    HB_CUDA(e->ctx, cudaSetDevice(e->ctx->device));
+    HB_CUDA(e->ctx, cudaEventRecord(e->ev_mark, e->ctx->stream));
+    e->have_last_done = false;
+    return HB_OK;
+}
+
+int hb_enc_elapsed(hb_encoder *e, float *ms)
+{
+    if (!e || !ms) return HB_ERR_ARG;
+    HB_ARG(e->ctx, e->have_last_done);
+    HB_CUDA(e->ctx, cudaEventSynchronize(e->ev_last_done));
+    HB_CUDA(e->ctx, cudaEventElapsedTime(ms, e->ev_mark, e->ev_last_done));
     return HB_OK;
 }
 
@@ -913,12 +1030,12 @@ int hb_enc_read_recon(hb_encoder *e, int i, uint16_t *y, uint16_t *u, uint16_t *
 {
     if (!e) return HB_ERR_ARG;
     hb_ctx *ctx = e->ctx;
-    HB_ARG(ctx, (e->prm.keep_recon || e->prm.hash_sei) && i >= 0 && i < e->max_batch && y && u && v);
+    HB_ARG(ctx, (e->prm.keep_recon || e->prm.hash_sei) && e->last_drained && i >= 0 && i < e->max_batch && y && u && v);
     const Geom &g = e->g;
     HB_CUDA(ctx, cudaSetDevice(ctx->device));
-    HB_CUDA(ctx, cudaMemcpy(y, e->slot[i].keep.y, (size_t)g.wc * g.hc * 2, cudaMemcpyDeviceToHost));
-    HB_CUDA(ctx, cudaMemcpy(u, e->slot[i].keep.u, (size_t)g.wc * g.hc / 2, cudaMemcpyDeviceToHost));
-    HB_CUDA(ctx, cudaMemcpy(v, e->slot[i].keep.v, (size_t)g.wc * g.hc / 2, cudaMemcpyDeviceToHost));
+    HB_CUDA(ctx, cudaMemcpy(y, e->last_drained->slot[i].keep.y, (size_t)g.wc * g.hc * 2, cudaMemcpyDeviceToHost));
+    HB_CUDA(ctx, cudaMemcpy(u, e->last_drained->slot[i].keep.u, (size_t)g.wc * g.hc / 2, cudaMemcpyDeviceToHost));
+    HB_CUDA(ctx, cudaMemcpy(v, e->last_drained->slot[i].keep.v, (size_t)g.wc * g.hc / 2, cudaMemcpyDeviceToHost));
     return HB_OK;
 }
 
@@ -926,11 +1043,11 @@ int hb_enc_read_decisions(hb_encoder *e, int i, void *cus, int16_t *coefs)
 {
     if (!e) return HB_ERR_ARG;
     hb_ctx *ctx = e->ctx;
-    HB_ARG(ctx, i >= 0 && i < e->max_batch);
+    HB_ARG(ctx, e->last_drained && i >= 0 && i < e->max_batch);
     const size_t ncu = (size_t)e->g.cuw * e->g.cuh;
     HB_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (cus) HB_CUDA(ctx, cudaMemcpy(cus, e->slot[i].cus, ncu * sizeof(CuInfo), cudaMemcpyDeviceToHost));
-    if (coefs) HB_CUDA(ctx, cudaMemcpy(coefs, e->slot[i].coefs, ncu * kCuCoefs * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (cus) HB_CUDA(ctx, cudaMemcpy(cus, e->last_drained->slot[i].cus, ncu * sizeof(CuInfo), cudaMemcpyDeviceToHost));
+    if (coefs) HB_CUDA(ctx, cudaMemcpy(coefs, e->last_drained->slot[i].coefs, ncu * kCuCoefs * sizeof(int16_t), cudaMemcpyDeviceToHost));
     return HB_OK;
 }
 

@@ -146,6 +146,46 @@ class B200Encoder:
         out = self._out[:n.value].tobytes()
         return out, [FrameStat(bool(s.is_idr), s.poc, s.qp, s.bytes) for s in stats[:n_frames]]
 
+    def encode_delayed(self, data, n_frames: int, fmt: int = PIX_YUV420P8, force_idr: bool = False, on_device: bool = False,
+                       frame_bytes: Optional[int] = None) -> Tuple[bytes, List[FrameStat]]:
+        """Pipelined form: enqueue ``n_frames`` frames, return the access units of frames submitted by earlier calls (possibly
+        none).  ``data is None`` flushes.  The input buffer must stay alive until its frames have been returned."""
+        if data is None:
+            frp = None
+        else:
+            fr = HbFrames()
+            if on_device:
+                fr.data = int(data)
+            else:
+                arr = np.ascontiguousarray(data)
+                self._inflight = (getattr(self, '_inflight', ()) + (arr,))[-3:]      # keep the host buffers of the batches in flight
+                fr.data = arr.ctypes.data
+            fr.on_device, fr.format, fr.n_frames = int(on_device), fmt, n_frames
+            fr.frame_bytes = frame_bytes or self.frame_bytes(fmt)
+            frp = C.byref(fr)
+        need = 2 * self.max_batch * self.frame_bytes(PIX_YUV420P8) + max(0, n_frames) * self.frame_bytes(PIX_YUV420P8) + (1 << 20)
+        if self._out.size < need:
+            self._out = np.empty(need, np.uint8)
+        cap_stats = max(1, 2 * self.max_batch + max(0, n_frames))
+        stats = (HbFrameStat * cap_stats)()
+        n, k = C.c_size_t(), C.c_int()
+        self.L.hb_enc_encode_delayed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.L.hb_enc_encode_delayed(self.h, frp, int(force_idr), self._out.ctypes.data, self._out.size, C.byref(n), stats, C.byref(k)))
+        return self._out[:n.value].tobytes(), [FrameStat(bool(s.is_idr), s.poc, s.qp, s.bytes) for s in stats[:k.value]]
+
+    def flush(self) -> Tuple[bytes, List[FrameStat]]:
+        return self.encode_delayed(None, 0)
+
+    def mark(self):
+        self.L.hb_enc_mark.argtypes = [C.c_void_p]
+        self._check(self.L.hb_enc_mark(self.h))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float()
+        self.L.hb_enc_elapsed.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self.L.hb_enc_elapsed(self.h, C.byref(ms)))
+        return ms.value
+
     def last_timing(self) -> Tuple[float, float]:
         a, b = C.c_float(), C.c_float()
         self.L.hb_enc_last_timing(self.h, C.byref(a), C.byref(b))

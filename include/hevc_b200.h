@@ -166,6 +166,17 @@ int hb_enc_coded_size(const hb_encoder *enc, int *coded_w, int *coded_h);
  * frame to out; stats (optional) receives one entry per frame.  The call returns when the bytes are in out. */
 int hb_enc_encode(hb_encoder *enc, const hb_frames *frames, int force_idr, uint8_t *out, size_t cap, size_t *out_len,
                   hb_frame_stat *stats);
+/* Pipelined form (the way libx265's x265_encoder_encode delivers its output with a delay): the frames are enqueued and the
+ * call returns the access units of the frames submitted by EARLIER calls that were still in flight, so that the frame
+ * chain of this batch overlaps the CABAC tail, download and access-unit assembly of the previous one.  frames == NULL
+ * flushes: everything still in flight is returned.  *frames_out = number of access units written (stats likewise).
+ * Host input buffers must stay valid until the frames have been returned. */
+int hb_enc_encode_delayed(hb_encoder *enc, const hb_frames *frames, int force_idr, uint8_t *out, size_t cap, size_t *out_len,
+                          hb_frame_stat *stats, int *frames_out);
+/* region timing across pipelined calls: hb_enc_mark records a CUDA event on the encoder's stream; hb_enc_elapsed returns the
+ * device time from that mark to the end of the last completed bitstream download */
+int hb_enc_mark(hb_encoder *enc);
+int hb_enc_elapsed(hb_encoder *enc, float *ms);
 /* device time of the last hb_enc_encode call, measured with CUDA events on the encoder's stream:
  * total (first upload to last download) and kernels only */
 int hb_enc_last_timing(const hb_encoder *enc, float *total_ms, float *kernel_ms);

@@ -189,3 +189,27 @@ def test_closed_gop_segments_concatenate(ctx):
     assert [len(d[0]) for d in fforacle.decode_hevc(whole, verify_hash=True)] == [len(d[0]) for d in dec]
     for a, b in zip(fforacle.decode_hevc(whole, verify_hash=False), dec):
         assert all((a[c] == b[c]).all() for c in range(3))
+
+
+def test_delayed_pipeline_matches_synchronous(ctx):
+    """hb_enc_encode_delayed returns the access units one batch late (the next batch's frame chain overlaps the previous
+    batch's CABAC tail and host assembly); the bytes are those of the synchronous call."""
+    from hevc_b200 import encoder as E
+    w, h, n = 192, 112, 23
+    p = ec.b200_params(w, h, 8, keyint=6)
+    frames = ec.clip_frames(w, h, n, seed=5)
+    ref_stream, _, _ = _gpu_encode(ctx, p, frames, (28, 30), batch=4, hash_sei=False, read_back=False, rate_control=True)
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=(28, 30), hash_sei=False, keep_recon=False, rate_control=True), max_batch=4)
+    out, counts, pos = b'', [], 0
+    for k in (4, 7, 1, 8, 3):                         # batches of mixed size, some calls spanning several batches
+        chunk, stats = enc.encode_delayed(E.pack_yuv420p8(frames[pos:pos + k]), k)
+        out += chunk
+        counts.append(len(stats))
+        pos += k
+    chunk, stats = enc.flush()
+    out += chunk
+    counts.append(len(stats))
+    enc.close()
+    assert pos == n and sum(counts) == n
+    assert counts[0] == 0 and counts[-1] > 0          # the first call has nothing to return yet, the flush returns the rest
+    assert out == ref_stream
