@@ -223,7 +223,8 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
         enc = B200Encoder(ctx, to_c_params(params), max_batch=batch)
         reader = open_reader(file_path, VideoInfo(**{**info.__dict__, 'width': src_w, 'height': src_h}))
         chunks: List[bytes] = []
-        done = 0
+        done = submitted = 0
+        inflight: list = []
         tdev = torch.device('cuda', dev)
         matrix = 'bt2020' if params.matrix_coeffs == 9 else 'bt709' if params.matrix_coeffs == 1 else 'bt601'
         for buf, n, fmt in reader.batches(batch):
@@ -254,18 +255,29 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
                              y8.shape[1], y8.shape[0], _cabi.dp(y16), w * 2, _cabi.dp(uv16), w * 2, w, h)
                 torch.cuda.synchronize(tdev)
                 ctx.sync()
-                data, _ = enc.encode(out.data_ptr(), n, fmt=PIX_P010, on_device=True)
+                inflight = (inflight + [out])[-3:]            # device input must outlive the batches still in the encoder
+                data, st = enc.encode_delayed(out.data_ptr(), n, fmt=PIX_P010, on_device=True)
             else:
-                data, _ = enc.encode(np.ascontiguousarray(buf), n, fmt=fmt)
+                data, st = enc.encode_delayed(np.ascontiguousarray(buf), n, fmt=fmt)
+            # pipelined: the call returns the access units of the previous batch while this one is being encoded
             chunks.append(data)
-            done += n
-            if progress_callback:
+            done += len(st)
+            submitted += n
+            if progress_callback and st:
                 try:
                     progress_callback(file_path.name, done, max(total_frames, done))
                 except Exception:
                     logger.debug('progress callback raised', exc_info=True)
-        if done == 0:
+        if submitted == 0:
             return 1, 'no frames decoded'
+        data, st = enc.flush()
+        chunks.append(data)
+        done += len(st)
+        if progress_callback and st:
+            try:
+                progress_callback(file_path.name, done, max(total_frames, done))
+            except Exception:
+                logger.debug('progress callback raised', exc_info=True)
         track = mp4.TrackInfo(params.width, params.height, params.fps_num, params.fps_den, params.profile_idc, params.level_idc, params.tier,
                               params.bit_depth, params.colour_primaries, params.transfer_characteristics, params.matrix_coeffs, params.full_range,
                               params.master_display if params.hdr10 else None, params.max_cll, params.max_fall)
