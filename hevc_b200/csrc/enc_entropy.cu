@@ -585,7 +585,7 @@ __device__ __forceinline__ int next_coded_cu(const EntropyWarpScratch &s, const 
 // down through global memory (sync area of the frame); CTAs of a grid are dispatched in index order, so the CTA owning row
 // r-1 is always resident (or done) when row r waits for it.  Nothing on the per-CU path waits for global memory: CU records
 // are staged two CTUs ahead and levels one coded CU ahead with cp.async.
-__global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(EntropyParams p)
+__global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams p)
 {
     const Geom &g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
