@@ -492,14 +492,15 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                     ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = B.ctl_dev + i;
                     // motion search, then two merge-aware passes over the field (the second one inside k_inter)
                     ip.mv_in = nullptr; ip.satd_in = nullptr; ip.mv_out = e->mvf[0]; ip.satd_out = e->satdf[0];
-                    k_me<<<nctu, 128, 0, st>>>(ip);
+                    static const int xs = getenv("HB_DEBUG_EXTRA_SMEM") ? atoi(getenv("HB_DEBUG_EXTRA_SMEM")) : 0;      // occupancy experiments
+                    k_me<<<nctu, 128, xs, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev_me[i], st));
                     ip.mv_in = e->mvf[0]; ip.satd_in = e->satdf[0]; ip.mv_out = e->mvf[1]; ip.satd_out = e->satdf[1];
-                    k_merge<<<nctu, 128, 0, st>>>(ip);
+                    k_merge<<<nctu, 128, xs, st>>>(ip);
                     HB_LAUNCHED(ctx);
                     ip.mv_in = e->mvf[1]; ip.satd_in = e->satdf[1]; ip.mv_out = nullptr; ip.satd_out = nullptr;
-                    k_inter<<<nctu, 128, 0, st>>>(ip);
+                    k_inter<<<nctu, 128, xs, st>>>(ip);
                     HB_LAUNCHED(ctx);
                 }
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[2 * i + 1], st));
