@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
                                                uint8_t *__restrict__ dst, int ds, int dw, int dh, const int2 *__restrict__ xtab,
                                                const int2 *__restrict__ ytab, int out_depth, int out_shift, int step)
 {
-    __shared__ uint8_t foot[PLANES][SC_FH][SC_FW];
+    __shared__ __align__(16) uint8_t foot[PLANES][SC_FH][SC_FW];
     __shared__ short hp[PLANES][SC_FH][SC_TW];
     __shared__ short xtap[SC_TW][4], ytap[SC_TH][4];     // per-tile copies of the phase taps (constant memory serialises on divergent phases)
     __shared__ int xfirst[SC_TW], yfirst[SC_TH];
@@ -234,28 +234,43 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
             for (int t = 0; t < 4; t++) ytap[tid - 64][t] = c_bicubic[yp.y][t];
         }
         if (staged) {
-            // no run-time divisions in the tile loops: warps walk rows, lanes walk columns
-            for (int r = tid >> 5; r < fh; r += 8) {
-                const int sy = min(max(fy0 + r, 0), sh - 1);
-                for (int cidx = tid & 31; cidx < fw; cidx += 32) {
-                    const int sx = min(max(fx0 + cidx, 0), sw - 1);
-                    foot[0][r][cidx] = s0[(size_t)sy * ss + sx];
-                    if (PLANES == 2)
-                        foot[1][r][cidx] = s1[(size_t)sy * ss + sx];
+            // footprint: interior tiles copy aligned 32-bit words (the footprint starts at fx0 rounded down to 4 bytes: `fskew`
+            // bytes of slack on the left), edge tiles clamp sample by sample
+            const int fxa = fx0 & ~3, fskew = fx0 - fxa, nw = (fskew + fw + 3) >> 2;
+            const bool words = fxa >= 0 && fxa + 4 * nw <= sw && fy0 >= 0 && fy1 < sh && (ss & 3) == 0 && 4 * nw <= SC_FW &&
+                               ((reinterpret_cast<uintptr_t>(s0) | (PLANES == 2 ? reinterpret_cast<uintptr_t>(s1) : 0)) & 3) == 0;
+            const int skew = words ? fskew : 0;
+            if (words) {
+                for (int i = tid; i < fh * nw; i += 256) {
+                    const int r = i / nw, wi = i - r * nw;
+                    const size_t off = (size_t)(fy0 + r) * ss + fxa + 4 * wi;
+                    reinterpret_cast<uint32_t *>(&foot[0][r][0])[wi] = *reinterpret_cast<const uint32_t *>(s0 + off);
+                    if (PLANES == 2) reinterpret_cast<uint32_t *>(&foot[1][r][0])[wi] = *reinterpret_cast<const uint32_t *>(s1 + off);
+                }
+            } else {
+                for (int r = tid >> 5; r < fh; r += 8) {
+                    const int sy = min(max(fy0 + r, 0), sh - 1);
+                    for (int cidx = tid & 31; cidx < fw; cidx += 32) {
+                        const int sx = min(max(fx0 + cidx, 0), sw - 1);
+                        foot[0][r][cidx] = s0[(size_t)sy * ss + sx];
+                        if (PLANES == 2)
+                            foot[1][r][cidx] = s1[(size_t)sy * ss + sx];
+                    }
                 }
             }
             __syncthreads();
-            for (int i = tid; i < fh * SC_TW; i += 256) {
-                const int r = i >> 6, ox = i & (SC_TW - 1);
-                if (ox >= tw) continue;
-                const int base = xfirst[ox] - fx0;
+            {   // horizontal pass: a thread keeps one output column (256 % 64 == 0), its taps and source offset live in registers
+                const int ox = tid & (SC_TW - 1);
+                if (ox < tw) {
+                    const int base = xfirst[ox] - fx0 + skew;
+                    const int t0 = xtap[ox][0], t1 = xtap[ox][1], t2 = xtap[ox][2], t3 = xtap[ox][3];
+                    for (int r = tid >> 6; r < fh; r += 4) {
 #pragma unroll
-                for (int p = 0; p < PLANES; p++) {
-                    int acc = 128;
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        acc += xtap[ox][t] * foot[p][r][base + t];
-                    hp[p][r][ox] = (short)(acc >> 8);
+                        for (int p = 0; p < PLANES; p++) {
+                            const uint8_t *f = &foot[p][r][base];
+                            hp[p][r][ox] = (short)((128 + t0 * f[0] + t1 * f[1] + t2 * f[2] + t3 * f[3]) >> 8);
+                        }
+                    }
                 }
             }
             __syncthreads();
