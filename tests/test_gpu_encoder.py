@@ -213,3 +213,26 @@ def test_delayed_pipeline_matches_synchronous(ctx):
     assert pos == n and sum(counts) == n
     assert counts[0] == 0 and counts[-1] > 0          # the first call has nothing to return yet, the flush returns the rest
     assert out == ref_stream
+
+
+def test_empty_call_stop_and_argument_errors(ctx):
+    """Edge cases of the C ABI: zero frames is a no-op, a flush with nothing in flight returns nothing, request_stop makes the
+    next call fail with HB_ERR_STOPPED instead of encoding, bad geometry is rejected at creation."""
+    from hevc_b200 import _cabi
+    from hevc_b200 import encoder as E
+    p = ec.b200_params(64, 64, 8, keyint=4)
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=(30, 32), hash_sei=False, keep_recon=False, rate_control=False), max_batch=4)
+    out, stats = enc.encode(np.zeros(1, np.uint8), 0)
+    assert out == b'' and stats == []
+    out, stats = enc.flush()
+    assert out == b'' and stats == []
+    frames = ec.clip_frames(64, 64, 2)
+    first, _ = enc.encode(E.pack_yuv420p8(frames), 2)
+    assert first[:5] == b'\x00\x00\x00\x01\x40'            # VPS first: the stream starts with its parameter sets
+    enc.request_stop()
+    with pytest.raises(_cabi.HbError):
+        enc.encode(E.pack_yuv420p8(frames), 2)
+    enc.close()
+    bad = ec.b200_params(63, 64, 8, keyint=4)
+    with pytest.raises(_cabi.HbError):
+        E.B200Encoder(ctx, E.to_c_params(bad, qp=(30, 32)), max_batch=2)
