@@ -385,48 +385,43 @@ __device__ __forceinline__ void merge_decide(const InterParams &p, WarpScratch &
     const Geom &g = p.g;
     const int x0 = cx * 16, y0 = cy * 16, idx = cy * g.cuw + cx;
     const MV own = unpack_mv(p.mv_in[idx]);
-    MV cand[6];
-    bool ok[6];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int nx = cx + (k == 2 ? 1 : k == 1 ? 0 : -1), ny = cy + (k == 0 ? 0 : k == 3 ? 1 : -1);
-        ok[k] = nx >= 0 && ny >= 0 && nx < g.cuw && ny < g.cuh;
-        cand[k] = ok[k] ? unpack_mv(p.mv_in[ny * g.cuw + nx]) : MV{0, 0};
+    // lane k < 6 owns candidate k (A1, B1, B0, A0, B2, zero): its vector, validity, duplicate and range checks are computed
+    // once, in parallel; the evaluation loop then walks the surviving candidates in order
+    bool okk = lane == 5;
+    uint32_t mine = 0;                                  // packed vector of this lane's candidate (zero vector for lane 5)
+    if (lane < 5) {
+        const int nx = cx + (lane == 2 ? 1 : lane == 1 ? 0 : -1), ny = cy + (lane == 0 ? 0 : lane == 3 ? 1 : -1);
+        okk = nx >= 0 && ny >= 0 && nx < g.cuw && ny < g.cuh;
+        if (okk) mine = p.mv_in[ny * g.cuw + nx];
     }
-    cand[5] = MV{0, 0};
-    ok[5] = true;
-    int own_bits = 0x7fffffff;
+    const MV m = unpack_mv(mine);
+    const bool same_as_own = m.x == own.x && m.y == own.y;
+    const int bts = !okk ? 0x7fffffff : same_as_own ? 0 : mv_bits1(own.x - m.x) + mv_bits1(own.y - m.y);
+    const int own_bits = __reduce_min_sync(0xffffffffu, bts);
+    const unsigned okmask = __ballot_sync(0xffffffffu, okk);
+    bool dup = same_as_own;
 #pragma unroll
-    for (int k = 0; k < 6; k++)
-        if (ok[k]) {
-            const int bts = (cand[k].x == own.x && cand[k].y == own.y) ? 0 : mv_bits1(own.x - cand[k].x) + mv_bits1(own.y - cand[k].y);
-            own_bits = min(own_bits, bts);
-        }
+    for (int j = 0; j < 5; j++) {
+        const uint32_t mj = __shfl_sync(0xffffffffu, mine, j);
+        dup |= j < lane && ((okmask >> j) & 1) && mj == mine;
+    }
+    const MV cm = clamp_mv(g, x0, y0, m);
+    const bool eval = okk && !dup && cm.x == m.x && cm.y == m.y && abs((m.x >> 2) - (own.x >> 2)) <= 2 && abs((m.y >> 2) - (own.y >> 2)) <= 2;
+    unsigned todo = __ballot_sync(0xffffffffu, eval) & 0x3fu;
     best = own;
     bsatd = p.satd_in[idx];
     int bcost = bsatd + ((lambda * (own_bits + 2)) >> 8) + 1;         // +1: ties go to a merge candidate
-    // not unrolled: the body holds a full interpolation + SATD, six copies of it made the kernel miss the instruction cache
-    // (k_inter: 35 % of issue cycles stalled on instruction fetch); the candidate is picked with a select chain instead
+    // (loop kept rolled: six inlined copies of interpolation + SATD made the kernel miss the instruction cache)
 #pragma unroll 1
-    for (int k = 0; k < 6; k++) {
-        MV m = cand[0];
-        bool okk = ok[0];
-#pragma unroll
-        for (int j = 1; j < 6; j++)
-            if (k == j) { m = cand[j]; okk = ok[j]; }
-        if (!okk) continue;
-        bool dup = m.x == own.x && m.y == own.y;
-#pragma unroll
-        for (int j = 0; j < 5; j++) dup |= j < k && ok[j] && cand[j].x == m.x && cand[j].y == m.y;
-        if (dup) continue;
-        const MV cm = clamp_mv(g, x0, y0, m);
-        if (cm.x != m.x || cm.y != m.y) continue;
-        if (abs((m.x >> 2) - (own.x >> 2)) > 2 || abs((m.y >> 2) - (own.y >> 2)) > 2) continue;
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const MV c = unpack_mv(__shfl_sync(0xffffffffu, mine, k));
         int pv[8];
-        interp_cols(s, (m.x >> 2) - wx0, (m.y >> 2) - wy0, m.x & 3, m.y & 3, g.bit_depth, lane, pv);
+        interp_cols(s, (c.x >> 2) - wx0, (c.y >> 2) - wy0, c.x & 3, c.y & 3, g.bit_depth, lane, pv);
         const int sd = satd_cols(st, pv, lane);
         const int cost = sd + ((lambda * 2) >> 8);
-        if (cost < bcost) { bcost = cost; best = m; bsatd = sd; }
+        if (cost < bcost) { bcost = cost; best = c; bsatd = sd; }
     }
 }
 
