@@ -455,18 +455,27 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
     const MV pred = clamp_mv(g, x0, y0, ctu_mv(g, p.cmv, tx, ty));
     MV best{0, 0};
     int bcost = 0x7fffffff;
-    // ---- integer stage 1: six candidates straight from global memory (lane -> row lane >> 1, 8 samples)
+    // ---- integer stage 1: six candidates straight from global memory (lane -> row lane >> 1, 8 samples).  Lane k < 6 fetches
+    //      and clamps candidate k and prices its vector once; the loop broadcasts them.
+    uint32_t my_c = 0;
+    int my_vc = 0;
+    if (lane < 6) {
+        MV c = lane == 0 ? MV{0, 0} : lane == 1 ? pred : lane == 2 ? ctu_mv(g, p.cmv, tx - 1, ty) : lane == 3 ? ctu_mv(g, p.cmv, tx, ty - 1)
+               : lane == 4 ? ctu_mv(g, p.cmv, tx + 1, ty) : ctu_mv(g, p.cmv, tx, ty + 1);
+        c = clamp_mv(g, x0, y0, c);
+        my_c = pack_mv(c);
+        my_vc = mv_cost(lambda8, c.x, c.y, pred.x, pred.y);
+    }
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
-        MV c = k == 0 ? MV{0, 0} : k == 1 ? pred : k == 2 ? ctu_mv(g, p.cmv, tx - 1, ty) : k == 3 ? ctu_mv(g, p.cmv, tx, ty - 1)
-               : k == 4 ? ctu_mv(g, p.cmv, tx + 1, ty) : ctu_mv(g, p.cmv, tx, ty + 1);
-        c = clamp_mv(g, x0, y0, c);
+        const MV c = unpack_mv(__shfl_sync(0xffffffffu, my_c, k));
+        const int vc = __shfl_sync(0xffffffffu, my_vc, k);
         const pixel *r = p.ref.y + (ptrdiff_t)(y0 + (c.y >> 2) + row) * g.rec_stride + x0 + (c.x >> 2) + c0;
         uint32_t rw[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) rw[i] = (uint32_t)r[2 * i] | ((uint32_t)r[2 * i + 1] << 16);
         const uint32_t sad = sad4(s8hi, pack4_msb8(rw[2], rw[3], sh8), sad4(s8lo, pack4_msb8(rw[0], rw[1], sh8), 0));
-        const int cost = warp_sum((int)sad) + mv_cost(lambda8, c.x, c.y, pred.x, pred.y);
+        const int cost = warp_sum((int)sad) + vc;
         if (cost < bcost) { bcost = cost; best = c; }
     }
     const MV centre = best;
@@ -516,26 +525,27 @@ __global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterPara
     for (int step = 2; step >= 1; step--) {
         const MV c2 = best;
         const int iy_min = (c2.y - step) >> 2;                    // the three rows of candidates start at integer row iy_min or iy_min + 1
+        // lane t < 9 owns candidate (dx, dy) = (t / 3 - 1, t % 3 - 1): validity and vector cost once, in parallel
+        int my_cost = -1;
+        if (lane < 9 && lane != 4) {
+            const MV m{c2.x + step * (lane / 3 - 1), c2.y + step * (lane % 3 - 1)};
+            const MV cm = clamp_mv(g, x0, y0, m);
+            if (cm.x == m.x && cm.y == m.y) my_cost = mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+        }
+        const unsigned okmask = __ballot_sync(0xffffffffu, my_cost >= 0);
 #pragma unroll 1
         for (int dx = -1; dx <= 1; dx++) {
             const int mx = c2.x + step * dx;
-            bool ok[3];
-            bool any = false;
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++) {
-                const MV m{mx, c2.y + step * dy};
-                const MV cm = clamp_mv(g, x0, y0, m);
-                ok[dy + 1] = (dx || dy) && cm.x == m.x && cm.y == m.y;
-                any |= ok[dy + 1];
-            }
-            if (!any) continue;
+            if (!((okmask >> (3 * (dx + 1))) & 7u)) continue;
             interp_hpass(s, (mx >> 2) - wx0, iy_min - wy0, mx & 3, 24, bd, lane);       // shared by the column's candidates
 #pragma unroll
             for (int dy = -1; dy <= 1; dy++) {
-                if (!ok[dy + 1]) continue;
+                const int t = 3 * (dx + 1) + dy + 1;
+                if (!((okmask >> t) & 1)) continue;
+                const int vc = __shfl_sync(0xffffffffu, my_cost, t);
                 const MV m{mx, c2.y + step * dy};
                 interp_vpass(s, (m.y >> 2) - iy_min, m.y & 3, bd, lane, pv);
-                const int cost = satd_cols(st, pv, lane) + mv_cost(lambda, m.x, m.y, pred.x, pred.y);
+                const int cost = satd_cols(st, pv, lane) + vc;
                 if (cost < bcost) { bcost = cost; best = m; }
             }
             __syncwarp();
