@@ -950,6 +950,10 @@ int encode_common(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
         HB_ARG(ctx, fr->format == HB_PIX_YUV420P8 || fr->format == HB_PIX_P010 || fr->format == HB_PIX_YUV420P16);
         HB_ARG(ctx, fr->frame_bytes >= input_frame_bytes(e->prm, fr->format));
     }
+    // the synchronous call sizes its output for its own frames: frames still in flight from the pipelined entry point must be
+    // flushed first
+    if (!delayed && (e->set[0].pending || e->set[1].pending))
+        return hb_fail(ctx, HB_ERR_ARG, "%s", "hb_enc_encode with frames in flight: flush hb_enc_encode_delayed first");
     HB_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t written = 0;
     float total_ms = 0, kernel_ms = 0;
