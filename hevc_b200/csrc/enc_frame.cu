@@ -128,12 +128,26 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
         const int i = tid & 7, j = tid >> 3;
         reinterpret_cast<uint8_t *>(curw)[tid] = dcur[(size_t)clampd(ty * 8 + j, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i, 0, g.dsw - 1)];
     }
-    for (int k = tid; k < 32 * 32; k += 128) {
-        const int i = k & 31, j = k >> 5;
-        const uint8_t v = dprev[(size_t)clampd(ty * 8 + j - kCmeRange, 0, g.dsh - 1) * g.dsw + clampd(tx * 8 + i - kCmeRange, 0, g.dsw - 1)];
+    // window: interior CTUs read aligned words and derive the three byte-shifted copies with funnel shifts (each thread owns
+    // two row-words plus their right neighbours); picture-edge CTUs clamp sample by sample
+    const int wx = tx * 8 - kCmeRange, wy = ty * 8 - kCmeRange;
+    if (wx >= 0 && wy >= 0 && wx + 32 <= g.dsw && wy + 32 <= g.dsh && (g.dsw & 3) == 0) {
+        for (int k = tid; k < 32 * 8; k += 128) {
+            const int j = k >> 3, wi = k & 7;
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(dprev + (size_t)(wy + j) * g.dsw + wx);
+            const uint32_t w0 = row[wi], w1 = wi < 7 ? row[wi + 1] : 0;
+            win[0][j * 9 + wi] = w0;
 #pragma unroll
-        for (int sft = 0; sft < 4; sft++)
-            if (i >= sft) reinterpret_cast<uint8_t *>(win[sft])[j * 36 + i - sft] = v;
+            for (int sft = 1; sft < 4; sft++) win[sft][j * 9 + wi] = __funnelshift_r(w0, w1, 8 * sft);
+        }
+    } else {
+        for (int k = tid; k < 32 * 32; k += 128) {
+            const int i = k & 31, j = k >> 5;
+            const uint8_t v = dprev[(size_t)clampd(wy + j, 0, g.dsh - 1) * g.dsw + clampd(wx + i, 0, g.dsw - 1)];
+#pragma unroll
+            for (int sft = 0; sft < 4; sft++)
+                if (i >= sft) reinterpret_cast<uint8_t *>(win[sft])[j * 36 + i - sft] = v;
+        }
     }
     __syncthreads();
     uint32_t c[16];
