@@ -236,3 +236,25 @@ def test_empty_call_stop_and_argument_errors(ctx):
     bad = ec.b200_params(63, 64, 8, keyint=4)
     with pytest.raises(_cabi.HbError):
         E.B200Encoder(ctx, E.to_c_params(bad, qp=(30, 32)), max_batch=2)
+
+
+def test_8k_maximum_size(ctx):
+    """Largest supported geometry class (7680x4320, 135 CTU rows, 240 CTUs per row): IDR + P through both batch sets; the
+    stream decodes under the FFmpeg decoder (picture hash on) to the encoder's reconstruction."""
+    from hevc_b200 import encoder as E
+    from hevc_b200.synth import TorchSynthClip
+    from oracle import fforacle
+    w, h, n = 7680, 4320, 2
+    p = ec.b200_params(w, h, 8, keyint=4)
+    p.level_idc = 183
+    clip = TorchSynthClip(w, h, seed=3, device='cuda:0')
+    frames = clip.frames(0, n).cpu().numpy()
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=(30, 32), hash_sei=True, keep_recon=True, rate_control=False), max_batch=1)
+    stream, stats = enc.encode(frames, n)                 # two batches of one frame: exercises the set hand-over at full width
+    rec1 = enc.read_recon(0)                              # the last drained batch holds frame 1
+    enc.close()
+    assert [s.is_idr for s in stats] == [True, False]
+    dec = fforacle.decode_hevc(stream, verify_hash=True)
+    assert len(dec) == n and dec[1][0].shape == (h, w)
+    for c in range(3):
+        assert (dec[1][c] == rec1[c][:dec[1][c].shape[0], :dec[1][c].shape[1]]).all()
