@@ -440,7 +440,7 @@ __device__ __forceinline__ void merge_decide(const InterParams &p, WarpScratch &
 }
 
 // pass 1 of the motion search: per CU, integer candidates -> 5x5 -> half / quarter sample; writes the vector field and its SATD
-__global__ void __launch_bounds__(128, 7) k_me(const __grid_constant__ InterParams p)
+__global__ void __launch_bounds__(128, 8) k_me(const __grid_constant__ InterParams p)
 {
     __shared__ WarpScratch scratch[4];
     const Geom &g = p.g;
