@@ -216,7 +216,7 @@ void md5(const uint8_t *data, size_t n, uint8_t out[16])
 
 constexpr int kChunk = 8;            // frames per upload / entropy chunk
 constexpr int kMaxChunks = 1024 / kChunk + 1;
-constexpr int kEntropyStreams = 4;
+constexpr int kEntropyStreams = 8;
 constexpr int kGroupFrames = 32;     // frames per drain group (a multiple of kChunk)
 constexpr int kMaxGroups = 1024 / kGroupFrames + 1;
 
@@ -406,9 +406,23 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
         const size_t kb = (size_t)2 * e->max_batch;      // batch-level profiling events start here
         float ingest_ms = 0, coarse_ms = 0;
         (void)ingest_ms; (void)coarse_ms;
+        // CABAC launches for the P frames [pend, end) not handed over yet (runs between key frames)
+        int pend = 0, cur_chunk = 0;
+        auto launch_p_runs = [&](int end) -> int {
+            for (int i0 = pend; i0 < end;) {
+                if (is_idr[i0]) { i0++; continue; }
+                int i1 = i0;
+                while (i1 < end && !is_idr[i1]) i1++;
+                HB_TRY(launch_entropy(e, B, i0, i1 - i0, B.ev_chunk[kMaxChunks + cur_chunk]));
+                i0 = i1;
+            }
+            pend = end;
+            return HB_OK;
+        };
         // ---- chunks: upload (copy stream) | ingest + coarse search + frame chain (main stream) | CABAC (entropy stream)
         for (int c0 = 0, chunk = 0; c0 < n; c0 += kChunk, chunk++) {
             const int cn = std::min(kChunk, n - c0);
+            cur_chunk = chunk;
             const uint8_t *dev_in = in + (size_t)c0 * fr->frame_bytes;
             size_t dev_fb = fr->frame_bytes;
             if (!fr->on_device) {
@@ -533,16 +547,16 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 if (idr) HB_TRY(launch_entropy(e, B, i, 1, B.ev_chunk[kMaxChunks + chunk]));
                 e->cur = 1 - e->cur;
                 e->frame_no++;
+                // last chunk of the batch: hand its frames to CABAC in shrinking groups (.., 2, 1, 1), so that when the chain
+                // ends only the last frame still has its whole entropy latency ahead of it
+                if (c0 + cn == n) {
+                    const int left = c0 + cn - (i + 1);
+                    if (left == 4 || left == 2 || left == 1) HB_TRY(launch_p_runs(i + 1));
+                }
             }
             // CABAC of this chunk on a side stream, overlapping the frame chain of the following chunks (key frames were
             // already launched on their own right after their mode kernel: they carry ~8x the bins of a P frame)
-            for (int i0 = c0; i0 < c0 + cn;) {
-                if (is_idr[i0]) { i0++; continue; }
-                int i1 = i0;
-                while (i1 < c0 + cn && !is_idr[i1]) i1++;
-                HB_TRY(launch_entropy(e, B, i0, i1 - i0, B.ev_chunk[kMaxChunks + chunk]));
-                i0 = i1;
-            }
+            HB_TRY(launch_p_runs(c0 + cn));
             // ---- end of a drain group: compaction + download of its sub-stream sizes behind its CABAC kernels
             if ((c0 + cn) % kGroupFrames == 0 || c0 + cn == n) {
                 const int grp = c0 / kGroupFrames, f0 = grp * kGroupFrames, cnt = c0 + cn - f0;
