@@ -43,12 +43,15 @@ def clip_info(name: str, frames: int):
 def workload_config(args, params, n_gpus):
     return {'workload': f'{args.clip}: {params.width}x{params.height}@{params.fps_num}/{params.fps_den} '
                         f'{"Main10 HDR10" if params.bit_depth == 10 else "Main"} yuv420p8 source -> P010-depth encode',
-            'frames_per_step': args.frames, 'keyint': params.keyint, 'crf': params.crf,
+            'frames_per_step': args.frames * getattr(args, 'streams', 1), 'segment_frames': args.frames, 'streams_per_gpu': getattr(args, 'streams', 1),
+            'keyint': params.keyint, 'crf': params.crf,
             'vbv_maxrate_kbps': params.vbv_maxrate_kbps, 'vbv_bufsize_kbit': params.vbv_bufsize_kbit,
             'level_idc': params.level_idc,
             'rate_control': 'crf quality ceiling (qp_i, qp_p) = %s, VBV-constrained on the device (vbv-maxrate / vbv-bufsize)' % (str(args.qp),),
-            'parallelism': f'{n_gpus} independent clips, one per GPU' if n_gpus > 1 else 'single GPU',
-            'l2': 'inputs (%.1f GB/step) exceed the 126 MB L2' % (args.frames * params.width * params.height * 1.5 / 1e9)}
+            'parallelism': ('%d GPU(s), one process each; per GPU %d independent encoder stream(s) fed with closed-GOP segments of %d frames '
+                            '(the reference\'s N-worker model applied to one device), no collective on the data path'
+                            % (n_gpus, getattr(args, 'streams', 1), args.frames)),
+            'l2': 'inputs (%.1f GB/step) exceed the 126 MB L2' % (args.frames * getattr(args, 'streams', 1) * params.width * params.height * 1.5 / 1e9)}
 
 
 class ClockSampler:
@@ -187,7 +190,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from hevc_b200 import _cabi, derive
-    from hevc_b200.encoder import B200Encoder, crf_to_qp, to_c_params
+    from hevc_b200.encoder import ParallelSegmentEncoder, crf_to_qp, to_c_params
     from hevc_b200.synth import TorchSynthClip
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -206,29 +209,35 @@ def run_b200(args):
 
     params = derive.derive_b200_params(clip_info(args.clip, args.frames))
     args.qp = crf_to_qp(params.crf)
-    ctx = _cabi.Context(local)
-    enc = B200Encoder(ctx, to_c_params(params), max_batch=args.batch)
-    clip = TorchSynthClip(params.width, params.height, seed=rank, device=f'cuda:{local}')
-    dev_frames = clip.frames(0, args.frames).contiguous()          # resident in HBM
-    host_frames = torch.empty(dev_frames.shape, dtype=torch.uint8, pin_memory=True)
-    host_frames.copy_(dev_frames)
+    S = max(1, args.streams)
+    if args.frames > args.batch:
+        raise SystemExit('--frames (one closed-GOP segment) must fit one device batch (--batch)')
+    enc = ParallelSegmentEncoder(local, to_c_params(params), streams=S, max_batch=args.batch)
+    n = args.frames
+    dev_frames, host_frames = [], []
+    for k in range(S):                                               # every stream encodes its own clip
+        clip = TorchSynthClip(params.width, params.height, seed=rank * 16 + k, device=f'cuda:{local}')
+        d = clip.frames(0, n).contiguous()                           # resident in HBM
+        hbuf = torch.empty(d.shape, dtype=torch.uint8, pin_memory=True)
+        hbuf.copy_(d)
+        dev_frames.append(d)
+        host_frames.append(hbuf)
     torch.cuda.synchronize()
-    n, fb = args.frames, clip.frame_bytes
+    fb = clip.frame_bytes
 
-    # Steps go through the pipelined entry point (hb_enc_encode_delayed, what transcoder.encode_b200 uses): a call enqueues its
-    # 120 frames and returns the access units of the previous step, so that the frame chain of step k+1 overlaps the CABAC tail,
-    # download and access-unit assembly of step k.  A flush closes every timed region, so exactly K steps are inside it.
+    # A step is one closed-GOP segment of `n` frames per stream, submitted through the pipelined entry point
+    # (hb_enc_encode_delayed under ParallelSegmentEncoder): a submit enqueues a segment and returns finished ones, so that the
+    # frame chain of a segment overlaps the CABAC tail, download and access-unit assembly of the previous one, and the second
+    # stream fills the SMs during the first one's key frames, kernel tails and small kernels.  A flush closes every timed
+    # region, so exactly K steps are inside it.
     def step_resident():
-        out, stats = enc.encode_delayed(dev_frames.data_ptr(), n, on_device=True, force_idr=True, frame_bytes=fb)
-        return len(out)
+        return sum(len(enc.submit(dev_frames[k].data_ptr(), n, on_device=True, frame_bytes=fb)[0]) for k in range(S))
 
     def step_host():
-        out, stats = enc.encode_delayed(host_frames.numpy(), n, on_device=False, force_idr=True, frame_bytes=fb)
-        return len(out)
+        return sum(len(enc.submit(host_frames[k].numpy(), n, on_device=False, frame_bytes=fb)[0]) for k in range(S))
 
     def flush():
-        out, stats = enc.flush()
-        return len(out)
+        return len(enc.finish()[0])
 
     for _ in range(args.warmup):
         step_resident()
@@ -237,7 +246,7 @@ def run_b200(args):
     flush()
     # ---- timed: device-resident input; device time from a CUDA event on the encoder's stream before the first step to the
     #      end of the last bitstream download
-    launches0 = ctx.launches
+    launches0 = enc.launches
     enc.profile(1)
     barrier()
     with ClockSampler(local) as clocks:
@@ -252,7 +261,7 @@ def run_b200(args):
         wall_resident = time.perf_counter() - t0
     bytes_out //= args.steps
     prof_ms, prof_n = enc.profile(0)
-    launches = ctx.launches - launches0
+    launches = enc.launches - launches0
     # ---- timed: host buffers through the C ABI (upload + encode + download + access-unit assembly), wall clock
     barrier()
     t0 = time.perf_counter()
@@ -266,7 +275,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_s, wall_res_s, wall_host_s = (float(x) for x in times.cpu())
-    total_frames = world * n * args.steps
+    total_frames = world * S * n * args.steps
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         w, h = params.width, params.height
@@ -290,12 +299,12 @@ def run_b200(args):
             'metric': METRIC, 'value': round(total_frames / dev_s, 3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': round(1000.0 * dev_s / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u16' if params.bit_depth > 8 else 'u8', 'data': 'synthetic', 'config': workload_config(args, params, world),
-            'timing': 'CUDA events: mark on the encoder stream before the first step -> end of the last bitstream download (K pipelined steps + flush), max over ranks',
+            'timing': 'CUDA events: mark on each encoder stream before the first step -> end of its last bitstream download (K pipelined steps + flush), max over streams and ranks',
             'wall_ms_per_step_resident': round(1000.0 * wall_res_s / args.steps, 3),
-            'e2e': {'value': round(total_frames / wall_host_s, 3), 'unit': UNIT, 'h2d_bytes_per_step': n * fb, 'd2h_bytes_per_step': bytes_out,
+            'e2e': {'value': round(total_frames / wall_host_s, 3), 'unit': UNIT, 'h2d_bytes_per_step': S * n * fb, 'd2h_bytes_per_step': bytes_out,
                     'timing': 'wall clock around K x hb_enc_encode_delayed + flush with pinned host buffers'},
             'gpu_launches': int(launches),
-            'bitrate_kbps': round(bytes_out * 8 / 1000.0 / (n * params.fps_den / params.fps_num), 1),
+            'bitrate_kbps': round(bytes_out / S * 8 / 1000.0 / (n * params.fps_den / params.fps_num), 1),
             'roofline': {'kernel': 'k_me (motion search, one launch per P frame)', 'bound': 'hbm', 'achieved': round(achieved, 2),
                          'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 5), 'traffic': traffic,
                          'peak_kind': peak_kind, 'algorithmic_bytes_per_launch': me_bytes, 'avg_launch_ms': round(me_ms, 4),
@@ -308,7 +317,7 @@ def run_b200(args):
             from oracle import cmodel
             cmodel.build()
             sample_n = 3
-            frames_h = [host_frames[i].numpy() for i in range(sample_n)]
+            frames_h = [host_frames[0][i].numpy() for i in range(sample_n)]
             fps, dt, _ = cpu_model_fps(frames_h, params.bit_depth, args.qp, params.keyint, w, h, 1, sample_n)
             line['cpu_baseline'] = {'value': round(fps, 4), 'unit': UNIT, 'cores': 1, 'kind': 'port',
                                     'sample': f'first {sample_n} frames (1 IDR + {sample_n - 1} P) of the same clip, single thread, {dt:.1f} s'}
@@ -316,7 +325,6 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     enc.close()
-    ctx.close()
 
 
 def main():
@@ -328,6 +336,7 @@ def main():
     ap.add_argument('--clip', default='4k60_hdr')
     ap.add_argument('--frames', type=int, default=120, help='frames per step (one closed GOP of the 4K60 HDR configuration)')
     ap.add_argument('--batch', type=int, default=120, help='frames per device batch (one GOP: lets the entropy stage use one SM per frame)')
+    ap.add_argument('--streams', type=int, default=2, help='independent encoder streams per GPU (closed-GOP segments round-robin)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

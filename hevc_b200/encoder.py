@@ -225,3 +225,146 @@ class B200Encoder:
 def pack_yuv420p8(frames: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]]) -> np.ndarray:
     """[(y, u, v)] uint8 planes -> one contiguous buffer in the layout ``hb_frames`` expects."""
     return np.concatenate([np.concatenate([p.reshape(-1) for p in f]) for f in frames]).astype(np.uint8, copy=False)
+
+
+class ParallelSegmentEncoder:
+    """Several independent encoders on ONE device, each on its own context / CUDA stream / host thread, fed with closed-GOP
+    segments round-robin (segment k -> encoder k mod S).  This is the per-GPU form of the reference's concurrency model -- N
+    worker threads on independent files or segments (gui/mainwindow.py:289-301): the frame chain of one
+    stream is serial (every P frame predicts from the previous reconstruction), so a second stream fills the SMs during the
+    first one's kernel tails, key frames and small kernels.  Every segment starts with an IDR frame and its parameter sets
+    and is rate-controlled by its own encoder, so segments concatenate into one valid stream in submission order.
+
+    ``submit`` returns the segments that have completed, in order (possibly none); ``finish`` returns the rest."""
+
+    def __init__(self, device: int, params: HbEncParams, streams: int = 2, max_batch: int = 32):
+        import queue
+        import threading
+        self.streams = max(1, int(streams))
+        self.max_batch = max_batch
+        self._ctxs = [_cabi.Context(device) for _ in range(self.streams)]
+        self._encs = [B200Encoder(c, params, max_batch=max_batch) for c in self._ctxs]
+        self._queues = [queue.Queue() for _ in range(self.streams)]
+        self._lock = threading.Lock()
+        self._done: dict = {}                  # segment number -> (bytes, stats)
+        self._frames: dict = {}                # segment number -> frame count
+        self._error: Optional[BaseException] = None
+        self._submitted = 0
+        self._emitted = 0
+        self._threads = [threading.Thread(target=self._work, args=(k,), daemon=True) for k in range(self.streams)]
+        for t in self._threads:
+            t.start()
+
+    @property
+    def launches(self) -> int:
+        return sum(c.launches for c in self._ctxs)
+
+    def _work(self, k: int):
+        enc, q = self._encs[k], self._queues[k]
+        pending: List[int] = []                # segment numbers inside the encoder's pipeline, oldest first
+        try:
+            while True:
+                job = q.get()
+                if job is None:
+                    break
+                if job == 'flush':
+                    out, stats = enc.flush()
+                    self._publish(pending, out, stats)
+                    pending = []
+                    with self._lock:
+                        self._done[('flushed', k)] = True
+                    continue
+                seq, data, n, kw = job
+                out, stats = enc.encode_delayed(data, n, force_idr=True, **kw)
+                pending.append(seq)
+                done_now = pending[:-1] if stats else []
+                if done_now:
+                    self._publish(done_now, out, stats)
+                    pending = pending[-1:]
+        except BaseException as exc:           # surfaced by the next submit / finish
+            with self._lock:
+                self._error = exc
+
+    def _publish(self, seqs: List[int], out: bytes, stats: List[FrameStat]):
+        # one or more whole segments came back concatenated: split them at their frame counts
+        pos = fpos = 0
+        with self._lock:
+            for s in seqs:
+                n = self._frames[s]
+                size = sum(st.bytes for st in stats[fpos:fpos + n])
+                self._done[s] = (out[pos:pos + size], stats[fpos:fpos + n])
+                pos += size
+                fpos += n
+
+    def _collect(self) -> Tuple[bytes, List[FrameStat]]:
+        out, stats = [], []
+        with self._lock:
+            if self._error is not None:
+                raise self._error
+            while self._emitted in self._done:
+                b, s = self._done.pop(self._emitted)
+                out.append(b)
+                stats += s
+                self._emitted += 1
+        return b''.join(out), stats
+
+    def submit(self, data, n_frames: int, **kw) -> Tuple[bytes, List[FrameStat]]:
+        """One closed-GOP segment of at most ``max_batch`` frames (same arguments as ``B200Encoder.encode_delayed``)."""
+        if n_frames < 1 or n_frames > self.max_batch:
+            raise ValueError('a segment is 1..max_batch frames')
+        seq = self._submitted
+        self._frames[seq] = n_frames
+        self._submitted += 1
+        self._queues[seq % self.streams].put((seq, data, n_frames, kw))
+        return self._collect()
+
+    def finish(self) -> Tuple[bytes, List[FrameStat]]:
+        """Drain every stream; returns the remaining segments in order."""
+        import time
+        for k, q in enumerate(self._queues):
+            with self._lock:
+                self._done.pop(('flushed', k), None)
+            q.put('flush')
+        while True:
+            with self._lock:
+                if self._error is not None:
+                    raise self._error
+                if all(('flushed', k) in self._done for k in range(self.streams)):
+                    for k in range(self.streams):
+                        self._done.pop(('flushed', k))
+                    break
+            time.sleep(0.0002)
+        return self._collect()
+
+    def mark(self):
+        for e in self._encs:
+            e.mark()
+
+    def elapsed_ms(self) -> float:
+        """Device time from ``mark`` to the last completed download, maximum over the streams."""
+        spans = []
+        for e in self._encs:
+            try:
+                spans.append(e.elapsed_ms())
+            except _cabi.HbError:              # a stream that received no segment since the mark
+                pass
+        return max(spans) if spans else 0.0
+
+    def profile(self, enable: int = -1):
+        ms, ln = {}, {}
+        for e in self._encs:
+            a, b = e.profile(enable)
+            for k in a:
+                ms[k] = ms.get(k, 0.0) + a[k]
+                ln[k] = ln.get(k, 0) + b[k]
+        return ms, ln
+
+    def close(self):
+        for q in self._queues:
+            q.put(None)
+        for t in self._threads:
+            t.join(timeout=30)
+        for e in self._encs:
+            e.close()
+        for c in self._ctxs:
+            c.close()

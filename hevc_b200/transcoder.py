@@ -202,8 +202,12 @@ def next_device() -> int:
 
 def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
                 stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
-                target_size: Optional[Tuple[int, int]] = None) -> Tuple[int, str]:
-    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on one B200.  Returns (0, '') or (1, reason) like run_ffmpeg."""
+                target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None) -> Tuple[int, str]:
+    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on one B200.  Returns (0, '') or (1, reason) like run_ffmpeg.
+
+    ``streams`` > 1 (or ``HEVC_B200_STREAMS``) encodes closed-GOP segments of one key-frame interval on that many independent
+    encoder streams of the same GPU (``ParallelSegmentEncoder``); planar 4:2:0 sources only, the pixel-pipeline paths (BGR
+    sources, up-scaling) stay on one stream."""
     import numpy as np
     import torch
 
@@ -220,8 +224,12 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
         if target_size:
             info = VideoInfo(**{**info.__dict__, 'width': target_size[0], 'height': target_size[1]})
         params = derive.derive_b200_params(info)
-        enc = B200Encoder(ctx, to_c_params(params), max_batch=batch)
         reader = open_reader(file_path, VideoInfo(**{**info.__dict__, 'width': src_w, 'height': src_h}))
+        if streams is None:
+            streams = int(os.environ.get('HEVC_B200_STREAMS', '1') or 1)
+        if streams > 1 and reader.kind != 'bgr' and not target_size:
+            return _encode_segments(file_path, out_path, reader, params, dev, streams, progress_callback, total_frames, stop_event)
+        enc = B200Encoder(ctx, to_c_params(params), max_batch=batch)
         chunks: List[bytes] = []
         done = submitted = 0
         inflight: list = []
@@ -292,6 +300,48 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
         except Exception:
             pass
         ctx.close()
+
+
+def _encode_segments(file_path, out_path, reader, params, dev, streams, progress_callback, total_frames, stop_event) -> Tuple[int, str]:
+    """Segment-parallel form of encode_b200: one key-frame interval per segment, segments round-robin over the streams."""
+    import numpy as np
+
+    from . import mp4
+    from .encoder import ParallelSegmentEncoder, to_c_params
+    seg = max(1, min(int(params.keyint), 1024))
+    pse = ParallelSegmentEncoder(dev, to_c_params(params), streams=streams, max_batch=seg)
+    try:
+        chunks: List[bytes] = []
+        done = submitted = 0
+
+        def tick(st):
+            nonlocal done
+            done += len(st)
+            if progress_callback and st:
+                try:
+                    progress_callback(file_path.name, done, max(total_frames, done))
+                except Exception:
+                    logger.debug('progress callback raised', exc_info=True)
+
+        for buf, n, fmt in reader.batches(seg):
+            if stop_event is not None and stop_event.is_set():
+                return 1, 'cancelled'
+            data, st = pse.submit(np.ascontiguousarray(buf), n, fmt=fmt)
+            chunks.append(data)
+            submitted += n
+            tick(st)
+        if submitted == 0:
+            return 1, 'no frames decoded'
+        data, st = pse.finish()
+        chunks.append(data)
+        tick(st)
+        track = mp4.TrackInfo(params.width, params.height, params.fps_num, params.fps_den, params.profile_idc, params.level_idc, params.tier,
+                              params.bit_depth, params.colour_primaries, params.transfer_characteristics, params.matrix_coeffs, params.full_range,
+                              params.master_display if params.hdr10 else None, params.max_cll, params.max_fall)
+        out_path.write_bytes(mp4.mux_annexb(track, b''.join(chunks)))
+        return 0, ''
+    finally:
+        pse.close()
 
 
 # ------------------------------------------------------------------ the drop-in entry point

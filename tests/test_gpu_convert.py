@@ -61,6 +61,27 @@ def test_convert_video_y4m(tmp_path, hdr):
     assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n
 
 
+def test_convert_video_segment_streams(tmp_path, monkeypatch):
+    """HEVC_B200_STREAMS=2: closed-GOP segments of one key-frame interval on two encoder streams of the same GPU; same
+    contract (result entry, progress ticks, compliant hvc1 MP4, every frame decodes)"""
+    w, h, n = 320, 192, 75                                   # 30 fps -> key-frame interval 30: three segments, the last one short
+    clip = SynthClip(w, h, seed=6)
+    frames = [clip.frame(i) for i in range(n)]
+    src = tmp_path / 'seg.y4m'
+    write_y4m(src, frames, w, h, (30, 1))
+    monkeypatch.setenv('HEVC_B200_STREAMS', '2')
+    ticks = []
+    res = transcoder.convert_video(src, tmp_path, progress_callback=lambda *a: ticks.append(a), encoder='b200', device=0)
+    assert res['status'] == 'SUCCESS' and res['method'] == 'B200'
+    assert ticks and ticks[-1][1] == ticks[-1][2] == n
+    data = (tmp_path / 'seg.mp4').read_bytes()
+    assert compliance.check_bytes(data, {'profile_idc': 1, 'tier': 0, 'hdr10': False}) == []
+    rep, dec = _decode_mp4(data)
+    assert len(dec) == n
+    for i in (0, 31, n - 1):
+        assert _psnr(dec[i][0], frames[i][0].astype(np.uint16), 255) > 28
+
+
 def test_convert_video_container_input_and_cancel(tmp_path):
     """BGR frames from a container (OpenCV decode) go through the device CSC kernel; the stop event cancels between batches"""
     import cv2
