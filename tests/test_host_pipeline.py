@@ -197,3 +197,67 @@ def test_rank_sharding_world_size_2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count('ok') == 2
+
+
+def test_parallel_segment_encoder_orders_and_splits_segments(monkeypatch):
+    """Host logic of ParallelSegmentEncoder without a GPU: stub encoders that return their input one call late (like
+    hb_enc_encode_delayed); segments must come back complete, in submission order, whichever stream finishes first."""
+    import time
+
+    from hevc_b200 import _cabi
+    from hevc_b200 import encoder as E
+
+    class StubCtx:
+        launches = 0
+
+        def __init__(self, device):
+            pass
+
+        def close(self):
+            pass
+
+    class StubEnc:
+        count = 0
+
+        def __init__(self, ctx, params, max_batch=32):
+            self.k = StubEnc.count
+            StubEnc.count += 1
+            self.held = None
+
+        def encode_delayed(self, data, n, force_idr=False, **kw):
+            assert force_idr
+            time.sleep(0.002 * (2 - self.k))                      # stream 0 is the slow one
+            prev, self.held = self.held, (bytes(data), n)
+            return self._emit(prev)
+
+        def flush(self):
+            prev, self.held = self.held, None
+            return self._emit(prev)
+
+        @staticmethod
+        def _emit(item):
+            if item is None:
+                return b'', []
+            payload, n = item
+            per = len(payload) // n
+            return payload, [E.FrameStat(i == 0, i, 30, per) for i in range(n)]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_cabi, 'Context', StubCtx)
+    monkeypatch.setattr(E, 'B200Encoder', StubEnc)
+    pse = E.ParallelSegmentEncoder(0, None, streams=2, max_batch=4)
+    segs = [bytes([65 + i]) * (4 * (i % 3 + 1)) for i in range(7)]          # 4 frames each, different sizes
+    got, frames = b'', 0
+    for s in segs:
+        out, stats = pse.submit(s, 4)
+        got += out
+        frames += len(stats)
+    out, stats = pse.finish()
+    got += out
+    frames += len(stats)
+    pse.close()
+    assert got == b''.join(segs) and frames == 28
+    with pytest.raises(ValueError):
+        E.ParallelSegmentEncoder.submit(pse, b'', 0)
