@@ -347,8 +347,6 @@ int launch_entropy(hb_encoder *e, BatchSet &B, int first, int count, cudaEvent_t
     HB_CUDA(ctx, cudaStreamWaitEvent(q, ev, 0));
     EntropyParams ep;
     ep.g = e->g; ep.frames = B.eframes_dev + first; ep.row_cap = e->row_cap; ep.overflow = B.overflow;
-    static const bool skip_dbg = getenv("HB_DEBUG_SKIP_ENTROPY") != nullptr;      // timing experiments only: output is garbage
-    if (!skip_dbg)
     k_entropy<<<dim3((e->g.ctuh + kEntropyWarps - 1) / kEntropyWarps, count), kEntropyWarps * 32, 0, q>>>(ep);
     HB_LAUNCHED(ctx);
     return HB_OK;
