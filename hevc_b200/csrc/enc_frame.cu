@@ -16,6 +16,13 @@ __constant__ int c_luma_pack[4][5];
 __constant__ int8_t c_chroma_taps[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
                                            {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
 __device__ __forceinline__ int clampd(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// clamp to [0, hi] in one instruction (VIMNMX.RELU)
+__device__ __forceinline__ int clamp0(int v, int hi)
+{
+    int r;
+    asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(hi));
+    return r;
+}
 // sum of absolute differences of four packed bytes, accumulated: one VABSDIFF4.U8.ACC
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t acc)
 {
@@ -329,7 +336,7 @@ __device__ __forceinline__ void interp_vpass(WarpScratch &s, int ro, int fy, int
     }
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        pv[k] = clampd(acc[k] >> sh, 0, maxv);
+        pv[k] = clamp0(acc[k] >> sh, maxv);
 }
 
 __device__ __forceinline__ void interp_cols(WarpScratch &s, int ix, int iy, int fx, int fy, int bd, int lane, int (&pv)[8])
@@ -498,9 +505,11 @@ __global__ void __launch_bounds__(128, 8) k_me(const __grid_constant__ InterPara
     //      interpolation scratch, unused so far); a candidate row is three aligned words funnel-shifted to the block position.
     {
         uint32_t *win8 = reinterpret_cast<uint32_t *>(&s.tmpT[0][0]);           // [28][10] words = 28 rows x 40 bytes
-        for (int t = lane; t < 28 * 10; t += 32) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(&s.win[t / 10][(t % 10) * 4]);
+        for (int t = lane, r = (lane * 13) >> 7, c = lane - 10 * ((lane * 13) >> 7); t < 28 * 10; t += 32) {       // r = t / 10, c = t % 10
+            const uint2 v = *reinterpret_cast<const uint2 *>(&s.win[r][c * 4]);
             win8[t] = pack4_msb8(v.x, v.y, sh8);
+            c += 2; r += 3;                                                   // t += 32
+            if (c >= 10) { c -= 10; r++; }
         }
         __syncwarp();
         // lane t < 25 owns position t (raster over dy, dx): its validity and vector cost are computed once, in parallel
@@ -510,17 +519,22 @@ __global__ void __launch_bounds__(128, 8) k_me(const __grid_constant__ InterPara
             const MV cm = clamp_mv(g, x0, y0, m);
             if (cm.x == m.x && cm.y == m.y) my_cost = mv_cost(lambda8, m.x, m.y, pred.x, pred.y);
         }
+        unsigned todo = __ballot_sync(0xffffffffu, my_cost >= 0);             // valid positions, bit t = raster index
+        const uint32_t *wrow = win8 + (4 + row) * 10;                         // window row of dy = -2
+        const int colb0 = 4 + woff + c0;                                      // byte column of this lane's first sample at dx = -2
 #pragma unroll 1
-        for (int t = 0, dx = -2, dy = -2; t < 25; t++, dx = dx == 2 ? -2 : dx + 1, dy += dx == -2) {
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1;
             const int vc = __shfl_sync(0xffffffffu, my_cost, t);
-            if (vc < 0) continue;
-            const int colb = 6 + dx + woff + c0;                              // byte column of this lane's first sample
-            const uint32_t *w = win8 + (6 + dy + row) * 10 + (colb >> 2);
+            const int dyi = (t * 13) >> 6, dxi = t - 5 * dyi;                 // t / 5, t % 5 for t < 25
+            const int colb = colb0 + dxi;
+            const uint32_t *w = wrow + dyi * 10 + (colb >> 2);
             const int fs = (colb & 3) * 8;
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
             const uint32_t sad = sad4(s8hi, __funnelshift_r(w1, w2, fs), sad4(s8lo, __funnelshift_r(w0, w1, fs), 0));
             const int cost = warp_sum((int)sad) + vc;
-            if (cost < bcost) { bcost = cost; best = MV{centre.x + 4 * dx, centre.y + 4 * dy}; }
+            if (cost < bcost) { bcost = cost; best = MV{centre.x + 4 * (dxi - 2), centre.y + 4 * (dyi - 2)}; }
         }
         __syncwarp();
     }
@@ -705,7 +719,7 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            rec[i] = clampd(pr[i] + s.a[row][c0 + i], 0, maxv);
+            rec[i] = clamp0(pr[i] + s.a[row][c0 + i], maxv);
     } else {
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -762,7 +776,7 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
 #pragma unroll
         for (int t = 0; t < 4; t++)
             acc += c_chroma_taps[fyc][t] * ctmp[cpl * 88 + (crow + t) * 8 + cc0 + c];
-        cpr[c] = clampd(((acc >> 6) + off14) >> s14, 0, maxv);
+        cpr[c] = clamp0(((acc >> 6) + off14) >> s14, maxv);
         ca[cpl][crow][cc0 + c] = (int16_t)(csrc[c] - cpr[c]);
     }
     __syncwarp();
@@ -805,7 +819,7 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 4; c++)
-            cpr[c] = clampd(cpr[c] + ca[cpl][crow][cc0 + c], 0, maxv);
+            cpr[c] = clamp0(cpr[c] + ca[cpl][crow][cc0 + c], maxv);
     }
     {
         pixel *rp = (cpl ? p.rec.v : p.rec.u) + (size_t)(cy * 8 + crow) * g.recc_stride + cx * 8 + cc0;
@@ -1009,8 +1023,8 @@ __device__ void intra_cu(IntraParams &p, IntraScratch &s, int cx, int cy)
     else inv_stage<8, 10>(s.m8, &s.cb[cpl][0][0], &s.ca[cpl][0][0], cyy, cxx, 12 - (bd - 8));
     __syncthreads();
     // ---- stage 8: reconstruction, CU record, size estimate
-    if (luma) p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)clampd(pv + s.a[py][px], 0, maxv);
-    else (cpl ? p.rec.v : p.rec.u)[(size_t)(cy * 8 + cyy) * g.recc_stride + cx * 8 + cxx] = (pixel)clampd(pv + s.ca[cpl][cyy][cxx], 0, maxv);
+    if (luma) p.rec.y[(size_t)(y0 + py) * g.rec_stride + x0 + px] = (pixel)clamp0(pv + s.a[py][px], maxv);
+    else (cpl ? p.rec.v : p.rec.u)[(size_t)(cy * 8 + cyy) * g.recc_stride + cx * 8 + cxx] = (pixel)clamp0(pv + s.ca[cpl][cyy][cxx], maxv);
     if (tid < 32) {
         const int nsb = __popc(__ballot_sync(0xffffffffu, tid < 24 && s.sbflag[tid < 24 ? tid : 0] != 0));
         if (tid == 0) {
@@ -1166,10 +1180,10 @@ __device__ __forceinline__ void deblock_luma_segment(pixel *s, ptrdiff_t step, p
             int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
             if (abs(delta) < 10 * tc) {
                 delta = clampd(delta, -tc, tc);
-                l[-1 * step] = (pixel)clampd(p0 + delta, 0, maxv);
-                l[0] = (pixel)clampd(q0 - delta, 0, maxv);
-                if (dep) l[-2 * step] = (pixel)clampd(p1 + clampd((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -(tc >> 1), tc >> 1), 0, maxv);
-                if (deq) l[step] = (pixel)clampd(q1 + clampd((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -(tc >> 1), tc >> 1), 0, maxv);
+                l[-1 * step] = (pixel)clamp0(p0 + delta, maxv);
+                l[0] = (pixel)clamp0(q0 - delta, maxv);
+                if (dep) l[-2 * step] = (pixel)clamp0(p1 + clampd((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -(tc >> 1), tc >> 1), maxv);
+                if (deq) l[step] = (pixel)clamp0(q1 + clampd((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -(tc >> 1), tc >> 1), maxv);
             }
         }
     }
@@ -1203,8 +1217,8 @@ __global__ void __launch_bounds__(256) k_deblock(DeblockParams p)
                     pixel *l = u + k * line;
                     const int p0 = l[-step], p1 = l[-2 * step], q0 = l[0], q1 = l[step];
                     const int delta = clampd((((q0 - p0) << 2) + p1 - q1 + 4) >> 3, -tcc, tcc);
-                    l[-step] = (pixel)clampd(p0 + delta, 0, maxv);
-                    l[0] = (pixel)clampd(q0 - delta, 0, maxv);
+                    l[-step] = (pixel)clamp0(p0 + delta, maxv);
+                    l[0] = (pixel)clamp0(q0 - delta, maxv);
                 }
             }
         }
