@@ -690,6 +690,14 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         }
         nz |= lv[i] != 0;
     }
+    {   // a block that carries nothing but one or two isolated +-1 levels is dropped (oracle/hevc_encode.c, code_block)
+        const int nnz_y = warp_sum(e_nnz), slog_y = warp_sum(e_slog);
+        if (nnz_y > 0 && nnz_y <= 2 && slog_y == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) lv[i] = 0;
+            nz = false; e_nnz = 0; e_slog = 0; nz_lo = 0; nz_hi = 0;
+        }
+    }
     int e_nsb;
     {   // coded 4x4 sub-blocks of the 16x16 block: a sub-block is 4 rows (lanes l, l+2, l+4, l+6) x one half-row group
         const unsigned mlo = __ballot_sync(0xffffffffu, nz_lo), mhi = __ballot_sync(0xffffffffu, nz_hi);
@@ -787,15 +795,31 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
     const QuantParam qc = ctl.qc;
     int clv[4];
     bool cnz = false;
+    int c_nnz = 0, c_slog = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         clv[c] = quant_one(ca[cpl][crow][cc0 + c], qc);
         if (clv[c]) {
-            e_nnz++;
-            e_slog += 31 - __clz(abs(clv[c]));
+            c_nnz++;
+            c_slog += 31 - __clz(abs(clv[c]));
         }
         cnz |= clv[c] != 0;
     }
+    {   // per plane (half warp): a single isolated +-1 level is dropped, as in luma
+        int pn = c_nnz, ps = c_slog;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            pn += __shfl_xor_sync(0xffffffffu, pn, o);
+            ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        }
+        if (pn == 1 && ps == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) clv[c] = 0;
+            cnz = false; c_nnz = 0; c_slog = 0;
+        }
+    }
+    e_nnz += c_nnz;
+    e_slog += c_slog;
     *reinterpret_cast<uint2 *>(coef + 256 + cpl * 64 + crow * 8 + cc0) =
         make_uint2((uint32_t)(uint16_t)clv[0] | ((uint32_t)(uint16_t)clv[1] << 16), (uint32_t)(uint16_t)clv[2] | ((uint32_t)(uint16_t)clv[3] << 16));
     const unsigned cmask = __ballot_sync(0xffffffffu, cnz);

@@ -35,7 +35,7 @@ def test_decoder_matches_model_reconstruction(w, h, depth, frames, qp):
             assert dec[c].shape == ((h, w) if c == 0 else (h // 2, w // 2))
             assert (dec[c] == rec[c][:dec[c].shape[0], :dec[c].shape[1]]).all()
     assert [i.is_idr for i in infos] == [int(n % 4 == 0) for n in range(frames)]
-    assert all(i.psnr_y > (22 if qp > 30 else 30) for i in infos)
+    assert all(i.psnr_y > (21 if qp > 45 else 22 if qp > 30 else 30) for i in infos)      # sanity floor, not a quality claim
 
 
 def test_deblocking_filter_on_and_off():
