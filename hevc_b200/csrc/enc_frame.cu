@@ -805,19 +805,6 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         }
         cnz |= clv[c] != 0;
     }
-    {   // per plane (half warp): a single isolated +-1 level is dropped, as in luma
-        int pn = c_nnz, ps = c_slog;
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) {
-            pn += __shfl_xor_sync(0xffffffffu, pn, o);
-            ps += __shfl_xor_sync(0xffffffffu, ps, o);
-        }
-        if (pn == 1 && ps == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) clv[c] = 0;
-            cnz = false; c_nnz = 0; c_slog = 0;
-        }
-    }
     e_nnz += c_nnz;
     e_slog += c_slog;
     *reinterpret_cast<uint2 *>(coef + 256 + cpl * 64 + crow * 8 + cc0) =
