@@ -1014,6 +1014,17 @@ int hb_enc_encode_delayed(hb_encoder *e, const hb_frames *fr, int force_idr, uin
     return encode_common(e, fr, force_idr, out, cap, out_len, stats, frames_out, true);
 }
 
+size_t hb_escape_rbsp(const uint8_t *in, size_t n, uint8_t *out, size_t cap)
+{
+    if ((!in && n) || !out) return 0;
+    std::vector<uint8_t> buf;
+    buf.reserve(n + n / 64 + 8);
+    append_escaped(buf, in, n);
+    if (buf.size() > cap) return 0;
+    if (!buf.empty()) memcpy(out, buf.data(), buf.size());
+    return buf.size();
+}
+
 int hb_enc_mark(hb_encoder *e)
 {
     if (!e) return HB_ERR_ARG;

@@ -177,6 +177,9 @@ int hb_enc_encode_delayed(hb_encoder *enc, const hb_frames *frames, int force_id
  * device time from that mark to the end of the last completed bitstream download */
 int hb_enc_mark(hb_encoder *enc);
 int hb_enc_elapsed(hb_encoder *enc, float *ms);
+/* Host-only helper (no device needed): emulation prevention of one RBSP / sub-stream exactly as the access-unit assembly applies
+ * it (H.265 7.4.2: 0x03 before any byte <= 3 that follows two zero bytes).  Returns the escaped size, or 0 if cap is too small. */
+size_t hb_escape_rbsp(const uint8_t *in, size_t n, uint8_t *out, size_t cap);
 /* device time of the last hb_enc_encode call, measured with CUDA events on the encoder's stream:
  * total (first upload to last download) and kernels only */
 int hb_enc_last_timing(const hb_encoder *enc, float *total_ms, float *kernel_ms);

@@ -21,3 +21,38 @@ def test_no_device_means_loud_failure():
         pytest.skip('device present')
     with pytest.raises(_cabi.BackendUnavailable):
         _cabi.Context(0)
+
+
+def test_host_escape_matches_oracle():
+    """hb_escape_rbsp is pure host code (usable without a GPU): emulation prevention must equal the oracle's orc_escape on
+    random payloads rich in zero runs, on the adversarial cases, and on empty input."""
+    import ctypes as C
+
+    import numpy as np
+
+    from hevc_b200 import _cabi
+    from oracle import cmodel
+    L = _cabi.lib()
+    L.hb_escape_rbsp.restype = C.c_size_t
+    L.hb_escape_rbsp.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    O = cmodel.lib()
+    O.orc_escape.restype = C.c_size_t
+    O.orc_escape.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(5)
+    cases = [b'', b'\x00', b'\x00\x00', b'\x00\x00\x00', b'\x00\x00\x01', b'\x00\x00\x03', b'\x00\x00\x04', b'\x00\x00\x00\x00\x00\x00',
+             b'\x01\x00\x00\x02\x00\x00\x03\x00\x00', bytes(1000)]
+    for _ in range(40):
+        n = int(rng.integers(1, 5000))
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        a[rng.random(n) < 0.6] = 0                              # long zero runs
+        a[rng.random(n) < 0.1] = rng.integers(0, 4)
+        cases.append(a.tobytes())
+    for data in cases:
+        src = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b'\x00')
+        cap = 2 * len(data) + 16
+        got, want = (C.c_uint8 * cap)(), (C.c_uint8 * cap)()
+        ng = L.hb_escape_rbsp(src, len(data), got, cap)
+        nw = O.orc_escape(want, cap, src, len(data))
+        assert ng == nw and bytes(got[:ng]) == bytes(want[:nw])
+        assert b'\x00\x00\x00' not in bytes(got[:ng]) and b'\x00\x00\x01' not in bytes(got[:ng]) and b'\x00\x00\x02' not in bytes(got[:ng])
+    assert L.hb_escape_rbsp(src, len(data), got, 1) == 0       # too small: refused, nothing written past cap
