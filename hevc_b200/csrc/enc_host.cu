@@ -921,6 +921,23 @@ int hb_enc_headers(hb_encoder *e, uint8_t *out, size_t cap, size_t *len)
     return HB_OK;
 }
 
+int hb_param_sets(const hb_enc_params *params, uint8_t *out, size_t cap, size_t *len)
+{
+    if (!params || !out || !len) return HB_ERR_ARG;
+    const hb_enc_params &p = *params;
+    if (p.width < 16 || p.height < 16 || (p.width % 2) || (p.height % 2) || p.width > 8192 || p.height > 8192) return HB_ERR_ARG;
+    if (p.bit_depth != 8 && p.bit_depth != 10) return HB_ERR_ARG;
+    const int wc = (p.width + 15) & ~15, hc = (p.height + 15) & ~15;
+    std::vector<uint8_t> buf;
+    append_nal(buf, NAL_VPS, make_vps(p), true);
+    append_nal(buf, NAL_SPS, make_sps(p, wc, hc), true);
+    append_nal(buf, NAL_PPS, make_pps(p), true);
+    if (buf.size() > cap) return HB_ERR_SPACE;
+    memcpy(out, buf.data(), buf.size());
+    *len = buf.size();
+    return HB_OK;
+}
+
 int hb_enc_coded_size(const hb_encoder *e, int *wc, int *hc)
 {
     if (!e || !wc || !hc) return HB_ERR_ARG;

@@ -161,6 +161,8 @@ void hb_enc_destroy(hb_encoder *enc);
 /* VPS + SPS + PPS as Annex-B (for the hvcC box) */
 int hb_enc_headers(hb_encoder *enc, uint8_t *out, size_t cap, size_t *len);
 int hb_enc_coded_size(const hb_encoder *enc, int *coded_w, int *coded_h);
+/* The same parameter sets without an encoder or a device (pure host code): what a muxer needs before the first frame exists. */
+int hb_param_sets(const hb_enc_params *params, uint8_t *out, size_t cap, size_t *len);
 /* Encode frames->n_frames consecutive frames, continuing the stream (closed GOP of params.keyint frames;
  * force_idr restarts the GOP at the first frame: closed-GOP segment sharding).  Appends one access unit per
  * frame to out; stats (optional) receives one entry per frame.  The call returns when the bytes are in out. */

@@ -1,6 +1,8 @@
 """The C-ABI library builds for sm_100a, loads, and exports every symbol include/hevc_b200.h declares."""
 import ctypes
 
+import pytest
+
 from hevc_b200 import _cabi
 
 
@@ -56,3 +58,32 @@ def test_host_escape_matches_oracle():
         assert ng == nw and bytes(got[:ng]) == bytes(want[:nw])
         assert b'\x00\x00\x00' not in bytes(got[:ng]) and b'\x00\x00\x01' not in bytes(got[:ng]) and b'\x00\x00\x02' not in bytes(got[:ng])
     assert L.hb_escape_rbsp(src, len(data), got, 1) == 0       # too small: refused, nothing written past cap
+
+
+@pytest.mark.parametrize('w,h,depth,hdr', [(1920, 1080, 8, False), (3840, 2160, 10, True), (200, 120, 10, True), (64, 64, 8, False)])
+def test_host_parameter_sets_match_oracle(w, h, depth, hdr):
+    """hb_param_sets (pure host code, no device): VPS + SPS + PPS must equal the CPU model's headers byte for byte and parse
+    back to the requested geometry."""
+    import ctypes as C
+
+    from hevc_b200 import _cabi, compliance
+    from hevc_b200 import encoder as E
+    from hevc_b200.mp4 import split_nals
+    from oracle import encoder_model as em
+    from tests import enc_common as ec
+    p = ec.b200_params(w, h, depth, keyint=60, hdr10=hdr)
+    cp = E.to_c_params(p, qp=(24, 26), hash_sei=False)
+    L = _cabi.lib()
+    L.hb_param_sets.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    buf, n = (C.c_uint8 * 1024)(), C.c_size_t()
+    assert L.hb_param_sets(C.byref(cp), buf, 1024, C.byref(n)) == 0
+    got = bytes(buf[:n.value])
+    model = em.ModelEncoder(ec.model_params(p, 24, 26, False))
+    want = model.headers()
+    model.close()
+    assert got == want
+    nals = split_nals(got)
+    assert [(x[0] >> 1) & 0x3f for x in nals] == [32, 33, 34]
+    sps = compliance.parse_sps(nals[1])
+    assert (sps['width'], sps['height'], sps['bit_depth']) == (w, h, depth)
+    assert L.hb_param_sets(C.byref(cp), buf, 8, C.byref(n)) != 0          # too small
