@@ -938,6 +938,23 @@ int hb_param_sets(const hb_enc_params *params, uint8_t *out, size_t cap, size_t 
     return HB_OK;
 }
 
+int hb_rc_simulate(const hb_enc_params *params, const long long *est16, const int *is_idr, int n, int *qps)
+{
+    if (!params || !est16 || !is_idr || !qps || n < 0) return HB_ERR_ARG;
+    const hb_enc_params &p = *params;
+    if (p.fps_num <= 0 || p.fps_den <= 0) return HB_ERR_ARG;
+    RcState rc{};                     // exactly the state hb_enc_create uploads, stepped by the functions the device kernels run
+    rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
+    rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
+    rc.fullness = rc.b16 * 9 / 10;
+    rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
+    for (int i = 0; i < n; i++) {
+        qps[i] = rc_pick_qp(rc, is_idr[i] != 0);
+        rc_update(rc, is_idr[i] != 0, qps[i], est16[i]);
+    }
+    return HB_OK;
+}
+
 int hb_enc_coded_size(const hb_encoder *e, int *wc, int *hc)
 {
     if (!e || !wc || !hc) return HB_ERR_ARG;

@@ -163,6 +163,9 @@ int hb_enc_headers(hb_encoder *enc, uint8_t *out, size_t cap, size_t *len);
 int hb_enc_coded_size(const hb_encoder *enc, int *coded_w, int *coded_h);
 /* The same parameter sets without an encoder or a device (pure host code): what a muxer needs before the first frame exists. */
 int hb_param_sets(const hb_enc_params *params, uint8_t *out, size_t cap, size_t *len);
+/* Rate controller on the host (pure host code, the same functions the device kernels k_rc_step run): QP of each of n frames
+ * given their types and size estimates in 1/16 bit.  Test hook: lets the controller be checked against the oracle without a GPU. */
+int hb_rc_simulate(const hb_enc_params *params, const long long *est16, const int *is_idr, int n, int *qps);
 /* Encode frames->n_frames consecutive frames, continuing the stream (closed GOP of params.keyint frames;
  * force_idr restarts the GOP at the first frame: closed-GOP segment sharding).  Appends one access unit per
  * frame to out; stats (optional) receives one entry per frame.  The call returns when the bytes are in out. */

@@ -87,3 +87,48 @@ def test_host_parameter_sets_match_oracle(w, h, depth, hdr):
     sps = compliance.parse_sps(nals[1])
     assert (sps['width'], sps['height'], sps['bit_depth']) == (w, h, depth)
     assert L.hb_param_sets(C.byref(cp), buf, 8, C.byref(n)) != 0          # too small
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_host_rate_controller_matches_oracle(seed):
+    """hb_rc_simulate steps the controller the device kernels run (csrc/enc_dev.cuh) on the host; against oracle/hevc_rc.c on
+    random size-estimate sequences (overshoots, starvation, key frames) the chosen QPs must be identical."""
+    import ctypes as C
+
+    import numpy as np
+
+    from hevc_b200 import _cabi
+    from hevc_b200 import encoder as E
+    from oracle import cmodel
+    from oracle import encoder_model as em
+    from tests import enc_common as ec
+    rng = np.random.default_rng(seed)
+    p = ec.b200_params(1920, 1080, 8 + 2 * (seed & 1), keyint=30)
+    p.vbv_maxrate_kbps, p.vbv_bufsize_kbit = int(rng.integers(500, 30000)), int(rng.integers(600, 40000))
+    qp = (int(rng.integers(10, 30)), int(rng.integers(12, 34)))
+    cp = E.to_c_params(p, qp=qp, hash_sei=False, rate_control=True)
+    n = 400
+    is_idr = (np.arange(n) % 30 == 0).astype(np.int32)
+    t16 = p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den // p.fps_num
+    est = (t16 * rng.lognormal(0.0, 1.2, n) * np.where(is_idr, 6.0, 1.0)).astype(np.int64)
+    qps = np.zeros(n, np.int32)
+    L = _cabi.lib()
+    L.hb_rc_simulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    assert L.hb_rc_simulate(C.byref(cp), est.ctypes.data, is_idr.ctypes.data, n, qps.ctypes.data) == 0
+    O = cmodel.lib()
+    mp = ec.model_params(p, qp[0], qp[1], False, rate_control=True)
+
+    class OrcRc(C.Structure):
+        _fields_ = [('t16', C.c_longlong), ('b16', C.c_longlong), ('fullness', C.c_longlong), ('have', C.c_int * 2), ('qp_prev', C.c_int * 2),
+                    ('est_prev', C.c_longlong * 2)]
+    rc = OrcRc()
+    O.orc_rc_init(C.byref(rc), C.byref(mp))
+    O.orc_rc_pick_qp.restype = C.c_int
+    O.orc_rc_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong]
+    want = []
+    for i in range(n):
+        q = O.orc_rc_pick_qp(C.byref(rc), C.byref(mp), int(is_idr[i]))
+        want.append(q)
+        O.orc_rc_update(C.byref(rc), int(is_idr[i]), q, int(est[i]))
+    assert qps.tolist() == want
+    assert max(want) > min(want)                 # the sequences really exercise the controller
