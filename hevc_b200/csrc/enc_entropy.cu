@@ -778,6 +778,9 @@ __global__ void __launch_bounds__(128) k_pack_copy(PackParams p)
     const int i = blockIdx.x, f = i / p.rows, r = i % p.rows;
     const uint8_t *src = p.frames[f].out + (size_t)r * p.row_cap;
     const uint32_t n = p.frames[f].row_len[r];
+    // a group whose sub-streams exceed the space reserved for it (or a row that overran its own buffer) is not copied: the
+    // host sees offsets[total] > cap / the overflow flag and fails the call, and nothing is written outside the group's region
+    if (n > p.row_cap || (unsigned long long)p.offsets[i] + n > p.cap) return;
     uint8_t *dst = p.packed + p.offsets[i];
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
 }

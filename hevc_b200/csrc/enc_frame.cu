@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) k_ingest(IngestParams p)
                 const int xx = min(4 * bx + i, p.w - 1);
                 uint32_t v;
                 if (p.fmt == HB_FMT_YUV420P8) v = (uint32_t)row[xx] << p.up_shift;
-                else v = (uint32_t)reinterpret_cast<const uint16_t *>(row)[xx] >> p.down_shift;
+                else v = min((((uint32_t)reinterpret_cast<const uint16_t *>(row)[xx] + p.round_add) >> p.down_shift) << p.up_shift, (uint32_t)p.maxv);
                 px[i] = v;
                 acc += v;
             }
@@ -81,12 +81,48 @@ __global__ void __launch_bounds__(256) k_ingest(IngestParams p)
                     uu[i] = (uint32_t)r[2 * xx] >> p.down_shift;
                     vv[i] = (uint32_t)r[2 * xx + 1] >> p.down_shift;
                 } else {
-                    uu[i] = (uint32_t)reinterpret_cast<const uint16_t *>(p.in_u + (size_t)yy * p.in_us)[xx] >> p.down_shift;
-                    vv[i] = (uint32_t)reinterpret_cast<const uint16_t *>(p.in_v + (size_t)yy * p.in_vs)[xx] >> p.down_shift;
+                    uu[i] = min((((uint32_t)reinterpret_cast<const uint16_t *>(p.in_u + (size_t)yy * p.in_us)[xx] + p.round_add) >> p.down_shift) << p.up_shift, (uint32_t)p.maxv);
+                    vv[i] = min((((uint32_t)reinterpret_cast<const uint16_t *>(p.in_v + (size_t)yy * p.in_vs)[xx] + p.round_add) >> p.down_shift) << p.up_shift, (uint32_t)p.maxv);
                 }
             }
             *reinterpret_cast<uint32_t *>(p.src.u + (size_t)(2 * by + j) * g.srcc_stride + 2 * bx) = uu[0] | (uu[1] << 16);
             *reinterpret_cast<uint32_t *>(p.src.v + (size_t)(2 * by + j) * g.srcc_stride + 2 * bx) = vv[0] | (vv[1] << 16);
+        }
+    }
+}
+
+// After a fused scale / colour-conversion ingest (pixel.cu) wrote the display area of the source planes: replicate the last
+// row / column into the coded-size padding and build the quarter-resolution plane.  One thread per 4x4 luma block; reads
+// touch only the display area, writes only the padding, so there is no ordering between threads.
+__global__ void __launch_bounds__(256) k_pad_ds(Geom g, Planes src, int w, int h, uint8_t *ds)
+{
+    const int total = g.dsw * g.dsh, cw = w >> 1, ch = h >> 1;
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < total; blk += gridDim.x * blockDim.x) {
+        const int bx = blk % g.dsw, by = blk / g.dsw;
+        int acc = 8;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int y = 4 * by + j, yy = min(y, h - 1);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int x = 4 * bx + i, xx = min(x, w - 1);
+                const pixel v = src.y[(size_t)yy * g.src_stride + xx];
+                acc += v;
+                if (y != yy || x != xx) src.y[(size_t)y * g.src_stride + x] = v;
+            }
+        }
+        ds[(size_t)by * g.dsw + bx] = (uint8_t)((acc >> 4) >> (g.bit_depth - 8));
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int y = 2 * by + j, yy = min(y, ch - 1);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int x = 2 * bx + i, xx = min(x, cw - 1);
+                if (y != yy || x != xx) {
+                    src.u[(size_t)y * g.srcc_stride + x] = src.u[(size_t)yy * g.srcc_stride + xx];
+                    src.v[(size_t)y * g.srcc_stride + x] = src.v[(size_t)yy * g.srcc_stride + xx];
+                }
+            }
         }
     }
 }

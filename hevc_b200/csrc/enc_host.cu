@@ -282,6 +282,8 @@ struct hb_encoder {
     uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
     int *satdf[2] = {nullptr, nullptr};
     size_t staging_bytes = 0;
+    uint8_t *csc_tmp = nullptr;       // 8-bit 4:2:0 scratch frame of the scaled-RGB ingest path
+    size_t csc_tmp_bytes = 0;
     int *progress = nullptr;
     RcState *rc_dev = nullptr;
     bool rc_have_idr = false;
@@ -352,9 +354,11 @@ int launch_entropy(hb_encoder *e, BatchSet &B, int first, int count, cudaEvent_t
     return HB_OK;
 }
 
-size_t input_frame_bytes(const hb_enc_params &p, int fmt)
+size_t input_frame_bytes(const hb_enc_params &p, int fmt, int sw = 0, int sh = 0)
 {
-    const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
+    const int w = sw > 0 ? sw : p.width, h = sh > 0 ? sh : p.height;
+    const size_t luma = (size_t)w * h, chroma = (size_t)(w / 2) * (h / 2);
+    if (fmt == HB_PIX_BGR24 || fmt == HB_PIX_RGB24) return 3 * luma;
     return fmt == HB_PIX_YUV420P8 ? luma + 2 * chroma : 2 * (luma + 2 * chroma);
 }
 
@@ -366,7 +370,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
     hb_ctx *ctx = e->ctx;
     const hb_enc_params &p = e->prm;
     const Geom &g = e->g;
-    const size_t fbytes = input_frame_bytes(p, fr->format);
+    const size_t fbytes = input_frame_bytes(p, fr->format, fr->src_width, fr->src_height);
     cudaStream_t st = ctx->stream;
     const int ncu = g.cuw * g.cuh, nctu = g.ctuw * g.ctuh;
     const size_t ds_stride = (size_t)g.dsw * g.dsh;
@@ -440,9 +444,50 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 HB_CUDA(ctx, cudaEventRecord(B.ev[1], st));
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[kb + 0], st));
             }
-            for (int i = 0; i < cn; i++) {
+            const bool scaled = fr->src_width > 0 && (fr->src_width != p.width || fr->src_height != p.height);
+            const bool packed_rgb = fr->format == HB_PIX_BGR24 || fr->format == HB_PIX_RGB24;
+            for (int i = 0; i < cn && (scaled || packed_rgb); i++) {
+                // fused pre-encode pixel pipeline: the scaler / colour conversion writes the encoder's source planes directly
+                const uint8_t *f = dev_in + (size_t)i * dev_fb;
+                const Planes &sp = B.slot[c0 + i].src;
+                int m = fr->matrix;
+                if (!m) m = p.matrix_coeffs == 9 ? HB_MATRIX_BT2020 : (p.matrix_coeffs == 5 || p.matrix_coeffs == 6) ? HB_MATRIX_BT601 : HB_MATRIX_BT709;
+                if (packed_rgb && scaled) {
+                    // colour conversion at the source size into an 8-bit 4:2:0 scratch frame, then the scaler (frames are serial on
+                    // this stream, so one scratch frame is enough)
+                    const int sw = fr->src_width, sh = fr->src_height;
+                    const size_t need = (size_t)sw * sh * 3 / 2;
+                    if (e->csc_tmp_bytes < need) {
+                        uint8_t *t = nullptr;
+                        HB_TRY(dev_alloc(e, &t, need));
+                        e->csc_tmp = t; e->csc_tmp_bytes = need;
+                    }
+                    uint8_t *ty = e->csc_tmp, *tu = ty + (size_t)sw * sh, *tv = tu + (size_t)(sw / 2) * (sh / 2);
+                    HB_TRY(hb_rgb_to_yuv420(ctx, (hb_devptr)(uintptr_t)f, 3 * sw, fr->format == HB_PIX_BGR24 ? HB_BGR : HB_RGB, m, 8, sw, sh,
+                                            (hb_devptr)(uintptr_t)ty, sw, (hb_devptr)(uintptr_t)tu, sw / 2, (hb_devptr)(uintptr_t)tv, sw / 2));
+                    HB_TRY(launch_scale8(ctx, ty, nullptr, sw, sw, sh, reinterpret_cast<uint8_t *>(sp.y), nullptr, g.src_stride * 2, p.width, p.height,
+                                         p.bit_depth, 0, 1));
+                    HB_TRY(launch_scale8(ctx, tu, tv, sw / 2, sw / 2, sh / 2, reinterpret_cast<uint8_t *>(sp.u), reinterpret_cast<uint8_t *>(sp.v),
+                                         g.srcc_stride * 2, p.width / 2, p.height / 2, p.bit_depth, 0, 1));
+                } else if (packed_rgb) {
+                    HB_TRY(launch_rgb_planar16(ctx, f, 3 * p.width, fr->format == HB_PIX_BGR24, m, p.bit_depth, p.width, p.height,
+                                               reinterpret_cast<uint8_t *>(sp.y), g.src_stride * 2, reinterpret_cast<uint8_t *>(sp.u),
+                                               reinterpret_cast<uint8_t *>(sp.v), g.srcc_stride * 2));
+                } else {
+                    const int sw = fr->src_width, sh = fr->src_height;
+                    const uint8_t *fu = f + (size_t)sw * sh, *fv = fu + (size_t)(sw / 2) * (sh / 2);
+                    HB_TRY(launch_scale8(ctx, f, nullptr, sw, sw, sh, reinterpret_cast<uint8_t *>(sp.y), nullptr, g.src_stride * 2, p.width, p.height,
+                                         p.bit_depth, 0, 1));
+                    HB_TRY(launch_scale8(ctx, fu, fv, sw / 2, sw / 2, sh / 2, reinterpret_cast<uint8_t *>(sp.u), reinterpret_cast<uint8_t *>(sp.v),
+                                         g.srcc_stride * 2, p.width / 2, p.height / 2, p.bit_depth, 0, 1));
+                }
+                k_pad_ds<<<hb_grid_for(ctx, (long long)g.dsw * g.dsh, 256, 8), 256, 0, st>>>(g, sp, p.width, p.height,
+                                                                                           e->ds + (size_t)(c0 + i + 1) * ds_stride);
+                HB_LAUNCHED(ctx);
+            }
+            for (int i = 0; i < cn && !(scaled || packed_rgb); i++) {
                 IngestParams ip;
-                ip.g = g;
+                ip.g = g; ip.round_add = 0; ip.maxv = (1 << p.bit_depth) - 1;
                 const uint8_t *f = dev_in + (size_t)i * dev_fb;
                 const size_t luma = (size_t)p.width * p.height, chroma = (size_t)(p.width / 2) * (p.height / 2);
                 if (fr->format == HB_PIX_YUV420P8) {
@@ -456,7 +501,10 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 } else {
                     ip.in_y = f; ip.in_u = f + 2 * luma; ip.in_v = f + 2 * luma + 2 * chroma;
                     ip.in_ys = 2 * p.width; ip.in_us = ip.in_vs = p.width;
-                    ip.up_shift = 0; ip.down_shift = 0;
+                    const int sd = fr->src_bit_depth ? fr->src_bit_depth : p.bit_depth;
+                    ip.up_shift = sd < p.bit_depth ? p.bit_depth - sd : 0;
+                    ip.down_shift = sd > p.bit_depth ? sd - p.bit_depth : 0;
+                    ip.round_add = ip.down_shift ? 1 << (ip.down_shift - 1) : 0;
                 }
                 ip.fmt = fr->format; ip.w = p.width; ip.h = p.height;
                 ip.src = B.slot[c0 + i].src;
@@ -564,7 +612,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 }
                 PackParams pp;
                 pp.frames = B.eframes_dev + f0; pp.n_frames = cnt; pp.rows = g.ctuh; pp.row_cap = e->row_cap;
-                pp.packed = B.packed_dev + (size_t)f0 * e->frame_cap; pp.offsets = B.offsets_dev + (size_t)f0 * g.ctuh + grp;
+                pp.packed = B.packed_dev + (size_t)f0 * e->frame_cap; pp.cap = (unsigned long long)cnt * e->frame_cap; pp.offsets = B.offsets_dev + (size_t)f0 * g.ctuh + grp;
                 k_pack_scan<<<1, 1024, 0, e->st_drain>>>(pp);
                 HB_LAUNCHED(ctx);
                 k_pack_copy<<<cnt * g.ctuh, 128, 0, e->st_drain>>>(pp);
@@ -669,6 +717,9 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
                 append_nal(au, NAL_PPS, e->pps, true);
             }
             if (p.hrd) {
+                // au_cpb_removal_delay counts from the most recent buffering period in a PRECEDING access unit (D.3.2), so an
+                // access unit that carries a buffering period itself still reports its distance to the previous one
+                const int delay = e->since_bp;
                 if (idr) {
                     BitWriter m;
                     const uint32_t delay = (uint32_t)((long long)90000 * 9 * p.vbv_bufsize_kbit / ((long long)10 * p.vbv_maxrate_kbps));
@@ -678,7 +729,7 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
                     e->since_bp = 0;
                 }
                 BitWriter m;
-                m.put((uint32_t)(e->since_bp > 0 ? e->since_bp - 1 : 0), 24); m.put(0, 24);
+                m.put((uint32_t)(delay > 0 ? delay - 1 : 0), 24); m.put(0, 24);
                 append_nal(au, NAL_SEI_PREFIX, make_sei(1, m.bytes()), false);
                 e->since_bp++;
             }
@@ -993,8 +1044,13 @@ int encode_common(hb_encoder *e, const hb_frames *fr, int force_idr, uint8_t *ou
     HB_ARG(ctx, delayed || fr);
     if (fr) {
         HB_ARG(ctx, fr->data && fr->n_frames >= 0);
-        HB_ARG(ctx, fr->format == HB_PIX_YUV420P8 || fr->format == HB_PIX_P010 || fr->format == HB_PIX_YUV420P16);
-        HB_ARG(ctx, fr->frame_bytes >= input_frame_bytes(e->prm, fr->format));
+        HB_ARG(ctx, fr->format >= HB_PIX_YUV420P8 && fr->format <= HB_PIX_RGB24);
+        HB_ARG(ctx, (fr->src_width == 0 && fr->src_height == 0) ||
+                        (fr->src_width == e->prm.width && fr->src_height == e->prm.height) ||
+                        ((fr->format == HB_PIX_YUV420P8 || fr->format == HB_PIX_BGR24 || fr->format == HB_PIX_RGB24) && fr->src_width >= 16 && fr->src_height >= 16 && !(fr->src_width & 1) && !(fr->src_height & 1)));
+        HB_ARG(ctx, fr->frame_bytes >= input_frame_bytes(e->prm, fr->format, fr->src_width, fr->src_height));
+        HB_ARG(ctx, input_frame_bytes(e->prm, fr->format, fr->src_width, fr->src_height) <= e->staging_bytes / e->max_batch);
+        HB_ARG(ctx, fr->src_bit_depth == 0 || (fr->format == HB_PIX_YUV420P16 && fr->src_bit_depth >= 8 && fr->src_bit_depth <= 16));
     }
     // the synchronous call sizes its output for its own frames: frames still in flight from the pipelined entry point must be
     // flushed first

@@ -4,7 +4,9 @@
 #include <cstddef>
 #include "enc_dev.cuh"
 
-enum { HB_FMT_YUV420P8 = 0, HB_FMT_P010 = 1, HB_FMT_YUV420P16 = 2 };
+struct hb_ctx;
+
+enum { HB_FMT_YUV420P8 = 0, HB_FMT_P010 = 1, HB_FMT_YUV420P16 = 2, HB_FMT_BGR24 = 3, HB_FMT_RGB24 = 4 };
 
 namespace hb {
 
@@ -14,6 +16,7 @@ struct IngestParams {
     int in_ys, in_us, in_vs;             // bytes
     int fmt, w, h;                       // display size
     int up_shift, down_shift;
+    int round_add, maxv;                 // added before the down shift (16-bit planar sources deeper than the encoder), sample clamp
     Planes src;
     uint8_t *ds;                         // quarter-resolution plane, 8 most significant bits
 };
@@ -90,6 +93,7 @@ struct PackParams {
     uint32_t row_cap;
     uint8_t *packed;                     // contiguous: frame 0 rows, frame 1 rows, ...
     uint32_t *offsets;                   // [n_frames * rows + 1] exclusive prefix of row lengths
+    unsigned long long cap;              // bytes reserved at `packed` for this group
 };
 
 constexpr int kEntropyWarps = 4;
@@ -129,6 +133,7 @@ static_assert(sizeof(EntropyWarpScratch) % 16 == 0, "per-warp scratch must keep 
 cudaError_t upload_inter_constants(cudaStream_t st);
 
 __global__ void k_ingest(IngestParams p);
+__global__ void k_pad_ds(Geom g, Planes src, int w, int h, uint8_t *ds);
 __global__ void k_border(Planes rec, Geom g);
 __global__ void k_coarse(CoarseParams p);
 __global__ void k_me(const __grid_constant__ InterParams p);
@@ -143,5 +148,12 @@ __global__ void k_rc_redo(RcState *rc, FrameCtl *ctl);
 __global__ void k_entropy(EntropyParams p);
 __global__ void k_pack_scan(PackParams p);
 __global__ void k_pack_copy(PackParams p);
+
+
+// pixel.cu: pre-encode pixel pipeline launchers the ingest stage uses (run on ctx->stream)
+int launch_scale8(hb_ctx *ctx, const uint8_t *s0, const uint8_t *s1, int ss, int sw, int sh, uint8_t *d0, uint8_t *d1, int ds, int dw, int dh,
+                  int out_depth, int out_shift, int out_mode);
+int launch_rgb_planar16(hb_ctx *ctx, const uint8_t *rgb, int rs, int bgr, int matrix, int depth, int w, int h, uint8_t *dy, int dys, uint8_t *du,
+                        uint8_t *dv, int dcs);
 
 }  // namespace hb

@@ -73,7 +73,8 @@ struct CscCoef {
 };
 
 // work item = 16 pixels x 2 rows
-template <int DEPTH>
+// PLANAR16: 16-bit planar output at DEPTH bits, samples LSB-aligned, separate U and V planes (the stream encoder's source planes)
+template <int DEPTH, bool PLANAR16 = false>
 __global__ void __launch_bounds__(128) k_rgb_to_yuv420(const uint8_t *__restrict__ rgb, int rs, int bgr, CscCoef c, int w, int h,
                                                        uint8_t *__restrict__ dy, int dys, uint8_t *__restrict__ du, int dus,
                                                        uint8_t *__restrict__ dv, int dvs, int aligned)
@@ -134,7 +135,38 @@ __global__ void __launch_bounds__(128) k_rgb_to_yuv420(const uint8_t *__restrict
             cr[q] = min(max(r, 0), c.maxv);
         }
         const int crow = row >> 1, cx = x >> 1;
-        if (DEPTH == 8) {
+        if (PLANAR16) {
+            if (aligned && n == 16) {
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; hlf++) {
+                        uint4 o;
+                        uint32_t *ow = &o.x;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            ow[k] = (uint32_t)yv[r][8 * hlf + 2 * k] | ((uint32_t)yv[r][8 * hlf + 2 * k + 1] << 16);
+                        *reinterpret_cast<uint4 *>(dy + (size_t)(row + r) * dys + 2 * x + 16 * hlf) = o;
+                    }
+                uint4 ob, orr;
+                uint32_t *pb = &ob.x, *pr = &orr.x;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    pb[k] = (uint32_t)cb[2 * k] | ((uint32_t)cb[2 * k + 1] << 16);
+                    pr[k] = (uint32_t)cr[2 * k] | ((uint32_t)cr[2 * k + 1] << 16);
+                }
+                *reinterpret_cast<uint4 *>(du + (size_t)crow * dus + 2 * cx) = ob;
+                *reinterpret_cast<uint4 *>(dv + (size_t)crow * dvs + 2 * cx) = orr;
+            } else {
+                for (int r = 0; r < 2; r++)
+                    for (int k = 0; k < n; k++)
+                        reinterpret_cast<uint16_t *>(dy + (size_t)(row + r) * dys)[x + k] = (uint16_t)yv[r][k];
+                for (int q = 0; q < n / 2; q++) {
+                    reinterpret_cast<uint16_t *>(du + (size_t)crow * dus)[cx + q] = (uint16_t)cb[q];
+                    reinterpret_cast<uint16_t *>(dv + (size_t)crow * dvs)[cx + q] = (uint16_t)cr[q];
+                }
+            }
+        } else if (DEPTH == 8) {
             if (aligned && n == 16) {
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
@@ -314,6 +346,169 @@ __global__ void __launch_bounds__(256) k_scale(const uint8_t *__restrict__ s0, c
     }
 }
 
+
+// ---- vectorised scaler: one CTA = one 128x16 output tile, one thread = 8 consecutive output samples of one row
+// (one 128-bit store per plane for 16-bit output).  Same arithmetic as k_scale above (oracle/pixel_ref.py scale_plane).
+//   OUT 0: 8-bit planar, OUT 1: 16-bit planar (PLANES == 2: two destination planes), OUT 2: 16-bit interleaved pairs (P010 UV)
+constexpr int S2_TW = 128, S2_TH = 16, S2_FW = 272, S2_FH = 40;
+template <int PLANES, int OUT>
+__global__ void __launch_bounds__(256) k_scale8(const uint8_t *__restrict__ s0, const uint8_t *__restrict__ s1, int ss, int sw, int sh,
+                                                uint8_t *__restrict__ d0, uint8_t *__restrict__ d1, int ds, int dw, int dh,
+                                                const int2 *__restrict__ xtab, const int2 *__restrict__ ytab, int out_depth, int out_shift,
+                                                int aligned)
+{
+    __shared__ __align__(16) uint8_t foot[PLANES][S2_FH][S2_FW];
+    __shared__ __align__(16) short hp[PLANES][S2_FH][S2_TW];
+    __shared__ short xtap[S2_TW][4], ytap[S2_TH][4];
+    __shared__ int xfirst[S2_TW], yfirst[S2_TH];
+    const int tiles_x = (dw + S2_TW - 1) / S2_TW;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int ox0 = (tile % tiles_x) * S2_TW, oy0 = (tile / tiles_x) * S2_TH;
+    const int tw = min(S2_TW, dw - ox0), th = min(S2_TH, dh - oy0);
+    const int fx0 = xtab[ox0].x, fx1 = xtab[ox0 + tw - 1].x + 3;
+    const int fy0 = ytab[oy0].x, fy1 = ytab[oy0 + th - 1].x + 3;
+    const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;
+    const int shift = 20 - (out_depth - 8), maxv = (1 << out_depth) - 1;
+    const int fxa = fx0 & ~3, fskew = fx0 - fxa, nw = (fskew + fw + 3) >> 2;
+    const bool staged = 4 * nw <= S2_FW && fh <= S2_FH;
+    if (tid < tw) {
+        const int2 xp = xtab[ox0 + tid];
+        xfirst[tid] = xp.x;
+#pragma unroll
+        for (int t = 0; t < 4; t++) xtap[tid][t] = c_bicubic[xp.y][t];
+    } else if (tid >= 128 && tid < 128 + th) {
+        const int2 yp = ytab[oy0 + tid - 128];
+        yfirst[tid - 128] = yp.x;
+#pragma unroll
+        for (int t = 0; t < 4; t++) ytap[tid - 128][t] = c_bicubic[yp.y][t];
+    }
+    if (!staged) {          // extreme down-scale ratios: every output straight from global memory
+        for (int i = tid; i < S2_TW * S2_TH; i += 256) {
+            const int oy = i >> 7, ox = i & (S2_TW - 1);
+            if (ox >= tw || oy >= th) continue;
+            const int2 yp = ytab[oy0 + oy], xp = xtab[ox0 + ox];
+            int outv[PLANES];
+#pragma unroll
+            for (int p = 0; p < PLANES; p++) {
+                const uint8_t *sp = p ? s1 : s0;
+                int acc = 1 << (shift - 1);
+                for (int t = 0; t < 4; t++) {
+                    const int sy = min(max(yp.x + t, 0), sh - 1);
+                    int hacc = 128;
+                    for (int k = 0; k < 4; k++) hacc += c_bicubic[xp.y][k] * sp[(size_t)sy * ss + min(max(xp.x + k, 0), sw - 1)];
+                    acc += c_bicubic[yp.y][t] * (short)(hacc >> 8);
+                }
+                outv[p] = min(max(acc >> shift, 0), maxv);
+            }
+            const int X = ox0 + ox;
+            const size_t ro = (size_t)(oy0 + oy) * ds;
+            if (OUT == 0) d0[ro + X] = (uint8_t)outv[0];
+            else if (OUT == 2) reinterpret_cast<uint32_t *>(d0 + ro)[X] = (uint32_t)(outv[0] << out_shift) | ((uint32_t)(outv[PLANES - 1] << out_shift) << 16);
+            else {
+                reinterpret_cast<uint16_t *>(d0 + ro)[X] = (uint16_t)(outv[0] << out_shift);
+                if (PLANES == 2) reinterpret_cast<uint16_t *>(d1 + ro)[X] = (uint16_t)(outv[PLANES - 1] << out_shift);
+            }
+        }
+        return;
+    }
+    // footprint: interior tiles copy aligned 32-bit words, picture-edge tiles clamp sample by sample
+    const bool words = fxa >= 0 && fxa + 4 * nw <= sw && fy0 >= 0 && fy1 < sh && (ss & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(s0) | (PLANES == 2 ? reinterpret_cast<uintptr_t>(s1) : 0)) & 3) == 0;
+    const int skew = words ? fskew : 0;
+    if (words) {
+        for (int i = tid; i < fh * nw; i += 256) {
+            const int r = i / nw, wi = i - r * nw;
+            const size_t off = (size_t)(fy0 + r) * ss + fxa + 4 * wi;
+            reinterpret_cast<uint32_t *>(&foot[0][r][0])[wi] = __ldg(reinterpret_cast<const uint32_t *>(s0 + off));
+            if (PLANES == 2) reinterpret_cast<uint32_t *>(&foot[PLANES - 1][r][0])[wi] = __ldg(reinterpret_cast<const uint32_t *>(s1 + off));
+        }
+    } else {
+        for (int r = tid >> 5; r < fh; r += 8) {
+            const int sy = min(max(fy0 + r, 0), sh - 1);
+            for (int cidx = tid & 31; cidx < fw; cidx += 32) {
+                const int sx = min(max(fx0 + cidx, 0), sw - 1);
+                foot[0][r][cidx] = s0[(size_t)sy * ss + sx];
+                if (PLANES == 2) foot[PLANES - 1][r][cidx] = s1[(size_t)sy * ss + sx];
+            }
+        }
+    }
+    __syncthreads();
+    {   // horizontal pass: a thread keeps one output column, its taps and source offset live in registers
+        const int ox = tid & (S2_TW - 1);
+        if (ox < tw) {
+            const int base = xfirst[ox] - fx0 + skew;
+            const int t0 = xtap[ox][0], t1 = xtap[ox][1], t2 = xtap[ox][2], t3 = xtap[ox][3];
+            for (int r = tid >> 7; r < fh; r += 2) {
+#pragma unroll
+                for (int p = 0; p < PLANES; p++) {
+                    const uint8_t *f = &foot[p][r][base];
+                    hp[p][r][ox] = (short)((128 + t0 * f[0] + t1 * f[1] + t2 * f[2] + t3 * f[3]) >> 8);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // vertical pass: 8 consecutive columns of one output row per thread
+    const int oy = tid >> 4, xg = (tid & 15) * 8;
+    if (oy >= th || xg >= tw) return;
+    const int base = yfirst[oy] - fy0;
+    int outv[PLANES][8];
+#pragma unroll
+    for (int p = 0; p < PLANES; p++) {
+        int acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 1 << (shift - 1);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int yt = ytap[oy][t];
+            const uint4 v = *reinterpret_cast<const uint4 *>(&hp[p][base + t][xg]);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                acc[2 * k] += yt * (short)(w[k] & 0xffff);
+                acc[2 * k + 1] += yt * (short)(w[k] >> 16);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) outv[p][k] = min(max(acc[k] >> shift, 0), maxv) << out_shift;
+    }
+    const int X = ox0 + xg, nvalid = min(8, tw - xg);
+    const size_t ro = (size_t)(oy0 + oy) * ds;
+    if (aligned && nvalid == 8) {
+        if (OUT == 0) {
+            uint2 o;
+            o.x = outv[0][0] | (outv[0][1] << 8) | (outv[0][2] << 16) | (outv[0][3] << 24);
+            o.y = outv[0][4] | (outv[0][5] << 8) | (outv[0][6] << 16) | (outv[0][7] << 24);
+            *reinterpret_cast<uint2 *>(d0 + ro + X) = o;
+        } else if (OUT == 1) {
+#pragma unroll
+            for (int p = 0; p < PLANES; p++) {
+                uint4 o;
+                o.x = outv[p][0] | (outv[p][1] << 16); o.y = outv[p][2] | (outv[p][3] << 16);
+                o.z = outv[p][4] | (outv[p][5] << 16); o.w = outv[p][6] | (outv[p][7] << 16);
+                *reinterpret_cast<uint4 *>((p ? d1 : d0) + ro + 2 * X) = o;
+            }
+        } else {
+            uint4 a, b;
+            a.x = outv[0][0] | (outv[PLANES - 1][0] << 16); a.y = outv[0][1] | (outv[PLANES - 1][1] << 16);
+            a.z = outv[0][2] | (outv[PLANES - 1][2] << 16); a.w = outv[0][3] | (outv[PLANES - 1][3] << 16);
+            b.x = outv[0][4] | (outv[PLANES - 1][4] << 16); b.y = outv[0][5] | (outv[PLANES - 1][5] << 16);
+            b.z = outv[0][6] | (outv[PLANES - 1][6] << 16); b.w = outv[0][7] | (outv[PLANES - 1][7] << 16);
+            *reinterpret_cast<uint4 *>(d0 + ro + 4 * X) = a;
+            *reinterpret_cast<uint4 *>(d0 + ro + 4 * X + 16) = b;
+        }
+    } else {
+        for (int k = 0; k < nvalid; k++) {
+            if (OUT == 0) d0[ro + X + k] = (uint8_t)outv[0][k];
+            else if (OUT == 2) reinterpret_cast<uint32_t *>(d0 + ro)[X + k] = (uint32_t)outv[0][k] | ((uint32_t)outv[PLANES - 1][k] << 16);
+            else {
+                reinterpret_cast<uint16_t *>(d0 + ro)[X + k] = (uint16_t)outv[0][k];
+                if (PLANES == 2) reinterpret_cast<uint16_t *>(d1 + ro)[X + k] = (uint16_t)outv[PLANES - 1][k];
+            }
+        }
+    }
+}
+
 bool is_aligned16(uint64_t p) { return (p & 15) == 0; }
 
 void bicubic_table(short tab[64][4])
@@ -386,7 +581,66 @@ int launch_scale(hb_ctx *ctx, const uint8_t *s0, const uint8_t *s1, int ss, int 
     return HB_OK;
 }
 
+bool csc_coefficients(int matrix, int depth, CscCoef &c)
+{
+    double kr, kb;
+    switch (matrix) {
+    case HB_MATRIX_BT709: kr = 0.2126; kb = 0.0722; break;
+    case HB_MATRIX_BT2020: kr = 0.2627; kb = 0.0593; break;
+    case HB_MATRIX_BT601: kr = 0.299; kb = 0.114; break;
+    default: return false;
+    }
+    const double kg = 1.0 - kr - kb;
+    const double sy = (219 << (depth - 8)) / 255.0 * 16384.0, sc = (224 << (depth - 8)) / 255.0 * 16384.0;
+    c.cy[0] = (int)nearbyint(kr * sy); c.cy[1] = (int)nearbyint(kg * sy); c.cy[2] = (int)nearbyint(kb * sy);
+    c.ccb[0] = (int)nearbyint(-kr / (2 * (1 - kb)) * sc); c.ccb[1] = (int)nearbyint(-kg / (2 * (1 - kb)) * sc); c.ccb[2] = (int)nearbyint(0.5 * sc);
+    c.ccr[0] = (int)nearbyint(0.5 * sc); c.ccr[1] = (int)nearbyint(-kg / (2 * (1 - kr)) * sc); c.ccr[2] = (int)nearbyint(-kb / (2 * (1 - kr)) * sc);
+    c.yoff = 16 << (depth - 8); c.coff = 128 << (depth - 8); c.maxv = (1 << depth) - 1;
+    return true;
+}
+
 }  // namespace
+
+namespace hb {
+
+// out_mode 0: 8-bit planar, 1: 16-bit planar (s1/d1 = second plane), 2: 16-bit interleaved pairs.  Runs on ctx->stream.
+int launch_scale8(hb_ctx *ctx, const uint8_t *s0, const uint8_t *s1, int ss, int sw, int sh, uint8_t *d0, uint8_t *d1, int ds, int dw, int dh,
+                  int out_depth, int out_shift, int out_mode)
+{
+    const int2 *xt, *yt;
+    int rc = scale_table(ctx, sw, dw, &xt);
+    if (rc) return rc;
+    rc = scale_table(ctx, sh, dh, &yt);
+    if (rc) return rc;
+    const int grid = ((dw + S2_TW - 1) / S2_TW) * ((dh + S2_TH - 1) / S2_TH);
+    const int aligned = is_aligned16((uint64_t)(uintptr_t)d0 | (uint64_t)(uintptr_t)d1 | (uint64_t)ds);
+    cudaStream_t st = ctx->stream;
+    if (s1 && out_mode == 2) k_scale8<2, 2><<<grid, 256, 0, st>>>(s0, s1, ss, sw, sh, d0, d1, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
+    else if (s1 && out_mode == 1) k_scale8<2, 1><<<grid, 256, 0, st>>>(s0, s1, ss, sw, sh, d0, d1, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
+    else if (!s1 && out_mode == 1) k_scale8<1, 1><<<grid, 256, 0, st>>>(s0, nullptr, ss, sw, sh, d0, nullptr, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
+    else if (!s1 && out_mode == 0) k_scale8<1, 0><<<grid, 256, 0, st>>>(s0, nullptr, ss, sw, sh, d0, nullptr, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
+    else return hb_fail(ctx, HB_ERR_ARG, "bad argument: %s", "scaler output mode");
+    HB_LAUNCHED(ctx);
+    return HB_OK;
+}
+
+// packed 8-bit RGB / BGR -> 16-bit planar 4:2:0 at `depth` bits (LSB-aligned), strides in bytes.  Runs on ctx->stream.
+int launch_rgb_planar16(hb_ctx *ctx, const uint8_t *rgb, int rs, int bgr, int matrix, int depth, int w, int h, uint8_t *dy, int dys, uint8_t *du,
+                        uint8_t *dv, int dcs)
+{
+    CscCoef c;
+    if (!csc_coefficients(matrix, depth, c)) return hb_fail(ctx, HB_ERR_ARG, "bad argument: %s", "matrix");
+    const int aligned = is_aligned16((uint64_t)(uintptr_t)rgb | (uint64_t)(uintptr_t)dy | (uint64_t)(uintptr_t)du | (uint64_t)(uintptr_t)dv |
+                                     (uint64_t)rs | (uint64_t)dys | (uint64_t)dcs);
+    const long long items = (long long)((w + 15) / 16) * (h / 2);
+    const int grid = hb_grid_for(ctx, items, 128, 8);
+    if (depth == 8) k_rgb_to_yuv420<8, true><<<grid, 128, 0, ctx->stream>>>(rgb, rs, bgr, c, w, h, dy, dys, du, dcs, dv, dcs, aligned);
+    else k_rgb_to_yuv420<10, true><<<grid, 128, 0, ctx->stream>>>(rgb, rs, bgr, c, w, h, dy, dys, du, dcs, dv, dcs, aligned);
+    HB_LAUNCHED(ctx);
+    return HB_OK;
+}
+
+}  // namespace hb
 
 extern "C" {
 
@@ -409,20 +663,8 @@ int hb_rgb_to_yuv420(hb_ctx *ctx, hb_devptr rgb, int rs, int order, int matrix, 
     HB_ARG(ctx, ctx && rgb && dy && du && w > 0 && h > 0 && (w % 2) == 0 && (h % 2) == 0);
     HB_ARG(ctx, depth == 8 || depth == 10);
     HB_ARG(ctx, depth == 10 || dv);
-    double kr, kb;
-    switch (matrix) {
-    case HB_MATRIX_BT709: kr = 0.2126; kb = 0.0722; break;
-    case HB_MATRIX_BT2020: kr = 0.2627; kb = 0.0593; break;
-    case HB_MATRIX_BT601: kr = 0.299; kb = 0.114; break;
-    default: return hb_fail(ctx, HB_ERR_ARG, "bad argument: %s", "matrix");
-    }
-    const double kg = 1.0 - kr - kb;
-    const double sy = (219 << (depth - 8)) / 255.0 * 16384.0, sc = (224 << (depth - 8)) / 255.0 * 16384.0;
     CscCoef c;
-    c.cy[0] = (int)nearbyint(kr * sy); c.cy[1] = (int)nearbyint(kg * sy); c.cy[2] = (int)nearbyint(kb * sy);
-    c.ccb[0] = (int)nearbyint(-kr / (2 * (1 - kb)) * sc); c.ccb[1] = (int)nearbyint(-kg / (2 * (1 - kb)) * sc); c.ccb[2] = (int)nearbyint(0.5 * sc);
-    c.ccr[0] = (int)nearbyint(0.5 * sc); c.ccr[1] = (int)nearbyint(-kg / (2 * (1 - kr)) * sc); c.ccr[2] = (int)nearbyint(-kb / (2 * (1 - kr)) * sc);
-    c.yoff = 16 << (depth - 8); c.coff = 128 << (depth - 8); c.maxv = (1 << depth) - 1;
+    if (!csc_coefficients(matrix, depth, c)) return hb_fail(ctx, HB_ERR_ARG, "bad argument: %s", "matrix");
     uint64_t bits = rgb | dy | du | (uint64_t)rs | (uint64_t)dys | (uint64_t)dus;
     if (depth == 8)
         bits |= dv | (uint64_t)dvs;
@@ -444,6 +686,9 @@ int hb_scale_plane(hb_ctx *ctx, hb_devptr src, int ss, int sw, int sh, hb_devptr
 {
     HB_ARG(ctx, ctx && src && dst && sw > 0 && sh > 0 && dw > 0 && dh > 0 && step >= 1);
     HB_ARG(ctx, (out_depth == 8 && out_shift == 0) || (out_depth == 10 && out_shift >= 0 && out_shift <= 6));
+    if (step == 1)
+        return hb::launch_scale8(ctx, (const uint8_t *)src, nullptr, ss, sw, sh, (uint8_t *)dst, nullptr, ds, dw, dh, out_depth, out_shift,
+                                 out_depth == 8 ? 0 : 1);
     return launch_scale(ctx, (const uint8_t *)src, nullptr, ss, sw, sh, (uint8_t *)dst, ds, dw, dh, out_depth, out_shift, step);
 }
 
@@ -452,9 +697,9 @@ int hb_scale_yuv420_to_p010(hb_ctx *ctx, hb_devptr y, int ys, hb_devptr u, int u
 {
     HB_ARG(ctx, ctx && y && u && v && dy && duv && sw > 0 && sh > 0 && dw > 0 && dh > 0);
     HB_ARG(ctx, us == vs && (dw % 2) == 0 && (dh % 2) == 0 && (sw % 2) == 0 && (sh % 2) == 0);
-    int rc = launch_scale(ctx, (const uint8_t *)y, nullptr, ys, sw, sh, (uint8_t *)dy, dys, dw, dh, 10, 6, 1);
+    int rc = hb::launch_scale8(ctx, (const uint8_t *)y, nullptr, ys, sw, sh, (uint8_t *)dy, nullptr, dys, dw, dh, 10, 6, 1);
     if (rc) return rc;
-    return launch_scale(ctx, (const uint8_t *)u, (const uint8_t *)v, us, sw / 2, sh / 2, (uint8_t *)duv, duvs, dw / 2, dh / 2, 10, 6, 1);
+    return hb::launch_scale8(ctx, (const uint8_t *)u, (const uint8_t *)v, us, sw / 2, sh / 2, (uint8_t *)duv, nullptr, duvs, dw / 2, dh / 2, 10, 6, 2);
 }
 
 }  // extern "C"

@@ -269,8 +269,12 @@ class B200Params:
         return 'main10' if self.profile_idc == 2 else 'main'
 
 
-def derive_b200_params(info: VideoInfo) -> B200Params:
+def derive_b200_params(info: VideoInfo, force_main10: bool = False) -> B200Params:
     """Translate the reference's x265 option list for ``info`` into encoder parameters.
+
+    ``force_main10`` raises only the coding bit depth (profile Main10, 10-bit samples) for an SDR source -- the upscale
+    path's scaler writes P010 -- and leaves every colour / HDR10 signalling decision to the source's own tags: bit depth
+    and HDR are separate properties.
 
     Equivalent of ``build_ffmpeg_params(info, use_nvenc=False, ...)`` (core/transcoder.py:357-412) for a
     backend that takes structured parameters instead of an argv.  Options the reference passes that
@@ -287,6 +291,8 @@ def derive_b200_params(info: VideoInfo) -> B200Params:
         crf=crf, vbv_maxrate_kbps=maxrate, vbv_bufsize_kbit=bufsize, keyint=gop, min_keyint=max(2, int(gop // 2)),
         colour_primaries=_PRIMARIES.get(info.color_primaries, 2), transfer_characteristics=_TRANSFER.get(info.color_transfer, 2),
         matrix_coeffs=_MATRIX.get(info.color_space, 2))
+    if force_main10 and not hdr:
+        p.bit_depth, p.profile_idc = 10, 2
     if hdr:
         # hdr10=1:colorprim=bt2020:transfer=smpte2084:colormatrix=bt2020nc:...:hrd=1:aud=1:chromaloc=0:repeat-headers=1
         p.colour_primaries, p.transfer_characteristics, p.matrix_coeffs = 9, 16, 9

@@ -14,7 +14,7 @@ import numpy as np
 from . import _cabi
 from .derive import B200Params
 
-PIX_YUV420P8, PIX_P010, PIX_YUV420P16 = 0, 1, 2
+PIX_YUV420P8, PIX_P010, PIX_YUV420P16, PIX_BGR24, PIX_RGB24 = 0, 1, 2, 3, 4
 
 
 class HbEncParams(C.Structure):
@@ -27,7 +27,8 @@ class HbEncParams(C.Structure):
 
 
 class HbFrames(C.Structure):
-    _fields_ = [('data', C.c_void_p), ('on_device', C.c_int), ('format', C.c_int), ('n_frames', C.c_int), ('frame_bytes', C.c_size_t)]
+    _fields_ = [('data', C.c_void_p), ('on_device', C.c_int), ('format', C.c_int), ('n_frames', C.c_int), ('src_bit_depth', C.c_int),
+                ('frame_bytes', C.c_size_t), ('src_width', C.c_int), ('src_height', C.c_int), ('matrix', C.c_int), ('reserved0', C.c_int)]
 
 
 class HbFrameStat(C.Structure):
@@ -121,22 +122,35 @@ class B200Encoder:
         self._check(self.L.hb_enc_headers(self.h, buf, 1024, C.byref(n)))
         return bytes(buf[:n.value])
 
-    def frame_bytes(self, fmt: int) -> int:
-        w, h = self.params.width, self.params.height
+    def frame_bytes(self, fmt: int, src_size: Optional[Tuple[int, int]] = None) -> int:
+        w, h = src_size if src_size else (self.params.width, self.params.height)
+        if fmt in (PIX_BGR24, PIX_RGB24):
+            return 3 * w * h
         n = w * h + 2 * (w // 2) * (h // 2)
         return n if fmt == PIX_YUV420P8 else 2 * n
 
-    def encode(self, data, n_frames: int, fmt: int = PIX_YUV420P8, force_idr: bool = False, on_device: bool = False,
-               frame_bytes: Optional[int] = None) -> Tuple[bytes, List[FrameStat]]:
-        """``data``: numpy array (host; pinned memory avoids a staging copy in the driver) or an integer device address."""
-        fr = HbFrames()
+    def _fill(self, fr: 'HbFrames', data, n_frames, fmt, on_device, frame_bytes, src_bit_depth, src_size, matrix):
         if on_device:
             fr.data = int(data)
+            arr = None
         else:
             arr = np.ascontiguousarray(data)
             fr.data = arr.ctypes.data
         fr.on_device, fr.format, fr.n_frames = int(on_device), fmt, n_frames
-        fr.frame_bytes = frame_bytes or self.frame_bytes(fmt)
+        fr.src_bit_depth = int(src_bit_depth) if fmt == PIX_YUV420P16 else 0
+        fr.frame_bytes = frame_bytes or self.frame_bytes(fmt, src_size)
+        fr.src_width, fr.src_height = (int(src_size[0]), int(src_size[1])) if src_size else (0, 0)
+        fr.matrix = int(matrix)
+        return arr
+
+    def encode(self, data, n_frames: int, fmt: int = PIX_YUV420P8, force_idr: bool = False, on_device: bool = False,
+               frame_bytes: Optional[int] = None, src_bit_depth: int = 0, src_size: Optional[Tuple[int, int]] = None,
+               matrix: int = 0) -> Tuple[bytes, List[FrameStat]]:
+        """``data``: numpy array (host; pinned memory avoids a staging copy in the driver) or an integer device address.
+        ``src_bit_depth``: significant bits of a PIX_YUV420P16 source (0 = the encoder's depth).  ``src_size``: (w, h) of a
+        PIX_YUV420P8 source that the ingest stage resamples to the encoder's size.  ``matrix``: HB_MATRIX_* for RGB sources."""
+        fr = HbFrames()
+        arr = self._fill(fr, data, n_frames, fmt, on_device, frame_bytes, src_bit_depth, src_size, matrix)   # noqa: F841 (keeps the buffer alive)
         need = n_frames * self.frame_bytes(PIX_YUV420P8) + (1 << 20)
         if self._out.size < need:
             self._out = np.empty(need, np.uint8)
@@ -147,21 +161,17 @@ class B200Encoder:
         return out, [FrameStat(bool(s.is_idr), s.poc, s.qp, s.bytes) for s in stats[:n_frames]]
 
     def encode_delayed(self, data, n_frames: int, fmt: int = PIX_YUV420P8, force_idr: bool = False, on_device: bool = False,
-                       frame_bytes: Optional[int] = None) -> Tuple[bytes, List[FrameStat]]:
+                       frame_bytes: Optional[int] = None, src_bit_depth: int = 0, src_size: Optional[Tuple[int, int]] = None,
+                       matrix: int = 0) -> Tuple[bytes, List[FrameStat]]:
         """Pipelined form: enqueue ``n_frames`` frames, return the access units of frames submitted by earlier calls (possibly
         none).  ``data is None`` flushes.  The input buffer must stay alive until its frames have been returned."""
         if data is None:
             frp = None
         else:
             fr = HbFrames()
-            if on_device:
-                fr.data = int(data)
-            else:
-                arr = np.ascontiguousarray(data)
+            arr = self._fill(fr, data, n_frames, fmt, on_device, frame_bytes, src_bit_depth, src_size, matrix)
+            if arr is not None:
                 self._inflight = (getattr(self, '_inflight', ()) + (arr,))[-3:]      # keep the host buffers of the batches in flight
-                fr.data = arr.ctypes.data
-            fr.on_device, fr.format, fr.n_frames = int(on_device), fmt, n_frames
-            fr.frame_bytes = frame_bytes or self.frame_bytes(fmt)
             frp = C.byref(fr)
         need = 2 * self.max_batch * self.frame_bytes(PIX_YUV420P8) + max(0, n_frames) * self.frame_bytes(PIX_YUV420P8) + (1 << 20)
         if self._out.size < need:
@@ -237,12 +247,18 @@ class ParallelSegmentEncoder:
 
     ``submit`` returns the segments that have completed, in order (possibly none); ``finish`` returns the rest."""
 
-    def __init__(self, device: int, params: HbEncParams, streams: int = 2, max_batch: int = 32):
+    def __init__(self, device, params: HbEncParams, streams: int = 2, max_batch: int = 32):
+        """``device``: one device index, or a sequence of them -- then ``streams`` encoders run on EACH device and segment k
+        goes to worker k mod (devices x streams), device-major, i.e. the reference's ``cycle(gpu_list)`` fan-out
+        (upscale_gui_final.py:25-30,123-126) with in-order collection (:164-178)."""
         import queue
         import threading
-        self.streams = max(1, int(streams))
+        devices = [int(device)] if isinstance(device, int) else [int(d) for d in device]
+        per = max(1, int(streams))
+        self.devices = devices
+        self.streams = per * len(devices)
         self.max_batch = max_batch
-        self._ctxs = [_cabi.Context(device) for _ in range(self.streams)]
+        self._ctxs = [_cabi.Context(devices[k % len(devices)]) for k in range(self.streams)]
         self._encs = [B200Encoder(c, params, max_batch=max_batch) for c in self._ctxs]
         self._queues = [queue.Queue() for _ in range(self.streams)]
         self._lock = threading.Lock()

@@ -22,6 +22,7 @@ class Y4MReader:
         if not self.meta['pix_fmt'].startswith('yuv420'):
             raise ValueError(f"unsupported Y4M chroma format {self.meta['pix_fmt']}")
         self.fmt = PIX_YUV420P16 if '10' in self.meta['pix_fmt'] else PIX_YUV420P8
+        self.src_bit_depth = 10 if self.fmt == PIX_YUV420P16 else 8
         self.frame_bytes = self.meta['frame_bytes']
         self.kind = 'yuv'
 
@@ -53,6 +54,7 @@ class RawYuvReader:
         self.path = Path(path)
         bps = 2 if '10' in info.pix_fmt else 1
         self.fmt = PIX_YUV420P16 if bps == 2 else PIX_YUV420P8
+        self.src_bit_depth = 10 if bps == 2 else 8
         self.frame_bytes = (info.width * info.height + 2 * (info.width // 2) * (info.height // 2)) * bps
         self.kind = 'yuv'
 
@@ -75,6 +77,7 @@ class Cv2Reader:
         if not self.cap.isOpened():
             raise ValueError(f'cannot open {path}')
         self.kind = 'bgr'
+        self.src_bit_depth = 8
 
     def batches(self, batch: int):
         while True:

@@ -122,30 +122,10 @@ def sample_entry(info: TrackInfo, vps: bytes, sps: bytes, pps: bytes) -> bytes:
     return box(b'hvc1', visual, extra)
 
 
-def mux(info: TrackInfo, access_units: Iterable[Tuple[List[bytes], bool]]) -> bytes:
-    """access_units: (NAL units of one frame, is_sync).  Parameter sets are taken from the first access unit that carries
-    them and are removed from the samples (``hvc1`` keeps them out of band).  Returns the complete file, moov first."""
-    vps = sps = pps = None
-    samples: List[bytes] = []
-    sync: List[int] = []
-    for i, (nals, is_sync) in enumerate(access_units):
-        body = bytearray()
-        for nal in nals:
-            t = nal_type(nal)
-            if t == NAL_VPS:
-                vps = vps or nal
-            elif t == NAL_SPS:
-                sps = sps or nal
-            elif t == NAL_PPS:
-                pps = pps or nal
-            else:
-                body += struct.pack('>I', len(nal)) + nal
-        samples.append(bytes(body))
-        if is_sync:
-            sync.append(i + 1)
-    if not (vps and sps and pps):
-        raise ValueError('stream carries no VPS/SPS/PPS')
-    n = len(samples)
+def _head(info: TrackInfo, vps: bytes, sps: bytes, pps: bytes, sizes: Sequence[int], sync: Sequence[int]) -> bytes:
+    """ftyp + moov (sample tables for one chunk holding every sample) + the 64-bit mdat header: everything before the samples."""
+    n = len(sizes)
+    payload_len = sum(sizes)
     timescale, delta = info.fps_num, info.fps_den
     duration = n * delta
     matrix = struct.pack('>9I', 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000)
@@ -155,7 +135,7 @@ def mux(info: TrackInfo, access_units: Iterable[Tuple[List[bytes], bool]]) -> by
         full_box(b'stts', 0, 0, struct.pack('>III', 1, n, delta)),
         full_box(b'stss', 0, 0, struct.pack('>I', len(sync)), b''.join(struct.pack('>I', s) for s in sync)),
         full_box(b'stsc', 0, 0, struct.pack('>IIII', 1, 1, n, 1)),       # one chunk holding every sample
-        full_box(b'stsz', 0, 0, struct.pack('>II', 0, n), b''.join(struct.pack('>I', len(s)) for s in samples)),
+        full_box(b'stsz', 0, 0, struct.pack('>II', 0, n), struct.pack('>%dI' % n, *sizes)),
     ]
 
     def moov(chunk_offset: int) -> bytes:
@@ -173,12 +153,82 @@ def mux(info: TrackInfo, access_units: Iterable[Tuple[List[bytes], bool]]) -> by
         return box(b'moov', mvhd, box(b'trak', tkhd, mdia))
 
     ftyp = box(b'ftyp', b'mp42', struct.pack('>I', 0), b'mp42', b'isom', b'iso2')
-    payload = b''.join(samples)
     head = ftyp + moov(0)
-    offset = len(head) + 16                                              # 64-bit mdat header
-    head = ftyp + moov(offset)
-    mdat = struct.pack('>I4sQ', 1, b'mdat', 16 + len(payload))
-    return head + mdat + payload
+    head = ftyp + moov(len(head) + 16)                                   # 64-bit mdat header
+    return head + struct.pack('>I4sQ', 1, b'mdat', 16 + payload_len)
+
+
+def _sample_of(nals: Sequence[bytes], sets: dict) -> bytes:
+    """length-prefixed sample of one access unit; parameter sets go to ``sets`` (``hvc1`` keeps them out of band)"""
+    body = bytearray()
+    for nal in nals:
+        t = nal_type(nal)
+        if t in (NAL_VPS, NAL_SPS, NAL_PPS):
+            sets.setdefault(t, nal)
+        else:
+            body += struct.pack('>I', len(nal)) + nal
+    return bytes(body)
+
+
+def mux(info: TrackInfo, access_units: Iterable[Tuple[List[bytes], bool]]) -> bytes:
+    """access_units: (NAL units of one frame, is_sync).  Parameter sets are taken from the first access unit that carries
+    them and are removed from the samples (``hvc1`` keeps them out of band).  Returns the complete file, moov first."""
+    sets: dict = {}
+    samples: List[bytes] = []
+    sync: List[int] = []
+    for i, (nals, is_sync) in enumerate(access_units):
+        samples.append(_sample_of(nals, sets))
+        if is_sync:
+            sync.append(i + 1)
+    if len(sets) != 3:
+        raise ValueError('stream carries no VPS/SPS/PPS')
+    return _head(info, sets[NAL_VPS], sets[NAL_SPS], sets[NAL_PPS], [len(x) for x in samples], sync) + b''.join(samples)
+
+
+class StreamMuxer:
+    """Incremental form of ``mux_annexb`` for long files: ``feed`` takes runs of whole access units as the encoder delivers
+    them and spools the samples to ``<out>.mdat.tmp``; only the sample-size table stays in memory.  On a clean exit the file
+    is written moov-first (faststart, core/transcoder.py:492) and the spool is appended and removed."""
+
+    def __init__(self, info: TrackInfo, out_path):
+        from pathlib import Path
+        self.info, self.out_path = info, Path(out_path)
+        self.spool_path = self.out_path.with_name(self.out_path.name + '.mdat.tmp')
+        self.sets: dict = {}
+        self.sizes: List[int] = []
+        self.sync: List[int] = []
+        self._spool = None
+
+    def __enter__(self):
+        self._spool = open(self.spool_path, 'wb')
+        return self
+
+    def feed(self, annexb: bytes):
+        if not annexb:
+            return
+        for au in split_access_units(annexb):
+            sample = _sample_of(au, self.sets)
+            self._spool.write(sample)
+            self.sizes.append(len(sample))
+            if any(16 <= nal_type(x) <= 23 for x in au):
+                self.sync.append(len(self.sizes))
+
+    def __exit__(self, exc_type, exc, tb):
+        import shutil
+        self._spool.close()
+        try:
+            if exc_type is None and self.sizes:
+                if len(self.sets) != 3:
+                    raise ValueError('stream carries no VPS/SPS/PPS')
+                with open(self.out_path, 'wb') as out, open(self.spool_path, 'rb') as spool:
+                    out.write(_head(self.info, self.sets[NAL_VPS], self.sets[NAL_SPS], self.sets[NAL_PPS], self.sizes, self.sync))
+                    shutil.copyfileobj(spool, out, 1 << 24)
+        finally:
+            try:
+                self.spool_path.unlink()
+            except OSError:
+                pass
+        return False
 
 
 def mux_annexb(info: TrackInfo, annexb: bytes) -> bytes:

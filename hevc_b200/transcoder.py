@@ -15,7 +15,7 @@ import subprocess
 import threading
 from collections import OrderedDict
 from pathlib import Path
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Sequence, Any, Callable, Dict, List, Optional, Tuple
 
 from . import derive
 from .derive import FFmpegParams, calculate_dynamic_values
@@ -202,116 +202,72 @@ def next_device() -> int:
 
 def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
                 stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
-                target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None) -> Tuple[int, str]:
-    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on one B200.  Returns (0, '') or (1, reason) like run_ffmpeg.
+                target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None, force_main10: bool = False,
+                devices: Optional[Sequence[int]] = None) -> Tuple[int, str]:
+    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on B200.  Returns (0, '') or (1, reason) like run_ffmpeg.
 
-    ``streams`` > 1 (or ``HEVC_B200_STREAMS``) encodes closed-GOP segments of one key-frame interval on that many independent
-    encoder streams of the same GPU (``ParallelSegmentEncoder``); planar 4:2:0 sources only, the pixel-pipeline paths (BGR
-    sources, up-scaling) stay on one stream."""
+    The pre-encode pixel pipeline (BGR -> 4:2:0 matrix conversion for container sources, polyphase scaling for
+    ``target_size``, bit-depth conversion) runs inside the encoder's ingest stage on the device: host frames go to
+    ``hb_enc_encode_delayed`` as they were read.
+
+    ``streams`` > 1 (or ``HEVC_B200_STREAMS``) and / or several ``devices`` encode closed-GOP segments of one key-frame interval
+    on that many independent encoder streams (``ParallelSegmentEncoder``), written in order and muxed once."""
     import numpy as np
-    import torch
 
-    from . import _cabi, mp4, ops
-    from .encoder import PIX_P010, B200Encoder, to_c_params
+    from . import _cabi, mp4
+    from .encoder import PIX_BGR24, PIX_YUV420P8, B200Encoder, ParallelSegmentEncoder, to_c_params
     from .frames import open_reader
+    enc = None
     try:
-        dev = next_device() if device is None else device
-        ctx = _cabi.Context(dev)
+        devs = [int(d) for d in devices] if devices else [next_device() if device is None else int(device)]
+        if _cabi.lib().hb_device_count() <= max(devs):
+            return 1, f'B200 backend unavailable: device {max(devs)} not present'
     except Exception as exc:
         return 1, f'B200 backend unavailable: {exc}'
     try:
         src_w, src_h = info.width, info.height
         if target_size:
             info = VideoInfo(**{**info.__dict__, 'width': target_size[0], 'height': target_size[1]})
-        params = derive.derive_b200_params(info)
+        params = derive.derive_b200_params(info, force_main10=force_main10)
         reader = open_reader(file_path, VideoInfo(**{**info.__dict__, 'width': src_w, 'height': src_h}))
+        if getattr(info, 'audio_channels', 0):
+            # the reference transcodes audio to AAC inside the same ffmpeg child (core/transcoder.py:423-450); this backend writes
+            # the video track only (SURVEY section 8f-4: audio stays with an external tool)
+            logger.warning('%s: %d audio channel(s) in the source are NOT carried over by encoder=b200 (video-only MP4)',
+                           file_path.name, info.audio_channels)
         if streams is None:
             streams = int(os.environ.get('HEVC_B200_STREAMS', '1') or 1)
-        if streams > 1 and reader.kind != 'bgr' and not target_size:
-            return _encode_segments(file_path, out_path, reader, params, dev, streams, progress_callback, total_frames, stop_event)
-        enc = B200Encoder(ctx, to_c_params(params), max_batch=batch)
-        chunks: List[bytes] = []
-        done = submitted = 0
-        inflight: list = []
-        tdev = torch.device('cuda', dev)
-        matrix = 'bt2020' if params.matrix_coeffs == 9 else 'bt709' if params.matrix_coeffs == 1 else 'bt601'
-        for buf, n, fmt in reader.batches(batch):
-            if stop_event is not None and stop_event.is_set():
-                return 1, 'cancelled'
-            if reader.kind == 'bgr' or target_size:
-                # device-side pre-encode pixel pipeline: BGR -> 4:2:0 (matrix), optional polyphase scale, pack to P010
-                w, h = params.width, params.height
-                out = torch.empty((n, (w * h + 2 * (w // 2) * (h // 2)) * 2), dtype=torch.uint8, device=tdev)
-                for i in range(n):
-                    y16 = out[i, :w * h * 2].view(torch.int16).view(h, w)
-                    uv16 = out[i, w * h * 2:].view(torch.int16).view(h // 2, w)
-                    if reader.kind == 'bgr':
-                        img = torch.from_numpy(buf[i]).to(tdev)
-                        if target_size:
-                            y8, u8, v8 = ops.rgb_to_yuv420(ctx, img, matrix, 8, bgr=True)
-                        else:
-                            ctx.call('hb_rgb_to_yuv420', _cabi.dp(img), img.stride(0), 1, ops.MATRIX_IDS[matrix], 10, w, h,
-                                     _cabi.dp(y16), w * 2, _cabi.dp(uv16), w * 2, 0, 0)
-                            continue
-                    else:
-                        f = torch.from_numpy(buf[i]).to(tdev)
-                        y8 = f[:src_w * src_h].view(src_h, src_w)
-                        u8 = f[src_w * src_h:src_w * src_h + (src_w // 2) * (src_h // 2)].view(src_h // 2, src_w // 2)
-                        v8 = f[src_w * src_h + (src_w // 2) * (src_h // 2):].view(src_h // 2, src_w // 2)
-                    torch.cuda.synchronize(tdev)
-                    ctx.call('hb_scale_yuv420_to_p010', _cabi.dp(y8), y8.stride(0), _cabi.dp(u8), u8.stride(0), _cabi.dp(v8), v8.stride(0),
-                             y8.shape[1], y8.shape[0], _cabi.dp(y16), w * 2, _cabi.dp(uv16), w * 2, w, h)
-                torch.cuda.synchronize(tdev)
-                ctx.sync()
-                inflight = (inflight + [out])[-3:]            # device input must outlive the batches still in the encoder
-                data, st = enc.encode_delayed(out.data_ptr(), n, fmt=PIX_P010, on_device=True)
-            else:
-                data, st = enc.encode_delayed(np.ascontiguousarray(buf), n, fmt=fmt)
-            # pipelined: the call returns the access units of the previous batch while this one is being encoded
-            chunks.append(data)
-            done += len(st)
-            submitted += n
-            if progress_callback and st:
-                try:
-                    progress_callback(file_path.name, done, max(total_frames, done))
-                except Exception:
-                    logger.debug('progress callback raised', exc_info=True)
-        if submitted == 0:
-            return 1, 'no frames decoded'
-        data, st = enc.flush()
-        chunks.append(data)
-        done += len(st)
-        if progress_callback and st:
-            try:
-                progress_callback(file_path.name, done, max(total_frames, done))
-            except Exception:
-                logger.debug('progress callback raised', exc_info=True)
+        kw = {}
+        if reader.kind == 'bgr':
+            fmt_override = PIX_BGR24
+        else:
+            fmt_override = None
+            if reader.src_bit_depth > 8:
+                kw['src_bit_depth'] = reader.src_bit_depth
+        if target_size and (src_w, src_h) != tuple(target_size):
+            if fmt_override is None and reader.src_bit_depth > 8:
+                return 1, 'scaling of 10-bit planar sources is not supported'
+            kw['src_size'] = (src_w, src_h)
+        segmented = streams > 1 or len(devs) > 1
+        unit = max(1, min(int(params.keyint), 1024)) if segmented else batch
+        if segmented:
+            enc = ParallelSegmentEncoder(devs, to_c_params(params), streams=streams, max_batch=unit)
+            submit = lambda data, n, fmt: enc.submit(data, n, fmt=fmt, **kw)      # noqa: E731
+            finish = enc.finish
+        else:
+            ctx = _cabi.Context(devs[0])
+            single = B200Encoder(ctx, to_c_params(params), max_batch=unit)
+
+            class _One:      # same close() shape as the segment encoder
+                def close(self_inner):
+                    single.close()
+                    ctx.close()
+            enc = _One()
+            submit = lambda data, n, fmt: single.encode_delayed(data, n, fmt=fmt, **kw)      # noqa: E731
+            finish = single.flush
         track = mp4.TrackInfo(params.width, params.height, params.fps_num, params.fps_den, params.profile_idc, params.level_idc, params.tier,
                               params.bit_depth, params.colour_primaries, params.transfer_characteristics, params.matrix_coeffs, params.full_range,
                               params.master_display if params.hdr10 else None, params.max_cll, params.max_fall)
-        out_path.write_bytes(mp4.mux_annexb(track, b''.join(chunks)))
-        return 0, ''
-    except Exception as exc:
-        logger.debug('B200 encode failed', exc_info=True)
-        return 1, f'{type(exc).__name__}: {exc}'
-    finally:
-        try:
-            enc.close()
-        except Exception:
-            pass
-        ctx.close()
-
-
-def _encode_segments(file_path, out_path, reader, params, dev, streams, progress_callback, total_frames, stop_event) -> Tuple[int, str]:
-    """Segment-parallel form of encode_b200: one key-frame interval per segment, segments round-robin over the streams."""
-    import numpy as np
-
-    from . import mp4
-    from .encoder import ParallelSegmentEncoder, to_c_params
-    seg = max(1, min(int(params.keyint), 1024))
-    pse = ParallelSegmentEncoder(dev, to_c_params(params), streams=streams, max_batch=seg)
-    try:
-        chunks: List[bytes] = []
         done = submitted = 0
 
         def tick(st):
@@ -323,25 +279,31 @@ def _encode_segments(file_path, out_path, reader, params, dev, streams, progress
                 except Exception:
                     logger.debug('progress callback raised', exc_info=True)
 
-        for buf, n, fmt in reader.batches(seg):
-            if stop_event is not None and stop_event.is_set():
-                return 1, 'cancelled'
-            data, st = pse.submit(np.ascontiguousarray(buf), n, fmt=fmt)
-            chunks.append(data)
-            submitted += n
+        # the elementary stream goes to the muxer as it arrives: samples are spooled to disk, the sample tables stay in memory
+        with mp4.StreamMuxer(track, out_path) as mux:
+            for buf, n, fmt in reader.batches(unit):
+                if stop_event is not None and stop_event.is_set():
+                    return 1, 'cancelled'
+                data = np.ascontiguousarray(buf).reshape(n, -1)
+                out, st = submit(data, n, fmt_override if fmt_override is not None else fmt)
+                mux.feed(out)
+                submitted += n
+                tick(st)
+            if submitted == 0:
+                return 1, 'no frames decoded'
+            out, st = finish()
+            mux.feed(out)
             tick(st)
-        if submitted == 0:
-            return 1, 'no frames decoded'
-        data, st = pse.finish()
-        chunks.append(data)
-        tick(st)
-        track = mp4.TrackInfo(params.width, params.height, params.fps_num, params.fps_den, params.profile_idc, params.level_idc, params.tier,
-                              params.bit_depth, params.colour_primaries, params.transfer_characteristics, params.matrix_coeffs, params.full_range,
-                              params.master_display if params.hdr10 else None, params.max_cll, params.max_fall)
-        out_path.write_bytes(mp4.mux_annexb(track, b''.join(chunks)))
         return 0, ''
+    except Exception as exc:
+        logger.debug('B200 encode failed', exc_info=True)
+        return 1, f'{type(exc).__name__}: {exc}'
     finally:
-        pse.close()
+        try:
+            if enc is not None:
+                enc.close()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------ the drop-in entry point

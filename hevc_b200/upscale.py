@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import threading
 from pathlib import Path
-from typing import Any, Callable, Dict, Optional, Tuple
+from typing import Any, Callable, Dict, Optional, Sequence, Tuple
 
 from . import transcoder
 from .derive import calculate_dynamic_values
@@ -24,17 +24,23 @@ def target_geometry(width: int, height: int, target_height: int = 0) -> Tuple[in
 
 
 def process_video(video_path: Path, output_dir: Path, target_height: int = 0, progress_callback: Optional[Callable[[str, int, int], None]] = None,
-                  stop_flag: Optional[threading.Event] = None, device: Optional[int] = None) -> Dict[str, Any]:
-    """Scale ``video_path`` to the target geometry and encode it as Main10 HEVC into ``output_dir/<stem>.mp4``."""
+                  stop_flag: Optional[threading.Event] = None, device: Optional[int] = None,
+                  devices: Optional[Sequence[int]] = None) -> Dict[str, Any]:
+    """Scale ``video_path`` to the target geometry and encode it as Main10 HEVC into ``output_dir/<stem>.mp4``.
+
+    ``devices``: several GPUs -> the clip is cut into closed-GOP segments of one key-frame interval, dealt round-robin to one
+    worker per device (the reference's ``cycle(gpu_list)`` fan-out, upscale_gui_final.py:25-30,123-126), written in order
+    (:164-178) and muxed once (BASELINE config 4)."""
     video_path, output_dir = Path(video_path), Path(output_dir)
     info = probe_media(video_path)
     tw, th = target_geometry(info.width, info.height, target_height)
     out_path = output_dir / (video_path.stem + '.mp4')
     total = max(1, int(info.duration * info.fps)) if info.duration and info.fps else 1
-    # the fused scaler writes P010, so the encode is Main10 whatever the source depth
-    info10 = type(info)(**{**info.__dict__, 'hdr': True}) if not info.hdr else info
-    rc, why = transcoder.encode_b200(video_path, out_path, info10, progress_callback, total, stop_flag, device, target_size=(tw, th))
-    crf = calculate_dynamic_values(type(info)(**{**info10.__dict__, 'width': tw, 'height': th}), False)[0]
+    # the fused scaler writes P010, so the encode is Main10 whatever the source depth; colour description and HDR10
+    # signalling stay the source's own (an SDR BT.709 clip stays BT.709 SDR: Main10 is a bit depth, not a transfer function)
+    rc, why = transcoder.encode_b200(video_path, out_path, info, progress_callback, total, stop_flag, device, target_size=(tw, th),
+                                     force_main10=True, devices=devices)
+    crf = calculate_dynamic_values(type(info)(**{**info.__dict__, 'width': tw, 'height': th}), False)[0]
     status = 'SUCCESS' if rc == 0 else ('CANCELLED' if stop_flag is not None and stop_flag.is_set() else 'FAILED')
-    return {'file': video_path.name, 'status': status, 'quality': crf, 'retries': 0, 'method': 'B200', 'hdr': True,
+    return {'file': video_path.name, 'status': status, 'quality': crf, 'retries': 0, 'method': 'B200', 'hdr': bool(info.hdr),
             'width': tw, 'height': th, 'reason': why}

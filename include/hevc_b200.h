@@ -137,7 +137,10 @@ typedef struct hb_enc_params {
     int reserved[7];
 } hb_enc_params;
 
-typedef enum hb_pix_fmt { HB_PIX_YUV420P8 = 0, HB_PIX_P010 = 1, HB_PIX_YUV420P16 = 2 } hb_pix_fmt;
+typedef enum hb_pix_fmt {
+    HB_PIX_YUV420P8 = 0, HB_PIX_P010 = 1, HB_PIX_YUV420P16 = 2,
+    HB_PIX_BGR24 = 3, HB_PIX_RGB24 = 4     /* packed 8-bit full-range RGB: converted by the ingest stage (what swscale does for -pix_fmt) */
+} hb_pix_fmt;
 
 /* a run of consecutive frames, tightly packed per frame: Y plane, then U and V planes (P010: Y then UV) */
 typedef struct hb_frames {
@@ -145,7 +148,15 @@ typedef struct hb_frames {
     int on_device;
     int format;                        /* hb_pix_fmt */
     int n_frames;
+    int src_bit_depth;                 /* HB_PIX_YUV420P16 only: significant bits per sample (8..16, LSB-aligned); 0 = the
+                                        * encoder's bit depth.  Deeper sources are rounded down to the encoder's depth, shallower
+                                        * ones shifted up (what swscale does for -pix_fmt, core/transcoder.py:464) */
     size_t frame_bytes;                /* distance between successive frames */
+    int src_width, src_height;         /* 0, 0 = the encoder's display size.  Other sizes (HB_PIX_YUV420P8 and the RGB formats): every frame is
+                                        * resampled on the device by the polyphase scaler straight into the encoder's source
+                                        * planes -- the upscale path (reference upscale_gui_final.py:81-87) without a P010 round trip */
+    int matrix;                        /* HB_PIX_BGR24 / RGB24: HB_MATRIX_*; 0 = follow params.matrix_coeffs (BT.709 if unspecified) */
+    int reserved0;
 } hb_frames;
 
 typedef struct hb_frame_stat {

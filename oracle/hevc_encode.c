@@ -152,6 +152,7 @@ static void load_source(orc_encoder *e, const pixel *y, int ys, const pixel *u, 
     }
     plane *ds = &e->ds[e->cur_ds];
     const plane *s = &e->src[0];
+#pragma omp parallel for
     for (int yy = 0; yy < ds->h; yy++)
         for (int xx = 0; xx < ds->w; xx++) {
             int acc = 8;
@@ -311,6 +312,7 @@ static void coarse_search(orc_encoder *e)
     const plane *cur = &e->ds[e->cur_ds], *prev = &e->ds[1 - e->cur_ds];
     /* the search runs on the 8 most significant bits of the quarter-resolution samples (byte SAD on the GPU) */
     const int sh = e->prm.bit_depth - 8, bias = 1;
+#pragma omp parallel for schedule(dynamic)
     for (int ty = 0; ty < e->ctuh; ty++)
         for (int tx = 0; tx < e->ctuw; tx++) {
             long best = -1;
@@ -368,6 +370,9 @@ static void encode_inter_frame(orc_encoder *e, int qp)
     plane *rec = e->rec[e->cur];
     const plane *ref = e->rec[1 - e->cur];
     coarse_search(e);
+    /* every loop over CUs below is order-independent (that is what lets the GPU run them as one launch each), so the model
+     * spreads them over the host cores */
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
     for (int cy = 0; cy < e->cuh; cy++)
         for (int cx = 0; cx < e->cuw; cx++) {
             const int x0 = cx * 16, y0 = cy * 16, tx = cx >> 1, ty = cy >> 1;
@@ -429,6 +434,7 @@ static void encode_inter_frame(orc_encoder *e, int qp)
         const int32_t *sdi = e->satdf[pass & 1];
         int16_t *mvo = e->mvf[(pass + 1) & 1];
         int32_t *sdo = e->satdf[(pass + 1) & 1];
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
         for (int cy = 0; cy < e->cuh; cy++)
             for (int cx = 0; cx < e->cuw; cx++) {
                 const int x0 = cx * 16, y0 = cy * 16, idx = cy * e->cuw + cx;
@@ -473,6 +479,7 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             }
     }
     const int16_t *mvfinal = e->mvf[MERGE_PASSES & 1];
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
     for (int cy = 0; cy < e->cuh; cy++)
         for (int cx = 0; cx < e->cuw; cx++) {
             orc_cu *cu = &e->cus[cy * e->cuw + cx];
@@ -657,8 +664,10 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
     if (p->aud) o += orc_write_aud(idr ? 0 : 1, out + o, cap - o);
     if (idr && (e->frame_no == 0 || p->repeat_headers || force_idr)) o += orc_enc_headers(e, out + o, cap - o);
     if (p->hrd) {
+        /* au_cpb_removal_delay counts from the most recent buffering period in a PRECEDING access unit (D.3.2) */
+        const int delay = e->since_bp;
         if (idr) { o += orc_write_sei_buffering_period(p, out + o, cap - o); e->since_bp = 0; }
-        o += orc_write_sei_pic_timing(p, e->since_bp > 0 ? e->since_bp : 1, out + o, cap - o);
+        o += orc_write_sei_pic_timing(p, delay > 0 ? delay : 1, out + o, cap - o);
         e->since_bp++;
     }
     if (idr && p->hdr10) o += orc_write_sei_hdr10(p, out + o, cap - o);

@@ -105,16 +105,80 @@ def test_convert_video_container_input_and_cancel(tmp_path):
 
 
 def test_upscale_and_encode(tmp_path):
-    """config 4 in miniature: geometry rule + fused scale -> P010 -> Main10"""
+    """config 4 in miniature: geometry rule + scaler fused into the encoder's ingest -> Main10.  Main10 is a bit depth, not a
+    transfer function: an SDR BT.709 source keeps SDR signalling (no HDR10 SEI, no mdcv / clli, VUI = the source's tags)."""
     assert upscale.target_geometry(1920, 1080) == (3840, 2160) and upscale.target_geometry(1280, 720) == (1920, 1080)
     w, h, n = 480, 270, 6
     clip = SynthClip(w, h, seed=8, noise=0.0)
     src = tmp_path / 'small.y4m'
     write_y4m(src, [clip.frame(i) for i in range(n)], w, h, (30, 1))
+    (tmp_path / 'small.y4m.json').write_text(json.dumps({'color_primaries': 'bt709', 'color_transfer': 'bt709', 'color_space': 'bt709'}))
     res = upscale.process_video(src, tmp_path, target_height=540, device=0)
-    assert res['status'] == 'SUCCESS' and (res['width'], res['height']) == (960, 540), res
-    rep, dec = _decode_mp4((tmp_path / 'small.mp4').read_bytes())
-    assert len(dec) == n and dec[0][0].shape == (540, 960) and rep['sps']['bit_depth'] == 10
+    assert res['status'] == 'SUCCESS' and (res['width'], res['height']) == (960, 540) and res['hdr'] is False, res
+    data = (tmp_path / 'small.mp4').read_bytes()
+    rep, dec = _decode_mp4(data)
+    sps = rep['sps']
+    assert len(dec) == n and dec[0][0].shape == (540, 960) and sps['bit_depth'] == 10 and sps['profile_idc'] == 2
+    assert (sps['colour_primaries'], sps['transfer_characteristics'], sps['matrix_coeffs']) == (1, 1, 1)
+    assert 137 not in rep['sei'] and 144 not in rep['sei'] and not sps.get('hrd')
+    assert 'mdcv' not in rep['entry_boxes'] and 'clli' not in rep['entry_boxes']
+    assert compliance.check_bytes(data, {'profile_idc': 2, 'tier': 0, 'hdr10': False}) == []
     from oracle import pixel_ref
     want = pixel_ref.scale_plane(clip.frame(2)[0], 960, 540, 10)
     assert _psnr(dec[2][0], want, 1023) > 33
+
+
+def test_upscale_hdr_source_keeps_hdr10(tmp_path):
+    w, h, n = 480, 270, 4
+    clip = SynthClip(w, h, seed=9, noise=0.0)
+    src = tmp_path / 'hdr.y4m'
+    write_y4m(src, [clip.frame(i) for i in range(n)], w, h, (30, 1))
+    (tmp_path / 'hdr.y4m.json').write_text(json.dumps({'color_primaries': 'bt2020', 'color_transfer': 'smpte2084', 'color_space': 'bt2020nc'}))
+    res = upscale.process_video(src, tmp_path, target_height=540, device=0)
+    assert res['status'] == 'SUCCESS' and res['hdr'] is True
+    assert compliance.check_bytes((tmp_path / 'hdr.mp4').read_bytes(), {'profile_idc': 2, 'hdr10': True}) == []
+
+
+def test_upscale_segments_over_devices(tmp_path):
+    """config 4's composition: one clip -> closed-GOP segments of one key-frame interval dealt round-robin to one worker per
+    entry of ``devices`` (here the same GPU twice), fused scale + Main10 encode per worker, in-order collection, ONE mux;
+    the result decodes as one stream and equals the single-worker encode of the same segments frame for frame."""
+    w, h, n = 320, 180, 70                                   # 30 fps -> keyint 30 at this size: segments 30 / 30 / 10
+    clip = SynthClip(w, h, seed=10)
+    frames = [clip.frame(i) for i in range(n)]
+    src = tmp_path / 'long.y4m'
+    write_y4m(src, frames, w, h, (30, 1))
+    ticks = []
+    res = upscale.process_video(src, tmp_path, target_height=360, devices=[0, 0], progress_callback=lambda *a: ticks.append(a))
+    assert res['status'] == 'SUCCESS' and (res['width'], res['height']) == (640, 360), res
+    rep, dec = _decode_mp4((tmp_path / 'long.mp4').read_bytes())
+    assert len(dec) == n and ticks and ticks[-1][1] == n
+    sync = rep['sync_samples']
+    assert sync[0] == 1 and 31 in sync and 61 in sync              # every segment opens with an IDR
+    from oracle import pixel_ref
+    for i in (0, 29, 30, 69):
+        assert _psnr(dec[i][0], pixel_ref.scale_plane(frames[i][0], 640, 360, 10), 1023) > 30
+
+
+@pytest.mark.parametrize('tagged_hdr', [False, True])
+def test_convert_video_10bit_y4m(tmp_path, tagged_hdr):
+    """10-bit planar source (HB_PIX_YUV420P16 with src_bit_depth = 10): without HDR tags the reference would hand libx265
+    8-bit samples (-pix_fmt yuv420p), so the ingest stage rounds to 8 bits; with HDR tags it is a Main10 encode at full depth."""
+    w, h, n = 256, 144, 6
+    clip = SynthClip(w, h, seed=12, noise=0.0)
+    f8 = [clip.frame(i) for i in range(n)]
+    rng = np.random.default_rng(3)
+    f10 = [tuple((p.astype(np.uint16) << 2) + rng.integers(0, 4, p.shape, dtype=np.uint16) for p in f) for f in f8]
+    src = tmp_path / 'ten.y4m'
+    write_y4m(src, f10, w, h, (30, 1), ten_bit=True)
+    if tagged_hdr:
+        (tmp_path / 'ten.y4m.json').write_text(json.dumps({'color_primaries': 'bt2020', 'color_transfer': 'smpte2084', 'color_space': 'bt2020nc'}))
+    res = transcoder.convert_video(src, tmp_path, encoder='b200', device=0)
+    assert res['status'] == 'SUCCESS' and res['hdr'] is tagged_hdr
+    rep, dec = _decode_mp4((tmp_path / 'ten.mp4').read_bytes())
+    assert rep['sps']['bit_depth'] == (10 if tagged_hdr else 8) and len(dec) == n
+    if tagged_hdr:
+        assert _psnr(dec[2][0], f10[2][0], 1023) > 26
+    else:
+        want = np.minimum((f10[2][0].astype(np.int32) + 2) >> 2, 255)
+        assert _psnr(dec[2][0], want, 255) > 26 and int(dec[2][0].max()) <= 255

@@ -288,3 +288,140 @@ def test_parallel_segment_streams_are_deterministic_and_decodable(ctx):
     assert got == want
     dec = fforacle.decode_hevc(got, verify_hash=True)
     assert len(dec) == seg * nseg
+
+
+@pytest.mark.parametrize('fmt,enc_depth', [('p16_10', 10), ('p010', 10), ('p16_10', 8), ('p16_12', 10)])
+def test_source_formats_match_cpu_model(ctx, fmt, enc_depth):
+    """encoder-level parity for the non-8-bit source formats: HB_PIX_YUV420P16 carrying 10- or 12-bit samples (src_bit_depth)
+    and HB_PIX_P010; the ingest stage's depth conversion ((v + round) >> shift, clamp) feeds the same samples the model gets"""
+    from hevc_b200 import encoder as E
+    w, h, n, qp = 176, 112, 4, (24, 26)
+    p = ec.b200_params(w, h, enc_depth, keyint=4, hdr10=False)
+    rng = np.random.default_rng(11)
+    src_depth = 12 if fmt == 'p16_12' else 10
+    base = ec.clip_frames(w, h, n, seed=9)
+    deep = [tuple(np.minimum((pl.astype(np.uint16) << (src_depth - 8)) + rng.integers(0, 1 << (src_depth - 8), pl.shape, dtype=np.uint16),
+                             (1 << src_depth) - 1).astype(np.uint16) for pl in f) for f in base]
+    if fmt == 'p010':
+        def pack(f):
+            y, u, v = f
+            uv = np.empty((h // 2, w), np.uint16)
+            uv[:, 0::2], uv[:, 1::2] = u << 6, v << 6
+            return np.concatenate([(y << 6).reshape(-1), uv.reshape(-1)])
+        data = np.concatenate([pack(f) for f in deep]).view(np.uint8)
+        pix, kw = E.PIX_P010, {}
+        want_in = deep
+    else:
+        data = np.concatenate([np.concatenate([pl.reshape(-1) for pl in f]) for f in deep]).view(np.uint8)
+        pix, kw = E.PIX_YUV420P16, {'src_bit_depth': src_depth}
+        sh = src_depth - enc_depth
+        want_in = [tuple(np.minimum((pl.astype(np.int32) + (1 << (sh - 1))) >> sh, (1 << enc_depth) - 1).astype(np.uint16) if sh > 0 else pl
+                         for pl in f) for f in deep]
+    from oracle import encoder_model as em
+    model = em.ModelEncoder(ec.model_params(p, qp[0], qp[1], True))
+    want = b''.join(model.encode(*f)[0] for f in want_in)
+    model.close()
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=True, keep_recon=True, rate_control=False), max_batch=4)
+    got, _ = enc.encode(data, n, fmt=pix, **kw)
+    enc.close()
+    assert got == want
+
+
+def test_rgb_and_scaled_ingest_feed_the_pixel_oracle_samples(ctx):
+    """fused ingest: BGR24 frames (matrix conversion) and a scaled 8-bit 4:2:0 source must give the encoder exactly the
+    samples oracle/pixel_ref.py defines -- checked by encoding the oracle's planes through the CPU model"""
+    from hevc_b200 import encoder as E
+    from oracle import encoder_model as em
+    from oracle import pixel_ref
+    rng = np.random.default_rng(5)
+    qp = (22, 24)
+    # ---- BGR24 -> Main10
+    w, h, n = 144, 80, 3
+    p = ec.b200_params(w, h, 10, keyint=4, hdr10=False)
+    imgs = [np.ascontiguousarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for _ in range(n)]
+    model = em.ModelEncoder(ec.model_params(p, qp[0], qp[1], True))
+    want = b''.join(model.encode(*pixel_ref.rgb_to_yuv420(im, 'bt709', 10, bgr=True))[0] for im in imgs)
+    model.close()
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=True, rate_control=False), max_batch=4)
+    got, _ = enc.encode(np.stack(imgs).reshape(n, -1), n, fmt=E.PIX_BGR24)
+    enc.close()
+    assert got == want
+    # ---- 8-bit 4:2:0 at 96x64 -> 192x128 Main10 and -> 8-bit Main (both scaler output depths), odd ratio 1.5 as well
+    for (sw, sh_, dw, dh, depth) in [(96, 64, 192, 128, 10), (96, 64, 144, 96, 8), (320, 180, 640, 360, 10)]:
+        p = ec.b200_params(dw, dh, depth, keyint=4, hdr10=False)
+        frames = ec.clip_frames(sw, sh_, n, seed=13)
+        model = em.ModelEncoder(ec.model_params(p, qp[0], qp[1], True))
+        want = b''
+        for y, u, v in frames:
+            want += model.encode(pixel_ref.scale_plane(y, dw, dh, depth), pixel_ref.scale_plane(u, dw // 2, dh // 2, depth),
+                                 pixel_ref.scale_plane(v, dw // 2, dh // 2, depth))[0]
+        model.close()
+        enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=True, rate_control=False), max_batch=4)
+        got, _ = enc.encode(E.pack_yuv420p8(frames), n, fmt=E.PIX_YUV420P8, src_size=(sw, sh_))
+        enc.close()
+        assert got == want, (sw, sh_, dw, dh, depth)
+
+
+def test_4k60_full_gop_matches_cpu_model_and_vbv(ctx):
+    """BASELINE configs[1], one whole key-frame interval plus the start of the next (122 frames, crf 19, VBV 23520 / 28224 on):
+    every byte equals the CPU model's (the model runs its CU loops on all host cores), and the ACTUAL access-unit sizes of
+    240 frames (two GOPs) keep the signalled HRD buffer from underflowing (hrd=1, reference core/utils.py:65)."""
+    from hevc_b200 import derive, encoder as E
+    from hevc_b200.probe import VideoInfo
+    from hevc_b200.synth import TorchSynthClip
+    from tests.test_oracle_encoder import vbv_underflows
+    info = VideoInfo(3840, 2160, 60.0, 'bt2020', 'smpte2084', 'bt2020nc', 'yuv420p', '', '', 0, True, None, None, 5.0)
+    p = derive.derive_b200_params(info)
+    clip = TorchSynthClip(3840, 2160, seed=5, device='cuda:0')
+    n_model, n = 122, 240
+    enc = E.B200Encoder(ctx, E.to_c_params(p, hash_sei=False), max_batch=120)
+    stream, stats = b'', []
+    for s in range(0, n, 60):
+        fr = clip.frames(s, 60).cpu().numpy()
+        out, st = enc.encode_delayed(fr, 60)
+        stream += out
+        stats += st
+    out, st = enc.flush()
+    stream += out
+    stats += st
+    enc.close()
+    assert len(stats) == n and [i for i, s in enumerate(stats) if s.is_idr] == [0, 120]
+    assert vbv_underflows([8 * s.bytes for s in stats], p.vbv_maxrate_kbps, p.vbv_bufsize_kbit, 60.0) == []
+    lw, cw = 3840 * 2160, 1920 * 1080
+    qi, qp = E.crf_to_qp(p.crf)
+    from oracle import encoder_model as em
+    model = em.ModelEncoder(ec.model_params(p, qi, qp, False, rate_control=True))
+    pos = 0
+    for i in range(n_model):
+        f = clip.frames(i, 1).cpu().numpy()[0]
+        au, minfo = model.encode(*(a.astype(np.uint16) << 2 for a in (f[:lw].reshape(2160, 3840), f[lw:lw + cw].reshape(1080, 1920),
+                                                                      f[lw + cw:].reshape(1080, 1920))))
+        assert stream[pos:pos + stats[i].bytes] == au, f'access unit {i} differs (model qp {minfo.qp}, gpu qp {stats[i].qp})'
+        pos += stats[i].bytes
+    model.close()
+
+
+def hard_cut_frames(w, h, n, cut, seed=21, noise=2.0):
+    """two unrelated synthetic scenes joined at frame `cut`"""
+    from hevc_b200.synth import SynthClip
+    a, b = SynthClip(w, h, seed=seed, noise=noise), SynthClip(w, h, seed=seed + 100, noise=noise)
+    return [a.frame(i) if i < cut else tuple(np.ascontiguousarray(p[::-1, ::-1]) for p in b.frame(i + 37)) for i in range(n)]
+
+
+@pytest.mark.parametrize('depth', [8, 10])
+def test_hard_cut_clip_matches_cpu_model(ctx, depth):
+    """a clip with a scene change in the middle of a GOP: same bytes as the model, decodable, and the frame after the cut is
+    not allowed to fall apart (intra CUs / scene-cut key frame instead of predicting from an unrelated picture)"""
+    from oracle import fforacle
+    w, h, n, cut = 320, 192, 16, 9
+    p = ec.b200_params(w, h, depth, keyint=12)
+    frames = hard_cut_frames(w, h, n, cut)
+    m_stream, m_aus, m_recs, _ = ec.run_model(p, frames, 26, 28, hash_sei=True)
+    g_stream, g_recs, _ = _gpu_encode(ctx, p, frames, (26, 28), batch=8, split=[8, 8])
+    assert g_stream == m_stream
+    dec = fforacle.decode_hevc(g_stream, verify_hash=True)
+    assert len(dec) == n
+    sh = depth - 8
+    src = frames[cut][0].astype(np.float64) * (1 << sh)
+    mse = np.mean((dec[cut][0].astype(np.float64) - src) ** 2)
+    assert 10 * np.log10(((255 << sh) ** 2) / mse) > 30

@@ -72,3 +72,31 @@ def test_hdr10_headers_present():
     assert types[:4] == [35, 32, 33, 34]            # AUD, VPS, SPS, PPS
     assert types.count(39) >= 5                     # buffering period, pic timing x2, mastering display, content light level
     assert 19 in types and 1 in types and 40 in types
+
+
+def vbv_underflows(au_bits, maxrate_kbps, bufsize_kbit, fps):
+    """Leaky-bucket check of ACTUAL access-unit sizes against the HRD the stream signals (Annex C, VBR / cbr_flag = 0): the
+    CPB fills at vbv-maxrate up to vbv-bufsize, the first removal happens at initial_cpb_removal_delay = 0.9 x bufsize / maxrate
+    (what the buffering-period SEI carries), one access unit leaves per frame interval.  -> [(frame, missing bits)]"""
+    B, per = bufsize_kbit * 1000.0, maxrate_kbps * 1000.0 / fps
+    fullness, bad = 0.9 * B, []
+    for i, bits in enumerate(au_bits):
+        if bits > fullness + 1e-6:
+            bad.append((i, bits - fullness))
+        fullness = min(B, max(0.0, fullness - bits) + per)
+    return bad
+
+
+@pytest.mark.parametrize('depth,kbps,qp', [(8, 300, 20), (10, 250, 20), (8, 120, 16)])
+def test_vbv_conformance_of_actual_sizes(depth, kbps, qp):
+    """wherever hrd=1 is signalled (reference core/utils.py:65) the real access-unit sizes -- not the controller's estimates --
+    must keep the decoder buffer from underflowing, over several GOPs, at caps that really bind"""
+    w, h, n, keyint = 320, 192, 40, 12
+    stream, _, infos = _run(w, h, depth, n, qp, keyint=keyint, seed=7, rate_control=1, vbv_maxrate_kbps=kbps,
+                            vbv_bufsize_kbit=int(kbps * 1.2), hrd=1)
+    assert max(i.qp for i in infos) > qp + 4                      # the cap binds
+    bits = [8 * i.bytes for i in infos]
+    assert vbv_underflows(bits, kbps, int(kbps * 1.2), 30.0) == []
+    # the estimate the controller steers by tracks the real size
+    tot_est = sum(i.est_bits16 for i in infos) / 16.0
+    assert abs(tot_est - sum(bits)) / sum(bits) < 0.15

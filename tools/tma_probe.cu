@@ -62,6 +62,7 @@ int main(int argc, char **argv)
     printf("entry point: %s q=%d fn=%p\n", cudaGetErrorString(e), (int)q, fn);
     CUtensorMap map;
     const int var = argc > 2 ? atoi(argv[2]) : 0;
+    const int X = argc > 3 ? atoi(argv[3]) : 37;
     cuuint64_t dims[2] = {W, H}; const cuuint64_t strides[1] = {W * 2}; cuuint32_t box[2] = {32, 28}; const cuuint32_t es[2] = {1, 1};
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_UINT16;
     CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
@@ -74,18 +75,18 @@ int main(int argc, char **argv)
     printf("encode rc=%d\n", (int)rc);
     CUtensorMap *gmap; cudaMalloc(&gmap, sizeof(map)); cudaMemcpy(gmap, &map, sizeof(map), cudaMemcpyHostToDevice);
     const int mode = argc > 1 ? atoi(argv[1]) : 1;
-    if (mode == 0) probe<0><<<1, 32>>>(map, gmap, 37, 11, out, status);
-    else if (mode == 1) probe<1><<<1, 32>>>(map, gmap, 37, 11, out, status);
-    else if (mode == 2) probe<2><<<1, 32>>>(map, gmap, 37, 11, out, status);
-    else if (mode == 3) probe<3><<<1, 32>>>(map, gmap, 37, 11, out, status);
-    else if (mode == 4) probe<4><<<1, 32>>>(map, gmap, 37, 11, out, status);
-    else probe<5><<<1, 32>>>(map, gmap, 37, 11, out, status);
+    if (mode == 0) probe<0><<<1, 32>>>(map, gmap, X, 11, out, status);
+    else if (mode == 1) probe<1><<<1, 32>>>(map, gmap, X, 11, out, status);
+    else if (mode == 2) probe<2><<<1, 32>>>(map, gmap, X, 11, out, status);
+    else if (mode == 3) probe<3><<<1, 32>>>(map, gmap, X, 11, out, status);
+    else if (mode == 4) probe<4><<<1, 32>>>(map, gmap, X, 11, out, status);
+    else probe<5><<<1, 32>>>(map, gmap, X, 11, out, status);
     e = cudaDeviceSynchronize();
     printf("mode %d kernel: %s\n", mode, cudaGetErrorString(e));
     int st[2]; std::vector<uint16_t> o(28 * 32);
     cudaMemcpy(st, status, 8, cudaMemcpyDeviceToHost); cudaMemcpy(o.data(), out, 28 * 32 * 2, cudaMemcpyDeviceToHost);
     int bad = 0;
-    for (int r = 0; r < 28; r++) for (int c = 0; c < 32; c++) bad += o[r * 32 + c] != host[(11 + r) * W + 37 + c];
-    printf("done=%d spins=%d mismatches=%d first=%d expect=%d\n", st[0], st[1], bad, o[0], host[11 * W + 37]);
+    for (int r = 0; r < 28; r++) for (int c = 0; c < 32; c++) bad += o[r * 32 + c] != host[(11 + r) * W + X + c];
+    printf("done=%d spins=%d mismatches=%d first=%d expect=%d\n", st[0], st[1], bad, o[0], host[11 * W + X]);
     return 0;
 }
