@@ -85,6 +85,7 @@ HB_HD bool cu_avail(const Geom &g, int cx, int cy, int nx, int ny)
 // device from the size *estimates* of earlier frames, so the frame chain never waits for the entropy coder or the host.
 struct FrameCtl {
     int qp, lambda, is_idr, redo;
+    int poc, scene_cut;            // picture order count decided on the device (scene cuts move the key-frame cadence)
     QuantParam qy, qc;
     unsigned long long est16;      // size estimate accumulated by the frame kernel, 1/16 bit
 };
@@ -94,7 +95,16 @@ struct RcState {
     int have[2], qp_prev[2];
     long long est_prev[2];
     int qp_i, qp_p, rate_control, bit_depth;
+    // frame-type state: key frames every `keyint` frames, earlier at a detected scene cut once `min_keyint` frames have passed
+    int keyint, min_keyint, scenecut, poc, started;
 };
+
+// scene-cut measures of one frame, accumulated by the coarse motion search (oracle/hevc_encode.c coarse_search / scene_cut)
+struct SceneStat {
+    unsigned long long inter, intra;
+};
+
+HB_HD bool scene_cut(const SceneStat &s, long long n_samples) { return (long long)s.inter >= 5 * n_samples && 2 * s.inter >= 3 * s.intra; }
 
 HB_HD long long rc_pow2_sixth(int k)      // round(65536 * 2^(k/6))
 {

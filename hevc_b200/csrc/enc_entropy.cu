@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_modes(ModeParams p)
     const CuInfo me = p.cus[idx];
     CuSyntax out;
     out.merge_idx = -1; out.skip = 0; out.mvp_idx = 0; out.pad = 0; out.mvdx = 0; out.mvdy = 0;
-    if (p.is_intra) {
+    if (p.ctl->is_idr || me.pred_mode == 0) {        // intra CU (I slice, or intra CU of a P slice): most-probable-mode signalling
         int a = 1, b = 1;
         if (cu_avail(g, cx, cy, cx - 1, cy) && p.cus[idx - 1].pred_mode == 0) a = p.cus[idx - 1].intra_mode;
         if ((cy & 1) && cu_avail(g, cx, cy, cx, cy - 1) && p.cus[idx - g.cuw].pred_mode == 0) b = p.cus[idx - g.cuw].intra_mode;
@@ -480,7 +480,13 @@ __device__ __forceinline__ void binarise_header(EntropyWarpScratch &s, int k, co
     out[nb++] = bin_ctx(CX_SPLIT_CU, 0);
     const int cb_y = cu.cbf & 1, cb_u = (cu.cbf >> 1) & 1, cb_v = (cu.cbf >> 2) & 1;
     bool coded_residual = true;
-    if (!h.is_intra) {
+    const bool intra_cu = h.is_intra || cu.pred_mode == 0;
+    if (!h.is_intra && intra_cu) {
+        // intra CU in a P slice: cu_skip_flag = 0, pred_mode_flag = 1 (no part_mode: the CU is larger than the minimum size)
+        out[nb++] = bin_ctx(CX_SKIP + (h.skip_l ? 1 : 0) + (h.skip_a ? 1 : 0), 0);
+        out[nb++] = bin_ctx(CX_PRED_MODE, 1);
+    }
+    if (!intra_cu) {
         out[nb++] = bin_ctx(CX_SKIP + (h.skip_l ? 1 : 0) + (h.skip_a ? 1 : 0), sy.skip);
         if (sy.merge_idx >= 0) {
             if (!sy.skip) {
@@ -532,7 +538,7 @@ __device__ __forceinline__ void binarise_header(EntropyWarpScratch &s, int k, co
     if (coded_residual) {
         out[nb++] = bin_ctx(CX_CBF_CHROMA, cb_u);
         out[nb++] = bin_ctx(CX_CBF_CHROMA, cb_v);
-        if (h.is_intra || cb_u || cb_v) out[nb++] = bin_ctx(CX_CBF_LUMA + 1, cb_y);
+        if (intra_cu || cb_u || cb_v) out[nb++] = bin_ctx(CX_CBF_LUMA + 1, cb_y);
     }
     s.nhdr[k] = (uint8_t)nb;
 }
@@ -600,7 +606,8 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
     volatile int *row_ready = fr.row_ready;                       // [ctuh], zeroed before the launch
     EntropyWarpScratch &s = g_ews[warp];
     const int w = warp;
-    const int init_type = fr.is_intra ? 0 : 1;
+    const int slice_intra = fr.ctl->is_idr;                       // slice type is decided on the device (scene cuts)
+    const int init_type = slice_intra ? 0 : 1;
 
     const int row = blockIdx.x * kEntropyWarps + warp;
     if (row >= g.ctuh) return;
@@ -657,7 +664,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
                 CuHeaderIn h;
                 h.cu = s.cu[slot][k].info;
                 h.sy = s.cu[slot][k].syn;
-                h.is_intra = fr.is_intra;
+                h.is_intra = slice_intra;
                 h.first_in_ctu = k == 0;
                 h.split_flag_coded = 32 * x + 32 <= g.wc && 32 * row + 32 <= g.hc;
                 h.split_inc = (x > 0 ? 1 : 0) + (row > 0 ? 1 : 0);

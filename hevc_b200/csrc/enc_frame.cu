@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
     __shared__ uint32_t curw[16];
     __shared__ uint32_t win[4][kCoarseCopyWords];
     __shared__ unsigned long long best[4];
+    __shared__ unsigned grad[2][2];
     const Geom &g = p.g;
     const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw, f = blockIdx.y;
     const uint8_t *dcur = p.ds + (size_t)(f + 1) * p.ds_frame_stride, *dprev = p.ds + (size_t)f * p.ds_frame_stride;
@@ -193,6 +194,13 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
         }
     }
     __syncthreads();
+    if (tid < 64) {         // intra measure of the scene-cut detector: horizontal / vertical neighbour differences inside the block
+        const uint8_t *cb = reinterpret_cast<const uint8_t *>(curw);
+        const int i = tid & 7, j = tid >> 3, v = cb[tid];
+        const unsigned hs = __reduce_add_sync(0xffffffffu, i ? (unsigned)abs(v - (int)cb[tid - 1]) : 0u);
+        const unsigned vs = __reduce_add_sync(0xffffffffu, j ? (unsigned)abs(v - (int)cb[tid - 8]) : 0u);
+        if ((tid & 31) == 0) { grad[tid >> 5][0] = hs; grad[tid >> 5][1] = vs; }
+    }
     uint32_t c[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) c[t] = curw[t];
@@ -222,6 +230,9 @@ __global__ void __launch_bounds__(128) k_coarse(CoarseParams p)
         int16_t *out = p.cmv + ((size_t)f * g.ctuw * g.ctuh + blockIdx.x) * 2;
         out[0] = (int16_t)(cbest % 25 - kCmeRange);
         out[1] = (int16_t)(cbest / 25 - kCmeRange);
+        const unsigned hs = grad[0][0] + grad[1][0], vs = grad[0][1] + grad[1][1];
+        atomicAdd(&p.scene[f].inter, b >> 10);
+        atomicAdd(&p.scene[f].intra, (unsigned long long)min(hs, vs));
     }
 }
 
@@ -437,7 +448,7 @@ __device__ __forceinline__ MV unpack_mv(uint32_t v) { return MV{(int)(int16_t)(v
 // neighbours (A1, B1, B0, A0, B2) held after the previous pass and with the zero vector (oracle/hevc_encode.c, "merge-aware
 // passes").  The window in `s.win` is centred on the own vector; candidates further than +-2 integer samples are not tried.
 __device__ __forceinline__ void merge_decide(const InterParams &p, WarpScratch &s, int cx, int cy, int lambda, int wx0, int wy0,
-                                             const int (&st)[8], int lane, MV &best, int &bsatd)
+                                             const int (&st)[8], int lane, MV &best, int &bsatd, int &bcost_out)
 {
     const Geom &g = p.g;
     const int x0 = cx * 16, y0 = cy * 16, idx = cy * g.cuw + cx;
@@ -480,6 +491,7 @@ __device__ __forceinline__ void merge_decide(const InterParams &p, WarpScratch &
         const int cost = sd + ((lambda * 2) >> 8);
         if (cost < bcost) { bcost = cost; best = c; bsatd = sd; }
     }
+    bcost_out = bcost;
 }
 
 // pass 1 of the motion search: per CU, integer candidates -> 5x5 -> half / quarter sample; writes the vector field and its SATD
@@ -490,7 +502,7 @@ __global__ void __launch_bounds__(128, 8) k_me(const __grid_constant__ InterPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw;
     const int cx = 2 * tx + (warp & 1), cy = 2 * ty + (warp >> 1);
-    if (cx >= g.cuw || cy >= g.cuh)
+    if (cx >= g.cuw || cy >= g.cuh || p.ctl->is_idr)        // (frame types are decided on the device: key frames skip the inter kernels)
         return;
     WarpScratch &s = scratch[warp];
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
@@ -629,7 +641,7 @@ __global__ void __launch_bounds__(128, 7) k_merge(const __grid_constant__ InterP
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw;
     const int cx = 2 * tx + (warp & 1), cy = 2 * ty + (warp >> 1);
-    if (cx >= g.cuw || cy >= g.cuh)
+    if (cx >= g.cuw || cy >= g.cuh || p.ctl->is_idr)        // (frame types are decided on the device: key frames skip the inter kernels)
         return;
     WarpScratch &s = scratch[warp];
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
@@ -646,8 +658,8 @@ __global__ void __launch_bounds__(128, 7) k_merge(const __grid_constant__ InterP
 #pragma unroll
     for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];
     MV best;
-    int bsatd;
-    merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd);
+    int bsatd, bcost;
+    merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd, bcost);
     if (lane == 0) {
         p.mv_out[cy * g.cuw + cx] = pack_mv(best);
         p.satd_out[cy * g.cuw + cx] = bsatd;
@@ -662,7 +674,7 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x % g.ctuw, ty = blockIdx.x / g.ctuw;
     const int cx = 2 * tx + (warp & 1), cy = 2 * ty + (warp >> 1);
-    if (cx >= g.cuw || cy >= g.cuh)
+    if (cx >= g.cuw || cy >= g.cuh || p.ctl->is_idr)        // (frame types are decided on the device: key frames skip the inter kernels)
         return;
     WarpScratch &s = scratch[warp];
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.mbar), win_smem = (uint32_t)__cvta_generic_to_shared(&s.win[0][0]);
@@ -691,8 +703,21 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
     for (int k = 0; k < 8; k++) st[k] = s.src[(lane & 1) * 8 + k][lane >> 1];
     MV best;
     {
-        int bsatd;
-        merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd);
+        int bsatd, bcost;
+        merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd, bcost);
+        // Intra CU in a P frame (oracle/hevc_encode.c): the best intra prediction searched on source neighbours, plus its
+        // signalling, must beat the final inter choice by a quarter; the wavefront kernel then reconstructs the CU
+        if (p.intra_best) {
+            const int icost = p.intra_best[cy * g.cuw + cx] + ((lambda * 12) >> 8);
+            if ((long long)icost * 4 < (long long)bcost * 3) {
+                if (lane == 0) {
+                    CuInfo ci;
+                    ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0; ci.skip = 0; ci.mvx = 0; ci.mvy = 0;
+                    p.cus[cy * g.cuw + cx] = ci;
+                }
+                return;
+            }
+        }
     }
     // ---- luma: predict, transform, quantise, reconstruct
     interp_cols(s, (best.x >> 2) - wx0, (best.y >> 2) - wy0, best.x & 3, best.y & 3, bd, lane, pv);
@@ -1104,6 +1129,7 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
     const Geom &g = p.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, bd = g.bit_depth, maxv = (1 << bd) - 1;
     IntraSearchScratch &s = scratch[warp];
+    if (!p.ctl->is_idr && !p.intra_in_p) return;
     const int nwarps = gridDim.x * (kIntraSearchThreads / 32);
     for (int cu = blockIdx.x * (kIntraSearchThreads / 32) + warp; cu < g.cuw * g.cuh; cu += nwarps) {
         const int cx = cu % g.cuw, cy = cu / g.cuw, x0 = cx * 16, y0 = cy * 16;
@@ -1130,6 +1156,7 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
         for (int y = 0; y < 4; y++)
 #pragma unroll
             for (int x = 0; x < 4; x++) sv[y][x] = s.src[sy + y][sx + x];
+        int cbest = 0x7fffffff;
 #pragma unroll 1
         for (int m0 = 0; m0 < 36; m0 += 2) {
             const int mode = min(m0 + (lane >> 4), 34);          // the upper half idles on mode 34 twice in the last round
@@ -1144,26 +1171,56 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
 #pragma unroll
             for (int o = 8; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
             if (sb == 0 && m0 + (lane >> 4) < 35) p.mode_cost[(size_t)cu * 35 + mode] = c;
+            cbest = min(cbest, c);
         }
+        cbest = min(cbest, __shfl_xor_sync(0xffffffffu, cbest, 16));
+        if (lane == 0) p.intra_best[cu] = cbest;
         __syncwarp();
     }
 }
 
-// one CTA per CTU row; row r may process CTU x once row r-1 has finished CTU x+1 (top-right dependency)
+// one CTA per CTU row; row r may process CTU x once row r-1 has finished CTU x+1 (top-right dependency).
+// I slices: every CU.  P slices: only the CUs k_inter marked intra -- the row's CTUs that hold such a CU are listed up front and
+// progress[] jumps from one listed CTU to the next (everything between is final since k_inter), so rows only wait on real
+// dependencies and a frame without intra CUs costs one scan.
 __global__ void __launch_bounds__(kIntraReconThreads) k_intra(IntraParams p)
 {
     __shared__ IntraScratch s;
+    __shared__ uint8_t has_intra[256];
+    __shared__ short ctu_list[256];
+    __shared__ int n_list;
     const Geom &g = p.g;
-    const int r = blockIdx.x;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const bool slice_intra = p.ctl->is_idr != 0;
     if (p.second_pass && !p.ctl->redo)
         return;
-    for (int i = threadIdx.x; i < 256; i += kIntraReconThreads) s.m16[i] = (int16_t)tmat_rt(16, i >> 4, i & 15);
-    for (int i = threadIdx.x; i < 64; i += kIntraReconThreads) s.m8[i] = (int16_t)tmat_rt(8, i >> 3, i & 7);
-    if (threadIdx.x == 0) { s.lambda = p.ctl->lambda; s.qy = p.ctl->qy; s.qc = p.ctl->qc; }
+    if (!slice_intra && !p.intra_in_p)
+        return;
+    for (int x = tid; x < g.ctuw; x += kIntraReconThreads) {
+        bool any = slice_intra;
+        for (int k = 0; k < 4 && !any; k++) {
+            const int cx = 2 * x + (k & 1), cy = 2 * r + (k >> 1);
+            any = cx < g.cuw && cy < g.cuh && p.cus[cy * g.cuw + cx].pred_mode == 0;
+        }
+        has_intra[x] = any;
+    }
+    for (int i = tid; i < 256; i += kIntraReconThreads) s.m16[i] = (int16_t)tmat_rt(16, i >> 4, i & 15);
+    for (int i = tid; i < 64; i += kIntraReconThreads) s.m8[i] = (int16_t)tmat_rt(8, i >> 3, i & 7);
+    if (tid == 0) { s.lambda = p.ctl->lambda; s.qy = p.ctl->qy; s.qc = p.ctl->qc; }
     __syncthreads();
-    for (int x = 0; x < g.ctuw; x++) {
+    if (tid == 0) {
+        int n = 0;
+        for (int x = 0; x < g.ctuw; x++)
+            if (has_intra[x]) ctu_list[n++] = (short)x;
+        n_list = n;
+        atomicExch(p.progress + r, n ? (int)ctu_list[0] : g.ctuw);
+    }
+    __syncthreads();
+    const int n = n_list;
+    for (int li = 0; li < n; li++) {
+        const int x = ctu_list[li];
         if (r > 0) {
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 const int need = min(x + 2, g.ctuw);
                 while (*reinterpret_cast<volatile int *>(p.progress + r - 1) < need)
                     __nanosleep(64);
@@ -1171,15 +1228,21 @@ __global__ void __launch_bounds__(kIntraReconThreads) k_intra(IntraParams p)
             __syncthreads();
             __threadfence();
         }
+        if (tid == 0 && (li == 0 || ctu_list[li - 1] != x - 1)) { s.left_mode[0] = 1; s.left_mode[1] = 1; }   // inter (or no) CUs to the left: DC
         for (int k = 0; k < 4; k++) {
             const int cx = 2 * x + (k & 1), cy = 2 * r + (k >> 1);
-            if (cx < g.cuw && cy < g.cuh)
+            if (cx >= g.cuw || cy >= g.cuh) continue;
+            if (slice_intra || p.cus[cy * g.cuw + cx].pred_mode == 0) {
                 intra_cu(p, s, cx, cy);
+            } else if (tid == 0) {         // an inter CU counts as DC in the most-probable-mode derivation of its neighbours
+                s.left_mode[k >> 1] = 1;
+                if (!(k >> 1)) s.top_mode[k & 1] = 1;
+            }
         }
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0)
-            atomicExch(p.progress + r, x + 1);
+        if (tid == 0)
+            atomicExch(p.progress + r, li + 1 < n ? (int)ctu_list[li + 1] : g.ctuw);
     }
 }
 
@@ -1290,15 +1353,20 @@ cudaError_t upload_inter_constants(cudaStream_t st)
 
 // ================================================================================================ rate control steps
 // single-thread kernels: close the books of the frame that just finished and choose the QP of the next one
-__global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr)
+__global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int force_idr, const SceneStat *scene, long long ds_samples)
 {
     if (threadIdx.x || blockIdx.x) return;
     RcState s = *rc;
     if (done) rc_update(s, done->is_idr, done->qp, (long long)done->est16);
     if (next) {
+        // frame type (oracle/hevc_encode.c orc_enc_frame): forced / first frame / keyint reached / scene cut past min-keyint
+        const int cut = s.started && s.scenecut && scene && scene_cut(*scene, ds_samples) && s.poc + 1 >= s.min_keyint;
+        const int idr = force_idr || !s.started || s.poc + 1 >= s.keyint || cut;
+        s.poc = idr ? 0 : s.poc + 1;
+        s.started = 1;
         FrameCtl c;
-        ctl_set_qp(c, rc_pick_qp(s, next_is_idr), next_is_idr, s.bit_depth);
-        c.redo = 0;
+        ctl_set_qp(c, rc_pick_qp(s, idr), idr, s.bit_depth);
+        c.redo = 0; c.poc = s.poc; c.scene_cut = cut;
         *next = c;
     }
     *rc = s;

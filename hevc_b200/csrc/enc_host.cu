@@ -278,7 +278,9 @@ struct hb_encoder {
     Planes rec[2];
     uint8_t *ds = nullptr;            // [max_batch + 1][dsh * dsw] quarter-resolution planes (8 MSBs)
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
-    int *mode_cost = nullptr;         // [cus][35] intra mode search result of the key frame in flight
+    int *mode_cost = nullptr;         // [cus][35] intra mode search result of the frame in flight
+    int *intra_best = nullptr;        // [cus] best of those per CU
+    SceneStat *scene = nullptr;       // [max_batch] scene-cut measures of the batch in flight (frame chain is serial: one array)
     uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
     int *satdf[2] = {nullptr, nullptr};
     size_t staging_bytes = 0;
@@ -286,13 +288,12 @@ struct hb_encoder {
     size_t csc_tmp_bytes = 0;
     int *progress = nullptr;
     RcState *rc_dev = nullptr;
-    bool rc_have_idr = false;
     const char *trace_path = nullptr;
     size_t packed_cap = 0;
     // stream state
     int cur = 0;                      // reconstruction buffer being written
     long long frame_no = 0;
-    int poc = 0, since_bp = 0;
+    int since_bp = 0;
     std::atomic<int> stop{0}, done{0};
     cudaStream_t st_copy = nullptr;
     cudaStream_t st_entropy[kEntropyStreams] = {};   // CABAC launches round-robin over these, concurrent with the frame chain
@@ -377,29 +378,22 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
     {
         if (e->stop.load()) return hb_fail(ctx, HB_ERR_STOPPED, "%s", "stopped");
         HB_CUDA(ctx, cudaEventRecord(B.ev[0], st));
-        // ---- frame types of the batch (pure host state) and the entropy-stage descriptors
+        // ---- frame types are decided on the device (k_rc_step: key-frame cadence + scene cuts) and read back with the frame
+        //      controls; the host only knows which frames it FORCES to be key frames (first of the stream / of a segment)
         B.n = n; B.forced_first = force_first; B.first_frame_no = e->frame_no;
         B.is_idr.assign(n, 0); B.qps.assign(n, 0); B.pocs.assign(n, 0);
-        std::vector<int> &is_idr = B.is_idr, &pocs = B.pocs;
-        {
-            int poc = e->poc;
-            long long fno = e->frame_no;
-            for (int i = 0; i < n; i++, fno++) {
-                const bool idr = (force_first && i == 0) || fno == 0 || poc + 1 >= p.keyint;
-                poc = idr ? 0 : poc + 1;
-                is_idr[i] = idr; pocs[i] = poc;
-            }
-            e->poc = poc;
-        }
+        std::vector<int> &is_idr = B.is_idr;
+        for (int i = 0; i < n; i++) is_idr[i] = (force_first && i == 0) || e->frame_no + i == 0;      // forced key frames
         std::vector<EntropyFrame> ef(n);
         for (int i = 0; i < n; i++) {
             FrameSlot &s = B.slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
-            ef[i].is_intra = is_idr[i]; ef[i].ctl = B.ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
+            ef[i].ctl = B.ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
             ef[i].trace = B.trace_dev ? B.trace_dev + (size_t)i * g.ctuh * 2 : nullptr;
         }
         HB_CUDA(ctx, cudaMemcpyAsync(B.eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
         HB_CUDA(ctx, cudaMemsetAsync(B.overflow, 0, sizeof(int), st));
+        HB_CUDA(ctx, cudaMemsetAsync(e->scene, 0, sizeof(SceneStat) * n, st));
         HB_CUDA(ctx, cudaMemsetAsync(B.row_ready_all, 0, sizeof(int) * (size_t)n * g.ctuh, st));
         // (the set's staging buffer and sync areas are free: its previous batch has been drained)
         HB_CUDA(ctx, cudaEventRecord(B.ev_misc[0], st));
@@ -515,41 +509,33 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
             // coarse motion search for the whole chunk in one launch (source-based, independent of the reconstruction chain)
             {
                 CoarseParams cp;
-                cp.g = g; cp.ds = e->ds + (size_t)c0 * ds_stride; cp.ds_frame_stride = ds_stride; cp.cmv = e->cmv + (size_t)c0 * nctu * 2;
+                cp.g = g; cp.ds = e->ds + (size_t)c0 * ds_stride; cp.ds_frame_stride = ds_stride; cp.cmv = e->cmv + (size_t)c0 * nctu * 2; cp.scene = e->scene + c0;
                 k_coarse<<<dim3(nctu, cn), 128, 0, st>>>(cp);
                 HB_LAUNCHED(ctx);
             }
             // frame chain
             for (int i = c0; i < c0 + cn; i++) {
-                const bool idr = is_idr[i] != 0;
+                const bool forced = is_idr[i] != 0;
+                const bool first_of_stream = e->frame_no == 0;
                 FrameSlot &s = B.slot[i];
                 const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
-                // rate control on the device: account for the previous frame, choose this frame's QP
-                k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? B.ctl_dev + i - 1 : nullptr, B.ctl_dev + i, idr ? 1 : 0);
+                // rate control + frame type on the device: account for the previous frame, choose this frame's type and QP
+                k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? B.ctl_dev + i - 1 : nullptr, B.ctl_dev + i, forced ? 1 : 0, e->scene + i,
+                                            (long long)nctu * 64);
                 HB_LAUNCHED(ctx);
-                if (idr) HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+                HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[2 * i], st));
-                if (idr) {
-                    IntraParams ip;
-                    ip.g = g; ip.src = s.src; ip.rec = rec; ip.cus = s.cus; ip.coefs = s.coefs; ip.progress = e->progress;
-                    ip.ctl = B.ctl_dev + i; ip.second_pass = 0; ip.mode_cost = e->mode_cost;
-                    k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(ip);
-                    HB_LAUNCHED(ctx);
-                    k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(ip);
-                    HB_LAUNCHED(ctx);
-                    if (p.rate_control && !e->rc_have_idr) {     // first key frame of the stream: second try if it overshot
-                        k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, B.ctl_dev + i);
-                        HB_LAUNCHED(ctx);
-                        HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
-                        ip.second_pass = 1;
-                        k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(ip);
-                        HB_LAUNCHED(ctx);
-                    }
-                    e->rc_have_idr = true;
-                } else {
+                // Every frame gets both kernel families; each kernel looks at the frame type in its control block and returns
+                // at once when it does not apply (key frame <-> inter kernels), so nothing waits for the host.
+                IntraParams np;
+                np.g = g; np.src = s.src; np.rec = rec; np.cus = s.cus; np.coefs = s.coefs; np.progress = e->progress;
+                np.ctl = B.ctl_dev + i; np.second_pass = 0; np.mode_cost = e->mode_cost; np.intra_best = e->intra_best;
+                np.intra_in_p = p.intra_in_p;
+                if (!forced) {
                     InterParams ip;
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
                     ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = B.ctl_dev + i;
+                    ip.intra_best = p.intra_in_p ? e->intra_best : nullptr;
                     // motion search, then two merge-aware passes over the field (the second one inside k_inter)
                     ip.mv_in = nullptr; ip.satd_in = nullptr; ip.mv_out = e->mvf[0]; ip.satd_out = e->satdf[0];
                     static const int xs = getenv("HB_DEBUG_EXTRA_SMEM") ? atoi(getenv("HB_DEBUG_EXTRA_SMEM")) : 0;      // occupancy experiments
@@ -559,8 +545,24 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                     ip.mv_in = e->mvf[0]; ip.satd_in = e->satdf[0]; ip.mv_out = e->mvf[1]; ip.satd_out = e->satdf[1];
                     k_merge<<<nctu, 128, xs, st>>>(ip);
                     HB_LAUNCHED(ctx);
+                    k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(np);
+                    HB_LAUNCHED(ctx);
                     ip.mv_in = e->mvf[1]; ip.satd_in = e->satdf[1]; ip.mv_out = nullptr; ip.satd_out = nullptr;
                     k_inter<<<nctu, 128, xs, st>>>(ip);
+                    HB_LAUNCHED(ctx);
+                } else {
+                    if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev_me[i], st));
+                    k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(np);
+                    HB_LAUNCHED(ctx);
+                }
+                k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(np);
+                HB_LAUNCHED(ctx);
+                if (p.rate_control && first_of_stream) {     // first key frame of the stream: second try if it overshot
+                    k_rc_redo<<<1, 32, 0, st>>>(e->rc_dev, B.ctl_dev + i);
+                    HB_LAUNCHED(ctx);
+                    HB_CUDA(ctx, cudaMemsetAsync(e->progress, 0, sizeof(int) * g.ctuh, st));
+                    np.second_pass = 1;
+                    k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(np);
                     HB_LAUNCHED(ctx);
                 }
                 if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev[2 * i + 1], st));
@@ -587,10 +589,10 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                     }
                 }
                 ModeParams mp;
-                mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.is_intra = idr;
+                mp.g = g; mp.cus = s.cus; mp.syn = s.syn; mp.ctl = B.ctl_dev + i;
                 k_modes<<<(ncu + 255) / 256, 256, 0, st>>>(mp);
                 HB_LAUNCHED(ctx);
-                if (idr) HB_TRY(launch_entropy(e, B, i, 1, B.ev_chunk[kMaxChunks + chunk]));
+                if (forced) HB_TRY(launch_entropy(e, B, i, 1, B.ev_chunk[kMaxChunks + chunk]));
                 e->cur = 1 - e->cur;
                 e->frame_no++;
                 // last chunk of the batch: hand its frames to CABAC in shrinking groups (.., 2, 1, 1), so that when the chain
@@ -628,7 +630,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 HB_CUDA(ctx, cudaEventRecord(B.ev_off[grp], e->st_drain));
             }
         }
-        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, B.ctl_dev + n - 1, nullptr, 0);
+        k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, B.ctl_dev + n - 1, nullptr, 0, nullptr, 0);
         HB_LAUNCHED(ctx);
         // the last frame's quarter-resolution plane becomes slot 0 (the predecessor) of the next batch / call
         HB_CUDA(ctx, cudaMemcpyAsync(e->ds, e->ds + (size_t)n * ds_stride, ds_stride * sizeof(uint8_t), cudaMemcpyDeviceToDevice, st));
@@ -660,6 +662,7 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
         const uint32_t *goff = B.offsets_host + (size_t)f0 * g.ctuh + grp;
         const uint8_t *gpay = B.packed_host + (size_t)f0 * e->frame_cap;
         HB_CUDA(ctx, cudaEventSynchronize(B.ev_off[grp]));
+        for (int i = f0; i < f1; i++) { qps[i] = B.ctl_host[i].qp; is_idr[i] = B.ctl_host[i].is_idr; pocs[i] = B.ctl_host[i].poc; }
         {
             const uint32_t total = goff[(size_t)(f1 - f0) * g.ctuh];
             if (total > (size_t)(f1 - f0) * e->frame_cap) return hb_fail(ctx, HB_ERR_SPACE, "%s", "packed bitstream exceeds the download buffer");
@@ -704,7 +707,6 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
                 }
             }
         }
-        for (int i = f0; i < f1; i++) qps[i] = B.ctl_host[i].qp;
         for (int i = f0; i < f1; i++) {
 
             au.clear();
@@ -895,6 +897,8 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
     HB_TRY(dev_alloc(E, &E->mode_cost, (size_t)g.cuw * g.cuh * 35));
+    HB_TRY(dev_alloc(E, &E->intra_best, (size_t)g.cuw * g.cuh));
+    HB_TRY(dev_alloc(E, &E->scene, (size_t)max_batch));
     for (int k = 0; k < 2; k++) {
         HB_TRY(dev_alloc(E, &E->mvf[k], (size_t)g.cuw * g.cuh));
         HB_TRY(dev_alloc(E, &E->satdf[k], (size_t)g.cuw * g.cuh));
@@ -907,6 +911,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
         rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
         rc.fullness = rc.b16 * 9 / 10;
         rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
+        rc.keyint = p.keyint; rc.min_keyint = p.min_keyint; rc.scenecut = p.scenecut; rc.poc = 0; rc.started = 0;
         HB_CUDA(ctx, cudaMemcpyAsync(E->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, ctx->stream));
         HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }

@@ -26,6 +26,7 @@ struct CoarseParams {
     const uint8_t *ds;                   // [slots][dsh * dsw]; frame f of the batch = slot f + 1, slot f = its predecessor
     size_t ds_frame_stride;
     int16_t *cmv;                        // [frames][ctuh * ctuw][2]
+    SceneStat *scene;                    // [frames] scene-cut measures, zeroed before the launch
 };
 
 struct InterParams {
@@ -39,6 +40,7 @@ struct InterParams {
     const int *satd_in;                  // ... and the luma SATD of each vector
     uint32_t *mv_out;
     int *satd_out;
+    const int *intra_best;               // [cus] best intra SATD of each CU (k_intra_search), or null: no intra CUs in P frames
 };
 
 struct IntraParams {
@@ -49,7 +51,9 @@ struct IntraParams {
     int *progress;                       // [ctuh], zeroed before launch
     FrameCtl *ctl;
     int *mode_cost;                      // [cus][35] luma SATD per intra mode from k_intra_search
+    int *intra_best;                     // [cus] min over the 35 modes
     int second_pass;                     // 1: run only when ctl->redo is set (first key frame of a stream under rate control)
+    int intra_in_p;                      // P frames: search every CU and reconstruct the CUs the inter kernel marked intra
 };
 
 struct DeblockParams {
@@ -64,7 +68,7 @@ struct ModeParams {
     Geom g;
     const CuInfo *cus;
     CuSyntax *syn;
-    int is_intra;
+    const FrameCtl *ctl;                 // slice type decided on the device
 };
 
 struct EntropyFrame {
@@ -76,7 +80,6 @@ struct EntropyFrame {
     const FrameCtl *ctl;                 // slice QP (context initialisation)
     uint8_t *ctx_save;                   // [ctuh][kNumCtx] WPP context snapshots (after the 2nd CTU of each row)
     int *row_ready;                      // [ctuh] snapshot-published flags, zeroed before the launch
-    int is_intra;
     unsigned long long *trace;           // debug (HB_ENTROPY_TRACE): [ctuh][2] globaltimer at row start (after the hand-off) / end, or null
 };
 
@@ -143,7 +146,7 @@ __global__ void k_intra_search(IntraParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_deblock(DeblockParams p);
 __global__ void k_modes(ModeParams p);
-__global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int next_is_idr);
+__global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int force_idr, const SceneStat *scene, long long ds_samples);
 __global__ void k_rc_redo(RcState *rc, FrameCtl *ctl);
 __global__ void k_entropy(EntropyParams p);
 __global__ void k_pack_scan(PackParams p);

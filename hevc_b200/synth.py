@@ -13,8 +13,9 @@ CLIP_TYPES = {  # name -> (width, height, fps, hdr)   -- the reference's five fi
 
 
 class SynthClip:
-    def __init__(self, width: int, height: int, seed: int = 0, noise: float = 2.0):
+    def __init__(self, width: int, height: int, seed: int = 0, noise: float = 2.0, pan=(0.75, 0.25), patch_speed: float = 1.0):
         self.w, self.h, self.seed, self.noise = width, height, seed, noise
+        self.pan, self.patch_speed = pan, patch_speed
         rng = np.random.default_rng(seed)
         tw, th = width + 512, height + 512
         # band-limited texture: smoothed noise + a few oriented sinusoids, so that sub-pel motion matters
@@ -37,19 +38,19 @@ class SynthClip:
         w, h = self.w, self.h
         rng = np.random.default_rng(self.seed * 100003 + n)
         yy, xx = np.mgrid[0:h, 0:w]
-        # global slow pan of the background texture (0.75 px / frame horizontally, 0.25 vertically)
-        ox, oy = 0.75 * n, 0.25 * n
+        # global pan of the background texture (default 0.75 px / frame horizontally, 0.25 vertically)
+        ox, oy = self.pan[0] * n, self.pan[1] * n
         ix, iy = int(np.floor(ox)), int(np.floor(oy))
         fx, fy = ox - ix, oy - iy
         t = self.tex
-        x0, y0 = 128 + ix, 128 + iy
+        x0, y0 = 128 + ix % 256, 128 + iy % 256
         bg = ((1 - fx) * (1 - fy) * t[y0:y0 + h, x0:x0 + w] + fx * (1 - fy) * t[y0:y0 + h, x0 + 1:x0 + w + 1]
               + (1 - fx) * fy * t[y0 + 1:y0 + h + 1, x0:x0 + w] + fx * fy * t[y0 + 1:y0 + h + 1, x0 + 1:x0 + w + 1])
         luma = 110 + 40 * np.sin((xx + 2 * n) / (w / 6.0)) * np.cos(yy / (h / 4.0)) + bg
         cb = 128 + 30 * np.sin((xx - n) / (w / 3.0)) + 0 * yy
         cr = 128 + 30 * np.cos((yy + n) / (h / 3.0)) + 0 * xx
         for (px, py, pw, ph, vx, vy, pcb, pcr) in self.patches:
-            qx, qy = px + vx * n, py + vy * n
+            qx, qy = px + vx * self.patch_speed * n, py + vy * self.patch_speed * n
             jx, jy = int(np.floor(qx)) % (w - pw), int(np.floor(qy)) % (h - ph)
             sub = t[300 + jy % 64:300 + jy % 64 + ph, 40 + jx % 64:40 + jx % 64 + pw]
             luma[jy:jy + ph, jx:jx + pw] = 128 + 1.6 * sub
@@ -133,3 +134,29 @@ class TorchSynthClip:
     def frames(self, start: int, count: int):
         """uint8 tensor [count, frame_bytes] on the device"""
         return self.torch.stack([self.frame(start + i) for i in range(count)])
+
+
+CONTENT_CLASSES = ('base', 'hardcut', 'pan', 'static', 'grain')
+
+
+def content_clip(kind: str, width: int, height: int, n_frames: int, seed: int = 0):
+    """The R-D harness's content classes -> list of (y, u, v) uint8 frames.  ``base``: the default recipe (slow pan, moving
+    patches that cover and uncover background, grain sigma 2); ``hardcut``: two unrelated scenes joined in the middle;
+    ``pan``: fast global pan (6.5, 2.25 px / frame); ``static``: nothing moves, only the grain changes; ``grain``: sigma 5."""
+    if kind == 'base':
+        c = SynthClip(width, height, seed=seed)
+        return [c.frame(i) for i in range(n_frames)]
+    if kind == 'hardcut':
+        a, b = SynthClip(width, height, seed=seed), SynthClip(width, height, seed=seed + 100)
+        cut = n_frames // 2 + 1
+        return [a.frame(i) if i < cut else tuple(np.ascontiguousarray(p[::-1, ::-1]) for p in b.frame(i + 37)) for i in range(n_frames)]
+    if kind == 'pan':
+        c = SynthClip(width, height, seed=seed, pan=(6.5, 2.25))
+        return [c.frame(i) for i in range(n_frames)]
+    if kind == 'static':
+        c = SynthClip(width, height, seed=seed, pan=(0.0, 0.0), patch_speed=0.0)
+        return [c.frame(i) for i in range(n_frames)]
+    if kind == 'grain':
+        c = SynthClip(width, height, seed=seed, noise=5.0)
+        return [c.frame(i) for i in range(n_frames)]
+    raise ValueError(kind)

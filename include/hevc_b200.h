@@ -134,7 +134,11 @@ typedef struct hb_enc_params {
     int keep_recon;                    /* verification: keep every reconstruction / decision of the last batch readable */
     int rate_control;                  /* 0 = constant QP, 1 = VBV-constrained */
     int deblock;                       /* in-loop deblocking filter (x265 default: on) */
-    int reserved[7];
+    int scenecut;                      /* key frame at a detected scene cut once min_keyint frames have passed (x265 default: on;
+                                        * min-keyint= from core/transcoder.py:405) */
+    int intra_in_p;                    /* intra CUs in P frames */
+    int sao;                           /* sample adaptive offset (x265 default: on) */
+    int reserved[4];
 } hb_enc_params;
 
 typedef enum hb_pix_fmt {

@@ -538,7 +538,12 @@ static void write_cu(cabac *c, orc_frame_syntax *f, int cx, int cy)
     const int16_t *coef = f->coef + (size_t)(cy * f->cuw + cx) * ORC_CU_COEFS;
     const int availL = cu_avail(f, cx, cy, cx - 1, cy), availA = cu_avail(f, cx, cy, cx, cy - 1);
     cu->skip = 0;
-    if (!f->is_intra) {
+    if (!f->is_intra && cu->pred_mode == 0) {
+        /* intra CU in a P slice: cu_skip_flag = 0, pred_mode_flag = 1; part_mode is not sent (the CU is larger than the minimum size) */
+        const int ctx = (availL && cu_at(f, cx - 1, cy)->skip) + (availA && cu_at(f, cx, cy - 1)->skip);
+        cb_bin(c, CX_SKIP + ctx, 0);
+        cb_bin(c, CX_PRED_MODE, 1);
+    } else if (!f->is_intra) {
         int16_t mc[5][2];
         int merge_idx = -1;
         orc_merge_candidates(f, cx, cy, mc);
@@ -581,7 +586,7 @@ static void write_cu(cabac *c, orc_frame_syntax *f, int cx, int cy)
         write_transform_unit(c, cu, coef, 0);
         return;
     }
-    /* intra 2Nx2N in an I slice: no skip / pred_mode / part_mode (CU larger than the minimum size) */
+    /* intra 2Nx2N: in an I slice no skip / pred_mode flags; no part_mode (CU larger than the minimum size) */
     int mpm[3], idx = -1;
     intra_mpm(f, cx, cy, mpm);
     for (int k = 0; k < 3; k++)

@@ -43,6 +43,9 @@ struct orc_encoder {
     int16_t *cmv;                    /* [ctuh][ctuw][2] coarse vectors, quarter-resolution samples */
     int16_t *mvf[2];                 /* [cuh][cuw][2] motion field, ping-pong between the merge-aware passes */
     int32_t *satdf[2];               /* [cuh][cuw] SATD of that vector */
+    int32_t *costf;                  /* [cuh][cuw] cost of the final inter choice (SATD + lambda * vector bits) */
+    int32_t *mode_cost;              /* [cuh * cuw][35] luma SATD of every intra mode, predicted from SOURCE neighbours */
+    long long sc_inter, sc_intra;    /* scene-cut measures of the current frame (coarse_search) */
     int frame_no, poc, since_bp;
     uint8_t *payload;                /* CABAC sub-streams */
     size_t payload_cap;
@@ -95,6 +98,8 @@ orc_encoder *orc_enc_create(const orc_enc_params *p)
         e->mvf[k] = (int16_t *)calloc((size_t)e->cuw * e->cuh * 2, sizeof(int16_t));
         e->satdf[k] = (int32_t *)calloc((size_t)e->cuw * e->cuh, sizeof(int32_t));
     }
+    e->costf = (int32_t *)calloc((size_t)e->cuw * e->cuh, sizeof(int32_t));
+    e->mode_cost = (int32_t *)calloc((size_t)e->cuw * e->cuh * 35, sizeof(int32_t));
     e->payload_cap = (size_t)e->wc * e->hc * 3 + 65536;
     e->payload = (uint8_t *)malloc(e->payload_cap);
     e->row_off = (uint32_t *)calloc(e->ctuh, sizeof(uint32_t));
@@ -108,7 +113,7 @@ void orc_enc_destroy(orc_encoder *e)
     if (!e) return;
     for (int c = 0; c < 3; c++) { free(e->src[c].base); free(e->rec[0][c].base); free(e->rec[1][c].base); }
     free(e->ds[0].base); free(e->ds[1].base);
-    free(e->cus); free(e->coefs); free(e->cmv); free(e->mvf[0]); free(e->mvf[1]); free(e->satdf[0]); free(e->satdf[1]); free(e->payload); free(e->row_off); free(e->row_len);
+    free(e->cus); free(e->coefs); free(e->cmv); free(e->mvf[0]); free(e->mvf[1]); free(e->satdf[0]); free(e->satdf[1]); free(e->costf); free(e->mode_cost); free(e->payload); free(e->row_off); free(e->row_len);
     free(e);
 }
 
@@ -173,7 +178,7 @@ static int chroma_qp(int qp_y)
 
 /* transform + quantise + reconstruct one NxN block; returns cbf */
 static int code_block(const orc_encoder *e, const pixel *src, int ss, const pixel *pred, int ps, pixel *rec, int rs, int N, int qp,
-                      int intra, int16_t *level)
+                      int intra_slice, int inter_cu, int16_t *level)
 {
     int16_t res[32 * 32], coef[32 * 32], deq[32 * 32];
     const int bd = e->prm.bit_depth, maxv = (1 << bd) - 1;
@@ -181,12 +186,12 @@ static int code_block(const orc_encoder *e, const pixel *src, int ss, const pixe
         for (int x = 0; x < N; x++)
             res[y * N + x] = (int16_t)((int)src[y * ss + x] - (int)pred[y * ps + x]);
     orc_fwd_transform(res, N, coef, N, bd, 0);
-    int nsig = orc_quant(coef, level, N, qp + 6 * (bd - 8), bd, intra);
+    int nsig = orc_quant(coef, level, N, qp + 6 * (bd - 8), bd, intra_slice);      /* dead zone: 171/512 in I slices, 85/512 in P slices */
     /* An inter luma block that carries nothing but one or two isolated +-1 levels is dropped: such levels cost far more bits
      * (last position, flags, and often the difference between a coded and a skipped CU) than the distortion they remove:
      * -7..-8 % bits for -0.1..-0.2 dB luma on the calibration clip.  Chroma blocks are kept (dropping them bought 1 % for up to
      * 0.6 dB of chroma PSNR). */
-    if (nsig && !intra && N == 16) {
+    if (nsig && inter_cu && N == 16) {
         int sum = 0, mx = 0;
         for (int i = 0; i < N * N; i++) { const int a = abs(level[i]); sum += a; if (a > mx) mx = a; }
         if (mx <= 1 && sum <= 2) { memset(level, 0, sizeof(int16_t) * N * N); nsig = 0; }
@@ -246,53 +251,81 @@ static void gather_neighbours(const orc_encoder *e, const plane *r, int cx, int 
     }
 }
 
-static void encode_intra_frame(orc_encoder *e, int qp)
+/* Intra mode search of every CU at once: luma SATD of the 35 predictions built from the SOURCE picture's neighbour samples
+ * (same availability / substitution rules as the real prediction), so that nothing here depends on the reconstruction and the
+ * GPU runs it as one launch.  The wavefront stage adds the signalling cost against the real most-probable modes. */
+static void intra_search_all(orc_encoder *e)
 {
     const int bd = e->prm.bit_depth;
-    const int lambda = k_lambda_q8[qp] << (bd - 8);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int idx = 0; idx < e->cuw * e->cuh; idx++) {
+        const int cx = idx % e->cuw, cy = idx / e->cuw;
+        const pixel *src = e->src[0].p + (size_t)cy * 16 * e->src[0].stride + cx * 16;
+        pixel nbs[65], flts[65], pred[256];
+        gather_neighbours(e, &e->src[0], cx, cy, 16, nbs);
+        orc_intra_filter(nbs, flts, 16, 0, bd);
+        for (int mode = 0; mode < 35; mode++) {
+            orc_intra_pred(orc_intra_use_filter(16, mode) ? flts : nbs, pred, 16, 16, mode, 1, bd);
+            e->mode_cost[idx * 35 + mode] = orc_satd(src, e->src[0].stride, pred, 16, 16, 16);
+        }
+    }
+}
+
+/* one intra CU: mode = argmin(searched SATD + lambda * bits against the real MPM list), prediction from the reconstructed
+ * neighbours (inter or intra: constrained_intra_pred is off), transform / quantisation / reconstruction */
+static void intra_cu(orc_encoder *e, const orc_frame_syntax *fs, plane *rec, int cx, int cy, int qp, int lambda, int intra_slice)
+{
+    const int bd = e->prm.bit_depth, idx = cy * e->cuw + cx;
+    orc_cu *cu = &e->cus[idx];
+    int16_t *coef = e->coefs + (size_t)idx * ORC_CU_COEFS;
+    pixel nb[65], flt[65], pred[256];
+    int mpm[3];
+    const pixel *src = e->src[0].p + (size_t)cy * 16 * e->src[0].stride + cx * 16;
+    gather_neighbours(e, &rec[0], cx, cy, 16, nb);
+    orc_intra_filter(nb, flt, 16, 0, bd);
+    cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->skip = 0;
+    orc_intra_mpm(fs, cx, cy, mpm);
+    long best = -1;
+    int best_mode = 0;
+    for (int mode = 0; mode < 35; mode++) {
+        const int bits = mode == mpm[0] ? 2 : (mode == mpm[1] || mode == mpm[2]) ? 3 : 6;
+        const long cost = e->mode_cost[idx * 35 + mode] + ((lambda * bits) >> 8);
+        if (best < 0 || cost < best) { best = cost; best_mode = mode; }
+    }
+    cu->intra_mode = (uint8_t)best_mode;
+    orc_intra_pred(orc_intra_use_filter(16, best_mode) ? flt : nb, pred, 16, 16, best_mode, 1, bd);
+    pixel *ry = rec[0].p + (size_t)cy * 16 * rec[0].stride + cx * 16;
+    int cbf = code_block(e, src, e->src[0].stride, pred, 16, ry, rec[0].stride, 16, qp, intra_slice, 0, coef);
+    for (int c = 1; c < 3; c++) {
+        pixel cnb[33], cpred[64];
+        const pixel *cs = e->src[c].p + (size_t)cy * 8 * e->src[c].stride + cx * 8;
+        pixel *rc = rec[c].p + (size_t)cy * 8 * rec[c].stride + cx * 8;
+        gather_neighbours(e, &rec[c], cx, cy, 8, cnb);
+        orc_intra_pred(cnb, cpred, 8, 8, best_mode, 0, bd);
+        cbf |= code_block(e, cs, e->src[c].stride, cpred, 8, rc, rec[c].stride, 8, chroma_qp(qp), intra_slice, 0, coef + (c == 1 ? 256 : 320)) << c;
+    }
+    cu->cbf = (uint8_t)cbf;
+}
+
+/* the wavefront stage in decoding order; `only_flagged`: P frame, reconstruct only the CUs the decision stage marked intra */
+static void intra_pass(orc_encoder *e, int qp, int intra_slice, int only_flagged)
+{
+    const int lambda = k_lambda_q8[qp] << (e->prm.bit_depth - 8);
     plane *rec = e->rec[e->cur];
-    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, 1, qp, e->cus, e->coefs};
+    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, intra_slice, qp, e->cus, e->coefs};
     for (int ctu = 0; ctu < e->ctuw * e->ctuh; ctu++)
         for (int k = 0; k < 4; k++) {
             const int cx = (ctu % e->ctuw) * 2 + (k & 1), cy = (ctu / e->ctuw) * 2 + (k >> 1);
             if (cx >= e->cuw || cy >= e->cuh) continue;
-            orc_cu *cu = &e->cus[cy * e->cuw + cx];
-            int16_t *coef = e->coefs + (size_t)(cy * e->cuw + cx) * ORC_CU_COEFS;
-            pixel nb[65], flt[65], pred[256];
-            int mpm[3];
-            const pixel *src = e->src[0].p + (size_t)cy * 16 * e->src[0].stride + cx * 16;
-            gather_neighbours(e, &rec[0], cx, cy, 16, nb);
-            orc_intra_filter(nb, flt, 16, 0, bd);
-            /* The mode search predicts from the SOURCE picture's neighbour samples (same availability rules), so that it does not
-             * depend on the reconstruction and can run for all CUs at once; only the chosen mode is then predicted from the
-             * reconstructed neighbours.  The signalling cost still uses the real most-probable modes. */
-            pixel nbs[65], flts[65];
-            gather_neighbours(e, &e->src[0], cx, cy, 16, nbs);
-            orc_intra_filter(nbs, flts, 16, 0, bd);
-            cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->skip = 0;
-            orc_intra_mpm(&fs, cx, cy, mpm);
-            long best = -1;
-            int best_mode = 0;
-            for (int mode = 0; mode < 35; mode++) {
-                orc_intra_pred(orc_intra_use_filter(16, mode) ? flts : nbs, pred, 16, 16, mode, 1, bd);
-                const int bits = mode == mpm[0] ? 2 : (mode == mpm[1] || mode == mpm[2]) ? 3 : 6;
-                const long cost = orc_satd(src, e->src[0].stride, pred, 16, 16, 16) + ((lambda * bits) >> 8);
-                if (best < 0 || cost < best) { best = cost; best_mode = mode; }
-            }
-            cu->intra_mode = (uint8_t)best_mode;
-            orc_intra_pred(orc_intra_use_filter(16, best_mode) ? flt : nb, pred, 16, 16, best_mode, 1, bd);
-            pixel *ry = rec[0].p + (size_t)cy * 16 * rec[0].stride + cx * 16;
-            int cbf = code_block(e, src, e->src[0].stride, pred, 16, ry, rec[0].stride, 16, qp, 1, coef);
-            for (int c = 1; c < 3; c++) {
-                pixel cnb[33], cpred[64];
-                const pixel *cs = e->src[c].p + (size_t)cy * 8 * e->src[c].stride + cx * 8;
-                pixel *rc = rec[c].p + (size_t)cy * 8 * rec[c].stride + cx * 8;
-                gather_neighbours(e, &rec[c], cx, cy, 8, cnb);
-                orc_intra_pred(cnb, cpred, 8, 8, best_mode, 0, bd);
-                cbf |= code_block(e, cs, e->src[c].stride, cpred, 8, rc, rec[c].stride, 8, chroma_qp(qp), 1, coef + (c == 1 ? 256 : 320)) << c;
-            }
-            cu->cbf = (uint8_t)cbf;
+            if (only_flagged && e->cus[cy * e->cuw + cx].pred_mode != 0) continue;
+            intra_cu(e, &fs, rec, cx, cy, qp, lambda, intra_slice);
         }
+}
+
+static void encode_intra_frame(orc_encoder *e, int qp)
+{
+    for (int i = 0; i < e->cuw * e->cuh; i++) e->cus[i].pred_mode = 0;
+    intra_pass(e, qp, 1, 0);
 }
 
 /* ------------------------------------------------------------------ inter frame */
@@ -312,7 +345,8 @@ static void coarse_search(orc_encoder *e)
     const plane *cur = &e->ds[e->cur_ds], *prev = &e->ds[1 - e->cur_ds];
     /* the search runs on the 8 most significant bits of the quarter-resolution samples (byte SAD on the GPU) */
     const int sh = e->prm.bit_depth - 8, bias = 1;
-#pragma omp parallel for schedule(dynamic)
+    long long sc_inter = 0, sc_intra = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : sc_inter, sc_intra)
     for (int ty = 0; ty < e->ctuh; ty++)
         for (int tx = 0; tx < e->ctuw; tx++) {
             long best = -1;
@@ -328,7 +362,27 @@ static void coarse_search(orc_encoder *e)
                 }
             e->cmv[(ty * e->ctuw + tx) * 2] = (int16_t)bdx;
             e->cmv[(ty * e->ctuw + tx) * 2 + 1] = (int16_t)bdy;
+            /* scene-cut measures: the winning inter cost against an intra measure of the same 8x8 block = the smaller of its
+             * horizontal / vertical neighbour-difference sums (56 sample pairs each) */
+            long hs = 0, vs = 0;
+            for (int j = 0; j < 8; j++)
+                for (int i = 0; i < 8; i++) {
+                    const int c = ds_at(cur, tx * 8 + i, ty * 8 + j) >> sh;
+                    if (i) hs += abs(c - (int)(ds_at(cur, tx * 8 + i - 1, ty * 8 + j) >> sh));
+                    if (j) vs += abs(c - (int)(ds_at(cur, tx * 8 + i, ty * 8 + j - 1) >> sh));
+                }
+            sc_inter += best;
+            sc_intra += hs < vs ? hs : vs;
         }
+    e->sc_inter = sc_inter; e->sc_intra = sc_intra;
+}
+
+/* a scene cut: the motion-compensated quarter-resolution picture is no better a predictor than the picture's own neighbour
+ * samples (inter >= 1.5 x intra) and the mismatch is large in absolute terms (mean >= 5 per sample at 8 bits) */
+static int scene_cut(const orc_encoder *e)
+{
+    const long long n = (long long)e->ctuw * e->ctuh * 64;
+    return e->sc_inter >= 5 * n && 2 * e->sc_inter >= 3 * e->sc_intra;
 }
 
 typedef struct { int x, y; } mv_t;
@@ -369,7 +423,6 @@ static void encode_inter_frame(orc_encoder *e, int qp)
     const int lambda = k_lambda_q8[qp] << (bd - 8);
     plane *rec = e->rec[e->cur];
     const plane *ref = e->rec[1 - e->cur];
-    coarse_search(e);
     /* every loop over CUs below is order-independent (that is what lets the GPU run them as one launch each), so the model
      * spreads them over the host cores */
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
@@ -476,8 +529,14 @@ static void encode_inter_frame(orc_encoder *e, int qp)
                 }
                 mvo[idx * 2] = (int16_t)best.x; mvo[idx * 2 + 1] = (int16_t)best.y;
                 sdo[idx] = (int32_t)bsatd;
+                e->costf[idx] = (int32_t)bcost;
             }
     }
+    /* Intra CUs in P frames: a CU goes intra when the best intra prediction (searched on source neighbours) plus its
+     * signalling beats the final inter choice by a quarter.  The margin covers what SATD does not see: the inter CU is
+     * usually skipped or merged (no residual, ~1 bit) while an intra CU always codes a mode and a residual, and the source
+     * neighbours flatter the intra prediction. */
+    if (e->prm.intra_in_p) intra_search_all(e);
     const int16_t *mvfinal = e->mvf[MERGE_PASSES & 1];
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
     for (int cy = 0; cy < e->cuh; cy++)
@@ -491,20 +550,31 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             pixel blk[256];
             cu->pred_mode = 1; cu->intra_mode = 1; cu->skip = 0;
             cu->mvx = (int16_t)best.x; cu->mvy = (int16_t)best.y;
+            if (e->prm.intra_in_p) {
+                const int idx = cy * e->cuw + cx;
+                long ibest = e->mode_cost[idx * 35];
+                for (int m = 1; m < 35; m++) if (e->mode_cost[idx * 35 + m] < ibest) ibest = e->mode_cost[idx * 35 + m];
+                const long icost = ibest + ((lambda * 12) >> 8);
+                if (icost * 4 < (long)e->costf[idx] * 3) {
+                    cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->cbf = 0;     /* reconstructed by the wavefront stage below */
+                    continue;
+                }
+            }
             /* reconstruct */
             predict_luma(e, &ref[0], x0, y0, best, blk);
             pixel *ry = rec[0].p + (size_t)y0 * rec[0].stride + x0;
-            int cbf = code_block(e, src, ss, blk, 16, ry, rec[0].stride, 16, qp, 0, coef);
+            int cbf = code_block(e, src, ss, blk, 16, ry, rec[0].stride, 16, qp, 0, 1, coef);
             for (int c = 1; c < 3; c++) {
                 pixel cpred[64];
                 const pixel *r = ref[c].p + (size_t)(cy * 8 + (best.y >> 3)) * ref[c].stride + cx * 8 + (best.x >> 3);
                 orc_interp_chroma(r, ref[c].stride, cpred, 8, 8, 8, best.x & 7, best.y & 7, bd);
                 const pixel *cs = e->src[c].p + (size_t)cy * 8 * e->src[c].stride + cx * 8;
                 pixel *rc = rec[c].p + (size_t)cy * 8 * rec[c].stride + cx * 8;
-                cbf |= code_block(e, cs, e->src[c].stride, cpred, 8, rc, rec[c].stride, 8, chroma_qp(qp), 0, coef + (c == 1 ? 256 : 320)) << c;
+                cbf |= code_block(e, cs, e->src[c].stride, cpred, 8, rc, rec[c].stride, 8, chroma_qp(qp), 0, 1, coef + (c == 1 ? 256 : 320)) << c;
             }
             cu->cbf = (uint8_t)cbf;
         }
+    if (e->prm.intra_in_p) intra_pass(e, qp, 0, 1);
 }
 
 /* ------------------------------------------------------------------ in-loop deblocking filter (H.265 8.7.2) */
@@ -631,11 +701,16 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
                    size_t cap, orc_frame_info *info)
 {
     const orc_enc_params *p = &e->prm;
-    const int idr = force_idr || e->frame_no == 0 || (p->keyint > 0 && e->poc + 1 >= p->keyint);
+    load_source(e, y, ys, u, v, cs);
+    int cut = 0;
+    if (e->frame_no > 0) {          /* coarse motion search against the previous source picture; also measures scene cuts */
+        coarse_search(e);
+        cut = p->scenecut && scene_cut(e) && e->poc + 1 >= p->min_keyint;
+    }
+    const int idr = force_idr || e->frame_no == 0 || (p->keyint > 0 && e->poc + 1 >= p->keyint) || cut;
     if (idr) e->poc = 0; else e->poc++;
     int qp = clampi(orc_rc_pick_qp(&e->rc, p, idr), 0, 51);
-    load_source(e, y, ys, u, v, cs);
-    if (idr) encode_intra_frame(e, qp); else encode_inter_frame(e, qp);
+    if (idr) { intra_search_all(e); encode_intra_frame(e, qp); } else encode_inter_frame(e, qp);
     long long est16 = 0;
     for (int i = 0; i < e->cuw * e->cuh; i++)
         est16 += orc_rc_cu_estimate(e->coefs + (size_t)i * ORC_CU_COEFS, e->cus[i].cbf);

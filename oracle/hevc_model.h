@@ -32,6 +32,10 @@ typedef struct orc_enc_params {
     int hash_sei;                 /* emit decoded-picture-hash (MD5) suffix SEI */
     int deblock;                  /* in-loop deblocking filter enabled */
     int rate_control;             /* 0 constant QP, 1 VBV-constrained (vbv_maxrate / vbv_bufsize) */
+    int min_keyint;               /* min-keyint= (reference core/transcoder.py:405): a scene cut closer than this to the last IDR stays a P frame */
+    int scenecut;                 /* scene-cut detection: key frame at a detected cut (x265 default: on) */
+    int intra_in_p;               /* intra CUs in P frames */
+    int sao;                      /* sample adaptive offset */
 } orc_enc_params;
 
 /* per-CU side information, also the interface between the decide/reconstruct stage and the entropy stage */

@@ -19,11 +19,14 @@ def b200_params(w, h, depth, keyint=4, hdr10=None):
     return p
 
 
-def model_params(p: B200Params, qp_i, qp_p, hash_sei, rate_control=False, deblock=True):
+def model_params(p: B200Params, qp_i, qp_p, hash_sei, rate_control=False, deblock=True, **tools):
+    """``tools``: scenecut / intra_in_p / sao overrides (defaults = hevc_b200.encoder.to_c_params's)"""
     from oracle import encoder_model as em
+    t = {'scenecut': 1, 'intra_in_p': 1, 'sao': 0}
+    t.update({k: int(v) for k, v in tools.items()})
     m = em.make_params(p.width, p.height, p.bit_depth, qp_i=qp_i, qp_p=qp_p, keyint=p.keyint, fps=(p.fps_num, p.fps_den),
-                       hdr10=bool(p.hdr10), hash_sei=hash_sei, level_idc=p.level_idc, tier=p.tier,
-                       vbv_maxrate_kbps=p.vbv_maxrate_kbps, vbv_bufsize_kbit=p.vbv_bufsize_kbit, rate_control=int(rate_control), deblock=int(deblock))
+                       hdr10=bool(p.hdr10), hash_sei=hash_sei, level_idc=p.level_idc, tier=p.tier, min_keyint=p.min_keyint,
+                       vbv_maxrate_kbps=p.vbv_maxrate_kbps, vbv_bufsize_kbit=p.vbv_bufsize_kbit, rate_control=int(rate_control), deblock=int(deblock), **t)
     return m
 
 
@@ -32,18 +35,20 @@ def clip_frames(w, h, n, seed=1, noise=2.0):
     return [clip.frame(i) for i in range(n)]
 
 
-def run_model(p, frames8, qp_i, qp_p, hash_sei=False, force_idr_at=(), rate_control=False, deblock=True):
+def run_model(p, frames8, qp_i, qp_p, hash_sei=False, force_idr_at=(), rate_control=False, deblock=True, **tools):
     """-> (stream bytes, per-frame AUs, per-frame recon, per-frame (cus, coefs))"""
     from oracle import encoder_model as em
-    enc = em.ModelEncoder(model_params(p, qp_i, qp_p, hash_sei, rate_control, deblock))
-    aus, recs, decs, qps = [], [], [], []
+    enc = em.ModelEncoder(model_params(p, qp_i, qp_p, hash_sei, rate_control, deblock, **tools))
+    aus, recs, decs, qps, infos = [], [], [], [], []
     sh = p.bit_depth - 8
     for i, (y, u, v) in enumerate(frames8):
         au, info = enc.encode(y.astype(np.uint16) << sh, u.astype(np.uint16) << sh, v.astype(np.uint16) << sh, force_idr=i in force_idr_at)
         aus.append(au)
         qps.append(info.qp)
+        infos.append((info.is_idr, info.poc, info.n_intra))
         recs.append(enc.recon())
         decs.append((enc.last_cus(), enc.last_coefs()))
     enc.close()
     run_model.last_qps = qps
+    run_model.last_infos = infos
     return b''.join(aus), aus, recs, decs

@@ -18,16 +18,19 @@ def ctx():
     c.close()
 
 
-def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True, rate_control=False, deblock=True):
+def _gpu_encode(ctx, p, frames8, qp, batch, hash_sei=True, split=None, read_back=True, rate_control=False, deblock=True, **tools):
     from hevc_b200 import encoder as E
-    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True, rate_control=rate_control, deblock=deblock), max_batch=batch)
+    enc = E.B200Encoder(ctx, E.to_c_params(p, qp=qp, hash_sei=hash_sei, keep_recon=True, rate_control=rate_control, deblock=deblock, **tools),
+                        max_batch=batch)
     stream, recs, decs = b'', [], []
     _gpu_encode.last_qps = []
+    _gpu_encode.last_stats = []
     pos = 0
     for n in (split or [len(frames8)]):
         out, stats = enc.encode(E.pack_yuv420p8(frames8[pos:pos + n]), n)
         stream += out
         _gpu_encode.last_qps = getattr(_gpu_encode, 'last_qps', []) + [s.qp for s in stats]
+        _gpu_encode.last_stats += [(int(s.is_idr), s.poc) for s in stats]
         if read_back and n <= batch:          # the encoder keeps the reconstructions of its last batch
             for i in range(n):
                 recs.append(enc.read_recon(i))
@@ -408,16 +411,24 @@ def hard_cut_frames(w, h, n, cut, seed=21, noise=2.0):
     return [a.frame(i) if i < cut else tuple(np.ascontiguousarray(p[::-1, ::-1]) for p in b.frame(i + 37)) for i in range(n)]
 
 
-@pytest.mark.parametrize('depth', [8, 10])
-def test_hard_cut_clip_matches_cpu_model(ctx, depth):
-    """a clip with a scene change in the middle of a GOP: same bytes as the model, decodable, and the frame after the cut is
-    not allowed to fall apart (intra CUs / scene-cut key frame instead of predicting from an unrelated picture)"""
+@pytest.mark.parametrize('depth,scenecut', [(8, True), (10, True), (8, False), (10, False)])
+def test_hard_cut_clip_matches_cpu_model(ctx, depth, scenecut):
+    """a clip with a scene change in the middle of a GOP.  scenecut on: the device-side detector makes the frame after the cut
+    a key frame (it is past min-keyint) and the key-frame cadence restarts there; scenecut off: the frame stays a P frame and
+    most of its CUs go intra.  Either way: same bytes as the model, same frame types, decodable, and the picture after the
+    cut does not fall apart."""
     from oracle import fforacle
     w, h, n, cut = 320, 192, 16, 9
-    p = ec.b200_params(w, h, depth, keyint=12)
+    p = ec.b200_params(w, h, depth, keyint=12)           # min-keyint 6
     frames = hard_cut_frames(w, h, n, cut)
-    m_stream, m_aus, m_recs, _ = ec.run_model(p, frames, 26, 28, hash_sei=True)
-    g_stream, g_recs, _ = _gpu_encode(ctx, p, frames, (26, 28), batch=8, split=[8, 8])
+    m_stream, m_aus, m_recs, _ = ec.run_model(p, frames, 26, 28, hash_sei=True, scenecut=scenecut)
+    infos = ec.run_model.last_infos
+    g_stream, g_recs, _ = _gpu_encode(ctx, p, frames, (26, 28), batch=8, split=[8, 8], scenecut=scenecut)
+    assert _gpu_encode.last_stats == [(i, pc) for i, pc, _ in infos]
+    if scenecut:
+        assert [k for k, (i, _, _) in enumerate(infos) if i] == [0, cut]              # no key frame at 12: the cadence restarted
+    else:
+        assert [k for k, (i, _, _) in enumerate(infos) if i] == [0, 12] and infos[cut][2] > (w // 16) * (h // 16) // 3
     assert g_stream == m_stream
     dec = fforacle.decode_hevc(g_stream, verify_hash=True)
     assert len(dec) == n
@@ -425,3 +436,23 @@ def test_hard_cut_clip_matches_cpu_model(ctx, depth):
     src = frames[cut][0].astype(np.float64) * (1 << sh)
     mse = np.mean((dec[cut][0].astype(np.float64) - src) ** 2)
     assert 10 * np.log10(((255 << sh) ** 2) / mse) > 30
+
+
+def test_intra_cus_in_p_frames_match_cpu_model(ctx):
+    """uncovered background / fast content: P frames carry intra CUs (sparse wavefront pass after the inter kernel); every
+    decision, level, sample and byte equals the model, with the tool on and off"""
+    from hevc_b200.synth import content_clip
+    w, h, n = 352, 208, 7
+    p = ec.b200_params(w, h, 8, keyint=30)
+    frames = content_clip('pan', w, h, n, seed=3)
+    for on in (True, False):
+        m_stream, _, m_recs, m_decs = ec.run_model(p, frames, 30, 32, hash_sei=True, intra_in_p=on, scenecut=False)
+        n_intra = sum(x[2] for x in ec.run_model.last_infos[1:])
+        assert (n_intra > 0) == on
+        g_stream, g_recs, g_decs = _gpu_encode(ctx, p, frames, (30, 32), batch=8, intra_in_p=on, scenecut=False)
+        for i in range(n):
+            for field in ('pred_mode', 'intra_mode', 'mvx', 'mvy', 'cbf'):
+                assert (m_decs[i][0][field] == g_decs[i][0][field]).all(), (on, i, field)
+            for c in range(3):
+                assert (m_recs[i][c] == g_recs[i][c]).all(), (on, i, c)
+        assert g_stream == m_stream
