@@ -12,7 +12,7 @@ constexpr int kPad = 80;            // luma border of reconstructed planes (chro
 constexpr int kCuCoefs = 384;       // 16x16 luma + 8x8 Cb + 8x8 Cr levels per CU
 constexpr int kCmeRange = 12;       // quarter-resolution search range
 constexpr int kMvOverhang = 64;     // predicted blocks may leave the picture by this many luma samples
-constexpr int kNumCtx = 142;
+constexpr int kNumCtx = 144;
 
 struct CuInfo {
     uint8_t pred_mode;   // 0 intra, 1 inter
@@ -30,6 +30,16 @@ struct CuSyntax {
     uint8_t pad;
     int16_t mvdx, mvdy;
 };
+
+// sample adaptive offset parameters of one CTU (oracle/hevc_model.h orc_sao); padded to 32 bytes for 16-byte staging copies
+struct __align__(16) SaoCtu {
+    uint8_t type[2];       // [0] luma, [1] chroma: 0 off, 1 band, 2 edge
+    uint8_t eo_class[2];
+    uint8_t band[3];
+    int8_t offset[3][4];
+    uint8_t pad[13];
+};
+static_assert(sizeof(SaoCtu) == 32, "SaoCtu layout");
 
 struct Geom {
     int wc, hc;          // coded size (multiples of 16)
@@ -88,6 +98,7 @@ struct FrameCtl {
     int poc, scene_cut;            // picture order count decided on the device (scene cuts move the key-frame cadence)
     QuantParam qy, qc;
     unsigned long long est16;      // size estimate accumulated by the frame kernel, 1/16 bit
+    unsigned long long satd_sum;   // sum of the luma SATDs after the first merge-aware pass (gate of the P-frame intra search)
 };
 
 struct RcState {
@@ -182,6 +193,7 @@ HB_HD void ctl_set_qp(FrameCtl &c, int qp, int is_idr, int bit_depth)
     c.qy = make_quant(4, qp + 6 * (bit_depth - 8), bit_depth, is_idr);
     c.qc = make_quant(3, chroma_qp(qp) + 6 * (bit_depth - 8), bit_depth, is_idr);
     c.est16 = 0;
+    c.satd_sum = 0;
 }
 
 }  // namespace hb

@@ -25,9 +25,10 @@ __constant__ uint8_t c_next_lps[64] = {0, 0, 1, 2, 2, 4, 4, 5, 6, 7, 8, 9, 9, 11
 enum {
     CX_SPLIT_CU = 0, CX_SKIP = 3, CX_PRED_MODE = 6, CX_PART_MODE = 7, CX_PREV_INTRA = 11, CX_CHROMA_PRED = 12, CX_MERGE_FLAG = 13,
     CX_MERGE_IDX = 14, CX_MVD_GR0 = 15, CX_MVD_GR1 = 16, CX_MVP_FLAG = 17, CX_ROOT_CBF = 18, CX_SPLIT_TU = 19, CX_CBF_LUMA = 22,
-    CX_CBF_CHROMA = 24, CX_LAST_X = 28, CX_LAST_Y = 46, CX_CSBF = 64, CX_SIG = 68, CX_GR1 = 110, CX_GR2 = 134, CX_QP_DELTA = 140
+    CX_CBF_CHROMA = 24, CX_LAST_X = 28, CX_LAST_Y = 46, CX_CSBF = 64, CX_SIG = 68, CX_GR1 = 110, CX_GR2 = 134, CX_QP_DELTA = 140,
+    CX_SAO_MERGE = 142, CX_SAO_TYPE = 143
 };
-static_assert(CX_QP_DELTA + 2 == kNumCtx, "context layout");
+static_assert(CX_SAO_TYPE + 1 == kNumCtx, "context layout");
 
 // initValue per context for initType 0 (I) and 1 (P); H.265 Tables 9-5 .. 9-37
 __constant__ uint8_t c_ctx_init[2][kNumCtx] = {
@@ -38,7 +39,7 @@ __constant__ uint8_t c_ctx_init[2][kNumCtx] = {
      111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
      140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,
      140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
-     138, 153, 136, 167, 152, 152, 154, 154},
+     138, 153, 136, 167, 152, 152, 154, 154, 153, 200},
     {107, 139, 126, 197, 185, 201, 149, 154, 139, 154, 154, 154, 152, 110, 122, 140, 198, 168, 79, 124, 138, 94, 153, 111, 149, 107, 167, 154,
      125, 110, 94, 110, 95, 79, 125, 111, 110, 78, 110, 111, 111, 95, 94, 108, 123, 108,
      125, 110, 94, 110, 95, 79, 125, 111, 110, 78, 110, 111, 111, 95, 94, 108, 123, 108,
@@ -46,7 +47,7 @@ __constant__ uint8_t c_ctx_init[2][kNumCtx] = {
      155, 154, 139, 153, 139, 123, 123, 63, 153, 166, 183, 140, 136, 153, 154, 166, 183, 140, 136, 153, 154, 166, 183, 140, 136, 153, 154,
      170, 153, 123, 123, 107, 121, 107, 121, 167, 151, 183, 140, 151, 183, 140,
      154, 196, 196, 167, 154, 152, 167, 182, 182, 134, 149, 136, 153, 121, 136, 137, 169, 194, 166, 167, 154, 167, 137, 182,
-     107, 167, 91, 122, 107, 167, 154, 154}};
+     107, 167, 91, 122, 107, 167, 154, 154, 153, 185}};
 
 // up-right diagonal scans as raster indices (y * size + x)
 __constant__ uint8_t c_diag4[16] = {0, 4, 1, 8, 5, 2, 12, 9, 6, 3, 13, 10, 7, 14, 11, 15};
@@ -543,6 +544,55 @@ __device__ __forceinline__ void binarise_header(EntropyWarpScratch &s, int k, co
     s.nhdr[k] = (uint8_t)nb;
 }
 
+// Lane 31: sao() of the CTU (7.3.8.3).  Merging is by identity with the left (else the upper) CTU's parameters.
+__device__ __forceinline__ bool sao_same(const SaoCtu &a, const SaoCtu &b)
+{
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(&a), *y = reinterpret_cast<const uint32_t *>(&b);
+    return x[0] == y[0] && x[1] == y[1] && x[2] == y[2] && x[3] == y[3] && x[4] == y[4];
+}
+__device__ __forceinline__ void binarise_sao(EntropyWarpScratch &s, const SaoCtu &c, bool have_left, bool have_up, const SaoCtu &up, int bit_depth)
+{
+    uint32_t *out = s.saob;
+    int nb = 0;
+    const int cmax = (1 << (min(bit_depth, 10) - 5)) - 1;
+    bool merged = false;
+    if (have_left) {
+        merged = sao_same(c, s.sao_left);
+        out[nb++] = bin_ctx(CX_SAO_MERGE, merged);
+    }
+    if (!merged && have_up) {
+        merged = sao_same(c, up);
+        out[nb++] = bin_ctx(CX_SAO_MERGE, merged);
+    }
+    if (!merged) {
+        for (int ci = 0; ci < 3; ci++) {
+            const int g = ci ? 1 : 0, type = c.type[g];
+            if (ci < 2) {
+                out[nb++] = bin_ctx(CX_SAO_TYPE, type != 0);
+                if (type) out[nb++] = bin_bypass(type == 2, 1);
+            }
+            if (!type) continue;
+            for (int i = 0; i < 4; i++) {              // sao_offset_abs: truncated unary, bypass
+                const int a = abs((int)c.offset[ci][i]);
+                if (a < cmax) out[nb++] = bin_unary(a);
+                else {
+                    if (a > 16) out[nb++] = bin_bypass(0xffff, 16);
+                    const int rest = a > 16 ? a - 16 : a;
+                    out[nb++] = bin_bypass((1u << rest) - 1, rest);
+                }
+            }
+            if (type == 1) {
+                for (int i = 0; i < 4; i++)
+                    if (c.offset[ci][i]) out[nb++] = bin_bypass(c.offset[ci][i] < 0, 1);
+                out[nb++] = bin_bypass(c.band[ci], 5);
+            } else if (ci < 2) {
+                out[nb++] = bin_bypass(c.eo_class[g], 2);
+            }
+        }
+    }
+    s.nsao = (uint32_t)nb;
+}
+
 // ------------------------------------------------------------------------------------------------ WPP CABAC kernel
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
@@ -570,6 +620,12 @@ __device__ __forceinline__ void stage_ctu(EntropyWarpScratch &s, const EntropyFr
     } else if (lane < 6) {
         const int cx = 2 * x + (lane - 4), cy = 2 * row - 1;
         if (cx < g.cuw && cy >= 0) cp_async8(&s.above[slot][lane - 4], fr.syn + cy * g.cuw + cx);
+    } else if (lane < 10 && fr.sao) {       // SAO parameters of this CTU (lanes 6, 7) and of the one above (lanes 8, 9): 2 x 16 bytes each
+        const int half = lane & 1, up = lane >= 8;
+        if (!up || row > 0) {
+            const SaoCtu *src = fr.sao + (row - up) * g.ctuw + x;
+            cp_async16(reinterpret_cast<uint4 *>(up ? &s.sao_up[slot] : &s.sao_cur[slot]) + half, reinterpret_cast<const uint4 *>(src) + half);
+        }
     }
 }
 
@@ -674,9 +730,15 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
                 binarise_header(s, k, h);
             }
         }
+        if (lane == 31 && fr.sao) binarise_sao(s, s.sao_cur[slot], x > 0, row > 0, s.sao_up[slot], g.bit_depth);
         left_skip0 = s.cu[slot][1].syn.skip;
         left_skip1 = s.cu[slot][3].syn.skip;
         __syncwarp();
+        if (fr.sao) {
+            if (lane == 0) st = code_list(st, w, EWS_OFF(saob), (int)s.nsao);
+            if (lane < 8) reinterpret_cast<uint32_t *>(&s.sao_left)[lane] = reinterpret_cast<const uint32_t *>(&s.sao_cur[slot])[lane];
+            __syncwarp();
+        }
         for (int k = 0; k < 4; k++) {
             const int cx = cx0 + (k & 1), cy = cy0 + (k >> 1);
             if (cx >= g.cuw || cy >= g.cuh) continue;

@@ -663,6 +663,7 @@ __global__ void __launch_bounds__(128, 7) k_merge(const __grid_constant__ InterP
     if (lane == 0) {
         p.mv_out[cy * g.cuw + cx] = pack_mv(best);
         p.satd_out[cy * g.cuw + cx] = bsatd;
+        atomicAdd(&p.ctl->satd_sum, (unsigned long long)bsatd);
     }
 }
 
@@ -708,8 +709,9 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         // Intra CU in a P frame (oracle/hevc_encode.c): the best intra prediction searched on source neighbours, plus its
         // signalling, must beat the final inter choice by a quarter; the wavefront kernel then reconstructs the CU
         if (p.intra_best) {
-            const int icost = p.intra_best[cy * g.cuw + cx] + ((lambda * 12) >> 8);
-            if ((long long)icost * 4 < (long long)bcost * 3) {
+            const int ibest = p.intra_best[cy * g.cuw + cx];
+            const long long icost = (long long)ibest + ((lambda * 12) >> 8);
+            if (ibest != 0x7fffffff && icost * 4 < (long long)bcost * 3) {
                 if (lane == 0) {
                     CuInfo ci;
                     ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0; ci.skip = 0; ci.mvx = 0; ci.mvy = 0;
@@ -1131,8 +1133,18 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
     IntraSearchScratch &s = scratch[warp];
     if (!p.ctl->is_idr && !p.intra_in_p) return;
     const int nwarps = gridDim.x * (kIntraSearchThreads / 32);
+    const bool gated = !p.ctl->is_idr;
+    const long long satd_sum = gated ? (long long)p.ctl->satd_sum : 0, ncu = (long long)g.cuw * g.cuh;
+    const int gate_thr = (256 * p.ctl->lambda) >> 9;
     for (int cu = blockIdx.x * (kIntraSearchThreads / 32) + warp; cu < g.cuw * g.cuh; cu += nwarps) {
         const int cx = cu % g.cuw, cy = cu / g.cuw, x0 = cx * 16, y0 = cy * 16;
+        if (gated) {        // P frame: only CUs that inter prediction serves badly (oracle/hevc_encode.c intra_search_all)
+            const int s1 = p.satd1[cu];
+            if (!(s1 > gate_thr && ((long long)s1 * ncu > 2 * satd_sum || s1 > 8 * gate_thr || s1 > (2048 << (bd - 8))))) {
+                if (lane == 0) p.intra_best[cu] = 0x7fffffff;
+                continue;
+            }
+        }
         for (int i = lane; i < 65; i += 32) s.nb[i] = gather_one(p.src.y, g.src_stride, g, cx, cy, 16, i, bd);
         {
             const int row = lane >> 1, c0 = (lane & 1) * 8;

@@ -116,7 +116,7 @@ std::vector<uint8_t> make_sps(const hb_enc_params &p, int wc, int hc)
     b.ue(0); b.ue(2);                                // CB 8..32
     b.ue(0); b.ue(3);                                // TB 4..32
     b.ue(0); b.ue(0);                                // transform hierarchy depth inter / intra
-    b.flag(false); b.flag(false); b.flag(false); b.flag(false);   // scaling lists, AMP, SAO, PCM
+    b.flag(false); b.flag(false); b.flag(p.sao != 0); b.flag(false);   // scaling lists, AMP, SAO, PCM
     b.ue(1); b.ue(1); b.ue(0); b.ue(0); b.flag(true);             // one RPS: previous picture
     b.flag(false); b.flag(false); b.flag(false);                  // long-term, temporal MVP, strong smoothing
     b.flag(true);                                                 // VUI
@@ -229,6 +229,7 @@ struct FrameSlot {
     uint32_t *row_len = nullptr;
     uint8_t *ctx_save = nullptr;      // WPP hand-off area of the entropy stage
     int *row_ready = nullptr;
+    SaoCtu *sao = nullptr;            // [ctus] SAO parameters (SAO on)
     Planes keep{};            // verification copy of the reconstruction (unpadded strides = rec strides)
 };
 
@@ -274,8 +275,8 @@ struct hb_encoder {
     BatchSet set[2];
     int next_set = 0;                 // set the next batch is enqueued into
     BatchSet *last_drained = nullptr; // what read_recon / read_decisions look at
-    pixel *rec_base[2][3] = {};
-    Planes rec[2];
+    pixel *rec_base[3][3] = {};
+    Planes rec[2], pre{};             // pre: reconstruction before SAO (SAO on); rec[cur] then receives the SAO output
     uint8_t *ds = nullptr;            // [max_batch + 1][dsh * dsw] quarter-resolution planes (8 MSBs)
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
     int *mode_cost = nullptr;         // [cus][35] intra mode search result of the frame in flight
@@ -388,7 +389,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
         for (int i = 0; i < n; i++) {
             FrameSlot &s = B.slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
-            ef[i].ctl = B.ctl_dev + i; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
+            ef[i].ctl = B.ctl_dev + i; ef[i].sao = s.sao; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
             ef[i].trace = B.trace_dev ? B.trace_dev + (size_t)i * g.ctuh * 2 : nullptr;
         }
         HB_CUDA(ctx, cudaMemcpyAsync(B.eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
@@ -518,7 +519,8 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 const bool forced = is_idr[i] != 0;
                 const bool first_of_stream = e->frame_no == 0;
                 FrameSlot &s = B.slot[i];
-                const Planes &rec = e->rec[e->cur], &ref = e->rec[1 - e->cur];
+                const Planes &fin = e->rec[e->cur], &ref = e->rec[1 - e->cur];
+                const Planes &rec = p.sao ? e->pre : fin;      // the frame is reconstructed and deblocked here; SAO writes `fin`
                 // rate control + frame type on the device: account for the previous frame, choose this frame's type and QP
                 k_rc_step<<<1, 32, 0, st>>>(e->rc_dev, i > 0 ? B.ctl_dev + i - 1 : nullptr, B.ctl_dev + i, forced ? 1 : 0, e->scene + i,
                                             (long long)nctu * 64);
@@ -530,7 +532,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 IntraParams np;
                 np.g = g; np.src = s.src; np.rec = rec; np.cus = s.cus; np.coefs = s.coefs; np.progress = e->progress;
                 np.ctl = B.ctl_dev + i; np.second_pass = 0; np.mode_cost = e->mode_cost; np.intra_best = e->intra_best;
-                np.intra_in_p = p.intra_in_p;
+                np.intra_in_p = p.intra_in_p; np.satd1 = e->satdf[1];
                 if (!forced) {
                     InterParams ip;
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
@@ -574,13 +576,21 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                         HB_LAUNCHED(ctx);
                     }
                 }
+                if (p.sao) {
+                    SaoParams sp;
+                    sp.g = g; sp.src = s.src; sp.pre = rec; sp.out = fin; sp.cus = s.cus; sp.ctl = B.ctl_dev + i; sp.sao = s.sao;
+                    k_sao_decide<<<nctu, 256, 0, st>>>(sp);
+                    HB_LAUNCHED(ctx);
+                    k_sao_apply<<<nctu, 256, 0, st>>>(sp);
+                    HB_LAUNCHED(ctx);
+                }
                 {
                     const int border = 2 * kPad * (g.wc + 2 * kPad) + g.hc * 2 * kPad;
-                    k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(rec, g);
+                    k_border<<<dim3((border + 255) / 256, 3), 256, 0, st>>>(fin, g);
                     HB_LAUNCHED(ctx);
                 }
                 if (p.keep_recon || p.hash_sei) {
-                    const pixel *srcp[3] = {rec.y, rec.u, rec.v};
+                    const pixel *srcp[3] = {fin.y, fin.u, fin.v};
                     pixel *dstp[3] = {s.keep.y, s.keep.u, s.keep.v};
                     for (int c = 0; c < 3; c++) {
                         const int w = c ? g.wc / 2 : g.wc, h = c ? g.hc / 2 : g.hc, stride = c ? g.recc_stride : g.rec_stride;
@@ -760,6 +770,7 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
             h.ue(0);
             h.ue(idr ? 2 : 1);
             if (!idr) { h.put(pocs[i] & 255, 8); h.flag(true); }
+            if (p.sao) { h.flag(true); h.flag(true); }              // slice_sao_luma_flag, slice_sao_chroma_flag
             if (!idr) { h.flag(false); h.ue(0); }
             h.se(qps[i] - 26);
             h.ue(g.ctuh - 1);
@@ -860,6 +871,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
             HB_TRY(dev_alloc(E, &s.row_len, (size_t)g.ctuh));
             HB_TRY(dev_alloc(E, &s.ctx_save, (size_t)g.ctuh * kNumCtx));
             if (p.keep_recon || p.hash_sei) HB_TRY(alloc_planes(E, &s.keep, g.wc, g.hc));
+            if (p.sao) HB_TRY(dev_alloc(E, &s.sao, (size_t)nctu));
         }
         HB_TRY(dev_alloc(E, &B.row_ready_all, (size_t)max_batch * g.ctuh));
         for (int i = 0; i < max_batch; i++) B.slot[i].row_ready = B.row_ready_all + (size_t)i * g.ctuh;
@@ -885,14 +897,15 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
         B.kev_me.resize((size_t)max_batch);
         for (auto &ev : B.kev_me) HB_CUDA(ctx, cudaEventCreate(&ev));
     }
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < (p.sao ? 3 : 2); k++)
         for (int c = 0; c < 3; c++) {
             const int h = c ? g.hc / 2 : g.hc, pad = c ? kPad / 2 : kPad;
             const int stride = c ? g.recc_stride : g.rec_stride;
             HB_TRY(dev_alloc(E, &E->rec_base[k][c], (size_t)stride * (h + 2 * pad)));
             HB_CUDA(ctx, cudaMemsetAsync(E->rec_base[k][c], 0, (size_t)stride * (h + 2 * pad) * sizeof(pixel), ctx->stream));
             pixel *origin = E->rec_base[k][c] + (size_t)pad * stride + pad;
-            if (c == 0) E->rec[k].y = origin; else if (c == 1) E->rec[k].u = origin; else E->rec[k].v = origin;
+            Planes &dst = k == 2 ? E->pre : E->rec[k];
+            if (c == 0) dst.y = origin; else if (c == 1) dst.u = origin; else dst.v = origin;
         }
     HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));

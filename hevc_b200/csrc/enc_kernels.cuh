@@ -51,7 +51,8 @@ struct IntraParams {
     int *progress;                       // [ctuh], zeroed before launch
     FrameCtl *ctl;
     int *mode_cost;                      // [cus][35] luma SATD per intra mode from k_intra_search
-    int *intra_best;                     // [cus] min over the 35 modes
+    int *intra_best;                     // [cus] min over the 35 modes (INT_MAX: not searched)
+    const int *satd1;                    // [cus] luma SATD after the first merge-aware pass: gate of the P-frame search
     int second_pass;                     // 1: run only when ctl->redo is set (first key frame of a stream under rate control)
     int intra_in_p;                      // P frames: search every CU and reconstruct the CUs the inter kernel marked intra
 };
@@ -62,6 +63,14 @@ struct DeblockParams {
     const CuInfo *cus;
     const FrameCtl *ctl;
     int dir;                             // 0 vertical edges, 1 horizontal edges
+};
+
+struct SaoParams {
+    Geom g;
+    Planes src, pre, out;                // source, deblocked reconstruction (padded strides), final reconstruction (padded strides)
+    const CuInfo *cus;
+    const FrameCtl *ctl;
+    SaoCtu *sao;                         // [ctuh * ctuw]
 };
 
 struct ModeParams {
@@ -78,6 +87,7 @@ struct EntropyFrame {
     uint8_t *out;                        // [ctuh][row_cap]
     uint32_t *row_len;                   // [ctuh]
     const FrameCtl *ctl;                 // slice QP (context initialisation)
+    const SaoCtu *sao;                   // [ctuh * ctuw] SAO parameters, or null: SAO disabled
     uint8_t *ctx_save;                   // [ctuh][kNumCtx] WPP context snapshots (after the 2nd CTU of each row)
     int *row_ready;                      // [ctuh] snapshot-published flags, zeroed before the launch
     unsigned long long *trace;           // debug (HB_ENTROPY_TRACE): [ctuh][2] globaltimer at row start (after the hand-off) / end, or null
@@ -116,6 +126,10 @@ struct __align__(16) EntropyWarpScratch {
     uint2 ctx[kNumCtx + 2];              // x: the four rangeTabLps bytes of the context's state; y: state << 1 | mps, next-LPS state << 8
     CuStage cu[3][4];                    // ring of staged CTUs (cp.async, two CTUs ahead); 8-byte aligned for the copies
     CuSyntax above[3][2];                // syntax of the two CUs above each staged CTU (skip-flag context)
+    SaoCtu sao_cur[3], sao_up[3];        // SAO parameters of the staged CTUs and of the CTUs above them (cp.async)
+    SaoCtu sao_left;                     // ... of the CTU coded last in this row
+    uint32_t saob[52];                   // sao() bin list of the current CTU
+    uint32_t nsao, pad3[3];
     // byte-output side of the arithmetic coder (touched only when a byte leaves it)
     uint8_t *out;
     uint32_t pos, cap;
@@ -131,6 +145,7 @@ struct __align__(16) EntropyWarpScratch {
     uint32_t pad2;
 };
 static_assert(offsetof(EntropyWarpScratch, cu) % 8 == 0 && offsetof(EntropyWarpScratch, above) % 8 == 0, "cp.async destinations");
+static_assert(offsetof(EntropyWarpScratch, sao_cur) % 16 == 0 && offsetof(EntropyWarpScratch, sao_up) % 16 == 0, "cp.async destinations");
 static_assert(sizeof(EntropyWarpScratch) % 16 == 0, "per-warp scratch must keep 16-byte alignment");
 // uploads the dp2a-packed interpolation taps into constant memory (call once per process/device before k_inter)
 cudaError_t upload_inter_constants(cudaStream_t st);
@@ -146,6 +161,8 @@ __global__ void k_intra_search(IntraParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_deblock(DeblockParams p);
 __global__ void k_modes(ModeParams p);
+__global__ void k_sao_decide(SaoParams p);
+__global__ void k_sao_apply(SaoParams p);
 __global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int force_idr, const SceneStat *scene, long long ds_samples);
 __global__ void k_rc_redo(RcState *rc, FrameCtl *ctl);
 __global__ void k_entropy(EntropyParams p);

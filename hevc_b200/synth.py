@@ -136,13 +136,13 @@ class TorchSynthClip:
         return self.torch.stack([self.frame(start + i) for i in range(count)])
 
 
-CONTENT_CLASSES = ('base', 'hardcut', 'pan', 'static', 'grain')
+CONTENT_CLASSES = ('base', 'hardcut', 'pan', 'static', 'grain', 'clean')
 
 
 def content_clip(kind: str, width: int, height: int, n_frames: int, seed: int = 0):
     """The R-D harness's content classes -> list of (y, u, v) uint8 frames.  ``base``: the default recipe (slow pan, moving
     patches that cover and uncover background, grain sigma 2); ``hardcut``: two unrelated scenes joined in the middle;
-    ``pan``: fast global pan (6.5, 2.25 px / frame); ``static``: nothing moves, only the grain changes; ``grain``: sigma 5."""
+    ``pan``: fast global pan (6.5, 2.25 px / frame); ``static``: nothing moves, only the grain changes; ``grain``: sigma 5; ``clean``: no grain."""
     if kind == 'base':
         c = SynthClip(width, height, seed=seed)
         return [c.frame(i) for i in range(n_frames)]
@@ -155,6 +155,9 @@ def content_clip(kind: str, width: int, height: int, n_frames: int, seed: int = 
         return [c.frame(i) for i in range(n_frames)]
     if kind == 'static':
         c = SynthClip(width, height, seed=seed, pan=(0.0, 0.0), patch_speed=0.0)
+        return [c.frame(i) for i in range(n_frames)]
+    if kind == 'clean':
+        c = SynthClip(width, height, seed=seed, noise=0.0)
         return [c.frame(i) for i in range(n_frames)]
     if kind == 'grain':
         c = SynthClip(width, height, seed=seed, noise=5.0)

@@ -180,7 +180,7 @@ size_t orc_write_sps(const orc_enc_params *p, uint8_t *out, size_t cap)
     orc_put_ue(&b, 0);                            /* max_transform_hierarchy_depth_intra */
     orc_put(&b, 0, 1);                            /* scaling_list_enabled */
     orc_put(&b, 0, 1);                            /* amp_enabled */
-    orc_put(&b, 0, 1);                            /* sample_adaptive_offset_enabled */
+    orc_put(&b, p->sao ? 1 : 0, 1);               /* sample_adaptive_offset_enabled */
     orc_put(&b, 0, 1);                            /* pcm_enabled */
     orc_put_ue(&b, 1);                            /* num_short_term_ref_pic_sets */
     orc_put_ue(&b, 1);                            /*   num_negative_pics */
@@ -361,7 +361,6 @@ size_t orc_write_slice_header(const orc_enc_params *p, int nal_type, int slice_t
                               const uint32_t *entry, int n_entry, uint8_t *out, size_t cap)
 {
     orc_bits b;
-    (void)p;
     orc_bits_init(&b, out, cap);
     orc_put(&b, 1, 1);                            /* first_slice_segment_in_pic */
     if (nal_type >= 16 && nal_type <= 23)
@@ -371,6 +370,10 @@ size_t orc_write_slice_header(const orc_enc_params *p, int nal_type, int slice_t
     if (nal_type != 19 && nal_type != 20) {
         orc_put(&b, poc & 255, 8);                /* slice_pic_order_cnt_lsb */
         orc_put(&b, 1, 1);                        /* short_term_ref_pic_set_sps_flag (single set: no idx bits) */
+    }
+    if (p->sao) {
+        orc_put(&b, 1, 1);                        /* slice_sao_luma_flag */
+        orc_put(&b, 1, 1);                        /* slice_sao_chroma_flag */
     }
     if (slice_type == 1) {
         orc_put(&b, 0, 1);                        /* num_ref_idx_active_override */

@@ -48,7 +48,9 @@ enum {
     CX_GR1 = 110,           /* 24 */
     CX_GR2 = 134,           /* 6 */
     CX_QP_DELTA = 140,      /* 2 */
-    CX_COUNT = 142
+    CX_SAO_MERGE = 142,     /* 1 */
+    CX_SAO_TYPE = 143,      /* 1 */
+    CX_COUNT = 144
 };
 
 #define CNU 154
@@ -74,7 +76,8 @@ static const uint8_t k_init[2][CX_COUNT] = {
         140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,                  /* sig_coeff_flag */
         140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,   /* greater1 */
         138, 153, 136, 167, 152, 152,                    /* greater2 */
-        154, 154 },                                      /* cu_qp_delta_abs */
+        154, 154,                                        /* cu_qp_delta_abs */
+        153, 200 },                                      /* sao_merge_left/up_flag, sao_type_idx */
     {   107, 139, 126,
         197, 185, 201,
         149,
@@ -95,7 +98,8 @@ static const uint8_t k_init[2][CX_COUNT] = {
         170, 153, 123, 123, 107, 121, 107, 121, 167, 151, 183, 140, 151, 183, 140,
         154, 196, 196, 167, 154, 152, 167, 182, 182, 134, 149, 136, 153, 121, 136, 137, 169, 194, 166, 167, 154, 167, 137, 182,
         107, 167, 91, 122, 107, 167,
-        154, 154 }};
+        154, 154,
+        153, 185 }};
 
 /* ------------------------------------------------------------------ arithmetic encoder (HM TEncBinCABAC form of 9.3.4) */
 
@@ -608,11 +612,52 @@ static void write_cu(cabac *c, orc_frame_syntax *f, int cx, int cy)
     write_transform_unit(c, cu, coef, 1);
 }
 
+static int sao_equal(const orc_sao *a, const orc_sao *b) { return memcmp(a, b, sizeof *a) == 0; }
+
+/* sao() of one CTU (7.3.8.3).  Merging is by identity: the flag is set when the left (else the upper) CTU carries exactly the
+ * same parameters, so it never changes the reconstruction, only the signalling. */
+static void write_sao(cabac *c, const orc_frame_syntax *f, int rx, int ry)
+{
+    const orc_sao *s = &f->sao[ry * f->ctuw + rx];
+    const int cmax = (1 << ((f->bit_depth < 10 ? f->bit_depth : 10) - 5)) - 1;
+    if (rx > 0) {
+        const int m = sao_equal(s, s - 1);
+        cb_bin(c, CX_SAO_MERGE, m);
+        if (m) return;
+    }
+    if (ry > 0) {
+        const int m = sao_equal(s, s - f->ctuw);
+        cb_bin(c, CX_SAO_MERGE, m);
+        if (m) return;
+    }
+    for (int ci = 0; ci < 3; ci++) {
+        const int g = ci ? 1 : 0, type = s->type[g];
+        if (ci < 2) {                              /* sao_type_idx_luma / _chroma: TR cMax 2, first bin context coded */
+            cb_bin(c, CX_SAO_TYPE, type != 0);
+            if (type) cb_bypass(c, type == 2);
+        }
+        if (!type) continue;
+        for (int i = 0; i < 4; i++) {              /* sao_offset_abs: TR, bypass */
+            const int a = abs(s->offset[ci][i]);
+            for (int k = 0; k < a; k++) cb_bypass(c, 1);
+            if (a < cmax) cb_bypass(c, 0);
+        }
+        if (type == 1) {
+            for (int i = 0; i < 4; i++)
+                if (s->offset[ci][i]) cb_bypass(c, s->offset[ci][i] < 0);
+            cb_bypass_bits(c, s->band[ci], 5);
+        } else if (ci < 2) {
+            cb_bypass_bits(c, s->eo_class[g], 2);
+        }
+    }
+}
+
 /* coding_quadtree at CTU level: split to four 16x16 CUs (those inside the picture) */
 static void write_ctu(cabac *c, orc_frame_syntax *f, int ctx_x, int ctx_y)
 {
     const int x0 = ctx_x * 32, y0 = ctx_y * 32;
     const int cx0 = ctx_x * 2, cy0 = ctx_y * 2;
+    if (f->sao) write_sao(c, f, ctx_x, ctx_y);
     if (x0 + 32 <= f->wc && y0 + 32 <= f->hc) {
         /* depth-0 split flag: neighbours, when available, are at depth 1 > 0 */
         const int inc = cu_avail(f, cx0, cy0, cx0 - 1, cy0) + cu_avail(f, cx0, cy0, cx0, cy0 - 1);

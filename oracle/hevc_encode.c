@@ -35,6 +35,8 @@ struct orc_encoder {
     orc_enc_params prm;
     int wc, hc, cuw, cuh, ctuw, ctuh;
     plane src[3], rec[2][3];
+    plane pre[3];                    /* SAO on: reconstruction before SAO (deblocked); rec[cur] then receives the SAO output */
+    orc_sao *sao;                    /* [ctuh][ctuw] SAO parameters of the current frame */
     int cur;                         /* index of the reconstruction being written */
     plane ds[2];                     /* quarter-resolution source: [cur_ds], [1 - cur_ds] = previous frame */
     int cur_ds;
@@ -88,7 +90,9 @@ orc_encoder *orc_enc_create(const orc_enc_params *p)
         plane_alloc(&e->src[c], e->wc >> sh, e->hc >> sh, 0);
         plane_alloc(&e->rec[0][c], e->wc >> sh, e->hc >> sh, ORC_PAD >> sh);
         plane_alloc(&e->rec[1][c], e->wc >> sh, e->hc >> sh, ORC_PAD >> sh);
+        plane_alloc(&e->pre[c], e->wc >> sh, e->hc >> sh, ORC_PAD >> sh);
     }
+    e->sao = (orc_sao *)calloc((size_t)e->ctuw * e->ctuh, sizeof(orc_sao));
     plane_alloc(&e->ds[0], e->wc / 4, e->hc / 4, 0);
     plane_alloc(&e->ds[1], e->wc / 4, e->hc / 4, 0);
     e->cus = (orc_cu *)calloc((size_t)e->cuw * e->cuh, sizeof(orc_cu));
@@ -111,7 +115,8 @@ orc_encoder *orc_enc_create(const orc_enc_params *p)
 void orc_enc_destroy(orc_encoder *e)
 {
     if (!e) return;
-    for (int c = 0; c < 3; c++) { free(e->src[c].base); free(e->rec[0][c].base); free(e->rec[1][c].base); }
+    for (int c = 0; c < 3; c++) { free(e->src[c].base); free(e->rec[0][c].base); free(e->rec[1][c].base); free(e->pre[c].base); }
+    free(e->sao);
     free(e->ds[0].base); free(e->ds[1].base);
     free(e->cus); free(e->coefs); free(e->cmv); free(e->mvf[0]); free(e->mvf[1]); free(e->satdf[0]); free(e->satdf[1]); free(e->costf); free(e->mode_cost); free(e->payload); free(e->row_off); free(e->row_len);
     free(e);
@@ -139,6 +144,9 @@ size_t orc_enc_headers(orc_encoder *e, uint8_t *out, size_t cap)
     o += orc_write_pps(&e->prm, out + o, cap - o);
     return o;
 }
+
+/* planes the frame is reconstructed and deblocked in: with SAO on that is the `pre` set, and SAO writes the final picture */
+static plane *work_planes(orc_encoder *e) { return e->prm.sao ? e->pre : e->rec[e->cur]; }
 
 /* ------------------------------------------------------------------ ingest */
 
@@ -254,12 +262,23 @@ static void gather_neighbours(const orc_encoder *e, const plane *r, int cx, int 
 /* Intra mode search of every CU at once: luma SATD of the 35 predictions built from the SOURCE picture's neighbour samples
  * (same availability / substitution rules as the real prediction), so that nothing here depends on the reconstruction and the
  * GPU runs it as one launch.  The wavefront stage adds the signalling cost against the real most-probable modes. */
-static void intra_search_all(orc_encoder *e)
+static void intra_search_all(orc_encoder *e, const int32_t *satd1, int lambda)
 {
-    const int bd = e->prm.bit_depth;
+    const int bd = e->prm.bit_depth, ncu = e->cuw * e->cuh;
+    /* P frames (satd1 = luma SATD of every CU's vector after the first merge-aware pass): only CUs that inter prediction
+     * serves badly are searched -- a residual worth coding at this quantiser (SATD above lambda / 2 per sample) that is also
+     * more than twice the frame's mean SATD, or above 4 lambda / 8 grey levels per sample outright */
+    const long thr = (256L * lambda) >> 9;
+    long long sum = 0;
+    if (satd1)
+        for (int i = 0; i < ncu; i++) sum += satd1[i];
 #pragma omp parallel for schedule(dynamic, 8)
-    for (int idx = 0; idx < e->cuw * e->cuh; idx++) {
+    for (int idx = 0; idx < ncu; idx++) {
         const int cx = idx % e->cuw, cy = idx / e->cuw;
+        if (satd1 && !(satd1[idx] > thr && ((long long)satd1[idx] * ncu > 2 * sum || satd1[idx] > 8 * thr || satd1[idx] > (2048 << (bd - 8))))) {
+            e->mode_cost[idx * 35] = -1;          /* not a candidate */
+            continue;
+        }
         const pixel *src = e->src[0].p + (size_t)cy * 16 * e->src[0].stride + cx * 16;
         pixel nbs[65], flts[65], pred[256];
         gather_neighbours(e, &e->src[0], cx, cy, 16, nbs);
@@ -311,8 +330,8 @@ static void intra_cu(orc_encoder *e, const orc_frame_syntax *fs, plane *rec, int
 static void intra_pass(orc_encoder *e, int qp, int intra_slice, int only_flagged)
 {
     const int lambda = k_lambda_q8[qp] << (e->prm.bit_depth - 8);
-    plane *rec = e->rec[e->cur];
-    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, intra_slice, qp, e->cus, e->coefs};
+    plane *rec = work_planes(e);
+    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, intra_slice, qp, e->cus, e->coefs, NULL, e->prm.bit_depth};
     for (int ctu = 0; ctu < e->ctuw * e->ctuh; ctu++)
         for (int k = 0; k < 4; k++) {
             const int cx = (ctu % e->ctuw) * 2 + (k & 1), cy = (ctu / e->ctuw) * 2 + (k >> 1);
@@ -421,7 +440,7 @@ static void encode_inter_frame(orc_encoder *e, int qp)
 {
     const int bd = e->prm.bit_depth;
     const int lambda = k_lambda_q8[qp] << (bd - 8);
-    plane *rec = e->rec[e->cur];
+    plane *rec = work_planes(e);
     const plane *ref = e->rec[1 - e->cur];
     /* every loop over CUs below is order-independent (that is what lets the GPU run them as one launch each), so the model
      * spreads them over the host cores */
@@ -536,7 +555,7 @@ static void encode_inter_frame(orc_encoder *e, int qp)
      * signalling beats the final inter choice by a quarter.  The margin covers what SATD does not see: the inter CU is
      * usually skipped or merged (no residual, ~1 bit) while an intra CU always codes a mode and a residual, and the source
      * neighbours flatter the intra prediction. */
-    if (e->prm.intra_in_p) intra_search_all(e);
+    if (e->prm.intra_in_p) intra_search_all(e, e->satdf[1], lambda);      /* [1] = output of the first merge-aware pass */
     const int16_t *mvfinal = e->mvf[MERGE_PASSES & 1];
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
     for (int cy = 0; cy < e->cuh; cy++)
@@ -553,9 +572,9 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             if (e->prm.intra_in_p) {
                 const int idx = cy * e->cuw + cx;
                 long ibest = e->mode_cost[idx * 35];
-                for (int m = 1; m < 35; m++) if (e->mode_cost[idx * 35 + m] < ibest) ibest = e->mode_cost[idx * 35 + m];
+                for (int m = 1; m < 35 && ibest >= 0; m++) if (e->mode_cost[idx * 35 + m] < ibest) ibest = e->mode_cost[idx * 35 + m];
                 const long icost = ibest + ((lambda * 12) >> 8);
-                if (icost * 4 < (long)e->costf[idx] * 3) {
+                if (ibest >= 0 && icost * 4 < (long)e->costf[idx] * 3) {
                     cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->cbf = 0;     /* reconstructed by the wavefront stage below */
                     continue;
                 }
@@ -678,6 +697,165 @@ static void deblock_frame(orc_encoder *e, plane *rec, int qp)
             }
 }
 
+/* ------------------------------------------------------------------ sample adaptive offset (H.265 8.7.3) */
+
+typedef struct {
+    long long cnt[4][5], sum[4][5];       /* edge classes x categories 1..4: samples, sum of (source - reconstruction) */
+    long long bcnt[32], bsum[32];         /* bands */
+} sao_stats;
+
+static const int8_t k_sao_dx[4][2] = {{-1, 1}, {0, 0}, {-1, 1}, {1, -1}}, k_sao_dy[4][2] = {{0, 0}, {-1, 1}, {-1, 1}, {-1, 1}};
+
+static int sgn(int v) { return (v > 0) - (v < 0); }
+
+/* edge category of 8.7.3.2: 1 valley, 2 / 3 edges, 4 peak, 0 none */
+static int sao_category(int r, int a, int b)
+{
+    static const uint8_t map[5] = {1, 2, 0, 3, 4};
+    return map[2 + sgn(r - a) + sgn(r - b)];
+}
+
+static void sao_collect(const orc_encoder *e, const plane *rec, const plane *src, int N, int rx, int ry, sao_stats *st)
+{
+    const int x0 = rx * N, y0 = ry * N, bshift = e->prm.bit_depth - 5;
+    memset(st, 0, sizeof *st);
+    for (int y = y0; y < y0 + N && y < rec->h; y++)
+        for (int x = x0; x < x0 + N && x < rec->w; x++) {
+            const int r = rec->p[(size_t)y * rec->stride + x], d = (int)src->p[(size_t)y * src->stride + x] - r;
+            st->bcnt[r >> bshift]++;
+            st->bsum[r >> bshift] += d;
+            for (int k = 0; k < 4; k++) {
+                const int xa = x + k_sao_dx[k][0], ya = y + k_sao_dy[k][0], xb = x + k_sao_dx[k][1], yb = y + k_sao_dy[k][1];
+                if (xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= rec->w || xb >= rec->w || ya >= rec->h || yb >= rec->h) continue;
+                const int cat = sao_category(r, rec->p[(size_t)ya * rec->stride + xa], rec->p[(size_t)yb * rec->stride + xb]);
+                if (cat) { st->cnt[k][cat]++; st->sum[k][cat] += d; }
+            }
+        }
+}
+
+/* best offset in [lo, hi] for `cnt` samples whose errors sum to `sum`: minimises (cnt o^2 - 2 o sum) * 65536 + lam * bits,
+ * walking from the rounded mean towards zero (first minimum wins).  sign_bit: band offsets carry a sign bit when non-zero. */
+static int sao_offset(long long cnt, long long sum, int lo, int hi, long long lam, int cmax, int sign_bit, long long *cost_out)
+{
+    long long best = lam * 1;                 /* offset 0: one bin */
+    int bo = 0;
+    if (cnt) {
+        int o = (int)(sum >= 0 ? (sum + cnt / 2) / cnt : -((-sum + cnt / 2) / cnt));
+        o = clampi(o, lo, hi);
+        for (int t = o; t != 0; t += t > 0 ? -1 : 1) {
+            const int a = abs(t);
+            const long long cost = (cnt * t * t - 2 * t * sum) * 65536 + lam * ((a < cmax ? a + 1 : cmax) + sign_bit);
+            if (cost < best) { best = cost; bo = t; }
+        }
+    }
+    *cost_out = best;
+    return bo;
+}
+
+/* parameters of one component group (luma, or Cb + Cr) from the statistics of its `ncomp` components */
+static void sao_decide_group(const sao_stats *st, int ncomp, long long lam, int cmax, orc_sao *out, int g)
+{
+    long long best = lam * 1;                 /* off: sao_type_idx = 0 */
+    int type = 0, eo_class = 0, band[2] = {0, 0};
+    int8_t off[2][4];
+    memset(off, 0, sizeof off);
+    for (int k = 0; k < 4; k++) {             /* edge classes */
+        long long cost = lam * 4;             /* type (2 bins) + class (2 bins) */
+        int8_t o[2][4];
+        for (int c = 0; c < ncomp; c++)
+            for (int cat = 1; cat <= 4; cat++) {
+                long long cc;
+                o[c][cat - 1] = (int8_t)sao_offset(st[c].cnt[k][cat], st[c].sum[k][cat], cat <= 2 ? 0 : -cmax, cat <= 2 ? cmax : 0, lam, cmax, 0, &cc);
+                cost += cc;
+            }
+        if (cost < best) { best = cost; type = 2; eo_class = k; memcpy(off, o, sizeof off); }
+    }
+    {                                         /* band offset: per component the best window of four consecutive bands */
+        long long cost = lam * 2;
+        int8_t o[2][4];
+        int bp[2] = {0, 0};
+        for (int c = 0; c < ncomp; c++) {
+            long long bc[32], wbest = 0;
+            int8_t bo_[32];
+            for (int b = 0; b < 32; b++) bo_[b] = (int8_t)sao_offset(st[c].bcnt[b], st[c].bsum[b], -cmax, cmax, lam, cmax, 1, &bc[b]);
+            for (int s0 = 0; s0 <= 28; s0++) {
+                const long long w = bc[s0] + bc[s0 + 1] + bc[s0 + 2] + bc[s0 + 3];
+                if (s0 == 0 || w < wbest) { wbest = w; bp[c] = s0; }
+            }
+            for (int i = 0; i < 4; i++) o[c][i] = bo_[bp[c] + i];
+            cost += wbest + lam * 5;
+        }
+        if (cost < best) { best = cost; type = 1; band[0] = bp[0]; band[1] = bp[1]; memcpy(off, o, sizeof off); }
+    }
+    out->type[g] = (uint8_t)type;
+    out->eo_class[g] = (uint8_t)(type == 2 ? eo_class : 0);
+    for (int c = 0; c < ncomp; c++) {
+        out->band[g + c] = (uint8_t)(type == 1 ? band[c] : 0);
+        for (int i = 0; i < 4; i++) out->offset[g + c][i] = type ? off[c][i] : 0;
+    }
+}
+
+static void sao_apply_ctb(const orc_encoder *e, const plane *in, plane *out, int N, int rx, int ry, int type, int eo_class, int band,
+                          const int8_t *off)
+{
+    const int x0 = rx * N, y0 = ry * N, bd = e->prm.bit_depth, maxv = (1 << bd) - 1, bshift = bd - 5;
+    for (int y = y0; y < y0 + N && y < in->h; y++)
+        for (int x = x0; x < x0 + N && x < in->w; x++) {
+            const int r = in->p[(size_t)y * in->stride + x];
+            int v = r;
+            if (type == 1) {
+                const int k = ((r >> bshift) - band) & 31;
+                if (k < 4) v = clampi(r + off[k], 0, maxv);
+            } else if (type == 2) {
+                const int xa = x + k_sao_dx[eo_class][0], ya = y + k_sao_dy[eo_class][0], xb = x + k_sao_dx[eo_class][1], yb = y + k_sao_dy[eo_class][1];
+                if (!(xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= in->w || xb >= in->w || ya >= in->h || yb >= in->h)) {
+                    const int cat = sao_category(r, in->p[(size_t)ya * in->stride + xa], in->p[(size_t)yb * in->stride + xb]);
+                    if (cat) v = clampi(r + off[cat - 1], 0, maxv);
+                }
+            }
+            out->p[(size_t)y * out->stride + x] = (pixel)v;
+        }
+}
+
+/* decide (per CTU, independently: one launch on the GPU) and apply: `pre` (deblocked) -> rec[cur].  The Lagrangian is twice
+ * the squared SATD-domain lambda: the rest of this encoder decides without RDO, and at lambda^2 SAO bought its PSNR at a worse
+ * rate than a QP change does (BD-rate +1..+3 % on the calibration clips; -1.4 / -2.1 % at 2 lambda^2). */
+static void sao_frame(orc_encoder *e, int qp)
+{
+    const int bd = e->prm.bit_depth, cmax = (1 << ((bd < 10 ? bd : 10) - 5)) - 1;
+    const long long ly = (long long)(k_lambda_q8[qp] << (bd - 8)), lc = (long long)(k_lambda_q8[chroma_qp(qp)] << (bd - 8));
+    plane *out = e->rec[e->cur];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int ctu = 0; ctu < e->ctuw * e->ctuh; ctu++) {
+        const int rx = ctu % e->ctuw, ry = ctu / e->ctuw;
+        orc_sao *s = &e->sao[ctu];
+        sao_stats st[2];
+        memset(s, 0, sizeof *s);
+        {   /* a CTU whose CUs are all inter without residual is a copy of reference samples that already went through SAO:
+             * offsetting it again fits noise and costs bits in every frame -- left off */
+            int copied = 1;
+            for (int k = 0; k < 4; k++) {
+                const int cx = 2 * rx + (k & 1), cy = 2 * ry + (k >> 1);
+                if (cx < e->cuw && cy < e->cuh && (e->cus[cy * e->cuw + cx].pred_mode == 0 || e->cus[cy * e->cuw + cx].cbf)) copied = 0;
+            }
+            if (copied) continue;
+        }
+        sao_collect(e, &e->pre[0], &e->src[0], 32, rx, ry, &st[0]);
+        sao_decide_group(st, 1, 2 * ly * ly, cmax, s, 0);
+        sao_collect(e, &e->pre[1], &e->src[1], 16, rx, ry, &st[0]);
+        sao_collect(e, &e->pre[2], &e->src[2], 16, rx, ry, &st[1]);
+        sao_decide_group(st, 2, 2 * lc * lc, cmax, s, 1);
+    }
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int ctu = 0; ctu < e->ctuw * e->ctuh; ctu++) {
+        const int rx = ctu % e->ctuw, ry = ctu / e->ctuw;
+        const orc_sao *s = &e->sao[ctu];
+        sao_apply_ctb(e, &e->pre[0], &out[0], 32, rx, ry, s->type[0], s->eo_class[0], s->band[0], s->offset[0]);
+        sao_apply_ctb(e, &e->pre[1], &out[1], 16, rx, ry, s->type[1], s->eo_class[1], s->band[1], s->offset[1]);
+        sao_apply_ctb(e, &e->pre[2], &out[2], 16, rx, ry, s->type[1], s->eo_class[1], s->band[2], s->offset[2]);
+    }
+}
+
 /* ------------------------------------------------------------------ access unit */
 
 static void picture_md5(const orc_encoder *e, const plane *rec, uint8_t md5[3][16])
@@ -710,7 +888,7 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
     const int idr = force_idr || e->frame_no == 0 || (p->keyint > 0 && e->poc + 1 >= p->keyint) || cut;
     if (idr) e->poc = 0; else e->poc++;
     int qp = clampi(orc_rc_pick_qp(&e->rc, p, idr), 0, 51);
-    if (idr) { intra_search_all(e); encode_intra_frame(e, qp); } else encode_inter_frame(e, qp);
+    if (idr) { intra_search_all(e, NULL, 0); encode_intra_frame(e, qp); } else encode_inter_frame(e, qp);
     long long est16 = 0;
     for (int i = 0; i < e->cuw * e->cuh; i++)
         est16 += orc_rc_cu_estimate(e->coefs + (size_t)i * ORC_CU_COEFS, e->cus[i].cbf);
@@ -726,12 +904,13 @@ long orc_enc_frame(orc_encoder *e, const pixel *y, int ys, const pixel *u, const
                 est16 += orc_rc_cu_estimate(e->coefs + (size_t)i * ORC_CU_COEFS, e->cus[i].cbf);
         }
     }
+    if (p->deblock) deblock_frame(e, work_planes(e), qp);
+    if (p->sao) sao_frame(e, qp);
     plane *rec = e->rec[e->cur];
-    if (p->deblock) deblock_frame(e, rec, qp);
     for (int c = 0; c < 3; c++) plane_extend(&rec[c]);
     orc_rc_update(&e->rc, idr, qp, est16);
 
-    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, idr, qp, e->cus, e->coefs};
+    orc_frame_syntax fs = {e->wc, e->hc, e->cuw, e->cuh, e->ctuw, e->ctuh, idr, qp, e->cus, e->coefs, p->sao ? e->sao : NULL, p->bit_depth};
     if (orc_cabac_encode_frame(&fs, e->payload, e->payload_cap, e->row_off, e->row_len) != 0)
         return -1;
 

@@ -47,6 +47,15 @@ typedef struct orc_cu {
     int16_t mvx, mvy;             /* quarter-sample units */
 } orc_cu;
 
+/* sample adaptive offset parameters of one CTU (7.3.8.3): per component group type 0 off / 1 band / 2 edge */
+typedef struct orc_sao {
+    uint8_t type[2];              /* [0] luma, [1] chroma (Cb and Cr share type and edge class) */
+    uint8_t eo_class[2];
+    uint8_t band[3];              /* band position per component */
+    int8_t offset[3][4];          /* signed offsets per component (edge: categories 1..4; band: the four bands) */
+    uint8_t pad;
+} orc_sao;
+
 #define ORC_CU_COEFS 384          /* 16x16 luma + 8x8 Cb + 8x8 Cr, raster inside each block */
 #define ORC_PAD 80                /* luma border of reconstructed planes */
 
@@ -91,6 +100,8 @@ typedef struct orc_frame_syntax {
     int qp;
     orc_cu *cu;                   /* [cuh][cuw] */
     const int16_t *coef;          /* [cuh*cuw][ORC_CU_COEFS] */
+    const orc_sao *sao;           /* [ctuh][ctuw], or NULL: SAO disabled */
+    int bit_depth;
 } orc_frame_syntax;
 
 /* encode all CTU rows as WPP sub-streams; row r -> out + row_off[r], size row_len[r].  returns 0 / -1 */

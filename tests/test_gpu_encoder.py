@@ -456,3 +456,24 @@ def test_intra_cus_in_p_frames_match_cpu_model(ctx):
             for c in range(3):
                 assert (m_recs[i][c] == g_recs[i][c]).all(), (on, i, c)
         assert g_stream == m_stream
+
+
+@pytest.mark.parametrize('w,h,depth,n,qp', [(192, 112, 8, 6, (30, 32)), (200, 120, 10, 5, (22, 24)), (416, 240, 8, 5, (12, 14)),
+                                            (328, 184, 10, 6, (38, 40)), (16, 16, 8, 3, (30, 32)), (96, 32, 10, 4, (26, 28))])
+def test_sao_matches_cpu_model(ctx, w, h, depth, n, qp):
+    """sample adaptive offset: per-CTU statistics, parameter decision (edge classes + band offset, luma and chroma), merge
+    signalling and application equal the model's -- parameters, reconstruction (= the next frame's reference) and bytes; the
+    FFmpeg decoder reproduces the reconstruction (picture hash on)"""
+    from oracle import fforacle
+    p = ec.b200_params(w, h, depth, keyint=4)
+    frames = ec.clip_frames(w, h, n, seed=4)
+    m_stream, _, m_recs, m_decs = ec.run_model(p, frames, qp[0], qp[1], hash_sei=True, sao=True)
+    g_stream, g_recs, g_decs = _gpu_encode(ctx, p, frames, qp, batch=8, sao=True)
+    for i in range(n):
+        for c in range(3):
+            assert (m_recs[i][c] == g_recs[i][c]).all(), f'frame {i} plane {c} reconstruction differs'
+    assert g_stream == m_stream
+    off_stream, _, _ = _gpu_encode(ctx, p, frames, qp, batch=8, sao=False, read_back=False)
+    assert off_stream != g_stream
+    dec = fforacle.decode_hevc(g_stream, verify_hash=True)
+    assert len(dec) == n
