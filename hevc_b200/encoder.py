@@ -48,7 +48,7 @@ def crf_to_qp(crf: int) -> Tuple[int, int]:
 
 def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: bool = False, keep_recon: bool = False,
                 rate_control: bool = True, deblock: bool = True, scenecut: bool = True, intra_in_p: bool = True,
-                sao: bool = False) -> HbEncParams:
+                sao: bool = True) -> HbEncParams:
     c = HbEncParams()
     qp_i, qp_p = qp if qp is not None else crf_to_qp(p.crf)
     for name in ('width', 'height', 'fps_num', 'fps_den', 'bit_depth', 'profile_idc', 'level_idc', 'tier', 'keyint', 'min_keyint',

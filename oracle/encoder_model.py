@@ -45,8 +45,7 @@ def make_params(width, height, bit_depth=8, qp_i=24, qp_p=26, keyint=60, fps=(30
     p.deblock = int(kw.get('deblock', 1))
     p.rate_control = int(kw.get('rate_control', 0))
     p.min_keyint = int(kw.get('min_keyint', max(2, keyint // 2)))
-    p.scenecut, p.intra_in_p = (int(kw.get(k, 1)) for k in ('scenecut', 'intra_in_p'))
-    p.sao = int(kw.get('sao', 0))
+    p.scenecut, p.intra_in_p, p.sao = (int(kw.get(k, 1)) for k in ('scenecut', 'intra_in_p', 'sao'))
     for k in ('aud', 'repeat_headers', 'hrd'):
         if k in kw:
             setattr(p, k, int(kw[k]))
