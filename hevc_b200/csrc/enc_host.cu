@@ -308,7 +308,7 @@ struct hb_encoder {
     int prof_launches[8] = {};
     float last_total_ms = 0, last_kernel_ms = 0;
     cudaEvent_t ev_mark = nullptr, ev_last_done = nullptr;   // region timing across pipelined calls (hb_enc_mark / hb_enc_elapsed)
-    bool have_last_done = false;
+    bool have_last_done = false, have_mark = false;
     std::vector<uint8_t> vps, sps, pps;
 };
 
@@ -337,6 +337,25 @@ int alloc_planes(hb_encoder *e, Planes *pl, int wc, int hc)
     HB_TRY(dev_alloc(e, &pl->y, (size_t)wc * hc));
     HB_TRY(dev_alloc(e, &pl->u, (size_t)(wc / 2) * (hc / 2)));
     HB_TRY(dev_alloc(e, &pl->v, (size_t)(wc / 2) * (hc / 2)));
+    return HB_OK;
+}
+
+RcState initial_rc(const hb_enc_params &p)
+{
+    RcState rc{};
+    rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
+    rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
+    rc.fullness = rc.b16 * 9 / 10;
+    rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
+    rc.keyint = p.keyint; rc.min_keyint = p.min_keyint; rc.scenecut = p.scenecut; rc.poc = 0; rc.started = 0;
+    return rc;
+}
+
+int upload_initial_rc(hb_encoder *e)
+{
+    const RcState rc = initial_rc(e->prm);
+    HB_CUDA(e->ctx, cudaMemcpyAsync(e->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, e->ctx->stream));
+    HB_CUDA(e->ctx, cudaStreamSynchronize(e->ctx->stream));
     return HB_OK;
 }
 
@@ -918,16 +937,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     }
     HB_TRY(dev_alloc(E, &E->progress, (size_t)g.ctuh));
     HB_TRY(dev_alloc(E, &E->rc_dev, 1));
-    {
-        RcState rc{};
-        rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
-        rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
-        rc.fullness = rc.b16 * 9 / 10;
-        rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
-        rc.keyint = p.keyint; rc.min_keyint = p.min_keyint; rc.scenecut = p.scenecut; rc.poc = 0; rc.started = 0;
-        HB_CUDA(ctx, cudaMemcpyAsync(E->rc_dev, &rc, sizeof(rc), cudaMemcpyHostToDevice, ctx->stream));
-        HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    HB_TRY(upload_initial_rc(E));
     HB_CUDA(ctx, cudaEventCreate(&E->ev_mark));
     HB_CUDA(ctx, cudaEventCreate(&E->ev_last_done));
     HB_CUDA(ctx, cudaStreamCreateWithFlags(&E->st_copy, cudaStreamNonBlocking));
@@ -976,6 +986,19 @@ void hb_enc_destroy(hb_encoder *e)
     delete e;
 }
 
+int hb_enc_reset(hb_encoder *e)
+{
+    if (!e) return HB_ERR_ARG;
+    hb_ctx *ctx = e->ctx;
+    if (e->set[0].pending || e->set[1].pending)
+        return hb_fail(ctx, HB_ERR_ARG, "%s", "hb_enc_reset with frames in flight: flush hb_enc_encode_delayed first");
+    HB_CUDA(ctx, cudaSetDevice(ctx->device));
+    HB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    e->frame_no = 0; e->since_bp = 0; e->cur = 0;
+    e->stop.store(0); e->done.store(0);
+    return upload_initial_rc(e);
+}
+
 int hb_enc_headers(hb_encoder *e, uint8_t *out, size_t cap, size_t *len)
 {
     if (!e) return HB_ERR_ARG;
@@ -1012,11 +1035,7 @@ int hb_rc_simulate(const hb_enc_params *params, const long long *est16, const in
     if (!params || !est16 || !is_idr || !qps || n < 0) return HB_ERR_ARG;
     const hb_enc_params &p = *params;
     if (p.fps_num <= 0 || p.fps_den <= 0) return HB_ERR_ARG;
-    RcState rc{};                     // exactly the state hb_enc_create uploads, stepped by the functions the device kernels run
-    rc.t16 = (long long)p.vbv_maxrate_kbps * 1000 * 16 * p.fps_den / p.fps_num;
-    rc.b16 = (long long)p.vbv_bufsize_kbit * 1000 * 16;
-    rc.fullness = rc.b16 * 9 / 10;
-    rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
+    RcState rc = initial_rc(p);       // exactly the state hb_enc_create uploads, stepped by the functions the device kernels run
     for (int i = 0; i < n; i++) {
         qps[i] = rc_pick_qp(rc, is_idr[i] != 0);
         rc_update(rc, is_idr[i] != 0, qps[i], est16[i]);
@@ -1139,13 +1158,14 @@ int hb_enc_mark(hb_encoder *e)
     HB_CUDA(e->ctx, cudaSetDevice(e->ctx->device));
     HB_CUDA(e->ctx, cudaEventRecord(e->ev_mark, e->ctx->stream));
     e->have_last_done = false;
+    e->have_mark = true;
     return HB_OK;
 }
 
 int hb_enc_elapsed(hb_encoder *e, float *ms)
 {
     if (!e || !ms) return HB_ERR_ARG;
-    HB_ARG(e->ctx, e->have_last_done);
+    HB_ARG(e->ctx, e->have_last_done && e->have_mark);      // (an unrecorded event would leave a sticky CUDA error behind)
     HB_CUDA(e->ctx, cudaEventSynchronize(e->ev_last_done));
     HB_CUDA(e->ctx, cudaEventElapsedTime(ms, e->ev_mark, e->ev_last_done));
     return HB_OK;

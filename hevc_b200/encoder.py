@@ -119,6 +119,11 @@ class B200Encoder:
         if rc != 0:
             raise _cabi.HbError(rc, self.L.hb_last_error(self.ctx.h).decode('utf-8', 'replace'))
 
+    def reset(self):
+        """start a new, independent stream on this encoder (``hb_enc_reset``): nothing may be in flight"""
+        self.L.hb_enc_reset.argtypes = [C.c_void_p]
+        self._check(self.L.hb_enc_reset(self.h))
+
     def headers(self) -> bytes:
         buf = (C.c_uint8 * 1024)()
         n = C.c_size_t()
@@ -235,6 +240,57 @@ class B200Encoder:
         return cus.reshape(self.coded_h // 16, self.coded_w // 16), coefs
 
 
+class EncoderPool:
+    """Idle encoders kept for reuse, keyed by (device, parameter block, batch size): a batch worker that transcodes many
+    short files of the same geometry resets one encoder per file (``hb_enc_reset``) instead of allocating and pinning
+    gigabytes per file.  At most ``max_idle`` encoders are kept; the oldest is closed first."""
+
+    def __init__(self, max_idle: int = 4):
+        import threading
+        self.max_idle = max_idle
+        self._idle: list = []                  # [(key, ctx, enc)], oldest first
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _key(device: int, params: HbEncParams, max_batch: int):
+        return (int(device), bytes(params), int(max_batch))
+
+    def acquire(self, device: int, params: HbEncParams, max_batch: int):
+        key = self._key(device, params, max_batch)
+        with self._lock:
+            for i, (k, ctx, enc) in enumerate(self._idle):
+                if k == key:
+                    del self._idle[i]
+                    enc.reset()
+                    return key, ctx, enc
+        ctx = _cabi.Context(device)
+        try:
+            return key, ctx, B200Encoder(ctx, params, max_batch=max_batch)
+        except BaseException:
+            ctx.close()
+            raise
+
+    def release(self, key, ctx, enc, reusable: bool = True):
+        drop = []
+        with self._lock:
+            if reusable and self.max_idle > 0:
+                self._idle.append((key, ctx, enc))
+                while len(self._idle) > self.max_idle:
+                    drop.append(self._idle.pop(0))
+            else:
+                drop.append((key, ctx, enc))
+        for _, c, e in drop:
+            e.close()
+            c.close()
+
+    def close(self):
+        with self._lock:
+            drop, self._idle = self._idle, []
+        for _, c, e in drop:
+            e.close()
+            c.close()
+
+
 def pack_yuv420p8(frames: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]]) -> np.ndarray:
     """[(y, u, v)] uint8 planes -> one contiguous buffer in the layout ``hb_frames`` expects."""
     return np.concatenate([np.concatenate([p.reshape(-1) for p in f]) for f in frames]).astype(np.uint8, copy=False)
@@ -270,6 +326,7 @@ class ParallelSegmentEncoder:
         self._error: Optional[BaseException] = None
         self._submitted = 0
         self._emitted = 0
+        self._timeline = [[] for _ in range(self.streams)]      # per stream: device time (ms since mark) at which each drain completed
         self._threads = [threading.Thread(target=self._work, args=(k,), daemon=True) for k in range(self.streams)]
         for t in self._threads:
             t.start()
@@ -288,6 +345,7 @@ class ParallelSegmentEncoder:
                     break
                 if job == 'flush':
                     out, stats = enc.flush()
+                    self._stamp(k, enc, stats)
                     self._publish(pending, out, stats)
                     pending = []
                     with self._lock:
@@ -295,6 +353,7 @@ class ParallelSegmentEncoder:
                     continue
                 seq, data, n, kw = job
                 out, stats = enc.encode_delayed(data, n, force_idr=True, **kw)
+                self._stamp(k, enc, stats)
                 pending.append(seq)
                 done_now = pending[:-1] if stats else []
                 if done_now:
@@ -303,6 +362,17 @@ class ParallelSegmentEncoder:
         except BaseException as exc:           # surfaced by the next submit / finish
             with self._lock:
                 self._error = exc
+
+    def _stamp(self, k: int, enc: 'B200Encoder', stats):
+        if stats:
+            try:
+                self._timeline[k].append(enc.elapsed_ms())
+            except (_cabi.HbError, AttributeError):      # no mark recorded yet
+                pass
+
+    def timeline(self) -> List[List[float]]:
+        """per stream: device time in ms (since ``mark``) of the end of every completed segment's bitstream download"""
+        return [list(t) for t in self._timeline]
 
     def _publish(self, seqs: List[int], out: bytes, stats: List[FrameStat]):
         # one or more whole segments came back concatenated: split them at their frame counts
@@ -356,8 +426,9 @@ class ParallelSegmentEncoder:
         return self._collect()
 
     def mark(self):
-        for e in self._encs:
+        for k, e in enumerate(self._encs):
             e.mark()
+            self._timeline[k] = []
 
     def elapsed_ms(self) -> float:
         """Device time from ``mark`` to the last completed download, maximum over the streams."""

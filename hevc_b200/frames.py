@@ -96,6 +96,19 @@ class Cv2Reader:
                 return
 
 
+class MemoryReader:
+    """Frames already in host memory (uint8 array [n, frame_bytes] in the hb_frames layout): the reader interface over a buffer,
+    for callers that decode elsewhere and for benchmarks that must not time a disk."""
+
+    def __init__(self, frames: np.ndarray, fmt: int = PIX_YUV420P8, src_bit_depth: int = 8):
+        self.frames, self.fmt, self.src_bit_depth, self.kind = frames, fmt, src_bit_depth, 'yuv'
+
+    def batches(self, batch: int):
+        for s in range(0, len(self.frames), batch):
+            chunk = self.frames[s:s + batch]
+            yield chunk, len(chunk), self.fmt
+
+
 def open_reader(path: Path, info: VideoInfo):
     path = Path(path)
     with open(path, 'rb') as fh:

@@ -200,11 +200,40 @@ def next_device() -> int:
     return d
 
 
+_ENCODER_POOL = None
+_ENCODER_POOL_LOCK = threading.Lock()
+
+
+def encoder_pool():
+    """process-wide pool of idle encoders (``HEVC_B200_POOL`` = how many to keep, default 4, 0 disables reuse)"""
+    global _ENCODER_POOL
+    with _ENCODER_POOL_LOCK:
+        if _ENCODER_POOL is None:
+            from .encoder import EncoderPool
+            _ENCODER_POOL = EncoderPool(int(os.environ.get('HEVC_B200_POOL', '4') or 0))
+        return _ENCODER_POOL
+
+
 def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
                 stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
                 target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None, force_main10: bool = False,
                 devices: Optional[Sequence[int]] = None) -> Tuple[int, str]:
-    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on B200.  Returns (0, '') or (1, reason) like run_ffmpeg.
+    """Encode ``file_path`` to ``out_path`` (hvc1 MP4) on B200.  Returns (0, '') or (1, reason) like run_ffmpeg."""
+    from .frames import open_reader
+    try:
+        src_info = info
+        reader = open_reader(file_path, src_info)
+    except Exception as exc:
+        return 1, f'{type(exc).__name__}: {exc}'
+    return encode_reader_b200(reader, Path(file_path).name, out_path, info, progress_callback, total_frames, stop_event, device, batch,
+                              target_size, streams, force_main10, devices)
+
+
+def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
+                       stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
+                       target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None, force_main10: bool = False,
+                       devices: Optional[Sequence[int]] = None) -> Tuple[int, str]:
+    """The encode step for frames delivered by ``reader`` (``frames.py``: file readers, or an in-memory source).
 
     The pre-encode pixel pipeline (BGR -> 4:2:0 matrix conversion for container sources, polyphase scaling for
     ``target_size``, bit-depth conversion) runs inside the encoder's ingest stage on the device: host frames go to
@@ -215,9 +244,8 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
     import numpy as np
 
     from . import _cabi, mp4
-    from .encoder import PIX_BGR24, PIX_YUV420P8, B200Encoder, ParallelSegmentEncoder, to_c_params
-    from .frames import open_reader
-    enc = None
+    from .encoder import PIX_BGR24, ParallelSegmentEncoder, to_c_params
+    release = None
     try:
         devs = [int(d) for d in devices] if devices else [next_device() if device is None else int(device)]
         if _cabi.lib().hb_device_count() <= max(devs):
@@ -229,12 +257,11 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
         if target_size:
             info = VideoInfo(**{**info.__dict__, 'width': target_size[0], 'height': target_size[1]})
         params = derive.derive_b200_params(info, force_main10=force_main10)
-        reader = open_reader(file_path, VideoInfo(**{**info.__dict__, 'width': src_w, 'height': src_h}))
         if getattr(info, 'audio_channels', 0):
             # the reference transcodes audio to AAC inside the same ffmpeg child (core/transcoder.py:423-450); this backend writes
             # the video track only (audio stays with an external tool)
             logger.warning('%s: %d audio channel(s) in the source are NOT carried over by encoder=b200 (video-only MP4)',
-                           file_path.name, info.audio_channels)
+                           name, info.audio_channels)
         if streams is None:
             streams = int(os.environ.get('HEVC_B200_STREAMS', '1') or 1)
         kw = {}
@@ -251,18 +278,15 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
         segmented = streams > 1 or len(devs) > 1
         unit = max(1, min(int(params.keyint), 1024)) if segmented else batch
         if segmented:
-            enc = ParallelSegmentEncoder(devs, to_c_params(params), streams=streams, max_batch=unit)
-            submit = lambda data, n, fmt: enc.submit(data, n, fmt=fmt, **kw)      # noqa: E731
-            finish = enc.finish
+            pse = ParallelSegmentEncoder(devs, to_c_params(params), streams=streams, max_batch=unit)
+            release = pse.close
+            submit = lambda data, n, fmt: pse.submit(data, n, fmt=fmt, **kw)      # noqa: E731
+            finish = pse.finish
         else:
-            ctx = _cabi.Context(devs[0])
-            single = B200Encoder(ctx, to_c_params(params), max_batch=unit)
-
-            class _One:      # same close() shape as the segment encoder
-                def close(self_inner):
-                    single.close()
-                    ctx.close()
-            enc = _One()
+            pool = encoder_pool()
+            key, ctx, single = pool.acquire(devs[0], to_c_params(params), unit)
+            ok = [False]
+            release = lambda: pool.release(key, ctx, single, reusable=ok[0])      # noqa: E731
             submit = lambda data, n, fmt: single.encode_delayed(data, n, fmt=fmt, **kw)      # noqa: E731
             finish = single.flush
         track = mp4.TrackInfo(params.width, params.height, params.fps_num, params.fps_den, params.profile_idc, params.level_idc, params.tier,
@@ -275,7 +299,7 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
             done += len(st)
             if progress_callback and st:
                 try:
-                    progress_callback(file_path.name, done, max(total_frames, done))
+                    progress_callback(name, done, max(total_frames, done))
                 except Exception:
                     logger.debug('progress callback raised', exc_info=True)
 
@@ -294,14 +318,16 @@ def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callb
             out, st = finish()
             mux.feed(out)
             tick(st)
+        if not segmented:
+            ok[0] = True                       # drained cleanly: the encoder can serve the next file
         return 0, ''
     except Exception as exc:
         logger.debug('B200 encode failed', exc_info=True)
         return 1, f'{type(exc).__name__}: {exc}'
     finally:
         try:
-            if enc is not None:
-                enc.close()
+            if release is not None:
+                release()
         except Exception:
             pass
 

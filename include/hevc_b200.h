@@ -173,6 +173,11 @@ typedef struct hb_encoder hb_encoder;
 
 int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_encoder **out);
 void hb_enc_destroy(hb_encoder *enc);
+/* Start a new stream on an existing encoder (same parameters): frame counter, POC, rate-control state and SEI timing return to
+ * their initial values, so the next frame is the first key frame of an independent stream.  Nothing may be in flight.  Lets a
+ * batch worker reuse one encoder (and its device memory) for successive files of the same geometry instead of paying the
+ * allocation per file (reference: one ffmpeg child per file, gui/worker.py:30-41). */
+int hb_enc_reset(hb_encoder *enc);
 /* VPS + SPS + PPS as Annex-B (for the hvcC box) */
 int hb_enc_headers(hb_encoder *enc, uint8_t *out, size_t cap, size_t *len);
 int hb_enc_coded_size(const hb_encoder *enc, int *coded_w, int *coded_h);
