@@ -394,7 +394,7 @@ def run_batch(args):
         clips[name] = hbuf.numpy()
     torch.cuda.synchronize()
     out_dir = Path(tempfile.mkdtemp(prefix='hb_batch_'))
-    os.environ['HEVC_B200_POOL'] = str(max(4, 2 * args.workers))
+    os.environ['HEVC_B200_POOL'] = str(len(BATCH_TYPES) * args.workers)      # one idle encoder per (geometry, worker): no re-allocation per file
 
     def one_pass():
         queue = list(mine)
@@ -526,29 +526,42 @@ def run_upscale(args):
         torch.cuda.synchronize()
 
     def one_pass(resident: bool):
-        chunks = []
+        runs = {}
+        pending = []
+
+        def take(out, stats):
+            # completed segments come back in submission order; each is converted to MP4 sample form here, on its own rank
+            pos = 0
+            while stats and pending:
+                k = pending[0]
+                cnt = segs[k][1] - segs[k][0]
+                if len(stats) < cnt:
+                    break
+                size = sum(st.bytes for st in stats[:cnt])
+                runs[k] = mp4.to_samples(out[pos:pos + size])
+                pos += size
+                stats = stats[cnt:]
+                pending.pop(0)
+
         for k in mine:
             a, b = segs[k]
             src = dev[k].data_ptr() if resident else host[k].numpy()
-            chunks.append(enc.submit(src, b - a, on_device=resident, frame_bytes=fb, src_size=(sw, sh))[0])
-        chunks.append(enc.finish()[0])
-        mine_bytes = b''.join(chunks)
-        # host side of the path: gather the per-rank streams, interleave the segments back into display order, one mux
+            pending.append(k)
+            take(*enc.submit(src, b - a, on_device=resident, frame_bytes=fb, src_size=(sw, sh)))
+        take(*enc.finish())
+        assert not pending
+        # host side of the path: gather the per-rank sample runs on rank 0, put the segments back into display order, ONE file
         if world > 1:
             gathered = [None] * world if rank == 0 else None
-            dist.gather_object(mine_bytes, gathered, dst=0)
+            dist.gather_object(runs, gathered, dst=0)
         else:
-            gathered = [mine_bytes]
+            gathered = [runs]
         if rank != 0:
             return 0, None
-        per_rank = [mp4.split_access_units(g) for g in gathered]
-        pos = [0] * world
-        ordered = []
-        for k, (a, b) in enumerate(segs):
-            r = k % world
-            ordered += per_rank[r][pos[r]:pos[r] + (b - a)]
-            pos[r] += b - a
-        data = mp4.mux(track, [(au, any(16 <= mp4.nal_type(x) <= 23 for x in au)) for au in ordered])
+        allruns = {}
+        for g_ in gathered:
+            allruns.update(g_)
+        data = mp4.assemble(track, [allruns[k] for k in range(len(segs))])
         return len(data), data
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -596,7 +609,8 @@ def run_upscale(args):
                 'vs_baseline': None, 'dtype': 'u16', 'data': 'synthetic',
                 'config': {'workload': f'one {n_total}-frame {sw}x{sh}@{fps} 8-bit clip -> {tw}x{th} Main10 (SDR signalling kept), fused scale + encode',
                            'baseline_config': 4, 'segments': len(segs), 'segment_frames': params.keyint, 'streams_per_gpu': S,
-                           'sharding': 'closed-GOP segment k -> rank k mod N; gather_object to rank 0, in-order concatenation, ONE hvc1 MP4 mux (inside the timed region)',
+                           'sharding': 'closed-GOP segment k -> rank k mod N; every rank converts its segments to MP4 sample form, gather_object to rank 0, in-order '
+                                       'assembly into ONE hvc1 MP4 (all inside the timed region)',
                            'crf': params.crf, 'vbv_maxrate_kbps': params.vbv_maxrate_kbps, 'level_idc': params.level_idc,
                            'decoded_frames_of_muxed_output': decoded},
                 'timing': 'CUDA events on the default stream around K passes (bracketed by device syncs), max over ranks; source segments resident in HBM',

@@ -263,6 +263,14 @@ __device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uin
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// TMA tiled copy global -> shared (SASS: UTMALDG.2D): one instruction moves the whole box.  The innermost coordinate times the
+// element size must be a multiple of 16 bytes (profiles/tma_probe_r2.log: x = 37 faults with 'illegal instruction', x = 40 works).
+__device__ __forceinline__ void tma_tile_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
@@ -424,19 +432,19 @@ __device__ __forceinline__ int satd_cols(const int (&st)[8], const int (&pv)[8],
     return warp_sum(sum) >> 1;
 }
 
-// Stage the 28-row x 40-sample luma window around integer position `centre` (quarter-sample vector) with TMA bulk copies, one
-// row per lane, all completing on the warp's mbarrier (first use of the barrier: phase 0).  The source is rounded down to
-// 16 bytes (8 samples); the remainder is returned.  Covers +-2 integer positions plus the 8-tap support; the padded plane
-// keeps every row inside the allocation.
+// Stage the 28-row x 40-sample luma window around integer position `centre` (quarter-sample vector) with ONE tiled TMA load
+// (cp.async.bulk.tensor.2d, box 40 x 28) completing on the warp's mbarrier (first use of the barrier: phase 0).  The column is
+// rounded down to 16 bytes (8 samples) -- the alignment the tiled form needs -- and the remainder is returned.  Covers +-2
+// integer positions plus the 8-tap support; the padded plane keeps the box inside the tensor, so nothing is ever zero-filled.
 __device__ __forceinline__ int stage_window(const InterParams &p, uint32_t bar, uint32_t win_smem, int x0, int y0, MV centre, int lane)
 {
-    const Geom &g = p.g;
     const int wx = x0 + (centre.x >> 2) - 6, wy = y0 + (centre.y >> 2) - 6;
     const int ax = wx & ~7, woff = wx - ax;
-    if (lane == 0) mbar_expect_tx(bar, 28 * 40 * sizeof(pixel));
+    if (lane == 0) {
+        mbar_expect_tx(bar, 28 * 40 * sizeof(pixel));
+        tma_tile_load_2d(win_smem, &p.ref_map, ax + kPad, wy + kPad, bar);      // tensor coordinates count from the padded allocation
+    }
     __syncwarp();
-    if (lane < 28)
-        tma_bulk_load(win_smem + lane * 40 * sizeof(pixel), p.ref.y + (ptrdiff_t)(wy + lane) * g.rec_stride + ax, 40 * sizeof(pixel), bar);
     mbar_wait(bar, 0);
     return woff;
 }

@@ -276,7 +276,8 @@ struct hb_encoder {
     int next_set = 0;                 // set the next batch is enqueued into
     BatchSet *last_drained = nullptr; // what read_recon / read_decisions look at
     pixel *rec_base[3][3] = {};
-    Planes rec[2], pre{};             // pre: reconstruction before SAO (SAO on); rec[cur] then receives the SAO output
+    Planes rec[2], pre{};
+    CUtensorMap ref_map[2];           // tiled TMA descriptors of the two padded luma reconstruction planes (search-window box)             // pre: reconstruction before SAO (SAO on); rec[cur] then receives the SAO output
     uint8_t *ds = nullptr;            // [max_batch + 1][dsh * dsw] quarter-resolution planes (8 MSBs)
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
     int *mode_cost = nullptr;         // [cus][35] intra mode search result of the frame in flight
@@ -465,7 +466,9 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 const uint8_t *f = dev_in + (size_t)i * dev_fb;
                 const Planes &sp = B.slot[c0 + i].src;
                 int m = fr->matrix;
-                if (!m) m = p.matrix_coeffs == 9 ? HB_MATRIX_BT2020 : (p.matrix_coeffs == 5 || p.matrix_coeffs == 6) ? HB_MATRIX_BT601 : HB_MATRIX_BT709;
+                // default: the matrix the stream will signal; unspecified (2) -> BT.601, which is what libswscale (and so OpenCV's
+                // decoder front end) assumes for untagged YUV sources when it produced these RGB samples
+                if (!m) m = p.matrix_coeffs == 9 ? HB_MATRIX_BT2020 : p.matrix_coeffs == 1 ? HB_MATRIX_BT709 : HB_MATRIX_BT601;
                 if (packed_rgb && scaled) {
                     // colour conversion at the source size into an 8-bit 4:2:0 scratch frame, then the scaler (frames are serial on
                     // this stream, so one scratch frame is enough)
@@ -554,6 +557,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 np.intra_in_p = p.intra_in_p; np.satd1 = e->satdf[1];
                 if (!forced) {
                     InterParams ip;
+                    ip.ref_map = e->ref_map[1 - e->cur];
                     ip.g = g; ip.src = s.src; ip.ref = ref; ip.rec = rec; ip.cmv = e->cmv + (size_t)i * nctu * 2;
                     ip.cus = s.cus; ip.coefs = s.coefs; ip.ctl = B.ctl_dev + i;
                     ip.intra_best = p.intra_in_p ? e->intra_best : nullptr;
@@ -926,6 +930,23 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
             Planes &dst = k == 2 ? E->pre : E->rec[k];
             if (c == 0) dst.y = origin; else if (c == 1) dst.u = origin; else dst.v = origin;
         }
+    {   // tiled TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency)
+        typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                        const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        HB_CUDA(ctx, cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return hb_fail(ctx, HB_ERR_CUDA, "%s", "cuTensorMapEncodeTiled is not available");
+        for (int k = 0; k < 2; k++) {
+            const cuuint64_t dims[2] = {(cuuint64_t)g.rec_stride, (cuuint64_t)(g.hc + 2 * kPad)};
+            const cuuint64_t strides[1] = {(cuuint64_t)g.rec_stride * sizeof(pixel)};
+            const cuuint32_t box[2] = {40, 28}, es[2] = {1, 1};
+            const CUresult rc = ((EncodeTiled)fn)(&E->ref_map[k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, E->rec_base[k][0], dims, strides, box, es,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) return hb_fail(ctx, HB_ERR_CUDA, "%s", "cuTensorMapEncodeTiled failed");
+        }
+    }
     HB_TRY(dev_alloc(E, &E->ds, (size_t)(max_batch + 1) * g.dsw * g.dsh));
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
     HB_TRY(dev_alloc(E, &E->mode_cost, (size_t)g.cuw * g.cuh * 35));

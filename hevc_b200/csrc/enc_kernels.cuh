@@ -2,6 +2,8 @@
 // driver (enc_host.cu).
 #pragma once
 #include <cstddef>
+#include <cuda.h>
+
 #include "enc_dev.cuh"
 
 struct hb_ctx;
@@ -30,6 +32,7 @@ struct CoarseParams {
 };
 
 struct InterParams {
+    CUtensorMap ref_map;                 // tiled TMA descriptor of the padded luma reference plane: box = 40 x 28 samples (the search window)
     Geom g;
     Planes src, ref, rec;
     const int16_t *cmv;                  // this frame's coarse vectors
@@ -172,7 +175,7 @@ __global__ void k_pack_copy(PackParams p);
 
 // pixel.cu: pre-encode pixel pipeline launchers the ingest stage uses (run on ctx->stream)
 int launch_scale8(hb_ctx *ctx, const uint8_t *s0, const uint8_t *s1, int ss, int sw, int sh, uint8_t *d0, uint8_t *d1, int ds, int dw, int dh,
-                  int out_depth, int out_shift, int out_mode);
+                  int out_depth, int out_shift, int out_mode, int n_frames = 1, size_t in_fs = 0, size_t out_fs = 0);
 int launch_rgb_planar16(hb_ctx *ctx, const uint8_t *rgb, int rs, int bgr, int matrix, int depth, int w, int h, uint8_t *dy, int dys, uint8_t *du,
                         uint8_t *dv, int dcs);
 

@@ -58,48 +58,44 @@ __device__ __forceinline__ void stage_tile(SaoScratch &s, const pixel *plane, in
     }
 }
 
-// statistics of one component: every thread takes samples i = tid, tid + 256, ... of the N x N block; edge statistics are kept
-// in registers and reduced per warp, band statistics go through warp-aggregated shared-memory atomics
+// statistics of one component.  The 256 threads form four groups of 64 (two warps), one per edge class: a group walks all
+// samples of the N x N block (sample i = (tid & 63) + 64 j), classifies them for ITS class only and keeps the four categories'
+// counts and sums in registers (8 accumulators instead of 32: the kernel stays at 6 resident CTAs per SM); the band statistics
+// of a sample are taken by the group whose class number equals j mod 4, through warp-aggregated shared-memory atomics.
 __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel *src, int src_stride, int x0, int y0, int N, int w, int h,
                                         int bshift, int tid)
 {
-    int cnt[4][4], sum[4][4];
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) { cnt[k][c] = 0; sum[k][c] = 0; }
-    for (int i = tid; i < N * N; i += kSaoThreads) {
+    const int k = tid >> 6, lane64 = tid & 63;
+    // neighbour pair of this group's class (oracle k_sao_dx / k_sao_dy): a = (dxa, dya), b = (-dxa, -dya)
+    const int dxa = k == 1 ? 0 : k == 3 ? 1 : -1, dya = k == 0 ? 0 : -1;
+    int cnt[4] = {0, 0, 0, 0}, sum[4] = {0, 0, 0, 0};
+    for (int j = 0; j < N * N / 64; j++) {
+        const int i = lane64 + 64 * j;
         const int ly = i / N, lx = i - ly * N, x = x0 + lx, y = y0 + ly;
         const bool inside = x < w && y < h;
         const int r = s.tile[ly + 1][lx + 1];
-        const int d = inside ? (int)src[(size_t)y * src_stride + x] - r : 0;
-        // band statistics: lanes with the same band pool their contribution
-        const int band = inside ? r >> bshift : 32 + (tid & 31);      // lanes outside the picture form singleton groups and do nothing
-        const unsigned grp = __match_any_sync(__activemask(), band);
-        const int gs = __reduce_add_sync(grp, d), gc = __popc(grp);
-        if (inside && (int)(__ffs(grp) - 1) == (tid & 31)) { atomicAdd(&st.bcnt[band], gc); atomicAdd(&st.bsum[band], gs); }
-        if (!inside) continue;
-        const bool l = x > 0, rr = x + 1 < w, u = y > 0, dn = y + 1 < h;
-        const int a0 = s.tile[ly + 1][lx], b0 = s.tile[ly + 1][lx + 2], a1 = s.tile[ly][lx + 1], b1 = s.tile[ly + 2][lx + 1];
-        const int a2 = s.tile[ly][lx], b2 = s.tile[ly + 2][lx + 2], a3 = s.tile[ly][lx + 2], b3 = s.tile[ly + 2][lx];
-        const int cat[4] = {l && rr ? sao_category(r, a0, b0) : 0, u && dn ? sao_category(r, a1, b1) : 0,
-                            l && rr && u && dn ? sao_category(r, a2, b2) : 0, l && rr && u && dn ? sao_category(r, a3, b3) : 0};
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const bool hit = cat[k] == c + 1;
-                cnt[k][c] += hit;
-                sum[k][c] += hit ? d : 0;
-            }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++)
+        const int d = inside ? (int)__ldg(src + (size_t)y * src_stride + x) - r : 0;
+        if ((j & 3) == k) {                  // band statistics: lanes with the same band pool their contribution
+            const int band = inside ? r >> bshift : 32 + (tid & 31);      // lanes outside the picture form singleton groups and do nothing
+            const unsigned grp = __match_any_sync(0xffffffffu, band);
+            const int gs = __reduce_add_sync(grp, d), gc = __popc(grp);
+            if (inside && (int)(__ffs(grp) - 1) == (tid & 31)) { atomicAdd(&st.bcnt[band], gc); atomicAdd(&st.bsum[band], gs); }
+        }
+        const int xa = x + dxa, ya = y + dya, xb = x - dxa, yb = y - dya;
+        const bool ok = inside && xa >= 0 && xb >= 0 && ya >= 0 && yb >= 0 && xa < w && xb < w && ya < h && yb < h;
+        const int cat = ok ? sao_category(r, s.tile[ly + 1 + dya][lx + 1 + dxa], s.tile[ly + 1 - dya][lx + 1 - dxa]) : 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const int tc = __reduce_add_sync(0xffffffffu, cnt[k][c]), ts = __reduce_add_sync(0xffffffffu, sum[k][c]);
-            if ((tid & 31) == 0 && tc) { atomicAdd(&st.cnt[k][c], tc); atomicAdd(&st.sum[k][c], ts); }
+            const bool hit = cat == c + 1;
+            cnt[c] += hit;
+            sum[c] += hit ? d : 0;
         }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int tc = __reduce_add_sync(0xffffffffu, cnt[c]), ts = __reduce_add_sync(0xffffffffu, sum[c]);
+        if ((tid & 31) == 0 && tc) { atomicAdd(&st.cnt[k][c], tc); atomicAdd(&st.sum[k][c], ts); }
+    }
 }
 
 // final choice of one component group from the per-entry best costs (oracle sao_decide_group); comps = first component, count
@@ -138,7 +134,7 @@ __device__ void decide_group(const SaoScratch &s, int c0, int ncomp, long long l
 
 }  // namespace
 
-__global__ void __launch_bounds__(kSaoThreads) k_sao_decide(SaoParams p)
+__global__ void __launch_bounds__(kSaoThreads, 6) k_sao_decide(SaoParams p)
 {
     __shared__ SaoScratch s;
     const Geom &g = p.g;

@@ -20,8 +20,11 @@ __device__ __forceinline__ void widen4(uint32_t x, uint32_t &lo, uint32_t &hi)
 // work item = 16 luma samples of one row, or 16 U + 16 V samples of one chroma row
 __global__ void __launch_bounds__(256) k_pack_p010(const uint8_t *__restrict__ y, int ys, const uint8_t *__restrict__ u, int us,
                                                    const uint8_t *__restrict__ v, int vs, int w, int h, uint8_t *__restrict__ dy,
-                                                   int dys, uint8_t *__restrict__ duv, int duvs, int aligned)
+                                                   int dys, uint8_t *__restrict__ duv, int duvs, int aligned, size_t in_fs, size_t out_fs)
 {
+    // blockIdx.y = frame of a batch (in_fs / out_fs: bytes between successive frames)
+    y += blockIdx.y * in_fs; u += blockIdx.y * in_fs; v += blockIdx.y * in_fs;
+    dy += blockIdx.y * out_fs; duv += blockIdx.y * out_fs;
     const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
     const int vy = (w + 15) >> 4, vc = (cw + 15) >> 4;
     const long long n_y = (long long)vy * h, total = n_y + (long long)vc * ch;
@@ -77,8 +80,11 @@ struct CscCoef {
 template <int DEPTH, bool PLANAR16 = false>
 __global__ void __launch_bounds__(128) k_rgb_to_yuv420(const uint8_t *__restrict__ rgb, int rs, int bgr, CscCoef c, int w, int h,
                                                        uint8_t *__restrict__ dy, int dys, uint8_t *__restrict__ du, int dus,
-                                                       uint8_t *__restrict__ dv, int dvs, int aligned)
+                                                       uint8_t *__restrict__ dv, int dvs, int aligned, size_t in_fs = 0, size_t out_fs = 0)
 {
+    rgb += blockIdx.y * in_fs;
+    dy += blockIdx.y * out_fs; du += blockIdx.y * out_fs;
+    if (dv) dv += blockIdx.y * out_fs;
     const int vpr = (w + 15) >> 4, rows2 = h >> 1;
     const long long total = (long long)vpr * rows2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -355,8 +361,10 @@ template <int PLANES, int OUT>
 __global__ void __launch_bounds__(256) k_scale8(const uint8_t *__restrict__ s0, const uint8_t *__restrict__ s1, int ss, int sw, int sh,
                                                 uint8_t *__restrict__ d0, uint8_t *__restrict__ d1, int ds, int dw, int dh,
                                                 const int2 *__restrict__ xtab, const int2 *__restrict__ ytab, int out_depth, int out_shift,
-                                                int aligned)
+                                                int aligned, size_t in_fs = 0, size_t out_fs = 0)
 {
+    s0 += blockIdx.y * in_fs; d0 += blockIdx.y * out_fs;
+    if (PLANES == 2) { s1 += blockIdx.y * in_fs; if (d1) d1 += blockIdx.y * out_fs; }
     __shared__ __align__(16) uint8_t foot[PLANES][S2_FH][S2_FW];
     __shared__ __align__(16) short hp[PLANES][S2_FH][S2_TW];
     __shared__ short xtap[S2_TW][4], ytap[S2_TH][4];
@@ -605,20 +613,20 @@ namespace hb {
 
 // out_mode 0: 8-bit planar, 1: 16-bit planar (s1/d1 = second plane), 2: 16-bit interleaved pairs.  Runs on ctx->stream.
 int launch_scale8(hb_ctx *ctx, const uint8_t *s0, const uint8_t *s1, int ss, int sw, int sh, uint8_t *d0, uint8_t *d1, int ds, int dw, int dh,
-                  int out_depth, int out_shift, int out_mode)
+                  int out_depth, int out_shift, int out_mode, int n_frames, size_t in_fs, size_t out_fs)
 {
     const int2 *xt, *yt;
     int rc = scale_table(ctx, sw, dw, &xt);
     if (rc) return rc;
     rc = scale_table(ctx, sh, dh, &yt);
     if (rc) return rc;
-    const int grid = ((dw + S2_TW - 1) / S2_TW) * ((dh + S2_TH - 1) / S2_TH);
-    const int aligned = is_aligned16((uint64_t)(uintptr_t)d0 | (uint64_t)(uintptr_t)d1 | (uint64_t)ds);
+    const dim3 grid(((dw + S2_TW - 1) / S2_TW) * ((dh + S2_TH - 1) / S2_TH), n_frames);
+    const int aligned = is_aligned16((uint64_t)(uintptr_t)d0 | (uint64_t)(uintptr_t)d1 | (uint64_t)ds | (uint64_t)out_fs);
     cudaStream_t st = ctx->stream;
-    if (s1 && out_mode == 2) k_scale8<2, 2><<<grid, 256, 0, st>>>(s0, s1, ss, sw, sh, d0, d1, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
-    else if (s1 && out_mode == 1) k_scale8<2, 1><<<grid, 256, 0, st>>>(s0, s1, ss, sw, sh, d0, d1, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
-    else if (!s1 && out_mode == 1) k_scale8<1, 1><<<grid, 256, 0, st>>>(s0, nullptr, ss, sw, sh, d0, nullptr, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
-    else if (!s1 && out_mode == 0) k_scale8<1, 0><<<grid, 256, 0, st>>>(s0, nullptr, ss, sw, sh, d0, nullptr, ds, dw, dh, xt, yt, out_depth, out_shift, aligned);
+    if (s1 && out_mode == 2) k_scale8<2, 2><<<grid, 256, 0, st>>>(s0, s1, ss, sw, sh, d0, d1, ds, dw, dh, xt, yt, out_depth, out_shift, aligned, in_fs, out_fs);
+    else if (s1 && out_mode == 1) k_scale8<2, 1><<<grid, 256, 0, st>>>(s0, s1, ss, sw, sh, d0, d1, ds, dw, dh, xt, yt, out_depth, out_shift, aligned, in_fs, out_fs);
+    else if (!s1 && out_mode == 1) k_scale8<1, 1><<<grid, 256, 0, st>>>(s0, nullptr, ss, sw, sh, d0, nullptr, ds, dw, dh, xt, yt, out_depth, out_shift, aligned, in_fs, out_fs);
+    else if (!s1 && out_mode == 0) k_scale8<1, 0><<<grid, 256, 0, st>>>(s0, nullptr, ss, sw, sh, d0, nullptr, ds, dw, dh, xt, yt, out_depth, out_shift, aligned, in_fs, out_fs);
     else return hb_fail(ctx, HB_ERR_ARG, "bad argument: %s", "scaler output mode");
     HB_LAUNCHED(ctx);
     return HB_OK;
@@ -652,7 +660,7 @@ int hb_pack_p010(hb_ctx *ctx, hb_devptr y, int ys, hb_devptr u, int us, hb_devpt
     const int aligned = is_aligned16(y | u | v | dy | duv | (uint64_t)ys | (uint64_t)us | (uint64_t)vs | (uint64_t)dys | (uint64_t)duvs);
     const long long items = (long long)((w + 15) / 16) * h + (long long)(((w + 1) / 2 + 15) / 16) * ((h + 1) / 2);
     k_pack_p010<<<hb_grid_for(ctx, items, 256, 8), 256, 0, ctx->stream>>>(
-        (const uint8_t *)y, ys, (const uint8_t *)u, us, (const uint8_t *)v, vs, w, h, (uint8_t *)dy, dys, (uint8_t *)duv, duvs, aligned);
+        (const uint8_t *)y, ys, (const uint8_t *)u, us, (const uint8_t *)v, vs, w, h, (uint8_t *)dy, dys, (uint8_t *)duv, duvs, aligned, 0, 0);
     HB_LAUNCHED(ctx);
     return HB_OK;
 }
@@ -688,7 +696,7 @@ int hb_scale_plane(hb_ctx *ctx, hb_devptr src, int ss, int sw, int sh, hb_devptr
     HB_ARG(ctx, (out_depth == 8 && out_shift == 0) || (out_depth == 10 && out_shift >= 0 && out_shift <= 6));
     if (step == 1)
         return hb::launch_scale8(ctx, (const uint8_t *)src, nullptr, ss, sw, sh, (uint8_t *)dst, nullptr, ds, dw, dh, out_depth, out_shift,
-                                 out_depth == 8 ? 0 : 1);
+                                 out_depth == 8 ? 0 : 1, 1, 0, 0);
     return launch_scale(ctx, (const uint8_t *)src, nullptr, ss, sw, sh, (uint8_t *)dst, ds, dw, dh, out_depth, out_shift, step);
 }
 
@@ -697,9 +705,56 @@ int hb_scale_yuv420_to_p010(hb_ctx *ctx, hb_devptr y, int ys, hb_devptr u, int u
 {
     HB_ARG(ctx, ctx && y && u && v && dy && duv && sw > 0 && sh > 0 && dw > 0 && dh > 0);
     HB_ARG(ctx, us == vs && (dw % 2) == 0 && (dh % 2) == 0 && (sw % 2) == 0 && (sh % 2) == 0);
-    int rc = hb::launch_scale8(ctx, (const uint8_t *)y, nullptr, ys, sw, sh, (uint8_t *)dy, nullptr, dys, dw, dh, 10, 6, 1);
+    int rc = hb::launch_scale8(ctx, (const uint8_t *)y, nullptr, ys, sw, sh, (uint8_t *)dy, nullptr, dys, dw, dh, 10, 6, 1, 1, 0, 0);
     if (rc) return rc;
-    return hb::launch_scale8(ctx, (const uint8_t *)u, (const uint8_t *)v, us, sw / 2, sh / 2, (uint8_t *)duv, nullptr, duvs, dw / 2, dh / 2, 10, 6, 2);
+    return hb::launch_scale8(ctx, (const uint8_t *)u, (const uint8_t *)v, us, sw / 2, sh / 2, (uint8_t *)duv, nullptr, duvs, dw / 2, dh / 2, 10, 6, 2, 1, 0, 0);
+}
+
+
+/* ---- batched forms: one launch for n_frames tightly packed frames (grid.y = frame) */
+int hb_pack_p010_batch(hb_ctx *ctx, hb_devptr src, size_t src_frame_bytes, hb_devptr dst, size_t dst_frame_bytes, int w, int h, int n_frames)
+{
+    HB_ARG(ctx, ctx && src && dst && w > 0 && h > 0 && !(w & 1) && !(h & 1) && n_frames >= 1 && n_frames <= 65535);
+    const size_t luma = (size_t)w * h, chroma = (size_t)(w / 2) * (h / 2);
+    HB_ARG(ctx, src_frame_bytes >= luma + 2 * chroma && dst_frame_bytes >= 2 * (luma + 2 * chroma));
+    const uint8_t *y = (const uint8_t *)src, *u = y + luma, *v = u + chroma;
+    uint8_t *dy = (uint8_t *)dst, *duv = dy + 2 * luma;
+    const int aligned = is_aligned16(src | dst | (uint64_t)luma | (uint64_t)chroma | (uint64_t)(w / 2) | (uint64_t)src_frame_bytes | (uint64_t)dst_frame_bytes);
+    const long long items = (long long)((w + 15) / 16) * h + (long long)((w / 2 + 15) / 16) * (h / 2);
+    k_pack_p010<<<dim3(hb_grid_for(ctx, items, 256, 8), n_frames), 256, 0, ctx->stream>>>(y, w, u, w / 2, v, w / 2, w, h, dy, 2 * w, duv, 2 * w, aligned,
+                                                                                          src_frame_bytes, dst_frame_bytes);
+    HB_LAUNCHED(ctx);
+    return HB_OK;
+}
+
+int hb_rgb_to_p010_batch(hb_ctx *ctx, hb_devptr rgb, size_t rgb_frame_bytes, int order, int matrix, int w, int h, hb_devptr dst,
+                         size_t dst_frame_bytes, int n_frames)
+{
+    HB_ARG(ctx, ctx && rgb && dst && w > 0 && h > 0 && !(w & 1) && !(h & 1) && n_frames >= 1 && n_frames <= 65535);
+    HB_ARG(ctx, rgb_frame_bytes >= (size_t)3 * w * h && dst_frame_bytes >= (size_t)3 * w * h);
+    CscCoef c;
+    if (!csc_coefficients(matrix, 10, c)) return hb_fail(ctx, HB_ERR_ARG, "bad argument: %s", "matrix");
+    uint8_t *dy = (uint8_t *)dst, *duv = dy + (size_t)2 * w * h;
+    const int aligned = is_aligned16(rgb | dst | (uint64_t)(3 * w) | (uint64_t)(2 * w) | (uint64_t)rgb_frame_bytes | (uint64_t)dst_frame_bytes | (uint64_t)((size_t)2 * w * h));
+    const long long items = (long long)((w + 15) / 16) * (h / 2);
+    k_rgb_to_yuv420<10><<<dim3(hb_grid_for(ctx, items, 128, 8), n_frames), 128, 0, ctx->stream>>>((const uint8_t *)rgb, 3 * w, order == HB_BGR, c, w, h, dy, 2 * w, duv,
+                                                                                                 2 * w, nullptr, 0, aligned, rgb_frame_bytes, dst_frame_bytes);
+    HB_LAUNCHED(ctx);
+    return HB_OK;
+}
+
+int hb_scale_yuv420_to_p010_batch(hb_ctx *ctx, hb_devptr src, size_t src_frame_bytes, int sw, int sh, hb_devptr dst, size_t dst_frame_bytes, int dw,
+                                  int dh, int n_frames)
+{
+    HB_ARG(ctx, ctx && src && dst && sw > 0 && sh > 0 && dw > 0 && dh > 0 && !(sw & 1) && !(sh & 1) && !(dw & 1) && !(dh & 1) && n_frames >= 1 && n_frames <= 65535);
+    const size_t sl = (size_t)sw * sh, sc = (size_t)(sw / 2) * (sh / 2), dl = (size_t)dw * dh;
+    HB_ARG(ctx, src_frame_bytes >= sl + 2 * sc && dst_frame_bytes >= 3 * dl);
+    const uint8_t *y = (const uint8_t *)src;
+    uint8_t *dy = (uint8_t *)dst;
+    int rc = hb::launch_scale8(ctx, y, nullptr, sw, sw, sh, dy, nullptr, 2 * dw, dw, dh, 10, 6, 1, n_frames, src_frame_bytes, dst_frame_bytes);
+    if (rc) return rc;
+    return hb::launch_scale8(ctx, y + sl, y + sl + sc, sw / 2, sw / 2, sh / 2, dy + 2 * dl, nullptr, 2 * dw, dw / 2, dh / 2, 10, 6, 2, n_frames, src_frame_bytes,
+                             dst_frame_bytes);
 }
 
 }  // extern "C"

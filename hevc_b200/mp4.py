@@ -14,22 +14,25 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 NAL_VPS, NAL_SPS, NAL_PPS, NAL_AUD = 32, 33, 34, 35
 
 
-def split_nals(annexb: bytes) -> List[bytes]:
-    """Annex-B byte stream -> NAL units (without start codes, emulation prevention untouched)."""
-    out, i, n = [], 0, len(annexb)
+def split_nals(annexb) -> List[memoryview]:
+    """Annex-B byte stream -> NAL units (without start codes, emulation prevention untouched) as zero-copy views."""
+    data = bytes(annexb) if not isinstance(annexb, (bytes, bytearray)) else annexb
+    view = memoryview(data)
+    out, i, n = [], 0, len(data)
     starts = []
+    find = data.find
     while True:
-        j = annexb.find(b'\x00\x00\x01', i)
+        j = find(b'\x00\x00\x01', i)
         if j < 0:
             break
         starts.append(j)
         i = j + 3
     for k, s in enumerate(starts):
         end = starts[k + 1] if k + 1 < len(starts) else n
-        nal = annexb[s + 3:end]
-        while nal and nal[-1] == 0 and k + 1 < len(starts):       # trailing zero_byte of the next start code
-            nal = nal[:-1]
-        out.append(nal)
+        if k + 1 < len(starts):
+            while end > s + 3 and data[end - 1] == 0:       # trailing zero_byte of the next start code
+                end -= 1
+        out.append(view[s + 3:end])
     return out
 
 
@@ -158,31 +161,71 @@ def _head(info: TrackInfo, vps: bytes, sps: bytes, pps: bytes, sizes: Sequence[i
     return head + struct.pack('>I4sQ', 1, b'mdat', 16 + payload_len)
 
 
-def _sample_of(nals: Sequence[bytes], sets: dict) -> bytes:
-    """length-prefixed sample of one access unit; parameter sets go to ``sets`` (``hvc1`` keeps them out of band)"""
-    body = bytearray()
+def _sample_pieces(nals, sets: dict):
+    """length-prefixed sample of one access unit as a list of pieces (no copy) + its size; parameter sets go to ``sets``
+    (``hvc1`` keeps them out of band)"""
+    pieces, size = [], 0
     for nal in nals:
         t = nal_type(nal)
         if t in (NAL_VPS, NAL_SPS, NAL_PPS):
-            sets.setdefault(t, nal)
+            if t not in sets:
+                sets[t] = bytes(nal)
         else:
-            body += struct.pack('>I', len(nal)) + nal
-    return bytes(body)
+            pieces.append(struct.pack('>I', len(nal)))
+            pieces.append(nal)
+            size += 4 + len(nal)
+    return pieces, size
+
+
+def _sample_of(nals, sets: dict) -> bytes:
+    return b''.join(_sample_pieces(nals, sets)[0])
+
+
+def to_samples(annexb):
+    """Annex-B run of whole access units -> (payload in MP4 sample form, sample sizes, 1-based indices of sync samples within
+    the run, parameter sets).  Independent runs (closed-GOP segments coded elsewhere) convert in parallel and ``assemble``
+    only concatenates."""
+    sets: dict = {}
+    pieces, sizes, sync = [], [], []
+    for au in split_access_units(annexb):
+        pc, size = _sample_pieces(au, sets)
+        pieces += pc
+        sizes.append(size)
+        if any(16 <= nal_type(x) <= 23 for x in au):
+            sync.append(len(sizes))
+    return b''.join(pieces), sizes, sync, sets
+
+
+def assemble(info: TrackInfo, runs) -> bytes:
+    """runs: iterable of ``to_samples`` results in presentation order -> the complete file, moov first"""
+    sets: dict = {}
+    payloads, sizes, sync = [], [], []
+    for payload, sz, sy, st in runs:
+        for t, nal in st.items():
+            sets.setdefault(t, nal)
+        sync += [len(sizes) + k for k in sy]
+        sizes += sz
+        payloads.append(payload)
+    if len(sets) != 3:
+        raise ValueError('stream carries no VPS/SPS/PPS')
+    return b''.join([_head(info, sets[NAL_VPS], sets[NAL_SPS], sets[NAL_PPS], sizes, sync)] + payloads)
 
 
 def mux(info: TrackInfo, access_units: Iterable[Tuple[List[bytes], bool]]) -> bytes:
     """access_units: (NAL units of one frame, is_sync).  Parameter sets are taken from the first access unit that carries
     them and are removed from the samples (``hvc1`` keeps them out of band).  Returns the complete file, moov first."""
     sets: dict = {}
-    samples: List[bytes] = []
+    pieces, sizes = [], []
     sync: List[int] = []
     for i, (nals, is_sync) in enumerate(access_units):
-        samples.append(_sample_of(nals, sets))
+        pc, size = _sample_pieces(nals, sets)
+        pieces += pc
+        sizes.append(size)
         if is_sync:
             sync.append(i + 1)
     if len(sets) != 3:
         raise ValueError('stream carries no VPS/SPS/PPS')
-    return _head(info, sets[NAL_VPS], sets[NAL_SPS], sets[NAL_PPS], [len(x) for x in samples], sync) + b''.join(samples)
+    return b''.join([_head(info, sets[NAL_VPS], sets[NAL_SPS], sets[NAL_PPS], sizes, sync)] + pieces)
 
 
 class StreamMuxer:
@@ -206,12 +249,12 @@ class StreamMuxer:
     def feed(self, annexb: bytes):
         if not annexb:
             return
-        for au in split_access_units(annexb):
-            sample = _sample_of(au, self.sets)
-            self._spool.write(sample)
-            self.sizes.append(len(sample))
-            if any(16 <= nal_type(x) <= 23 for x in au):
-                self.sync.append(len(self.sizes))
+        payload, sizes, sync, sets = to_samples(annexb)
+        for t, nal in sets.items():
+            self.sets.setdefault(t, nal)
+        self._spool.write(payload)
+        self.sync += [len(self.sizes) + k for k in sync]
+        self.sizes += sizes
 
     def __exit__(self, exc_type, exc, tb):
         import shutil
@@ -232,8 +275,7 @@ class StreamMuxer:
 
 
 def mux_annexb(info: TrackInfo, annexb: bytes) -> bytes:
-    aus = split_access_units(annexb)
-    return mux(info, [(au, any(16 <= nal_type(x) <= 23 for x in au)) for au in aus])
+    return assemble(info, [to_samples(annexb)])
 
 
 def parse_boxes(data: bytes, start: int = 0, end: Optional[int] = None, depth: int = 0):

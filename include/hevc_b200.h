@@ -84,6 +84,16 @@ int hb_scale_yuv420_to_p010(hb_ctx *ctx, hb_devptr y, int y_stride, hb_devptr u,
                             int src_w, int src_h, hb_devptr dst_y, int dst_y_stride, hb_devptr dst_uv, int dst_uv_stride,
                             int dst_w, int dst_h);
 
+/* Batched forms: ONE launch converts n_frames consecutive, tightly packed frames (source side: the hb_frames layout -- Y plane,
+ * U plane, V plane, or packed RGB; destination side: P010 frames -- Y plane, then the interleaved UV plane).  The byte distance
+ * between successive frames is given for both sides.  This is how a batch worker feeds whole read batches to the device. */
+int hb_pack_p010_batch(hb_ctx *ctx, hb_devptr src, size_t src_frame_bytes, hb_devptr dst, size_t dst_frame_bytes, int width, int height,
+                       int n_frames);
+int hb_rgb_to_p010_batch(hb_ctx *ctx, hb_devptr rgb, size_t rgb_frame_bytes, int order, int matrix, int width, int height, hb_devptr dst,
+                         size_t dst_frame_bytes, int n_frames);
+int hb_scale_yuv420_to_p010_batch(hb_ctx *ctx, hb_devptr src, size_t src_frame_bytes, int src_w, int src_h, hb_devptr dst,
+                                  size_t dst_frame_bytes, int dst_w, int dst_h, int n_frames);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Encoder primitives, batched over blocks (BASELINE config 5).  These are the functions libx265 spends
  * its time in behind `-c:v libx265` (reference core/transcoder.py:398-412): x265 primitives sad / satd /
@@ -159,7 +169,7 @@ typedef struct hb_frames {
     int src_width, src_height;         /* 0, 0 = the encoder's display size.  Other sizes (HB_PIX_YUV420P8 and the RGB formats): every frame is
                                         * resampled on the device by the polyphase scaler straight into the encoder's source
                                         * planes -- the upscale path (reference upscale_gui_final.py:81-87) without a P010 round trip */
-    int matrix;                        /* HB_PIX_BGR24 / RGB24: HB_MATRIX_*; 0 = follow params.matrix_coeffs (BT.709 if unspecified) */
+    int matrix;                        /* HB_PIX_BGR24 / RGB24: HB_MATRIX_*; 0 = follow params.matrix_coeffs (1 -> BT.709, 9 -> BT.2020, anything else -> BT.601) */
     int reserved0;
 } hb_frames;
 

@@ -103,3 +103,49 @@ def test_fused_upscale_to_p010(env):
     assert (gy == pixel_ref.scale_plane(y, dw, dh, 10) << 6).all()
     assert (guv[:, 0::2] == pixel_ref.scale_plane(u, dw // 2, dh // 2, 10) << 6).all()
     assert (guv[:, 1::2] == pixel_ref.scale_plane(v, dw // 2, dh // 2, 10) << 6).all()
+
+
+@pytest.mark.parametrize('w,h,n', [(1920, 1080, 3), (130, 70, 4), (64, 32, 2)])
+def test_batched_forms_match_the_oracle_frame_by_frame(env, w, h, n):
+    """hb_pack_p010_batch / hb_rgb_to_p010_batch / hb_scale_yuv420_to_p010_batch: one launch over n tightly packed frames"""
+    import ctypes as C
+
+    from hevc_b200 import _cabi
+    from oracle import pixel_ref
+    ctx, torch = env
+    rng = np.random.default_rng(w + h + n)
+    lw, cw = w * h, (w // 2) * (h // 2)
+    src = rng.integers(0, 256, (n, lw + 2 * cw), dtype=np.uint8)
+    d_src = _gpu(torch, src)
+    dst = torch.zeros((n, 3 * lw), dtype=torch.uint8, device='cuda')
+    ctx.call('hb_pack_p010_batch', _cabi.dp(d_src), C.c_size_t(lw + 2 * cw), _cabi.dp(dst), C.c_size_t(3 * lw), w, h, n)
+    ctx.sync()
+    got = dst.cpu().numpy().view(np.uint16).reshape(n, -1)
+    for i in range(n):
+        ry, ruv = pixel_ref.pack_p010(src[i, :lw].reshape(h, w), src[i, lw:lw + cw].reshape(h // 2, w // 2), src[i, lw + cw:].reshape(h // 2, w // 2))
+        assert (got[i, :lw] == ry.reshape(-1)).all() and (got[i, lw:] == ruv.reshape(-1)).all()
+    # ---- BGR -> P010
+    img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    d_img = _gpu(torch, img)
+    dst.zero_()
+    ctx.call('hb_rgb_to_p010_batch', _cabi.dp(d_img), C.c_size_t(3 * lw), 1, 9, w, h, _cabi.dp(dst), C.c_size_t(3 * lw), n)
+    ctx.sync()
+    got = dst.cpu().numpy().view(np.uint16).reshape(n, -1)
+    for i in range(n):
+        y, u, v = pixel_ref.rgb_to_yuv420(img[i], 'bt2020', 10, bgr=True)
+        uv = np.empty((h // 2, w), np.uint16)
+        uv[:, 0::2], uv[:, 1::2] = u << 6, v << 6
+        assert (got[i, :lw] == (y << 6).reshape(-1)).all() and (got[i, lw:] == uv.reshape(-1)).all()
+    # ---- scale x2 -> P010
+    dw, dh = 2 * w, 2 * h
+    big = torch.zeros((n, 3 * dw * dh), dtype=torch.uint8, device='cuda')
+    ctx.call('hb_scale_yuv420_to_p010_batch', _cabi.dp(d_src), C.c_size_t(lw + 2 * cw), w, h, _cabi.dp(big), C.c_size_t(3 * dw * dh), dw, dh, n)
+    ctx.sync()
+    got = big.cpu().numpy().view(np.uint16).reshape(n, -1)
+    for i in range(n):
+        y = pixel_ref.scale_plane(src[i, :lw].reshape(h, w), dw, dh, 10) << 6
+        u = pixel_ref.scale_plane(src[i, lw:lw + cw].reshape(h // 2, w // 2), dw // 2, dh // 2, 10) << 6
+        v = pixel_ref.scale_plane(src[i, lw + cw:].reshape(h // 2, w // 2), dw // 2, dh // 2, 10) << 6
+        uv = np.empty((dh // 2, dw), np.uint16)
+        uv[:, 0::2], uv[:, 1::2] = u, v
+        assert (got[i, :dw * dh] == y.reshape(-1)).all() and (got[i, dw * dh:] == uv.reshape(-1)).all()

@@ -23,6 +23,10 @@ TOOLSETS = {           # name -> model parameter overrides
     'cut': dict(scenecut=1, intra_in_p=1, sao=0),
     'sao': dict(scenecut=1, intra_in_p=1, sao=1),
     'r2': dict(scenecut=1, intra_in_p=1, sao=1),                 # everything this round added
+    # experiments: P-frame QP offset against the key frame (default +2)
+    'r2_p1': dict(scenecut=1, intra_in_p=1, sao=1, qp_p_offset=1),
+    'r2_p3': dict(scenecut=1, intra_in_p=1, sao=1, qp_p_offset=3),
+    'r2_p4': dict(scenecut=1, intra_in_p=1, sao=1, qp_p_offset=4),
 }
 
 
@@ -62,9 +66,10 @@ def bd_rate(anchor, test):
 def run_point(frames, w, h, depth, qp, fps, keyint, tools, rc=None):
     from oracle import encoder_model as em
     kw = dict(tools)
+    off = kw.pop('qp_p_offset', 2)
     if rc:
         kw.update(rate_control=1, vbv_maxrate_kbps=rc[0], vbv_bufsize_kbit=rc[1])
-    enc = em.ModelEncoder(em.make_params(w, h, depth, qp_i=qp, qp_p=min(51, qp + 2), keyint=keyint, fps=(fps, 1), hdr10=(depth == 10),
+    enc = em.ModelEncoder(em.make_params(w, h, depth, qp_i=qp, qp_p=min(51, qp + off), keyint=keyint, fps=(fps, 1), hdr10=(depth == 10),
                                          hash_sei=False, **kw))
     sh = depth - 8
     nbytes, ps, ss, idr, intra = 0, [], [], 0, 0

@@ -26,49 +26,43 @@ def main():
     ctx = _cabi.Context(0)
     dev = torch.device('cuda', 0)
     out = []
-    # ---- pack P010, 4K, 16 distinct frames (16 x 12.4 MB in + 16 x 24.9 MB out > L2)
-    w, h, nbuf = 3840, 2160, 16
-    ys = [torch.randint(0, 256, (h, w), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-    us = [torch.randint(0, 256, (h // 2, w // 2), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-    vs = [torch.randint(0, 256, (h // 2, w // 2), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-    dy = [torch.empty((h, w), dtype=torch.int16, device=dev) for _ in range(nbuf)]
-    duv = [torch.empty((h // 2, w), dtype=torch.int16, device=dev) for _ in range(nbuf)]
+    # ---- batched launches (one launch per 32-frame read batch, the way a worker feeds the device): every launch moves > 1 GB,
+    #      several times the 126 MB L2, so nothing is served from cache
+    import ctypes as C
+    w, h, nb = 3840, 2160, 32
+    lw, cw = w * h, (w // 2) * (h // 2)
+    src = torch.randint(0, 256, (nb, lw + 2 * cw), dtype=torch.uint8, device=dev)
+    dst = torch.empty((nb, 3 * lw), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-
-    def pack(i):
-        k = i % nbuf
-        ctx.call('hb_pack_p010', _cabi.dp(ys[k]), w, _cabi.dp(us[k]), w // 2, _cabi.dp(vs[k]), w // 2, w, h, _cabi.dp(dy[k]), 2 * w, _cabi.dp(duv[k]), 2 * w)
-    ms = timeit(ctx, pack)
-    out.append({'kernel': 'k_pack_p010', 'shape': '3840x2160 yuv420p8 -> P010', 'ms': ms, 'bytes': int(w * h * 4.5)})
-    # ---- BGR -> P010 BT.2020 (6 B/px)
-    imgs = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device=dev) for _ in range(8)]
+    ms = timeit(ctx, lambda i: ctx.call('hb_pack_p010_batch', _cabi.dp(src), C.c_size_t(lw + 2 * cw), _cabi.dp(dst), C.c_size_t(3 * lw), w, h, nb), iters=10)
+    out.append({'kernel': 'k_pack_p010', 'shape': f'{nb} x 3840x2160 yuv420p8 -> P010, one launch', 'ms': ms, 'bytes': int(nb * w * h * 4.5)})
+    del src
+    img = torch.randint(0, 256, (nb, 3 * lw), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-
-    def csc(i):
-        k = i % 8
-        ctx.call('hb_rgb_to_yuv420', _cabi.dp(imgs[k]), 3 * w, 1, 9, 10, w, h, _cabi.dp(dy[k]), 2 * w, _cabi.dp(duv[k]), 2 * w, 0, 0)
-    ms = timeit(ctx, csc)
-    out.append({'kernel': 'k_rgb_to_yuv420<10>', 'shape': '3840x2160 BGR24 -> P010 BT.2020', 'ms': ms, 'bytes': w * h * 6})
-    # ---- fused upscale 1080p -> 4K P010
+    ms = timeit(ctx, lambda i: ctx.call('hb_rgb_to_p010_batch', _cabi.dp(img), C.c_size_t(3 * lw), 1, 9, w, h, _cabi.dp(dst), C.c_size_t(3 * lw), nb), iters=10)
+    out.append({'kernel': 'k_rgb_to_yuv420<10>', 'shape': f'{nb} x 3840x2160 BGR24 -> P010 BT.2020, one launch', 'ms': ms, 'bytes': nb * w * h * 6})
+    del img
     sw, sh = 1920, 1080
-    sy = [torch.randint(0, 256, (sh, sw), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-    su = [torch.randint(0, 256, (sh // 2, sw // 2), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-    sv = [torch.randint(0, 256, (sh // 2, sw // 2), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    sl, sc = sw * sh, (sw // 2) * (sh // 2)
+    small = torch.randint(0, 256, (nb, sl + 2 * sc), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-
-    def scale(i):
-        k = i % nbuf
-        ctx.call('hb_scale_yuv420_to_p010', _cabi.dp(sy[k]), sw, _cabi.dp(su[k]), sw // 2, _cabi.dp(sv[k]), sw // 2, sw, sh,
-                 _cabi.dp(dy[k]), 2 * w, _cabi.dp(duv[k]), 2 * w, w, h)
-    ms = timeit(ctx, scale)
-    out.append({'kernel': 'k_scale<1>+<2>', 'shape': '1920x1080 yuv420p8 -> 3840x2160 P010 (fused scale + pack)', 'ms': ms,
-                'bytes': int(sw * sh * 1.5 + w * h * 3)})
+    ms = timeit(ctx, lambda i: ctx.call('hb_scale_yuv420_to_p010_batch', _cabi.dp(small), C.c_size_t(sl + 2 * sc), sw, sh, _cabi.dp(dst), C.c_size_t(3 * lw),
+                                        w, h, nb), iters=10)
+    out.append({'kernel': 'k_scale8<1,1> + <2,2>', 'shape': f'{nb} x 1920x1080 yuv420p8 -> 3840x2160 P010 (fused scale + pack), two launches', 'ms': ms,
+                'bytes': int(nb * (sw * sh * 1.5 + w * h * 3))})
+    # single-frame launches of the same kernels, for comparison with round 1
+    ms = timeit(ctx, lambda i: ctx.call('hb_scale_yuv420_to_p010_batch', _cabi.dp(small[i % nb]), C.c_size_t(sl + 2 * sc), sw, sh, _cabi.dp(dst[i % nb]),
+                                        C.c_size_t(3 * lw), w, h, 1), iters=32)
+    out.append({'kernel': 'k_scale8<1,1> + <2,2>', 'shape': '1920x1080 -> 3840x2160 P010, one frame per call', 'ms': ms, 'bytes': int(sw * sh * 1.5 + w * h * 3)})
     for r in out:
         r['GB/s'] = round(r['bytes'] / r['ms'] / 1e6, 1)
         r['frac_of_measured_hbm'] = round(r['GB/s'] / peaks['hbm_gbs'], 3)
         r['ms'] = round(r['ms'], 4)
-        print(json.dumps(r))
-    del ys, us, vs, imgs, sy, su, sv, dy, duv
+        print(json.dumps(r), flush=True)
+    del small, dst
+    if '--pixel-only' in sys.argv:
+        ctx.close()
+        return
     # ---- primitives, 2^20 blocks per launch
     n = 1 << 20
     g = torch.Generator(device=dev).manual_seed(1)
