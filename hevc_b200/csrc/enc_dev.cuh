@@ -99,6 +99,7 @@ struct FrameCtl {
     QuantParam qy, qc;
     unsigned long long est16;      // size estimate accumulated by the frame kernel, 1/16 bit
     unsigned long long satd_sum;   // sum of the luma SATDs after the first merge-aware pass (gate of the P-frame intra search)
+    int n_cand, pad_;              // CUs on the intra-search work list of this frame
 };
 
 struct RcState {
@@ -194,6 +195,7 @@ HB_HD void ctl_set_qp(FrameCtl &c, int qp, int is_idr, int bit_depth)
     c.qc = make_quant(3, chroma_qp(qp) + 6 * (bit_depth - 8), bit_depth, is_idr);
     c.est16 = 0;
     c.satd_sum = 0;
+    c.n_cand = 0; c.pad_ = 0;
 }
 
 }  // namespace hb

@@ -1131,8 +1131,35 @@ struct __align__(16) IntraSearchScratch {
     pixel src[16][16];
     int dc;
 };
-// one warp per CU (grid-stride), no block barriers: lanes 0-15 / 16-31 take the 16 sub-blocks of two modes per round and
-// reduce their SATD with shuffles
+// Work list of the intra search: every CU of a key frame; in a P frame only the CUs that inter prediction serves badly
+// (oracle/hevc_encode.c intra_search_all) -- they cluster, so handing them out through a list (rather than by CU index) is
+// what keeps all warps busy.  One thread per CU; appends are warp-aggregated.
+__global__ void __launch_bounds__(256) k_intra_list(IntraParams p)
+{
+    const Geom &g = p.g;
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x, ncu = g.cuw * g.cuh, lane = threadIdx.x & 31;
+    const bool key = p.ctl->is_idr != 0;
+    if (!key && !p.intra_in_p) return;
+    bool cand = false;
+    if (cu < ncu) {
+        if (key) cand = true;
+        else {
+            const long long satd_sum = (long long)p.ctl->satd_sum;
+            const int gate_thr = (256 * p.ctl->lambda) >> 9, s1 = p.satd1[cu];
+            cand = s1 > gate_thr && ((long long)s1 * ncu > 2 * satd_sum || s1 > 8 * gate_thr || s1 > (2048 << (g.bit_depth - 8)));
+        }
+        p.intra_best[cu] = 0x7fffffff;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, cand);
+    if (!m) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&p.ctl->n_cand, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cand) p.cand_list[base + __popc(m & ((1u << lane) - 1))] = cu;
+}
+
+// one warp per work item = (listed CU, third of the 35 modes), grid-stride, no block barriers: lanes 0-15 / 16-31 take the 16
+// sub-blocks of two modes per round and reduce their SATD with shuffles; the per-CU minimum is combined with atomicMin
 __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParams p)
 {
     __shared__ IntraSearchScratch scratch[kIntraSearchThreads / 32];
@@ -1141,18 +1168,10 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
     IntraSearchScratch &s = scratch[warp];
     if (!p.ctl->is_idr && !p.intra_in_p) return;
     const int nwarps = gridDim.x * (kIntraSearchThreads / 32);
-    const bool gated = !p.ctl->is_idr;
-    const long long satd_sum = gated ? (long long)p.ctl->satd_sum : 0, ncu = (long long)g.cuw * g.cuh;
-    const int gate_thr = (256 * p.ctl->lambda) >> 9;
-    for (int cu = blockIdx.x * (kIntraSearchThreads / 32) + warp; cu < g.cuw * g.cuh; cu += nwarps) {
+    const int n_items = 3 * __ldcg(&p.ctl->n_cand);
+    for (int item = blockIdx.x * (kIntraSearchThreads / 32) + warp; item < n_items; item += nwarps) {
+        const int cu = __ldcg(p.cand_list + item / 3), part = item % 3;
         const int cx = cu % g.cuw, cy = cu / g.cuw, x0 = cx * 16, y0 = cy * 16;
-        if (gated) {        // P frame: only CUs that inter prediction serves badly (oracle/hevc_encode.c intra_search_all)
-            const int s1 = p.satd1[cu];
-            if (!(s1 > gate_thr && ((long long)s1 * ncu > 2 * satd_sum || s1 > 8 * gate_thr || s1 > (2048 << (bd - 8))))) {
-                if (lane == 0) p.intra_best[cu] = 0x7fffffff;
-                continue;
-            }
-        }
         for (int i = lane; i < 65; i += 32) s.nb[i] = gather_one(p.src.y, g.src_stride, g, cx, cy, 16, i, bd);
         {
             const int row = lane >> 1, c0 = (lane & 1) * 8;
@@ -1178,7 +1197,7 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
             for (int x = 0; x < 4; x++) sv[y][x] = s.src[sy + y][sx + x];
         int cbest = 0x7fffffff;
 #pragma unroll 1
-        for (int m0 = 0; m0 < 36; m0 += 2) {
+        for (int m0 = 12 * part; m0 < 12 * part + 12; m0 += 2) {
             const int mode = min(m0 + (lane >> 4), 34);          // the upper half idles on mode 34 twice in the last round
             const pixel *nbuf = intra_use_filter(4, mode) ? s.flt : s.nb;
             int d[4][4];
@@ -1194,7 +1213,7 @@ __global__ void __launch_bounds__(kIntraSearchThreads) k_intra_search(IntraParam
             cbest = min(cbest, c);
         }
         cbest = min(cbest, __shfl_xor_sync(0xffffffffu, cbest, 16));
-        if (lane == 0) p.intra_best[cu] = cbest;
+        if (lane == 0) atomicMin(&p.intra_best[cu], cbest);
         __syncwarp();
     }
 }

@@ -282,6 +282,7 @@ struct hb_encoder {
     int16_t *cmv = nullptr;           // [max_batch][ctus][2]
     int *mode_cost = nullptr;         // [cus][35] intra mode search result of the frame in flight
     int *intra_best = nullptr;        // [cus] best of those per CU
+    int *cand_list = nullptr;         // [cus] work list of the intra search
     SceneStat *scene = nullptr;       // [max_batch] scene-cut measures of the batch in flight (frame chain is serial: one array)
     uint32_t *mvf[2] = {nullptr, nullptr};   // [cus] motion field, ping-pong between the merge-aware passes of one frame
     int *satdf[2] = {nullptr, nullptr};
@@ -554,7 +555,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                 IntraParams np;
                 np.g = g; np.src = s.src; np.rec = rec; np.cus = s.cus; np.coefs = s.coefs; np.progress = e->progress;
                 np.ctl = B.ctl_dev + i; np.second_pass = 0; np.mode_cost = e->mode_cost; np.intra_best = e->intra_best;
-                np.intra_in_p = p.intra_in_p; np.satd1 = e->satdf[1];
+                np.intra_in_p = p.intra_in_p; np.satd1 = e->satdf[1]; np.cand_list = e->cand_list;
                 if (!forced) {
                     InterParams ip;
                     ip.ref_map = e->ref_map[1 - e->cur];
@@ -570,14 +571,18 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
                     ip.mv_in = e->mvf[0]; ip.satd_in = e->satdf[0]; ip.mv_out = e->mvf[1]; ip.satd_out = e->satdf[1];
                     k_merge<<<nctu, 128, xs, st>>>(ip);
                     HB_LAUNCHED(ctx);
-                    k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(np);
+                    k_intra_list<<<(ncu + 255) / 256, 256, 0, st>>>(np);
+                    HB_LAUNCHED(ctx);
+                    k_intra_search<<<std::min((3 * ncu + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(np);
                     HB_LAUNCHED(ctx);
                     ip.mv_in = e->mvf[1]; ip.satd_in = e->satdf[1]; ip.mv_out = nullptr; ip.satd_out = nullptr;
                     k_inter<<<nctu, 128, xs, st>>>(ip);
                     HB_LAUNCHED(ctx);
                 } else {
                     if (e->profiling) HB_CUDA(ctx, cudaEventRecord(B.kev_me[i], st));
-                    k_intra_search<<<std::min((g.cuw * g.cuh + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(np);
+                    k_intra_list<<<(ncu + 255) / 256, 256, 0, st>>>(np);
+                    HB_LAUNCHED(ctx);
+                    k_intra_search<<<std::min((3 * ncu + 3) / 4, 16 * ctx->sm_count), kIntraSearchThreads, 0, st>>>(np);
                     HB_LAUNCHED(ctx);
                 }
                 k_intra<<<g.ctuh, kIntraReconThreads, 0, st>>>(np);
@@ -951,6 +956,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
     HB_TRY(dev_alloc(E, &E->cmv, (size_t)max_batch * nctu * 2));
     HB_TRY(dev_alloc(E, &E->mode_cost, (size_t)g.cuw * g.cuh * 35));
     HB_TRY(dev_alloc(E, &E->intra_best, (size_t)g.cuw * g.cuh));
+    HB_TRY(dev_alloc(E, &E->cand_list, (size_t)g.cuw * g.cuh));
     HB_TRY(dev_alloc(E, &E->scene, (size_t)max_batch));
     for (int k = 0; k < 2; k++) {
         HB_TRY(dev_alloc(E, &E->mvf[k], (size_t)g.cuw * g.cuh));

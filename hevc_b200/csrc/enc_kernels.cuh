@@ -56,6 +56,7 @@ struct IntraParams {
     int *mode_cost;                      // [cus][35] luma SATD per intra mode from k_intra_search
     int *intra_best;                     // [cus] min over the 35 modes (INT_MAX: not searched)
     const int *satd1;                    // [cus] luma SATD after the first merge-aware pass: gate of the P-frame search
+    int *cand_list;                      // [cus] work list of the intra search (k_intra_list -> k_intra_search)
     int second_pass;                     // 1: run only when ctl->redo is set (first key frame of a stream under rate control)
     int intra_in_p;                      // P frames: search every CU and reconstruct the CUs the inter kernel marked intra
 };
@@ -160,6 +161,7 @@ __global__ void k_coarse(CoarseParams p);
 __global__ void k_me(const __grid_constant__ InterParams p);
 __global__ void k_merge(const __grid_constant__ InterParams p);
 __global__ void k_inter(const __grid_constant__ InterParams p);
+__global__ void k_intra_list(IntraParams p);
 __global__ void k_intra_search(IntraParams p);
 __global__ void k_intra(IntraParams p);
 __global__ void k_deblock(DeblockParams p);

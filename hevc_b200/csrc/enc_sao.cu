@@ -203,11 +203,33 @@ __global__ void __launch_bounds__(kSaoThreads) k_sao_apply(SaoParams p)
     const int tid = threadIdx.x, rx = blockIdx.x % g.ctuw, ry = blockIdx.x / g.ctuw;
     const int bd = g.bit_depth, maxv = (1 << bd) - 1, bshift = bd - 5;
     if (tid < 8) reinterpret_cast<uint32_t *>(&sc)[tid] = reinterpret_cast<const uint32_t *>(&p.sao[blockIdx.x])[tid];
+    __syncthreads();
     for (int comp = 0; comp < 3; comp++) {
         const int N = comp ? 16 : 32, w = comp ? g.wc >> 1 : g.wc, h = comp ? g.hc >> 1 : g.hc, stride = comp ? g.recc_stride : g.rec_stride;
         const pixel *pre = comp == 0 ? p.pre.y : comp == 1 ? p.pre.u : p.pre.v;
         pixel *out = comp == 0 ? p.out.y : comp == 1 ? p.out.u : p.out.v;
         const int x0 = rx * N, y0 = ry * N;
+        const int gi = comp ? 1 : 0, type = sc.type[gi], cls = sc.eo_class[gi], band = sc.band[comp];
+        if (type != 2) {
+            // off or band offset: no neighbours involved -- straight from global memory, four samples per work item
+            for (int i = tid; i < N * N / 4; i += kSaoThreads) {
+                const int ly = i / (N / 4), lx = (i - ly * (N / 4)) * 4, y = y0 + ly;
+                if (y >= h || x0 + lx >= w) continue;
+                const ptrdiff_t o = (ptrdiff_t)y * stride + x0 + lx;
+                uint2 v = *reinterpret_cast<const uint2 *>(pre + o);
+                if (type == 1) {
+                    uint32_t q[4] = {v.x & 0xffff, v.x >> 16, v.y & 0xffff, v.y >> 16};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int b = (((int)q[k] >> bshift) - band) & 31;
+                        if (b < 4) q[k] = (uint32_t)min(max((int)q[k] + sc.offset[comp][b], 0), maxv);
+                    }
+                    v = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+                }
+                *reinterpret_cast<uint2 *>(out + o) = v;
+            }
+            continue;
+        }
         __syncthreads();
         for (int i = tid; i < (N + 2) * (N + 2); i += kSaoThreads) {
             const int ty = i / (N + 2), tx = i - ty * (N + 2);
@@ -215,7 +237,6 @@ __global__ void __launch_bounds__(kSaoThreads) k_sao_apply(SaoParams p)
             tile[ty][tx] = pre[(ptrdiff_t)y * stride + x];
         }
         __syncthreads();
-        const int gi = comp ? 1 : 0, type = sc.type[gi], cls = sc.eo_class[gi], band = sc.band[comp];
         int dxa = 0, dya = 0;
         if (cls == 0) dxa = -1; else if (cls == 1) dya = -1; else if (cls == 2) { dxa = -1; dya = -1; } else { dxa = 1; dya = -1; }
         // four consecutive samples per work item: 64-bit stores
@@ -227,10 +248,7 @@ __global__ void __launch_bounds__(kSaoThreads) k_sao_apply(SaoParams p)
             for (int k = 0; k < 4; k++) {
                 const int x = x0 + lx + k, r = tile[ly + 1][lx + k + 1];
                 int o = r;
-                if (type == 1) {
-                    const int b = ((r >> bshift) - band) & 31;
-                    if (b < 4) o = min(max(r + sc.offset[comp][b], 0), maxv);
-                } else if (type == 2) {
+                {
                     const int xa = x + dxa, ya = y + dya, xb = x - dxa, yb = y - dya;
                     if (xa >= 0 && xb >= 0 && ya >= 0 && yb >= 0 && xa < w && xb < w && ya < h && yb < h) {
                         const int cat = sao_category(r, tile[ly + 1 + dya][lx + k + 1 + dxa], tile[ly + 1 - dya][lx + k + 1 - dxa]);
