@@ -477,3 +477,27 @@ def test_sao_matches_cpu_model(ctx, w, h, depth, n, qp):
     assert off_stream != g_stream
     dec = fforacle.decode_hevc(g_stream, verify_hash=True)
     assert len(dec) == n
+
+
+def test_reset_starts_an_independent_stream(ctx):
+    """hb_enc_reset: a reused encoder (the batch worker's pool) produces exactly the bytes a fresh encoder would, including the
+    rate-control trajectory and the two-pass first key frame"""
+    from hevc_b200 import encoder as E
+    w, h = 192, 112
+    p = ec.b200_params(w, h, 8, keyint=5)
+    p.vbv_maxrate_kbps, p.vbv_bufsize_kbit = 300, 360
+    a, b = ec.clip_frames(w, h, 7, seed=31), ec.clip_frames(w, h, 6, seed=32)
+    cp = E.to_c_params(p, qp=(22, 24), hash_sei=False, rate_control=True)
+    fresh = []
+    for frames in (a, b):
+        enc = E.B200Encoder(ctx, cp, max_batch=4)
+        fresh.append(enc.encode(E.pack_yuv420p8(frames), len(frames))[0])
+        enc.close()
+    enc = E.B200Encoder(ctx, cp, max_batch=4)
+    first = enc.encode(E.pack_yuv420p8(a), len(a))[0]
+    enc.reset()
+    second = enc.encode(E.pack_yuv420p8(b), len(b))[0]
+    enc.close()
+    assert first == fresh[0] and second == fresh[1]
+    m_stream, _, _, _ = ec.run_model(p, b, 22, 24, hash_sei=False, rate_control=True)
+    assert second == m_stream
