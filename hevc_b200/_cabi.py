@@ -119,3 +119,66 @@ class Context:
 def dp(t) -> C.c_uint64:
     """Device pointer of a torch tensor (or a raw integer address)."""
     return C.c_uint64(t if isinstance(t, int) else t.data_ptr())
+
+
+# ---------------------------------------------------------------- page-locked host buffers for frame readers
+import threading as _threading
+
+_PINNED_LOCK = _threading.Lock()
+_PINNED_FREE: dict = {}            # size in bytes -> [address]
+_PINNED_CAP = 24 << 30             # keep at most this many idle bytes
+
+
+def pinned_array(nbytes: int):
+    """uint8 NumPy array of ``nbytes`` backed by page-locked memory from a process-wide pool (``hb_host_alloc``); falls back to
+    ordinary memory when the CUDA library or a device is missing (reading files does not need a GPU).  Return it with
+    ``pinned_release`` so that the next file reuses the pages instead of pinning fresh ones (~0.3 s per GB)."""
+    import numpy as np
+    nbytes = int(nbytes)
+    with _PINNED_LOCK:
+        lst = _PINNED_FREE.get(nbytes)
+        addr = lst.pop() if lst else None
+    if addr is None:
+        try:
+            L = lib()
+            L.hb_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+            out = C.c_void_p()
+            if L.hb_host_alloc(nbytes, C.byref(out)) != 0 or not out.value:
+                return np.empty(nbytes, np.uint8)
+            addr = out.value
+        except Exception:
+            return np.empty(nbytes, np.uint8)
+    arr = np.frombuffer((C.c_uint8 * nbytes).from_address(addr), dtype=np.uint8)
+    arr = arr.view(_PinnedArray)
+    arr.hb_addr, arr.hb_bytes = addr, nbytes
+    return arr
+
+
+def pinned_release(arr):
+    addr = getattr(arr, 'hb_addr', None)
+    if addr is None:
+        return
+    arr.hb_addr = None
+    with _PINNED_LOCK:
+        idle = sum(k * len(v) for k, v in _PINNED_FREE.items())
+        if idle + arr.hb_bytes <= _PINNED_CAP:
+            _PINNED_FREE.setdefault(arr.hb_bytes, []).append(addr)
+            return
+    L = lib()
+    L.hb_host_free.argtypes = [C.c_void_p]
+    L.hb_host_free(C.c_void_p(addr))
+
+
+def _make_pinned_cls():
+    import numpy as np
+
+    class PinnedArray(np.ndarray):
+        hb_addr = None
+        hb_bytes = 0
+    return PinnedArray
+
+
+try:
+    _PinnedArray = _make_pinned_cls()
+except Exception:          # NumPy missing: pinned_array is never reached either
+    _PinnedArray = None

@@ -92,6 +92,27 @@ int hb_free(hb_ctx *ctx, hb_devptr p)
     return hb_fail(ctx, HB_ERR_ARG, "hb_free: %s", "pointer not owned by this context");
 }
 
+int hb_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return HB_ERR_ARG;
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return HB_ERR_NOMEM;
+    }
+    *out = p;
+    return HB_OK;
+}
+
+int hb_host_free(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return HB_ERR_CUDA;
+    }
+    return HB_OK;
+}
+
 int hb_upload(hb_ctx *ctx, hb_devptr dst, const void *src, size_t bytes)
 {
     HB_ARG(ctx, ctx && src);

@@ -326,6 +326,8 @@ class ParallelSegmentEncoder:
         self._error: Optional[BaseException] = None
         self._submitted = 0
         self._emitted = 0
+        self._finished = 0                     # segments whose access units have come back from an encoder
+        self.max_outstanding = 2 * self.streams      # submit() blocks beyond this: callers may recycle input buffers behind it
         self._timeline = [[] for _ in range(self.streams)]      # per stream: device time (ms since mark) at which each drain completed
         self._threads = [threading.Thread(target=self._work, args=(k,), daemon=True) for k in range(self.streams)]
         for t in self._threads:
@@ -378,6 +380,7 @@ class ParallelSegmentEncoder:
         # one or more whole segments came back concatenated: split them at their frame counts
         pos = fpos = 0
         with self._lock:
+            self._finished += len(seqs)
             for s in seqs:
                 n = self._frames[s]
                 size = sum(st.bytes for st in stats[fpos:fpos + n])
@@ -401,11 +404,28 @@ class ParallelSegmentEncoder:
         """One closed-GOP segment of at most ``max_batch`` frames (same arguments as ``B200Encoder.encode_delayed``)."""
         if n_frames < 1 or n_frames > self.max_batch:
             raise ValueError('a segment is 1..max_batch frames')
+        import time
+        while True:                            # back-pressure: at most max_outstanding segments between submit and completion
+            with self._lock:
+                if self._error is not None:
+                    raise self._error
+                if self._submitted - self._finished < self.max_outstanding:
+                    break
+            time.sleep(0.0002)      # (queued segments always drain: an encoder holds at most one segment back, so 2 x streams is never idle)
         seq = self._submitted
         self._frames[seq] = n_frames
         self._submitted += 1
         self._queues[seq % self.streams].put((seq, data, n_frames, kw))
         return self._collect()
+
+    def reset(self):
+        """start a new clip on the same encoders (nothing may be in flight: call after ``finish``)"""
+        for e in self._encs:
+            e.reset()
+        with self._lock:
+            self._done.clear()
+            self._frames.clear()
+            self._submitted = self._emitted = self._finished = 0
 
     def finish(self) -> Tuple[bytes, List[FrameStat]]:
         """Drain every stream; returns the remaining segments in order."""

@@ -9,8 +9,29 @@ from typing import Iterator, Tuple
 
 import numpy as np
 
+from . import _cabi
 from .encoder import PIX_YUV420P8, PIX_YUV420P16
 from .probe import VideoInfo, _probe_y4m
+
+
+class _Ring:
+    """``count`` page-locked buffers of ``nbytes`` from the process-wide pool, handed out round-robin"""
+
+    def __init__(self, nbytes: int, count: int):
+        self.nbytes, self.count, self.bufs, self.i = nbytes, max(2, count), [], 0
+
+    def next(self) -> np.ndarray:
+        if len(self.bufs) < self.count:
+            self.bufs.append(_cabi.pinned_array(self.nbytes))
+            self.i = len(self.bufs) - 1
+            return self.bufs[-1]
+        self.i = (self.i + 1) % self.count
+        return self.bufs[self.i]
+
+    def close(self):
+        for b in self.bufs:
+            _cabi.pinned_release(b)
+        self.bufs = []
 
 
 class Y4MReader:
@@ -26,11 +47,19 @@ class Y4MReader:
         self.frame_bytes = self.meta['frame_bytes']
         self.kind = 'yuv'
 
-    def batches(self, batch: int) -> Iterator[Tuple[np.ndarray, int, int]]:
+    def batches(self, batch: int, ring: int = 4) -> Iterator[Tuple[np.ndarray, int, int]]:
+        """``ring`` page-locked buffers are filled in turn: a yielded batch stays valid until ``ring - 1`` more were yielded"""
+        bufs = _Ring(batch * self.frame_bytes, ring)
+        try:
+            yield from self._batches(batch, bufs)
+        finally:
+            bufs.close()
+
+    def _batches(self, batch: int, bufs: '_Ring'):
         with open(self.path, 'rb') as fh:
             fh.seek(self.meta['header_len'])
             while True:
-                buf = np.empty((batch, self.frame_bytes), np.uint8)
+                buf = bufs.next().reshape(batch, self.frame_bytes)
                 n = 0
                 while n < batch:
                     line = fh.readline()
@@ -58,14 +87,21 @@ class RawYuvReader:
         self.frame_bytes = (info.width * info.height + 2 * (info.width // 2) * (info.height // 2)) * bps
         self.kind = 'yuv'
 
-    def batches(self, batch: int):
-        with open(self.path, 'rb') as fh:
-            while True:
-                raw = fh.read(batch * self.frame_bytes)
-                n = len(raw) // self.frame_bytes
-                if n == 0:
-                    return
-                yield np.frombuffer(raw[:n * self.frame_bytes], np.uint8).reshape(n, self.frame_bytes), n, self.fmt
+    def batches(self, batch: int, ring: int = 4):
+        bufs = _Ring(batch * self.frame_bytes, ring)
+        try:
+            with open(self.path, 'rb') as fh:
+                while True:
+                    buf = bufs.next()
+                    got = fh.readinto(memoryview(buf))
+                    n = got // self.frame_bytes
+                    if n == 0:
+                        return
+                    yield buf[:n * self.frame_bytes].reshape(n, self.frame_bytes), n, self.fmt
+                    if n < batch:
+                        return
+        finally:
+            bufs.close()
 
 
 class Cv2Reader:
@@ -79,7 +115,7 @@ class Cv2Reader:
         self.kind = 'bgr'
         self.src_bit_depth = 8
 
-    def batches(self, batch: int):
+    def batches(self, batch: int, ring: int = 0):
         while True:
             frames = []
             while len(frames) < batch:
@@ -103,7 +139,7 @@ class MemoryReader:
     def __init__(self, frames: np.ndarray, fmt: int = PIX_YUV420P8, src_bit_depth: int = 8):
         self.frames, self.fmt, self.src_bit_depth, self.kind = frames, fmt, src_bit_depth, 'yuv'
 
-    def batches(self, batch: int):
+    def batches(self, batch: int, ring: int = 0):
         for s in range(0, len(self.frames), batch):
             chunk = self.frames[s:s + batch]
             yield chunk, len(chunk), self.fmt

@@ -214,6 +214,33 @@ def encoder_pool():
         return _ENCODER_POOL
 
 
+_SEGMENT_POOL: Dict[Any, list] = {}
+
+
+def _segment_pool_get(key):
+    with _ENCODER_POOL_LOCK:
+        lst = _SEGMENT_POOL.get(key)
+        pse = lst.pop() if lst else None
+    if pse is not None:
+        try:
+            pse.reset()
+        except Exception:
+            pse.close()
+            return None
+    return pse
+
+
+def _segment_pool_put(key, pse, reusable: bool):
+    keep = int(os.environ.get('HEVC_B200_POOL', '4') or 0) > 0
+    if reusable and keep:
+        with _ENCODER_POOL_LOCK:
+            lst = _SEGMENT_POOL.setdefault(key, [])
+            if len(lst) < 1:
+                lst.append(pse)
+                return
+    pse.close()
+
+
 def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
                 stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
                 target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None, force_main10: bool = False,
@@ -277,11 +304,16 @@ def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progr
             kw['src_size'] = (src_w, src_h)
         segmented = streams > 1 or len(devs) > 1
         unit = max(1, min(int(params.keyint), 1024)) if segmented else batch
+        ring = 4
         if segmented:
-            pse = ParallelSegmentEncoder(devs, to_c_params(params), streams=streams, max_batch=unit)
-            release = pse.close
+            cparams = to_c_params(params)
+            skey = (tuple(devs), bytes(cparams), int(streams), int(unit))
+            pse = _segment_pool_get(skey) or ParallelSegmentEncoder(devs, cparams, streams=streams, max_batch=unit)
+            ok = [False]
+            release = lambda: _segment_pool_put(skey, pse, ok[0])      # noqa: E731
             submit = lambda data, n, fmt: pse.submit(data, n, fmt=fmt, **kw)      # noqa: E731
             finish = pse.finish
+            ring = pse.max_outstanding + 2           # submit() blocks beyond max_outstanding segments, + one being filled + slack
         else:
             pool = encoder_pool()
             key, ctx, single = pool.acquire(devs[0], to_c_params(params), unit)
@@ -305,7 +337,7 @@ def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progr
 
         # the elementary stream goes to the muxer as it arrives: samples are spooled to disk, the sample tables stay in memory
         with mp4.StreamMuxer(track, out_path) as mux:
-            for buf, n, fmt in reader.batches(unit):
+            for buf, n, fmt in reader.batches(unit, ring):
                 if stop_event is not None and stop_event.is_set():
                     return 1, 'cancelled'
                 data = np.ascontiguousarray(buf).reshape(n, -1)
@@ -318,8 +350,7 @@ def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progr
             out, st = finish()
             mux.feed(out)
             tick(st)
-        if not segmented:
-            ok[0] = True                       # drained cleanly: the encoder can serve the next file
+        ok[0] = True                           # drained cleanly: the encoder(s) can serve the next file
         return 0, ''
     except Exception as exc:
         logger.debug('B200 encode failed', exc_info=True)

@@ -47,6 +47,10 @@ uint64_t hb_launch_count(const hb_ctx *ctx);
 /* device scratch allocation owned by the context (freed by hb_free or hb_destroy) */
 int hb_alloc(hb_ctx *ctx, size_t bytes, hb_devptr *out);
 int hb_free(hb_ctx *ctx, hb_devptr p);
+/* page-locked host memory for frame buffers (cudaMallocHost): uploads from it run at full PCIe rate and truly asynchronously,
+ * which is what lets the reader fill batch k+1 while batch k is still being copied */
+int hb_host_alloc(size_t bytes, void **out);
+int hb_host_free(void *p);
 int hb_upload(hb_ctx *ctx, hb_devptr dst, const void *src, size_t bytes);     /* async on the ctx stream */
 int hb_download(hb_ctx *ctx, void *dst, hb_devptr src, size_t bytes);         /* async on the ctx stream */
 /* event timing on the context's stream: start/stop bracket launches, elapsed is in milliseconds */
