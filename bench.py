@@ -635,7 +635,7 @@ def main():
     ap.add_argument('--clip', default=None)
     ap.add_argument('--frames', type=int, default=None, help='frames per step and stream (default: one closed GOP of the configuration)')
     ap.add_argument('--batch', type=int, default=None, help='frames per device batch (default: --frames)')
-    ap.add_argument('--streams', type=int, default=2, help='independent encoder streams per GPU (closed-GOP segments round-robin)')
+    ap.add_argument('--streams', type=int, default=3, help='independent encoder streams per GPU (closed-GOP segments round-robin)')
     ap.add_argument('--ref-frames', type=int, default=30, help='--impl reference: frames per step (one closed GOP)')
     ap.add_argument('--files', type=int, default=64, help='config 3: files in the batch')
     ap.add_argument('--clip-frames', type=int, default=None, help='config 3: frames per file (150); config 4: frames of the clip (1800)')
