@@ -68,7 +68,9 @@ __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel
     const int k = tid >> 6, lane64 = tid & 63;
     // neighbour pair of this group's class (oracle k_sao_dx / k_sao_dy): a = (dxa, dya), b = (-dxa, -dya)
     const int dxa = k == 1 ? 0 : k == 3 ? 1 : -1, dya = k == 0 ? 0 : -1;
-    int cnt[4] = {0, 0, 0, 0}, sum[4] = {0, 0, 0, 0};
+    // count and error sum of a category share one accumulator: (count << 22) + sum.  A thread sees at most 16 samples (|sum| < 2^15), a
+    // warp 512 (|sum| < 2^20), so the signed sum never reaches bit 21 and the pair comes apart again after the warp reduction.
+    int acc[4] = {0, 0, 0, 0};
     for (int j = 0; j < N * N / 64; j++) {
         const int i = lane64 + 64 * j;
         const int ly = i / N, lx = i - ly * N, x = x0 + lx, y = y0 + ly;
@@ -84,16 +86,14 @@ __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel
         const int xa = x + dxa, ya = y + dya, xb = x - dxa, yb = y - dya;
         const bool ok = inside && xa >= 0 && xb >= 0 && ya >= 0 && yb >= 0 && xa < w && xb < w && ya < h && yb < h;
         const int cat = ok ? sao_category(r, s.tile[ly + 1 + dya][lx + 1 + dxa], s.tile[ly + 1 - dya][lx + 1 - dxa]) : 0;
+        const int contrib = (1 << 22) + d;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const bool hit = cat == c + 1;
-            cnt[c] += hit;
-            sum[c] += hit ? d : 0;
-        }
+        for (int c = 0; c < 4; c++) acc[c] += cat == c + 1 ? contrib : 0;
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        const int tc = __reduce_add_sync(0xffffffffu, cnt[c]), ts = __reduce_add_sync(0xffffffffu, sum[c]);
+        const int t = __reduce_add_sync(0xffffffffu, acc[c]);
+        const int ts = (int)((unsigned)t << 10) >> 10, tc = (t - ts) >> 22;
         if ((tid & 31) == 0 && tc) { atomicAdd(&st.cnt[k][c], tc); atomicAdd(&st.sum[k][c], ts); }
     }
 }

@@ -45,6 +45,48 @@ __global__ void __launch_bounds__(256) k_sad(const pixel *__restrict__ a, const 
     }
 }
 
+// x265 sad_x3 / sad_x4: one source block against R (3 or 4) reference blocks; the source vectors are loaded once
+template <int R>
+__global__ void __launch_bounds__(256) k_sad_multi(const pixel *__restrict__ a, const pixel *__restrict__ b0, const pixel *__restrict__ b1,
+                                                   const pixel *__restrict__ b2, const pixel *__restrict__ b3, int n, int wh, int T,
+                                                   int *__restrict__ out)
+{
+    const int lane_in = threadIdx.x % T;
+    const long long first = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
+    const long long stride = (long long)gridDim.x * blockDim.x / T;
+    const long long rounds = (n + stride - 1) / stride;
+    const int vecs = wh >> 3;
+    const pixel *refs[4] = {b0, b1, b2, b3};
+    for (long long r = 0; r < rounds; r++) {
+        const long long blk = first + r * stride;
+        int s[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) s[k] = 0;
+        if (blk < n) {
+            const uint4 *pa = reinterpret_cast<const uint4 *>(a + blk * wh);
+            for (int v = lane_in; v < vecs; v += T) {
+                const uint4 x = __ldg(pa + v);
+                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    const uint4 y = __ldg(reinterpret_cast<const uint4 *>(refs[k] + blk * wh) + v);
+                    const uint32_t ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        s[k] += abs((int)(xs[j] & 0xffff) - (int)(ys[j] & 0xffff));
+                        s[k] += abs((int)(xs[j] >> 16) - (int)(ys[j] >> 16));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int t = group_sum(s[k], T);
+            if (blk < n && lane_in == 0) out[blk * R + k] = t;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ SATD
 // one lane per 4x4 sub-block; SATD(WxH) = sum over sub-blocks of raw/2 (raw sums are always even, so the
 // x265 8x4 pairing "(raw0 + raw1) >> 1" gives the same value)
@@ -275,6 +317,26 @@ int hb_sad(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int w, int h, hb_devptr
     T = T > 32 ? 32 : T;
     while (T & (T - 1)) T &= T - 1;   // power of two for the shuffle width
     k_sad<<<hb_grid_for(ctx, (long long)n * T, 256, 8), 256, 0, ctx->stream>>>((const pixel *)a, (const pixel *)b, n, w * h, T, (int *)out);
+    HB_LAUNCHED(ctx);
+    return HB_OK;
+}
+
+int hb_sad_multi(hb_ctx *ctx, hb_devptr fenc, hb_devptr ref0, hb_devptr ref1, hb_devptr ref2, hb_devptr ref3, int n_refs, int n, int w, int h,
+                 hb_devptr out)
+{
+    HB_ARG(ctx, ctx && fenc && ref0 && ref1 && ref2 && out && (n_refs == 3 || (n_refs == 4 && ref3)) && n >= 0 && w >= 4 && h >= 4 && (w * h) % 8 == 0);
+    HB_ARG(ctx, ((fenc | ref0 | ref1 | ref2 | (n_refs == 4 ? ref3 : 0)) & 15) == 0);
+    if (!n) return HB_OK;
+    int T = w * h / 8;
+    T = T > 32 ? 32 : T;
+    while (T & (T - 1)) T &= T - 1;
+    const int grid = hb_grid_for(ctx, (long long)n * T, 256, 8);
+    if (n_refs == 3)
+        k_sad_multi<3><<<grid, 256, 0, ctx->stream>>>((const pixel *)fenc, (const pixel *)ref0, (const pixel *)ref1, (const pixel *)ref2, nullptr, n, w * h, T,
+                                                      (int *)out);
+    else
+        k_sad_multi<4><<<grid, 256, 0, ctx->stream>>>((const pixel *)fenc, (const pixel *)ref0, (const pixel *)ref1, (const pixel *)ref2, (const pixel *)ref3, n,
+                                                      w * h, T, (int *)out);
     HB_LAUNCHED(ctx);
     return HB_OK;
 }

@@ -71,6 +71,16 @@ def sad(ctx, a, b):
     return _cost(ctx, 'hb_sad', a, b, a.shape[2], a.shape[1])
 
 
+def sad_multi(ctx, fenc, refs):
+    """x265 sad_x3 / sad_x4: ``fenc`` [n, H, W] against 3 or 4 reference batches -> int32 [n, len(refs)]"""
+    n = fenc.shape[0]
+    out = torch.empty((n, len(refs)), dtype=torch.int32, device=fenc.device)
+    r = list(refs) + [None] * (4 - len(refs))
+    ctx.call('hb_sad_multi', dp(fenc), dp(r[0]), dp(r[1]), dp(r[2]), dp(r[3]) if r[3] is not None else C.c_uint64(0), len(refs), n,
+             fenc.shape[2], fenc.shape[1], dp(out))
+    return out
+
+
 def satd(ctx, a, b):
     return _cost(ctx, 'hb_satd', a, b, a.shape[2], a.shape[1])
 

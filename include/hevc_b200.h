@@ -107,6 +107,9 @@ int hb_scale_yuv420_to_p010_batch(hb_ctx *ctx, hb_devptr src, size_t src_frame_b
 
 /* out[i] = SAD / SATD of block i of `a` against block i of `b`; out is int32[n] */
 int hb_sad(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int w, int h, hb_devptr out);
+/* x265 sad_x3 / sad_x4: one source block against n_refs (3 or 4) reference blocks, the source read once; out int32[n][n_refs] */
+int hb_sad_multi(hb_ctx *ctx, hb_devptr fenc, hb_devptr ref0, hb_devptr ref1, hb_devptr ref2, hb_devptr ref3, int n_refs, int n,
+                 int w, int h, hb_devptr out);
 int hb_satd(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int w, int h, hb_devptr out);
 /* square blocks, size 4 (== satd 4x4), 8, 16, 32, 64 */
 int hb_sa8d(hb_ctx *ctx, hb_devptr a, hb_devptr b, int n, int size, hb_devptr out);

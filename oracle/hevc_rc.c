@@ -5,7 +5,7 @@
  * integer-only one both implementations share: the CRF-derived QP is a quality ceiling (never go
  * below it) and the QP is raised so that a leaky-bucket model of the decoder buffer does not underflow.  Frame sizes are
  * *estimated* from the quantised levels (so the GPU never has to wait for the entropy coder): within a few percent of
- * the real size (tools/calibrate_rc.py). */
+ * the real size (tools/calibrate_rc.py -> profiles/rc_estimate_calibration_r2.jsonl). */
 #include <stdlib.h>
 
 #include "hevc_model.h"

@@ -47,6 +47,24 @@ def test_sad_satd_all_pu_sizes(env, w, h):
         assert (satd.cpu().numpy() == cmodel.satd(a, b)).all()
 
 
+@pytest.mark.parametrize('w,h', [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (16, 12), (12, 16), (64, 48), (8, 32)])
+def test_sad_x3_x4(env, w, h):
+    """x265 sad_x3 / sad_x4: one source block against three / four references = the single SADs"""
+    from hevc_b200 import ops
+    from oracle import cmodel
+    ctx, torch = env
+    rng = np.random.default_rng(w * 31 + h)
+    n = 53
+    a, _ = _blocks(rng, n, h, w, 10)
+    refs = [rng.integers(0, 1024, (n, h, w)).astype(np.uint16) for _ in range(4)]
+    ga, gr = _g16(torch, a), [_g16(torch, r) for r in refs]
+    for k in (3, 4):
+        got = ops.sad_multi(ctx, ga, gr[:k])
+        ctx.sync()
+        want = np.stack([cmodel.sad(a, r) for r in refs[:k]], axis=1)
+        assert (got.cpu().numpy() == want).all()
+
+
 @pytest.mark.parametrize('size', [4, 8, 16, 32, 64])
 def test_sa8d(env, size):
     from hevc_b200 import ops
