@@ -501,3 +501,30 @@ def test_reset_starts_an_independent_stream(ctx):
     assert first == fresh[0] and second == fresh[1]
     m_stream, _, _, _ = ec.run_model(p, b, 22, 24, hash_sei=False, rate_control=True)
     assert second == m_stream
+
+
+@pytest.mark.parametrize('seed', range(14))
+def test_randomised_configurations_match_cpu_model(ctx, seed):
+    """fuzz over geometry (odd CU counts, conformance-window crops), bit depth, quantiser, key-frame cadence, content class
+    (incl. hard cuts and fast pans -> scene-cut key frames, intra CUs in P frames), rate control and tool flags"""
+    from hevc_b200.synth import content_clip
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(9, 60)) * 8, int(rng.integers(5, 34)) * 8
+    depth = int(rng.choice([8, 10]))
+    qp = int(rng.integers(8, 46))
+    keyint = int(rng.choice([3, 5, 8, 30]))
+    kind = str(rng.choice(['base', 'hardcut', 'pan', 'static', 'grain', 'clean']))
+    n = int(rng.integers(4, 10))
+    rc = bool(rng.integers(0, 2))
+    tools = {'scenecut': bool(rng.integers(0, 4) > 0), 'intra_in_p': bool(rng.integers(0, 4) > 0), 'sao': bool(rng.integers(0, 4) > 0)}
+    deblock = bool(rng.integers(0, 5) > 0)
+    p = ec.b200_params(w, h, depth, keyint=keyint)
+    if rc:
+        p.vbv_maxrate_kbps = int(rng.choice([150, 600, 4000]))
+        p.vbv_bufsize_kbit = int(p.vbv_maxrate_kbps * 1.2)
+    frames = content_clip(kind, w, h, n, seed=seed)
+    m_stream, m_aus, _, _ = ec.run_model(p, frames, qp, min(51, qp + 2), hash_sei=True, rate_control=rc, deblock=deblock, **tools)
+    split = [n] if n < 6 else [n // 2, n - n // 2]
+    g_stream, _, _ = _gpu_encode(ctx, p, frames, (qp, min(51, qp + 2)), batch=int(rng.choice([2, 3, 8])), split=split, read_back=False,
+                                 rate_control=rc, deblock=deblock, **tools)
+    assert g_stream == m_stream, (w, h, depth, qp, keyint, kind, n, rc, tools, deblock)
