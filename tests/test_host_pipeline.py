@@ -261,3 +261,151 @@ def test_parallel_segment_encoder_orders_and_splits_segments(monkeypatch):
     assert got == b''.join(segs) and frames == 28
     with pytest.raises(ValueError):
         E.ParallelSegmentEncoder.submit(pse, b'', 0)
+
+
+_SEGMENT_MUX_SCRIPT = r'''
+import os, sys, pickle, torch, torch.distributed as dist
+root, work = sys.argv[1], sys.argv[2]
+sys.path.insert(0, root)
+import numpy as np
+from hevc_b200 import mp4
+from hevc_b200.batch import gop_segments
+from hevc_b200.synth import SynthClip
+from oracle import encoder_model as em
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+w, h, n, keyint = 96, 64, 14, 4
+segs = gop_segments(n, keyint)                         # config 4 in miniature: closed-GOP segment k -> rank k mod world
+clip = SynthClip(w, h, seed=5)
+runs = {}
+for k, (a, b) in enumerate(segs):
+    if k % world != rank:
+        continue
+    enc = em.ModelEncoder(em.make_params(w, h, 8, qp_i=30, qp_p=32, keyint=keyint, hash_sei=False))     # every segment: its own encoder, IDR first
+    es = b''.join(enc.encode(*clip.frame(i))[0] for i in range(a, b))
+    enc.close()
+    runs[k] = mp4.to_samples(es)                       # converted to MP4 sample form on the rank that coded it
+    open(os.path.join(work, 'seg%02d.es' % k), 'wb').write(es)
+gathered = [None] * world if rank == 0 else None
+dist.gather_object(runs, gathered, dst=0)
+if rank == 0:
+    allruns = {}
+    for g in gathered:
+        allruns.update(g)
+    track = mp4.TrackInfo(w, h, 30, 1, 1, 90, 0, 8, 1, 1, 1)
+    open(os.path.join(work, 'out.mp4'), 'wb').write(mp4.assemble(track, [allruns[k] for k in range(len(segs))]))
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok', sorted(runs))
+'''
+
+
+def test_segment_gather_and_single_mux_world_size_2(tmp_path):
+    """the N > 1 host path of config 4 on two gloo ranks: per-rank closed-GOP segments (CPU model streams), per-rank conversion
+    to MP4 sample form, gather on rank 0, ONE file -- equal to muxing the concatenated stream in one process, and decodable"""
+    from oracle import fforacle
+    script = tmp_path / 'segmux.py'
+    script.write_text(_SEGMENT_MUX_SCRIPT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29547', str(script), str(Path(__file__).resolve().parent.parent), str(tmp_path)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    es = b''.join((tmp_path / f'seg{k:02d}.es').read_bytes() for k in range(4))
+    track = mp4.TrackInfo(96, 64, 30, 1, 1, 90, 0, 8, 1, 1, 1)
+    data = (tmp_path / 'out.mp4').read_bytes()
+    assert data == mp4.mux_annexb(track, es)
+    rep = compliance.inspect(data)
+    assert rep['n_samples'] == 14 and rep['sync_samples'] == [1, 5, 9, 13]
+    assert len(fforacle.decode_hevc(es, verify_hash=False)) == 14
+
+
+def test_stream_muxer_equals_one_shot_mux(tmp_path):
+    """the incremental muxer (samples spooled to disk, tables in memory) writes the same bytes as mux_annexb, leaves no spool
+    behind, and writes nothing when the encode fails half way"""
+    from oracle import encoder_model as em
+    clip = SynthClip(64, 48, seed=3)
+    enc = em.ModelEncoder(em.make_params(64, 48, 8, qp_i=30, qp_p=32, keyint=3, hash_sei=False))
+    aus = [enc.encode(*clip.frame(i))[0] for i in range(7)]
+    enc.close()
+    track = mp4.TrackInfo(64, 48, 30, 1, 1, 90, 0, 8, 1, 1, 1)
+    out = tmp_path / 'a.mp4'
+    with mp4.StreamMuxer(track, out) as m:
+        m.feed(b'')
+        m.feed(b''.join(aus[:2]))
+        m.feed(aus[2])
+        m.feed(b''.join(aus[3:]))
+    assert out.read_bytes() == mp4.mux_annexb(track, b''.join(aus))
+    assert sorted(p.name for p in tmp_path.iterdir()) == ['a.mp4']
+    bad = tmp_path / 'b.mp4'
+    with pytest.raises(RuntimeError):
+        with mp4.StreamMuxer(track, bad) as m:
+            m.feed(aus[0])
+            raise RuntimeError('encoder died')
+    assert not bad.exists() and not (tmp_path / 'b.mp4.mdat.tmp').exists()
+
+
+def test_encoder_pool_reuses_and_evicts(monkeypatch):
+    from hevc_b200 import _cabi
+    from hevc_b200 import encoder as E
+    made, closed = [], []
+
+    class StubCtx:
+        def __init__(self, device):
+            self.device = device
+
+        def close(self):
+            closed.append(('ctx', self.device))
+
+    class StubEnc:
+        def __init__(self, ctx, params, max_batch=32):
+            self.resets = 0
+            made.append(self)
+
+        def reset(self):
+            self.resets += 1
+
+        def close(self):
+            closed.append(('enc', id(self)))
+
+    monkeypatch.setattr(_cabi, 'Context', StubCtx)
+    monkeypatch.setattr(E, 'B200Encoder', StubEnc)
+    pool = E.EncoderPool(max_idle=2)
+    pa, pb = E.HbEncParams(width=64, height=64), E.HbEncParams(width=128, height=64)
+    k1, c1, e1 = pool.acquire(0, pa, 8)
+    pool.release(k1, c1, e1)
+    k2, c2, e2 = pool.acquire(0, pa, 8)
+    assert e2 is e1 and e1.resets == 1 and len(made) == 1                 # same geometry: reused after a reset
+    k3, c3, e3 = pool.acquire(0, pb, 8)
+    assert e3 is not e1 and len(made) == 2                                # other geometry: a new one
+    pool.release(k2, c2, e2)
+    pool.release(k3, c3, e3, reusable=False)                              # a failed encode never goes back
+    assert ('enc', id(e3)) in closed and ('enc', id(e1)) not in closed
+    for _ in range(3):
+        k, c, e = pool.acquire(1, pa, 8)                                  # other device: new encoders; the idle list is capped
+        pool.release(k, c, e)
+    pool.close()
+    assert sum(1 for x in closed if x[0] == 'enc') == len(made)
+
+
+def test_memory_reader_and_ring_buffers(tmp_path):
+    from hevc_b200.frames import MemoryReader, RawYuvReader, _Ring
+    frames = np.arange(7 * 24, dtype=np.uint8).reshape(7, 24)
+    got = list(MemoryReader(frames).batches(3))
+    assert [n for _, n, _ in got] == [3, 3, 1] and (np.concatenate([b for b, _, _ in got]) == frames).all()
+    ring = _Ring(16, 3)
+    ids = [ring.next().ctypes.data for _ in range(7)]
+    assert ids[:3] == ids[3:6] and ids[6] == ids[0] and len(set(ids[:3])) == 3
+    ring.close()
+    # raw planar reader: a yielded batch stays intact while ring - 1 further batches are read
+    w, h = 16, 8
+    raw = np.random.default_rng(0).integers(0, 256, (5, w * h * 3 // 2), dtype=np.uint8)
+    path = tmp_path / 'c.yuv'
+    path.write_bytes(raw.tobytes())
+    info = probe.VideoInfo(**{**probe._FALLBACK, 'width': w, 'height': h, 'pix_fmt': 'yuv420p'})
+    held = []
+    for buf, n, fmt in RawYuvReader(path, info).batches(2, ring=3):
+        held.append((buf, buf.copy()))
+        for view, snap in held[-2:]:
+            assert (view == snap).all()
+    assert sum(len(v) for v, _ in held) == 5 and (np.concatenate([s for _, s in held]) == raw).all()

@@ -96,6 +96,7 @@ def main():
     ap.add_argument('--classes', default='base,hardcut,pan,static,grain')
     ap.add_argument('--sets', default='r1,r2')
     ap.add_argument('--qps', default='22,27,32,37')
+    ap.add_argument('--vbv', default='', help='maxrate,bufsize in kbit: crf + VBV mode (rate control on; --qps are then the crf-derived key-frame QPs)')
     ap.add_argument('--out', default='')
     args = ap.parse_args()
     from hevc_b200.synth import content_clip
@@ -108,7 +109,10 @@ def main():
         curves = {}
         for name in sets:
             for qp in (int(q) for q in args.qps.split(',')):
-                r = run_point(frames, w, h, args.depth, qp, args.fps, args.keyint, TOOLSETS[name])
+                rc = tuple(int(x) for x in args.vbv.split(',')) if args.vbv else None
+                r = run_point(frames, w, h, args.depth, qp, args.fps, args.keyint, TOOLSETS[name], rc=rc)
+                if rc:
+                    r['vbv'] = list(rc)
                 r.update({'class': kind, 'set': name, 'qp_i': qp, 'size': args.size, 'frames': args.frames, 'depth': args.depth,
                           'x265_anchor': None})
                 curves.setdefault(name, []).append(r)
