@@ -49,7 +49,8 @@ __device__ int sao_offset(long long cnt, long long sum, int lo, int hi, long lon
 }
 
 // stage the N x N block at (x0, y0) of `plane` with a one-sample halo; samples outside the picture are never read back
-__device__ __forceinline__ void stage_tile(SaoScratch &s, const pixel *plane, int stride, int x0, int y0, int N, int w, int h, int tid)
+template <int N>
+__device__ __forceinline__ void stage_tile(SaoScratch &s, const pixel *plane, int stride, int x0, int y0, int w, int h, int tid)
 {
     for (int i = tid; i < (N + 2) * (N + 2); i += kSaoThreads) {
         const int ty = i / (N + 2), tx = i - ty * (N + 2);
@@ -62,10 +63,11 @@ __device__ __forceinline__ void stage_tile(SaoScratch &s, const pixel *plane, in
 // samples of the N x N block (sample i = (tid & 63) + 64 j), classifies them for ITS class only and keeps the four categories'
 // counts and sums in registers (8 accumulators instead of 32: the kernel stays at 6 resident CTAs per SM); the band statistics
 // of a sample are taken by the group whose class number equals j mod 4, through warp-aggregated shared-memory atomics.
-__device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel *src, int src_stride, int x0, int y0, int N, int w, int h,
+template <int N>
+__device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel *src, int src_stride, int x0, int y0, int w, int h,
                                         int bshift, int tid)
 {
-    const int k = tid >> 6, lane64 = tid & 63;
+    const int k = tid >> 6, lane64 = tid & 63, logn = N == 32 ? 5 : 4;
     // neighbour pair of this group's class (oracle k_sao_dx / k_sao_dy): a = (dxa, dya), b = (-dxa, -dya)
     const int dxa = k == 1 ? 0 : k == 3 ? 1 : -1, dya = k == 0 ? 0 : -1;
     // count and error sum of a category share one accumulator: (count << 22) + sum.  A thread sees at most 16 samples (|sum| < 2^15), a
@@ -73,7 +75,7 @@ __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel
     int acc[4] = {0, 0, 0, 0};
     for (int j = 0; j < N * N / 64; j++) {
         const int i = lane64 + 64 * j;
-        const int ly = i / N, lx = i - ly * N, x = x0 + lx, y = y0 + ly;
+        const int ly = i >> logn, lx = i & (N - 1), x = x0 + lx, y = y0 + ly;      // N is 32 or 16
         const bool inside = x < w && y < h;
         const int r = s.tile[ly + 1][lx + 1];
         const int d = inside ? (int)__ldg(src + (size_t)y * src_stride + x) - r : 0;
@@ -161,9 +163,11 @@ __global__ void __launch_bounds__(kSaoThreads, 6) k_sao_decide(SaoParams p)
     for (int comp = 0; comp < 3; comp++) {
         const int N = comp ? 16 : 32, w = comp ? g.wc >> 1 : g.wc, h = comp ? g.hc >> 1 : g.hc;
         const pixel *pre = comp == 0 ? p.pre.y : comp == 1 ? p.pre.u : p.pre.v, *src = comp == 0 ? p.src.y : comp == 1 ? p.src.u : p.src.v;
-        stage_tile(s, pre, comp ? g.recc_stride : g.rec_stride, rx * N, ry * N, N, w, h, tid);
+        if (comp == 0) stage_tile<32>(s, pre, g.rec_stride, rx * N, ry * N, w, h, tid);
+        else stage_tile<16>(s, pre, g.recc_stride, rx * N, ry * N, w, h, tid);
         __syncthreads();
-        collect(s, s.st[comp], src, comp ? g.srcc_stride : g.src_stride, rx * N, ry * N, N, w, h, bshift, tid);
+        if (comp == 0) collect<32>(s, s.st[comp], src, g.src_stride, rx * N, ry * N, w, h, bshift, tid);
+        else collect<16>(s, s.st[comp], src, g.srcc_stride, rx * N, ry * N, w, h, bshift, tid);
         __syncthreads();
     }
     const int qp = p.ctl->qp;
@@ -208,12 +212,12 @@ __global__ void __launch_bounds__(kSaoThreads) k_sao_apply(SaoParams p)
         const int N = comp ? 16 : 32, w = comp ? g.wc >> 1 : g.wc, h = comp ? g.hc >> 1 : g.hc, stride = comp ? g.recc_stride : g.rec_stride;
         const pixel *pre = comp == 0 ? p.pre.y : comp == 1 ? p.pre.u : p.pre.v;
         pixel *out = comp == 0 ? p.out.y : comp == 1 ? p.out.u : p.out.v;
-        const int x0 = rx * N, y0 = ry * N;
+        const int x0 = rx * N, y0 = ry * N, lq = comp ? 2 : 3;      // log2(N / 4)
         const int gi = comp ? 1 : 0, type = sc.type[gi], cls = sc.eo_class[gi], band = sc.band[comp];
         if (type != 2) {
             // off or band offset: no neighbours involved -- straight from global memory, four samples per work item
             for (int i = tid; i < N * N / 4; i += kSaoThreads) {
-                const int ly = i / (N / 4), lx = (i - ly * (N / 4)) * 4, y = y0 + ly;
+                const int ly = i >> lq, lx = (i & (N / 4 - 1)) * 4, y = y0 + ly;
                 if (y >= h || x0 + lx >= w) continue;
                 const ptrdiff_t o = (ptrdiff_t)y * stride + x0 + lx;
                 uint2 v = *reinterpret_cast<const uint2 *>(pre + o);
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(kSaoThreads) k_sao_apply(SaoParams p)
         if (cls == 0) dxa = -1; else if (cls == 1) dya = -1; else if (cls == 2) { dxa = -1; dya = -1; } else { dxa = 1; dya = -1; }
         // four consecutive samples per work item: 64-bit stores
         for (int i = tid; i < N * N / 4; i += kSaoThreads) {
-            const int ly = i / (N / 4), lx = (i - ly * (N / 4)) * 4, y = y0 + ly;
+            const int ly = i >> lq, lx = (i & (N / 4 - 1)) * 4, y = y0 + ly;
             if (y >= h || x0 + lx >= w) continue;
             uint32_t v[4];
 #pragma unroll
