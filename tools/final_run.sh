@@ -5,7 +5,7 @@ mkdir -p $o
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $o/pytest_gpu.txt; cat $o/pytest_gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $o/smoke.txt 2>&1; tail -1 $o/smoke.txt
 python bench.py --gpus 1 --steps 10 --warmup 3 > $o/bench_c2_n1.json 2> $o/bench_c2_n1.err; tail -c 300 $o/bench_c2_n1.err
-python bench.py --steps 5 --streams 3 --no-cpu-baseline > $o/bench_c2_n1_streams3.json 2>/dev/null
+python bench.py --steps 5 --streams 2 --no-cpu-baseline > $o/bench_c2_n1_streams2.json 2>/dev/null
 python bench.py --steps 5 --streams 1 --no-cpu-baseline > $o/bench_c2_n1_streams1.json 2>/dev/null
 python bench.py --config 1 --steps 10 > $o/bench_c1_n1.json 2> $o/bench_c1_n1.err
 python bench.py --config 3 --steps 2 > $o/bench_c3_n1.json 2> $o/bench_c3_n1.err
@@ -15,7 +15,7 @@ python tools/pixel_bench.py > $o/microbench.jsonl 2> $o/microbench.err
 python tools/dropin_bench.py 4k60_hdr 1080p_sdr > $o/dropin.jsonl 2> $o/dropin.err; cat $o/dropin.jsonl
 ncu -k regex:^k_ --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $o/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $o/ncu_launches.log 2>&1
 python tools/launch_summary.py $o/launches.csv > $o/launch_summary.md; cat $o/launch_summary.md
-for f in c2_n1 c2_n1_streams3 c2_n1_streams1 c1_n1 c3_n1 c4_n1 reference_arm; do python - <<PY
+for f in c2_n1 c2_n1_streams2 c2_n1_streams1 c1_n1 c3_n1 c4_n1 reference_arm; do python - <<PY
 import json
 try:
     d=json.loads(open('$o/bench_$f.json').read().strip().splitlines()[-1]); print('$f', d['value'], d['e2e']['value'], d.get('ms_per_step_median'), (d.get('roofline') or {}).get('frac'), (d.get('cpu_baseline') or {}).get('value'))
