@@ -48,14 +48,9 @@ class Y4MReader:
         self.kind = 'yuv'
 
     def batches(self, batch: int, ring: int = 4) -> Iterator[Tuple[np.ndarray, int, int]]:
-        """``ring`` page-locked buffers are filled in turn: a yielded batch stays valid until ``ring - 1`` more were yielded"""
-        bufs = _Ring(batch * self.frame_bytes, ring)
-        try:
-            yield from self._batches(batch, bufs)
-        finally:
-            bufs.close()
-
-    def _batches(self, batch: int, bufs: '_Ring'):
+        """``ring`` page-locked buffers are filled in turn: a yielded batch stays valid until ``ring - 1`` more were yielded.
+        The buffers go back to the pool in ``close()`` -- call it only when the encoder no longer reads from them."""
+        bufs = self._ring = _Ring(batch * self.frame_bytes, ring)
         with open(self.path, 'rb') as fh:
             fh.seek(self.meta['header_len'])
             while True:
@@ -75,6 +70,13 @@ class Y4MReader:
                 if n < batch:
                     return
 
+    def close(self):
+        ring, self._ring = getattr(self, '_ring', None), None
+        if ring is not None:
+            ring.close()
+
+    __del__ = close
+
 
 class RawYuvReader:
     """Headerless planar 4:2:0; geometry and bit depth come from the probe (sidecar JSON)."""
@@ -88,20 +90,24 @@ class RawYuvReader:
         self.kind = 'yuv'
 
     def batches(self, batch: int, ring: int = 4):
-        bufs = _Ring(batch * self.frame_bytes, ring)
-        try:
-            with open(self.path, 'rb') as fh:
-                while True:
-                    buf = bufs.next()
-                    got = fh.readinto(memoryview(buf))
-                    n = got // self.frame_bytes
-                    if n == 0:
-                        return
-                    yield buf[:n * self.frame_bytes].reshape(n, self.frame_bytes), n, self.fmt
-                    if n < batch:
-                        return
-        finally:
-            bufs.close()
+        bufs = self._ring = _Ring(batch * self.frame_bytes, ring)
+        with open(self.path, 'rb') as fh:
+            while True:
+                buf = bufs.next()
+                got = fh.readinto(memoryview(buf))
+                n = got // self.frame_bytes
+                if n == 0:
+                    return
+                yield buf[:n * self.frame_bytes].reshape(n, self.frame_bytes), n, self.fmt
+                if n < batch:
+                    return
+
+    def close(self):
+        ring, self._ring = getattr(self, '_ring', None), None
+        if ring is not None:
+            ring.close()
+
+    __del__ = close
 
 
 class Cv2Reader:
@@ -131,6 +137,9 @@ class Cv2Reader:
                 self.cap.release()
                 return
 
+    def close(self):
+        pass
+
 
 class MemoryReader:
     """Frames already in host memory (uint8 array [n, frame_bytes] in the hb_frames layout): the reader interface over a buffer,
@@ -143,6 +152,9 @@ class MemoryReader:
         for s in range(0, len(self.frames), batch):
             chunk = self.frames[s:s + batch]
             yield chunk, len(chunk), self.fmt
+
+    def close(self):
+        pass
 
 
 def open_reader(path: Path, info: VideoInfo):

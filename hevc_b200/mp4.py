@@ -241,10 +241,15 @@ class StreamMuxer:
         self.sizes: List[int] = []
         self.sync: List[int] = []
         self._spool = None
+        self._aborted = False
 
     def __enter__(self):
         self._spool = open(self.spool_path, 'wb')
         return self
+
+    def abort(self):
+        """cancelled / failed: leave no output file behind"""
+        self._aborted = True
 
     def feed(self, annexb: bytes):
         if not annexb:
@@ -260,7 +265,7 @@ class StreamMuxer:
         import shutil
         self._spool.close()
         try:
-            if exc_type is None and self.sizes:
+            if exc_type is None and self.sizes and not self._aborted:
                 if len(self.sets) != 3:
                     raise ValueError('stream carries no VPS/SPS/PPS')
                 with open(self.out_path, 'wb') as out, open(self.spool_path, 'rb') as spool:

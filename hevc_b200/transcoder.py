@@ -339,6 +339,7 @@ def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progr
         with mp4.StreamMuxer(track, out_path) as mux:
             for buf, n, fmt in reader.batches(unit, ring):
                 if stop_event is not None and stop_event.is_set():
+                    mux.abort()
                     return 1, 'cancelled'
                 data = np.ascontiguousarray(buf).reshape(n, -1)
                 out, st = submit(data, n, fmt_override if fmt_override is not None else fmt)
@@ -346,6 +347,7 @@ def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progr
                 submitted += n
                 tick(st)
             if submitted == 0:
+                mux.abort()
                 return 1, 'no frames decoded'
             out, st = finish()
             mux.feed(out)
@@ -358,7 +360,11 @@ def encode_reader_b200(reader, name: str, out_path: Path, info: VideoInfo, progr
     finally:
         try:
             if release is not None:
-                release()
+                release()              # (a failed or cancelled run closes its encoder: nothing reads the frame buffers after this)
+        except Exception:
+            pass
+        try:
+            reader.close()             # page-locked frame buffers back to the pool -- only now, after the encoder has let go of them
         except Exception:
             pass
 

@@ -101,7 +101,10 @@ def test_convert_video_container_input_and_cancel(tmp_path):
     assert _psnr(dec[3][0], clip.frame(3)[0], 255) > 26       # tiny picture: the reference VBV clamp for this level binds hard
     ev = threading.Event()
     ev.set()
-    assert transcoder.convert_video(src, tmp_path, encoder='b200', device=0, stop_event=ev)['status'] == 'CANCELLED'
+    other = tmp_path / 'cancelled'
+    other.mkdir()
+    assert transcoder.convert_video(src, other, encoder='b200', device=0, stop_event=ev)['status'] == 'CANCELLED'
+    assert list(other.iterdir()) == []                      # a cancelled run leaves neither a partial MP4 nor a spool file
 
 
 def test_upscale_and_encode(tmp_path):
