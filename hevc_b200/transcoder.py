@@ -241,6 +241,30 @@ def _segment_pool_put(key, pse, reusable: bool):
     pse.close()
 
 
+def _shutdown_pools():
+    """close pooled encoders while the CUDA library is still loaded (interpreter exit)"""
+    global _ENCODER_POOL
+    with _ENCODER_POOL_LOCK:
+        pool, _ENCODER_POOL = _ENCODER_POOL, None
+        segs = [p for lst in _SEGMENT_POOL.values() for p in lst]
+        _SEGMENT_POOL.clear()
+    for pse in segs:
+        try:
+            pse.close()
+        except Exception:
+            pass
+    if pool is not None:
+        try:
+            pool.close()
+        except Exception:
+            pass
+
+
+import atexit  # noqa: E402
+
+atexit.register(_shutdown_pools)
+
+
 def encode_b200(file_path: Path, out_path: Path, info: VideoInfo, progress_callback: ProgressCb, total_frames: int,
                 stop_event: Optional[threading.Event], device: Optional[int] = None, batch: int = 32,
                 target_size: Optional[Tuple[int, int]] = None, streams: Optional[int] = None, force_main10: bool = False,
