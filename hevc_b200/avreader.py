@@ -1,0 +1,238 @@
+"""Container sources at their native bit depth: demux + decode through the FFmpeg libraries bundled with the OpenCV wheel
+(libavformat / libavcodec via ctypes), planar 4:2:0 out -- the decode step of the reference's ffmpeg child.
+
+``cv2.VideoCapture`` hands over 8-bit BGR: a Main10 / 10-bit source loses two bits and takes a YUV -> BGR -> YUV round trip.  This
+reader keeps the decoder's own samples (yuv420p -> HB_PIX_YUV420P8, yuv420p10le -> HB_PIX_YUV420P16 with 10 significant bits).
+Anything else (4:2:2, 4:4:4, RGB codecs, a library layout this module does not recognise) raises ``Unsupported`` and the caller
+falls back to the OpenCV reader.
+
+No FFmpeg headers are available, so only long-stable, documented structure heads are touched, each guarded by a sanity check:
+``AVFormatContext.nb_streams / .streams`` (offsets 44 / 48 since libavformat 58), ``AVStream.codecpar`` (offset 16 since
+libavformat 59, where ``av_class`` became the first member), ``AVPacket.stream_index`` (offset 36), and the head of ``AVFrame``
+(data, linesize, width, height, format).  Everything else goes through functions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+from pathlib import Path
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+
+AV_PIX_FMT_YUV420P, AV_PIX_FMT_YUVJ420P, AV_PIX_FMT_YUV420P10LE = 0, 12, 62
+_EAGAIN, _EOF = -11, -541478725
+
+
+class Unsupported(RuntimeError):
+    pass
+
+
+class _AVFrameHead(C.Structure):
+    _fields_ = [('data', C.c_void_p * 8), ('linesize', C.c_int * 8), ('extended_data', C.c_void_p),
+                ('width', C.c_int), ('height', C.c_int), ('nb_samples', C.c_int), ('format', C.c_int)]
+
+
+class _AVPacketHead(C.Structure):
+    _fields_ = [('buf', C.c_void_p), ('pts', C.c_int64), ('dts', C.c_int64), ('data', C.c_void_p), ('size', C.c_int),
+                ('stream_index', C.c_int)]
+
+
+_LIBS: dict = {}
+
+
+def _libdir() -> str:
+    import cv2
+    base = os.path.dirname(os.path.dirname(cv2.__file__))
+    for name in ('opencv_python_headless.libs', 'opencv_python.libs', 'opencv_contrib_python_headless.libs', 'opencv_contrib_python.libs'):
+        d = os.path.join(base, name)
+        if os.path.isdir(d):
+            return d
+    raise Unsupported('OpenCV-bundled FFmpeg libraries not found')
+
+
+def _lib(stem: str) -> C.CDLL:
+    if stem not in _LIBS:
+        d = _libdir()
+        for dep in {'avcodec': ('avutil', 'swresample'), 'avformat': ('avutil', 'swresample', 'avcodec'), 'swresample': ('avutil',)}.get(stem, ()):
+            _lib(dep)
+        hits = sorted(glob.glob(os.path.join(d, f'lib{stem}-*.so*')))
+        if not hits:
+            raise Unsupported(f'lib{stem} is not bundled')
+        _LIBS[stem] = C.CDLL(hits[0], mode=C.RTLD_GLOBAL)
+    return _LIBS[stem]
+
+
+class AvReader:
+    """Yields batches as (uint8 buffer in the hb_frames layout, n_frames, pix_fmt), like the readers in ``frames.py``."""
+
+    kind = 'yuv'
+
+    def __init__(self, path: Path):
+        from .encoder import PIX_YUV420P8, PIX_YUV420P16
+        self._fmt_ids = (PIX_YUV420P8, PIX_YUV420P16)
+        try:
+            self.avf, self.avc, self.avu = _lib('avformat'), _lib('avcodec'), _lib('avutil')
+        except OSError as exc:
+            raise Unsupported(str(exc))
+        f, a, u = self.avf, self.avc, self.avu
+        f.avformat_version.restype = C.c_uint
+        if (f.avformat_version() >> 16) < 59:
+            raise Unsupported('libavformat older than 59: AVStream layout differs')
+        f.avformat_open_input.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_void_p, C.c_void_p]
+        f.avformat_find_stream_info.argtypes = [C.c_void_p, C.c_void_p]
+        f.av_find_best_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int]
+        f.av_read_frame.argtypes = [C.c_void_p, C.c_void_p]
+        f.avformat_close_input.argtypes = [C.POINTER(C.c_void_p)]
+        a.avcodec_alloc_context3.restype = C.c_void_p
+        a.avcodec_alloc_context3.argtypes = [C.c_void_p]
+        a.avcodec_parameters_to_context.argtypes = [C.c_void_p, C.c_void_p]
+        a.avcodec_open2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        a.avcodec_free_context.argtypes = [C.POINTER(C.c_void_p)]
+        a.av_packet_alloc.restype = C.c_void_p
+        a.av_packet_free.argtypes = [C.POINTER(C.c_void_p)]
+        a.av_packet_unref.argtypes = [C.c_void_p]
+        a.avcodec_send_packet.argtypes = [C.c_void_p, C.c_void_p]
+        a.avcodec_receive_frame.argtypes = [C.c_void_p, C.c_void_p]
+        u.av_frame_alloc.restype = C.c_void_p
+        u.av_frame_free.argtypes = [C.POINTER(C.c_void_p)]
+        u.av_frame_unref.argtypes = [C.c_void_p]
+        u.av_opt_set.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        u.av_log_set_level.argtypes = [C.c_int]
+        u.av_log_set_level(16)
+        self.fmt = C.c_void_p()
+        self.ctx = C.c_void_p()
+        self.pkt = C.c_void_p()
+        self.frame = C.c_void_p()
+        self._ring = None
+        if f.avformat_open_input(C.byref(self.fmt), str(path).encode(), None, None) < 0:
+            self.fmt = C.c_void_p()
+            raise Unsupported(f'avformat cannot open {path}')
+        try:
+            if f.avformat_find_stream_info(self.fmt, None) < 0:
+                raise Unsupported('no stream info')
+            dec = C.c_void_p()
+            self.stream = f.av_find_best_stream(self.fmt, 0, -1, -1, C.byref(dec), 0)        # AVMEDIA_TYPE_VIDEO
+            if self.stream < 0 or not dec:
+                raise Unsupported('no decodable video stream')
+            nb = C.c_uint.from_address(self.fmt.value + 44).value
+            if not (0 < nb <= 256 and self.stream < nb):
+                raise Unsupported('unexpected AVFormatContext layout')
+            streams = C.c_void_p.from_address(self.fmt.value + 48).value
+            st = C.c_void_p.from_address(streams + 8 * self.stream).value
+            index = C.c_int.from_address(st + 8).value
+            codecpar = C.c_void_p.from_address(st + 16).value
+            if index != self.stream or not codecpar or C.c_int.from_address(codecpar).value != 0:      # codec_type == VIDEO
+                raise Unsupported('unexpected AVStream layout')
+            self.ctx = C.c_void_p(a.avcodec_alloc_context3(dec))
+            if a.avcodec_parameters_to_context(self.ctx, codecpar) < 0:
+                raise Unsupported('avcodec_parameters_to_context failed')
+            u.av_opt_set(self.ctx, b'threads', b'auto', 0)
+            if a.avcodec_open2(self.ctx, dec, None) < 0:
+                raise Unsupported('avcodec_open2 failed')
+            self.pkt = C.c_void_p(a.av_packet_alloc())
+            self.frame = C.c_void_p(u.av_frame_alloc())
+            self._eof = self._flushed = False
+            self._pending = self._next_frame()           # decode one frame now: geometry and pixel format
+            if self._pending is None:
+                raise Unsupported('no frames decoded')
+        except Exception:
+            self.close()
+            raise
+        self.width, self.height, bps = self._pending[1], self._pending[2], self._pending[3]
+        self.fmt_id = self._fmt_ids[0] if bps == 1 else self._fmt_ids[1]
+        self.src_bit_depth = 8 if bps == 1 else 10
+        self.pix_fmt = 'yuv420p' if bps == 1 else 'yuv420p10le'
+        self.frame_bytes = (self.width * self.height + 2 * (self.width // 2) * (self.height // 2)) * bps
+
+    # ---- one decoded frame as (packed planes uint8, width, height, bytes per sample), or None at the end of the stream
+    def _next_frame(self):
+        a, f, u = self.avc, self.avf, self.avu
+        while True:
+            rc = a.avcodec_receive_frame(self.ctx, self.frame)
+            if rc >= 0:
+                fr = _AVFrameHead.from_address(self.frame.value)
+                if fr.format in (AV_PIX_FMT_YUV420P, AV_PIX_FMT_YUVJ420P):
+                    bps = 1
+                elif fr.format == AV_PIX_FMT_YUV420P10LE:
+                    bps = 2
+                else:
+                    u.av_frame_unref(self.frame)
+                    raise Unsupported(f'pixel format {fr.format} is not planar 4:2:0 at 8 / 10 bits')
+                w, h = fr.width & ~1, fr.height & ~1
+                parts = []
+                for i, (pw, ph) in enumerate(((w, h), (w // 2, h // 2), (w // 2, h // 2))):
+                    ls = fr.linesize[i]
+                    raw = np.frombuffer((C.c_uint8 * (ls * ph)).from_address(fr.data[i]), dtype=np.uint8).reshape(ph, ls)
+                    parts.append(np.ascontiguousarray(raw[:, :pw * bps]).reshape(-1))
+                out = np.concatenate(parts)
+                u.av_frame_unref(self.frame)
+                return out, w, h, bps
+            if rc not in (_EAGAIN, _EOF):
+                raise Unsupported(f'avcodec_receive_frame -> {rc}')
+            if self._flushed:
+                return None
+            if self._eof:
+                a.avcodec_send_packet(self.ctx, None)
+                self._flushed = True
+                continue
+            rc = f.av_read_frame(self.fmt, self.pkt)
+            if rc < 0:
+                self._eof = True
+                continue
+            if _AVPacketHead.from_address(self.pkt.value).stream_index == self.stream:
+                a.avcodec_send_packet(self.ctx, self.pkt)
+            a.av_packet_unref(self.pkt)
+
+    def batches(self, batch: int, ring: int = 4) -> Iterator[Tuple[np.ndarray, int, int]]:
+        from .frames import _Ring
+        bufs = self._ring = _Ring(batch * self.frame_bytes, ring)
+        while True:
+            buf = bufs.next().reshape(batch, self.frame_bytes)
+            n = 0
+            while n < batch:
+                item, self._pending = (self._pending, None) if self._pending is not None else (self._next_frame(), None)
+                if item is None:
+                    break
+                if item[0].size != self.frame_bytes:
+                    raise Unsupported('geometry changes in mid-stream')
+                buf[n] = item[0]
+                n += 1
+            if n == 0:
+                return
+            yield buf[:n], n, self.fmt_id
+            if n < batch:
+                return
+
+    def close(self):
+        ring, self._ring = getattr(self, '_ring', None), None
+        if ring is not None:
+            ring.close()
+        if getattr(self, 'frame', None) and self.frame.value:
+            self.avu.av_frame_free(C.byref(self.frame))
+        if getattr(self, 'pkt', None) and self.pkt.value:
+            self.avc.av_packet_free(C.byref(self.pkt))
+        if getattr(self, 'ctx', None) and self.ctx.value:
+            self.avc.avcodec_free_context(C.byref(self.ctx))
+        if getattr(self, 'fmt', None) and self.fmt.value:
+            self.avf.avformat_close_input(C.byref(self.fmt))
+        self.frame = self.pkt = self.ctx = self.fmt = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decoded_format(path: Path) -> Optional[dict]:
+    """geometry and pixel format of the first decoded frame, or None when this reader cannot handle the file"""
+    try:
+        r = AvReader(path)
+    except Exception:
+        return None
+    try:
+        return {'width': r.width, 'height': r.height, 'pix_fmt': r.pix_fmt}
+    finally:
+        r.close()

@@ -165,7 +165,11 @@ def open_reader(path: Path, info: VideoInfo):
         return Y4MReader(path)
     if path.suffix.lower() in ('.yuv', '.raw'):
         return RawYuvReader(path, info)
-    return Cv2Reader(path)
+    try:                          # containers: the decoder's own 4:2:0 samples at their native depth when the bundled FFmpeg allows it
+        from .avreader import AvReader
+        return AvReader(path)
+    except Exception:
+        return Cv2Reader(path)    # 8-bit BGR through OpenCV (other chroma formats, RGB codecs, unknown library layout)
 
 
 def write_y4m(path: Path, frames, width: int, height: int, fps: Tuple[int, int] = (30, 1), ten_bit: bool = False):

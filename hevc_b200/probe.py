@@ -182,6 +182,84 @@ def _probe_cv2(path: Path) -> dict:
         cap.release()
 
 
+_PRIM_NAMES = {1: 'bt709', 5: 'bt470bg', 6: 'smpte170m', 9: 'bt2020'}
+_TRC_NAMES = {1: 'bt709', 6: 'smpte170m', 14: 'bt2020-10', 15: 'bt2020-12', 16: 'smpte2084', 18: 'arib-std-b67'}
+_SPC_NAMES = {1: 'bt709', 5: 'bt470bg', 6: 'smpte170m', 9: 'bt2020nc', 10: 'bt2020c'}
+
+
+def _probe_mp4_colour(path: Path) -> dict:
+    """colour description and HDR10 static metadata from an ISO-BMFF file's video sample entry: ``colr`` (nclx), ``mdcv``, ``clli``
+    -- what ffprobe reports as color_primaries / color_transfer / color_space and the mastering-display side data
+    (reference core/probe.py:47-111).  Only ``moov`` is read; returns {} for anything unexpected."""
+    import struct
+    out: dict = {}
+    containers = (b'moov', b'trak', b'mdia', b'minf', b'stbl')
+
+    def walk(buf: bytes, start: int, end: int, depth: int):
+        pos = start
+        while pos + 8 <= end:
+            size, kind = struct.unpack('>I4s', buf[pos:pos + 8])
+            hdr = 8
+            if size == 1:
+                size = struct.unpack('>Q', buf[pos + 8:pos + 16])[0]
+                hdr = 16
+            if size < hdr or pos + size > end:
+                return
+            if kind in containers:
+                walk(buf, pos + hdr, pos + size, depth + 1)
+            elif kind == b'stsd':
+                entry = pos + hdr + 8                                  # version/flags + entry_count
+                esize, etype = struct.unpack('>I4s', buf[entry:entry + 8])
+                if etype in (b'hvc1', b'hev1', b'avc1', b'avc3', b'av01', b'vp09', b'apch', b'apcn', b'ap4h') and esize >= 86:
+                    inner(buf, entry + 86, min(entry + esize, end))
+            pos += size
+
+    def inner(buf: bytes, pos: int, end: int):
+        while pos + 8 <= end:
+            size, kind = struct.unpack('>I4s', buf[pos:pos + 8])
+            if size < 8 or pos + size > end:
+                return
+            body = buf[pos + 8:pos + size]
+            if kind == b'colr' and body[:4] in (b'nclx', b'nclc') and len(body) >= 10:
+                p_, t_, m_ = struct.unpack('>HHH', body[4:10])
+                out['color_primaries'] = _PRIM_NAMES.get(p_, 'unknown')
+                out['color_transfer'] = _TRC_NAMES.get(t_, 'unknown')
+                out['color_space'] = _SPC_NAMES.get(m_, 'unknown')
+            elif kind == b'mdcv' and len(body) >= 24:
+                v = struct.unpack('>8HII', body[:24])
+                out['master_display'] = 'G(%d,%d)B(%d,%d)R(%d,%d)WP(%d,%d)L(%d,%d)' % v
+            elif kind == b'clli' and len(body) >= 4:
+                out['max_cll'] = '%d,%d' % struct.unpack('>HH', body[:4])
+            pos += size
+
+    try:
+        with open(path, 'rb') as fh:
+            fsize = path.stat().st_size
+            pos = 0
+            while pos + 8 <= fsize:
+                fh.seek(pos)
+                head = fh.read(16)
+                size, kind = struct.unpack('>I4s', head[:8])
+                hdr = 8
+                if size == 1:
+                    size = struct.unpack('>Q', head[8:16])[0]
+                    hdr = 16
+                elif size == 0:
+                    size = fsize - pos
+                if size < hdr:
+                    break
+                if kind == b'moov' and size <= (256 << 20):
+                    fh.seek(pos + hdr)
+                    buf = fh.read(size - hdr)
+                    walk(buf, 0, len(buf), 0)
+                    break
+                pos += size
+    except Exception:
+        logger.debug('mp4 colour probe failed for %s', path, exc_info=True)
+        return {}
+    return out
+
+
 def _sidecar(path: Path) -> dict:
     side = path.with_suffix(path.suffix + '.json')
     if side.exists():
@@ -201,6 +279,16 @@ def _probe_without_ffprobe(path: Path) -> VideoInfo:
             base = {}
         else:
             base = _probe_cv2(path)
+            # what OpenCV does not tell: the decoder's pixel format (bit depth) and the container's colour / HDR10 boxes
+            try:
+                from .avreader import decoded_format
+                fmt = decoded_format(path)
+                if fmt:
+                    base['pix_fmt'] = fmt['pix_fmt']
+            except Exception:
+                logger.debug('decoded-format probe failed', exc_info=True)
+            if path.suffix.lower() in ('.mp4', '.mov', '.m4v'):
+                base.update(_probe_mp4_colour(path))
     base.update({k: v for k, v in side.items() if v is not None})
     prim = str(base.get('color_primaries', 'bt709')).lower()
     trc = str(base.get('color_transfer', 'bt709')).lower()

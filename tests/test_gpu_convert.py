@@ -185,3 +185,22 @@ def test_convert_video_10bit_y4m(tmp_path, tagged_hdr):
     else:
         want = np.minimum((f10[2][0].astype(np.int32) + 2) >> 2, 255)
         assert _psnr(dec[2][0], want, 255) > 26 and int(dec[2][0].max()) <= 255
+
+
+def test_convert_video_main10_hdr10_container(tmp_path):
+    """a Main10 HDR10 MP4 in (made by the CPU model + muxer) -> convert_video(encoder='b200'): the source is decoded at 10 bits
+    through the bundled libavcodec (not 8-bit BGR), the prober picks the HDR10 boxes up, and the output is a compliant Main10
+    HDR10 hvc1 MP4 carrying the SAME mastering-display / content-light values, close to the 10-bit source"""
+    from tests.test_host_pipeline import _model_mp4
+    src, dec_src = _model_mp4(tmp_path, 10, w=256, h=144, n=8, name='hdr_in.mp4')
+    out_dir = tmp_path / 'out'
+    out_dir.mkdir()
+    res = transcoder.convert_video(src, out_dir, encoder='b200', device=0)
+    assert res['status'] == 'SUCCESS' and res['hdr'] is True and res['method'] == 'B200'
+    data = (out_dir / 'hdr_in.mp4').read_bytes()
+    expect = {'profile_idc': 2, 'tier': 0, 'hdr10': True, 'master_display': (13250, 34500, 7500, 3000, 34000, 16000, 15635, 16450, 10000000, 50),
+              'max_cll': 1000, 'max_fall': 400}
+    assert compliance.check_bytes(data, expect) == []
+    rep, dec = _decode_mp4(data)
+    assert len(dec) == 8 and rep['sps']['bit_depth'] == 10
+    assert _psnr(dec[3][0], dec_src[3][0], 1023) > 30          # against the 10-bit decoded source, full depth kept

@@ -409,3 +409,60 @@ def test_memory_reader_and_ring_buffers(tmp_path):
         for view, snap in held[-2:]:
             assert (view == snap).all()
     assert sum(len(v) for v, _ in held) == 5 and (np.concatenate([s for _, s in held]) == raw).all()
+
+
+def _model_mp4(tmp_path, depth, w=176, h=112, n=5, name='src.mp4'):
+    """an hvc1 MP4 written by the CPU model + the muxer; returns (path, decoded planes per frame)"""
+    from oracle import encoder_model as em
+    from oracle import fforacle
+    clip = SynthClip(w, h, seed=2)
+    enc = em.ModelEncoder(em.make_params(w, h, depth, qp_i=20, qp_p=22, keyint=10, hash_sei=False, hdr10=(depth == 10)))
+    es = b''.join(enc.encode(*[a.astype(np.uint16) << (depth - 8) for a in clip.frame(i)])[0] for i in range(n))
+    enc.close()
+    md = (13250, 34500, 7500, 3000, 34000, 16000, 15635, 16450, 10000000, 50)
+    hdr = depth == 10
+    track = mp4.TrackInfo(w, h, 30, 1, 2 if hdr else 1, 90, 0, depth, 9 if hdr else 1, 16 if hdr else 1, 9 if hdr else 1, 0, md if hdr else None, 1000, 400)
+    path = tmp_path / name
+    path.write_bytes(mp4.mux_annexb(track, es))
+    return path, fforacle.decode_hevc(es, verify_hash=False)
+
+
+@pytest.mark.parametrize('depth', [8, 10])
+def test_container_reader_keeps_native_depth_and_probe_reads_hdr10_boxes(tmp_path, depth):
+    """a11: container sources are demuxed + decoded through the bundled libavformat / libavcodec at their own bit depth (the
+    samples are exactly the decoder's), and the ffprobe-less prober reads the pixel format and the colr / mdcv / clli boxes --
+    a Main10 HDR10 MP4 is classified HDR with its mastering-display string, like ffprobe would report it (core/probe.py:47-111)"""
+    from hevc_b200.avreader import AvReader
+    from hevc_b200.frames import open_reader
+    path, dec = _model_mp4(tmp_path, depth)
+    info = probe.probe_media(path)
+    assert (info.width, info.height, info.nb_frames) == (176, 112, 5)
+    if depth == 10:
+        assert info.hdr and info.pix_fmt == 'yuv420p10le' and (info.color_primaries, info.color_transfer, info.color_space) == ('bt2020', 'smpte2084', 'bt2020nc')
+        assert info.master_display == 'G(13250,34500)B(7500,3000)R(34000,16000)WP(15635,16450)L(10000000,50)' and info.max_cll == '1000,400'
+    else:
+        assert not info.hdr and info.pix_fmt == 'yuv420p' and info.color_primaries == 'bt709'
+    r = open_reader(path, info)
+    assert isinstance(r, AvReader) and r.src_bit_depth == depth and r.kind == 'yuv'
+    got = []
+    for buf, k, fmt in r.batches(2):
+        got += [b.copy() for b in buf[:k]]
+    r.close()
+    assert len(got) == 5
+    for g, d in zip(got, dec):
+        want = np.concatenate([pl.astype('<u2' if depth == 10 else np.uint8).reshape(-1).view(np.uint8) for pl in d])
+        assert (g == want).all()
+
+
+def test_container_reader_falls_back_to_opencv_for_rgb_codecs(tmp_path):
+    import cv2
+
+    from hevc_b200.frames import Cv2Reader, open_reader
+    src = tmp_path / 'rgb.avi'
+    vw = cv2.VideoWriter(str(src), cv2.VideoWriter_fourcc(*'FFV1'), 25.0, (64, 48))
+    for i in range(3):
+        vw.write(np.full((48, 64, 3), 40 * i, np.uint8))
+    vw.release()
+    r = open_reader(src, probe.probe_media(src))
+    assert isinstance(r, Cv2Reader) and r.kind == 'bgr'
+    assert sum(n for _, n, _ in r.batches(2)) == 3
