@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import struct
 from pathlib import Path
-from typing import Dict, List, Optional
+from typing import Tuple, Dict, List, Optional
 
 from . import mp4
 
@@ -122,7 +122,39 @@ def parse_sps(nal: bytes) -> Dict[str, int]:
             if r.u(1):
                 r.ue()
             s['hrd'] = r.u(1)
+            if s['hrd']:
+                # hrd_parameters(1, 0) (E.2.2): only the NAL HRD of the single sub-layer is expected here
+                nal_hrd, vcl_hrd = r.u(1), r.u(1)
+                if nal_hrd or vcl_hrd:
+                    if r.u(1):                       # sub_pic_hrd_params_present_flag
+                        r.u(8); r.u(5); r.u(1); r.u(5)
+                    bit_rate_scale, cpb_size_scale = r.u(4), r.u(4)
+                    r.u(5); r.u(5); r.u(5)           # delay / output-delay lengths
+                fixed_general = r.u(1)
+                fixed_cvs = 1 if fixed_general else r.u(1)
+                if fixed_cvs:
+                    r.ue()                           # elemental_duration_in_tc_minus1
+                low_delay = 0 if fixed_cvs else r.u(1)
+                cpb_cnt = 0 if low_delay else r.ue()
+                if nal_hrd:
+                    for _ in range(cpb_cnt + 1):
+                        br, cpb = r.ue(), r.ue()
+                        s['hrd_cbr'] = r.u(1)
+                    s['hrd_bit_rate'] = (br + 1) << (6 + bit_rate_scale)
+                    s['hrd_cpb_size'] = (cpb + 1) << (4 + cpb_size_scale)
     return s
+
+
+def hrd_underflows(sample_bits: List[int], bit_rate: float, cpb_bits: float, fps: float, initial_fullness: float = 0.9) -> List[Tuple[int, float]]:
+    """Leaky-bucket check of the ACTUAL access-unit sizes against the HRD a stream signals (Annex C, VBR): the CPB fills at
+    ``bit_rate`` up to ``cpb_bits``, the first removal happens when it holds ``initial_fullness`` of its size (the
+    buffering-period SEI's initial_cpb_removal_delay), one access unit leaves per frame interval.  -> [(frame, missing bits)]"""
+    per, full, bad = bit_rate / fps, initial_fullness * cpb_bits, []
+    for i, bits in enumerate(sample_bits):
+        if bits > full + 1e-6:
+            bad.append((i, bits - full))
+        full = min(cpb_bits, max(0.0, full - bits) + per)
+    return bad
 
 
 def parse_sei(nal: bytes) -> Dict[int, bytes]:
@@ -251,6 +283,12 @@ def check_bytes(data: bytes, expect: Optional[Dict[str, int]] = None) -> List[st
             bad.append('hvcC profile/level differ from the SPS')
     else:
         bad.append('SPS not parsed')
+    if sps.get('hrd_bit_rate') and sps.get('num_units_in_tick') and rep.get('sample_sizes'):
+        # the stream signals an HRD (hrd=1, reference core/utils.py:65): its real sample sizes must not underflow that buffer
+        fps = sps['time_scale'] / sps['num_units_in_tick']
+        under = hrd_underflows([8 * n for n in rep['sample_sizes']], sps['hrd_bit_rate'], sps['hrd_cpb_size'], fps)
+        if under:
+            bad.append(f'HRD buffer underflow at sample {under[0][0]} ({int(under[0][1])} bits short; {len(under)} samples in all)')
     if rep.get('handler_name') != 'VideoHandler':
         bad.append('handler_name is not VideoHandler')
     if rep.get('sync_samples', [0])[0] != 1:

@@ -466,3 +466,27 @@ def test_container_reader_falls_back_to_opencv_for_rgb_codecs(tmp_path):
     r = open_reader(src, probe.probe_media(src))
     assert isinstance(r, Cv2Reader) and r.kind == 'bgr'
     assert sum(n for _, n, _ in r.batches(2)) == 3
+
+
+def test_compliance_checks_hrd_conformance_of_sample_sizes():
+    """the self-check parses the HRD the stream signals (hrd=1, core/utils.py:65) and runs the decoder-buffer model over the real
+    sample sizes: a rate-controlled stream passes, the same content coded far above the signalled rate is flagged"""
+    from oracle import encoder_model as em
+    w, h = 320, 192
+    clip = SynthClip(w, h, seed=7)
+    md = (13250, 34500, 7500, 3000, 34000, 16000, 15635, 16450, 10000000, 50)
+    track = mp4.TrackInfo(w, h, 30, 1, 2, 120, 0, 10, 9, 16, 9, 0, md, 1000, 400)
+
+    def stream(n, **kw):
+        enc = em.ModelEncoder(em.make_params(w, h, 10, keyint=12, hash_sei=False, hdr10=True, vbv_maxrate_kbps=250, vbv_bufsize_kbit=300, **kw))
+        es = b''.join(enc.encode(*[a.astype(np.uint16) << 2 for a in clip.frame(i)])[0] for i in range(n))
+        enc.close()
+        return mp4.mux_annexb(track, es)
+
+    good = stream(30, qp_i=20, qp_p=22, rate_control=1)
+    sps = compliance.inspect(good)['sps']
+    assert sps['hrd'] == 1 and abs(sps['hrd_bit_rate'] - 250000) < 64 and sps['hrd_cpb_size'] == 300000
+    assert compliance.check_bytes(good, {'hdr10': True}) == []
+    bad = compliance.check_bytes(stream(12, qp_i=12, qp_p=14, rate_control=0), {'hdr10': True})
+    assert len(bad) == 1 and bad[0].startswith('HRD buffer underflow')
+    assert compliance.hrd_underflows([100, 100, 5000, 100], 3000.0, 1000.0, 30.0) == [(2, 5000 - 900.0)]       # starts 90 % full, refills 100 / frame
