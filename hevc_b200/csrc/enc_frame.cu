@@ -604,9 +604,12 @@ __global__ void __launch_bounds__(128, 8) k_me(const __grid_constant__ InterPara
 #pragma unroll
         for (int k = 0; k < 8; k++) pv[k] = w[k * 40];
     }
-    bcost = satd_cols(st, pv, lane) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+    const int satd_int = satd_cols(st, pv, lane);
+    bcost = satd_int + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+    // a block the integer vector already predicts to within a quarter grey level per sample (static, clean content) has nothing
+    // to gain from sub-sample refinement: the search stops here (warp-uniform)
 #pragma unroll 1
-    for (int step = 2; step >= 1; step--) {
+    for (int step = satd_int > (64 << (bd - 8)) ? 2 : 0; step >= 1; step--) {
         const MV c2 = best;
         const int iy_min = (c2.y - step) >> 2;                    // the three rows of candidates start at integer row iy_min or iy_min + 1
         // lane t < 9 owns candidate (dx, dy) = (t / 3 - 1, t % 3 - 1): validity and vector cost once, in parallel

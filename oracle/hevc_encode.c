@@ -478,8 +478,11 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             /* sub-sample stages: SATD on the normative interpolation */
             pixel blk[256];
             predict_luma(e, &ref[0], x0, y0, best, blk);
-            bcost = orc_satd(src, ss, blk, 16, 16, 16) + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
-            for (int step = 2; step >= 1; step--) {
+            const long satd_int = orc_satd(src, ss, blk, 16, 16, 16);
+            bcost = satd_int + mv_cost(lambda, best.x, best.y, pred.x, pred.y);
+            /* a block the integer vector already predicts to within a quarter grey level per sample (static, clean content) has
+             * nothing to gain from sub-sample refinement: the search stops here */
+            for (int step = satd_int > (64 << (bd - 8)) ? 2 : 0; step >= 1; step--) {
                 const mv_t centre = best;
                 /* column by column: the three candidates of a column share their horizontal filter pass on the GPU */
                 for (int dx = -1; dx <= 1; dx++)
