@@ -59,45 +59,53 @@ __device__ __forceinline__ void stage_tile(SaoScratch &s, const pixel *plane, in
     }
 }
 
-// statistics of one component.  The 256 threads form four groups of 64 (two warps), one per edge class: a group walks all
-// samples of the N x N block (sample i = (tid & 63) + 64 j), classifies them for ITS class only and keeps the four categories'
-// counts and sums in registers (8 accumulators instead of 32: the kernel stays at 6 resident CTAs per SM); the band statistics
-// of a sample are taken by the group whose class number equals j mod 4, through warp-aggregated shared-memory atomics.
+// statistics of one component.  Every thread takes samples i = tid, tid + 256, ... of the N x N block and classifies each for
+// all four edge classes from the halo tile (the sample and its eight neighbours are read once).  Count and error sum of a
+// category share one accumulator, (count << 22) + sum: a thread sees at most 4 samples, a warp 128 (|sum| < 2^18), so the signed
+// sum never reaches bit 21 and the pair comes apart again after the warp reduction -- 16 accumulators instead of 32, which keeps
+// the kernel at 6 resident CTAs per SM.  Band statistics go through warp-aggregated shared-memory atomics.
 template <int N>
 __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel *src, int src_stride, int x0, int y0, int w, int h,
                                         int bshift, int tid)
 {
-    const int k = tid >> 6, lane64 = tid & 63, logn = N == 32 ? 5 : 4;
-    // neighbour pair of this group's class (oracle k_sao_dx / k_sao_dy): a = (dxa, dya), b = (-dxa, -dya)
-    const int dxa = k == 1 ? 0 : k == 3 ? 1 : -1, dya = k == 0 ? 0 : -1;
-    // count and error sum of a category share one accumulator: (count << 22) + sum.  A thread sees at most 16 samples (|sum| < 2^15), a
-    // warp 512 (|sum| < 2^20), so the signed sum never reaches bit 21 and the pair comes apart again after the warp reduction.
-    int acc[4] = {0, 0, 0, 0};
-    for (int j = 0; j < N * N / 64; j++) {
-        const int i = lane64 + 64 * j;
-        const int ly = i >> logn, lx = i & (N - 1), x = x0 + lx, y = y0 + ly;      // N is 32 or 16
+    constexpr int logn = N == 32 ? 5 : 4;
+    int acc[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[k][c] = 0;
+#pragma unroll 1
+    for (int i = tid; i < N * N; i += kSaoThreads) {
+        const int ly = i >> logn, lx = i & (N - 1), x = x0 + lx, y = y0 + ly;
         const bool inside = x < w && y < h;
         const int r = s.tile[ly + 1][lx + 1];
         const int d = inside ? (int)__ldg(src + (size_t)y * src_stride + x) - r : 0;
-        if ((j & 3) == k) {                  // band statistics: lanes with the same band pool their contribution
+        {   // band statistics: lanes with the same band pool their contribution
             const int band = inside ? r >> bshift : 32 + (tid & 31);      // lanes outside the picture form singleton groups and do nothing
             const unsigned grp = __match_any_sync(0xffffffffu, band);
             const int gs = __reduce_add_sync(grp, d), gc = __popc(grp);
             if (inside && (int)(__ffs(grp) - 1) == (tid & 31)) { atomicAdd(&st.bcnt[band], gc); atomicAdd(&st.bsum[band], gs); }
         }
-        const int xa = x + dxa, ya = y + dya, xb = x - dxa, yb = y - dya;
-        const bool ok = inside && xa >= 0 && xb >= 0 && ya >= 0 && yb >= 0 && xa < w && xb < w && ya < h && yb < h;
-        const int cat = ok ? sao_category(r, s.tile[ly + 1 + dya][lx + 1 + dxa], s.tile[ly + 1 - dya][lx + 1 - dxa]) : 0;
+        const bool l = x > 0, rr = x + 1 < w, u = y > 0, dn = y + 1 < h;
+        const bool okh = inside && l && rr, okv = inside && u && dn, okd = okh && okv;
+        const int cat[4] = {okh ? sao_category(r, s.tile[ly + 1][lx], s.tile[ly + 1][lx + 2]) : 0,
+                            okv ? sao_category(r, s.tile[ly][lx + 1], s.tile[ly + 2][lx + 1]) : 0,
+                            okd ? sao_category(r, s.tile[ly][lx], s.tile[ly + 2][lx + 2]) : 0,
+                            okd ? sao_category(r, s.tile[ly][lx + 2], s.tile[ly + 2][lx]) : 0};
         const int contrib = (1 << 22) + d;
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[c] += cat == c + 1 ? contrib : 0;
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[k][c] += cat[k] == c + 1 ? contrib : 0;
     }
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const int t = __reduce_add_sync(0xffffffffu, acc[c]);
-        const int ts = (int)((unsigned)t << 10) >> 10, tc = (t - ts) >> 22;
-        if ((tid & 31) == 0 && tc) { atomicAdd(&st.cnt[k][c], tc); atomicAdd(&st.sum[k][c], ts); }
-    }
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int t = __reduce_add_sync(0xffffffffu, acc[k][c]);
+            const int ts = (int)((unsigned)t << 10) >> 10, tc = (t - ts) >> 22;
+            if ((tid & 31) == 0 && tc) { atomicAdd(&st.cnt[k][c], tc); atomicAdd(&st.sum[k][c], ts); }
+        }
 }
 
 // final choice of one component group from the per-entry best costs (oracle sao_decide_group); comps = first component, count
