@@ -718,11 +718,12 @@ __global__ void __launch_bounds__(128, 7) k_inter(const __grid_constant__ InterP
         int bsatd, bcost;
         merge_decide(p, s, cx, cy, lambda, wx0, wy0, st, lane, best, bsatd, bcost);
         // Intra CU in a P frame (oracle/hevc_encode.c): the best intra prediction searched on source neighbours, plus its
-        // signalling, must beat the final inter choice by a quarter; the wavefront kernel then reconstructs the CU
+        // signalling, against 9/8 of the final inter choice (the SATD of the source-neighbour search understates what the
+        // reconstructed-neighbour prediction and its flatter residual save); the wavefront kernel then reconstructs the CU
         if (p.intra_best) {
             const int ibest = p.intra_best[cy * g.cuw + cx];
             const long long icost = (long long)ibest + ((lambda * 12) >> 8);
-            if (ibest != 0x7fffffff && icost * 4 < (long long)bcost * 3) {
+            if (ibest != 0x7fffffff && icost * 8 < (long long)bcost * 9) {
                 if (lane == 0) {
                     CuInfo ci;
                     ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0; ci.skip = 0; ci.mvx = 0; ci.mvy = 0;

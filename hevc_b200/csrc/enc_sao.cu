@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kSaoThreads, 6) k_sao_decide(SaoParams p)
     }
     const int qp = p.ctl->qp;
     const long long ly = (long long)(lambda_q8(qp) << (bd - 8)), lc = (long long)(lambda_q8(chroma_qp(qp)) << (bd - 8));
-    const long long lam_y = 2 * ly * ly, lam_c = 2 * lc * lc;
+    const long long lam_y = 3 * ly * ly, lam_c = 3 * lc * lc;
     if (tid < 144) {          // one (component, entry) per thread: entries 0..15 edge class x category, 16..47 bands
         const int comp = tid / 48, e = tid % 48;
         const long long lam = comp ? lam_c : lam_y;

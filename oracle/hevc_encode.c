@@ -555,9 +555,10 @@ static void encode_inter_frame(orc_encoder *e, int qp)
             }
     }
     /* Intra CUs in P frames: a CU goes intra when the best intra prediction (searched on source neighbours) plus its
-     * signalling beats the final inter choice by a quarter.  The margin covers what SATD does not see: the inter CU is
-     * usually skipped or merged (no residual, ~1 bit) while an intra CU always codes a mode and a residual, and the source
-     * neighbours flatter the intra prediction. */
+     * signalling costs less than 9/8 of the final inter choice.  Only CUs the gate in intra_search_all() passes are candidates
+     * -- inter residuals worth coding -- and for those the measured optimum sits past parity (BD-rate against the margin, 360p
+     * calibration clips: 3/4 -3.9 %, 1 -6.2 %, 9/8 -7.0 %, 5/4 -7.3 % with static scenes starting to lose): an intra residual
+     * after a good angular prediction is flatter and quantises cheaper than an inter residual of equal SATD. */
     if (e->prm.intra_in_p) intra_search_all(e, e->satdf[1], lambda);      /* [1] = output of the first merge-aware pass */
     const int16_t *mvfinal = e->mvf[MERGE_PASSES & 1];
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
@@ -577,7 +578,7 @@ static void encode_inter_frame(orc_encoder *e, int qp)
                 long ibest = e->mode_cost[idx * 35];
                 for (int m = 1; m < 35 && ibest >= 0; m++) if (e->mode_cost[idx * 35 + m] < ibest) ibest = e->mode_cost[idx * 35 + m];
                 const long icost = ibest + ((lambda * 12) >> 8);
-                if (ibest >= 0 && icost * 4 < (long)e->costf[idx] * 3) {
+                if (ibest >= 0 && icost * 8 < (long)e->costf[idx] * 9) {
                     cu->pred_mode = 0; cu->mvx = cu->mvy = 0; cu->cbf = 0;     /* reconstructed by the wavefront stage below */
                     continue;
                 }
@@ -820,9 +821,10 @@ static void sao_apply_ctb(const orc_encoder *e, const plane *in, plane *out, int
         }
 }
 
-/* decide (per CTU, independently: one launch on the GPU) and apply: `pre` (deblocked) -> rec[cur].  The Lagrangian is twice
- * the squared SATD-domain lambda: the rest of this encoder decides without RDO, and at lambda^2 SAO bought its PSNR at a worse
- * rate than a QP change does (BD-rate +1..+3 % on the calibration clips; -1.4 / -2.1 % at 2 lambda^2). */
+/* decide (per CTU, independently: one launch on the GPU) and apply: `pre` (deblocked) -> rec[cur].  The Lagrangian is three
+ * times the squared SATD-domain lambda: the rest of this encoder decides without RDO, and at lambda^2 SAO bought its PSNR at a
+ * worse rate than a QP change does (BD-rate +1..+3 % on the calibration clips; 2 lambda^2 and 3 lambda^2 are within 0.4 % of
+ * each other on moving content, 3 lambda^2 halves the cost on static scenes; tools/model_rd.py). */
 static void sao_frame(orc_encoder *e, int qp)
 {
     const int bd = e->prm.bit_depth, cmax = (1 << ((bd < 10 ? bd : 10) - 5)) - 1;
@@ -844,10 +846,10 @@ static void sao_frame(orc_encoder *e, int qp)
             if (copied) continue;
         }
         sao_collect(e, &e->pre[0], &e->src[0], 32, rx, ry, &st[0]);
-        sao_decide_group(st, 1, 2 * ly * ly, cmax, s, 0);
+        sao_decide_group(st, 1, 3 * ly * ly, cmax, s, 0);
         sao_collect(e, &e->pre[1], &e->src[1], 16, rx, ry, &st[0]);
         sao_collect(e, &e->pre[2], &e->src[2], 16, rx, ry, &st[1]);
-        sao_decide_group(st, 2, 2 * lc * lc, cmax, s, 1);
+        sao_decide_group(st, 2, 3 * lc * lc, cmax, s, 1);
     }
 #pragma omp parallel for schedule(dynamic, 4)
     for (int ctu = 0; ctu < e->ctuw * e->ctuh; ctu++) {
