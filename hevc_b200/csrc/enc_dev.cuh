@@ -109,6 +109,7 @@ struct RcState {
     int qp_i, qp_p, rate_control, bit_depth;
     // frame-type state: key frames every `keyint` frames, earlier at a detected scene cut once `min_keyint` frames have passed
     int keyint, min_keyint, scenecut, poc, started;
+    int cascade;              // hb_enc_params.qp_cascade
 };
 
 // scene-cut measures of one frame, accumulated by the coarse motion search (oracle/hevc_encode.c coarse_search / scene_cut)
@@ -155,35 +156,44 @@ HB_HD long long rc_budget(const RcState &rc, int is_idr)
     return budget;
 }
 
-HB_HD int rc_pick_qp(const RcState &rc, int is_idr)
+// QP cascade over P frames (oracle/hevc_rc.c k_cascade): the anchor (poc % 4 == 0) at the P-frame QP, +4 / +2 / +4 between anchors
+HB_HD int rc_cascade(const RcState &rc, int is_idr, int poc) { return !is_idr && rc.cascade ? (0x4240 >> (4 * (poc & 3))) & 15 : 0; }
+
+// `poc` = frames since the last IDR of the frame being decided; qp_prev / est_prev are kept in anchor terms (oracle orc_rc_pick_qp)
+HB_HD int rc_pick_qp(const RcState &rc, int is_idr, int poc)
 {
-    const int base = is_idr ? rc.qp_i : rc.qp_p;
+    const int off = rc_cascade(rc, is_idr, poc);
+    int base = (is_idr ? rc.qp_i : rc.qp_p) + off;
+    if (base > 51) base = 51;
     if (!rc.rate_control) return base;
     const long long budget = rc_budget(rc, is_idr);
     const int t = is_idr ? 1 : 0;
     int qp = base;
     if (rc.have[t]) {
-        int step = rc_step(rc.est_prev[t], budget);
-        if (step < 0) step = rc.est_prev[t] * 5 <= budget * 4 ? -1 : 0;
-        qp = rc.qp_prev[t] + step;
+        const long long est = rc.est_prev[t] * 65536 / rc_pow2_sixth(off);
+        int step = rc_step(est, budget);
+        if (step < 0) step = est * 5 <= budget * 4 ? -1 : 0;
+        qp = rc.qp_prev[t] + step + off;
     } else if (!is_idr && rc.have[1]) {
-        int step = rc_step(rc.est_prev[1] / 4, budget);
+        int step = rc_step(rc.est_prev[1] / 4 * 65536 / rc_pow2_sixth(off), budget);
         if (step < 0) step = 0;
-        qp = rc.qp_prev[1] + (rc.qp_p - rc.qp_i) + step;
+        qp = rc.qp_prev[1] + (rc.qp_p - rc.qp_i) + step + off;
     }
     return qp < base ? base : qp > 51 ? 51 : qp;
 }
 
-HB_HD void rc_update(RcState &rc, int is_idr, int qp, long long est16)
+// `poc` = that of the frame just coded
+HB_HD void rc_update(RcState &rc, int is_idr, int qp, long long est16, int poc)
 {
     const int t = is_idr ? 1 : 0;
+    const int off = rc_cascade(rc, is_idr, poc);
     rc.fullness += rc.t16;
     if (rc.fullness > rc.b16) rc.fullness = rc.b16;
     rc.fullness -= est16;
     if (rc.fullness < 0) rc.fullness = 0;
     rc.have[t] = 1;
-    rc.qp_prev[t] = qp;
-    rc.est_prev[t] = est16;
+    rc.qp_prev[t] = qp - off;
+    rc.est_prev[t] = est16 * rc_pow2_sixth(off) / 65536;
 }
 
 HB_HD void ctl_set_qp(FrameCtl &c, int qp, int is_idr, int bit_depth)

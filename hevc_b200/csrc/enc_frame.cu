@@ -1400,7 +1400,7 @@ __global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int force
 {
     if (threadIdx.x || blockIdx.x) return;
     RcState s = *rc;
-    if (done) rc_update(s, done->is_idr, done->qp, (long long)done->est16);
+    if (done) rc_update(s, done->is_idr, done->qp, (long long)done->est16, done->poc);
     if (next) {
         // frame type (oracle/hevc_encode.c orc_enc_frame): forced / first frame / keyint reached / scene cut past min-keyint
         const int cut = s.started && s.scenecut && scene && scene_cut(*scene, ds_samples) && s.poc + 1 >= s.min_keyint;
@@ -1408,7 +1408,7 @@ __global__ void k_rc_step(RcState *rc, FrameCtl *done, FrameCtl *next, int force
         s.poc = idr ? 0 : s.poc + 1;
         s.started = 1;
         FrameCtl c;
-        ctl_set_qp(c, rc_pick_qp(s, idr), idr, s.bit_depth);
+        ctl_set_qp(c, rc_pick_qp(s, idr, s.poc), idr, s.bit_depth);
         c.redo = 0; c.poc = s.poc; c.scene_cut = cut;
         *next = c;
     }

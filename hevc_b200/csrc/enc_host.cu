@@ -350,6 +350,7 @@ RcState initial_rc(const hb_enc_params &p)
     rc.fullness = rc.b16 * 9 / 10;
     rc.qp_i = p.qp_i; rc.qp_p = p.qp_p; rc.rate_control = p.rate_control; rc.bit_depth = p.bit_depth;
     rc.keyint = p.keyint; rc.min_keyint = p.min_keyint; rc.scenecut = p.scenecut; rc.poc = 0; rc.started = 0;
+    rc.cascade = p.qp_cascade;
     return rc;
 }
 
@@ -1063,9 +1064,11 @@ int hb_rc_simulate(const hb_enc_params *params, const long long *est16, const in
     const hb_enc_params &p = *params;
     if (p.fps_num <= 0 || p.fps_den <= 0) return HB_ERR_ARG;
     RcState rc = initial_rc(p);       // exactly the state hb_enc_create uploads, stepped by the functions the device kernels run
+    int poc = 0;
     for (int i = 0; i < n; i++) {
-        qps[i] = rc_pick_qp(rc, is_idr[i] != 0);
-        rc_update(rc, is_idr[i] != 0, qps[i], est16[i]);
+        poc = is_idr[i] ? 0 : poc + 1;
+        qps[i] = rc_pick_qp(rc, is_idr[i] != 0, poc);
+        rc_update(rc, is_idr[i] != 0, qps[i], est16[i], poc);
     }
     return HB_OK;
 }

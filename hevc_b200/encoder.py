@@ -24,7 +24,7 @@ class HbEncParams(C.Structure):
         'chroma_loc', 'full_range', 'aud', 'repeat_headers', 'hrd', 'hdr10')] + [
         ('master_display', C.c_uint32 * 10), ('max_cll', C.c_int), ('max_fall', C.c_int), ('hash_sei', C.c_int),
         ('keep_recon', C.c_int), ('rate_control', C.c_int), ('deblock', C.c_int), ('scenecut', C.c_int), ('intra_in_p', C.c_int),
-        ('sao', C.c_int), ('reserved', C.c_int * 4)]
+        ('sao', C.c_int), ('qp_cascade', C.c_int), ('reserved', C.c_int * 3)]
 
 
 class HbFrames(C.Structure):
@@ -48,7 +48,7 @@ def crf_to_qp(crf: int) -> Tuple[int, int]:
 
 def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: bool = False, keep_recon: bool = False,
                 rate_control: bool = True, deblock: bool = True, scenecut: bool = True, intra_in_p: bool = True,
-                sao: bool = True) -> HbEncParams:
+                sao: bool = True, qp_cascade: bool = True) -> HbEncParams:
     c = HbEncParams()
     qp_i, qp_p = qp if qp is not None else crf_to_qp(p.crf)
     for name in ('width', 'height', 'fps_num', 'fps_den', 'bit_depth', 'profile_idc', 'level_idc', 'tier', 'keyint', 'min_keyint',
@@ -65,6 +65,7 @@ def to_c_params(p: B200Params, qp: Optional[Tuple[int, int]] = None, hash_sei: b
     c.rate_control = int(rate_control)
     c.deblock = int(deblock)          # libx265 runs with the in-loop deblocking filter on unless told otherwise
     c.scenecut, c.intra_in_p, c.sao = int(scenecut), int(intra_in_p), int(sao)      # likewise on in libx265 (scenecut=40, sao)
+    c.qp_cascade = int(qp_cascade)    # P-frame QP cascade, in place of x265's P / B quantiser ratio (pbratio)
     return c
 
 

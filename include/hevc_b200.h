@@ -155,7 +155,9 @@ typedef struct hb_enc_params {
                                         * min-keyint= from core/transcoder.py:405) */
     int intra_in_p;                    /* intra CUs in P frames */
     int sao;                           /* sample adaptive offset (x265 default: on) */
-    int reserved[4];
+    int qp_cascade;                    /* P-frame QP cascade: qp_p applies to every fourth P frame (poc % 4 == 0), +4 / +2 / +4 between.
+                                          In place of the P / B QP ratio of x265 (pbratio): no B frames here */
+    int reserved[3];
 } hb_enc_params;
 
 typedef enum hb_pix_fmt {

@@ -15,7 +15,7 @@ class EncParams(C.Structure):
         'colour_primaries', 'transfer_characteristics', 'matrix_coeffs', 'vui_colour', 'chroma_loc', 'full_range',
         'aud', 'repeat_headers', 'hrd', 'hdr10', 'vbv_maxrate_kbps', 'vbv_bufsize_kbit')] + [
         ('master_display', C.c_uint32 * 10), ('max_cll', C.c_int), ('max_fall', C.c_int), ('hash_sei', C.c_int), ('deblock', C.c_int), ('rate_control', C.c_int),
-        ('min_keyint', C.c_int), ('scenecut', C.c_int), ('intra_in_p', C.c_int), ('sao', C.c_int)]
+        ('min_keyint', C.c_int), ('scenecut', C.c_int), ('intra_in_p', C.c_int), ('sao', C.c_int), ('qp_cascade', C.c_int)]
 
 
 class FrameInfo(C.Structure):
@@ -45,7 +45,7 @@ def make_params(width, height, bit_depth=8, qp_i=24, qp_p=26, keyint=60, fps=(30
     p.deblock = int(kw.get('deblock', 1))
     p.rate_control = int(kw.get('rate_control', 0))
     p.min_keyint = int(kw.get('min_keyint', max(2, keyint // 2)))
-    p.scenecut, p.intra_in_p, p.sao = (int(kw.get(k, 1)) for k in ('scenecut', 'intra_in_p', 'sao'))
+    p.scenecut, p.intra_in_p, p.sao, p.qp_cascade = (int(kw.get(k, 1)) for k in ('scenecut', 'intra_in_p', 'sao', 'qp_cascade'))
     for k in ('aud', 'repeat_headers', 'hrd'):
         if k in kw:
             setattr(p, k, int(kw[k]))

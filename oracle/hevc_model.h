@@ -36,6 +36,7 @@ typedef struct orc_enc_params {
     int scenecut;                 /* scene-cut detection: key frame at a detected cut (x265 default: on) */
     int intra_in_p;               /* intra CUs in P frames */
     int sao;                      /* sample adaptive offset */
+    int qp_cascade;               /* P-frame QP cascade (hevc_rc.c): qp_p applies to every fourth P frame, +4 / +2 / +4 between */
 } orc_enc_params;
 
 /* per-CU side information, also the interface between the decide/reconstruct stage and the entropy stage */
@@ -138,6 +139,8 @@ typedef struct orc_rc {
     long long fullness;           /* bits*16 currently in the decoder buffer model */
     int have[2], qp_prev[2];      /* [0] P frames, [1] IDR frames */
     long long est_prev[2];
+    int poc;                      /* frames since the last IDR, of the frame last passed to orc_rc_update */
+    int cascade;                  /* orc_enc_params.qp_cascade */
 } orc_rc;
 void orc_rc_init(orc_rc *rc, const orc_enc_params *p);
 int orc_rc_pick_qp(const orc_rc *rc, const orc_enc_params *p, int is_idr);

@@ -16,8 +16,17 @@ static const unsigned k_pow2_sixth[37] = {65536, 73562, 82570, 92682, 104032, 11
                                           1176987, 1321123, 1482910, 1664511, 1868350, 2097152, 2353974, 2642246, 2965821, 3329021, 3736700,
                                           4194304};
 
+/* QP cascade over P frames: every fourth P frame (poc % 4 == 0) is the anchor and is coded at the P-frame QP, the three between
+ * anchors at +4 / +2 / +4.  One reference picture and no B frames leave this as the way to spend bits where they are inherited:
+ * the anchors refresh the quality that the skipped and merged CUs of the following frames copy (the role the P / B QP ratio
+ * plays in x265, pbratio).  Offsets are >= 0 and the anchor's is 0, so the controller's state stays in anchor terms. */
+static const int8_t k_cascade[4] = {0, 4, 2, 4};
+int orc_rc_cascade(const orc_rc *rc, int is_idr, int poc) { return !is_idr && rc->cascade ? k_cascade[poc & 3] : 0; }
+
 void orc_rc_init(orc_rc *rc, const orc_enc_params *p)
 {
+    rc->poc = 0;
+    rc->cascade = p->qp_cascade;
     rc->t16 = (long long)p->vbv_maxrate_kbps * 1000 * 16 * p->fps_den / p->fps_num;
     rc->b16 = (long long)p->vbv_bufsize_kbit * 1000 * 16;
     rc->fullness = rc->b16 * 9 / 10;
@@ -58,23 +67,28 @@ long long orc_rc_budget(const orc_rc *rc, int is_idr)
     return budget;
 }
 
+/* QP of the next frame.  qp_prev / est_prev are kept in anchor terms (cascade offset removed, size scaled up by 2^(offset / 6)),
+ * so the size expected of this frame is the remembered one scaled down by its own offset. */
 int orc_rc_pick_qp(const orc_rc *rc, const orc_enc_params *p, int is_idr)
 {
-    const int base = is_idr ? p->qp_i : p->qp_p;
+    const int off = orc_rc_cascade(rc, is_idr, is_idr ? 0 : rc->poc + 1);
+    int base = (is_idr ? p->qp_i : p->qp_p) + off;
+    if (base > 51) base = 51;
     if (!p->rate_control) return base;
     const long long budget = orc_rc_budget(rc, is_idr);
     const int t = is_idr ? 1 : 0;
     int qp = base;
     if (rc->have[t]) {
-        int step = orc_rc_step(rc->est_prev[t], budget);
+        const long long est = rc->est_prev[t] * 65536 / k_pow2_sixth[off];
+        int step = orc_rc_step(est, budget);
         if (step < 0)                                  /* come down one step at a time and only with 25 % headroom */
-            step = rc->est_prev[t] * 5 <= budget * 4 ? -1 : 0;
-        qp = rc->qp_prev[t] + step;
+            step = est * 5 <= budget * 4 ? -1 : 0;
+        qp = rc->qp_prev[t] + step + off;
     } else if (!is_idr && rc->have[1]) {
         /* first P frame: start from the IDR's operating point (P frames are ~1/4 of an IDR at the same QP) */
-        int step = orc_rc_step(rc->est_prev[1] / 4, budget);
+        int step = orc_rc_step(rc->est_prev[1] / 4 * 65536 / k_pow2_sixth[off], budget);
         if (step < 0) step = 0;
-        qp = rc->qp_prev[1] + (p->qp_p - p->qp_i) + step;
+        qp = rc->qp_prev[1] + (p->qp_p - p->qp_i) + step + off;
     }
     if (qp < base) qp = base;
     if (qp > 51) qp = 51;
@@ -84,13 +98,15 @@ int orc_rc_pick_qp(const orc_rc *rc, const orc_enc_params *p, int is_idr)
 void orc_rc_update(orc_rc *rc, int is_idr, int qp, long long est16)
 {
     const int t = is_idr ? 1 : 0;
+    rc->poc = is_idr ? 0 : rc->poc + 1;
+    const int off = orc_rc_cascade(rc, is_idr, rc->poc);
     rc->fullness += rc->t16;
     if (rc->fullness > rc->b16) rc->fullness = rc->b16;
     rc->fullness -= est16;
     if (rc->fullness < 0) rc->fullness = 0;
     rc->have[t] = 1;
-    rc->qp_prev[t] = qp;
-    rc->est_prev[t] = est16;
+    rc->qp_prev[t] = qp - off;
+    rc->est_prev[t] = est16 * k_pow2_sixth[off] / 65536;
 }
 
 long long orc_rc_cu_estimate(const int16_t *coef, int cbf)

@@ -20,9 +20,9 @@ def b200_params(w, h, depth, keyint=4, hdr10=None):
 
 
 def model_params(p: B200Params, qp_i, qp_p, hash_sei, rate_control=False, deblock=True, **tools):
-    """``tools``: scenecut / intra_in_p / sao overrides (defaults = hevc_b200.encoder.to_c_params's)"""
+    """``tools``: scenecut / intra_in_p / sao / qp_cascade overrides (defaults = hevc_b200.encoder.to_c_params's)"""
     from oracle import encoder_model as em
-    t = {'scenecut': 1, 'intra_in_p': 1, 'sao': 1}
+    t = {'scenecut': 1, 'intra_in_p': 1, 'sao': 1, 'qp_cascade': 1}
     t.update({k: int(v) for k, v in tools.items()})
     m = em.make_params(p.width, p.height, p.bit_depth, qp_i=qp_i, qp_p=qp_p, keyint=p.keyint, fps=(p.fps_num, p.fps_den),
                        hdr10=bool(p.hdr10), hash_sei=hash_sei, level_idc=p.level_idc, tier=p.tier, min_keyint=p.min_keyint,

@@ -120,7 +120,7 @@ def test_host_rate_controller_matches_oracle(seed):
 
     class OrcRc(C.Structure):
         _fields_ = [('t16', C.c_longlong), ('b16', C.c_longlong), ('fullness', C.c_longlong), ('have', C.c_int * 2), ('qp_prev', C.c_int * 2),
-                    ('est_prev', C.c_longlong * 2)]
+                    ('est_prev', C.c_longlong * 2), ('poc', C.c_int), ('cascade', C.c_int)]
     rc = OrcRc()
     O.orc_rc_init(C.byref(rc), C.byref(mp))
     O.orc_rc_pick_qp.restype = C.c_int

@@ -18,15 +18,15 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 TOOLSETS = {           # name -> model parameter overrides
-    'r1': dict(scenecut=0, intra_in_p=0, sao=0),         # the round-1 tool set
-    'intra': dict(scenecut=0, intra_in_p=1, sao=0),
-    'cut': dict(scenecut=1, intra_in_p=1, sao=0),
-    'sao': dict(scenecut=1, intra_in_p=1, sao=1),
-    'r2': dict(scenecut=1, intra_in_p=1, sao=1),         # everything this round added
+    'r1': dict(scenecut=0, intra_in_p=0, sao=0, qp_cascade=0),         # the round-1 tool set
+    'intra': dict(scenecut=0, intra_in_p=1, sao=0, qp_cascade=0),
+    'cut': dict(scenecut=1, intra_in_p=1, sao=0, qp_cascade=0),
+    'sao': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0),
+    'r2': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=1),         # everything this round added
     # experiments: P-frame QP offset against the key frame (default +2)
-    'r2_p1': dict(scenecut=1, intra_in_p=1, sao=1, qp_p_offset=1),
-    'r2_p3': dict(scenecut=1, intra_in_p=1, sao=1, qp_p_offset=3),
-    'r2_p4': dict(scenecut=1, intra_in_p=1, sao=1, qp_p_offset=4),
+    'r2_p1': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0, qp_p_offset=1),
+    'r2_p3': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0, qp_p_offset=3),
+    'r2_p4': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0, qp_p_offset=4),
 }
 
 
