@@ -56,7 +56,7 @@ def workload_config(args, params, n_gpus):
             'keyint': params.keyint, 'min_keyint': params.min_keyint, 'crf': params.crf,
             'vbv_maxrate_kbps': params.vbv_maxrate_kbps, 'vbv_bufsize_kbit': params.vbv_bufsize_kbit,
             'level_idc': params.level_idc,
-            'coding_tools': 'CTU32/CU16, 35-mode intra, intra CUs in P frames, quarter-sample ME + merge, scene-cut key frames, deblocking, SAO, WPP CABAC',
+            'coding_tools': 'CTU32/CU16, 35-mode intra, intra CUs in P frames, quarter-sample ME + merge, scene-cut key frames, P-frame QP cascade, deblocking, SAO, WPP CABAC',
             'rate_control': 'crf quality ceiling (qp_i, qp_p) = %s, VBV-constrained on the device (vbv-maxrate / vbv-bufsize)' % (str(args.qp),),
             'parallelism': ('%d GPU(s), one process each; per GPU %d independent encoder stream(s) fed with closed-GOP segments of %d frames '
                             '(the reference\'s N-worker model applied to one device), no collective on the data path'
