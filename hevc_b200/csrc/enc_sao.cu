@@ -64,7 +64,8 @@ __device__ __forceinline__ void stage_tile(SaoScratch &s, const pixel *plane, in
 // category share one accumulator, (count << 22) + sum: a thread sees at most 4 samples, a warp 128 (|sum| < 2^18), so the signed
 // sum never reaches bit 21 and the pair comes apart again after the warp reduction -- 16 accumulators instead of 32, which keeps
 // the kernel at 6 resident CTAs per SM.  Band statistics go through warp-aggregated shared-memory atomics.
-template <int N>
+// EDGE = false: the block and its halo lie inside the picture, every picture-border test folds away.
+template <int N, bool EDGE>
 __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel *src, int src_stride, int x0, int y0, int w, int h,
                                         int bshift, int tid)
 {
@@ -77,7 +78,7 @@ __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel
 #pragma unroll 1
     for (int i = tid; i < N * N; i += kSaoThreads) {
         const int ly = i >> logn, lx = i & (N - 1), x = x0 + lx, y = y0 + ly;
-        const bool inside = x < w && y < h;
+        const bool inside = !EDGE || (x < w && y < h);
         const int r = s.tile[ly + 1][lx + 1];
         const int d = inside ? (int)__ldg(src + (size_t)y * src_stride + x) - r : 0;
         {   // band statistics: lanes with the same band pool their contribution
@@ -86,7 +87,7 @@ __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel
             const int gs = __reduce_add_sync(grp, d), gc = __popc(grp);
             if (inside && (int)(__ffs(grp) - 1) == (tid & 31)) { atomicAdd(&st.bcnt[band], gc); atomicAdd(&st.bsum[band], gs); }
         }
-        const bool l = x > 0, rr = x + 1 < w, u = y > 0, dn = y + 1 < h;
+        const bool l = !EDGE || x > 0, rr = !EDGE || x + 1 < w, u = !EDGE || y > 0, dn = !EDGE || y + 1 < h;
         const bool okh = inside && l && rr, okv = inside && u && dn, okd = okh && okv;
         const int cat[4] = {okh ? sao_category(r, s.tile[ly + 1][lx], s.tile[ly + 1][lx + 2]) : 0,
                             okv ? sao_category(r, s.tile[ly][lx + 1], s.tile[ly + 2][lx + 1]) : 0,
@@ -98,14 +99,19 @@ __device__ __forceinline__ void collect(SaoScratch &s, SaoStats &st, const pixel
 #pragma unroll
             for (int c = 0; c < 4; c++) acc[k][c] += cat[k] == c + 1 ? contrib : 0;
     }
+    // warp totals: lane k * 4 + c keeps accumulator (k, c), so the unpacking and the shared-memory atomics run once, 16 lanes wide
+    int mine = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int t = __reduce_add_sync(0xffffffffu, acc[k][c]);
-            const int ts = (int)((unsigned)t << 10) >> 10, tc = (t - ts) >> 22;
-            if ((tid & 31) == 0 && tc) { atomicAdd(&st.cnt[k][c], tc); atomicAdd(&st.sum[k][c], ts); }
+            if ((tid & 31) == k * 4 + c) mine = t;
         }
+    if ((tid & 31) < 16) {
+        const int ts = (int)((unsigned)mine << 10) >> 10, tc = (mine - ts) >> 22;
+        if (tc) { atomicAdd(&st.cnt[0][tid & 15], tc); atomicAdd(&st.sum[0][tid & 15], ts); }
+    }
 }
 
 // final choice of one component group from the per-entry best costs (oracle sao_decide_group); comps = first component, count
@@ -174,8 +180,14 @@ __global__ void __launch_bounds__(kSaoThreads, 6) k_sao_decide(SaoParams p)
         if (comp == 0) stage_tile<32>(s, pre, g.rec_stride, rx * N, ry * N, w, h, tid);
         else stage_tile<16>(s, pre, g.recc_stride, rx * N, ry * N, w, h, tid);
         __syncthreads();
-        if (comp == 0) collect<32>(s, s.st[comp], src, g.src_stride, rx * N, ry * N, w, h, bshift, tid);
-        else collect<16>(s, s.st[comp], src, g.srcc_stride, rx * N, ry * N, w, h, bshift, tid);
+        const bool edge = rx == 0 || ry == 0 || (rx + 1) * N >= w || (ry + 1) * N >= h;
+        if (comp == 0) {
+            if (edge) collect<32, true>(s, s.st[comp], src, g.src_stride, rx * N, ry * N, w, h, bshift, tid);
+            else collect<32, false>(s, s.st[comp], src, g.src_stride, rx * N, ry * N, w, h, bshift, tid);
+        } else {
+            if (edge) collect<16, true>(s, s.st[comp], src, g.srcc_stride, rx * N, ry * N, w, h, bshift, tid);
+            else collect<16, false>(s, s.st[comp], src, g.srcc_stride, rx * N, ry * N, w, h, bshift, tid);
+        }
         __syncthreads();
     }
     const int qp = p.ctl->qp;

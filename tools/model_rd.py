@@ -23,6 +23,8 @@ TOOLSETS = {           # name -> model parameter overrides
     'cut': dict(scenecut=1, intra_in_p=1, sao=0, qp_cascade=0),
     'sao': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0),
     'r2': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=1),         # everything this round added
+    'r2_c3': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=1, qp_p_offset=3),     # cascade with the anchors 3 / 4 above the key frame
+    'r2_c4': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=1, qp_p_offset=4),
     # experiments: P-frame QP offset against the key frame (default +2)
     'r2_p1': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0, qp_p_offset=1),
     'r2_p3': dict(scenecut=1, intra_in_p=1, sao=1, qp_cascade=0, qp_p_offset=3),
