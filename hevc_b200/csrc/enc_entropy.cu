@@ -149,9 +149,15 @@ __global__ void __launch_bounds__(256) k_modes(ModeParams p)
 
 // ------------------------------------------------------------------------------------------------ CABAC engine (lane 0)
 // Per-warp scratch at file scope so that the (deliberately not inlined) coding functions address it as shared memory.
-__shared__ EntropyWarpScratch g_ews[kEntropyWarps];
-// per state: x = the four rangeTabLps bytes, y = the state after an LPS (built once per CTA from the constant tables)
-__shared__ uint2 g_state_tab[64];
+// per state: x = the four rangeTabLps bytes, y = the state after an LPS | the renormalisation shifts of the four LPS ranges << 8
+// (four bits each; built once per CTA from the constant tables).  One struct, so every shared-space address derives from one base.
+struct EntropyShared {
+    EntropyWarpScratch ws[kEntropyWarps];
+    uint2 state_tab[64];
+};
+__shared__ EntropyShared g_es;
+#define g_ews g_es.ws
+#define g_state_tab g_es.state_tab
 
 // Arithmetic-coder state, passed and returned BY VALUE so that it lives in registers (a struct passed by reference to
 // non-inlined functions sat in local memory and put local loads / stores on the critical path of every bin).
@@ -219,86 +225,130 @@ __device__ __forceinline__ uint2 ctx_entry(int state, int mps)
     return make_uint2(t.x, (t.y << 8) | ((uint32_t)state << 1) | (uint32_t)mps);
 }
 
-// Lane 0: the arithmetic coder proper, one tight loop over a bin list in shared memory (word offset `off` inside the warp's
-// scratch).  Per context-coded bin the critical path is one 64-bit shared load (the context entry carries the four LPS ranges
-// of its state), a byte select and the range / low update; the state transition (one more table load and the store) is off it.
-__device__ __forceinline__ CabacState code_list(CabacState st, int w, int off, int n)
+// Shared-memory accesses of the coding loop by 32-bit shared-space address: the generic-address forms recomputed the shared
+// window base (S2UR SR_CgaCtaId + three uniform-datapath instructions) in every iteration, and the explicit order of the
+// accesses is what the software pipeline below relies on.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a)
 {
-    EntropyWarpScratch &s = g_ews[w];
-    const uint32_t *e = reinterpret_cast<const uint32_t *>(&s) + off;
-    uint32_t low = st.x, range = st.y & 0xffffu;
-    int bits_left = (int)(st.y >> 16);
-    for (int k = 0; k < n; k++) {
-        const uint32_t v = e[k];
-        const uint32_t kind = v & 0xff, arg = (v >> 8) & 0xff;
-        if (kind < kTerminate) {
-            const uint2 c = s.ctx[kind];
-            const uint32_t lps = __byte_perm(c.x, 0, 0x4440u | ((range >> 6) & 3));
-            const uint32_t state = (c.y >> 1) & 63;
-            uint32_t mps = c.y & 1, next;
-            range -= lps;
-            if (arg != mps) {
-                const int nb = __clz(lps) - 23;             // renormalisation shift: lps in [6, 240] -> 1..6
-                low = (low + range) << nb;
-                range = lps << nb;
-                bits_left -= nb;
-                next = (c.y >> 8) & 0xff;
-                if (state == 0) mps ^= 1;
-            } else {
-                next = state < 62 ? state + 1 : state;
-                if (range < 256) { low <<= 1; range <<= 1; bits_left--; }
-            }
-            s.ctx[kind] = ctx_entry((int)next, (int)mps);
-            if (bits_left < 12) { const CabacState r = cb_write_out(low, range, bits_left, w); low = r.x; bits_left = (int)(r.y >> 16); }
-        } else if (kind == kTerminate) {
-            range -= 2;
-            if (arg) {
-                low = (low + range) << 7;
-                range = 2 << 7;
-                bits_left -= 7;
-            } else if (range < 256) {
-                low <<= 1; range <<= 1; bits_left--;
-            }
-            if (bits_left < 12) { const CabacState r = cb_write_out(low, range, bits_left, w); low = r.x; bits_left = (int)(r.y >> 16); }
-        } else {
-            // equiprobable bins, up to 8 at a time (H.265 9.3.4.3.4 applied c times: low = low * 2^c + range * bits)
-            uint32_t bits = kind == kBypass ? v >> 16 : (2u << arg) - 2;
-            int nbit = kind == kBypass ? (int)arg : (int)arg + 1;
-            while (nbit > 0) {
-                const int c = nbit > 8 ? 8 : nbit;
-                nbit -= c;
-                low = (low << c) + range * ((bits >> nbit) & ((1u << c) - 1));
-                bits_left -= c;
-                if (bits_left < 12) { const CabacState r = cb_write_out(low, range, bits_left, w); low = r.x; bits_left = (int)(r.y >> 16); }
-            }
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+
+// Lane 0: the arithmetic coder proper, one tight loop over a bin list in shared memory (word offset `off` inside the warp's
+// scratch), software-pipelined by hand: the list entry is fetched two bins ahead and the context entry of the NEXT bin one bin
+// ahead (patched when it is the context this bin updates), and the table entry of the state this bin moves to is requested as
+// soon as the bin value is compared with the MPS -- before the range arithmetic, which then covers its latency.  The MPS / LPS
+// paths are one branch-free update (the LPS renormalisation shift comes out of the context entry, four bits per range quarter),
+// so what stays on the critical path from bin to bin is the range / low recurrence alone: quarter select, LPS byte select,
+// subtract, renormalise.  One step codes `cur`, refills it with the entry two places on and returns the context entry of `nxt`;
+// the loop alternates the two registers so nothing is moved between iterations.
+// (Entries are read up to two words past the end of a list and context entries are fetched for non-context kinds: both stay
+// inside the warp's scratch and are never used.)
+struct CoderRegs {
+    uint32_t low, range;
+    int bits_left;
+};
+__device__ __forceinline__ uint2 code_step(CoderRegs &r, uint32_t &cur, const uint32_t nxt, const uint2 c, uint32_t &ep, const uint32_t cbase,
+                                           const uint32_t tbase, const int w)
+{
+    const uint32_t kind = cur & 0xff, arg = __byte_perm(cur, 0, 0x4441), bypass = cur >> 16, kn = nxt & 0xff;
+    cur = lds32(ep);
+    ep += 4;
+    uint2 cn = lds64(cbase + (kn << 3));
+    if (kind < kTerminate) {
+        const uint32_t mps = c.y & 1, state = (c.y >> 1) & 63;
+        const bool is_lps = arg != mps;
+        const uint32_t next = is_lps ? __byte_perm(c.y, 0, 0x4441) : (state < 62 ? state + 1 : state);
+        const uint32_t nmps = (is_lps && state == 0) ? mps ^ 1 : mps;
+        const uint2 t = lds64(tbase + (next << 3));
+        const uint32_t q = (r.range >> 6) & 3;
+        const uint32_t lps = __byte_perm(c.x, 0, 0x4440u | q);
+        const uint32_t nbl = (c.y >> (16 + 4 * q)) & 15;             // renormalisation shift of this LPS range: clz(lps) - 23 = 1..6
+        const uint32_t rmps = r.range - lps;
+        const uint32_t nb = is_lps ? nbl : (rmps < 256 ? 1u : 0u);
+        r.low = (r.low + (is_lps ? rmps : 0u)) << nb;
+        r.range = (is_lps ? lps : rmps) << nb;
+        r.bits_left -= (int)nb;
+        // (r.range >> 9 is always 0 -- a renormalised range is below 512 -- and makes the first use of the table entry depend on
+        // the finished range update: without it the assembler schedules that use right behind the load, and the in-order issue
+        // of the single active lane waits there for the whole shared-memory latency before the range arithmetic starts)
+        const uint2 ne = make_uint2(t.x, (t.y * 256u + (r.range >> 9)) | (next << 1) | nmps);
+        sts64(cbase + (kind << 3), ne);
+        if (kn == kind) cn = ne;
+        if (r.bits_left < 12) { const CabacState o = cb_write_out(r.low, r.range, r.bits_left, w); r.low = o.x; r.bits_left = (int)(o.y >> 16); }
+    } else if (kind == kTerminate) {
+        r.range -= 2;
+        if (arg) {
+            r.low = (r.low + r.range) << 7;
+            r.range = 2 << 7;
+            r.bits_left -= 7;
+        } else if (r.range < 256) {
+            r.low <<= 1; r.range <<= 1; r.bits_left--;
+        }
+        if (r.bits_left < 12) { const CabacState o = cb_write_out(r.low, r.range, r.bits_left, w); r.low = o.x; r.bits_left = (int)(o.y >> 16); }
+    } else {
+        // equiprobable bins, up to 8 at a time (H.265 9.3.4.3.4 applied c times: low = low * 2^c + range * bits)
+        const uint32_t bits = kind == kBypass ? bypass : (2u << arg) - 2;
+        int nbit = kind == kBypass ? (int)arg : (int)arg + 1;
+        while (nbit > 0) {
+            const int cnt = nbit > 8 ? 8 : nbit;
+            nbit -= cnt;
+            r.low = (r.low << cnt) + r.range * ((bits >> nbit) & ((1u << cnt) - 1));
+            r.bits_left -= cnt;
+            if (r.bits_left < 12) { const CabacState o = cb_write_out(r.low, r.range, r.bits_left, w); r.low = o.x; r.bits_left = (int)(o.y >> 16); }
         }
     }
-    return cs_make(low, range, bits_left);
+    return cn;
+}
+
+// `esb`: shared-space address of the CTA's entropy scratch (computed once per kernel: taking the address of a shared variable
+// costs an S2UR and three uniform-datapath instructions wherever the compiler rematerialises it)
+__device__ __noinline__ CabacState code_list(CabacState st, uint32_t esb, int w, int off, int n)
+{
+    if (n <= 0) return st;
+    const uint32_t sbase = esb + (uint32_t)(offsetof(EntropyShared, ws) + w * sizeof(EntropyWarpScratch));
+    const uint32_t tbase = esb + (uint32_t)offsetof(EntropyShared, state_tab);
+    const uint32_t cbase = sbase + (uint32_t)offsetof(EntropyWarpScratch, ctx);
+    uint32_t ep = sbase + 4u * (uint32_t)off;
+    CoderRegs r{st.x, st.y & 0xffffu, (int)(st.y >> 16)};
+    uint32_t v0 = lds32(ep), v1 = lds32(ep + 4);
+    uint2 c0 = lds64(cbase + ((v0 & 0xff) << 3)), c1;
+    ep += 8;
+    for (;;) {
+        c1 = code_step(r, v0, v1, c0, ep, cbase, tbase, w);
+        if (--n == 0) break;
+        c0 = code_step(r, v1, v0, c1, ep, cbase, tbase, w);
+        if (--n == 0) break;
+    }
+    return cs_make(r.low, r.range, r.bits_left);
 }
 
 #define EWS_OFF(member) ((int)(offsetof(EntropyWarpScratch, member) / 4))
 
 // lane 0: everything CU `k` of the current CTU contributes: header list, then per coded transform block its last-position list
 // and the sub-block lists in coding order
-__device__ __noinline__ CabacState code_cu(CabacState st, int w, int k, int cbf)
+__device__ __noinline__ CabacState code_cu(CabacState st, uint32_t esb, int w, int k, int cbf)
 {
     EntropyWarpScratch &s = g_ews[w];
-    st = code_list(st, w, EWS_OFF(hdr) + k * kHdrBins, s.nhdr[k]);
+    st = code_list(st, esb, w, EWS_OFF(hdr) + k * kHdrBins, s.nhdr[k]);
     for (int tu = 0; tu < 3; tu++) {
         if (!((cbf >> tu) & 1)) continue;
         const int base = tu == 0 ? 0 : 12 + 4 * tu;
-        st = code_list(st, w, EWS_OFF(tuh) + tu * kTuHdrBins, s.ntuh[tu]);
-        for (int i = s.last_sb[tu]; i >= 0; i--) st = code_list(st, w, EWS_OFF(bins) + (base + i) * kBinStride, s.nbins[base + i]);
+        st = code_list(st, esb, w, EWS_OFF(tuh) + tu * kTuHdrBins, s.ntuh[tu]);
+        for (int i = s.last_sb[tu]; i >= 0; i--) st = code_list(st, esb, w, EWS_OFF(bins) + (base + i) * kBinStride, s.nbins[base + i]);
     }
     return st;
 }
 
 // lane 0: one stand-alone list entry (end_of_slice_segment_flag / end_of_subset_one_bit)
-__device__ __noinline__ CabacState code_terminate(CabacState st, int w, int bin)
+__device__ __noinline__ CabacState code_terminate(CabacState st, uint32_t esb, int w, int bin)
 {
     EntropyWarpScratch &s = g_ews[w];
     s.hdr[0][0] = kTerminate | ((uint32_t)bin << 8);
-    return code_list(st, w, EWS_OFF(hdr), 1);
+    return code_list(st, esb, w, EWS_OFF(hdr), 1);
 }
 
 // ------------------------------------------------------------------------------------------------ residual coding
@@ -653,9 +703,16 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 64) {
         const int t = threadIdx.x;
-        g_state_tab[t] = make_uint2((uint32_t)c_range_lps[t][0] | ((uint32_t)c_range_lps[t][1] << 8) | ((uint32_t)c_range_lps[t][2] << 16) |
-                                        ((uint32_t)c_range_lps[t][3] << 24), c_next_lps[t]);
+        uint32_t lps4 = 0, nb4 = 0;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t lps = c_range_lps[t][q];
+            lps4 |= lps << (8 * q);
+            nb4 |= (uint32_t)(__clz(lps) - 23) << (4 * q);
+        }
+        g_state_tab[t] = make_uint2(lps4, (uint32_t)c_next_lps[t] | (nb4 << 8));
     }
+    uint32_t esb = (uint32_t)__cvta_generic_to_shared(&g_es);
+    asm volatile("" : "+r"(esb));                     // opaque: keep it in a register instead of rematerialising the address
     __syncthreads();
     const EntropyFrame fr = p.frames[blockIdx.y];
     uint8_t *ctx_save = fr.ctx_save;                              // [ctuh][kNumCtx]
@@ -735,7 +792,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
         left_skip1 = s.cu[slot][3].syn.skip;
         __syncwarp();
         if (fr.sao) {
-            if (lane == 0) st = code_list(st, w, EWS_OFF(saob), (int)s.nsao);
+            if (lane == 0) st = code_list(st, esb, w, EWS_OFF(saob), (int)s.nsao);
             if (lane < 8) reinterpret_cast<uint32_t *>(&s.sao_left)[lane] = reinterpret_cast<const uint32_t *>(&s.sao_cur[slot])[lane];
             __syncwarp();
         }
@@ -785,7 +842,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
                 __syncwarp();
             }
             // ---- lane 0: the arithmetic coder over this CU's lists
-            if (lane == 0) st = code_cu(st, w, k, cbf);
+            if (lane == 0) st = code_cu(st, esb, w, k, cbf);
             __syncwarp();
         }
         // ---- end of CTU
@@ -797,8 +854,8 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
         }
         if (lane == 0) {
             const bool last_in_pic = row == g.ctuh - 1 && x == g.ctuw - 1;
-            st = code_terminate(st, w, last_in_pic);
-            if (x == g.ctuw - 1 && !last_in_pic) st = code_terminate(st, w, 1);
+            st = code_terminate(st, esb, w, last_in_pic);
+            if (x == g.ctuw - 1 && !last_in_pic) st = code_terminate(st, esb, w, 1);
         }
         // the staging of CTU x + 2 has had a whole CTU of time; the level prefetch (if any) is the only younger group
         if (pf_before_stage) cp_async_wait<0>(); else cp_async_wait<1>();
