@@ -754,6 +754,8 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
         }
     }
     unsigned long long t_start = 0;
+    const bool tracing = fr.trace != nullptr;                     // debug (HB_ENTROPY_TRACE): phase cycle counters of lane 0
+    if (tracing && lane == 0) s.pad3[0] = s.pad3[1] = s.pad3[2] = 0;   // all-lane phase cycles, coding cycles, list entries (shared: no registers)
     if (fr.trace && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     CabacState st = cs_make(0, 510, 23);
     if (lane == 0) { s.buffered = 0; s.held = 0xff; s.out = fr.out + (size_t)row * p.row_cap; s.pos = 0; s.cap = p.row_cap; }
@@ -802,6 +804,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
             const int idx = cy * g.cuw + cx;
             const int cbf = s.cu[slot][k].info.cbf;
             // ---- all lanes: levels of this CU (normally already in flight), sub-block masks, next prefetch, binarisation
+            if (tracing && lane == 0) s.pad2 = (uint32_t)clock();
             if (cbf) {
                 int buf;
                 if (pf_idx == idx) {
@@ -842,8 +845,19 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
                 __syncwarp();
             }
             // ---- lane 0: the arithmetic coder over this CU's lists
+            if (tracing && lane == 0) { const uint32_t t = (uint32_t)clock(); s.pad3[0] += t - s.pad2; s.pad2 = t; }
             if (lane == 0) st = code_cu(st, esb, w, k, cbf);
             __syncwarp();
+            if (tracing && lane == 0) {
+                s.pad3[1] += (uint32_t)clock() - s.pad2;
+                uint32_t ne = s.nhdr[k];
+                for (int tu = 0; tu < 3; tu++)
+                    if ((cbf >> tu) & 1) {
+                        ne += s.ntuh[tu];
+                        for (int i = s.last_sb[tu]; i >= 0; i--) ne += s.nbins[(tu == 0 ? 0 : 12 + 4 * tu) + i];
+                    }
+                s.pad3[2] += ne;
+            }
         }
         // ---- end of CTU
         if (x == 1) {       // snapshot for the row below (taken before the terminating bin, contexts only)
@@ -867,7 +881,8 @@ __global__ void __launch_bounds__(kEntropyWarps * 32, 8) k_entropy(EntropyParams
         if (fr.trace) {
             unsigned long long t_end;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-            fr.trace[2 * row] = t_start; fr.trace[2 * row + 1] = t_end;
+            unsigned long long *t = fr.trace + (size_t)kTraceWords * row;
+            t[0] = t_start; t[1] = t_end; t[2] = s.pad3[0]; t[3] = s.pad3[1]; t[4] = s.pad3[2];
         }
         if (n > p.row_cap) atomicExch(p.overflow, 1);
     }

@@ -412,7 +412,7 @@ int enqueue_batch(hb_encoder *e, BatchSet &B, const hb_frames *fr, int base, int
             FrameSlot &s = B.slot[i];
             ef[i].cus = s.cus; ef[i].syn = s.syn; ef[i].coefs = s.coefs; ef[i].out = s.rows; ef[i].row_len = s.row_len;
             ef[i].ctl = B.ctl_dev + i; ef[i].sao = s.sao; ef[i].ctx_save = s.ctx_save; ef[i].row_ready = s.row_ready;
-            ef[i].trace = B.trace_dev ? B.trace_dev + (size_t)i * g.ctuh * 2 : nullptr;
+            ef[i].trace = B.trace_dev ? B.trace_dev + (size_t)i * g.ctuh * kTraceWords : nullptr;
         }
         HB_CUDA(ctx, cudaMemcpyAsync(B.eframes_dev, ef.data(), sizeof(EntropyFrame) * n, cudaMemcpyHostToDevice, st));
         HB_CUDA(ctx, cudaMemsetAsync(B.overflow, 0, sizeof(int), st));
@@ -730,8 +730,8 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
                 cudaEventElapsedTime(&ms, B.kev[kb + 3], B.kev[kb + 4]); e->prof_ms[3] += ms; e->prof_launches[3] += 2;     // entropy tail + compaction
                 cudaEventElapsedTime(&ms, B.kev[kb + 0], B.kev[kb + 3]); e->prof_ms[5] += ms; e->prof_launches[5] += 4 * n;   // ingest + coarse + frame chain
             }
-            if (B.trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes}
-                std::vector<unsigned long long> tr((size_t)n * g.ctuh * 2);
+            if (B.trace_dev) {      // debug dump: n, ctuh, then per frame / row {start ns, end ns, bytes, binarisation cycles, coding cycles, list entries}
+                std::vector<unsigned long long> tr((size_t)n * g.ctuh * kTraceWords);
                 cudaMemcpy(tr.data(), B.trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
                 if (FILE *f = fopen(e->trace_path, "wb")) {
                     const unsigned long long hdr[2] = {(unsigned long long)n, (unsigned long long)g.ctuh};
@@ -739,7 +739,8 @@ int drain_batch(hb_encoder *e, BatchSet &B, uint8_t *out, size_t cap, size_t &wr
                     for (size_t k = 0; k < (size_t)n * g.ctuh; k++) {
                         const size_t fi = k / g.ctuh, gi = fi / kGroupFrames;
                         const uint32_t *o = B.offsets_host + k + gi;
-                        const unsigned long long rec[3] = {tr[2 * k], tr[2 * k + 1], (unsigned long long)(o[1] - o[0])};
+                        const unsigned long long *t = &tr[kTraceWords * k];
+                        const unsigned long long rec[6] = {t[0], t[1], (unsigned long long)(o[1] - o[0]), t[2], t[3], t[4]};
                         fwrite(rec, sizeof(rec), 1, f);
                     }
                     fclose(f);
@@ -909,7 +910,7 @@ int hb_enc_create(hb_ctx *ctx, const hb_enc_params *params, int max_batch, hb_en
         HB_TRY(dev_alloc(E, &B.ctl_dev, (size_t)max_batch));
         HB_CUDA(ctx, cudaMallocHost(&B.ctl_host, sizeof(FrameCtl) * max_batch));
         HB_TRY(dev_alloc(E, &B.eframes_dev, (size_t)max_batch));
-        if (E->trace_path) HB_TRY(dev_alloc(E, &B.trace_dev, (size_t)max_batch * g.ctuh * 2));
+        if (E->trace_path) HB_TRY(dev_alloc(E, &B.trace_dev, (size_t)max_batch * g.ctuh * kTraceWords));
         HB_TRY(dev_alloc(E, &B.offsets_dev, (size_t)max_batch * g.ctuh + kMaxGroups + 1));
         HB_TRY(dev_alloc(E, &B.packed_dev, E->packed_cap));
         HB_CUDA(ctx, cudaMallocHost(&B.offsets_host, ((size_t)max_batch * g.ctuh + kMaxGroups + 1) * sizeof(uint32_t)));

@@ -114,6 +114,7 @@ struct PackParams {
 };
 
 constexpr int kEntropyWarps = 4;
+constexpr int kTraceWords = 5;             // debug trace per CTU row: start ns, end ns, binarisation cycles, coding cycles, list entries
 constexpr int kIntraSearchThreads = 128;   // k_intra_search CTA: four warps, one CU each
 constexpr int kIntraReconThreads = 384;   // k_intra CTA: one thread per luma sample + one per chroma sample (both planes) of the CU
 constexpr int kBinStride = 61;            // 32-bit words per sub-block bin list (<= 60 entries, odd stride: no bank conflicts)

@@ -76,6 +76,36 @@ def test_satd_sa8d_against_matrix_hadamard():
         assert list(cmodel.sa8d(a, b)) == want
 
 
+def test_sad_matches_libavutil_pixelutils():
+    """SAD pinned against an independent implementation: av_pixelutils_get_sad_fn of the FFmpeg libavutil bundled with the OpenCV
+    wheel (square 8-bit blocks 4x4 ... 32x32, the x265 `sad[]` sizes on the CU grid).  libx265 itself is not in the image."""
+    import ctypes as C
+    from hevc_b200 import avreader
+    try:
+        av = avreader._lib('avutil')
+        get = av.av_pixelutils_get_sad_fn
+    except (avreader.Unsupported, AttributeError, OSError):
+        pytest.skip('bundled libavutil without pixelutils')
+    get.restype = C.c_void_p
+    get.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t)
+    rng = np.random.default_rng(5)
+    checked = 0
+    for bits in (2, 3, 4, 5):
+        addr = get(bits, bits, 0, None)
+        if not addr:
+            continue
+        fn, n = proto(addr), 1 << bits
+        for trial in range(20):
+            a = rng.integers(0, 256, (n, n), dtype=np.uint8)
+            b = (255 - a if trial == 0 else rng.integers(0, 256, (n, n), dtype=np.uint8))
+            want = fn(a.ctypes.data, n, b.ctypes.data, n)
+            got = int(cmodel.sad(a.astype(np.uint16)[None], b.astype(np.uint16)[None])[0])
+            assert got == want == int(np.abs(a.astype(int) - b.astype(int)).sum()), (n, trial)
+            checked += 1
+    assert checked >= 20
+
+
 def test_quant_dequant_properties():
     for depth in (8, 10):
         for size in (4, 8, 16, 32):
