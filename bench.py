@@ -113,6 +113,22 @@ def measured_peaks():
         return {'hbm_gbs': 6650.0}, 'fallback'
 
 
+def committed_rd(size: str):
+    """Bjontegaard delta rate of the shipped tool set against the round-1 tool set, per content class, as committed under profiles/
+    (measured on the CPU model, to which the CUDA encoder is byte-identical: tools/model_rd.py).  Not measured in this run."""
+    path = ROOT / 'profiles' / f'rd_model_{size}_r2.jsonl'
+    try:
+        rows = [json.loads(l) for l in path.read_text().splitlines() if l.strip()]
+    except (OSError, ValueError):
+        return None
+    bd = {r['class']: [r['bd_rate_psnr_pct'], r['bd_rate_ssim_pct']] for r in rows if r.get('anchor') == 'r1' and r.get('set') == 'r2'}
+    if not bd:
+        return None
+    return {'bd_rate_pct_psnr_ssim': bd, 'anchor': 'round-1 tool set of this encoder (own anchor)', 'x265_anchor': None,
+            'x265_anchor_note': 'libx265 is not in the image (BASELINE.md section 4): the anchor column stays empty',
+            'source': f'profiles/{path.name} (committed; constant QP 22/27/32/37, PSNR-Y and SSIM of the reconstruction)'}
+
+
 def dist_env():
     return int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
 
@@ -347,6 +363,9 @@ def run_b200(args):
         }
         if cores_bound:
             line['host_cores_per_rank'] = cores_bound
+        rd = committed_rd('4k' if params.height >= 2160 else '1080p')
+        if rd:
+            line['rd_vs_round1'] = rd
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cmodel
             cmodel.build()
