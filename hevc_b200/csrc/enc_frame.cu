@@ -1262,6 +1262,18 @@ __global__ void __launch_bounds__(kIntraReconThreads) k_intra(IntraParams p)
     const int n = n_list;
     for (int li = 0; li < n; li++) {
         const int x = ctu_list[li];
+        // which of the CTU's CUs are intra: final since k_inter, so the four records are fetched together and before the wait
+        // (one global round trip instead of up to four dependent ones on the wavefront's critical path)
+        unsigned intra_mask = 0xfu;
+        if (!slice_intra) {
+            uint8_t pm[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int cx = min(2 * x + (k & 1), g.cuw - 1), cy = min(2 * r + (k >> 1), g.cuh - 1);
+                pm[k] = p.cus[cy * g.cuw + cx].pred_mode;
+            }
+            intra_mask = (pm[0] == 0 ? 1u : 0u) | (pm[1] == 0 ? 2u : 0u) | (pm[2] == 0 ? 4u : 0u) | (pm[3] == 0 ? 8u : 0u);
+        }
         if (r > 0) {
             if (tid == 0) {
                 const int need = min(x + 2, g.ctuw);
@@ -1275,7 +1287,7 @@ __global__ void __launch_bounds__(kIntraReconThreads) k_intra(IntraParams p)
         for (int k = 0; k < 4; k++) {
             const int cx = 2 * x + (k & 1), cy = 2 * r + (k >> 1);
             if (cx >= g.cuw || cy >= g.cuh) continue;
-            if (slice_intra || p.cus[cy * g.cuw + cx].pred_mode == 0) {
+            if ((intra_mask >> k) & 1) {
                 intra_cu(p, s, cx, cy);
             } else if (tid == 0) {         // an inter CU counts as DC in the most-probable-mode derivation of its neighbours
                 s.left_mode[k >> 1] = 1;
