@@ -3,8 +3,11 @@
 
 ``cv2.VideoCapture`` hands over 8-bit BGR: a Main10 / 10-bit source loses two bits and takes a YUV -> BGR -> YUV round trip.  This
 reader keeps the decoder's own samples (yuv420p -> HB_PIX_YUV420P8, yuv420p10le -> HB_PIX_YUV420P16 with 10 significant bits).
-Anything else (4:2:2, 4:4:4, RGB codecs, a library layout this module does not recognise) raises ``Unsupported`` and the caller
-falls back to the OpenCV reader.
+Every other YUV layout -- 4:2:2 / 4:4:4 (ProRes, DNxHR, v210, Y4M C422 / C444), full-range yuvj*, 12- / 16-bit, packed or
+semi-planar -- goes through the bundled libswscale to yuv420p (8-bit sources) or yuv420p10le (deeper ones): the same library call
+the reference gets from the scaler ffmpeg inserts for ``-pix_fmt`` (core/transcoder.py:464), so 10-bit 4:2:2 masters keep their
+precision.  RGB / palette / Bayer formats and library layouts this module does not recognise raise ``Unsupported`` and the caller
+falls back to the OpenCV reader (the RGB -> YUV matrix then follows the probe, hevc_b200/transcoder.py).
 
 No FFmpeg headers are available, so only long-stable, documented structure heads are touched, each guarded by a sanity check:
 ``AVFormatContext.nb_streams / .streams`` (offsets 44 / 48 since libavformat 58), ``AVStream.codecpar`` (offset 16 since
@@ -22,6 +25,8 @@ from typing import Iterator, Optional, Tuple
 import numpy as np
 
 AV_PIX_FMT_YUV420P, AV_PIX_FMT_YUVJ420P, AV_PIX_FMT_YUV420P10LE = 0, 12, 62
+_PIX_FLAG_PAL, _PIX_FLAG_RGB, _PIX_FLAG_BAYER = 1 << 1, 1 << 5, 1 << 8
+_SWS_BICUBIC = 4                   # ffmpeg's default for the scaler it auto-inserts
 _EAGAIN, _EOF = -11, -541478725
 
 
@@ -32,6 +37,15 @@ class Unsupported(RuntimeError):
 class _AVFrameHead(C.Structure):
     _fields_ = [('data', C.c_void_p * 8), ('linesize', C.c_int * 8), ('extended_data', C.c_void_p),
                 ('width', C.c_int), ('height', C.c_int), ('nb_samples', C.c_int), ('format', C.c_int)]
+
+
+class _AVComponentDescriptor(C.Structure):
+    _fields_ = [('plane', C.c_int), ('step', C.c_int), ('offset', C.c_int), ('shift', C.c_int), ('depth', C.c_int)]
+
+
+class _AVPixFmtDescriptorHead(C.Structure):          # libavutil >= 58: five ints per component, no deprecated members
+    _fields_ = [('name', C.c_char_p), ('nb_components', C.c_uint8), ('log2_chroma_w', C.c_uint8), ('log2_chroma_h', C.c_uint8),
+                ('flags', C.c_uint64), ('comp', _AVComponentDescriptor * 4)]
 
 
 class _AVPacketHead(C.Structure):
@@ -55,7 +69,7 @@ def _libdir() -> str:
 def _lib(stem: str) -> C.CDLL:
     if stem not in _LIBS:
         d = _libdir()
-        for dep in {'avcodec': ('avutil', 'swresample'), 'avformat': ('avutil', 'swresample', 'avcodec'), 'swresample': ('avutil',)}.get(stem, ()):
+        for dep in {'avcodec': ('avutil', 'swresample'), 'avformat': ('avutil', 'swresample', 'avcodec'), 'swresample': ('avutil',), 'swscale': ('avutil',)}.get(stem, ()):
             _lib(dep)
         hits = sorted(glob.glob(os.path.join(d, f'lib{stem}-*.so*')))
         if not hits:
@@ -106,6 +120,7 @@ class AvReader:
         self.pkt = C.c_void_p()
         self.frame = C.c_void_p()
         self._ring = None
+        self._sws = None               # ((format, w, h), SwsContext, bytes per sample, library, format name) of the conversion in use
         if f.avformat_open_input(C.byref(self.fmt), str(path).encode(), None, None) < 0:
             self.fmt = C.c_void_p()
             raise Unsupported(f'avformat cannot open {path}')
@@ -143,8 +158,51 @@ class AvReader:
         self.width, self.height, bps = self._pending[1], self._pending[2], self._pending[3]
         self.fmt_id = self._fmt_ids[0] if bps == 1 else self._fmt_ids[1]
         self.src_bit_depth = 8 if bps == 1 else 10
-        self.pix_fmt = 'yuv420p' if bps == 1 else 'yuv420p10le'
+        self.pix_fmt = 'yuv420p' if bps == 1 else 'yuv420p10le'          # what this reader DELIVERS
+        self.source_pix_fmt = self._sws[4] if self._sws else self.pix_fmt     # what the decoder produced
         self.frame_bytes = (self.width * self.height + 2 * (self.width // 2) * (self.height // 2)) * bps
+
+    # ---- a decoded frame in any YUV layout -> planar 4:2:0 at 8 bits (8-bit sources) or 10 bits (deeper ones) through libswscale
+    def _sws_to_420(self, fr: _AVFrameHead, w: int, h: int):
+        u = self.avu
+        if self._sws is None or self._sws[0] != (fr.format, w, h):
+            u.av_pix_fmt_desc_get.restype = C.POINTER(_AVPixFmtDescriptorHead)
+            u.av_pix_fmt_desc_get.argtypes = [C.c_int]
+            d = u.av_pix_fmt_desc_get(fr.format)
+            if not d:
+                raise Unsupported(f'pixel format {fr.format} unknown to libavutil')
+            d = d.contents
+            depth = d.comp[0].depth
+            if not (d.name and 3 <= d.nb_components <= 4 and 8 <= depth <= 16 and d.log2_chroma_w <= 2 and d.log2_chroma_h <= 2):
+                raise Unsupported(f'pixel format {fr.format}: unexpected descriptor layout or not a three-component format')
+            if d.flags & (_PIX_FLAG_RGB | _PIX_FLAG_PAL | _PIX_FLAG_BAYER):
+                raise Unsupported(f'pixel format {d.name.decode()} is not YUV')
+            try:
+                sws = _lib('swscale')
+            except OSError as exc:
+                raise Unsupported(str(exc))
+            sws.sws_getContext.restype = C.c_void_p
+            sws.sws_getContext.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3
+            sws.sws_scale.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+            sws.sws_freeContext.argtypes = [C.c_void_p]
+            bps = 1 if depth <= 8 else 2
+            ctx = sws.sws_getContext(w, h, fr.format, w, h, AV_PIX_FMT_YUV420P if bps == 1 else AV_PIX_FMT_YUV420P10LE, _SWS_BICUBIC, None, None, None)
+            if not ctx:
+                raise Unsupported(f'libswscale cannot convert {d.name.decode()}')
+            if self._sws is not None:
+                sws.sws_freeContext(self._sws[1])
+            self._sws = ((fr.format, w, h), ctx, bps, sws, d.name.decode())
+        _, ctx, bps, sws, _ = self._sws
+        luma, chroma = w * h * bps, (w // 2) * (h // 2) * bps
+        out = np.empty(luma + 2 * chroma, np.uint8)
+        base = out.ctypes.data
+        dst = (C.c_void_p * 4)(base, base + luma, base + luma + chroma, None)
+        dst_ls = (C.c_int * 4)(w * bps, (w // 2) * bps, (w // 2) * bps, 0)
+        src = (C.c_void_p * 4)(*[fr.data[i] for i in range(4)])
+        src_ls = (C.c_int * 4)(*[fr.linesize[i] for i in range(4)])
+        if sws.sws_scale(ctx, src, src_ls, 0, h, dst, dst_ls) <= 0:
+            raise Unsupported('sws_scale failed')
+        return out, bps
 
     # ---- one decoded frame as (packed planes uint8, width, height, bytes per sample), or None at the end of the stream
     def _next_frame(self):
@@ -153,14 +211,17 @@ class AvReader:
             rc = a.avcodec_receive_frame(self.ctx, self.frame)
             if rc >= 0:
                 fr = _AVFrameHead.from_address(self.frame.value)
-                if fr.format in (AV_PIX_FMT_YUV420P, AV_PIX_FMT_YUVJ420P):
+                w, h = fr.width & ~1, fr.height & ~1
+                if fr.format == AV_PIX_FMT_YUV420P:
                     bps = 1
                 elif fr.format == AV_PIX_FMT_YUV420P10LE:
                     bps = 2
-                else:
-                    u.av_frame_unref(self.frame)
-                    raise Unsupported(f'pixel format {fr.format} is not planar 4:2:0 at 8 / 10 bits')
-                w, h = fr.width & ~1, fr.height & ~1
+                else:                                        # any other YUV layout: libswscale, as the reference's ffmpeg child does
+                    try:
+                        out, bps = self._sws_to_420(fr, w, h)
+                    finally:
+                        u.av_frame_unref(self.frame)
+                    return out, w, h, bps
                 parts = []
                 for i, (pw, ph) in enumerate(((w, h), (w // 2, h // 2), (w // 2, h // 2))):
                     ls = fr.linesize[i]
@@ -209,6 +270,9 @@ class AvReader:
         ring, self._ring = getattr(self, '_ring', None), None
         if ring is not None:
             ring.close()
+        sws, self._sws = getattr(self, '_sws', None), None
+        if sws is not None:
+            sws[3].sws_freeContext(sws[1])
         if getattr(self, 'frame', None) and self.frame.value:
             self.avu.av_frame_free(C.byref(self.frame))
         if getattr(self, 'pkt', None) and self.pkt.value:

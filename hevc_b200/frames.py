@@ -40,8 +40,8 @@ class Y4MReader:
     def __init__(self, path: Path):
         self.path = Path(path)
         self.meta = _probe_y4m(self.path)
-        if not self.meta['pix_fmt'].startswith('yuv420'):
-            raise ValueError(f"unsupported Y4M chroma format {self.meta['pix_fmt']}")
+        if self.meta['pix_fmt'] not in ('yuv420p', 'yuv420p10le'):       # open_reader then goes through avreader (libswscale)
+            raise ValueError(f"Y4M pixel format {self.meta['pix_fmt']} is not read natively")
         self.fmt = PIX_YUV420P16 if '10' in self.meta['pix_fmt'] else PIX_YUV420P8
         self.src_bit_depth = 10 if self.fmt == PIX_YUV420P16 else 8
         self.frame_bytes = self.meta['frame_bytes']
@@ -162,7 +162,10 @@ def open_reader(path: Path, info: VideoInfo):
     with open(path, 'rb') as fh:
         magic = fh.read(9)
     if magic == b'YUV4MPEG2':
-        return Y4MReader(path)
+        try:
+            return Y4MReader(path)
+        except ValueError:        # C422 / C444 / C4xxp12 ...: libavformat's y4m demuxer + libswscale (avreader) below
+            pass
     if path.suffix.lower() in ('.yuv', '.raw'):
         return RawYuvReader(path, info)
     try:                          # containers: the decoder's own 4:2:0 samples at their native depth when the bundled FFmpeg allows it

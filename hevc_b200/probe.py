@@ -132,7 +132,8 @@ def info_from_ffprobe_json(doc: dict) -> VideoInfo:
 # ---------------------------------------------------------------- ffprobe-less probers
 
 _Y4M_CSP = {'420': 'yuv420p', '420jpeg': 'yuv420p', '420mpeg2': 'yuv420p', '420paldv': 'yuv420p',
-            '420p10': 'yuv420p10le', '444': 'yuv444p', '444p10': 'yuv444p10le', '422': 'yuv422p'}
+            '420p10': 'yuv420p10le', '444': 'yuv444p', '444p10': 'yuv444p10le', '422': 'yuv422p', '422p10': 'yuv422p10le',
+            '420p12': 'yuv420p12le', '422p12': 'yuv422p12le', '444p12': 'yuv444p12le'}
 
 
 def _probe_y4m(path: Path) -> dict:
@@ -153,7 +154,7 @@ def _probe_y4m(path: Path) -> dict:
         elif k == 'C':
             out['pix_fmt'] = _Y4M_CSP.get(val, 'yuv420p')
     out['header_len'] = len(head)
-    bps = 2 if '10' in out['pix_fmt'] else 1
+    bps = 2 if out['pix_fmt'].endswith('le') else 1
     w, h = out['width'], out['height']
     if out['pix_fmt'].startswith('yuv444'):
         fsz = w * h * 3 * bps

@@ -204,3 +204,37 @@ def test_convert_video_main10_hdr10_container(tmp_path):
     rep, dec = _decode_mp4(data)
     assert len(dec) == 8 and rep['sps']['bit_depth'] == 10
     assert _psnr(dec[3][0], dec_src[3][0], 1023) > 30          # against the 10-bit decoded source, full depth kept
+
+
+@pytest.mark.parametrize('tagged_hdr', [False, True])
+def test_convert_video_422_10bit_master(tmp_path, tagged_hdr):
+    """a 4:2:2 10-bit master (the ProRes-style source of the reference's users; here Y4M C422p10): libswscale reduces the chroma to 4:2:0 at
+    10 bits on the host (what ffmpeg does for -pix_fmt, core/transcoder.py:464), HDR-tagged it becomes a Main10 encode at full depth,
+    untagged the reference's 8-bit Main encode"""
+    w, h, n = 256, 144, 6
+    clip = SynthClip(w, h, seed=14, noise=0.0)
+    rng = np.random.default_rng(5)
+    frames = []
+    for i in range(n):
+        y, u, v = clip.frame(i)
+        y10 = (y.astype(np.uint16) << 2) + rng.integers(0, 4, y.shape, dtype=np.uint16)
+        frames.append((y10, np.repeat(u.astype(np.uint16) << 2, 2, axis=0), np.repeat(v.astype(np.uint16) << 2, 2, axis=0)))   # 4:2:2: full-height chroma
+    src = tmp_path / 'master.y4m'
+    with open(src, 'wb') as fh:
+        fh.write(f'YUV4MPEG2 W{w} H{h} F30:1 Ip A1:1 C422p10\n'.encode())
+        for planes in frames:
+            fh.write(b'FRAME\n')
+            for pl in planes:
+                fh.write(np.ascontiguousarray(pl, dtype='<u2').tobytes())
+    if tagged_hdr:
+        (tmp_path / 'master.y4m.json').write_text(json.dumps({'color_primaries': 'bt2020', 'color_transfer': 'smpte2084', 'color_space': 'bt2020nc'}))
+    res = transcoder.convert_video(src, tmp_path, encoder='b200', device=0)
+    assert res['status'] == 'SUCCESS' and res['hdr'] is tagged_hdr and res['method'] == 'B200', res
+    rep, dec = _decode_mp4((tmp_path / 'master.mp4').read_bytes())
+    assert rep['sps']['bit_depth'] == (10 if tagged_hdr else 8) and len(dec) == n and dec[0][0].shape == (h, w)
+    if tagged_hdr:
+        assert _psnr(dec[2][0], frames[2][0], 1023) > 26
+        assert _psnr(dec[2][1], clip.frame(2)[1].astype(np.uint16) << 2, 1023) > 30      # chroma survived the 4:2:2 -> 4:2:0 reduction
+    else:
+        want = np.minimum((frames[2][0].astype(np.int32) + 2) >> 2, 255)
+        assert _psnr(dec[2][0], want, 255) > 26 and int(dec[2][0].max()) <= 255

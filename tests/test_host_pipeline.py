@@ -454,6 +454,54 @@ def test_container_reader_keeps_native_depth_and_probe_reads_hdr10_boxes(tmp_pat
         assert (g == want).all()
 
 
+def _write_y4m_tag(path, tag, w, h, frames, dtype):
+    with open(path, 'wb') as fh:
+        fh.write(f'YUV4MPEG2 W{w} H{h} F30:1 Ip A1:1 C{tag}\n'.encode())
+        for planes in frames:
+            fh.write(b'FRAME\n')
+            for pl in planes:
+                fh.write(np.ascontiguousarray(pl, dtype=dtype).tobytes())
+
+
+@pytest.mark.parametrize('tag,depth,cdiv', [('422p10', 10, (2, 1)), ('444', 8, (1, 1)), ('422', 8, (2, 1)), ('444p10', 10, (1, 1)), ('420p12', 12, (2, 2))])
+def test_other_yuv_layouts_go_through_libswscale_at_native_depth(tmp_path, tag, depth, cdiv):
+    """4:2:2 / 4:4:4 / 12-bit sources (ProRes-style masters; here Y4M C422p10 ...) are converted to planar 4:2:0 by the bundled libswscale
+    -- the call the reference's ffmpeg child makes for -pix_fmt (core/transcoder.py:464) -- at 8 bits for 8-bit sources and 10 bits for
+    deeper ones: luma passes through untouched (rounded from 12 bits), chroma is the filtered 2:1 reduction of the source planes"""
+    from hevc_b200.avreader import AvReader
+    from hevc_b200.frames import open_reader
+    w, h, n = 64, 48, 3
+    cw, ch = w // cdiv[0], h // cdiv[1]
+    mx = (1 << depth) - 1
+    yy, xx = np.mgrid[0:h, 0:w]
+    cy, cx = np.mgrid[0:ch, 0:cw]
+    src = [(((np.sin(xx / 7 + i) + np.cos(yy / 5)) * 0.2 + 0.5) * mx, ((np.sin(cx / (12 / cdiv[0]) + i) * 0.2) + 0.5) * mx,
+            ((np.cos(cy / (8 / cdiv[1]) + i) * 0.2) + 0.5) * mx) for i in range(n)]
+    src = [tuple(p.astype(np.int64) for p in f) for f in src]
+    path = tmp_path / f'src_{tag}.y4m'
+    _write_y4m_tag(path, tag, w, h, src, '<u2' if depth > 8 else np.uint8)
+    info = probe.probe_media(path)
+    assert (info.width, info.height) == (w, h) and info.pix_fmt.startswith('yuv4') and str(depth if depth > 8 else '') in info.pix_fmt
+    r = open_reader(path, info)
+    assert isinstance(r, AvReader) and r.kind == 'yuv' and r.src_bit_depth == (10 if depth > 8 else 8)
+    assert r.source_pix_fmt == info.pix_fmt and r.pix_fmt == ('yuv420p10le' if depth > 8 else 'yuv420p')
+    out_depth = r.src_bit_depth
+    got = []
+    for buf, k, _ in r.batches(2, ring=3):
+        got += [np.array(buf[i] if buf.ndim > 1 else buf[i * r.frame_bytes:(i + 1) * r.frame_bytes]) for i in range(k)]
+    r.close()
+    assert len(got) == n
+    sh = depth - out_depth
+    for f, g in zip(src, got):
+        g = g.view('<u2' if out_depth > 8 else np.uint8).astype(np.int64)
+        y, u, v = g[:w * h].reshape(h, w), g[w * h:w * h + w * h // 4].reshape(h // 2, w // 2), g[w * h + w * h // 4:].reshape(h // 2, w // 2)
+        want_y = (f[0] + (1 << sh >> 1)) >> sh if sh else f[0]
+        assert np.abs(y - want_y).max() <= (1 if sh else 0)
+        for got_c, src_c in ((u, f[1]), (v, f[2])):
+            box = src_c.reshape(h // 2, cdiv[1] and (ch // (h // 2)), w // 2, cw // (w // 2)).mean(axis=(1, 3)) / (1 << sh)
+            assert np.abs(got_c - box).max() <= 0.02 * (1 << out_depth)      # smooth content: any sane 2:1 filter stays within 2 % of the box mean
+
+
 def test_container_reader_falls_back_to_opencv_for_rgb_codecs(tmp_path):
     import cv2
 
