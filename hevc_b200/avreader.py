@@ -120,6 +120,7 @@ class AvReader:
         self.pkt = C.c_void_p()
         self.frame = C.c_void_p()
         self._ring = None
+        self.stream_tags = None        # colour description + HDR10 static metadata of the first decoded frame (_read_stream_tags)
         self._sws = None               # ((format, w, h), SwsContext, bytes per sample, library, format name) of the conversion in use
         if f.avformat_open_input(C.byref(self.fmt), str(path).encode(), None, None) < 0:
             self.fmt = C.c_void_p()
@@ -161,6 +162,51 @@ class AvReader:
         self.pix_fmt = 'yuv420p' if bps == 1 else 'yuv420p10le'          # what this reader DELIVERS
         self.source_pix_fmt = self._sws[4] if self._sws else self.pix_fmt     # what the decoder produced
         self.frame_bytes = (self.width * self.height + 2 * (self.width // 2) * (self.height // 2)) * bps
+
+    # ---- what ffprobe reports per stream: colour description (codec context, filled from the container or the bitstream's VUI once a
+    #      frame is decoded; read through the AVOption API, no structure offsets) and the HDR10 static metadata carried as frame side
+    #      data (SEI 137 / 144, or the container's equivalent): AVFrameSideData = {type, data, size, ...}; AVMasteringDisplayMetadata =
+    #      {AVRational display_primaries[3][2] (R, G, B), white_point[2], min_luminance, max_luminance, int has_primaries, has_luminance};
+    #      AVContentLightMetadata = {unsigned MaxCLL, MaxFALL} -- all unchanged since libavutil 55
+    def _read_stream_tags(self) -> dict:
+        u = self.avu
+        out: dict = {}
+        try:
+            u.av_opt_get_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64)]
+            for key, opt in (('color_primaries', b'color_primaries'), ('color_transfer', b'color_trc'), ('color_space', b'colorspace'),
+                             ('color_range', b'color_range')):
+                v = C.c_int64(-1)
+                if u.av_opt_get_int(self.ctx, opt, 0, C.byref(v)) >= 0 and 0 <= v.value < 256:
+                    out[key] = int(v.value)
+            u.av_frame_get_side_data.restype = C.c_void_p
+            u.av_frame_get_side_data.argtypes = [C.c_void_p, C.c_int]
+
+            def side(kind, need):
+                sd = u.av_frame_get_side_data(self.frame, kind)
+                if not sd:
+                    return None
+                data, size = C.c_void_p.from_address(sd + 8).value, C.c_size_t.from_address(sd + 16).value
+                return data if data and size >= need else None
+            md = side(11, 88)              # AV_FRAME_DATA_MASTERING_DISPLAY_METADATA
+            if md:
+                q = (C.c_int * 20).from_address(md)
+                has_prim, has_lum = C.c_int.from_address(md + 80).value, C.c_int.from_address(md + 84).value
+
+                def scaled(i, unit):
+                    num, den = q[2 * i], q[2 * i + 1]
+                    return int(round(num * unit / den)) if den else 0
+                if has_prim == 1 and has_lum == 1:
+                    r, g, b = ((scaled(2 * c, 50000), scaled(2 * c + 1, 50000)) for c in range(3))
+                    wp = (scaled(6, 50000), scaled(7, 50000))
+                    lmin, lmax = scaled(8, 10000), scaled(9, 10000)
+                    out['master_display'] = 'G(%d,%d)B(%d,%d)R(%d,%d)WP(%d,%d)L(%d,%d)' % (g + b + r + wp + (lmax, lmin))
+            cl = side(14, 8)               # AV_FRAME_DATA_CONTENT_LIGHT_LEVEL
+            if cl:
+                v = (C.c_uint * 2).from_address(cl)
+                out['max_cll'] = '%d,%d' % (v[0], v[1])
+        except Exception:                  # a probe nicety, never a reason to lose the reader
+            pass
+        return out
 
     # ---- a decoded frame in any YUV layout -> planar 4:2:0 at 8 bits (8-bit sources) or 10 bits (deeper ones) through libswscale
     def _sws_to_420(self, fr: _AVFrameHead, w: int, h: int):
@@ -211,6 +257,8 @@ class AvReader:
             rc = a.avcodec_receive_frame(self.ctx, self.frame)
             if rc >= 0:
                 fr = _AVFrameHead.from_address(self.frame.value)
+                if self.stream_tags is None:
+                    self.stream_tags = self._read_stream_tags()
                 w, h = fr.width & ~1, fr.height & ~1
                 if fr.format == AV_PIX_FMT_YUV420P:
                     bps = 1
@@ -291,12 +339,13 @@ class AvReader:
 
 
 def decoded_format(path: Path) -> Optional[dict]:
-    """geometry and pixel format of the first decoded frame, or None when this reader cannot handle the file"""
+    """geometry, the decoder's pixel format and the stream's colour description / HDR10 static metadata (numeric H.273 codes, x265-style
+    strings) as of the first decoded frame, or None when this reader cannot handle the file"""
     try:
         r = AvReader(path)
     except Exception:
         return None
     try:
-        return {'width': r.width, 'height': r.height, 'pix_fmt': r.pix_fmt}
+        return {'width': r.width, 'height': r.height, 'pix_fmt': r.source_pix_fmt, **(r.stream_tags or {})}
     finally:
         r.close()

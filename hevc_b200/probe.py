@@ -167,6 +167,15 @@ def _probe_y4m(path: Path) -> dict:
     return out
 
 
+def _sane_count(v) -> Optional[int]:
+    """OpenCV reports garbage (negative, or astronomically large) frame counts for streams without an index, e.g. raw Annex-B files"""
+    try:
+        n = int(v)
+    except (TypeError, ValueError, OverflowError):
+        return None
+    return n if 0 < n < (1 << 31) else None
+
+
 def _probe_cv2(path: Path) -> dict:
     import cv2  # deferred: optional dependency
     cap = cv2.VideoCapture(str(path))
@@ -174,7 +183,7 @@ def _probe_cv2(path: Path) -> dict:
         if not cap.isOpened():
             raise ValueError('cv2 cannot open')
         out = {'width': int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), 'height': int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)),
-               'fps': float(cap.get(cv2.CAP_PROP_FPS)) or 30.0, 'nb_frames': int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) or None,
+               'fps': float(cap.get(cv2.CAP_PROP_FPS)) or 30.0, 'nb_frames': _sane_count(cap.get(cv2.CAP_PROP_FRAME_COUNT)),
                'pix_fmt': 'yuv420p'}
         if out['width'] <= 0 or out['height'] <= 0:
             raise ValueError('cv2 reports no video')
@@ -286,6 +295,14 @@ def _probe_without_ffprobe(path: Path) -> VideoInfo:
                 fmt = decoded_format(path)
                 if fmt:
                     base['pix_fmt'] = fmt['pix_fmt']
+                    # stream-level colour description and HDR10 static metadata (any container: MKV, TS, MP4 ...), as ffprobe's
+                    # color_primaries / color_transfer / color_space and side_data_list (reference core/probe.py:47-111); 2 = unspecified
+                    for key, names in (('color_primaries', _PRIM_NAMES), ('color_transfer', _TRC_NAMES), ('color_space', _SPC_NAMES)):
+                        if fmt.get(key) in names:
+                            base[key] = names[fmt[key]]
+                    for key in ('master_display', 'max_cll'):
+                        if fmt.get(key):
+                            base[key] = fmt[key]
             except Exception:
                 logger.debug('decoded-format probe failed', exc_info=True)
             if path.suffix.lower() in ('.mp4', '.mov', '.m4v'):

@@ -454,6 +454,38 @@ def test_container_reader_keeps_native_depth_and_probe_reads_hdr10_boxes(tmp_pat
         assert (g == want).all()
 
 
+def test_stream_level_hdr10_probe_for_any_container(tmp_path):
+    """without ffprobe and outside MP4 / MOV (MKV, TS, raw Annex-B ...) the colour description comes from the decoder context and
+    the HDR10 static metadata from the first frame's side data, both through the bundled libavcodec: an HDR10 stream is classified
+    HDR with its mastering-display string like ffprobe's side_data_list would give it (reference core/probe.py:47-111)"""
+    import shutil
+
+    from hevc_b200.avreader import decoded_format
+    src, _ = _model_mp4(tmp_path, 10)
+    fmt = decoded_format(src)
+    assert (fmt['color_primaries'], fmt['color_transfer'], fmt['color_space']) == (9, 16, 9) and fmt['pix_fmt'] == 'yuv420p10le'
+    assert fmt['master_display'] == 'G(13250,34500)B(7500,3000)R(34000,16000)WP(15635,16450)L(10000000,50)' and fmt['max_cll'] == '1000,400'
+    other = tmp_path / 'no_boxes_probed.dat'               # same bytes, but the MP4 box prober only looks at .mp4 / .mov / .m4v
+    shutil.copy(src, other)
+    info = probe.probe_media(other)
+    assert info.hdr and (info.color_primaries, info.color_transfer, info.color_space) == ('bt2020', 'smpte2084', 'bt2020nc')
+    assert info.master_display == fmt['master_display'] and info.max_cll == '1000,400'
+    # a raw Annex-B elementary stream: no container at all, tags from VUI + SEI 137 / 144; OpenCV's bogus frame count is dropped
+    from oracle import encoder_model as em
+    clip = SynthClip(176, 112, seed=2)
+    enc = em.ModelEncoder(em.make_params(176, 112, 10, qp_i=20, qp_p=22, keyint=10, hash_sei=False, hdr10=True))
+    es = b''.join(enc.encode(*[a.astype(np.uint16) << 2 for a in clip.frame(i)])[0] for i in range(4))
+    enc.close()
+    raw = tmp_path / 'raw.hevc'
+    raw.write_bytes(es)
+    info = probe.probe_media(raw)
+    assert info.hdr and info.pix_fmt == 'yuv420p10le' and info.master_display == fmt['master_display'] and (info.width, info.height) == (176, 112)
+    assert info.nb_frames is None or 0 < info.nb_frames < 100
+    sdr, _ = _model_mp4(tmp_path, 8, name='sdr.mp4')
+    f8 = decoded_format(sdr)
+    assert f8['color_primaries'] == 1 and 'master_display' not in f8
+
+
 def _write_y4m_tag(path, tag, w, h, frames, dtype):
     with open(path, 'wb') as fh:
         fh.write(f'YUV4MPEG2 W{w} H{h} F30:1 Ip A1:1 C{tag}\n'.encode())
