@@ -152,7 +152,7 @@ def _probe_y4m(path: Path) -> dict:
             n, d = val.split(':')
             out['fps'] = int(n) / int(d) if int(d) else 30.0
         elif k == 'C':
-            out['pix_fmt'] = _Y4M_CSP.get(val, 'yuv420p')
+            out['pix_fmt'] = _Y4M_CSP.get(val, 'gray' if val.startswith('mono') else 'unknown')
     out['header_len'] = len(head)
     bps = 2 if out['pix_fmt'].endswith('le') else 1
     w, h = out['width'], out['height']
@@ -160,8 +160,12 @@ def _probe_y4m(path: Path) -> dict:
         fsz = w * h * 3 * bps
     elif out['pix_fmt'].startswith('yuv422'):
         fsz = w * h * 2 * bps
-    else:
+    elif out['pix_fmt'].startswith('yuv420'):
         fsz = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)) * bps
+    else:                         # mono / unknown tags: the size of a frame is not known here, the container reader finds out
+        out['frame_bytes'] = 0
+        out['nb_frames'] = None
+        return out
     out['frame_bytes'] = fsz
     out['nb_frames'] = (path.stat().st_size - len(head)) // (fsz + 6)  # 'FRAME\n' per frame
     return out
