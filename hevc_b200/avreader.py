@@ -349,3 +349,66 @@ def decoded_format(path: Path) -> Optional[dict]:
         return {'width': r.width, 'height': r.height, 'pix_fmt': r.source_pix_fmt, **(r.stream_tags or {})}
     finally:
         r.close()
+
+
+_LAYOUT_CHANNELS = {'mono': 1, 'stereo': 2, '2.1': 3, '3.0': 3, '3.0(back)': 3, '4.0': 4, 'quad': 4, 'quad(side)': 4, '3.1': 4, '5.0': 5,
+                    '5.0(side)': 5, '4.1': 5, '5.1': 6, '5.1(side)': 6, '6.0': 6, '6.0(front)': 6, 'hexagonal': 6, '6.1': 7, '6.1(back)': 7,
+                    '6.1(front)': 7, '7.0': 7, '7.0(front)': 7, '7.1': 8, '7.1(wide)': 8, '7.1(wide-side)': 8, 'octagonal': 8}
+
+
+def audio_channels(path: Path) -> Optional[int]:
+    """channel count of the best audio stream (0: the file has no audio), or None when libavformat cannot tell -- what ffprobe reports as
+    ``channels`` (reference core/probe.py:47-111).  The count is read through the AVOption API of a scratch codec context
+    (``ch_layout`` as a string: a layout name or "<n> channels"), not from structure offsets."""
+    import re
+    try:
+        f, a, u = _lib('avformat'), _lib('avcodec'), _lib('avutil')
+    except (OSError, Unsupported):
+        return None
+    f.avformat_version.restype = C.c_uint
+    if (f.avformat_version() >> 16) < 59:
+        return None
+    f.avformat_open_input.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_void_p, C.c_void_p]
+    f.avformat_find_stream_info.argtypes = [C.c_void_p, C.c_void_p]
+    f.av_find_best_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int]
+    f.avformat_close_input.argtypes = [C.POINTER(C.c_void_p)]
+    a.avcodec_alloc_context3.restype = C.c_void_p
+    a.avcodec_alloc_context3.argtypes = [C.c_void_p]
+    a.avcodec_parameters_to_context.argtypes = [C.c_void_p, C.c_void_p]
+    a.avcodec_free_context.argtypes = [C.POINTER(C.c_void_p)]
+    u.av_opt_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    u.av_free.argtypes = [C.c_void_p]
+    u.av_log_set_level.argtypes = [C.c_int]
+    u.av_log_set_level(16)
+    fmt, ctx = C.c_void_p(), C.c_void_p()
+    if f.avformat_open_input(C.byref(fmt), str(path).encode(), None, None) < 0:
+        return None
+    try:
+        if f.avformat_find_stream_info(fmt, None) < 0:
+            return None
+        idx = f.av_find_best_stream(fmt, 1, -1, -1, None, 0)              # AVMEDIA_TYPE_AUDIO
+        if idx < 0:
+            return 0
+        nb = C.c_uint.from_address(fmt.value + 44).value
+        if not (0 < nb <= 256 and idx < nb):
+            return None
+        st = C.c_void_p.from_address(C.c_void_p.from_address(fmt.value + 48).value + 8 * idx).value
+        codecpar = C.c_void_p.from_address(st + 16).value
+        if C.c_int.from_address(st + 8).value != idx or not codecpar or C.c_int.from_address(codecpar).value != 1:     # codec_type == AUDIO
+            return None
+        ctx = C.c_void_p(a.avcodec_alloc_context3(None))
+        if not ctx or a.avcodec_parameters_to_context(ctx, codecpar) < 0:
+            return None
+        s = C.c_void_p()
+        if u.av_opt_get(ctx, b'ch_layout', 0, C.byref(s)) < 0 or not s:
+            return None
+        name = C.cast(s, C.c_char_p).value.decode('ascii', 'replace')
+        u.av_free(s)
+        if name in _LAYOUT_CHANNELS:
+            return _LAYOUT_CHANNELS[name]
+        m = re.match(r'(\d+) channels', name)
+        return int(m.group(1)) if m else name.count('+') + 1 if '+' in name else None
+    finally:
+        if ctx:
+            a.avcodec_free_context(C.byref(ctx))
+        f.avformat_close_input(C.byref(fmt))

@@ -311,6 +311,13 @@ def _probe_without_ffprobe(path: Path) -> VideoInfo:
                 logger.debug('decoded-format probe failed', exc_info=True)
             if path.suffix.lower() in ('.mp4', '.mov', '.m4v'):
                 base.update(_probe_mp4_colour(path))
+            try:                  # ffprobe's audio `channels` (core/probe.py:47-111): the b200 path warns that it writes no audio track
+                from .avreader import audio_channels
+                ach = audio_channels(path)
+                if ach:
+                    base['audio_channels'] = ach
+            except Exception:
+                logger.debug('audio probe failed', exc_info=True)
     base.update({k: v for k, v in side.items() if v is not None})
     prim = str(base.get('color_primaries', 'bt709')).lower()
     trc = str(base.get('color_transfer', 'bt709')).lower()

@@ -486,6 +486,24 @@ def test_stream_level_hdr10_probe_for_any_container(tmp_path):
     assert f8['color_primaries'] == 1 and 'master_display' not in f8
 
 
+def test_audio_channel_probe_through_libavformat(tmp_path):
+    """ffprobe-less audio `channels` (reference core/probe.py:47-111): WAV files of 1 / 2 / 6 / 8 channels, and 0 for a video-only MP4"""
+    import wave
+
+    from hevc_b200.avreader import audio_channels
+    for ch in (1, 2, 6, 8):
+        p = tmp_path / f'a{ch}.wav'
+        with wave.open(str(p), 'wb') as w:
+            w.setnchannels(ch)
+            w.setsampwidth(2)
+            w.setframerate(48000)
+            w.writeframes(np.zeros((480, ch), np.int16).tobytes())
+        assert audio_channels(p) == ch
+    src, _ = _model_mp4(tmp_path, 8)
+    assert audio_channels(src) == 0 and probe.probe_media(src).audio_channels == 0
+    assert audio_channels(tmp_path / 'missing.mkv') is None
+
+
 def _write_y4m_tag(path, tag, w, h, frames, dtype):
     with open(path, 'wb') as fh:
         fh.write(f'YUV4MPEG2 W{w} H{h} F30:1 Ip A1:1 C{tag}\n'.encode())
