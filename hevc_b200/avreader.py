@@ -219,8 +219,8 @@ class AvReader:
                 raise Unsupported(f'pixel format {fr.format} unknown to libavutil')
             d = d.contents
             depth = d.comp[0].depth
-            if not (d.name and 3 <= d.nb_components <= 4 and 8 <= depth <= 16 and d.log2_chroma_w <= 2 and d.log2_chroma_h <= 2):
-                raise Unsupported(f'pixel format {fr.format}: unexpected descriptor layout or not a three-component format')
+            if not (d.name and 1 <= d.nb_components <= 4 and 8 <= depth <= 16 and d.log2_chroma_w <= 2 and d.log2_chroma_h <= 2):
+                raise Unsupported(f'pixel format {fr.format}: unexpected descriptor layout')
             if d.flags & (_PIX_FLAG_RGB | _PIX_FLAG_PAL | _PIX_FLAG_BAYER):
                 raise Unsupported(f'pixel format {d.name.decode()} is not YUV')
             try:
